@@ -1,0 +1,254 @@
+// K5: bipartite single-head GAT pool (local -> virtual), forward and backward.
+// Replaces GATConv((-1,-1), H, add_self_loops=False) on ("local","to","virtual")
+// (model/hscn.py:85-87,118-125).
+//
+// HBM-bound: reads hs [N,H] once (gathered by cluster membership), 8N score terms, writes [V,H].
+// One warp owns one destination (virtual) row: lanes stride the row's slots for the score /
+// softmax passes and own 128-bit column chunks for the weighted feature sum, which runs in slot
+// (= edge) order like the CPU scatter_add_.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ghscn {
+
+__global__ void __launch_bounds__(256) row_dot_kernel(const float* __restrict__ x, int64_t ldx,
+                                                      const float* __restrict__ v, int num_rows, int num_feat,
+                                                      float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= num_rows) return;
+  const float* xr = x + (int64_t)row * ldx;
+  float acc = 0.f;
+  for (int f = lane; f < num_feat; f += 32) acc += __ldg(xr + f) * __ldg(v + f);
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
+}
+
+__device__ __forceinline__ float leaky(float z, float slope) { return z > 0.f ? z : z * slope; }
+
+template <int VEC, int ITERS>
+__global__ void __launch_bounds__(256) gat_pool_fwd_kernel(const int* __restrict__ rowptr,
+                                                           const int* __restrict__ col,
+                                                           const float* __restrict__ hs, int64_t ldhs,
+                                                           const float* __restrict__ a_src,
+                                                           const float* __restrict__ a_dst,
+                                                           const float* __restrict__ bias, float slope,
+                                                           int num_rows, int num_feat, float* __restrict__ alpha,
+                                                           float* __restrict__ out, int64_t ldout) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= num_rows) return;
+  const int beg = rowptr[row], end = rowptr[row + 1];
+  const float ad = a_dst ? a_dst[row] : 0.f;
+
+  // pass 1: row max of the leaky-relu scores
+  float m = -INFINITY;
+  for (int s = beg + lane; s < end; s += 32) m = fmaxf(m, leaky(a_src[col[s]] + ad, slope));
+  m = warp_max(m);
+  // pass 2: exp and denominator (+1e-16 as PyG's softmax)
+  float sum = 0.f;
+  for (int s = beg + lane; s < end; s += 32) {
+    const float p = expf(leaky(a_src[col[s]] + ad, slope) - m);
+    alpha[s] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum) + 1e-16f;
+  for (int s = beg + lane; s < end; s += 32) alpha[s] = __fdiv_rn(alpha[s], sum);
+  __syncwarp();
+
+  // pass 3: out[row,:] = sum_s alpha[s] * hs[col[s],:] (+ bias), slot order, unfused mul/add
+  for (int f0 = 0; f0 < num_feat; f0 += 32 * VEC * ITERS) {
+    float acc[ITERS][VEC];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[it][v] = 0.f;
+    for (int s = beg; s < end; ++s) {
+      const float a = alpha[s];
+      const float* hr = hs + (int64_t)col[s] * ldhs;
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int f = f0 + (it * 32 + lane) * VEC;
+        if (f < num_feat) {
+          if (VEC == 4) {
+            const float4 q = ldg_f4(hr + f);
+            acc[it][0] = mul_then_add(acc[it][0], a, q.x);
+            acc[it][1 % VEC] = mul_then_add(acc[it][1 % VEC], a, q.y);
+            acc[it][2 % VEC] = mul_then_add(acc[it][2 % VEC], a, q.z);
+            acc[it][3 % VEC] = mul_then_add(acc[it][3 % VEC], a, q.w);
+          } else {
+            acc[it][0] = mul_then_add(acc[it][0], a, __ldg(hr + f));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int f = f0 + (it * 32 + lane) * VEC;
+      if (f < num_feat) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          float r = acc[it][v];
+          if (bias) r = __fadd_rn(r, bias[f + v]);
+          out[(int64_t)row * ldout + f + v] = r;
+        }
+      }
+    }
+  }
+}
+
+// Backward, destination side.  Per row: dalpha_s = <dout[row], hs[col_s]>; softmax + leaky-relu
+// backward give dz_s (gradient of the pre-activation score) and da_dst[row] = sum_s dz_s.
+__global__ void __launch_bounds__(256) gat_pool_bwd_scores_kernel(const int* __restrict__ rowptr,
+                                                                  const int* __restrict__ col,
+                                                                  const float* __restrict__ hs, int64_t ldhs,
+                                                                  const float* __restrict__ a_src,
+                                                                  const float* __restrict__ a_dst,
+                                                                  const float* __restrict__ alpha,
+                                                                  const float* __restrict__ dout, int64_t lddout,
+                                                                  float slope, int num_rows, int num_feat,
+                                                                  float* __restrict__ dz,
+                                                                  float* __restrict__ da_dst) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= num_rows) return;
+  const int beg = rowptr[row], end = rowptr[row + 1];
+  const float* dr = dout + (int64_t)row * lddout;
+  float t = 0.f;  // sum_s alpha_s * dalpha_s
+  for (int s = beg; s < end; ++s) {
+    const float* hr = hs + (int64_t)col[s] * ldhs;
+    float acc = 0.f;
+    for (int f = lane; f < num_feat; f += 32) acc += __ldg(dr + f) * __ldg(hr + f);
+    acc = warp_sum(acc);
+    if (lane == 0) dz[s] = acc;
+    t += alpha[s] * acc;
+  }
+  __syncwarp();
+  const float ad = a_dst ? a_dst[row] : 0.f;
+  float dsum = 0.f;
+  for (int s = beg + lane; s < end; s += 32) {
+    const float de = alpha[s] * (dz[s] - t);
+    const float z = a_src[col[s]] + ad;
+    const float g = z > 0.f ? de : de * slope;
+    dz[s] = g;
+    dsum += g;
+  }
+  dsum = warp_sum(dsum);
+  if (lane == 0 && da_dst) da_dst[row] = dsum;
+}
+
+// Backward, source side, on the transposed structure (rows = source nodes):
+//   da_src[j] = sum_t dz[map[t]];  dhs[j,:] = sum_t alpha[map[t]] * dout[col_t[t],:] + da_src[j] * att_src
+__global__ void __launch_bounds__(256) gat_pool_bwd_src_kernel(const int* __restrict__ rowptr_t,
+                                                               const int* __restrict__ col_t,
+                                                               const int* __restrict__ map_t,
+                                                               const float* __restrict__ alpha,
+                                                               const float* __restrict__ dz,
+                                                               const float* __restrict__ dout, int64_t lddout,
+                                                               const float* __restrict__ att_src, int num_rows,
+                                                               int num_feat, float* __restrict__ dhs,
+                                                               int64_t lddhs, float* __restrict__ da_src) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= num_rows) return;
+  const int beg = rowptr_t[row], end = rowptr_t[row + 1];
+  float das = 0.f;
+  for (int t = beg; t < end; ++t) das += dz[map_t[t]];
+  if (lane == 0 && da_src) da_src[row] = das;
+  for (int f = lane; f < num_feat; f += 32) {
+    float acc = 0.f;
+    for (int t = beg; t < end; ++t) acc += alpha[map_t[t]] * __ldg(dout + (int64_t)col_t[t] * lddout + f);
+    dhs[(int64_t)row * lddhs + f] = acc + das * __ldg(att_src + f);
+  }
+}
+
+// map_t[t] = slot (in the by-destination structure) of the edge sitting in transposed slot t.
+__global__ void slot_pos_kernel(const int* __restrict__ perm, int64_t nnz, int* __restrict__ pos) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nnz) pos[perm[s]] = (int)s;
+}
+__global__ void slot_map_kernel(const int* __restrict__ perm_t, const int* __restrict__ pos, int64_t nnz,
+                                int* __restrict__ map_t) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nnz) map_t[t] = pos[perm_t[t]];
+}
+
+}  // namespace ghscn
+
+using namespace ghscn;
+
+extern "C" {
+
+int ghscn_row_dot(const float* x, int64_t ldx, const float* v, int64_t num_rows, int64_t num_feat, float* out,
+                  ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && num_rows < ((int64_t)1 << 31));
+  if (num_rows == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(x && v && out && ldx >= num_feat);
+  row_dot_kernel<<<(unsigned)ceil_div<int64_t>(num_rows, 8), 256, 0, as_stream(stream)>>>(
+      x, ldx, v, (int)num_rows, (int)num_feat, out);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+int ghscn_gat_pool_fwd(const int32_t* rowptr, const int32_t* col, const float* hs, int64_t ldhs,
+                       const float* a_src, const float* a_dst, const float* bias, float negative_slope,
+                       int64_t num_rows, int64_t num_feat, float* alpha, float* out, int64_t ldout,
+                       ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && num_rows < ((int64_t)1 << 31));
+  if (num_rows == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(rowptr && col && hs && a_src && alpha && out && ldhs >= num_feat && ldout >= num_feat);
+  const unsigned blocks = (unsigned)ceil_div<int64_t>(num_rows, 8);
+  const bool vec4 = num_feat % 4 == 0 && ldhs % 4 == 0 && (reinterpret_cast<uintptr_t>(hs) % 16 == 0);
+  if (vec4)
+    gat_pool_fwd_kernel<4, 3><<<blocks, 256, 0, as_stream(stream)>>>(rowptr, col, hs, ldhs, a_src, a_dst, bias,
+                                                                      negative_slope, (int)num_rows,
+                                                                      (int)num_feat, alpha, out, ldout);
+  else
+    gat_pool_fwd_kernel<1, 4><<<blocks, 256, 0, as_stream(stream)>>>(rowptr, col, hs, ldhs, a_src, a_dst, bias,
+                                                                      negative_slope, (int)num_rows,
+                                                                      (int)num_feat, alpha, out, ldout);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+int ghscn_gat_pool_bwd_scores(const int32_t* rowptr, const int32_t* col, const float* hs, int64_t ldhs,
+                              const float* a_src, const float* a_dst, const float* alpha, const float* dout,
+                              int64_t lddout, float negative_slope, int64_t num_rows, int64_t num_feat, float* dz,
+                              float* da_dst, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && num_rows < ((int64_t)1 << 31));
+  if (num_rows == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(rowptr && col && hs && a_src && alpha && dout && dz);
+  gat_pool_bwd_scores_kernel<<<(unsigned)ceil_div<int64_t>(num_rows, 8), 256, 0, as_stream(stream)>>>(
+      rowptr, col, hs, ldhs, a_src, a_dst, alpha, dout, lddout, negative_slope, (int)num_rows, (int)num_feat, dz,
+      da_dst);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+int ghscn_gat_pool_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* map_t, const float* alpha,
+                           const float* dz, const float* dout, int64_t lddout, const float* att_src,
+                           int64_t num_rows, int64_t num_feat, float* dhs, int64_t lddhs, float* da_src,
+                           ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && num_rows < ((int64_t)1 << 31));
+  if (num_rows == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(rowptr_t && col_t && map_t && alpha && dz && dout && att_src && dhs);
+  gat_pool_bwd_src_kernel<<<(unsigned)ceil_div<int64_t>(num_rows, 8), 256, 0, as_stream(stream)>>>(
+      rowptr_t, col_t, map_t, alpha, dz, dout, lddout, att_src, (int)num_rows, (int)num_feat, dhs, lddhs, da_src);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+int ghscn_slot_map(const int32_t* perm, const int32_t* perm_t, int64_t nnz, int64_t num_items, int32_t* scratch_pos,
+                   int32_t* map_t, ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(nnz >= 0 && num_items >= nnz);
+  if (nnz == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(perm && perm_t && scratch_pos && map_t);
+  cudaStream_t stream = as_stream(stream_);
+  slot_pos_kernel<<<(unsigned)ceil_div<int64_t>(nnz, 256), 256, 0, stream>>>(perm, nnz, scratch_pos);
+  slot_map_kernel<<<(unsigned)ceil_div<int64_t>(nnz, 256), 256, 0, stream>>>(perm_t, scratch_pos, nnz, map_t);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+}  // extern "C"

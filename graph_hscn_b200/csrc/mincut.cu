@@ -1,0 +1,434 @@
+// K6: fused MinCUT pool, one CTA per graph, forward and analytic backward.
+// Replaces to_dense_adj + dense_mincut_pool (model/hscn.py:61-63).
+//
+// The [n,n] dense adjacency is never materialised: the graph's CSR slice is consumed directly
+// ((A S)[r] = sum_{e: row_e = r} val_e S[col_e]).  Per graph the CTA stages S = softmax(logits)
+// and A S in shared memory (falls back to an HBM workspace when n*K does not fit), and produces
+// S^T X, S^T A S, S^T S, both traces and both losses without any other round trip through HBM.
+// HBM-bound at the reference's sizes (K <= 32): algorithmic bytes per graph
+//   4nK (logits) + 4nH (X, only if `out` is requested) + 4(n+1) + 4 nnz  ->  4nK (S) + 4KH + 8K^2 + 32.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ghscn {
+
+constexpr int kMincutThreads = 256;
+constexpr int kMaxClusters = 128;
+constexpr int kStatsStride = 8;  // per graph: num, den, ||SS||_F, ||R||_F (= ortho_g), mc_g, -, -, -
+constexpr size_t kSmemBudget = 200 * 1024;
+
+__device__ __forceinline__ float adj_value(const float* __restrict__ adj_val, int s) {
+  return adj_val ? adj_val[s] : 1.0f;
+}
+
+// rows of `buf` (n x K) <- (A S) using the CSR slice whose rows are the graph's nodes.
+__device__ __forceinline__ void csr_times_s(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                            const float* __restrict__ adj_val, const float* __restrict__ S,
+                                            int base, int n, int K, float* __restrict__ buf) {
+  for (int e = threadIdx.x; e < n * K; e += blockDim.x) {
+    const int i = e / K, k = e - i * K;
+    float acc = 0.f;
+    const int beg = rowptr[base + i], end = rowptr[base + i + 1];
+    for (int s = beg; s < end; ++s) {
+      const int c = col[s] - base;
+      if (c >= 0 && c < n) acc += adj_value(adj_val, s) * S[c * K + k];
+    }
+    buf[e] = acc;
+  }
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kMincutThreads) mincut_fwd_kernel(
+    const float* __restrict__ logits, int64_t ldz, const float* __restrict__ x, int64_t ldx,
+    const int* __restrict__ ptr, const int* __restrict__ rowptr, const int* __restrict__ col,
+    const float* __restrict__ adj_val, float temp, int K, int H, int n_cap, float* __restrict__ s_soft,
+    float* __restrict__ out, float* __restrict__ out_adj, float* __restrict__ ss_raw,
+    float* __restrict__ adj_raw, float* __restrict__ stats, float* __restrict__ as_ws) {
+  extern __shared__ float smem[];
+  __shared__ float red[32];
+  __shared__ float dk[kMaxClusters];
+  const int g = blockIdx.x;
+  const int base = ptr[g];
+  const int n = ptr[g + 1] - base;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = kMincutThreads / 32;
+
+  float* Sg = s_soft + (int64_t)base * K;
+  float* S = SMEM ? smem : Sg;
+  float* AS = SMEM ? smem + (size_t)n_cap * K : as_ws + (int64_t)base * K;
+  float* deg = SMEM ? smem + 2 * (size_t)n_cap * K : smem;
+
+  // A. S = softmax(logits / temp), one warp per node row
+  for (int i = wid; i < n; i += nwarps) {
+    const float* zr = logits + (int64_t)(base + i) * ldz;
+    float m = -INFINITY;
+    for (int k = lane; k < K; k += 32) {
+      const float z = temp != 1.0f ? __fdiv_rn(zr[k], temp) : zr[k];
+      m = fmaxf(m, z);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float z = temp != 1.0f ? __fdiv_rn(zr[k], temp) : zr[k];
+      const float p = expf(z - m);
+      S[i * K + k] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    for (int k = lane; k < K; k += 32) {
+      const float p = __fdiv_rn(S[i * K + k], sum);
+      S[i * K + k] = p;
+      if (SMEM) Sg[i * K + k] = p;
+    }
+    if (lane == 0) {
+      float d = 0.f;
+      for (int s = rowptr[base + i]; s < rowptr[base + i + 1]; ++s) d += adj_value(adj_val, s);
+      deg[i] = d;
+    }
+  }
+  __syncthreads();
+
+  // B. AS = A S
+  csr_times_s(rowptr, col, adj_val, S, base, n, K, AS);
+  __syncthreads();
+
+  // C. traces, S^T S, S^T A S, S^T X
+  float pnum = 0.f, pden = 0.f;
+  for (int e = tid; e < n * K; e += kMincutThreads) {
+    const float sv = S[e];
+    pnum += sv * AS[e];
+    pden += deg[e / K] * sv * sv;
+  }
+  const float num = block_sum(pnum, red);
+  const float den = block_sum(pden, red);
+
+  float* ssg = ss_raw + (int64_t)g * K * K;
+  float* oag = adj_raw + (int64_t)g * K * K;
+  for (int p = tid; p < K * K; p += kMincutThreads) {
+    const int k = p / K, l = p - k * K;
+    float ss = 0.f, oa = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const float sk = S[i * K + k];
+      ss += sk * S[i * K + l];
+      oa += sk * AS[i * K + l];
+    }
+    ssg[p] = ss;
+    oag[p] = oa;
+  }
+  if (out != nullptr) {
+    constexpr int KC = 8;
+    float* og = out + (int64_t)g * K * H;
+    const int chunks = ceil_div(K, KC);
+    for (int item = tid; item < chunks * H; item += kMincutThreads) {
+      const int kc = (item / H) * KC, h = item % H;
+      float acc[KC];
+#pragma unroll
+      for (int j = 0; j < KC; ++j) acc[j] = 0.f;
+      const float* xp = x + (int64_t)base * ldx + h;
+      for (int i = 0; i < n; ++i) {
+        const float xv = __ldg(xp + (int64_t)i * ldx);
+#pragma unroll
+        for (int j = 0; j < KC; ++j)
+          if (kc + j < K) acc[j] += S[i * K + kc + j] * xv;
+      }
+#pragma unroll
+      for (int j = 0; j < KC; ++j)
+        if (kc + j < K) og[(int64_t)(kc + j) * H + h] = acc[j];
+    }
+  }
+  __syncthreads();  // ssg / oag visible to the whole CTA
+
+  // D. losses and the normalised coarse adjacency
+  float pf = 0.f;
+  for (int p = tid; p < K * K; p += kMincutThreads) pf += ssg[p] * ssg[p];
+  const float fro = sqrtf(block_sum(pf, red));
+  const float inv_sqrt_k = __fdiv_rn(1.0f, sqrtf((float)K));
+  float pr = 0.f;
+  for (int p = tid; p < K * K; p += kMincutThreads) {
+    const int k = p / K, l = p - k * K;
+    const float r = __fdiv_rn(ssg[p], fro) - (k == l ? inv_sqrt_k : 0.f);
+    pr += r * r;
+  }
+  const float ortho = sqrtf(block_sum(pr, red));
+  if (tid == 0) {
+    float* st = stats + (int64_t)g * kStatsStride;
+    st[0] = num; st[1] = den; st[2] = fro; st[3] = ortho; st[4] = -__fdiv_rn(num, den);
+    st[5] = 0.f; st[6] = 0.f; st[7] = 0.f;
+  }
+  if (out_adj != nullptr) {
+    for (int k = tid; k < K; k += kMincutThreads) {
+      float r = 0.f;
+      for (int l = 0; l < K; ++l)
+        if (l != k) r += oag[k * K + l];
+      dk[k] = sqrtf(r) + 1e-15f;
+    }
+    __syncthreads();
+    float* ng = out_adj + (int64_t)g * K * K;
+    for (int p = tid; p < K * K; p += kMincutThreads) {
+      const int k = p / K, l = p - k * K;
+      ng[p] = (k == l) ? 0.f : __fdiv_rn(__fdiv_rn(oag[p], dk[l]), dk[k]);
+    }
+  }
+}
+
+// losses[0] = mean_g(-num/den), losses[1] = mean_g(ortho_g); fixed reduction order.
+__global__ void __launch_bounds__(256) mincut_reduce_losses_kernel(const float* __restrict__ stats, int B,
+                                                                   float* __restrict__ losses) {
+  __shared__ float red[32];
+  float a = 0.f, b = 0.f;
+  for (int g = threadIdx.x; g < B; g += blockDim.x) {
+    a += stats[(int64_t)g * kStatsStride + 4];
+    b += stats[(int64_t)g * kStatsStride + 3];
+  }
+  a = block_sum(a, red);
+  b = block_sum(b, red);
+  if (threadIdx.x == 0) {
+    losses[0] = __fdiv_rn(a, (float)B);
+    losses[1] = __fdiv_rn(b, (float)B);
+  }
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kMincutThreads) mincut_bwd_kernel(
+    const float* __restrict__ s_soft, const float* __restrict__ x, int64_t ldx, const int* __restrict__ ptr,
+    const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ adj_val,
+    const int* __restrict__ rowptr_t, const int* __restrict__ col_t, const float* __restrict__ adj_val_t,
+    float temp, int B, int K, int H, int n_cap, const float* __restrict__ ss_raw,
+    const float* __restrict__ adj_raw, const float* __restrict__ stats, const float* __restrict__ g_out,
+    const float* __restrict__ g_out_adj, const float* __restrict__ g_losses, float* __restrict__ d_logits,
+    int64_t lddz, float* __restrict__ d_x, int64_t lddx, float* __restrict__ ws) {
+  extern __shared__ float smem[];
+  __shared__ float red[32];
+  __shared__ float dk[kMaxClusters], dr[kMaxClusters];
+  const int g = blockIdx.x;
+  const int base = ptr[g];
+  const int n = ptr[g + 1] - base;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = kMincutThreads / 32;
+  const size_t nk_cap = (size_t)n_cap * K;
+
+  // shared layout: [Gsym K*K][Gam K*K][deg n_cap] (+ [S][AS][ATS][dS] when SMEM)
+  float* Gsym = smem;
+  float* Gam = smem + K * K;
+  float* deg = smem + 2 * K * K;
+  const float* Sg = s_soft + (int64_t)base * K;
+  float* S = SMEM ? deg + n_cap : nullptr;
+  float* AS = SMEM ? S + nk_cap : ws + (int64_t)base * K;
+  float* ATS = SMEM ? AS + nk_cap : ws + (int64_t)(ptr[B] + base) * K;
+  float* dS = SMEM ? ATS + nk_cap : ws + (int64_t)(2 * ptr[B] + base) * K;
+  if (SMEM) {
+    for (int e = tid; e < n * K; e += kMincutThreads) S[e] = Sg[e];
+  }
+  const float* Sr = SMEM ? S : Sg;
+  for (int i = tid; i < n; i += kMincutThreads) {
+    float d = 0.f;
+    for (int s = rowptr[base + i]; s < rowptr[base + i + 1]; ++s) d += adj_value(adj_val, s);
+    deg[i] = d;
+  }
+  __syncthreads();
+  csr_times_s(rowptr, col, adj_val, Sr, base, n, K, AS);
+  csr_times_s(rowptr_t, col_t, adj_val_t, Sr, base, n, K, ATS);
+
+  const float* st = stats + (int64_t)g * kStatsStride;
+  const float num = st[0], den = st[1], fro = st[2], nrm = st[3];
+  const float gmc = g_losses ? __fdiv_rn(g_losses[0], (float)B) : 0.f;
+  const float go = g_losses ? __fdiv_rn(g_losses[1], (float)B) : 0.f;
+  const float* ssg = ss_raw + (int64_t)g * K * K;
+  const float* oag = adj_raw + (int64_t)g * K * K;
+  const float inv_sqrt_k = __fdiv_rn(1.0f, sqrtf((float)K));
+
+  // ortho: G = R/||R||, G' = (G - M <G,M>)/F, Gsym = go * (G' + G'^T)
+  float pin = 0.f;
+  for (int p = tid; p < K * K; p += kMincutThreads) {
+    const int k = p / K, l = p - k * K;
+    const float M = ssg[p] / fro;
+    const float G = nrm > 0.f ? (M - (k == l ? inv_sqrt_k : 0.f)) / nrm : 0.f;
+    pin += G * M;
+  }
+  const float inner = block_sum(pin, red);
+  for (int p = tid; p < K * K; p += kMincutThreads) {
+    const int k = p / K, l = p - k * K;
+    const float M = ssg[p] / fro, Mt = ssg[l * K + k] / fro;
+    const float G = nrm > 0.f ? (M - (k == l ? inv_sqrt_k : 0.f)) / nrm : 0.f;
+    const float Gt = nrm > 0.f ? (Mt - (k == l ? inv_sqrt_k : 0.f)) / nrm : 0.f;
+    Gsym[p] = go * ((G - M * inner) + (Gt - Mt * inner)) / fro;
+  }
+  // Gamma = dL/d(S^T A S): trace term of the mincut loss + chain through the normalised out_adj
+  if (g_out_adj != nullptr) {
+    const float* gb = g_out_adj + (int64_t)g * K * K;
+    for (int k = tid; k < K; k += kMincutThreads) {
+      float r = 0.f;
+      for (int l = 0; l < K; ++l)
+        if (l != k) r += oag[k * K + l];
+      dk[k] = sqrtf(r) + 1e-15f;
+      dr[k] = r;
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += kMincutThreads) {
+      float acc = 0.f;  // sum_l Gbar[k][l] N[k][l] + Gbar[l][k] N[l][k]
+      for (int l = 0; l < K; ++l) {
+        if (l == k) continue;
+        const float nkl = (oag[k * K + l] / dk[l]) / dk[k];
+        const float nlk = (oag[l * K + k] / dk[k]) / dk[l];
+        acc += gb[k * K + l] * nkl + gb[l * K + k] * nlk;
+      }
+      const float ddk = -acc / dk[k];
+      const float sq = sqrtf(dr[k]);
+      dr[k] = sq > 0.f ? ddk / (2.f * sq) : 0.f;  // dL/d(rowsum_k)
+    }
+    __syncthreads();
+    for (int p = tid; p < K * K; p += kMincutThreads) {
+      const int k = p / K, l = p - k * K;
+      Gam[p] = (k == l) ? 0.f : gb[p] / (dk[k] * dk[l]) + dr[k];
+    }
+  } else {
+    for (int p = tid; p < K * K; p += kMincutThreads) Gam[p] = 0.f;
+  }
+  __syncthreads();
+  for (int k = tid; k < K; k += kMincutThreads) Gam[k * K + k] += -gmc / den;
+  __syncthreads();
+
+  const float cden = gmc * num / (den * den);
+  const bool diag_only = (g_out_adj == nullptr);
+  const float gdiag = -gmc / den;
+  const float* gog = g_out ? g_out + (int64_t)g * K * H : nullptr;
+  for (int e = tid; e < n * K; e += kMincutThreads) {
+    const int i = e / K, k = e - i * K;
+    float v;
+    if (diag_only) {
+      v = gdiag * (AS[e] + ATS[e]);
+    } else {
+      v = 0.f;
+      for (int l = 0; l < K; ++l) v += AS[i * K + l] * Gam[k * K + l] + ATS[i * K + l] * Gam[l * K + k];
+    }
+    v += cden * 2.f * deg[i] * Sr[e];
+    float o = 0.f;
+    for (int l = 0; l < K; ++l) o += Sr[i * K + l] * Gsym[l * K + k];
+    v += o;
+    if (gog) {
+      const float* xr = x + (int64_t)(base + i) * ldx;
+      const float* gr = gog + (int64_t)k * H;
+      float acc = 0.f;
+      for (int h = 0; h < H; ++h) acc += __ldg(xr + h) * __ldg(gr + h);
+      v += acc;
+    }
+    dS[e] = v;
+  }
+  __syncthreads();
+  // softmax backward, one warp per node row
+  for (int i = wid; i < n; i += nwarps) {
+    float dot = 0.f;
+    for (int k = lane; k < K; k += 32) dot += dS[i * K + k] * Sr[i * K + k];
+    dot = warp_sum(dot);
+    for (int k = lane; k < K; k += 32) {
+      float dz = Sr[i * K + k] * (dS[i * K + k] - dot);
+      if (temp != 1.0f) dz = dz / temp;
+      d_logits[(int64_t)(base + i) * lddz + k] = dz;
+    }
+  }
+  if (d_x != nullptr) {
+    for (int e = tid; e < n * H; e += kMincutThreads) {
+      const int i = e / H, h = e - i * H;
+      float acc = 0.f;
+      if (gog)
+        for (int k = 0; k < K; ++k) acc += Sr[i * K + k] * __ldg(gog + (int64_t)k * H + h);
+      d_x[(int64_t)(base + i) * lddx + h] = acc;
+    }
+  }
+}
+
+static inline size_t fwd_smem_bytes(int n_cap, int K, bool smem) {
+  return smem ? (2 * (size_t)n_cap * K + n_cap) * 4 : (size_t)n_cap * 4;
+}
+static inline size_t bwd_smem_bytes(int n_cap, int K, bool smem) {
+  return (2 * (size_t)K * K + n_cap + (smem ? 4 * (size_t)n_cap * K : 0)) * 4;
+}
+
+}  // namespace ghscn
+
+using namespace ghscn;
+
+extern "C" {
+
+size_t ghscn_mincut_workspace_bytes(int64_t num_nodes, int64_t num_graphs, int64_t num_clusters) {
+  (void)num_graphs;
+  if (num_nodes < 0 || num_clusters < 0) return 0;
+  return (size_t)3 * num_nodes * num_clusters * 4 + 256;
+}
+
+int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x, int64_t ldx, const int32_t* ptr,
+                     const int32_t* rowptr, const int32_t* col, const float* adj_val, float temp,
+                     int64_t num_graphs, int64_t num_nodes, int64_t num_clusters, int64_t num_feat,
+                     int32_t max_nodes_per_graph, float* s_soft, float* out, float* out_adj, float* ss_raw,
+                     float* adj_raw, float* stats, float* losses, void* workspace, size_t workspace_bytes,
+                     ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(num_graphs >= 0 && num_nodes >= 0 && num_clusters > 0 && num_feat >= 0);
+  GHSCN_REQUIRE(num_graphs < ((int64_t)1 << 31) && num_nodes < ((int64_t)1 << 31));
+  if (num_clusters > kMaxClusters) return GHSCN_E_UNSUPPORTED;
+  if (num_graphs == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(logits && ptr && rowptr && col && s_soft && ss_raw && adj_raw && stats && losses);
+  GHSCN_REQUIRE(ldz >= num_clusters && (out == nullptr || (x != nullptr && ldx >= num_feat)));
+  GHSCN_REQUIRE(max_nodes_per_graph > 0);
+  cudaStream_t stream = as_stream(stream_);
+  const int K = (int)num_clusters, H = (int)num_feat, n_cap = max_nodes_per_graph;
+  const bool smem = fwd_smem_bytes(n_cap, K, true) <= kSmemBudget;
+  const size_t shm = fwd_smem_bytes(n_cap, K, smem);
+  if (shm > kSmemBudget) return GHSCN_E_UNSUPPORTED;
+  float* as_ws = nullptr;
+  if (!smem) {
+    if (workspace == nullptr || workspace_bytes < (size_t)num_nodes * K * 4) return GHSCN_E_WORKSPACE;
+    as_ws = static_cast<float*>(workspace);
+  }
+  if (smem) {
+    cudaFuncSetAttribute(mincut_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    mincut_fwd_kernel<true><<<(unsigned)num_graphs, kMincutThreads, shm, stream>>>(
+        logits, ldz, x, ldx, ptr, rowptr, col, adj_val, temp, K, H, n_cap, s_soft, out, out_adj, ss_raw, adj_raw,
+        stats, as_ws);
+  } else {
+    mincut_fwd_kernel<false><<<(unsigned)num_graphs, kMincutThreads, shm, stream>>>(
+        logits, ldz, x, ldx, ptr, rowptr, col, adj_val, temp, K, H, n_cap, s_soft, out, out_adj, ss_raw, adj_raw,
+        stats, as_ws);
+  }
+  mincut_reduce_losses_kernel<<<1, 256, 0, stream>>>(stats, (int)num_graphs, losses);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+int ghscn_mincut_bwd(const float* s_soft, const float* x, int64_t ldx, const int32_t* ptr, const int32_t* rowptr,
+                     const int32_t* col, const float* adj_val, const int32_t* rowptr_t, const int32_t* col_t,
+                     const float* adj_val_t, float temp, int64_t num_graphs, int64_t num_nodes,
+                     int64_t num_clusters, int64_t num_feat, int32_t max_nodes_per_graph, const float* ss_raw,
+                     const float* adj_raw, const float* stats, const float* g_out, const float* g_out_adj,
+                     const float* g_losses, float* d_logits, int64_t lddz, float* d_x, int64_t lddx,
+                     void* workspace, size_t workspace_bytes, ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(num_graphs >= 0 && num_nodes >= 0 && num_clusters > 0 && num_feat >= 0);
+  if (num_clusters > kMaxClusters) return GHSCN_E_UNSUPPORTED;
+  if (num_graphs == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(s_soft && ptr && rowptr && col && rowptr_t && col_t && ss_raw && adj_raw && stats && d_logits);
+  GHSCN_REQUIRE(lddz >= num_clusters && max_nodes_per_graph > 0);
+  GHSCN_REQUIRE((g_out == nullptr && d_x == nullptr) || x != nullptr);
+  cudaStream_t stream = as_stream(stream_);
+  const int K = (int)num_clusters, H = (int)num_feat, n_cap = max_nodes_per_graph;
+  const bool smem = bwd_smem_bytes(n_cap, K, true) <= kSmemBudget;
+  const size_t shm = bwd_smem_bytes(n_cap, K, smem);
+  if (shm > kSmemBudget) return GHSCN_E_UNSUPPORTED;
+  float* ws = nullptr;
+  if (!smem) {
+    if (workspace == nullptr || workspace_bytes < (size_t)3 * num_nodes * K * 4) return GHSCN_E_WORKSPACE;
+    ws = static_cast<float*>(workspace);
+  }
+  if (smem) {
+    cudaFuncSetAttribute(mincut_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    mincut_bwd_kernel<true><<<(unsigned)num_graphs, kMincutThreads, shm, stream>>>(
+        s_soft, x, ldx, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, temp, (int)num_graphs, K, H, n_cap,
+        ss_raw, adj_raw, stats, g_out, g_out_adj, g_losses, d_logits, lddz, d_x, lddx, ws);
+  } else {
+    cudaFuncSetAttribute(mincut_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    mincut_bwd_kernel<false><<<(unsigned)num_graphs, kMincutThreads, shm, stream>>>(
+        s_soft, x, ldx, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, temp, (int)num_graphs, K, H, n_cap,
+        ss_raw, adj_raw, stats, g_out, g_out_adj, g_losses, d_logits, lddz, d_x, lddx, ws);
+  }
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+"""Host-side mirror of the reference's model callers, parameterised by an operator namespace.
+
+The reference's own model files (graph_hscn/model/mpnn.py, graph_hscn/model/hscn.py) run unchanged on
+top of `graph_hscn_b200.pyg.install()`; they are not available on the GPU box, so the benchmark and the
+GPU parity tests use these mirrors instead.  Same constructor arguments, same submodule / parameter
+names (state_dicts interchange with the reference classes), same forward semantics including the
+reference's quirks.  tests/golden pins mirror == unchanged reference source.
+
+`ops` is an operator namespace: `graph_hscn_b200.pyg.namespace()` (CUDA kernels, default) or
+`oracle.namespace()` (CPU oracle; only bench.py's cpu_baseline and tests pass that one in).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+
+ACTIVATIONS: Dict[str, Callable] = {   # config/config.py:13-18
+    "elu": F.elu, "relu": F.relu, "tanh": torch.tanh, "identity": nn.Identity(),
+}
+
+
+def _default_ops() -> SimpleNamespace:
+    from . import pyg
+    return pyg.namespace()
+
+
+class MPNN(nn.Module):
+    """Stack of `conv` layers + mean readout (model/mpnn.py:13-60)."""
+
+    def __init__(self, conv, activation: Callable, num_features: int, hidden_channels: int, num_classes: int,
+                 num_layers: int, dropout: float = 0.0, use_batch_norm: bool = False,
+                 use_layer_norm: bool = False, ops: Optional[SimpleNamespace] = None):
+        super().__init__()
+        self.ops = ops or _default_ops()
+        if isinstance(conv, str):
+            conv = {"gcn": self.ops.GCNConv, "gat": self.ops.GATConv, "gin": self.ops.GINConv}[conv.lower()]
+        widths = [num_features] + [hidden_channels] * (num_layers - 1) + [num_classes]
+        self.num_layers = num_layers
+        self.conv_layers = nn.ModuleList(conv(widths[i], widths[i + 1]) for i in range(num_layers))
+        self.use_batch_norm, self.use_layer_norm = use_batch_norm, use_layer_norm
+        if use_layer_norm:  # the reference creates BOTH lists under this flag (Appendix B-8)
+            self.bns = nn.ModuleList(nn.BatchNorm1d(hidden_channels) for _ in range(num_layers - 1))
+            self.lns = nn.ModuleList(nn.LayerNorm(hidden_channels) for _ in range(num_layers - 1))
+        self.activation, self.dropout = activation, dropout
+
+    def forward(self, batch) -> Tensor:
+        h, edge_index, graph_of_node = batch.x, batch.edge_index, batch.batch
+        for i, conv in enumerate(self.conv_layers[:-1]):
+            h = F.relu(conv(h, edge_index))
+            if self.use_batch_norm:
+                h = self.bns[i](h)
+            if self.use_layer_norm:
+                h = self.lns[i](h)
+            h = F.dropout(self.activation(h), p=self.dropout, training=self.training)
+        h = self.conv_layers[-1](h, edge_index)
+        return self.ops.scatter_mean(h, graph_of_node, dim=0)
+
+
+class SCN(nn.Module):
+    """Spectral-clustering net: GraphConv stack -> MLP logits -> MinCUT losses (model/hscn.py:19-64)."""
+
+    def __init__(self, mp_units: Sequence[int], mp_act: str, num_features: int, num_clusters: int,
+                 mlp_units: Sequence[int] = (), mlp_act: str = "identity",
+                 ops: Optional[SimpleNamespace] = None):
+        super().__init__()
+        o = self.ops = ops or _default_ops()
+        act = ACTIVATIONS[mp_act.lower()]
+        sig = "x, edge_index, edge_weight -> x"
+        dims = [num_features] + list(mp_units)
+        steps: List = []
+        for i in range(len(mp_units)):
+            steps += [(o.GraphConv(dims[i], dims[i + 1]), sig), act]
+        self.mp = o.Sequential("x, edge_index, edge_weight", steps)
+        width = dims[-1]
+        self.mlp = nn.Sequential()
+        for units in mlp_units:  # the reference never advances `width` (Appendix B-9)
+            self.mlp.append(o.Linear(width, units))
+            self.mlp.append(ACTIVATIONS[mlp_act.lower()])
+        self.mlp.append(o.Linear(width, num_clusters))
+
+    def forward(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor]):
+        """One graph per call, as train_clustering.py:44-47 drives it."""
+        o = self.ops
+        h = self.mp(x, edge_index, edge_weight)
+        s = self.mlp(h)
+        adj = o.to_dense_adj(edge_index)
+        _, _, mc_loss, o_loss = o.dense_mincut_pool(h, adj, s)
+        return torch.softmax(s, dim=-1), mc_loss, o_loss, adj
+
+    def forward_batched(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor], batch: Tensor):
+        """Throughput form: the whole `batch`/`ptr` mini-batch in one launch (losses are batch means)."""
+        o = self.ops
+        h = self.mp(x, edge_index, edge_weight)
+        s = self.mlp(h)
+        _, _, mc_loss, o_loss = o.mincut_pool_ragged(h, edge_index, s, batch, want_out=False, want_adj=False)
+        return s, mc_loss, o_loss
+
+
+def build_conv_relation(conv_type: str, hidden_channels: int, ops: SimpleNamespace):
+    """model/hscn.py:117-125, including the case-sensitive 'GAT' test (Appendix B-10)."""
+    dim = (-1, -1) if conv_type == "GAT" else -1
+    cls = {"gcn": ops.GCNConv, "gat": ops.GATConv, "gin": ops.GINConv}[conv_type.lower()]
+    return cls(dim, hidden_channels, add_self_loops=False, cached=False)
+
+
+class HSCN(nn.Module):
+    """Hetero GNN over local/virtual nodes (model/hscn.py:67-114)."""
+
+    def __init__(self, lv_conv: str, ll_conv: str, vv_conv: str, activation: Callable, num_features: int,
+                 hidden_channels: int, num_classes: int, num_layers: int,
+                 ops: Optional[SimpleNamespace] = None):
+        super().__init__()
+        o = self.ops = ops or _default_ops()
+        self.activation = activation
+        self.convs = nn.ModuleList(
+            o.HeteroConv({
+                ("local", "to", "virtual"): build_conv_relation(lv_conv, hidden_channels, o),
+                ("local", "to", "local"): build_conv_relation(ll_conv, hidden_channels, o),
+                ("virtual", "to", "virtual"): build_conv_relation(vv_conv, hidden_channels, o),
+            }, aggr="sum") for _ in range(num_layers))
+        self.lin_1 = o.Linear(hidden_channels, hidden_channels)
+        self.lin_2 = o.Linear(hidden_channels, num_classes)
+
+    def forward(self, x_dict: Dict[str, Tensor], edge_index_dict, batch) -> Tensor:
+        for conv in self.convs:
+            x_dict = {k: v.relu() for k, v in conv(x_dict, edge_index_dict).items()}
+        pooled = self.ops.global_mean_pool(x_dict["local"], batch["local"].batch)
+        return self.lin_2(self.activation(self.lin_1(pooled)))
+
+
+def criterion(loss_fn: str, pred: Tensor, true: Tensor):
+    """graph_hscn/loss.py:6-19 (incl. sigmoid score for L1, Appendix B-12)."""
+    if loss_fn == "cross_entropy":
+        if pred.ndim > 1 and true.ndim == 1:
+            logp = F.log_softmax(pred, dim=-1)
+            return F.nll_loss(logp, true), logp
+        return F.binary_cross_entropy_with_logits(pred, true.float()), torch.sigmoid(pred)
+    return F.l1_loss(pred, true), torch.sigmoid(pred)

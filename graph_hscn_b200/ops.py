@@ -1,0 +1,393 @@
+"""torch custom ops (`torch.ops.ghscn.*`) over the C-ABI kernels of libghscn.so.
+
+Each op is a thin marshalling layer: it allocates outputs with PyTorch (caller-owns-memory contract
+of include/ghscn.h), passes raw device pointers + the current CUDA stream through ctypes, and wires
+the analytic backward with `torch.library.register_autograd`.  CUDA only -- there is no CPU
+implementation registered, so a CPU tensor fails loudly in the dispatcher.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from ._lib import lib
+from .structure import _p, _stream
+
+_custom_op = torch.library.custom_op
+_STATS_STRIDE = 8
+
+
+def _rowmajor(x: Tensor) -> Tensor:
+    if x.dim() != 2:
+        raise ValueError("expected a 2-D feature matrix")
+    if x.dtype != torch.float32:
+        raise TypeError(f"ghscn kernels compute in fp32, got {x.dtype}")
+    if x.stride(1) != 1 or x.stride(0) < x.size(1):
+        x = x.contiguous()
+    return x
+
+
+# =============================================================================================
+# K2/K3  SpMM
+# =============================================================================================
+@_custom_op("ghscn::spmm_raw", mutates_args=(), device_types="cuda")
+def spmm_raw(rowptr: Tensor, col: Tensor, w: Optional[Tensor], x: Tensor, bias: Optional[Tensor],
+             num_rows: int, relu: bool) -> Tensor:
+    x = _rowmajor(x)
+    F = x.size(1)
+    y = torch.empty((num_rows, F), dtype=torch.float32, device=x.device)
+    lib().call("ghscn_spmm", _p(rowptr), _p(col), _p(w), _p(x), x.stride(0), _p(y), F, _p(bias), num_rows, F,
+               int(relu), _stream())
+    return y
+
+
+@spmm_raw.register_fake
+def _(rowptr, col, w, x, bias, num_rows, relu):
+    return x.new_empty((num_rows, x.size(1)))
+
+
+@_custom_op("ghscn::spmm_edge_grad", mutates_args=(), device_types="cuda")
+def spmm_edge_grad(rowptr: Tensor, col: Tensor, x: Tensor, dy: Tensor, num_slots: int) -> Tensor:
+    x, dy = _rowmajor(x), _rowmajor(dy)
+    dw = torch.zeros(num_slots, dtype=torch.float32, device=x.device)
+    lib().call("ghscn_spmm_edge_grad", _p(rowptr), _p(col), None, _p(x), x.stride(0), _p(dy), dy.stride(0),
+               dy.size(0), x.size(1), num_slots, _p(dw), _stream())
+    return dw
+
+
+@spmm_edge_grad.register_fake
+def _(rowptr, col, x, dy, num_slots):
+    return x.new_empty((num_slots,))
+
+
+@_custom_op("ghscn::spmm", mutates_args=(), device_types="cuda")
+def spmm(rowptr: Tensor, col: Tensor, w: Optional[Tensor], rowptr_t: Tensor, col_t: Tensor,
+         w_t: Optional[Tensor], x: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """y = A_w x (+ bias); rows of (rowptr, col) are destinations, (rowptr_t, col_t) is the transpose."""
+    return spmm_raw(rowptr, col, w, x, bias, rowptr.numel() - 1, False)
+
+
+@spmm.register_fake
+def _(rowptr, col, w, rowptr_t, col_t, w_t, x, bias):
+    return x.new_empty((rowptr.numel() - 1, x.size(1)))
+
+
+def _spmm_setup(ctx, inputs, output):
+    rowptr, col, w, rowptr_t, col_t, w_t, x, bias = inputs
+    ctx.has_bias = bias is not None
+    ctx.w_needs_grad = w is not None and w.requires_grad
+    ctx.save_for_backward(rowptr, col, rowptr_t, col_t, w_t, x if ctx.w_needs_grad else None)
+
+
+def _spmm_backward(ctx, dy):
+    rowptr, col, rowptr_t, col_t, w_t, x = ctx.saved_tensors
+    dy = dy.contiguous()
+    dx = dw = dbias = None
+    if ctx.needs_input_grad[6]:
+        dx = spmm_raw(rowptr_t, col_t, w_t, dy, None, rowptr_t.numel() - 1, False)
+    if ctx.w_needs_grad:
+        dw = spmm_edge_grad(rowptr, col, x, dy, col.numel())
+    if ctx.has_bias and ctx.needs_input_grad[7]:
+        dbias = dy.sum(0)
+    return None, None, dw, None, None, None, dx, dbias
+
+
+torch.library.register_autograd("ghscn::spmm", _spmm_backward, setup_context=_spmm_setup)
+
+
+# =============================================================================================
+# K4  segment mean / sum
+# =============================================================================================
+@_custom_op("ghscn::segment_broadcast", mutates_args=(), device_types="cuda")
+def segment_broadcast(dy: Tensor, ptr: Tensor, perm: Optional[Tensor], num_rows: int, mean: bool) -> Tensor:
+    dy = _rowmajor(dy)
+    F = dy.size(1)
+    if perm is None:
+        dx = torch.empty((num_rows, F), dtype=torch.float32, device=dy.device)
+    else:
+        dx = torch.zeros((num_rows, F), dtype=torch.float32, device=dy.device)
+    lib().call("ghscn_segment_broadcast", _p(dy), dy.stride(0), _p(ptr), _p(perm), ptr.numel() - 1, F, int(mean),
+               _p(dx), F, _stream())
+    return dx
+
+
+@segment_broadcast.register_fake
+def _(dy, ptr, perm, num_rows, mean):
+    return dy.new_empty((num_rows, dy.size(1)))
+
+
+@_custom_op("ghscn::segment_reduce", mutates_args=(), device_types="cuda")
+def segment_reduce(x: Tensor, ptr: Tensor, perm: Optional[Tensor], mean: bool) -> Tensor:
+    x = _rowmajor(x)
+    B, F = ptr.numel() - 1, x.size(1)
+    y = torch.empty((B, F), dtype=torch.float32, device=x.device)
+    lib().call("ghscn_segment_reduce", _p(x), x.stride(0), _p(ptr), _p(perm), B, F, int(mean), _p(y), F, _stream())
+    return y
+
+
+@segment_reduce.register_fake
+def _(x, ptr, perm, mean):
+    return x.new_empty((ptr.numel() - 1, x.size(1)))
+
+
+def _seg_setup(ctx, inputs, output):
+    x, ptr, perm, mean = inputs
+    ctx.mean, ctx.num_rows = mean, x.size(0)
+    ctx.save_for_backward(ptr, perm)
+
+
+def _seg_backward(ctx, dy):
+    ptr, perm = ctx.saved_tensors
+    return segment_broadcast(dy.contiguous(), ptr, perm, ctx.num_rows, ctx.mean), None, None, None
+
+
+torch.library.register_autograd("ghscn::segment_reduce", _seg_backward, setup_context=_seg_setup)
+
+
+# =============================================================================================
+# K5  bipartite GAT pool
+# =============================================================================================
+@_custom_op("ghscn::row_dot", mutates_args=(), device_types="cuda")
+def row_dot(x: Tensor, v: Tensor) -> Tensor:
+    x = _rowmajor(x)
+    v = v.contiguous()
+    out = torch.empty(x.size(0), dtype=torch.float32, device=x.device)
+    lib().call("ghscn_row_dot", _p(x), x.stride(0), _p(v), x.size(0), x.size(1), _p(out), _stream())
+    return out
+
+
+@row_dot.register_fake
+def _(x, v):
+    return x.new_empty((x.size(0),))
+
+
+@_custom_op("ghscn::gat_pool_fwd", mutates_args=(), device_types="cuda")
+def gat_pool_fwd(rowptr: Tensor, col: Tensor, hs: Tensor, a_src: Tensor, a_dst: Optional[Tensor],
+                 bias: Optional[Tensor], slope: float, num_slots: int) -> Tuple[Tensor, Tensor]:
+    hs = _rowmajor(hs)
+    V, H = rowptr.numel() - 1, hs.size(1)
+    alpha = torch.zeros(num_slots, dtype=torch.float32, device=hs.device)
+    out = torch.empty((V, H), dtype=torch.float32, device=hs.device)
+    lib().call("ghscn_gat_pool_fwd", _p(rowptr), _p(col), _p(hs), hs.stride(0), _p(a_src), _p(a_dst), _p(bias),
+               float(slope), V, H, _p(alpha), _p(out), H, _stream())
+    return out, alpha
+
+
+@gat_pool_fwd.register_fake
+def _(rowptr, col, hs, a_src, a_dst, bias, slope, num_slots):
+    return hs.new_empty((rowptr.numel() - 1, hs.size(1))), hs.new_empty((num_slots,))
+
+
+@_custom_op("ghscn::gat_pool_bwd", mutates_args=(), device_types="cuda")
+def gat_pool_bwd(rowptr: Tensor, col: Tensor, rowptr_t: Tensor, col_t: Tensor, map_t: Tensor, hs: Tensor,
+                 a_src: Tensor, a_dst: Optional[Tensor], alpha: Tensor, att_src: Tensor, dout: Tensor,
+                 slope: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (dhs [N,H], da_src [N], da_dst [V])"""
+    hs, dout = _rowmajor(hs), _rowmajor(dout)
+    N, H, V = hs.size(0), hs.size(1), rowptr.numel() - 1
+    dev = hs.device
+    dz = torch.zeros(alpha.numel(), dtype=torch.float32, device=dev)
+    da_dst = torch.empty(V, dtype=torch.float32, device=dev)
+    L, st = lib(), _stream()
+    L.call("ghscn_gat_pool_bwd_scores", _p(rowptr), _p(col), _p(hs), hs.stride(0), _p(a_src), _p(a_dst), _p(alpha),
+           _p(dout), dout.stride(0), float(slope), V, H, _p(dz), _p(da_dst), st)
+    dhs = torch.empty((N, H), dtype=torch.float32, device=dev)
+    da_src = torch.empty(N, dtype=torch.float32, device=dev)
+    L.call("ghscn_gat_pool_bwd_src", _p(rowptr_t), _p(col_t), _p(map_t), _p(alpha), _p(dz), _p(dout),
+           dout.stride(0), _p(att_src.contiguous()), N, H, _p(dhs), H, _p(da_src), st)
+    return dhs, da_src, da_dst
+
+
+@gat_pool_bwd.register_fake
+def _(rowptr, col, rowptr_t, col_t, map_t, hs, a_src, a_dst, alpha, att_src, dout, slope):
+    return hs.new_empty(hs.shape), hs.new_empty((hs.size(0),)), hs.new_empty((rowptr.numel() - 1,))
+
+
+@_custom_op("ghscn::gat_pool", mutates_args=(), device_types="cuda")
+def gat_pool(rowptr: Tensor, col: Tensor, rowptr_t: Tensor, col_t: Tensor, map_t: Tensor, hs: Tensor,
+             hd: Optional[Tensor], att_src: Tensor, att_dst: Optional[Tensor], bias: Optional[Tensor],
+             slope: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Bipartite single-head GAT aggregation. -> (out [V,H], alpha [slots], a_src [N], a_dst [V])"""
+    a_src = row_dot(hs, att_src)
+    a_dst = row_dot(hd, att_dst) if hd is not None else torch.zeros(rowptr.numel() - 1, device=hs.device)
+    out, alpha = gat_pool_fwd(rowptr, col, hs, a_src, a_dst, bias, slope, col.numel())
+    return out, alpha, a_src, a_dst
+
+
+@gat_pool.register_fake
+def _(rowptr, col, rowptr_t, col_t, map_t, hs, hd, att_src, att_dst, bias, slope):
+    V = rowptr.numel() - 1
+    return (hs.new_empty((V, hs.size(1))), hs.new_empty((col.numel(),)), hs.new_empty((hs.size(0),)),
+            hs.new_empty((V,)))
+
+
+def _gat_setup(ctx, inputs, output):
+    rowptr, col, rowptr_t, col_t, map_t, hs, hd, att_src, att_dst, bias, slope = inputs
+    out, alpha, a_src, a_dst = output
+    ctx.slope = slope
+    ctx.has = (hd is not None, att_dst is not None, bias is not None)
+    ctx.save_for_backward(rowptr, col, rowptr_t, col_t, map_t, hs, hd, att_src, att_dst, alpha, a_src, a_dst)
+
+
+def _gat_backward(ctx, dout, _dalpha, _das, _dad):
+    rowptr, col, rowptr_t, col_t, map_t, hs, hd, att_src, att_dst, alpha, a_src, a_dst = ctx.saved_tensors
+    has_hd, has_ad, has_bias = ctx.has
+    dout = dout.contiguous()
+    dhs, da_src, da_dst = gat_pool_bwd(rowptr, col, rowptr_t, col_t, map_t, hs, a_src, a_dst, alpha, att_src, dout,
+                                       ctx.slope)
+    datt_src = da_src @ hs
+    dhd = datt_dst = dbias = None
+    if has_hd:
+        dhd = da_dst.unsqueeze(1) * att_dst.unsqueeze(0)
+        datt_dst = da_dst @ hd
+    if has_bias:
+        dbias = dout.sum(0)
+    return None, None, None, None, None, dhs, dhd, datt_src, datt_dst, dbias, None
+
+
+torch.library.register_autograd("ghscn::gat_pool", _gat_backward, setup_context=_gat_setup)
+
+
+# =============================================================================================
+# K6  fused MinCUT pool
+# =============================================================================================
+@_custom_op("ghscn::mincut_bwd", mutates_args=(), device_types="cuda")
+def mincut_bwd(s_soft: Tensor, x: Optional[Tensor], ptr: Tensor, rowptr: Tensor, col: Tensor,
+               adj_val: Optional[Tensor], rowptr_t: Tensor, col_t: Tensor, adj_val_t: Optional[Tensor],
+               ss_raw: Tensor, adj_raw: Tensor, stats: Tensor, g_out: Optional[Tensor],
+               g_out_adj: Optional[Tensor], g_losses: Tensor, temp: float, max_nodes: int, num_feat: int,
+               want_dx: bool) -> Tuple[Tensor, Tensor]:
+    N, K = s_soft.shape
+    B = ptr.numel() - 1
+    dev = s_soft.device
+    dz = torch.empty((N, K), dtype=torch.float32, device=dev)
+    dx = torch.empty((N, num_feat), dtype=torch.float32, device=dev) if want_dx else torch.empty(0, device=dev)
+    L = lib()
+    ws_bytes = L.query("ghscn_mincut_workspace_bytes", N, B, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if x is not None:
+        x = _rowmajor(x)
+    L.call("ghscn_mincut_bwd", _p(s_soft), _p(x), x.stride(0) if x is not None else 0, _p(ptr), _p(rowptr), _p(col),
+           _p(adj_val), _p(rowptr_t), _p(col_t), _p(adj_val_t), float(temp), B, N, K, num_feat, max_nodes,
+           _p(ss_raw), _p(adj_raw), _p(stats), _p(g_out), _p(g_out_adj), _p(g_losses), _p(dz), K,
+           _p(dx) if want_dx else None, num_feat, _p(ws), ws_bytes, _stream())
+    return dz, dx
+
+
+@mincut_bwd.register_fake
+def _(s_soft, x, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, ss_raw, adj_raw, stats, g_out, g_out_adj,
+      g_losses, temp, max_nodes, num_feat, want_dx):
+    return s_soft.new_empty(s_soft.shape), s_soft.new_empty((s_soft.size(0), num_feat) if want_dx else (0,))
+
+
+@_custom_op("ghscn::mincut_pool", mutates_args=(), device_types="cuda")
+def mincut_pool(logits: Tensor, x: Tensor, ptr: Tensor, rowptr: Tensor, col: Tensor, adj_val: Optional[Tensor],
+                rowptr_t: Tensor, col_t: Tensor, adj_val_t: Optional[Tensor], temp: float, max_nodes: int,
+                want_out: bool, want_adj: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Ragged-batch MinCUT pool.  (rowptr, col) rows are edge_index[0] (rows of A); *_t the transpose.
+    -> (out [B,K,H], out_adj [B,K,K], losses [2] = (mincut, ortho), s_soft [N,K], ss_raw, adj_raw, stats)"""
+    logits, x = _rowmajor(logits), _rowmajor(x)
+    N, K = logits.shape
+    H = x.size(1)
+    B = ptr.numel() - 1
+    dev = logits.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    s_soft = torch.empty((N, K), **f32)
+    out = torch.empty((B, K, H), **f32) if want_out else torch.empty(0, **f32)
+    out_adj = torch.empty((B, K, K), **f32) if want_adj else torch.empty(0, **f32)
+    ss_raw = torch.empty((B, K, K), **f32)
+    adj_raw = torch.empty((B, K, K), **f32)
+    stats = torch.empty((B, _STATS_STRIDE), **f32)
+    losses = torch.empty(2, **f32)
+    L = lib()
+    ws_bytes = L.query("ghscn_mincut_workspace_bytes", N, B, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    L.call("ghscn_mincut_fwd", _p(logits), logits.stride(0), _p(x), x.stride(0), _p(ptr), _p(rowptr), _p(col),
+           _p(adj_val), float(temp), B, N, K, H, max_nodes, _p(s_soft), _p(out) if want_out else None,
+           _p(out_adj) if want_adj else None, _p(ss_raw), _p(adj_raw), _p(stats), _p(losses), _p(ws), ws_bytes,
+           _stream())
+    return out, out_adj, losses, s_soft, ss_raw, adj_raw, stats
+
+
+@mincut_pool.register_fake
+def _(logits, x, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, temp, max_nodes, want_out, want_adj):
+    N, K = logits.shape
+    B, H = ptr.numel() - 1, x.size(1)
+    e = logits.new_empty
+    return (e((B, K, H) if want_out else (0,)), e((B, K, K) if want_adj else (0,)), e((2,)), e((N, K)),
+            e((B, K, K)), e((B, K, K)), e((B, _STATS_STRIDE)))
+
+
+def _mincut_setup(ctx, inputs, output):
+    (logits, x, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, temp, max_nodes, want_out, want_adj) = inputs
+    out, out_adj, losses, s_soft, ss_raw, adj_raw, stats = output
+    ctx.temp, ctx.max_nodes, ctx.want = temp, max_nodes, (want_out, want_adj)
+    ctx.num_feat = x.size(1)
+    ctx.save_for_backward(s_soft, x, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, ss_raw, adj_raw, stats)
+
+
+def _mincut_backward(ctx, g_out, g_adj, g_losses, *_unused):
+    (s_soft, x, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, ss_raw, adj_raw, stats) = ctx.saved_tensors
+    want_out, want_adj = ctx.want
+    g_out = g_out.contiguous() if (want_out and g_out is not None) else None
+    g_adj = g_adj.contiguous() if (want_adj and g_adj is not None) else None
+    if g_losses is None:
+        g_losses = torch.zeros(2, dtype=torch.float32, device=s_soft.device)
+    want_dx = bool(ctx.needs_input_grad[1])
+    dz, dx = mincut_bwd(s_soft, x, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, ss_raw, adj_raw, stats,
+                        g_out, g_adj, g_losses.contiguous(), ctx.temp, ctx.max_nodes, ctx.num_feat, want_dx)
+    return (dz, dx if want_dx else None) + (None,) * 11
+
+
+torch.library.register_autograd("ghscn::mincut_pool", _mincut_backward, setup_context=_mincut_setup)
+
+
+# =============================================================================================
+# K7  cluster assignment -> virtual nodes (integer work, no autograd)
+# =============================================================================================
+@_custom_op("ghscn::cluster_argmax", mutates_args=(), device_types="cuda")
+def cluster_argmax(s_soft: Tensor) -> Tensor:
+    s_soft = _rowmajor(s_soft)
+    out = torch.empty(s_soft.size(0), dtype=torch.int32, device=s_soft.device)
+    lib().call("ghscn_cluster_argmax", _p(s_soft), s_soft.stride(0), s_soft.size(0), s_soft.size(1), _p(out),
+               _stream())
+    return out
+
+
+@cluster_argmax.register_fake
+def _(s_soft):
+    return s_soft.new_empty((s_soft.size(0),), dtype=torch.int32)
+
+
+@_custom_op("ghscn::virtual_build", mutates_args=(), device_types="cuda")
+def virtual_build(cluster: Tensor, ptr: Tensor, x_raw: Tensor, num_clusters: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (cluster_remapped int32 [N], num_virtual int32 [B], virt_x_padded fp32 [B*K, F])"""
+    if x_raw.dtype not in (torch.int64, torch.float32):
+        raise TypeError("raw node features must be int64 (OGB atoms) or float32")
+    x_raw = x_raw.contiguous()
+    N, F = x_raw.shape
+    B = ptr.numel() - 1
+    dev = x_raw.device
+    remap = torch.empty(N, dtype=torch.int32, device=dev)
+    nv = torch.empty(B, dtype=torch.int32, device=dev)
+    vx = torch.empty((B * num_clusters, F), dtype=torch.float32, device=dev)
+    lib().call("ghscn_virtual_build", _p(cluster), _p(ptr), _p(x_raw), int(x_raw.dtype == torch.int64), F, B,
+               num_clusters, F, _p(remap), _p(nv), _p(vx), _stream())
+    return remap, nv, vx
+
+
+@virtual_build.register_fake
+def _(cluster, ptr, x_raw, num_clusters):
+    B = ptr.numel() - 1
+    return (cluster.new_empty(cluster.shape), cluster.new_empty((B,)),
+            x_raw.new_empty((B * num_clusters, x_raw.size(1)), dtype=torch.float32))
+
+
+def cast_i64_f32(x: Tensor) -> Tensor:
+    """`batch.x.float()` (train.py:79) for int64 OGB atom features."""
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    lib().call("ghscn_cast_i64_f32", _p(x), x.numel(), _p(out), _stream())
+    return out

@@ -1,0 +1,301 @@
+"""PyG-named layers backed by the sm_100a kernels (drop-in boundary).
+
+Constructor signatures, parameter names/shapes and forward semantics mirror torch_geometric so the
+reference's model code (model/mpnn.py, model/hscn.py) instantiates and calls them unchanged and
+state_dicts interchange with a real PyG install:
+  GCNConv   lin.weight [out,in], bias [out]                        model/mpnn.py:29-32,52,59; hscn.py:88-93
+  GraphConv lin_rel.{weight,bias}, lin_root.weight                 model/hscn.py:32-34,40-41
+  GATConv   lin_src/lin_dst.weight, att_src/att_dst [1,H,C], bias  model/hscn.py:85-87
+  HeteroConv convs.<src__rel__dst>.*                               model/hscn.py:83-96,109
+Dense GEMMs (x @ W^T) stay on cuBLAS fp32 through F.linear (TF32 off: parity is 1e-5).
+"""
+from __future__ import annotations
+
+import math
+from collections import defaultdict
+from typing import Callable, Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+from torch.nn.parameter import UninitializedParameter
+
+from ..structure import _require_cuda, structure_cache
+
+
+def glorot(t: Optional[Tensor]) -> None:
+    if t is not None:
+        stdv = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+        with torch.no_grad():
+            t.uniform_(-stdv, stdv)
+
+
+class Linear(nn.Module):
+    """torch_geometric.nn.Linear: supports lazy `in_channels=-1` (hscn.py:50-54,99-100)."""
+
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True,
+                 weight_initializer: Optional[str] = None, bias_initializer: Optional[str] = None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight_initializer, self.bias_initializer = weight_initializer, bias_initializer
+        self.weight = (nn.Parameter(torch.empty(out_channels, in_channels)) if in_channels > 0
+                       else UninitializedParameter())
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        if isinstance(self.weight, UninitializedParameter):
+            return
+        if self.weight_initializer == "glorot":
+            glorot(self.weight)
+        else:
+            nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            if self.bias_initializer == "zeros":
+                nn.init.zeros_(self.bias)
+            else:
+                bound = 1.0 / math.sqrt(self.weight.size(1)) if self.weight.size(1) > 0 else 0.0
+                nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, x: Tensor) -> Tensor:
+        if isinstance(self.weight, UninitializedParameter):
+            self.in_channels = x.size(-1)
+            self.weight.materialize((self.out_channels, self.in_channels), device=x.device)
+            self.reset_parameters()
+        return F.linear(x, self.weight, self.bias)
+
+    def extra_repr(self) -> str:
+        return f"{self.in_channels}, {self.out_channels}, bias={self.bias is not None}"
+
+
+class MessagePassing(nn.Module):
+    """Base type (config/config.py:9 and model/mpnn.py:7 annotate with it)."""
+
+
+def _aggregate(x_src: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor], num_dst: int,
+               normalize: bool = False, improved: bool = False, add_self_loops: bool = False,
+               bias: Optional[Tensor] = None) -> Tensor:
+    """out[i] = sum_{e: col_e = i} w_e * x_src[row_e] (+ bias): CSR lookup + K2 SpMM."""
+    _require_cuda(x_src, edge_index)
+    st = structure_cache().graph(edge_index, x_src.size(0), num_dst, add_self_loops)
+    w_param = None
+    if edge_weight is not None and edge_weight.requires_grad and not normalize:
+        # differentiable explicit weights: gather to slot order with autograd, unit loops not involved
+        w_param = edge_weight.float()[st.by_dst.perm.long()]
+        w, w_t = w_param, edge_weight.detach().float()[st.by_src.perm.long()]
+    else:
+        if edge_weight is not None and edge_weight.requires_grad:
+            raise NotImplementedError("gradients w.r.t. edge_weight through gcn_norm are not on the reference's path")
+        w, w_t, _ = st.weights(edge_weight, normalize=normalize, improved=improved)
+    d, s = st.by_dst, st.by_src
+    if x_src.dtype != torch.float32:
+        x_src = x_src.float()
+    return torch.ops.ghscn.spmm(d.rowptr, d.col, w, s.rowptr, s.col, w_t, x_src, bias)
+
+
+class GCNConv(MessagePassing):
+    """out = D^-1/2 (A [+ I]) D^-1/2 (x W^T) + b  (SURVEY A.3).  gcn_norm is folded into the batch CSR,
+    which is built once per `edge_index` tensor and shared by all layers and by the backward."""
+
+    def __init__(self, in_channels: int, out_channels: int, improved: bool = False, cached: bool = False,
+                 add_self_loops: bool = True, normalize: bool = True, bias: bool = True, **kwargs):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.improved, self.cached = improved, cached
+        self.add_self_loops, self.normalize = add_self_loops, normalize
+        self.lin = Linear(in_channels, out_channels, bias=False, weight_initializer="glorot")
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+        else:
+            self.register_parameter("bias", None)
+
+    def reset_parameters(self) -> None:
+        self.lin.reset_parameters()
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def forward(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor] = None) -> Tensor:
+        h = self.lin(x)
+        return _aggregate(h, edge_index, edge_weight, x.size(0), normalize=self.normalize,
+                          improved=self.improved, add_self_loops=self.add_self_loops and self.normalize,
+                          bias=self.bias)
+
+
+class GraphConv(MessagePassing):
+    """out = lin_rel(sum_j w_ji x_j) + lin_root(x_i)  (SURVEY A.4): aggregate at input width first."""
+
+    def __init__(self, in_channels: Union[int, Tuple[int, int]], out_channels: int, aggr: str = "add",
+                 bias: bool = True, **kwargs):
+        super().__init__()
+        if aggr != "add":
+            raise NotImplementedError("GraphConv aggr must be 'add' (the reference's default)")
+        if isinstance(in_channels, int):
+            in_channels = (in_channels, in_channels)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_rel = Linear(in_channels[0], out_channels, bias=bias)
+        self.lin_root = Linear(in_channels[1], out_channels, bias=False)
+
+    def forward(self, x, edge_index: Tensor, edge_weight: Optional[Tensor] = None, size=None) -> Tensor:
+        if isinstance(x, Tensor):
+            x = (x, x)
+        n_dst = x[1].size(0) if x[1] is not None else (size[1] if size is not None else x[0].size(0))
+        out = self.lin_rel(_aggregate(x[0], edge_index, edge_weight, n_dst))
+        if x[1] is not None:
+            out = out + self.lin_root(x[1])
+        return out
+
+
+class GINConv(MessagePassing):
+    """Listed in CONV_DICT (config/config.py:19-23): out = nn((1 + eps) x_i + sum_j x_j)."""
+
+    def __init__(self, nn_module: Callable, eps: float = 0.0, train_eps: bool = False, **kwargs):
+        super().__init__()
+        self.nn = nn_module
+        self.initial_eps = eps
+        if train_eps:
+            self.eps = nn.Parameter(torch.tensor([eps]))
+        else:
+            self.register_buffer("eps", torch.tensor([eps]))
+
+    def forward(self, x, edge_index: Tensor, size=None) -> Tensor:
+        if isinstance(x, Tensor):
+            x = (x, x)
+        out = _aggregate(x[0], edge_index, None, x[1].size(0))
+        if x[1] is not None:
+            out = out + (1 + self.eps) * x[1]
+        return self.nn(out)
+
+
+class GATConv(MessagePassing):
+    """Single-head graph attention.  The bipartite form GATConv((-1,-1), C,
+    add_self_loops=False) on ("local","to","virtual") is the reference's cluster pool."""
+
+    def __init__(self, in_channels: Union[int, Tuple[int, int]], out_channels: int, heads: int = 1,
+                 concat: bool = True, negative_slope: float = 0.2, dropout: float = 0.0,
+                 add_self_loops: bool = True, bias: bool = True, **kwargs):
+        super().__init__()
+        if heads != 1:
+            raise NotImplementedError("heads > 1 is not on the reference's path (SURVEY 8f rank 3)")
+        if dropout != 0.0:
+            raise NotImplementedError("attention dropout is not on the reference's path")
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.concat, self.negative_slope, self.dropout = concat, negative_slope, dropout
+        self.add_self_loops = add_self_loops
+        if isinstance(in_channels, int):
+            self.lin_src = Linear(in_channels, heads * out_channels, bias=False, weight_initializer="glorot")
+            self.lin_dst = self.lin_src
+        else:
+            self.lin_src = Linear(in_channels[0], heads * out_channels, False, weight_initializer="glorot")
+            self.lin_dst = Linear(in_channels[1], heads * out_channels, False, weight_initializer="glorot")
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        glorot(self.att_src)
+        glorot(self.att_dst)
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(heads * out_channels if concat else out_channels))
+        else:
+            self.register_parameter("bias", None)
+
+    def forward(self, x, edge_index: Tensor, edge_attr=None, size=None) -> Tensor:
+        if edge_attr is not None:
+            raise NotImplementedError("GATConv edge features are not on the reference's path")
+        if isinstance(x, Tensor):
+            hs = self.lin_src(x)
+            hd = hs
+        else:
+            x_src, x_dst = x
+            hs = self.lin_src(x_src)
+            hd = self.lin_dst(x_dst) if x_dst is not None else None
+        _require_cuda(hs, edge_index)
+        n_src = hs.size(0)
+        n_dst = hd.size(0) if hd is not None else (size[1] if size is not None else n_src)
+        if self.add_self_loops and n_src != n_dst:
+            raise NotImplementedError("add_self_loops on a bipartite relation is not on the reference's path")
+        st = structure_cache().graph(edge_index, n_src, n_dst, self.add_self_loops)
+        d, s = st.by_dst, st.by_src
+        out, *_ = torch.ops.ghscn.gat_pool(d.rowptr, d.col, s.rowptr, s.col, st.slot_map_t, hs, hd,
+                                            self.att_src.view(-1), self.att_dst.view(-1), self.bias,
+                                            float(self.negative_slope))
+        return out
+
+
+class HeteroConv(nn.Module):
+    """Runs one conv per relation in `edge_index_dict` order and sums per destination type (A.9)."""
+
+    def __init__(self, convs: Dict[Tuple[str, str, str], nn.Module], aggr: Optional[str] = "sum"):
+        super().__init__()
+        self.convs = nn.ModuleDict({"__".join(k): v for k, v in convs.items()})
+        self.aggr = aggr
+
+    def forward(self, x_dict: Dict[str, Tensor], edge_index_dict: Dict[Tuple[str, str, str], Tensor]
+                ) -> Dict[str, Tensor]:
+        outs: Dict[str, List[Tensor]] = defaultdict(list)
+        for edge_type, edge_index in edge_index_dict.items():
+            src, _, dst = edge_type
+            key = "__".join(edge_type)
+            if key not in self.convs:
+                continue
+            conv = self.convs[key]
+            if src == dst:
+                out = conv(x_dict[src], edge_index)
+            else:
+                out = conv((x_dict[src], x_dict[dst]), edge_index)
+            outs[dst].append(out)
+        result: Dict[str, Tensor] = {}
+        for key, xs in outs.items():
+            if self.aggr in ("sum", "add"):
+                acc = xs[0]
+                for t in xs[1:]:      # == torch.stack(xs).sum(0) for <= 2 terms; left-to-right beyond
+                    acc = acc + t
+                result[key] = acc
+            elif self.aggr == "mean":
+                result[key] = torch.stack(xs, 0).mean(0)
+            elif self.aggr == "max":
+                result[key] = torch.stack(xs, 0).max(0)[0]
+            elif self.aggr == "min":
+                result[key] = torch.stack(xs, 0).min(0)[0]
+            elif self.aggr == "cat":
+                result[key] = torch.cat(xs, -1)
+            else:
+                result[key] = torch.stack(xs, 1)
+        return result
+
+
+class Sequential(nn.Module):
+    """torch_geometric.nn.Sequential(input_args, [(module, 'a, b -> c') | callable, ...]) (hscn.py:30-45)."""
+
+    def __init__(self, input_args: str, modules: List[Union[Tuple[Callable, str], Callable]]):
+        super().__init__()
+        self._inputs = [a.strip() for a in input_args.split(",")]
+        self._steps: List[Tuple[str, List[str], List[str]]] = []
+        last = [self._inputs[0]]
+        for i, entry in enumerate(modules):
+            if isinstance(entry, (tuple, list)):
+                fn, desc = entry
+                lhs, rhs = desc.split("->")
+                ins = [a.strip() for a in lhs.split(",")]
+                outs = [a.strip() for a in rhs.split(",")]
+            else:
+                fn, ins, outs = entry, list(last), list(last)
+            name = f"module_{i}"
+            if isinstance(fn, nn.Module):
+                self.add_module(name, fn)
+            else:
+                object.__setattr__(self, name, fn)
+            self._steps.append((name, ins, outs))
+            last = outs
+
+    def forward(self, *args):
+        env = dict(zip(self._inputs, args))
+        out = None
+        for name, ins, outs in self._steps:
+            out = getattr(self, name)(*[env[k] for k in ins])
+            if len(outs) == 1:
+                env[outs[0]] = out
+            else:
+                env.update(zip(outs, out))
+        return out

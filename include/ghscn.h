@@ -1,0 +1,217 @@
+/*
+ * ghscn.h -- C ABI of libghscn.so: the B200 (sm_100a) kernels behind the
+ * Graph-HSCN hot path.
+ *
+ * The reference (camille-004/Graph-HSCN) has no FFI layer of its own: its
+ * hot path is reached by importing PyTorch Geometric / torch_scatter
+ * operators.  Each entry point below therefore cites the *reference call
+ * site* whose operator it replaces (paths relative to the reference root) and
+ * the SURVEY.md section 8a row.  The Python host
+ * (graph_hscn_b200/_lib.py -> ops.py -> pyg/*) binds these with ctypes and
+ * wraps them as torch custom ops; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller (PyTorch) owns every buffer; the library never allocates,
+ *     frees, synchronises or keeps global state; all work is enqueued on
+ *     `stream` and is CUDA-graph-capture safe;
+ *   - feature matrices are row-major fp32 with an explicit leading dimension
+ *     (elements); index arrays produced by this library are int32, index
+ *     arrays received from PyTorch (edge_index, batch) are int64;
+ *   - return value: 0 = ok, <0 = GHSCN_E_* argument error (nothing was
+ *     launched), >0 = cudaError_t reported by the launch.
+ */
+#ifndef GHSCN_H_
+#define GHSCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GHSCN_API __attribute__((visibility("default")))
+
+typedef void* ghscn_stream_t; /* cudaStream_t */
+
+enum {
+  GHSCN_OK = 0,
+  GHSCN_E_INVALID = -1,    /* null pointer / negative size / bad flag */
+  GHSCN_E_WORKSPACE = -2,  /* workspace smaller than *_workspace_bytes() */
+  GHSCN_E_UNSUPPORTED = -3 /* shape outside what the kernel supports */
+};
+
+GHSCN_API int ghscn_abi_version(void);
+GHSCN_API const char* ghscn_error_string(int code);
+
+/* ---- K1: CSR construction (stable integer radix sort + boundary scan) ------------------------
+ * Replaces the implicit COO handling of PyG MessagePassing and `add_remaining_self_loops`
+ * inside gcn_norm (train/train_clustering.py:37-42; every GCNConv.forward at model/mpnn.py:52,59
+ * and model/hscn.py:109).  SURVEY 8a rows a1, a2.
+ * Sorts the E edges stably by key[] (destination for the forward structure, source for the
+ * transposed one).  With add_self_loops != 0, edges with key == other are dropped and one loop
+ * (i,i) per row is appended after all original edges, exactly PyG's edge order.  Negative keys are
+ * padding and are dropped.
+ *   rowptr [num_rows+1]  row r owns slots rowptr[r] .. rowptr[r+1]-1; rowptr[num_rows] = nnz
+ *   col    [E (+num_rows)] other endpoint of the edge in each slot (-1 in unused tail slots)
+ *   perm   [E (+num_rows)] original edge id of each slot; ids >= E are the appended loops
+ */
+GHSCN_API size_t ghscn_csr_workspace_bytes(int64_t num_edges, int64_t num_rows, int32_t add_self_loops);
+GHSCN_API int ghscn_csr_build(const int64_t* key, const int64_t* other, int64_t num_edges, int64_t num_rows,
+                              int32_t add_self_loops, int32_t* rowptr, int32_t* col, int32_t* perm,
+                              void* workspace, size_t workspace_bytes, ghscn_stream_t stream);
+
+/* sorted `batch` vector -> ptr[num_graphs+1] (PyG collate convention). */
+GHSCN_API int ghscn_batch_to_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs, int32_t* ptr,
+                                 ghscn_stream_t stream);
+
+/* ---- K1b: gcn_norm folded onto the CSR ------------------------------------------------------
+ * Replaces gcn_norm's scatter_add degree + deg^-1/2[row] * w * deg^-1/2[col]
+ * (train/train_clustering.py:37-42; GCNConv.forward).  SURVEY 8a row a1, Appendix A.2.
+ * `rowptr/perm` must be the BY-DESTINATION structure.  edge_weight may be NULL (all ones).
+ * loop_weight[num_rows] (nullable) carries the weight of appended loops (fill value, or the
+ * weight of a pre-existing loop); NULL means 1.0.  dis[r] = deg^-1/2 with inf -> 0.
+ */
+GHSCN_API int ghscn_gcn_deg_inv_sqrt(const int32_t* rowptr, const int32_t* perm, const float* edge_weight,
+                                     const float* loop_weight, int64_t num_edges, int64_t num_rows, float* dis,
+                                     ghscn_stream_t stream);
+/* Per-slot weights for either orientation of the same edge set:
+ *   normalize != 0: w[s] = (dis[src] * ew) * dis[dst]   (PyG multiplication order)
+ *   normalize == 0: w[s] = ew
+ * rows_are_dst tells which endpoint the structure's rows are. */
+GHSCN_API int ghscn_edge_weights(const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                                 const float* edge_weight, const float* loop_weight, const float* dis,
+                                 int64_t num_edges, int64_t num_rows, int32_t normalize, int32_t rows_are_dst,
+                                 float* w, ghscn_stream_t stream);
+/* loop_weight[i] = weight of the LAST edge (i,i) in edge order, else fill (PyG add_remaining_self_loops). */
+GHSCN_API int ghscn_loop_weights(const int64_t* row, const int64_t* colidx, const float* edge_weight,
+                                 int64_t num_edges, int64_t num_rows, float fill, int32_t* scratch_last,
+                                 float* loop_weight, ghscn_stream_t stream);
+
+/* ---- K2/K3: SpMM  y[r,:] = sum_{s in row r} w[s] * x[col[s],:]  (+ bias) (+ relu) ----------------
+ * Replaces MessagePassing.propagate = index_select -> mul -> scatter_add_ of GCNConv
+ * (model/mpnn.py:52,59; model/hscn.py:88-93) and GraphConv (model/hscn.py:32-34,40-41).
+ * SURVEY 8a rows a2, a3.  The sum runs sequentially in slot (= edge) order with separate
+ * multiply and add roundings, i.e. the CPU scatter_add_ order.  The same entry computes the
+ * backward w.r.t. x when given the transposed structure.  w == NULL means unit weights.
+ */
+GHSCN_API int ghscn_spmm(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, int64_t ldx,
+                         float* y, int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat,
+                         int32_t relu, ghscn_stream_t stream);
+/* d(edge weight)[s] = <dy[row(s),:], x[col[s],:]> written at the ORIGINAL edge position perm[s]
+ * (entries for appended loops, perm >= num_edges, are skipped).  perm == NULL writes dw_edge[s]. */
+GHSCN_API int ghscn_spmm_edge_grad(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* x,
+                                   int64_t ldx, const float* dy, int64_t lddy, int64_t num_rows, int64_t num_feat,
+                                   int64_t num_edges, float* dw_edge, ghscn_stream_t stream);
+
+/* ---- K4: segment mean / sum over contiguous row ranges ---------------------------------------
+ * Replaces torch_scatter.scatter_mean(x, batch, dim=0) (model/mpnn.py:60) and
+ * global_mean_pool (model/hscn.py:111).  SURVEY 8a row a10.  mean != 0 divides by max(count,1).
+ * perm (nullable) gathers rows (x[perm[i]]) for unsorted indices. */
+GHSCN_API int ghscn_segment_reduce(const float* x, int64_t ldx, const int32_t* ptr, const int32_t* perm,
+                                   int64_t num_segments, int64_t num_feat, int32_t mean, float* y, int64_t ldy,
+                                   ghscn_stream_t stream);
+/* backward: dx[i,:] = dy[seg(i),:] * (mean ? 1/max(count,1) : 1) */
+GHSCN_API int ghscn_segment_broadcast(const float* dy, int64_t lddy, const int32_t* ptr, const int32_t* perm,
+                                      int64_t num_segments, int64_t num_feat, int32_t mean, float* dx, int64_t lddx,
+                                      ghscn_stream_t stream);
+
+/* ---- K5: bipartite GAT cluster pool (local -> virtual) ---------------------------------------
+ * Replaces GATConv((-1,-1), H, add_self_loops=False) on ("local","to","virtual")
+ * (model/hscn.py:85-87,118-125).  SURVEY 8a row a9, Appendix A.8.  heads = 1.
+ *   a_src[j] = <hs[j,:], att_src>, a_dst[i] = <hd[i,:], att_dst>          (ghscn_row_dot)
+ *   e = leaky_relu(a_src[col[s]] + a_dst[r]); alpha = segment softmax over row r (+1e-16)
+ *   out[r,:] = sum_s alpha[s] * hs[col[s],:] + bias
+ * alpha[nnz] is written per slot for the backward. a_dst may be NULL (no destination term).
+ */
+GHSCN_API int ghscn_row_dot(const float* x, int64_t ldx, const float* v, int64_t num_rows, int64_t num_feat,
+                            float* out, ghscn_stream_t stream);
+GHSCN_API int ghscn_gat_pool_fwd(const int32_t* rowptr, const int32_t* col, const float* hs, int64_t ldhs,
+                                 const float* a_src, const float* a_dst, const float* bias, float negative_slope,
+                                 int64_t num_rows, int64_t num_feat, float* alpha, float* out, int64_t ldout,
+                                 ghscn_stream_t stream);
+/* backward part 1 (per destination row): dz[s] = d(loss)/d(pre-activation score of slot s),
+ * da_dst[r] = sum_s dz[s].   part 2 is ghscn_spmm on the transposed structure with w = alpha_t,
+ * plus the rank-1 term handled by the host. */
+GHSCN_API int ghscn_gat_pool_bwd_scores(const int32_t* rowptr, const int32_t* col, const float* hs, int64_t ldhs,
+                                        const float* a_src, const float* a_dst, const float* alpha,
+                                        const float* dout, int64_t lddout, float negative_slope, int64_t num_rows,
+                                        int64_t num_feat, float* dz, float* da_dst, ghscn_stream_t stream);
+/* backward part 2 (per source row, transposed structure):
+ *   da_src[j] = sum_t dz[map_t[t]];  dhs[j,:] = sum_t alpha[map_t[t]] * dout[col_t[t],:] + da_src[j] * att_src */
+GHSCN_API int ghscn_gat_pool_bwd_src(const int32_t* rowptr_t, const int32_t* col_t, const int32_t* map_t,
+                                     const float* alpha, const float* dz, const float* dout, int64_t lddout,
+                                     const float* att_src, int64_t num_rows, int64_t num_feat, float* dhs,
+                                     int64_t lddhs, float* da_src, ghscn_stream_t stream);
+/* map_t[t] = slot, in the by-destination structure, of the edge stored in transposed slot t
+ * (perm / perm_t are the slot -> edge-id arrays of the two orientations; scratch_pos[num_items]). */
+GHSCN_API int ghscn_slot_map(const int32_t* perm, const int32_t* perm_t, int64_t nnz, int64_t num_items,
+                             int32_t* scratch_pos, int32_t* map_t, ghscn_stream_t stream);
+
+/* ---- K6: fused MinCUT pool, one CTA per graph --------------------------------------------------
+ * Replaces to_dense_adj + dense_mincut_pool (model/hscn.py:61-63).  SURVEY 8a rows a4, a5,
+ * Appendix A.6/A.7.  The adjacency is consumed as the batch CSR whose ROWS ARE edge_index[0]
+ * (A[r,c] = multiplicity or adj_val of edge (r,c)); adj_val == NULL means 1 per stored edge.
+ * The backward also needs the other orientation (rows = edge_index[1]) for A^T S.
+ * graph g owns nodes ptr[g]..ptr[g+1]-1; column ids are global node ids of the same graph.
+ *   s_soft   [N,K]   softmax(logits)                     (written; saved for backward)
+ *   out      [B,K,H] S^T X            (nullable: skipped)
+ *   out_adj  [B,K,K] normalised, zero-diagonal S^T A S   (nullable)
+ *   stats    [B,8]   per graph: num, den, ||SS||_F, ortho_g, mc_g, reserved...
+ *   mc_loss / ortho_loss scalars are the batch means, reduced deterministically by
+ *   ghscn_mincut_reduce_losses.
+ */
+GHSCN_API size_t ghscn_mincut_workspace_bytes(int64_t num_nodes, int64_t num_graphs, int64_t num_clusters);
+GHSCN_API int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x, int64_t ldx, const int32_t* ptr,
+                               const int32_t* rowptr, const int32_t* col, const float* adj_val, float temp,
+                               int64_t num_graphs, int64_t num_nodes, int64_t num_clusters, int64_t num_feat,
+                               int32_t max_nodes_per_graph, float* s_soft, float* out, float* out_adj,
+                               float* ss_raw, float* adj_raw, float* stats, float* losses /*[2]*/,
+                               void* workspace, size_t workspace_bytes, ghscn_stream_t stream);
+GHSCN_API int ghscn_mincut_bwd(const float* s_soft, const float* x, int64_t ldx, const int32_t* ptr,
+                               const int32_t* rowptr, const int32_t* col, const float* adj_val,
+                               const int32_t* rowptr_t, const int32_t* col_t, const float* adj_val_t, float temp,
+                               int64_t num_graphs, int64_t num_nodes, int64_t num_clusters, int64_t num_feat,
+                               int32_t max_nodes_per_graph, const float* ss_raw, const float* adj_raw,
+                               const float* stats, const float* g_out /*[B,K,H]|NULL*/,
+                               const float* g_out_adj /*[B,K,K]|NULL*/, const float* g_losses /*[2] device*/,
+                               float* d_logits, int64_t lddz, float* d_x /*nullable*/, int64_t lddx,
+                               void* workspace, size_t workspace_bytes, ghscn_stream_t stream);
+
+/* ---- K7: cluster assignment -> virtual-node construction --------------------------------------
+ * Replaces softmax(s).max(1)[1] (train/train_clustering.py:68) and the Python/numpy loops of
+ * loader/hetero_data.py:44-86.  SURVEY 8a rows a6, a7.  One CTA per graph, integer work bit-exact:
+ *   cluster[i]   first-max index of row i of s_soft (int32)
+ *   remap to 0..U-1 by sorted unique; bucket slot (c-1) mod K (negative index quirk, :53);
+ *   non-empty slots compacted -> virtual feature rows (float64 mean of raw features -> fp32);
+ *   lv edge (i, c_i); vv edges {(i,j): i+j <= U-1} in the reference's [col;row] order.
+ * Padded outputs (static shapes, K virtual slots per graph) + per-graph U; the compaction to the
+ * reference's ragged layout is ghscn_virtual_compact.
+ */
+GHSCN_API int ghscn_cluster_argmax(const float* s_soft, int64_t lds, int64_t num_nodes, int64_t num_clusters,
+                                   int32_t* cluster, ghscn_stream_t stream);
+GHSCN_API int ghscn_virtual_build(const int32_t* cluster, const int32_t* ptr, const void* x_raw, int32_t x_is_int64,
+                                  int64_t ldx, int64_t num_graphs, int64_t num_clusters, int64_t num_feat,
+                                  int32_t* cluster_remapped /*[N] 0..U-1*/, int32_t* num_virtual /*[B] U_g*/,
+                                  float* virt_x_padded /*[B*K,F]*/, ghscn_stream_t stream);
+GHSCN_API int ghscn_virtual_edges(const int32_t* cluster_remapped, const int32_t* ptr, const int32_t* num_virtual,
+                                  const int32_t* virt_offset /*[B+1] exclusive scan of U_g, or NULL => g*K*/,
+                                  int64_t num_graphs, int64_t num_nodes, int64_t num_clusters,
+                                  int64_t* lv_edge_index /*[2,N]*/, int64_t* vv_edge_index /*[2,vv_cap]*/,
+                                  int64_t vv_cap, const int32_t* vv_offset /*[B+1] or NULL => g*K(K+1)/2*/,
+                                  ghscn_stream_t stream);
+GHSCN_API int ghscn_virtual_offsets(const int32_t* num_virtual, int64_t num_graphs, int32_t* virt_offset /*[B+1]*/,
+                                    int32_t* vv_offset /*[B+1]*/, ghscn_stream_t stream);
+GHSCN_API int ghscn_virtual_compact(const float* virt_x_padded, const int32_t* num_virtual,
+                                    const int32_t* virt_offset, int64_t num_graphs, int64_t num_clusters,
+                                    int64_t num_feat, float* virt_x /*[V,F]*/, int64_t* virt_batch /*[V]*/,
+                                    ghscn_stream_t stream);
+
+/* ---- small fused elementwise epilogues ------------------------------------ */
+GHSCN_API int ghscn_cast_i64_f32(const int64_t* in, int64_t n, float* out, ghscn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GHSCN_H_ */

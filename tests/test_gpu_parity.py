@@ -1,0 +1,471 @@
+"""GPU parity tests: CUDA path (through the C ABI / torch custom ops) vs the CPU oracle.
+
+Bars (BASELINE.json north_star): bit-exact for CSR construction, cluster argmax and virtual-node
+indexing; <= 1e-5 relative (fp32) for features, pooled adjacency, losses and gradients.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import RTOL, assert_close, random_edge_index, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle.namespace import namespace
+    return namespace()
+
+
+def _product():
+    from graph_hscn_b200 import pyg
+    return pyg.namespace()
+
+
+def _to_dev(model_cpu_ctor, model_gpu_ctor, dev, prime):
+    """Build the oracle model on CPU and the product model on GPU with identical parameters."""
+    torch.manual_seed(0)
+    ref = model_cpu_ctor()
+    prime(ref, "cpu")               # materialise lazy parameters
+    tst = model_gpu_ctor().to(dev)
+    from torch.nn.parameter import UninitializedParameter
+    sd = ref.state_dict()
+    for name, p in tst.named_parameters():
+        if isinstance(p, UninitializedParameter):
+            p.materialize(sd[name].shape, device=dev)
+    tst.load_state_dict(sd)
+    return ref, tst
+
+
+# ------------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (7, 5, 1), (300, 2000, 2), (19200, 39296, 3), (70000, 300000, 4),
+                                       (5, 4097, 5)])
+@pytest.mark.parametrize("loops", [False, True])
+def test_csr_build_bit_exact(cuda, n, e, seed, loops):
+    from graph_hscn_b200.structure import build_csr
+    from oracle import ops as oops
+    g = torch.Generator().manual_seed(seed)
+    ei = random_edge_index(n, n, e, g)
+    if loops:
+        ei2, _ = oops.add_remaining_self_loops(ei, None, 1.0, n)
+        keep_ids = torch.cat([torch.nonzero(ei[0] != ei[1]).flatten(), e + torch.arange(n)])
+    else:
+        ei2, keep_ids = ei, torch.arange(e)
+    order = torch.sort(ei2[1], stable=True)[1]
+    want_perm = keep_ids[order].int()
+    want_col = ei2[0][order].int()
+    want_rowptr = torch.cat([torch.zeros(1, dtype=torch.long), torch.bincount(ei2[1], minlength=n).cumsum(0)]).int()
+
+    eid = ei.to(cuda)
+    csr = build_csr(eid[1], eid[0], n, loops)
+    nnz = ei2.size(1)
+    assert torch.equal(csr.rowptr.cpu(), want_rowptr)
+    assert torch.equal(csr.perm[:nnz].cpu(), want_perm)
+    assert torch.equal(csr.col[:nnz].cpu(), want_col)
+    if nnz < csr.num_items:      # dropped loops: tail holds them in edge order, col = -1
+        assert bool((csr.col[nnz:] == -1).all())
+        dropped = torch.nonzero(ei[0] == ei[1]).flatten().int()
+        assert torch.equal(csr.perm[nnz:].cpu(), dropped)
+
+
+def test_csr_ignores_negative_padding(cuda):
+    from graph_hscn_b200.structure import build_csr
+    ei = torch.tensor([[0, -1, 2, 1, -1], [1, -1, 0, 1, -1]])
+    csr = build_csr(ei[1].to(cuda), ei[0].to(cuda), 3, False)
+    assert csr.rowptr.tolist() == [0, 1, 3, 3]
+    assert csr.perm[:3].tolist() == [2, 0, 3]
+
+
+def test_batch_to_ptr(cuda):
+    from graph_hscn_b200.structure import structure_cache
+    batch = torch.tensor([0, 0, 0, 2, 2, 5])
+    seg = structure_cache().segments(batch.to(cuda), 7)
+    assert seg.ptr.tolist() == [0, 3, 3, 5, 5, 5, 6, 6]
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("loops", [False, True])
+def test_gcn_norm_bit_exact(cuda, weighted, loops):
+    from graph_hscn_b200.pyg import gcn_norm
+    from oracle import ops as oops
+    g = torch.Generator().manual_seed(11)
+    n, e = 500, 3000
+    ei = random_edge_index(n, n, e, g)
+    w = torch.rand(e, generator=g) + 0.1 if weighted else None
+    ref_ei, ref_w = oops.gcn_norm(ei, w, n, False, loops)
+    got_ei, got_w = gcn_norm(ei.to(cuda), None if w is None else w.to(cuda), n, False, loops)
+    assert torch.equal(got_ei.cpu(), ref_ei)
+    assert torch.equal(got_w.cpu(), ref_w), f"max diff {(got_w.cpu() - ref_w).abs().max()}"
+
+
+# ------------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("feat", [1, 9, 10, 16, 64, 300, 512, 700])
+def test_spmm_matches_scatter_add(cuda, feat):
+    from graph_hscn_b200.structure import structure_cache
+    from oracle import ops as oops
+    g = torch.Generator().manual_seed(feat)
+    n, e = 1000, 4000
+    ei = random_edge_index(n, n, e, g)
+    w = torch.randn(e, generator=g)
+    x = torch.randn(n, feat, generator=g)
+    ref = oops.propagate_add(x, ei, w, n)
+    st = structure_cache().graph(ei.to(cuda), n, n, False)
+    wd, wt, _ = st.weights(w.to(cuda), normalize=False)
+    d, s = st.by_dst, st.by_src
+    got = torch.ops.ghscn.spmm(d.rowptr, d.col, wd, s.rowptr, s.col, wt, x.to(cuda), None)
+    # same summation order and roundings as CPU scatter_add_: expect (near) bit equality
+    assert_close(got, ref, 1e-6, f"spmm F={feat}")
+    exact = float((got.cpu() == ref).float().mean())
+    assert exact > 0.99, f"only {exact:.3f} of outputs bit-equal"
+
+
+@pytest.mark.parametrize("add_loops", [True, False])
+def test_gcnconv_fwd_bwd(cuda, add_loops):
+    o, p = _oracle(), _product()
+    g = torch.Generator().manual_seed(5)
+    n, e, fi, fo = 800, 2400, 9, 300
+    ei = random_edge_index(n, n, e, g)
+    x = torch.randn(n, fi, generator=g)
+    ref, tst = _to_dev(lambda: o.GCNConv(fi, fo, add_self_loops=add_loops),
+                       lambda: p.GCNConv(fi, fo, add_self_loops=add_loops), cuda, lambda m, d: None)
+    with torch.no_grad():
+        ref.bias.uniform_(-1, 1)
+        tst.bias.copy_(ref.bias)
+    xr = x.clone().requires_grad_()
+    xt = x.to(cuda).requires_grad_()
+    yr = ref(xr, ei)
+    yt = tst(xt, ei.to(cuda))
+    assert_close(yt, yr, RTOL, "GCNConv out")
+    gy = torch.randn(n, fo, generator=g)
+    yr.backward(gy)
+    yt.backward(gy.to(cuda))
+    assert_close(xt.grad, xr.grad, RTOL, "GCNConv dx")
+    assert_close(tst.lin.weight.grad, ref.lin.weight.grad, RTOL, "GCNConv dW")
+    assert_close(tst.bias.grad, ref.bias.grad, RTOL, "GCNConv db")
+
+
+def test_graphconv_weighted_fwd_bwd(cuda):
+    o, p = _oracle(), _product()
+    g = torch.Generator().manual_seed(6)
+    n, e = 150, 460
+    ei = random_edge_index(n, n, e, g, self_loops=False)
+    x = torch.randint(0, 10, (n, 9), generator=g).float()
+    ei_n, w_n = o.gcn_norm(ei, None, n, add_self_loops=True)
+    ref, tst = _to_dev(lambda: o.GraphConv(9, 16), lambda: p.GraphConv(9, 16), cuda, lambda m, d: None)
+    wr = w_n.clone().requires_grad_()
+    wt = w_n.to(cuda).requires_grad_()
+    yr = ref(x, ei_n, wr)
+    yt = tst(x.to(cuda), ei_n.to(cuda), wt)
+    assert_close(yt, yr, RTOL, "GraphConv out")
+    yr.sum().backward()
+    yt.sum().backward()
+    assert_close(tst.lin_rel.weight.grad, ref.lin_rel.weight.grad, RTOL, "dW_rel")
+    assert_close(tst.lin_root.weight.grad, ref.lin_root.weight.grad, RTOL, "dW_root")
+    assert_close(wt.grad, wr.grad, RTOL, "d edge_weight")
+
+
+# ------------------------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("feat", [10, 11, 300])
+@pytest.mark.parametrize("sorted_index", [True, False])
+def test_scatter_mean_fwd_bwd(cuda, feat, sorted_index):
+    o, p = _oracle(), _product()
+    g = torch.Generator().manual_seed(7)
+    B, n = 37, 3000
+    idx = torch.randint(0, B, (n,), generator=g)
+    idx[idx == 5] = 6  # an empty segment
+    if sorted_index:
+        idx = idx.sort()[0]
+    x = torch.randn(n, feat, generator=g)
+    xr = x.clone().requires_grad_()
+    xt = x.to(cuda).requires_grad_()
+    yr = o.scatter_mean(xr, idx, dim=0, dim_size=B)
+    yt = p.scatter_mean(xt, idx.to(cuda), dim=0, dim_size=B)
+    assert_close(yt, yr, 1e-6, "scatter_mean")
+    gy = torch.randn(B, feat, generator=g)
+    yr.backward(gy)
+    yt.backward(gy.to(cuda))
+    assert_close(xt.grad, xr.grad, 1e-6, "scatter_mean dx")
+    # global_mean_pool with inferred size
+    assert_close(p.global_mean_pool(x.to(cuda), idx.to(cuda)), o.global_mean_pool(x, idx), 1e-6, "gmp")
+
+
+# ------------------------------------------------------------------------------------------- K5
+def test_gat_bipartite_fwd_bwd(cuda):
+    o, p = _oracle(), _product()
+    g = torch.Generator().manual_seed(8)
+    N, V, fi, H = 1500, 100, 9, 300
+    lv = torch.stack([torch.arange(N), torch.randint(0, V - 3, (N,), generator=g)])   # last 3 virtual: empty
+    xl = torch.randn(N, fi, generator=g)
+    xv = torch.randn(V, fi, generator=g)
+
+    def prime(m, d):
+        m((xl.to(d), xv.to(d)), lv.to(d))
+    ref, tst = _to_dev(lambda: o.GATConv((-1, -1), H, add_self_loops=False),
+                       lambda: p.GATConv((-1, -1), H, add_self_loops=False), cuda, prime)
+    with torch.no_grad():
+        ref.bias.uniform_(-1, 1)
+        tst.bias.copy_(ref.bias)
+    xlr, xvr = xl.clone().requires_grad_(), xv.clone().requires_grad_()
+    xlt, xvt = xl.to(cuda).requires_grad_(), xv.to(cuda).requires_grad_()
+    yr = ref((xlr, xvr), lv)
+    yt = tst((xlt, xvt), lv.to(cuda))
+    assert_close(yt, yr, RTOL, "GAT out")
+    gy = torch.randn(V, H, generator=g)
+    yr.backward(gy)
+    yt.backward(gy.to(cuda))
+    assert_close(xlt.grad, xlr.grad, 2 * RTOL, "GAT dx_local")
+    assert_close(xvt.grad, xvr.grad, 2 * RTOL, "GAT dx_virtual")
+    for name in ["lin_src.weight", "lin_dst.weight", "att_src", "att_dst", "bias"]:
+        gr = dict(ref.named_parameters())[name].grad
+        gt = dict(tst.named_parameters())[name].grad
+        assert_close(gt, gr, 2 * RTOL, f"GAT d{name}")
+
+
+def test_gat_homogeneous_self_loops(cuda):
+    o, p = _oracle(), _product()
+    g = torch.Generator().manual_seed(9)
+    n, e = 400, 1500
+    ei = random_edge_index(n, n, e, g)
+    x = torch.randn(n, 9, generator=g)
+    ref, tst = _to_dev(lambda: o.GATConv(9, 32), lambda: p.GATConv(9, 32), cuda, lambda m, d: None)
+    assert_close(tst(x.to(cuda), ei.to(cuda)), ref(x, ei), RTOL, "GAT homogeneous")
+
+
+# ------------------------------------------------------------------------------------------- K6
+def _peptide_batch(num_graphs, seed):
+    from graph_hscn_b200 import synthetic
+    return synthetic.peptides_batch(num_graphs, seed=seed)
+
+
+@pytest.mark.parametrize("K,H", [(10, 16), (4, 64), (32, 40), (128, 24)])
+def test_mincut_ragged_fwd_bwd(cuda, K, H):
+    o, p = _oracle(), _product()
+    b = _peptide_batch(6, seed=K)
+    g = torch.Generator().manual_seed(K)
+    N = b.x.size(0)
+    ei, _ = o.gcn_norm(b.edge_index, None, N, add_self_loops=True)   # binary A + I, as hscn.py:61 sees it
+    x = torch.randn(N, H, generator=g)
+    s = torch.randn(N, K, generator=g)
+    xr, sr = x.clone().requires_grad_(), s.clone().requires_grad_()
+    xt, st_ = x.to(cuda).requires_grad_(), s.to(cuda).requires_grad_()
+    out_r, adj_r, mc_r, or_r = o.mincut_pool_ragged(xr, ei, sr, b.batch)
+    out_t, adj_t, mc_t, or_t = p.mincut_pool_ragged(xt, ei.to(cuda), st_, b.batch.to(cuda))
+    assert_close(out_t, out_r, RTOL, "mincut out")
+    assert_close(adj_t, adj_r, RTOL, "mincut out_adj")
+    assert_close(mc_t, mc_r, RTOL, "mincut loss")
+    assert_close(or_t, or_r, RTOL, "ortho loss")
+    # full backward: all four outputs feed the objective
+    go = torch.randn(out_r.shape, generator=g)
+    ga = torch.randn(adj_r.shape, generator=g)
+    (mc_r * 1.3 + or_r * 0.7 + (out_r * go).sum() * 0.01 + (adj_r * ga).sum()).backward()
+    (mc_t * 1.3 + or_t * 0.7 + (out_t * go.to(cuda)).sum() * 0.01 + (adj_t * ga.to(cuda)).sum()).backward()
+    assert_close(st_.grad, sr.grad, 5 * RTOL, "mincut d logits")
+    assert_close(xt.grad, xr.grad, 5 * RTOL, "mincut d x")
+
+
+def test_mincut_losses_only_backward(cuda):
+    """The reference keeps only the two losses (hscn.py:63): the diag-only fast path."""
+    o, p = _oracle(), _product()
+    b = _peptide_batch(9, seed=77)
+    g = torch.Generator().manual_seed(1)
+    N, K, H = b.x.size(0), 10, 16
+    ei, _ = o.gcn_norm(b.edge_index, None, N, add_self_loops=True)
+    x = torch.randn(N, H, generator=g)
+    s = torch.randn(N, K, generator=g)
+    sr, st_ = s.clone().requires_grad_(), s.to(cuda).requires_grad_()
+    _, _, mc_r, or_r = o.mincut_pool_ragged(x, ei, sr, b.batch)
+    _, _, mc_t, or_t = p.mincut_pool_ragged(x.to(cuda), ei.to(cuda), st_, b.batch.to(cuda), want_out=False,
+                                            want_adj=False)
+    (mc_r + or_r).backward()
+    (mc_t + or_t).backward()
+    assert_close(mc_t, mc_r, RTOL, "mc")
+    assert_close(or_t, or_r, RTOL, "ortho")
+    assert_close(st_.grad, sr.grad, 5 * RTOL, "d logits")
+
+
+def test_dense_mincut_pool_single_graph_api(cuda):
+    """Exactly the reference call pattern: to_dense_adj(edge_index) -> dense_mincut_pool(x, adj, s)."""
+    o, p = _oracle(), _product()
+    from graph_hscn_b200 import synthetic
+    d = synthetic.peptides_graphs(1, seed=4)[0]
+    n = d.num_nodes
+    ei, _ = o.gcn_norm(d.edge_index, None, n, add_self_loops=True)
+    g = torch.Generator().manual_seed(2)
+    x, s = torch.randn(n, 16, generator=g), torch.randn(n, 5, generator=g)
+    ref = o.dense_mincut_pool(x, o.to_dense_adj(ei), s)
+    adj = p.to_dense_adj(ei.to(cuda))
+    got = p.dense_mincut_pool(x.to(cuda), adj, s.to(cuda))
+    for a, b_, nm in zip(got, ref, ["out", "out_adj", "mc", "ortho"]):
+        assert_close(a, b_, RTOL, nm)
+    assert got[0].shape == ref[0].shape and got[1].shape == ref[1].shape
+    # the lazy adjacency densifies to the same tensor PyG would have returned
+    assert torch.equal(adj.to_dense().cpu(), o.to_dense_adj(ei))
+    # dense-input overload (a real dense tensor, weighted) + mask
+    dense = torch.rand(2, 30, 30, generator=g) * (torch.rand(2, 30, 30, generator=g) < 0.2)
+    xs, ss = torch.randn(2, 30, 8, generator=g), torch.randn(2, 30, 5, generator=g)
+    mask = torch.ones(2, 30, dtype=torch.bool)
+    mask[1, 20:] = False
+    ref = o.dense_mincut_pool(xs, dense, ss, mask)
+    got = p.dense_mincut_pool(xs.to(cuda), dense.to(cuda), ss.to(cuda), mask.to(cuda))
+    for a, b_, nm in zip(got, ref, ["out", "out_adj", "mc", "ortho"]):
+        assert_close(a, b_, RTOL, "dense " + nm)
+
+
+# ------------------------------------------------------------------------------------------- K7
+@pytest.mark.parametrize("K", [4, 10, 32])
+@pytest.mark.parametrize("int_feats", [True, False])
+def test_virtual_nodes_bit_exact(cuda, K, int_feats):
+    from graph_hscn_b200 import hetero, synthetic
+    from graph_hscn_b200.data import Batch, HeteroData
+    from oracle import hetero as ohet
+    graphs = synthetic.peptides_graphs(7, seed=K)
+    g = torch.Generator().manual_seed(K)
+    if not int_feats:
+        for d in graphs:
+            d.x = torch.randn(d.x.shape, generator=g)
+    b = Batch.from_data_list(graphs)
+    N = b.x.size(0)
+    s = torch.softmax(torch.randn(N, K, generator=g) * 3, -1)
+    s[3] = s[3, 0]          # an exact tie row: first index must win
+    clusters_ref = ohet.cluster_argmax(s)
+    clusters = hetero.assign_clusters(s.to(cuda))
+    assert np.array_equal(clusters.cpu().numpy(), clusters_ref)
+    if K == 4:
+        clusters_ref[: graphs[0].num_nodes] = 2      # a graph with a single non-empty cluster
+        clusters = torch.from_numpy(clusters_ref).int().to(cuda)
+    # reference: per-graph HeteroData + PyG collate
+    hlist = []
+    for gi, d in enumerate(graphs):
+        lo, hi = int(b.ptr[gi]), int(b.ptr[gi + 1])
+        _, vx, vv, lv = ohet.virtual_nodes(d.x, clusters_ref[lo:hi], K)
+        h = HeteroData()
+        h["local"].x = d.x.float()
+        h["local"].y = d.y
+        h["virtual"].x = vx
+        h["local", "to", "local"].edge_index = d.edge_index
+        h["virtual", "to", "virtual"].edge_index = vv
+        h["local", "to", "virtual"].edge_index = lv
+        hlist.append(h)
+    ref = Batch.from_data_list(hlist)
+    got = hetero.build_hetero_batch(b.x.to(cuda), b.edge_index.to(cuda), b.batch.to(cuda), clusters, K,
+                                    y=b.y.to(cuda))
+    assert list(got.edge_index_dict.keys()) == list(ref.edge_index_dict.keys())
+    for et in ref.edge_index_dict:
+        assert torch.equal(got.edge_index_dict[et].cpu(), ref.edge_index_dict[et]), et
+    assert torch.equal(got["virtual"].x.cpu(), ref["virtual"].x), "virtual features must be bit-exact"
+    assert torch.equal(got["virtual"].batch.cpu(), ref["virtual"].batch)
+    assert torch.equal(got["local"].x.cpu(), ref["local"].x)
+    # padded layout == compact layout after dropping the empty slots
+    pad = hetero.build_hetero_batch(b.x.to(cuda), b.edge_index.to(cuda), b.batch.to(cuda), clusters, K,
+                                    padded=True)
+    nv = got.num_virtual.cpu()
+    sel = torch.cat([gi * K + torch.arange(int(u)) for gi, u in enumerate(nv)])
+    assert torch.equal(pad["virtual"].x.cpu()[sel], ref["virtual"].x)
+    vvp = pad[("virtual", "to", "virtual")].edge_index.cpu()
+    assert int((vvp[0] >= 0).sum()) == ref[("virtual", "to", "virtual")].edge_index.size(1)
+
+
+# ------------------------------------------------------------------------------------- model level
+def test_mpnn_model_fwd_bwd(cuda):
+    """Config #1 shape at reduced width: MPNN(GCN) on a Peptides-shaped batch, BCE loss."""
+    from graph_hscn_b200 import models
+    o, p = _oracle(), _product()
+    b = _peptide_batch(16, seed=21)
+    b.x = b.x.float()
+    ref, tst = _to_dev(lambda: models.MPNN("gcn", torch.relu, 9, 64, 10, 5, ops=o),
+                       lambda: models.MPNN("gcn", torch.relu, 9, 64, 10, 5, ops=p), cuda, lambda m, d: None)
+    bt = b.to(cuda)
+    yr, yt = ref(b), tst(bt)
+    assert_close(yt, yr, RTOL, "MPNN logits")
+    lr, _ = models.criterion("cross_entropy", yr, b.y)
+    lt, _ = models.criterion("cross_entropy", yt, bt.y)
+    lr.backward()
+    lt.backward()
+    assert_close(lt, lr, RTOL, "loss")
+    for (n1, p1), (n2, p2) in zip(ref.named_parameters(), tst.named_parameters()):
+        assert_close(p2.grad, p1.grad, 10 * RTOL, f"grad {n1}")
+
+
+def test_scn_per_graph_and_batched(cuda):
+    from graph_hscn_b200 import models, synthetic
+    o, p = _oracle(), _product()
+    ref, tst = _to_dev(lambda: models.SCN([16], "elu", 9, 10, ops=o), lambda: models.SCN([16], "elu", 9, 10, ops=p),
+                       cuda, lambda m, d: None)
+    d = synthetic.peptides_graphs(1, seed=31)[0]
+    n = d.num_nodes
+    ei_r, w_r = o.gcn_norm(d.edge_index, None, n, add_self_loops=True)
+    ei_t, w_t = p.gcn_norm(d.edge_index.to(cuda), None, n, add_self_loops=True)
+    Sr, mcr, orr, adjr = ref(d.x.float(), ei_r, w_r)
+    St, mct, ort, adjt = tst(d.x.float().to(cuda), ei_t, w_t)
+    assert_close(St, Sr, RTOL, "S")
+    assert_close(mct, mcr, RTOL, "mc")
+    assert_close(ort, orr, RTOL, "ortho")
+    (mcr + orr).backward()
+    (mct + ort).backward()
+    for (n1, p1), (n2, p2) in zip(ref.named_parameters(), tst.named_parameters()):
+        assert_close(p2.grad, p1.grad, 20 * RTOL, f"SCN grad {n1}")
+    # cluster ids: bit-exact wherever the fp32 softmax margin exceeds rounding noise
+    top2 = Sr.topk(2, dim=1)[0]
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-5
+    from graph_hscn_b200 import hetero
+    cl = hetero.assign_clusters(St).cpu()
+    assert torch.equal(cl[safe].long(), Sr.max(1)[1][safe])
+    assert float(safe.float().mean()) > 0.9
+    # batched
+    b = _peptide_batch(12, seed=32)
+    N = b.x.size(0)
+    ref.zero_grad(); tst.zero_grad()
+    ei_r, w_r = o.gcn_norm(b.edge_index, None, N, add_self_loops=True)
+    ei_t, w_t = p.gcn_norm(b.edge_index.to(cuda), None, N, add_self_loops=True)
+    _, mcr, orr = ref.forward_batched(b.x.float(), ei_r, w_r, b.batch)
+    _, mct, ort = tst.forward_batched(b.x.float().to(cuda), ei_t, w_t, b.batch.to(cuda))
+    assert_close(mct, mcr, RTOL, "batched mc")
+    assert_close(ort, orr, RTOL, "batched ortho")
+    (mcr + orr).backward()
+    (mct + ort).backward()
+    for (n1, p1), (n2, p2) in zip(ref.named_parameters(), tst.named_parameters()):
+        assert_close(p2.grad, p1.grad, 20 * RTOL, f"SCN batched grad {n1}")
+
+
+def test_hscn_model_fwd_bwd(cuda):
+    """Config #2 shape at reduced width: 3-relation HeteroConv (GAT l->v, GCN l->l, GCN v->v)."""
+    from graph_hscn_b200 import hetero, models
+    o, p = _oracle(), _product()
+    K = 10
+    b = _peptide_batch(10, seed=41)
+    g = torch.Generator().manual_seed(41)
+    clusters = torch.randint(0, K, (b.x.size(0),), generator=g).int()
+    hb = hetero.build_hetero_batch(b.x.to(cuda), b.edge_index.to(cuda), b.batch.to(cuda), clusters.to(cuda), K,
+                                   y=b.y.to(cuda))
+    hb_cpu = hb.to("cpu")
+
+    def prime(m, d):
+        src = hb_cpu if d == "cpu" else hb
+        m(src.x_dict, src.edge_index_dict, src)
+    ref, tst = _to_dev(lambda: models.HSCN("GAT", "GCN", "GCN", torch.relu, 9, 48, 10, 3, ops=o),
+                       lambda: models.HSCN("GAT", "GCN", "GCN", torch.relu, 9, 48, 10, 3, ops=p), cuda, prime)
+    yr = ref(hb_cpu.x_dict, hb_cpu.edge_index_dict, hb_cpu)
+    yt = tst(hb.x_dict, hb.edge_index_dict, hb)
+    assert_close(yt, yr, RTOL, "HSCN logits")
+    # operator-level parity of the virtual branch (dead w.r.t. the loss but part of HeteroConv's output)
+    xr = ref.convs[0](hb_cpu.x_dict, hb_cpu.edge_index_dict)
+    xt = tst.convs[0](hb.x_dict, hb.edge_index_dict)
+    assert set(xr) == set(xt) == {"local", "virtual"}
+    assert_close(xt["virtual"], xr["virtual"], RTOL, "HeteroConv virtual")
+    assert_close(xt["local"], xr["local"], RTOL, "HeteroConv local")
+    lr, _ = models.criterion("cross_entropy", yr, hb_cpu["local"].y)
+    lt, _ = models.criterion("cross_entropy", yt, hb["local"].y)
+    lr.backward()
+    lt.backward()
+    for (n1, p1), (n2, p2) in zip(ref.named_parameters(), tst.named_parameters()):
+        if p1.grad is None:
+            assert p2.grad is None or float(p2.grad.abs().max()) == 0.0, n1   # dead virtual branch
+        else:
+            assert_close(p2.grad, p1.grad, 10 * RTOL, f"HSCN grad {n1}")
+
+
+def test_cpu_tensor_fails_loudly(cuda):
+    from graph_hscn_b200 import pyg
+    conv = pyg.GCNConv(4, 4)
+    with pytest.raises(RuntimeError):
+        conv(torch.randn(3, 4), torch.tensor([[0, 1], [1, 2]]))
