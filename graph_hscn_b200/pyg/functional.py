@@ -166,7 +166,10 @@ def dense_mincut_pool(x: Tensor, adj, s: Tensor, mask: Optional[Tensor] = None, 
     new_id = (torch.cumsum(keep.view(-1).long(), 0) - 1).view(B, n)     # ragged node ids
     b_idx, r_idx, c_idx = dense.nonzero(as_tuple=True)
     ok = keep[b_idx, r_idx] & keep[b_idx, c_idx]
-    b_idx, r_idx, c_idx = b_idx[ok], r_idx[ok], c_idx[ok]
+    if not bool(ok.all()):
+        # PyG would count edges into masked nodes in the degree term; padded nodes of a collated batch never
+        # have edges, so refuse instead of silently computing something else.
+        raise ValueError("dense_mincut_pool: adjacency has entries on masked-out nodes")
     ei = torch.stack([new_id[b_idx, r_idx], new_id[b_idx, c_idx]])
     vals = dense[b_idx, r_idx, c_idx].float()
     batch = torch.repeat_interleave(torch.arange(B, device=x.device), counts)
