@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the Graph-HSCN hot path (BASELINE.json metric: fwd+bwd graphs/sec, config #2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the hot path over one Peptides-func-shaped batch of 128 graphs per GPU:
+SCN (GraphConv 9->16, ELU, Linear->K=10) + fused MinCUT losses fwd+bwd+AdamW  ->  cluster argmax and
+on-device virtual-node construction  ->  HSCN (3 x HeteroConv{GAT l->v, GCN l->l, GCN v->v}, h=300,
+mean readout, 2 linears) + BCE fwd+bwd+AdamW.  Rank 0 prints ONE JSON line.
+
+  value        graphs/s, whole job, inputs resident in HBM, CUDA-graph replay, CUDA-event timed,
+               L2 flushed between timed steps, max over ranks
+  e2e          same metric through the public step API with pinned HOST buffers: H2D of the batch and
+               D2H of the losses inside the timed region every step
+  roofline     achieved HBM GB/s of the dominant hand-written kernel (the h=300 SpMM) vs MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (oracle/step.py, the reference's algorithm) on this host's cores, bounded sample
+  --impl reference   times that CPU oracle as its own arm (PyG is not installable here)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GRAPHS_PER_GPU = 128
+SEED = 1234 + 2            # manual_seed(1234 + config_id), config #2
+METRIC = "Graph-HSCN fwd+bwd graphs/sec"
+WORKLOAD = ("config#2: Graph-HSCN step on a Peptides-func-shaped batch (128 graphs/GPU, ~151 nodes, ~307 directed "
+            "edges, 9 atom feats): SCN MinCUT K=10 fwd+bwd+AdamW -> cluster argmax + virtual nodes -> "
+            "HSCN 3x HeteroConv(GAT l->v, GCN l->l, GCN v->v) h=300 + BCE fwd+bwd+AdamW")
+
+
+def _env_int(name: str, default: int) -> int:
+    return int(os.environ.get(name, default))
+
+
+def _peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed regions run (NVML)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index: int, period: float = 0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def finish(self) -> dict:
+        self._stop.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def _physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------
+def make_batch(rank: int):
+    from graph_hscn_b200 import synthetic
+    return synthetic.peptides_batch(GRAPHS_PER_GPU, seed=SEED + 1000 * rank, task="func")
+
+
+def time_cpu_oracle(batch, steps: int, warmup: int, budget_s: float):
+    """Runs oracle/step.py; shrinks the sample (graphs per step) so the run fits the time budget."""
+    import torch
+    from graph_hscn_b200.data import Batch
+    from graph_hscn_b200.train import StepConfig
+    from oracle.step import OracleStep
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    graphs = batch.to_data_list()
+    n_graphs = len(graphs)
+    st = OracleStep(StepConfig(), batch)
+    t0 = time.perf_counter()
+    st.run()
+    t_first = time.perf_counter() - t0
+    planned = (max(warmup, 1) - 1 + steps) * t_first
+    if planned > budget_s:
+        n_graphs = max(8, int(n_graphs * budget_s / planned))
+        batch = Batch.from_data_list(graphs[:n_graphs])
+        st = OracleStep(StepConfig(), batch)
+        st.run()
+    for _ in range(max(warmup - 1, 0)):
+        st.run()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        st.run()
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": n_graphs * steps / total, "ms_per_step": 1e3 * total / steps, "cores": cores,
+            "graphs_per_step": n_graphs, "steps": steps, "losses": st.losses}
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    if rank != 0:
+        return
+    batch = make_batch(0)
+    r = time_cpu_oracle(batch, args.steps, args.warmup, budget_s=150.0)
+    sample = (f"{r['graphs_per_step']} of {GRAPHS_PER_GPU} graphs per step, {r['steps']} timed steps after "
+              f"{args.warmup} warm-up, torch CPU threads={r['cores']}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "graphs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "graphs_per_step": r["graphs_per_step"], "device": "cpu"},
+        "cpu_baseline": {"value": r["value"], "unit": "graphs/s", "cores": r["cores"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": r["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU oracle port of the reference path (PyG/torch_scatter are not installable offline)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def spmm_roofline(step, hidden: int, flush, reps: int = 30) -> dict:
+    """Times the dominant hand-written kernel (GCN aggregation SpMM at width `hidden`) alone, cold L2."""
+    import torch
+    from graph_hscn_b200.structure import structure_cache, structure_hints
+    dev = step.device
+    N = step.dev["x"].size(0)
+    with structure_hints(**step.hints):
+        st = structure_cache().graph(step.dev["edge_index"], N, N, False)
+        w, w_t, _ = st.weights(None, normalize=True)
+        d = st.by_dst
+    nnz = d.num_items
+    x = torch.randn(N, hidden, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for _ in range(3):
+        torch.ops.ghscn.spmm_raw(d.rowptr, d.col, w, x, None, N, False)
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        torch.ops.ghscn.spmm_raw(d.rowptr, d.col, w, x, None, N, False)
+        b.record()
+    torch.cuda.synchronize()
+    ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    algo_bytes = 4 * hidden * (N + N) + 4 * nnz + 4 * nnz + 4 * (N + 1)
+    peaks = _peaks()
+    achieved = algo_bytes / (ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("spmm_h300_dram_bytes_per_launch")
+    return {"bound": "hbm", "kernel": f"spmm_kernel<4,32,3,weighted> N={N} F={hidden} nnz={nnz}",
+            "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "algorithmic_bytes": algo_bytes,
+            "avg_launch_us": ms * 1e3, "timing": "CUDA events, L2 flushed before every launch"}
+
+
+def run_product(args, rank: int, local_rank: int, world: int) -> None:
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle arm)")
+    torch.backends.cuda.matmul.allow_tf32 = False      # parity bar is 1e-5 relative: fp32 GEMMs
+    torch.backends.cudnn.allow_tf32 = False
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from graph_hscn_b200._lib import lib
+    from graph_hscn_b200.train import GraphHSCNStep, StepConfig
+
+    cfg = StepConfig()
+    batch = make_batch(rank)
+    step = GraphHSCNStep(cfg, batch, dev, padded=True)
+    n0 = lib().query("ghscn_launch_count")
+    step.capture(world=world, warmup=3)
+    # the capture pass issues each kernel of one step exactly once
+    launches_per_step = None
+    n1 = lib().query("ghscn_launch_count")
+    step_probe = n1 - n0
+    launches_per_step = step_probe // 4            # 3 eager warm-up steps + 1 captured step
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(_physical_gpu_index(local_rank)) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step.run(world)
+    barrier()
+    if sampler:
+        sampler.start()
+    # ---- device-resident timing ------------------------------------------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        step.run(world)
+        b.record()
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    # ---- end-to-end timing: pinned host inputs -> H2D -> step -> D2H losses, every step ------------
+    for _ in range(3):
+        step.upload(); step.run(world); step.download()
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step.upload()
+        step.run(world)
+        out = step.download()
+        torch.cuda.current_stream().synchronize()
+        e2e_s += time.perf_counter() - t0
+    losses = [float(v) for v in out]
+    barrier()
+    clocks = sampler.finish() if sampler else None
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    total_graphs = world * GRAPHS_PER_GPU * args.steps
+
+    roof = cpu = None
+    if rank == 0:
+        roof = spmm_roofline(step, cfg.hidden, flush)
+        if world == 1 and not args.no_cpu_baseline:
+            r = time_cpu_oracle(batch, steps=3, warmup=1, budget_s=25.0)
+            cpu = {"value": r["value"], "unit": "graphs/s", "cores": r["cores"], "kind": "port",
+                   "sample": f"{r['graphs_per_step']} of {GRAPHS_PER_GPU} graphs per step, 3 timed steps after 1 warm-up "
+                             f"({r['ms_per_step']:.0f} ms/step), same synthetic batch, oracle/step.py"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": total_graphs / (dev_ms * 1e-3), "unit": "graphs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "graphs_per_gpu": GRAPHS_PER_GPU, "nodes_per_gpu": int(batch.x.size(0)),
+                       "edges_per_gpu": int(batch.edge_index.size(1)), "parallelism": f"dp{world} by graph",
+                       "execution": "one CUDA graph per step (padded virtual-node layout)",
+                       "l2": "flushed between timed steps (256 MiB write)", "gemm": "cuBLAS fp32 (TF32 off)"},
+            "e2e": {"value": total_graphs / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": 12},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "losses_last_step": losses,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ghscn", choices=["ghscn", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = _env_int("RANK", 0), _env_int("LOCAL_RANK", 0), _env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if world != args.gpus and world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (see module docstring)")
+        run_product(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,7 @@ SZ = c_size_t
 SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_abi_version": (I32, []),
     "ghscn_error_string": (c_char_p, [I32]),
+    "ghscn_launch_count": (ctypes.c_uint64, []),
     "ghscn_csr_workspace_bytes": (SZ, [I64, I64, I32]),
     "ghscn_csr_build": (I32, [P, P, I64, I64, I32, P, P, P, P, SZ, P]),
     "ghscn_batch_to_ptr": (I32, [P, I64, I64, P, P]),

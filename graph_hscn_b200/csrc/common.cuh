@@ -10,13 +10,19 @@
     if (!(cond)) return GHSCN_E_INVALID; \
   } while (0)
 
-#define GHSCN_LAUNCH_CHECK()                   \
+// Checks the launch status and accounts `n` kernel launches in the library-wide counter
+// (ghscn_launch_count(); bench.py reports it as gpu_launches).
+#define GHSCN_LAUNCH_CHECK_N(n)                \
   do {                                         \
     cudaError_t e__ = cudaPeekAtLastError();   \
     if (e__ != cudaSuccess) return (int)e__;   \
+    ghscn::note_launches(n);                   \
   } while (0)
+#define GHSCN_LAUNCH_CHECK() GHSCN_LAUNCH_CHECK_N(1)
 
 namespace ghscn {
+
+void note_launches(int n);  // defined in csr.cu
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 constexpr unsigned kFullMask = 0xffffffffu;

@@ -6,9 +6,14 @@
 // (smem atomics) -> single-CTA exclusive scan of the [256 x tiles] matrix -> stable scatter
 // (warp match-any ranking, per-warp digit counters in shared memory).  Stability of every pass
 // makes the final order "by key, then by original edge id", i.e. torch.sort(stable=True).
+#include <atomic>
+
 #include "common.cuh"
 
 namespace ghscn {
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
@@ -58,10 +63,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(SortSource src
 // In-place exclusive scan of n ints by one CTA (n = 256 * tiles; tiles <= a few thousand).
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(int* __restrict__ data, int n) {
   __shared__ int warp_tot[32];
-  __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
   const int per_thread = ceil_div(n, 1024);
   const int beg = min(n, tid * per_thread), end = min(n, beg + per_thread);
   int sum = 0;
@@ -271,6 +273,8 @@ extern "C" {
 
 int ghscn_abi_version(void) { return 1; }
 
+unsigned long long ghscn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 const char* ghscn_error_string(int code) {
   switch (code) {
     case GHSCN_OK: return "ok";
@@ -342,7 +346,7 @@ int ghscn_csr_build(const int64_t* key, const int64_t* other, int64_t num_edges,
   }
   csr_finalize_kernel<<<ceil_div<int64_t>(m, 256), 256, 0, stream>>>(k_in, perm, other, num_edges, (int)num_rows,
                                                                      m, rowptr, col);
-  GHSCN_LAUNCH_CHECK();
+  GHSCN_LAUNCH_CHECK_N(3 * passes + 1);
   return GHSCN_OK;
 }
 
@@ -394,7 +398,7 @@ int ghscn_loop_weights(const int64_t* row, const int64_t* colidx, const float* e
                                                                             scratch_last);
   loop_weight_kernel<<<ceil_div<int64_t>(num_rows, 256), 256, 0, stream>>>(scratch_last, edge_weight,
                                                                            (int)num_rows, fill, loop_weight);
-  GHSCN_LAUNCH_CHECK();
+  GHSCN_LAUNCH_CHECK_N(num_edges > 0 ? 3 : 2);
   return GHSCN_OK;
 }
 

@@ -247,7 +247,7 @@ int ghscn_slot_map(const int32_t* perm, const int32_t* perm_t, int64_t nnz, int6
   cudaStream_t stream = as_stream(stream_);
   slot_pos_kernel<<<(unsigned)ceil_div<int64_t>(nnz, 256), 256, 0, stream>>>(perm, nnz, scratch_pos);
   slot_map_kernel<<<(unsigned)ceil_div<int64_t>(nnz, 256), 256, 0, stream>>>(perm_t, scratch_pos, nnz, map_t);
-  GHSCN_LAUNCH_CHECK();
+  GHSCN_LAUNCH_CHECK_N(2);
   return GHSCN_OK;
 }
 

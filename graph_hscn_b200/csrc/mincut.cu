@@ -389,7 +389,7 @@ int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x, int64_t l
         stats, as_ws);
   }
   mincut_reduce_losses_kernel<<<1, 256, 0, stream>>>(stats, (int)num_graphs, losses);
-  GHSCN_LAUNCH_CHECK();
+  GHSCN_LAUNCH_CHECK_N(2);
   return GHSCN_OK;
 }
 

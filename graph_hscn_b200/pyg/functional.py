@@ -38,7 +38,25 @@ def gcn_norm(edge_index: Tensor, edge_weight: Optional[Tensor] = None, num_nodes
     st = structure_cache().graph(edge_index, num_nodes, num_nodes, add_self_loops)
     w, _, _ = st.weights(edge_weight, normalize=True, improved=improved, need_transpose=False)
     d = st.by_dst
-    nnz = int(d.rowptr[-1].item())  # PyG's masked indexing syncs here as well
+    M = d.num_items
+    no_drop = (not add_self_loops) or bool(current_hints().get("no_self_loops"))
+    if not no_drop:
+        if _capturing():
+            raise RuntimeError("gcn_norm must know whether self loops exist; use structure_hints(no_self_loops=1)")
+        no_drop = int(d.rowptr[-1].item()) == M   # PyG's masked indexing syncs here as well
+    if no_drop:
+        # nothing was dropped: item ids are exactly the positions of PyG's output edge list
+        if add_self_loops:
+            loops = torch.arange(num_nodes, device=edge_index.device).unsqueeze(0).expand(2, num_nodes)
+            new_index = torch.cat([edge_index, loops], dim=1)
+        else:
+            new_index = edge_index
+        w_coo = torch.empty(M, dtype=torch.float32, device=edge_index.device)
+        w_coo[d.perm.long()] = w
+        if add_self_loops:   # layers called with (new_index, w_coo) reuse this CSR instead of sorting again
+            structure_cache().alias(new_index, st)
+        return new_index, w_coo
+    nnz = int(d.rowptr[-1].item())
     # back to PyG's COO order: slot s holds item perm[s]; items = kept edges (in order) then loops
     perm = d.perm[:nnz].long()
     rows = d.col[:nnz].long()           # `col` of the by-destination CSR is the source endpoint

@@ -110,19 +110,28 @@ class GraphStructure:
         self._weights: Dict[tuple, Tuple[Optional[Tensor], Optional[Tensor], Optional[Tensor]]] = {}
         self._slot_map_t: Optional[Tensor] = None
         self._keep: list = []
+        self._parent: Optional["GraphStructure"] = None   # set by StructureCache.alias
 
     @property
     def num_edges(self) -> int:
         return self.edge_index.size(1)
 
+    @staticmethod
+    def _as_plain(c: CSR) -> CSR:
+        return CSR(c.rowptr, c.col, c.perm, c.num_rows, c.num_items, c.num_items)
+
     @property
     def by_dst(self) -> CSR:
+        if self._by_dst is None and self._parent is not None:
+            self._by_dst = self._as_plain(self._parent.by_dst)
         if self._by_dst is None:
             self._by_dst = build_csr(self.edge_index[1], self.edge_index[0], self.num_dst, self.add_self_loops)
         return self._by_dst
 
     @property
     def by_src(self) -> CSR:
+        if self._by_src is None and self._parent is not None:
+            self._by_src = self._as_plain(self._parent.by_src)
         if self._by_src is None:
             self._by_src = build_csr(self.edge_index[0], self.edge_index[1], self.num_src, self.add_self_loops)
         return self._by_src
@@ -225,6 +234,16 @@ class StructureCache:
         else:
             self._graphs.move_to_end(key)
         return st
+
+    def alias(self, new_index: Tensor, parent: GraphStructure) -> GraphStructure:
+        """Register `new_index` (= parent's edges followed by parent's appended self loops, nothing dropped)
+        as a plain relation sharing parent's sorted arrays: item ids coincide, so no second sort is needed."""
+        n = parent.num_dst
+        view = GraphStructure(new_index, n, n, False)
+        view._parent = parent
+        key = self._key(new_index, n, n, False)
+        self._graphs[key] = view
+        return view
 
     def register_segments(self, index: Tensor, ptr: Tensor, num_segments: int, max_rows: int = 0) -> Segments:
         """Prime the cache from collate-time knowledge (Batch.to(device) does this): no sync needed later."""

@@ -1,0 +1,238 @@
+"""Graph-HSCN training step on one B200 (optionally CUDA-graph captured) and its data-parallel form.
+
+One step = one pass of the hot path over one `batch`/`ptr` mini-batch (BASELINE config #2):
+    1. SCN stage   -- gcn_norm(add_self_loops) -> GraphConv stack -> logits -> fused MinCUT losses,
+                      backward, AdamW step                    (train/train_clustering.py:34-50, batched)
+    2. assignment  -- SCN forward with the updated weights, softmax, first-max cluster id
+                      (train_clustering.py:57-69) and on-device virtual-node construction
+                      (loader/hetero_data.py:42-87)
+    3. HSCN stage  -- 3-relation HeteroConv stack, mean readout, 2 linears, loss, backward, AdamW step
+                      (train/train.py:73-95)
+Data parallelism: graphs are independent, so ranks take disjoint contiguous graph
+ranges and exchange nothing in forward/backward; one NCCL all-reduce of a single flat fp32 gradient
+buffer per model per step averages the gradients (the reference has no distributed code).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+from torch import Tensor
+from torch.nn.parameter import UninitializedParameter
+
+from . import hetero, models, ops
+from .data import Batch
+from .structure import capture_scope, structure_cache, structure_hints
+
+
+# ---------------------------------------------------------------------------------------------
+# data-parallel plumbing
+# ---------------------------------------------------------------------------------------------
+def shard_range(num_graphs: int, rank: int, world: int, weights: Optional[Sequence[int]] = None) -> Tuple[int, int]:
+    """Contiguous graph range [lo, hi) of `rank`.  With `weights` (nodes or edges per graph) the cut points
+    balance the summed weight instead of the graph count (SURVEY 8e "balance by sum n_g")."""
+    if weights is None:
+        base, rem = divmod(num_graphs, world)
+        lo = rank * base + min(rank, rem)
+        return lo, lo + base + (1 if rank < rem else 0)
+    csum = torch.as_tensor(list(weights), dtype=torch.float64).cumsum(0)
+    total = float(csum[-1]) if len(csum) else 0.0
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(torch.searchsorted(csum, torch.tensor(total * r / world, dtype=torch.float64))))
+    cuts.append(num_graphs)
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return cuts[rank], cuts[rank + 1]
+
+
+class FlatGradients:
+    """All gradients of a module as views into ONE flat fp32 buffer: zeroing is one memset and the
+    data-parallel exchange is one all-reduce (K8).  Parameters that never receive a gradient
+    (the HSCN l->v / v->v branches are dead w.r.t. the loss) are left out on every rank."""
+
+    def __init__(self, module: nn.Module, live: Optional[Sequence[str]] = None):
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        if live is not None:
+            keep = set(live)
+            named = [(n, p) for n, p in named if n in keep]
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce_mean(self, world: Optional[int] = None, group=None) -> None:
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        world = world or dist.get_world_size(group)
+        if world == 1:
+            return
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        self.flat.mul_(1.0 / world)
+
+
+def live_parameter_names(module: nn.Module, loss: Tensor) -> List[str]:
+    """Names of the parameters reachable from `loss` (consistent on all ranks for the same model)."""
+    named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+    grads = torch.autograd.grad(loss, [p for _, p in named], allow_unused=True, retain_graph=False)
+    return [n for (n, _), g in zip(named, grads) if g is not None]
+
+
+# ---------------------------------------------------------------------------------------------
+# the step
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class StepConfig:
+    num_features: int = 9
+    num_classes: int = 10
+    num_clusters: int = 10
+    scn_units: Tuple[int, ...] = (16,)
+    scn_act: str = "elu"
+    hidden: int = 300
+    num_layers: int = 3
+    activation: str = "relu"
+    loss_fn: str = "cross_entropy"
+    lr: float = 1e-3
+    weight_decay: float = 5e-4
+
+
+class GraphHSCNStep:
+    """Owns the two models, their optimizers and static device buffers for one batch shape."""
+
+    def __init__(self, cfg: StepConfig, host_batch: Batch, device: torch.device, op_ns: Optional[SimpleNamespace] = None,
+                 seed: int = 0, padded: bool = True):
+        from . import pyg
+        self.cfg, self.device, self.padded = cfg, device, padded
+        self.ns = op_ns or pyg.namespace()
+        self.B = int(host_batch.num_graphs)
+        counts = host_batch.ptr[1:] - host_batch.ptr[:-1]
+        self.hints = dict(num_graphs=self.B, batch_sorted=1, max_nodes_per_graph=int(counts.max()),
+                          no_self_loops=int(not bool((host_batch.edge_index[0] == host_batch.edge_index[1]).any())))
+        # pinned host staging + static device buffers (inputs are re-copied every step in the e2e path)
+        self.host = {k: host_batch[k].contiguous().pin_memory() if device.type == "cuda" else host_batch[k]
+                     for k in ("x", "edge_index", "batch", "y")}
+        self.dev = {k: torch.empty_like(v, device=device) for k, v in self.host.items()}
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        torch.manual_seed(seed)
+        self.scn = models.SCN(list(cfg.scn_units), cfg.scn_act, cfg.num_features, cfg.num_clusters, ops=self.ns).to(device)
+        self.hscn = models.HSCN("GAT", "GCN", "GCN", models.ACTIVATIONS[cfg.activation], cfg.num_features, cfg.hidden,
+                                cfg.num_classes, cfg.num_layers, ops=self.ns).to(device)
+        self.losses = torch.zeros(3, dtype=torch.float32, device=device)     # mincut, ortho, task
+        self.losses_host = torch.zeros(3, dtype=torch.float32).pin_memory() if device.type == "cuda" else torch.zeros(3)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.upload()
+        self._prepare()
+
+    # -- host <-> device ---------------------------------------------------------------------------
+    def upload(self) -> None:
+        for k, v in self.host.items():
+            self.dev[k].copy_(v, non_blocking=True)
+
+    def download(self) -> Tensor:
+        self.losses_host.copy_(self.losses, non_blocking=True)
+        return self.losses_host
+
+    # -- one-time preparation: materialise lazy parameters, find live parameters, build optimizers ------
+    def _forward_scn(self, x_f: Tensor):
+        ei, ew = self.ns.gcn_norm(self.dev["edge_index"], None, x_f.size(0), add_self_loops=True)
+        return (ei, ew) + tuple(self.scn.forward_batched(x_f, ei, ew, self.dev["batch"]))
+
+    def _assign(self, x_f: Tensor, ei: Tensor, ew: Tensor):
+        with torch.no_grad():
+            s = self.scn.mlp(self.scn.mp(x_f, ei, ew))
+            clusters = hetero.assign_clusters(torch.softmax(s, dim=-1))
+        return hetero.build_hetero_batch(self.dev["x"], self.dev["edge_index"], self.dev["batch"], clusters,
+                                         self.cfg.num_clusters, y=self.dev["y"], padded=self.padded,
+                                         num_graphs=self.B)
+
+    def _prepare(self) -> None:
+        cfg = self.cfg
+        with structure_hints(**self.hints):
+            x_f = self._cast(self.dev["x"])
+            ei, ew, _, mc, ol = self._forward_scn(x_f)
+            scn_live = live_parameter_names(self.scn, mc + ol)
+            hb = self._assign(x_f, ei, ew)
+            pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)            # materialises lazy weights
+            loss, _ = models.criterion(cfg.loss_fn, pred, hb["local"].y)
+            hscn_live = live_parameter_names(self.hscn, loss)
+        self.scn_grads = FlatGradients(self.scn, scn_live)
+        self.hscn_grads = FlatGradients(self.hscn, hscn_live)
+        kw = dict(lr=cfg.lr, weight_decay=cfg.weight_decay)
+        if self.device.type == "cuda":
+            kw.update(fused=True, capturable=True)
+        self.scn_opt = torch.optim.AdamW(self.scn_grads.params, **kw)
+        self.hscn_opt = torch.optim.AdamW(self.hscn_grads.params, **kw)
+        structure_cache().clear()
+
+    def _cast(self, x: Tensor) -> Tensor:
+        if x.dtype == torch.int64 and x.is_cuda:
+            return ops.cast_i64_f32(x)
+        return x.float()
+
+    # -- the three stages; `sync_grads` hooks the data-parallel all-reduce in between ------------------
+    def stage_scn_backward(self):
+        self.scn_grads.zero()
+        x_f = self._cast(self.dev["x"])
+        ei, ew, _, mc, ol = self._forward_scn(x_f)
+        (mc + ol).backward()
+        self.losses[0:1].copy_(mc.detach().view(1))
+        self.losses[1:2].copy_(ol.detach().view(1))
+        return x_f, ei, ew
+
+    def stage_assign_and_hscn_backward(self, x_f, ei, ew):
+        self.scn_opt.step()
+        hb = self._assign(x_f, ei, ew)
+        self.hscn_grads.zero()
+        pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)
+        loss, _ = models.criterion(self.cfg.loss_fn, pred, hb["local"].y)
+        loss.backward()
+        self.losses[2:3].copy_(loss.detach().view(1))
+
+    def stage_hscn_update(self):
+        self.hscn_opt.step()
+
+    def run_eager(self, world: int = 1) -> None:
+        with structure_hints(**self.hints):
+            structure_cache().clear()
+            st = self.stage_scn_backward()
+            self.scn_grads.all_reduce_mean(world)
+            self.stage_assign_and_hscn_backward(*st)
+            self.hscn_grads.all_reduce_mean(world)
+            self.stage_hscn_update()
+
+    # -- CUDA graph capture: static shapes (padded virtual layout), no host sync inside -------------------
+    def capture(self, world: int = 1, warmup: int = 3) -> None:
+        assert self.device.type == "cuda" and self.padded, "capture needs CUDA and the padded virtual layout"
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.run_eager(world)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with capture_scope(), structure_hints(**self.hints):
+            with torch.cuda.graph(self.graph):
+                st = self.stage_scn_backward()
+                self.scn_grads.all_reduce_mean(world)
+                self.stage_assign_and_hscn_backward(*st)
+                self.hscn_grads.all_reduce_mean(world)
+                self.stage_hscn_update()
+
+    def run(self, world: int = 1) -> None:
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run_eager(world)

@@ -44,6 +44,8 @@ enum {
 
 GHSCN_API int ghscn_abi_version(void);
 GHSCN_API const char* ghscn_error_string(int code);
+/* number of CUDA kernels this library has launched in this process (monotonic; bench accounting) */
+GHSCN_API unsigned long long ghscn_launch_count(void);
 
 /* ---- K1: CSR construction (stable integer radix sort + boundary scan) ------------------------
  * Replaces the implicit COO handling of PyG MessagePassing and `add_remaining_self_loops`
