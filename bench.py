@@ -62,7 +62,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -78,7 +78,7 @@ class ClockSampler(threading.Thread):
         if not self.ok:
             return
         nv = self.nv
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 try:
@@ -93,7 +93,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def finish(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         if self.is_alive():
             self.join(timeout=2)
         if not self.samples:

@@ -1,0 +1,235 @@
+"""CPU tests (no GPU): C-ABI surface, oracle self-checks, collate convention, synthetic shapes, DP host logic."""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import assert_close, random_edge_index
+
+
+# ----------------------------------------------------------------------------------------- C ABI
+def test_header_and_binding_agree(built_lib):
+    from graph_hscn_b200 import _abi_check
+    _abi_check.check()
+    assert len(_abi_check.header_functions()) >= 25
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from graph_hscn_b200 import _abi_check
+    out = subprocess.run(["nm", "-D", "--defined-only", str(built_lib)], capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    missing = sorted(set(_abi_check.header_functions()) - exported)
+    assert not missing, f"declared in include/ghscn.h but not exported: {missing}"
+    leaked = sorted(s for s in exported if " T " in s)
+    assert not leaked
+
+
+def test_library_loads_and_validates_arguments_without_a_gpu(built_lib):
+    from graph_hscn_b200._lib import GhscnError, lib
+    L = lib()
+    assert L.query("ghscn_abi_version") == 1
+    assert L.error_string(0) == "ok" and "invalid" in L.error_string(-1)
+    assert L.query("ghscn_csr_workspace_bytes", 1000, 100, 1) > 3 * 1100 * 4
+    # argument errors are reported before anything is launched (negative sizes / null pointers)
+    with pytest.raises(GhscnError):
+        L.call("ghscn_spmm", None, None, None, None, 4, None, 4, None, -1, 4, 0, None)
+    with pytest.raises(GhscnError):
+        L.call("ghscn_csr_build", None, None, 10, 4, 0, None, None, None, None, 0, None)
+    with pytest.raises(GhscnError):
+        L.call("ghscn_mincut_fwd", None, 0, None, 0, None, None, None, None, 1.0, 1, 1, 200, 1, 1,
+               None, None, None, None, None, None, None, None, 0, None)
+
+
+def test_built_for_sm100a(built_lib):
+    out = subprocess.run(["cuobjdump", "-lelf", str(built_lib)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_product_path_refuses_cpu_tensors(built_lib):
+    from graph_hscn_b200 import pyg
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        pyg.scatter_mean(torch.randn(4, 3), torch.tensor([0, 0, 1, 1]), dim=0)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        pyg.gcn_norm(torch.tensor([[0, 1], [1, 0]]))
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(__file__))
+    pkg = os.path.join(root, "graph_hscn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+# ------------------------------------------------------------------------------------ oracle checks
+def _ops():
+    from oracle import ops
+    return ops
+
+
+def test_oracle_gcn_norm_self_loop_rules():
+    ops = _ops()
+    ei = torch.tensor([[0, 1, 1, 2, 2], [1, 0, 1, 2, 0]])
+    w = torch.tensor([1.0, 2.0, 5.0, 7.0, 3.0])
+    ei2, w2 = ops.add_remaining_self_loops(ei, w, 1.0, 3)
+    assert ei2.tolist() == [[0, 1, 2, 0, 1, 2], [1, 0, 0, 0, 1, 2]]
+    assert w2.tolist() == [1.0, 2.0, 3.0, 1.0, 5.0, 7.0]       # existing loops keep their weight
+    _, wn = ops.gcn_norm(ei, None, 3, add_self_loops=True)
+    deg = torch.tensor([3.0, 2.0, 1.0])                         # in-degree incl. the appended loop
+    want = deg.pow(-0.5)[ei2[0]] * deg.pow(-0.5)[ei2[1]]
+    assert torch.allclose(wn, want)
+
+
+def test_oracle_mincut_dense_equals_sparse_identities():
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    n, K = 40, 6
+    ei = random_edge_index(n, n, 150, g)
+    s = torch.randn(n, K, generator=g, dtype=torch.float64)
+    x = torch.randn(n, 8, generator=g, dtype=torch.float64)
+    adj = ops.to_dense_adj(ei, max_num_nodes=n).double()
+    out, out_adj, mc, ol = ops.dense_mincut_pool(x, adj, s)
+    S = torch.softmax(s, -1)
+    num, den, AS = ops.mincut_sparse_terms(ei, S)
+    assert torch.allclose(mc, -num / den)
+    assert torch.allclose(AS, adj[0] @ S)
+    assert -1.0 - 1e-9 <= float(mc) <= 1e-9 and -1e-9 <= float(ol) <= 2.0 + 1e-9
+    assert torch.allclose(out[0], S.t() @ x)
+    assert torch.allclose(torch.diagonal(out_adj[0]), torch.zeros(K, dtype=torch.float64))
+
+
+def test_oracle_mincut_analytic_backward_matches_autograd():
+    """SURVEY A.7 (the formulas the CUDA backward implements), checked in fp64 on the oracle."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    n, K = 30, 5
+    ei = random_edge_index(n, n, 100, g)
+    z = torch.randn(n, K, generator=g, dtype=torch.float64, requires_grad=True)
+    adj = ops.to_dense_adj(ei, max_num_nodes=n).double()
+    _, _, mc, ol = ops.dense_mincut_pool(torch.zeros(n, 1, dtype=torch.float64), adj, z)
+    (mc + ol).backward()
+    A = adj[0]
+    S = torch.softmax(z.detach(), -1)
+    d = A.sum(-1)
+    num, den = (S * (A @ S)).sum(), (d[:, None] * S * S).sum()
+    dS = -(((A @ S) + (A.t() @ S)) * den - num * 2 * d[:, None] * S) / den ** 2
+    SS = S.t() @ S
+    Fn = SS.norm()
+    M = SS / Fn
+    R = M - torch.eye(K, dtype=torch.float64) / math.sqrt(K)
+    G = R / R.norm()
+    Gp = (G - M * (G * M).sum()) / Fn
+    dS = dS + S @ (Gp + Gp.t())
+    dz = S * (dS - (dS * S).sum(-1, keepdim=True))
+    assert torch.allclose(dz, z.grad, rtol=1e-9, atol=1e-12)
+
+
+def test_oracle_gcnconv_permutation_equivariance_and_gat_softmax():
+    from oracle import nn as onn
+    ops = _ops()
+    g = torch.Generator().manual_seed(2)
+    n = 50
+    ei = random_edge_index(n, n, 200, g)
+    x = torch.randn(n, 7, generator=g)
+    torch.manual_seed(0)
+    conv = onn.GCNConv(7, 5)
+    perm = torch.randperm(n, generator=g)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n)
+    y = conv(x, ei)
+    y_p = conv(x[perm], inv[ei])
+    assert torch.allclose(y[perm], y_p, atol=1e-5)
+    a = ops.segment_softmax(torch.randn(200, generator=g), ei[1], n)
+    sums = ops.scatter_sum(a, ei[1], 0, None, n)
+    has = torch.bincount(ei[1], minlength=n) > 0
+    assert torch.allclose(sums[has], torch.ones(int(has.sum())), atol=1e-5)
+
+
+def test_oracle_scatter_mean_and_pool():
+    ops = _ops()
+    x = torch.tensor([[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]])
+    idx = torch.tensor([0, 0, 2])
+    out = ops.scatter_mean(x, idx, dim=0)
+    assert out.tolist() == [[2.0, 3.0], [0.0, 0.0], [5.0, 6.0]]
+    assert torch.equal(ops.global_mean_pool(x, idx), out)
+
+
+# --------------------------------------------------------------------------------- data / collate
+def test_collate_batch_ptr_convention():
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.data import Batch
+    graphs = synthetic.peptides_graphs(5, seed=9)
+    b = Batch.from_data_list(graphs)
+    n = [g.num_nodes for g in graphs]
+    assert b.ptr.tolist() == np.concatenate([[0], np.cumsum(n)]).tolist()
+    assert bool((b.batch[1:] >= b.batch[:-1]).all()) and b.num_graphs == 5
+    off = 0
+    for gi, g in enumerate(graphs):
+        e = g.edge_index.size(1)
+        assert torch.equal(b.edge_index[:, off:off + e], g.edge_index + int(b.ptr[gi]))
+        off += e
+    assert b.y.shape == (5, 10)
+    back = b.to_data_list()
+    assert all(torch.equal(a.edge_index, c.edge_index) and torch.equal(a.x, c.x) for a, c in zip(back, graphs))
+    assert graphs[0].edge_weight is None          # PyG: missing standard attributes read as None
+
+
+def test_hetero_collate_offsets():
+    from graph_hscn_b200.data import Batch, HeteroData
+    hl = []
+    for n, u in [(4, 2), (3, 1)]:
+        h = HeteroData()
+        h["local"].x = torch.zeros(n, 2)
+        h["local"].y = torch.zeros(1, 3)
+        h["virtual"].x = torch.zeros(u, 2)
+        h["local", "to", "local"].edge_index = torch.tensor([[0, 1], [1, 0]])
+        h["virtual", "to", "virtual"].edge_index = torch.tensor([[0], [0]])
+        h["local", "to", "virtual"].edge_index = torch.stack([torch.arange(n), torch.zeros(n, dtype=torch.long)])
+        hl.append(h)
+    b = Batch.from_data_list(hl)
+    assert list(b.edge_index_dict) == [("local", "to", "local"), ("virtual", "to", "virtual"),
+                                       ("local", "to", "virtual")]
+    assert b["local", "to", "local"].edge_index.tolist() == [[0, 1, 4, 5], [1, 0, 5, 4]]
+    assert b["virtual", "to", "virtual"].edge_index.tolist() == [[0, 2], [0, 2]]
+    lv = b["local", "to", "virtual"].edge_index
+    assert lv[0].tolist() == list(range(7)) and lv[1].tolist() == [0, 0, 0, 0, 2, 2, 2]
+    assert b["local"].batch.tolist() == [0, 0, 0, 0, 1, 1, 1] and b["virtual"].batch.tolist() == [0, 0, 1]
+    assert b["local"].y.shape == (2, 3)
+
+
+def test_dataloader_and_synthetic_shapes():
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.data import DataLoader
+    graphs = synthetic.peptides_graphs(256, seed=1234)
+    n = np.array([g.num_nodes for g in graphs])
+    e = np.array([g.num_edges for g in graphs])
+    assert 135 < n.mean() < 168 and n.min() >= 8 and n.max() <= 444
+    assert 1.95 < (e / n).mean() < 2.12                     # ~307 directed edges per ~151 nodes
+    g0 = graphs[0]
+    assert g0.x.dtype == torch.int64 and g0.x.shape[1] == 9 and int(g0.x[:, 0].max()) < 119
+    assert torch.equal(g0.edge_index[:, 0::2], g0.edge_index[:, 1::2].flip(0))   # (i,j),(j,i) adjacent
+    deg = torch.bincount(g0.edge_index[0], minlength=g0.num_nodes)
+    assert int(deg.max()) <= 6
+    loader = DataLoader(graphs, 32, shuffle=False, num_workers=0, persistent_workers=False)
+    b = next(iter(loader))
+    assert b.num_graphs == 32 and len(loader) == 8
+    v = synthetic.vocsp_graphs(8)
+    dv = np.mean([g.num_edges / g.num_nodes for g in v])
+    assert 4.5 < dv < 6.5 and v[0].x.shape[1] == 14 and 395 <= v[0].num_nodes <= 500
+
+
+def test_shard_range_covers_all_graphs():
+    from graph_hscn_b200.train import shard_range
+    for B, W in [(128, 8), (10, 4), (3, 8), (1024, 3)]:
+        r = [shard_range(B, k, W) for k in range(W)]
+        assert r[0][0] == 0 and r[-1][1] == B and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
+    w = [1] * 50 + [9] * 50
+    r = [shard_range(100, k, 2, w) for k in range(2)]
+    assert r[0][1] > 50 and r[0][1] == r[1][0] and r[1][1] == 100
