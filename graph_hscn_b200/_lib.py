@@ -27,6 +27,10 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_launch_count": (ctypes.c_uint64, []),
     "ghscn_csr_workspace_bytes": (SZ, [I64, I64, I32]),
     "ghscn_csr_build": (I32, [P, P, I64, I64, I32, P, P, P, P, SZ, P]),
+    "ghscn_csr_add_loops": (I32, [P, P, P, I64, I64, P, P, P, P]),
+    "ghscn_colsum_workspace_bytes": (SZ, [I64, I64]),
+    "ghscn_colsum": (I32, [P, I64, I64, I64, P, P, SZ, P]),
+    "ghscn_virtual_csr": (I32, [P, P, P, P, P, I64, I64, I32] + [P] * 12 + [P]),
     "ghscn_batch_to_ptr": (I32, [P, I64, I64, P, P]),
     "ghscn_gcn_deg_inv_sqrt": (I32, [P, P, P, P, I64, I64, P, P]),
     "ghscn_edge_weights": (I32, [P, P, P, P, P, P, I64, I64, I32, I32, P, P]),

@@ -168,6 +168,72 @@ __global__ void virtual_compact_kernel(const float* __restrict__ virt_x_padded,
     for (int j = threadIdx.x; j < U; j += blockDim.x) virt_batch[off + j] = g;
 }
 
+// Both orientations of the l->v and v->v relations straight from the cluster assignment: no sort.
+//   l->v  by source: node i owns exactly slot i;  by destination: members of each virtual node in node order
+//   v->v  edge p = (a, b), a-major, b = 0..U-1-a: by source slots are consecutive in p; by destination row b
+//         holds sources a = 0..U-1-b in that order (closed-form offsets b*U - b(b-1)/2)
+__global__ void __launch_bounds__(256) virtual_csr_kernel(
+    const int* __restrict__ cluster_remapped, const int* __restrict__ ptr, const int* __restrict__ num_virtual,
+    const int* __restrict__ virt_offset, const int* __restrict__ vv_offset, int B, int K, int padded,
+    int* __restrict__ lvd_rowptr, int* __restrict__ lvd_col, int* __restrict__ lvd_perm,
+    int* __restrict__ lvs_rowptr, int* __restrict__ lvs_col, int* __restrict__ lvs_perm,
+    int* __restrict__ vvd_rowptr, int* __restrict__ vvd_col, int* __restrict__ vvd_perm,
+    int* __restrict__ vvs_rowptr, int* __restrict__ vvs_col, int* __restrict__ vvs_perm) {
+  __shared__ int cnt[kMaxK];
+  __shared__ int start[kMaxK + 1];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const int base = ptr[g], n = ptr[g + 1] - base;
+  const int U = num_virtual[g];
+  const int voff = padded ? g * K : virt_offset[g];
+  const int rows = padded ? K : U;
+  const int eslot = vv_offset[g];                                  // compact slot offset in both layouts
+  const int eid0 = padded ? g * (K * (K + 1) / 2) : vv_offset[g];  // id of the graph's first v->v edge
+  for (int k = tid; k < K; k += blockDim.x) cnt[k] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) atomicAdd(&cnt[cluster_remapped[base + i]], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = 0; k < K; ++k) { start[k] = run; run += cnt[k]; }
+    start[K] = run;
+  }
+  __syncthreads();
+  for (int j = tid; j < rows; j += blockDim.x) {
+    lvd_rowptr[voff + j] = base + start[j];
+    const int jj = min(j, U);
+    vvd_rowptr[voff + j] = eslot + jj * U - jj * (jj - 1) / 2;
+    vvs_rowptr[voff + j] = eslot + jj * U - jj * (jj - 1) / 2;
+  }
+  if (g == B - 1 && tid == 0) {
+    const int vrows = padded ? B * K : virt_offset[B];
+    lvd_rowptr[vrows] = ptr[B];
+    vvd_rowptr[vrows] = vv_offset[B];
+    vvs_rowptr[vrows] = vv_offset[B];
+    lvs_rowptr[ptr[B]] = ptr[B];
+  }
+  // l->v by source (one slot per node) and by destination (stable: node order inside each cluster)
+  for (int i = tid; i < n; i += blockDim.x) {
+    lvs_rowptr[base + i] = base + i;
+    lvs_col[base + i] = voff + cluster_remapped[base + i];
+    lvs_perm[base + i] = base + i;
+  }
+  for (int j = tid; j < U; j += blockDim.x) {
+    int o = base + start[j];
+    for (int i = 0; i < n; ++i)
+      if (cluster_remapped[base + i] == j) { lvd_col[o] = base + i; lvd_perm[o] = base + i; ++o; }
+  }
+  const int ne = U * (U + 1) / 2;
+  for (int p = tid; p < ne; p += blockDim.x) {
+    int a = 0, b = p;
+    while (b >= U - a) { b -= U - a; ++a; }
+    vvs_col[eslot + p] = voff + b;
+    vvs_perm[eslot + p] = eid0 + p;
+    const int o = eslot + b * U - b * (b - 1) / 2 + a;
+    vvd_col[o] = voff + a;
+    vvd_perm[o] = eid0 + p;
+  }
+}
+
 }  // namespace ghscn
 
 using namespace ghscn;
@@ -225,6 +291,26 @@ int ghscn_virtual_edges(const int32_t* cluster_remapped, const int32_t* ptr, con
   virtual_edges_kernel<<<(unsigned)num_graphs, 256, 0, as_stream(stream)>>>(
       cluster_remapped, ptr, num_virtual, virt_offset, vv_offset, (int)num_clusters, num_nodes, lv_edge_index,
       vv_edge_index, vv_cap);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+int ghscn_virtual_csr(const int32_t* cluster_remapped, const int32_t* ptr, const int32_t* num_virtual,
+                      const int32_t* virt_offset, const int32_t* vv_offset, int64_t num_graphs,
+                      int64_t num_clusters, int32_t padded, int32_t* lvd_rowptr, int32_t* lvd_col,
+                      int32_t* lvd_perm, int32_t* lvs_rowptr, int32_t* lvs_col, int32_t* lvs_perm,
+                      int32_t* vvd_rowptr, int32_t* vvd_col, int32_t* vvd_perm, int32_t* vvs_rowptr,
+                      int32_t* vvs_col, int32_t* vvs_perm, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_graphs >= 0 && num_clusters > 0);
+  if (num_clusters > kMaxK) return GHSCN_E_UNSUPPORTED;
+  if (num_graphs == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(cluster_remapped && ptr && num_virtual && vv_offset && (padded || virt_offset));
+  GHSCN_REQUIRE(lvd_rowptr && lvd_col && lvd_perm && lvs_rowptr && lvs_col && lvs_perm);
+  GHSCN_REQUIRE(vvd_rowptr && vvd_col && vvd_perm && vvs_rowptr && vvs_col && vvs_perm);
+  virtual_csr_kernel<<<(unsigned)num_graphs, 256, 0, as_stream(stream)>>>(
+      cluster_remapped, ptr, num_virtual, virt_offset, vv_offset, (int)num_graphs, (int)num_clusters, padded,
+      lvd_rowptr, lvd_col, lvd_perm, lvs_rowptr, lvs_col, lvs_perm, vvd_rowptr, vvd_col, vvd_perm, vvs_rowptr,
+      vvs_col, vvs_perm);
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }

@@ -265,6 +265,23 @@ __global__ void cast_i64_f32_kernel(const int64_t* __restrict__ in, int64_t n, f
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// CSR of (edges + one appended loop per row) from the plain CSR of the same edges; valid when the edge list
+// holds no self loop (nothing to drop).  The loop (r,r) has item id E + r and is the last slot of row r,
+// exactly where the stable sort of PyG's appended edge list puts it.
+__global__ void csr_add_loops_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                     const int* __restrict__ perm, int num_rows, int num_edges,
+                                     int* __restrict__ rowptr2, int* __restrict__ col2, int* __restrict__ perm2) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > num_rows) return;
+  if (r == num_rows) { rowptr2[r] = rowptr[r] + r; return; }
+  const int beg = rowptr[r], end = rowptr[r + 1];
+  int o = beg + r;
+  rowptr2[r] = o;
+  for (int s = beg; s < end; ++s, ++o) { col2[o] = col[s]; perm2[o] = perm[s]; }
+  col2[o] = r;
+  perm2[o] = num_edges + r;
+}
+
 }  // namespace ghscn
 
 using namespace ghscn;
@@ -399,6 +416,16 @@ int ghscn_loop_weights(const int64_t* row, const int64_t* colidx, const float* e
   loop_weight_kernel<<<ceil_div<int64_t>(num_rows, 256), 256, 0, stream>>>(scratch_last, edge_weight,
                                                                            (int)num_rows, fill, loop_weight);
   GHSCN_LAUNCH_CHECK_N(num_edges > 0 ? 3 : 2);
+  return GHSCN_OK;
+}
+
+int ghscn_csr_add_loops(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t num_rows,
+                        int64_t num_edges, int32_t* rowptr2, int32_t* col2, int32_t* perm2, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_edges >= 0 && num_rows + num_edges < ((int64_t)1 << 31));
+  GHSCN_REQUIRE(rowptr && rowptr2 && (num_rows + num_edges == 0 || (col2 && perm2)) && (num_edges == 0 || (col && perm)));
+  csr_add_loops_kernel<<<(unsigned)ceil_div<int64_t>(num_rows + 1, 256), 256, 0, as_stream(stream)>>>(
+      rowptr, col, perm, (int)num_rows, (int)num_edges, rowptr2, col2, perm2);
+  GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }
 

@@ -3,9 +3,8 @@
 // (model/hscn.py:85-87,118-125).
 //
 // HBM-bound: reads hs [N,H] once (gathered by cluster membership), 8N score terms, writes [V,H].
-// One warp owns one destination (virtual) row: lanes stride the row's slots for the score /
-// softmax passes and own 128-bit column chunks for the weighted feature sum, which runs in slot
-// (= edge) order like the CPU scatter_add_.
+// Forward = one warp per destination (virtual) row for the segment softmax of the scores, then the
+// generic K2 SpMM with w = alpha for the weighted feature sum (slot = edge order, like CPU scatter_add_).
 #include <math.h>
 
 #include "common.cuh"
@@ -27,26 +26,31 @@ __global__ void __launch_bounds__(256) row_dot_kernel(const float* __restrict__ 
 
 __device__ __forceinline__ float leaky(float z, float slope) { return z > 0.f ? z : z * slope; }
 
-template <int VEC, int ITERS>
-__global__ void __launch_bounds__(256) gat_pool_fwd_kernel(const int* __restrict__ rowptr,
-                                                           const int* __restrict__ col,
-                                                           const float* __restrict__ hs, int64_t ldhs,
-                                                           const float* __restrict__ a_src,
-                                                           const float* __restrict__ a_dst,
-                                                           const float* __restrict__ bias, float slope,
-                                                           int num_rows, int num_feat, float* __restrict__ alpha,
-                                                           float* __restrict__ out, int64_t ldout) {
+// Attention coefficients of one destination row per warp: alpha[s] = softmax_s(leaky_relu(a_src[col[s]] + a_dst[row])).
+// The weighted feature sum itself is the generic K2 SpMM with w = alpha (slot order, unfused mul/add).
+__global__ void __launch_bounds__(256) gat_scores_kernel(const int* __restrict__ rowptr,
+                                                         const int* __restrict__ col,
+                                                         const float* __restrict__ a_src,
+                                                         const float* __restrict__ a_dst, float slope,
+                                                         int num_rows, float* __restrict__ alpha) {
   const int lane = threadIdx.x & 31;
   const int row = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
   if (row >= num_rows) return;
   const int beg = rowptr[row], end = rowptr[row + 1];
   const float ad = a_dst ? a_dst[row] : 0.f;
-
-  // pass 1: row max of the leaky-relu scores
+  if (end - beg <= 32) {  // common case: the whole row fits one lane each, scores stay in registers
+    const int s = beg + lane;
+    const bool on = s < end;
+    const float e = on ? leaky(a_src[col[s]] + ad, slope) : -INFINITY;
+    const float m = warp_max(e);
+    const float p = on ? expf(e - m) : 0.f;
+    const float sum = warp_sum(p) + 1e-16f;   // PyG softmax: + 1e-16 in the denominator
+    if (on) alpha[s] = __fdiv_rn(p, sum);
+    return;
+  }
   float m = -INFINITY;
   for (int s = beg + lane; s < end; s += 32) m = fmaxf(m, leaky(a_src[col[s]] + ad, slope));
   m = warp_max(m);
-  // pass 2: exp and denominator (+1e-16 as PyG's softmax)
   float sum = 0.f;
   for (int s = beg + lane; s < end; s += 32) {
     const float p = expf(leaky(a_src[col[s]] + ad, slope) - m);
@@ -55,47 +59,6 @@ __global__ void __launch_bounds__(256) gat_pool_fwd_kernel(const int* __restrict
   }
   sum = warp_sum(sum) + 1e-16f;
   for (int s = beg + lane; s < end; s += 32) alpha[s] = __fdiv_rn(alpha[s], sum);
-  __syncwarp();
-
-  // pass 3: out[row,:] = sum_s alpha[s] * hs[col[s],:] (+ bias), slot order, unfused mul/add
-  for (int f0 = 0; f0 < num_feat; f0 += 32 * VEC * ITERS) {
-    float acc[ITERS][VEC];
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[it][v] = 0.f;
-    for (int s = beg; s < end; ++s) {
-      const float a = alpha[s];
-      const float* hr = hs + (int64_t)col[s] * ldhs;
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int f = f0 + (it * 32 + lane) * VEC;
-        if (f < num_feat) {
-          if (VEC == 4) {
-            const float4 q = ldg_f4(hr + f);
-            acc[it][0] = mul_then_add(acc[it][0], a, q.x);
-            acc[it][1 % VEC] = mul_then_add(acc[it][1 % VEC], a, q.y);
-            acc[it][2 % VEC] = mul_then_add(acc[it][2 % VEC], a, q.z);
-            acc[it][3 % VEC] = mul_then_add(acc[it][3 % VEC], a, q.w);
-          } else {
-            acc[it][0] = mul_then_add(acc[it][0], a, __ldg(hr + f));
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const int f = f0 + (it * 32 + lane) * VEC;
-      if (f < num_feat) {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          float r = acc[it][v];
-          if (bias) r = __fadd_rn(r, bias[f + v]);
-          out[(int64_t)row * ldout + f + v] = r;
-        }
-      }
-    }
-  }
 }
 
 // Backward, destination side.  Per row: dalpha_s = <dout[row], hs[col_s]>; softmax + leaky-relu
@@ -198,18 +161,10 @@ int ghscn_gat_pool_fwd(const int32_t* rowptr, const int32_t* col, const float* h
   GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && num_rows < ((int64_t)1 << 31));
   if (num_rows == 0) return GHSCN_OK;
   GHSCN_REQUIRE(rowptr && col && hs && a_src && alpha && out && ldhs >= num_feat && ldout >= num_feat);
-  const unsigned blocks = (unsigned)ceil_div<int64_t>(num_rows, 8);
-  const bool vec4 = num_feat % 4 == 0 && ldhs % 4 == 0 && (reinterpret_cast<uintptr_t>(hs) % 16 == 0);
-  if (vec4)
-    gat_pool_fwd_kernel<4, 3><<<blocks, 256, 0, as_stream(stream)>>>(rowptr, col, hs, ldhs, a_src, a_dst, bias,
-                                                                      negative_slope, (int)num_rows,
-                                                                      (int)num_feat, alpha, out, ldout);
-  else
-    gat_pool_fwd_kernel<1, 4><<<blocks, 256, 0, as_stream(stream)>>>(rowptr, col, hs, ldhs, a_src, a_dst, bias,
-                                                                      negative_slope, (int)num_rows,
-                                                                      (int)num_feat, alpha, out, ldout);
+  gat_scores_kernel<<<(unsigned)ceil_div<int64_t>(num_rows, 8), 256, 0, as_stream(stream)>>>(
+      rowptr, col, a_src, a_dst, negative_slope, (int)num_rows, alpha);
   GHSCN_LAUNCH_CHECK();
-  return GHSCN_OK;
+  return ghscn_spmm(rowptr, col, alpha, hs, ldhs, out, ldout, bias, num_rows, num_feat, 0, stream);
 }
 
 int ghscn_gat_pool_bwd_scores(const int32_t* rowptr, const int32_t* col, const float* hs, int64_t ldhs,

@@ -1,58 +1,69 @@
-// K4: segment mean / sum over contiguous row ranges (graph readout) and its broadcast backward.
+// K4: segment mean / sum over contiguous row ranges (graph readout), its broadcast backward, and the
+// column sum used for bias gradients.
 // Replaces torch_scatter.scatter_mean (model/mpnn.py:60) / global_mean_pool (model/hscn.py:111).
-// HBM-bound: 4F(N + B) bytes.  One thread owns one (segment, column-vector) pair and walks the
-// segment's rows in order (CPU scatter_add_ order); consecutive threads read consecutive columns so
-// every row is fetched with coalesced 128-bit loads; 4 rows are kept in flight per thread.
+// HBM-bound: 4F(N + B) bytes.  One CTA owns one (segment, 128-column tile): its 8 warps stride the
+// segment's rows (coalesced 128-bit loads, 2 rows in flight per warp) and the 8 partial sums are combined
+// in fixed warp order in shared memory, so the result is deterministic (run-to-run bit-identical).
 #include "common.cuh"
 
 namespace ghscn {
 
+constexpr int kSegWarps = 8;
+
 template <int VEC>
-__global__ void __launch_bounds__(128) segment_reduce_kernel(const float* __restrict__ x, int64_t ldx,
-                                                             const int* __restrict__ ptr,
-                                                             const int* __restrict__ perm, int num_feat,
-                                                             int mean, float* __restrict__ y, int64_t ldy) {
+__global__ void __launch_bounds__(kSegWarps * 32) segment_reduce_kernel(const float* __restrict__ x, int64_t ldx,
+                                                                        const int* __restrict__ ptr,
+                                                                        const int* __restrict__ perm, int num_feat,
+                                                                        int mean, float* __restrict__ y,
+                                                                        int64_t ldy) {
+  __shared__ float part[kSegWarps][32 * VEC];
   const int g = blockIdx.y;
-  const int f = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-  if (f >= num_feat) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int f = (blockIdx.x * 32 + lane) * VEC;
+  const bool on = f < num_feat;
   const int beg = ptr[g], end = ptr[g + 1];
   float acc[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-  int i = beg;
-  for (; i + 3 < end; i += 4) {
-    float t[4][VEC];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t r = perm ? perm[i + u] : (i + u);
+  if (on) {
+    int i = beg + wid;
+    for (; i + kSegWarps < end; i += 2 * kSegWarps) {
+      const int64_t r0 = perm ? perm[i] : i, r1 = perm ? perm[i + kSegWarps] : (i + kSegWarps);
       if (VEC == 4) {
-        const float4 q = ldg_f4(x + r * ldx + f);
-        t[u][0] = q.x; t[u][1 % VEC] = q.y; t[u][2 % VEC] = q.z; t[u][3 % VEC] = q.w;
+        const float4 a = ldg_f4(x + r0 * ldx + f), b = ldg_f4(x + r1 * ldx + f);
+        acc[0] += a.x; acc[1 % VEC] += a.y; acc[2 % VEC] += a.z; acc[3 % VEC] += a.w;
+        acc[0] += b.x; acc[1 % VEC] += b.y; acc[2 % VEC] += b.z; acc[3 % VEC] += b.w;
       } else {
-        t[u][0] = __ldg(x + r * ldx + f);
+        const float a = __ldg(x + r0 * ldx + f), b = __ldg(x + r1 * ldx + f);
+        acc[0] += a;
+        acc[0] += b;
       }
     }
+    for (; i < end; i += kSegWarps) {
+      const int64_t r0 = perm ? perm[i] : i;
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], t[u][v]);
+      for (int v = 0; v < VEC; ++v) acc[v] += __ldg(x + r0 * ldx + f + v);
+    }
   }
-  for (; i < end; ++i) {
-    const int64_t r = perm ? perm[i] : i;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __ldg(x + r * ldx + f + v));
-  }
-  if (mean) {
-    const float cnt = (float)max(end - beg, 1);
+  for (int v = 0; v < VEC; ++v) part[wid][lane * VEC + v] = acc[v];
+  __syncthreads();
+  if (wid == 0 && on) {
+    float out[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = __fdiv_rn(acc[v], cnt);
+    for (int v = 0; v < VEC; ++v) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kSegWarps; ++w) t += part[w][lane * VEC + v];
+      out[v] = mean ? __fdiv_rn(t, (float)max(end - beg, 1)) : t;
+    }
+    float* yo = y + (int64_t)g * ldy + f;
+    if (VEC == 4) *reinterpret_cast<float4*>(yo) = make_float4(out[0], out[1 % VEC], out[2 % VEC], out[3 % VEC]);
+    else yo[0] = out[0];
   }
-  float* yo = y + (int64_t)g * ldy + f;
-  if (VEC == 4) *reinterpret_cast<float4*>(yo) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
-  else yo[0] = acc[0];
 }
 
-// dx[row(p), :] = dy[seg(p), :] * scale(seg);  grid.y tiles rows, grid.x tiles columns.
+// dx[row(p), :] = dy[seg(p), :] / count(seg) (mean) ; one warp-sized column tile per thread group.
 template <int VEC>
 __global__ void __launch_bounds__(256) segment_broadcast_kernel(const float* __restrict__ dy, int64_t lddy,
                                                                 const int* __restrict__ ptr,
@@ -86,6 +97,66 @@ __global__ void __launch_bounds__(256) segment_broadcast_kernel(const float* __r
   }
 }
 
+// ---- column sum (bias gradients: db = sum_rows dY) ---------------------------------------------------
+// Stage 1: CTA (rows chunk, 128-column tile) -> partial[chunk, :];  stage 2: fixed-order sum over chunks.
+constexpr int kColsumRows = 64;  // rows per CTA (8 per warp)
+
+template <int VEC>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int64_t ldx,
+                                                             int num_rows, int num_feat,
+                                                             float* __restrict__ partial) {
+  __shared__ float part[8][32 * VEC];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int f = (blockIdx.x * 32 + lane) * VEC;
+  const bool on = f < num_feat;
+  const int r0 = blockIdx.y * kColsumRows;
+  float acc[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+  if (on) {
+#pragma unroll 4
+    for (int k = 0; k < kColsumRows / 8; ++k) {
+      const int r = r0 + k * 8 + wid;
+      if (r < num_rows) {
+        if (VEC == 4) {
+          const float4 a = ldg_f4(x + (int64_t)r * ldx + f);
+          acc[0] += a.x; acc[1 % VEC] += a.y; acc[2 % VEC] += a.z; acc[3 % VEC] += a.w;
+        } else {
+          acc[0] += __ldg(x + (int64_t)r * ldx + f);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) part[wid][lane * VEC + v] = acc[v];
+  __syncthreads();
+  if (wid == 0 && on) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w][lane * VEC + v];
+      partial[(int64_t)blockIdx.y * num_feat + f + v] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) colsum_final_kernel(const float* __restrict__ partial, int num_chunks,
+                                                           int num_feat, float* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= num_feat) return;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  int c = 0;
+  for (; c + 3 < num_chunks; c += 4) {
+    t0 += partial[(int64_t)c * num_feat + f];
+    t1 += partial[(int64_t)(c + 1) * num_feat + f];
+    t2 += partial[(int64_t)(c + 2) * num_feat + f];
+    t3 += partial[(int64_t)(c + 3) * num_feat + f];
+  }
+  for (; c < num_chunks; ++c) t0 += partial[(int64_t)c * num_feat + f];
+  out[f] = (t0 + t1) + (t2 + t3);
+}
+
 static inline bool aligned16(const void* a, const void* b) {
   return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) % 16) == 0;
 }
@@ -104,11 +175,13 @@ int ghscn_segment_reduce(const float* x, int64_t ldx, const int32_t* ptr, const 
   GHSCN_REQUIRE(num_segments <= 65535);  // grid.y; readout batches are far below this
   const bool vec4 = num_feat % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && aligned16(x, y);
   if (vec4) {
-    dim3 grid((unsigned)ceil_div<int64_t>(num_feat / 4, 128), (unsigned)num_segments);
-    segment_reduce_kernel<4><<<grid, 128, 0, as_stream(stream)>>>(x, ldx, ptr, perm, (int)num_feat, mean, y, ldy);
-  } else {
     dim3 grid((unsigned)ceil_div<int64_t>(num_feat, 128), (unsigned)num_segments);
-    segment_reduce_kernel<1><<<grid, 128, 0, as_stream(stream)>>>(x, ldx, ptr, perm, (int)num_feat, mean, y, ldy);
+    segment_reduce_kernel<4><<<grid, kSegWarps * 32, 0, as_stream(stream)>>>(x, ldx, ptr, perm, (int)num_feat, mean,
+                                                                            y, ldy);
+  } else {
+    dim3 grid((unsigned)ceil_div<int64_t>(num_feat, 32), (unsigned)num_segments);
+    segment_reduce_kernel<1><<<grid, kSegWarps * 32, 0, as_stream(stream)>>>(x, ldx, ptr, perm, (int)num_feat, mean,
+                                                                            y, ldy);
   }
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
@@ -129,6 +202,38 @@ int ghscn_segment_broadcast(const float* dy, int64_t lddy, const int32_t* ptr, c
     segment_broadcast_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(dy, lddy, ptr, perm, (int)num_segments,
                                                                         (int)num_feat, mean, dx, lddx);
   GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+size_t ghscn_colsum_workspace_bytes(int64_t num_rows, int64_t num_feat) {
+  if (num_rows < 0 || num_feat < 0) return 0;
+  return (size_t)ceil_div<int64_t>(num_rows > 0 ? num_rows : 1, kColsumRows) * num_feat * 4 + 256;
+}
+
+int ghscn_colsum(const float* x, int64_t ldx, int64_t num_rows, int64_t num_feat, float* out, void* workspace,
+                 size_t workspace_bytes, ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && num_rows < ((int64_t)1 << 31) && num_feat < ((int64_t)1 << 24));
+  if (num_feat == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(out && (num_rows == 0 || (x && ldx >= num_feat)));
+  if (workspace_bytes < ghscn_colsum_workspace_bytes(num_rows, num_feat) || workspace == nullptr)
+    return GHSCN_E_WORKSPACE;
+  cudaStream_t stream = as_stream(stream_);
+  float* partial = static_cast<float*>(workspace);
+  const int chunks = (int)ceil_div<int64_t>(num_rows, kColsumRows);
+  if (chunks > 65535) return GHSCN_E_UNSUPPORTED;
+  if (chunks > 0) {
+    const bool vec4 = num_feat % 4 == 0 && ldx % 4 == 0 && aligned16(x, x);
+    if (vec4) {
+      dim3 grid((unsigned)ceil_div<int64_t>(num_feat, 128), (unsigned)chunks);
+      colsum_partial_kernel<4><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial);
+    } else {
+      dim3 grid((unsigned)ceil_div<int64_t>(num_feat, 32), (unsigned)chunks);
+      colsum_partial_kernel<1><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial);
+    }
+  }
+  colsum_final_kernel<<<(unsigned)ceil_div<int64_t>(num_feat, 128), 128, 0, stream>>>(partial, chunks,
+                                                                                      (int)num_feat, out);
+  GHSCN_LAUNCH_CHECK_N(chunks > 0 ? 2 : 1);
   return GHSCN_OK;
 }
 

@@ -68,40 +68,51 @@ __global__ void __launch_bounds__(256) spmm_kernel(const int* __restrict__ rowpt
   for (int it = 0; it < ITERS; ++it) acc[it].zero();
 
   const int beg = rowptr[row], end = rowptr[row + 1];
-  int s = beg;
-  // two slots per trip: both index loads, then all feature loads, then the ordered accumulation
-  for (; s + 1 < end; s += 2) {
-    const int c0 = col[s], c1 = col[s + 1];
-    float w0 = 1.f, w1 = 1.f;
-    if (WEIGHTED) { w0 = w[s]; w1 = w[s + 1]; }
-    const float* x0 = x + (int64_t)c0 * ldx + f0;
-    const float* x1 = x + (int64_t)c1 * ldx + f0;
-    Vec<VEC> a[ITERS], b[ITERS];
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const int f = f0 + it * LPR * VEC;
-      if (f < num_feat) { a[it].load(x0 + it * LPR * VEC); b[it].load(x1 + it * LPR * VEC); }
+  // The row's lane group fetches up to LPR (col, w) pairs with ONE coalesced load each and hands them out
+  // by shuffle: the dependent chain per row is rowptr -> col/w -> features instead of one hop per slot.
+  const unsigned group_mask = (LPR == 32) ? kFullMask : (((1u << LPR) - 1u) << ((lane / LPR) * LPR));
+  for (int base = beg; base < end; base += LPR) {
+    int my_c = 0;
+    float my_w = 1.f;
+    if (base + sub < end) {
+      my_c = col[base + sub];
+      if (WEIGHTED) my_w = w[base + sub];
     }
+    const int cnt = min(LPR, end - base);
+    int j = 0;
+    // two slots per trip: all feature loads first, then the ordered (slot-order) accumulation
+    for (; j + 1 < cnt; j += 2) {
+      const int c0 = __shfl_sync(group_mask, my_c, j, LPR), c1 = __shfl_sync(group_mask, my_c, j + 1, LPR);
+      const float w0 = __shfl_sync(group_mask, my_w, j, LPR), w1 = __shfl_sync(group_mask, my_w, j + 1, LPR);
+      const float* x0 = x + (int64_t)c0 * ldx + f0;
+      const float* x1 = x + (int64_t)c1 * ldx + f0;
+      Vec<VEC> a[ITERS], b[ITERS];
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const int f = f0 + it * LPR * VEC;
-      if (f < num_feat) {
-        if (WEIGHTED) { acc[it].fma_unfused(w0, a[it]); acc[it].fma_unfused(w1, b[it]); }
-        else { acc[it].add(a[it]); acc[it].add(b[it]); }
+      for (int it = 0; it < ITERS; ++it) {
+        const int f = f0 + it * LPR * VEC;
+        if (f < num_feat) { a[it].load(x0 + it * LPR * VEC); b[it].load(x1 + it * LPR * VEC); }
+      }
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int f = f0 + it * LPR * VEC;
+        if (f < num_feat) {
+          if (WEIGHTED) { acc[it].fma_unfused(w0, a[it]); acc[it].fma_unfused(w1, b[it]); }
+          else { acc[it].add(a[it]); acc[it].add(b[it]); }
+        }
       }
     }
-  }
-  if (s < end) {
-    const int c0 = col[s];
-    const float w0 = WEIGHTED ? w[s] : 1.f;
-    const float* x0 = x + (int64_t)c0 * ldx + f0;
+    if (j < cnt) {
+      const int c0 = __shfl_sync(group_mask, my_c, j, LPR);
+      const float w0 = __shfl_sync(group_mask, my_w, j, LPR);
+      const float* x0 = x + (int64_t)c0 * ldx + f0;
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const int f = f0 + it * LPR * VEC;
-      if (f < num_feat) {
-        Vec<VEC> a;
-        a.load(x0 + it * LPR * VEC);
-        if (WEIGHTED) acc[it].fma_unfused(w0, a); else acc[it].add(a);
+      for (int it = 0; it < ITERS; ++it) {
+        const int f = f0 + it * LPR * VEC;
+        if (f < num_feat) {
+          Vec<VEC> a;
+          a.load(x0 + it * LPR * VEC);
+          if (WEIGHTED) acc[it].fma_unfused(w0, a); else acc[it].add(a);
+        }
       }
     }
   }

@@ -20,7 +20,7 @@ from torch import Tensor
 from . import ops
 from ._lib import lib
 from .data import HeteroBatch
-from .structure import _p, _require_cuda, _stream, structure_cache
+from .structure import CSR, _p, _require_cuda, _stream, structure_cache
 
 LL = ("local", "to", "local")
 VV = ("virtual", "to", "virtual")
@@ -46,7 +46,11 @@ def build_hetero_batch(x_raw: Tensor, edge_index: Tensor, batch: Tensor, cluster
     F = x_raw.size(1)
     lv = torch.empty((2, N), dtype=torch.int64, device=dev)
     out = HeteroBatch()
+    voff = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    eoff = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    L.call("ghscn_virtual_offsets", _p(num_virtual), B, _p(voff), _p(eoff), st)
     if padded:
+        V = B * K
         vv_cap = B * (K * (K + 1) // 2)
         vv = torch.empty((2, vv_cap), dtype=torch.int64, device=dev)
         L.call("ghscn_virtual_edges", _p(remap), _p(ptr), _p(num_virtual), None, B, N, K, _p(lv), _p(vv), vv_cap,
@@ -55,10 +59,8 @@ def build_hetero_batch(x_raw: Tensor, edge_index: Tensor, batch: Tensor, cluster
         virt_batch = torch.arange(B, device=dev).repeat_interleave(K)
         virt_ptr = torch.arange(B + 1, device=dev) * K
     else:
-        voff = torch.empty(B + 1, dtype=torch.int32, device=dev)
-        eoff = torch.empty(B + 1, dtype=torch.int32, device=dev)
-        L.call("ghscn_virtual_offsets", _p(num_virtual), B, _p(voff), _p(eoff), st)
         V, E_vv = torch.stack([voff[-1], eoff[-1]]).tolist()      # the one host sync of the compact layout
+        vv_cap = E_vv
         vv = torch.empty((2, E_vv), dtype=torch.int64, device=dev)
         L.call("ghscn_virtual_edges", _p(remap), _p(ptr), _p(num_virtual), _p(voff), B, N, K, _p(lv), _p(vv), E_vv,
                _p(eoff), st)
@@ -77,6 +79,18 @@ def build_hetero_batch(x_raw: Tensor, edge_index: Tensor, batch: Tensor, cluster
     out[LL].edge_index = edge_index      # insertion order ll, vv, lv == hetero_data.py:67,77,84
     out[VV].edge_index = vv
     out[LV].edge_index = lv
+    # K7 also emits both CSR orientations of the two virtual relations, so the layers never sort them
+    i32 = dict(dtype=torch.int32, device=dev)
+    lvd = CSR(torch.empty(V + 1, **i32), torch.empty(N, **i32), torch.empty(N, **i32), V, N, N)
+    lvs = CSR(torch.empty(N + 1, **i32), torch.empty(N, **i32), torch.empty(N, **i32), N, N, N)
+    vvd = CSR(torch.empty(V + 1, **i32), torch.empty(vv_cap, **i32), torch.empty(vv_cap, **i32), V, vv_cap, vv_cap)
+    vvs = CSR(torch.empty(V + 1, **i32), torch.empty(vv_cap, **i32), torch.empty(vv_cap, **i32), V, vv_cap, vv_cap)
+    L.call("ghscn_virtual_csr", _p(remap), _p(ptr), _p(num_virtual), _p(voff), _p(eoff), B, K, int(padded),
+           _p(lvd.rowptr), _p(lvd.col), _p(lvd.perm), _p(lvs.rowptr), _p(lvs.col), _p(lvs.perm),
+           _p(vvd.rowptr), _p(vvd.col), _p(vvd.perm), _p(vvs.rowptr), _p(vvs.col), _p(vvs.perm), st)
+    cache = structure_cache()
+    cache.register_graph(lv, N, V, by_dst=lvd, by_src=lvs)
+    cache.register_graph(vv, V, V, by_dst=vvd, by_src=vvs)
     out.__dict__["num_graphs"] = B
     out.__dict__["cluster"] = remap
     out.__dict__["num_virtual"] = num_virtual

@@ -30,6 +30,26 @@ def _rowmajor(x: Tensor) -> Tensor:
 
 
 # =============================================================================================
+# column sum (bias gradients)
+# =============================================================================================
+@_custom_op("ghscn::colsum", mutates_args=(), device_types="cuda")
+def colsum(x: Tensor) -> Tensor:
+    x = _rowmajor(x)
+    N, F = x.shape
+    out = torch.empty(F, dtype=torch.float32, device=x.device)
+    L = lib()
+    ws_bytes = L.query("ghscn_colsum_workspace_bytes", N, F)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    L.call("ghscn_colsum", _p(x), x.stride(0), N, F, _p(out), _p(ws), ws_bytes, _stream())
+    return out
+
+
+@colsum.register_fake
+def _(x):
+    return x.new_empty((x.size(1),))
+
+
+# =============================================================================================
 # K2/K3  SpMM
 # =============================================================================================
 @_custom_op("ghscn::spmm_raw", mutates_args=(), device_types="cuda")
@@ -90,7 +110,7 @@ def _spmm_backward(ctx, dy):
     if ctx.w_needs_grad:
         dw = spmm_edge_grad(rowptr, col, x, dy, col.numel())
     if ctx.has_bias and ctx.needs_input_grad[7]:
-        dbias = dy.sum(0)
+        dbias = colsum(dy)
     return None, None, dw, None, None, None, dx, dbias
 
 
@@ -243,7 +263,7 @@ def _gat_backward(ctx, dout, _dalpha, _das, _dad):
         dhd = da_dst.unsqueeze(1) * att_dst.unsqueeze(0)
         datt_dst = da_dst @ hd
     if has_bias:
-        dbias = dout.sum(0)
+        dbias = colsum(dout)
     return None, None, None, None, None, dhs, dhd, datt_src, datt_dst, dbias, None
 
 

@@ -111,6 +111,7 @@ class GraphStructure:
         self._slot_map_t: Optional[Tensor] = None
         self._keep: list = []
         self._parent: Optional["GraphStructure"] = None   # set by StructureCache.alias
+        self._plain: Optional["GraphStructure"] = None    # loop-free edge list: derive instead of sorting again
 
     @property
     def num_edges(self) -> int:
@@ -120,10 +121,24 @@ class GraphStructure:
     def _as_plain(c: CSR) -> CSR:
         return CSR(c.rowptr, c.col, c.perm, c.num_rows, c.num_items, c.num_items)
 
+    @staticmethod
+    def _with_loops(c: CSR) -> CSR:
+        """K1 shortcut: CSR(edges + appended loops) from CSR(edges) when no edge is a self loop."""
+        R, E = c.num_rows, c.num_edges
+        dev = c.rowptr.device
+        rowptr = torch.empty(R + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(E + R, dtype=torch.int32, device=dev)
+        perm = torch.empty(E + R, dtype=torch.int32, device=dev)
+        lib().call("ghscn_csr_add_loops", _p(c.rowptr), _p(c.col), _p(c.perm), R, E, _p(rowptr), _p(col), _p(perm),
+                   _stream())
+        return CSR(rowptr, col, perm, R, E, E + R)
+
     @property
     def by_dst(self) -> CSR:
         if self._by_dst is None and self._parent is not None:
             self._by_dst = self._as_plain(self._parent.by_dst)
+        if self._by_dst is None and self._plain is not None:
+            self._by_dst = self._with_loops(self._plain.by_dst)
         if self._by_dst is None:
             self._by_dst = build_csr(self.edge_index[1], self.edge_index[0], self.num_dst, self.add_self_loops)
         return self._by_dst
@@ -132,6 +147,8 @@ class GraphStructure:
     def by_src(self) -> CSR:
         if self._by_src is None and self._parent is not None:
             self._by_src = self._as_plain(self._parent.by_src)
+        if self._by_src is None and self._plain is not None:
+            self._by_src = self._with_loops(self._plain.by_src)
         if self._by_src is None:
             self._by_src = build_csr(self.edge_index[0], self.edge_index[1], self.num_src, self.add_self_loops)
         return self._by_src
@@ -227,12 +244,31 @@ class StructureCache:
         st = self._graphs.get(key)
         if st is None:
             st = GraphStructure(edge_index, num_src, num_dst, add_self_loops)
+            if add_self_loops and self._known_loop_free(edge_index):
+                st._plain = self.graph(edge_index, num_src, num_dst, False)
             self._graphs[key] = st
             self.builds += 1
             while len(self._graphs) > self.capacity:
                 self._graphs.popitem(last=False)
         else:
             self._graphs.move_to_end(key)
+        return st
+
+    @staticmethod
+    def _known_loop_free(edge_index: Tensor) -> bool:
+        """True when the edge list is known to hold no self loop (hint, or one cheap check outside capture)."""
+        if current_hints().get("no_self_loops"):
+            return True
+        if _capturing() or edge_index.numel() == 0:
+            return False            # unknown: the general sort-with-loops path needs no host sync
+        return not bool((edge_index[0] == edge_index[1]).any().item())
+
+    def register_graph(self, edge_index: Tensor, num_src: int, num_dst: int, by_dst: CSR, by_src: CSR
+                       ) -> GraphStructure:
+        """Install a relation whose CSRs were produced directly (K7 emits l->v / v->v without sorting)."""
+        st = GraphStructure(edge_index, num_src, num_dst, False)
+        st._by_dst, st._by_src = by_dst, by_src
+        self._graphs[self._key(edge_index, int(num_src), int(num_dst), False)] = st
         return st
 
     def alias(self, new_index: Tensor, parent: GraphStructure) -> GraphStructure:

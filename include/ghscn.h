@@ -64,6 +64,13 @@ GHSCN_API int ghscn_csr_build(const int64_t* key, const int64_t* other, int64_t 
                               int32_t add_self_loops, int32_t* rowptr, int32_t* col, int32_t* perm,
                               void* workspace, size_t workspace_bytes, ghscn_stream_t stream);
 
+/* CSR of the same edges plus one appended loop per row, derived from the plain CSR without sorting again.
+ * Only valid when the edge list holds no self loop (nothing for add_remaining_self_loops to drop);
+ * outputs are sized num_edges + num_rows and equal ghscn_csr_build(..., add_self_loops = 1). */
+GHSCN_API int ghscn_csr_add_loops(const int32_t* rowptr, const int32_t* col, const int32_t* perm, int64_t num_rows,
+                                  int64_t num_edges, int32_t* rowptr2, int32_t* col2, int32_t* perm2,
+                                  ghscn_stream_t stream);
+
 /* sorted `batch` vector -> ptr[num_graphs+1] (PyG collate convention). */
 GHSCN_API int ghscn_batch_to_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs, int32_t* ptr,
                                  ghscn_stream_t stream);
@@ -118,6 +125,12 @@ GHSCN_API int ghscn_segment_reduce(const float* x, int64_t ldx, const int32_t* p
 GHSCN_API int ghscn_segment_broadcast(const float* dy, int64_t lddy, const int32_t* ptr, const int32_t* perm,
                                       int64_t num_segments, int64_t num_feat, int32_t mean, float* dx, int64_t lddx,
                                       ghscn_stream_t stream);
+
+/* Column sum out[f] = sum_r x[r,f] (bias gradients db = sum_rows dY of GCNConv / GATConv); two-stage,
+ * fixed order => deterministic.  workspace >= ghscn_colsum_workspace_bytes(). */
+GHSCN_API size_t ghscn_colsum_workspace_bytes(int64_t num_rows, int64_t num_feat);
+GHSCN_API int ghscn_colsum(const float* x, int64_t ldx, int64_t num_rows, int64_t num_feat, float* out,
+                           void* workspace, size_t workspace_bytes, ghscn_stream_t stream);
 
 /* ---- K5: bipartite GAT cluster pool (local -> virtual) ---------------------------------------
  * Replaces GATConv((-1,-1), H, add_self_loops=False) on ("local","to","virtual")
@@ -205,6 +218,17 @@ GHSCN_API int ghscn_virtual_edges(const int32_t* cluster_remapped, const int32_t
                                   ghscn_stream_t stream);
 GHSCN_API int ghscn_virtual_offsets(const int32_t* num_virtual, int64_t num_graphs, int32_t* virt_offset /*[B+1]*/,
                                     int32_t* vv_offset /*[B+1]*/, ghscn_stream_t stream);
+/* Both orientations of the l->v and v->v relations straight from the cluster assignment (no sort):
+ * lvd_* rows = virtual nodes, lvs_* rows = local nodes, vvd_* / vvs_* rows = virtual nodes (by destination /
+ * by source).  vv_offset[B+1] is the exclusive scan of U_g(U_g+1)/2 (ghscn_virtual_offsets); with padded != 0
+ * virtual ids are g*K + j and v->v edge ids g*K(K+1)/2 + p, otherwise the compact virt_offset / vv_offset ids.
+ * Equals ghscn_csr_build on the edge lists of ghscn_virtual_edges. */
+GHSCN_API int ghscn_virtual_csr(const int32_t* cluster_remapped, const int32_t* ptr, const int32_t* num_virtual,
+                                const int32_t* virt_offset, const int32_t* vv_offset, int64_t num_graphs,
+                                int64_t num_clusters, int32_t padded, int32_t* lvd_rowptr, int32_t* lvd_col,
+                                int32_t* lvd_perm, int32_t* lvs_rowptr, int32_t* lvs_col, int32_t* lvs_perm,
+                                int32_t* vvd_rowptr, int32_t* vvd_col, int32_t* vvd_perm, int32_t* vvs_rowptr,
+                                int32_t* vvs_col, int32_t* vvs_perm, ghscn_stream_t stream);
 GHSCN_API int ghscn_virtual_compact(const float* virt_x_padded, const int32_t* num_virtual,
                                     const int32_t* virt_offset, int64_t num_graphs, int64_t num_clusters,
                                     int64_t num_feat, float* virt_x /*[V,F]*/, int64_t* virt_batch /*[V]*/,

@@ -1,0 +1,67 @@
+"""GPU tests of the sort-free structure shortcuts: they must equal the general stable radix sort bit for bit."""
+import pytest
+import torch
+
+from tests.util import assert_close, random_edge_index
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(a, b, nnz=None):
+    assert torch.equal(a.rowptr, b.rowptr)
+    n = int(a.rowptr[-1]) if nnz is None else nnz
+    assert torch.equal(a.col[:n], b.col[:n]) and torch.equal(a.perm[:n], b.perm[:n])
+
+
+def test_csr_add_loops_equals_sort_with_loops(cuda):
+    from graph_hscn_b200.structure import GraphStructure, build_csr
+    g = torch.Generator().manual_seed(3)
+    n, e = 3000, 9000
+    ei = random_edge_index(n, n, e, g, self_loops=False).to(cuda)
+    for key, other in ((ei[1], ei[0]), (ei[0], ei[1])):
+        full = build_csr(key, other, n, True)
+        derived = GraphStructure._with_loops(build_csr(key, other, n, False))
+        _same(derived, full)
+        assert derived.num_items == e + n
+
+
+def test_cache_derives_loops_only_when_loop_free(cuda):
+    from graph_hscn_b200.structure import StructureCache
+    g = torch.Generator().manual_seed(4)
+    cache = StructureCache()
+    clean = random_edge_index(50, 50, 200, g, self_loops=False).to(cuda)
+    dirty = torch.cat([clean, torch.tensor([[3, 7], [3, 7]], device=cuda)], 1)
+    assert cache.graph(clean, 50, 50, True)._plain is not None
+    assert cache.graph(dirty, 50, 50, True)._plain is None          # existing loops: general path
+    d = cache.graph(dirty, 50, 50, True).by_dst
+    assert int(d.rowptr[-1]) == 200 + 50                             # 2 dropped, 50 appended
+
+
+@pytest.mark.parametrize("padded", [False, True])
+@pytest.mark.parametrize("K", [3, 10])
+def test_virtual_csr_equals_sort(cuda, padded, K):
+    from graph_hscn_b200 import hetero, synthetic
+    from graph_hscn_b200.structure import build_csr, structure_cache
+    b = synthetic.peptides_batch(9, seed=K)
+    g = torch.Generator().manual_seed(K)
+    clusters = torch.randint(0, K, (b.x.size(0),), generator=g).int()
+    clusters[: int(b.ptr[1])] = 1                      # a graph with a single cluster
+    hb = hetero.build_hetero_batch(b.x.to(cuda), b.edge_index.to(cuda), b.batch.to(cuda), clusters.to(cuda), K,
+                                   padded=padded)
+    N, V = b.x.size(0), hb["virtual"].x.size(0)
+    lv = hb["local", "to", "virtual"].edge_index
+    vv = hb["virtual", "to", "virtual"].edge_index
+    st_lv = structure_cache().graph(lv, N, V, False)
+    st_vv = structure_cache().graph(vv, V, V, False)
+    assert st_lv._by_dst is not None and st_vv._by_src is not None      # pre-registered, not sorted
+    _same(st_lv.by_dst, build_csr(lv[1], lv[0], V, False))
+    _same(st_lv.by_src, build_csr(lv[0], lv[1], N, False))
+    _same(st_vv.by_dst, build_csr(vv[1], vv[0], V, False))
+    _same(st_vv.by_src, build_csr(vv[0], vv[1], V, False))
+
+
+def test_colsum_matches_torch(cuda):
+    g = torch.Generator().manual_seed(5)
+    for n, f in [(1, 4), (18269, 300), (1000, 10), (65, 33)]:
+        x = torch.randn(n, f, generator=g).to(cuda)
+        assert_close(torch.ops.ghscn.colsum(x), x.double().sum(0).float(), 1e-5, f"colsum {n}x{f}")
