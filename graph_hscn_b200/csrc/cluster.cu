@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) virtual_build_kernel(const int* __restric
                                                             int64_t ldx, int K, int F,
                                                             int* __restrict__ cluster_remapped,
                                                             int* __restrict__ num_virtual,
-                                                            float* __restrict__ virt_x) {
+                                                            float* __restrict__ virt_x, int dyn_smem_ints) {
   __shared__ int present[kMaxK];
   __shared__ int rank[kMaxK];
   __shared__ int U_s;
@@ -61,6 +61,31 @@ __global__ void __launch_bounds__(256) virtual_build_kernel(const int* __restric
     cluster_remapped[base + i] = (c >= 0 && c < K) ? rank[c] : 0;
   }
   __syncthreads();
+  if (sizeof(T) == 8 && dyn_smem_ints > 0) {
+    // integer (OGB atom) features: exact int64 sums with shared-memory atomics, node-parallel; the result does
+    // not depend on the order, so it equals numpy's float64 mean of integers bit for bit.
+    extern __shared__ unsigned long long sums[];           // [U][F] then counts [U] (as ull)
+    unsigned long long* cnts = sums + (size_t)K * F;
+    for (int i = tid; i < K * F + K; i += blockDim.x) sums[i] = 0ull;
+    __syncthreads();
+    for (int item = tid; item < n * F; item += blockDim.x) {
+      const int i = item / F, f = item - i * F;
+      const int c = cluster_remapped[base + i];
+      atomicAdd(&sums[(size_t)c * F + f], (unsigned long long)(long long)x[(int64_t)(base + i) * ldx + f]);
+      if (f == 0) atomicAdd(&cnts[c], 1ull);
+    }
+    __syncthreads();
+    for (int item = tid; item < K * F; item += blockDim.x) {
+      const int j = item / F, f = item - j * F;
+      float r = 0.f;
+      if (j < U) {
+        const int want = (j + 1) % U;
+        r = (float)((double)(long long)sums[(size_t)want * F + f] / (double)(long long)cnts[want]);
+      }
+      virt_x[((int64_t)g * K + j) * F + f] = r;
+    }
+    return;
+  }
   // virtual row j <- mean over nodes whose remapped cluster is (j+1) mod U, in node order
   for (int item = tid; item < K * F; item += blockDim.x) {
     const int j = item / F, f = item - j * F;
@@ -259,14 +284,17 @@ int ghscn_virtual_build(const int32_t* cluster, const int32_t* ptr, const void* 
   if (num_clusters > kMaxK) return GHSCN_E_UNSUPPORTED;
   if (num_graphs == 0) return GHSCN_OK;
   GHSCN_REQUIRE(cluster && ptr && x_raw && cluster_remapped && num_virtual && virt_x_padded && ldx >= num_feat);
-  if (x_is_int64)
-    virtual_build_kernel<int64_t><<<(unsigned)num_graphs, 256, 0, as_stream(stream)>>>(
+  if (x_is_int64) {
+    size_t dyn = ((size_t)num_clusters * num_feat + num_clusters) * 8;
+    if (dyn > 40 * 1024) dyn = 0;  // too many cluster x feature sums for shared memory: sequential path
+    virtual_build_kernel<int64_t><<<(unsigned)num_graphs, 256, dyn, as_stream(stream)>>>(
         cluster, ptr, static_cast<const int64_t*>(x_raw), ldx, (int)num_clusters, (int)num_feat, cluster_remapped,
-        num_virtual, virt_x_padded);
-  else
+        num_virtual, virt_x_padded, (int)(dyn / 4));
+  } else {
     virtual_build_kernel<float><<<(unsigned)num_graphs, 256, 0, as_stream(stream)>>>(
         cluster, ptr, static_cast<const float*>(x_raw), ldx, (int)num_clusters, (int)num_feat, cluster_remapped,
-        num_virtual, virt_x_padded);
+        num_virtual, virt_x_padded, 0);
+  }
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }

@@ -23,6 +23,9 @@
 namespace ghscn {
 
 void note_launches(int n);  // defined in csr.cu
+// spmm.cu: y[r,:] = sum_s w[s] x[col[s],:] (+ bias) for relations with few, long rows (128-bit path only)
+int spmm_long_rows(const int* rowptr, const int* col, const float* w, const float* x, int64_t ldx, float* y,
+                   int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, cudaStream_t stream);
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 constexpr unsigned kFullMask = 0xffffffffu;

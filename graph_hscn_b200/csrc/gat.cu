@@ -164,6 +164,12 @@ int ghscn_gat_pool_fwd(const int32_t* rowptr, const int32_t* col, const float* h
   gat_scores_kernel<<<(unsigned)ceil_div<int64_t>(num_rows, 8), 256, 0, as_stream(stream)>>>(
       rowptr, col, a_src, a_dst, negative_slope, (int)num_rows, alpha);
   GHSCN_LAUNCH_CHECK();
+  // pooling relation: few destination rows with many members each -> one CTA per row
+  const bool vec4 = num_feat % 4 == 0 && ldhs % 4 == 0 && ldout % 4 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(hs) | reinterpret_cast<uintptr_t>(out) |
+                      reinterpret_cast<uintptr_t>(bias)) % 16 == 0);
+  if (vec4 && num_feat >= 64 && num_rows <= 65535)
+    return spmm_long_rows(rowptr, col, alpha, hs, ldhs, out, ldout, bias, num_rows, num_feat, as_stream(stream));
   return ghscn_spmm(rowptr, col, alpha, hs, ldhs, out, ldout, bias, num_rows, num_feat, 0, stream);
 }
 

@@ -13,7 +13,8 @@
 
 namespace ghscn {
 
-constexpr int kMincutThreads = 256;
+// few graphs: one big CTA per graph keeps an SM busy; many graphs: several small CTAs per SM
+static inline int mincut_threads(int64_t num_graphs) { return num_graphs >= 4 * kNumSMs ? 256 : (num_graphs >= 2 * kNumSMs ? 512 : 1024); }
 constexpr int kMaxClusters = 128;
 constexpr int kStatsStride = 8;  // per graph: num, den, ||SS||_F, ||R||_F (= ortho_g), mc_g, -, -, -
 constexpr size_t kSmemBudget = 200 * 1024;
@@ -39,7 +40,7 @@ __device__ __forceinline__ void csr_times_s(const int* __restrict__ rowptr, cons
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(kMincutThreads) mincut_fwd_kernel(
+__global__ void __launch_bounds__(1024) mincut_fwd_kernel(
     const float* __restrict__ logits, int64_t ldz, const float* __restrict__ x, int64_t ldx,
     const int* __restrict__ ptr, const int* __restrict__ rowptr, const int* __restrict__ col,
     const float* __restrict__ adj_val, float temp, int K, int H, int n_cap, float* __restrict__ s_soft,
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_fwd_kernel(
   const int g = blockIdx.x;
   const int base = ptr[g];
   const int n = ptr[g + 1] - base;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = kMincutThreads / 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x / 32;
 
   float* Sg = s_soft + (int64_t)base * K;
   float* S = SMEM ? smem : Sg;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_fwd_kernel(
 
   // C. traces, S^T S, S^T A S, S^T X
   float pnum = 0.f, pden = 0.f;
-  for (int e = tid; e < n * K; e += kMincutThreads) {
+  for (int e = tid; e < n * K; e += blockDim.x) {
     const float sv = S[e];
     pnum += sv * AS[e];
     pden += deg[e / K] * sv * sv;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_fwd_kernel(
 
   float* ssg = ss_raw + (int64_t)g * K * K;
   float* oag = adj_raw + (int64_t)g * K * K;
-  for (int p = tid; p < K * K; p += kMincutThreads) {
+  for (int p = tid; p < K * K; p += blockDim.x) {
     const int k = p / K, l = p - k * K;
     float ss = 0.f, oa = 0.f;
     for (int i = 0; i < n; ++i) {
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_fwd_kernel(
     constexpr int KC = 8;
     float* og = out + (int64_t)g * K * H;
     const int chunks = ceil_div(K, KC);
-    for (int item = tid; item < chunks * H; item += kMincutThreads) {
+    for (int item = tid; item < chunks * H; item += blockDim.x) {
       const int kc = (item / H) * KC, h = item % H;
       float acc[KC];
 #pragma unroll
@@ -140,11 +141,11 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_fwd_kernel(
 
   // D. losses and the normalised coarse adjacency
   float pf = 0.f;
-  for (int p = tid; p < K * K; p += kMincutThreads) pf += ssg[p] * ssg[p];
+  for (int p = tid; p < K * K; p += blockDim.x) pf += ssg[p] * ssg[p];
   const float fro = sqrtf(block_sum(pf, red));
   const float inv_sqrt_k = __fdiv_rn(1.0f, sqrtf((float)K));
   float pr = 0.f;
-  for (int p = tid; p < K * K; p += kMincutThreads) {
+  for (int p = tid; p < K * K; p += blockDim.x) {
     const int k = p / K, l = p - k * K;
     const float r = __fdiv_rn(ssg[p], fro) - (k == l ? inv_sqrt_k : 0.f);
     pr += r * r;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_fwd_kernel(
     st[5] = 0.f; st[6] = 0.f; st[7] = 0.f;
   }
   if (out_adj != nullptr) {
-    for (int k = tid; k < K; k += kMincutThreads) {
+    for (int k = tid; k < K; k += blockDim.x) {
       float r = 0.f;
       for (int l = 0; l < K; ++l)
         if (l != k) r += oag[k * K + l];
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_fwd_kernel(
     }
     __syncthreads();
     float* ng = out_adj + (int64_t)g * K * K;
-    for (int p = tid; p < K * K; p += kMincutThreads) {
+    for (int p = tid; p < K * K; p += blockDim.x) {
       const int k = p / K, l = p - k * K;
       ng[p] = (k == l) ? 0.f : __fdiv_rn(__fdiv_rn(oag[p], dk[l]), dk[k]);
     }
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(256) mincut_reduce_losses_kernel(const float* 
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(kMincutThreads) mincut_bwd_kernel(
+__global__ void __launch_bounds__(1024) mincut_bwd_kernel(
     const float* __restrict__ s_soft, const float* __restrict__ x, int64_t ldx, const int* __restrict__ ptr,
     const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ adj_val,
     const int* __restrict__ rowptr_t, const int* __restrict__ col_t, const float* __restrict__ adj_val_t,
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_bwd_kernel(
   const int g = blockIdx.x;
   const int base = ptr[g];
   const int n = ptr[g + 1] - base;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = kMincutThreads / 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x / 32;
   const size_t nk_cap = (size_t)n_cap * K;
 
   // shared layout: [Gsym K*K][Gam K*K][deg n_cap] (+ [S][AS][ATS][dS] when SMEM)
@@ -216,10 +217,10 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_bwd_kernel(
   float* ATS = SMEM ? AS + nk_cap : ws + (int64_t)(ptr[B] + base) * K;
   float* dS = SMEM ? ATS + nk_cap : ws + (int64_t)(2 * ptr[B] + base) * K;
   if (SMEM) {
-    for (int e = tid; e < n * K; e += kMincutThreads) S[e] = Sg[e];
+    for (int e = tid; e < n * K; e += blockDim.x) S[e] = Sg[e];
   }
   const float* Sr = SMEM ? S : Sg;
-  for (int i = tid; i < n; i += kMincutThreads) {
+  for (int i = tid; i < n; i += blockDim.x) {
     float d = 0.f;
     for (int s = rowptr[base + i]; s < rowptr[base + i + 1]; ++s) d += adj_value(adj_val, s);
     deg[i] = d;
@@ -238,14 +239,14 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_bwd_kernel(
 
   // ortho: G = R/||R||, G' = (G - M <G,M>)/F, Gsym = go * (G' + G'^T)
   float pin = 0.f;
-  for (int p = tid; p < K * K; p += kMincutThreads) {
+  for (int p = tid; p < K * K; p += blockDim.x) {
     const int k = p / K, l = p - k * K;
     const float M = ssg[p] / fro;
     const float G = nrm > 0.f ? (M - (k == l ? inv_sqrt_k : 0.f)) / nrm : 0.f;
     pin += G * M;
   }
   const float inner = block_sum(pin, red);
-  for (int p = tid; p < K * K; p += kMincutThreads) {
+  for (int p = tid; p < K * K; p += blockDim.x) {
     const int k = p / K, l = p - k * K;
     const float M = ssg[p] / fro, Mt = ssg[l * K + k] / fro;
     const float G = nrm > 0.f ? (M - (k == l ? inv_sqrt_k : 0.f)) / nrm : 0.f;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_bwd_kernel(
   // Gamma = dL/d(S^T A S): trace term of the mincut loss + chain through the normalised out_adj
   if (g_out_adj != nullptr) {
     const float* gb = g_out_adj + (int64_t)g * K * K;
-    for (int k = tid; k < K; k += kMincutThreads) {
+    for (int k = tid; k < K; k += blockDim.x) {
       float r = 0.f;
       for (int l = 0; l < K; ++l)
         if (l != k) r += oag[k * K + l];
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_bwd_kernel(
       dr[k] = r;
     }
     __syncthreads();
-    for (int k = tid; k < K; k += kMincutThreads) {
+    for (int k = tid; k < K; k += blockDim.x) {
       float acc = 0.f;  // sum_l Gbar[k][l] N[k][l] + Gbar[l][k] N[l][k]
       for (int l = 0; l < K; ++l) {
         if (l == k) continue;
@@ -276,22 +277,22 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_bwd_kernel(
       dr[k] = sq > 0.f ? ddk / (2.f * sq) : 0.f;  // dL/d(rowsum_k)
     }
     __syncthreads();
-    for (int p = tid; p < K * K; p += kMincutThreads) {
+    for (int p = tid; p < K * K; p += blockDim.x) {
       const int k = p / K, l = p - k * K;
       Gam[p] = (k == l) ? 0.f : gb[p] / (dk[k] * dk[l]) + dr[k];
     }
   } else {
-    for (int p = tid; p < K * K; p += kMincutThreads) Gam[p] = 0.f;
+    for (int p = tid; p < K * K; p += blockDim.x) Gam[p] = 0.f;
   }
   __syncthreads();
-  for (int k = tid; k < K; k += kMincutThreads) Gam[k * K + k] += -gmc / den;
+  for (int k = tid; k < K; k += blockDim.x) Gam[k * K + k] += -gmc / den;
   __syncthreads();
 
   const float cden = gmc * num / (den * den);
   const bool diag_only = (g_out_adj == nullptr);
   const float gdiag = -gmc / den;
   const float* gog = g_out ? g_out + (int64_t)g * K * H : nullptr;
-  for (int e = tid; e < n * K; e += kMincutThreads) {
+  for (int e = tid; e < n * K; e += blockDim.x) {
     const int i = e / K, k = e - i * K;
     float v;
     if (diag_only) {
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(kMincutThreads) mincut_bwd_kernel(
     }
   }
   if (d_x != nullptr) {
-    for (int e = tid; e < n * H; e += kMincutThreads) {
+    for (int e = tid; e < n * H; e += blockDim.x) {
       const int i = e / H, h = e - i * H;
       float acc = 0.f;
       if (gog)
@@ -370,6 +371,7 @@ int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x, int64_t l
   GHSCN_REQUIRE(max_nodes_per_graph > 0);
   cudaStream_t stream = as_stream(stream_);
   const int K = (int)num_clusters, H = (int)num_feat, n_cap = max_nodes_per_graph;
+  const int threads = mincut_threads(num_graphs);
   const bool smem = fwd_smem_bytes(n_cap, K, true) <= kSmemBudget;
   const size_t shm = fwd_smem_bytes(n_cap, K, smem);
   if (shm > kSmemBudget) return GHSCN_E_UNSUPPORTED;
@@ -380,11 +382,11 @@ int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x, int64_t l
   }
   if (smem) {
     cudaFuncSetAttribute(mincut_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-    mincut_fwd_kernel<true><<<(unsigned)num_graphs, kMincutThreads, shm, stream>>>(
+    mincut_fwd_kernel<true><<<(unsigned)num_graphs, threads, shm, stream>>>(
         logits, ldz, x, ldx, ptr, rowptr, col, adj_val, temp, K, H, n_cap, s_soft, out, out_adj, ss_raw, adj_raw,
         stats, as_ws);
   } else {
-    mincut_fwd_kernel<false><<<(unsigned)num_graphs, kMincutThreads, shm, stream>>>(
+    mincut_fwd_kernel<false><<<(unsigned)num_graphs, threads, shm, stream>>>(
         logits, ldz, x, ldx, ptr, rowptr, col, adj_val, temp, K, H, n_cap, s_soft, out, out_adj, ss_raw, adj_raw,
         stats, as_ws);
   }
@@ -408,6 +410,7 @@ int ghscn_mincut_bwd(const float* s_soft, const float* x, int64_t ldx, const int
   GHSCN_REQUIRE((g_out == nullptr && d_x == nullptr) || x != nullptr);
   cudaStream_t stream = as_stream(stream_);
   const int K = (int)num_clusters, H = (int)num_feat, n_cap = max_nodes_per_graph;
+  const int threads = mincut_threads(num_graphs);
   const bool smem = bwd_smem_bytes(n_cap, K, true) <= kSmemBudget;
   const size_t shm = bwd_smem_bytes(n_cap, K, smem);
   if (shm > kSmemBudget) return GHSCN_E_UNSUPPORTED;
@@ -418,12 +421,12 @@ int ghscn_mincut_bwd(const float* s_soft, const float* x, int64_t ldx, const int
   }
   if (smem) {
     cudaFuncSetAttribute(mincut_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-    mincut_bwd_kernel<true><<<(unsigned)num_graphs, kMincutThreads, shm, stream>>>(
+    mincut_bwd_kernel<true><<<(unsigned)num_graphs, threads, shm, stream>>>(
         s_soft, x, ldx, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, temp, (int)num_graphs, K, H, n_cap,
         ss_raw, adj_raw, stats, g_out, g_out_adj, g_losses, d_logits, lddz, d_x, lddx, ws);
   } else {
     cudaFuncSetAttribute(mincut_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-    mincut_bwd_kernel<false><<<(unsigned)num_graphs, kMincutThreads, shm, stream>>>(
+    mincut_bwd_kernel<false><<<(unsigned)num_graphs, threads, shm, stream>>>(
         s_soft, x, ldx, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, temp, (int)num_graphs, K, H, n_cap,
         ss_raw, adj_raw, stats, g_out, g_out_adj, g_losses, d_logits, lddz, d_x, lddx, ws);
   }

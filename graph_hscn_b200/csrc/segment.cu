@@ -141,20 +141,31 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
   }
 }
 
-__global__ void __launch_bounds__(128) colsum_final_kernel(const float* __restrict__ partial, int num_chunks,
+// One CTA per 32 columns: 8 warps stride the chunk partials (4 loads in flight each), fixed-order combine.
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int num_chunks,
                                                            int num_feat, float* __restrict__ out) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= num_feat) return;
+  __shared__ float part[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int f = blockIdx.x * 32 + lane;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-  int c = 0;
-  for (; c + 3 < num_chunks; c += 4) {
-    t0 += partial[(int64_t)c * num_feat + f];
-    t1 += partial[(int64_t)(c + 1) * num_feat + f];
-    t2 += partial[(int64_t)(c + 2) * num_feat + f];
-    t3 += partial[(int64_t)(c + 3) * num_feat + f];
+  if (f < num_feat) {
+    int c = wid;
+    for (; c + 24 < num_chunks; c += 32) {
+      t0 += partial[(int64_t)c * num_feat + f];
+      t1 += partial[(int64_t)(c + 8) * num_feat + f];
+      t2 += partial[(int64_t)(c + 16) * num_feat + f];
+      t3 += partial[(int64_t)(c + 24) * num_feat + f];
+    }
+    for (; c < num_chunks; c += 8) t0 += partial[(int64_t)c * num_feat + f];
   }
-  for (; c < num_chunks; ++c) t0 += partial[(int64_t)c * num_feat + f];
-  out[f] = (t0 + t1) + (t2 + t3);
+  part[wid][lane] = (t0 + t1) + (t2 + t3);
+  __syncthreads();
+  if (wid == 0 && f < num_feat) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    out[f] = t;
+  }
 }
 
 static inline bool aligned16(const void* a, const void* b) {
@@ -231,8 +242,8 @@ int ghscn_colsum(const float* x, int64_t ldx, int64_t num_rows, int64_t num_feat
       colsum_partial_kernel<1><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial);
     }
   }
-  colsum_final_kernel<<<(unsigned)ceil_div<int64_t>(num_feat, 128), 128, 0, stream>>>(partial, chunks,
-                                                                                      (int)num_feat, out);
+  colsum_final_kernel<<<(unsigned)ceil_div<int64_t>(num_feat, 32), 256, 0, stream>>>(partial, chunks,
+                                                                                     (int)num_feat, out);
   GHSCN_LAUNCH_CHECK_N(chunks > 0 ? 2 : 1);
   return GHSCN_OK;
 }

@@ -128,6 +128,189 @@ __global__ void __launch_bounds__(256) spmm_kernel(const int* __restrict__ rowpt
   }
 }
 
+// ---- wide rows (F >= 128, 128-bit path): CTA-staged indices ------------------------------------------
+// A CTA owns kRowsPerCta consecutive rows.  Their rowptr entries and the whole contiguous (col, w) slot range
+// are staged in shared memory with two coalesced passes, so no warp has an index load on its critical path;
+// each warp then walks its rows issuing the feature loads of up to 4 slots (4 x ITERS 128-bit loads per lane)
+// before the ordered, unfused accumulation.  This keeps several KB per warp in flight, which is what a
+// gather with ~3 slots per row needs to approach HBM/L2 bandwidth.
+constexpr int kRowsPerCta = 64;
+constexpr int kSlotCap = 1024;
+
+template <int ITERS, bool WEIGHTED>
+__global__ void __launch_bounds__(256, 2) spmm_wide_kernel(const int* __restrict__ rowptr,
+                                                           const int* __restrict__ col,
+                                                           const float* __restrict__ w,
+                                                           const float* __restrict__ x, int64_t ldx,
+                                                           float* __restrict__ y, int64_t ldy,
+                                                           const float* __restrict__ bias, int num_rows,
+                                                           int num_feat, int relu) {
+  __shared__ int s_rowptr[kRowsPerCta + 1];
+  __shared__ int s_col[kSlotCap];
+  __shared__ float s_w[kSlotCap];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int row0 = blockIdx.x * kRowsPerCta;
+  const int nrows = min(kRowsPerCta, num_rows - row0);
+  if (tid <= nrows) s_rowptr[tid] = rowptr[row0 + tid];
+  __syncthreads();
+  const int sbeg = s_rowptr[0];
+  const int staged = min(s_rowptr[nrows] - sbeg, kSlotCap);
+  for (int i = tid; i < staged; i += 256) {
+    s_col[i] = col[sbeg + i];
+    if (WEIGHTED) s_w[i] = w[sbeg + i];
+  }
+  __syncthreads();
+  const int f0 = blockIdx.y * (128 * ITERS) + lane * 4;
+
+  for (int r = wid; r < nrows; r += 8) {
+    const int beg = s_rowptr[r] - sbeg, end = s_rowptr[r + 1] - sbeg;
+    float4 acc[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = beg; s < end; s += 4) {
+      const int n4 = min(4, end - s);
+      float4 v[4][ITERS];
+      float wv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < n4) {
+          const int slot = s + k;
+          const int c = slot < kSlotCap ? s_col[slot] : col[sbeg + slot];
+          wv[k] = WEIGHTED ? (slot < kSlotCap ? s_w[slot] : w[sbeg + slot]) : 1.f;
+          const float* xr = x + (int64_t)c * ldx + f0;
+#pragma unroll
+          for (int it = 0; it < ITERS; ++it)
+            if (f0 + it * 128 < num_feat) v[k][it] = ldg_f4(xr + it * 128);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < n4) {
+#pragma unroll
+          for (int it = 0; it < ITERS; ++it) {
+            if (f0 + it * 128 < num_feat) {
+              if (WEIGHTED) {
+                acc[it].x = mul_then_add(acc[it].x, wv[k], v[k][it].x);
+                acc[it].y = mul_then_add(acc[it].y, wv[k], v[k][it].y);
+                acc[it].z = mul_then_add(acc[it].z, wv[k], v[k][it].z);
+                acc[it].w = mul_then_add(acc[it].w, wv[k], v[k][it].w);
+              } else {
+                acc[it].x = __fadd_rn(acc[it].x, v[k][it].x);
+                acc[it].y = __fadd_rn(acc[it].y, v[k][it].y);
+                acc[it].z = __fadd_rn(acc[it].z, v[k][it].z);
+                acc[it].w = __fadd_rn(acc[it].w, v[k][it].w);
+              }
+            }
+          }
+        }
+      }
+    }
+    float* yrow = y + (int64_t)(row0 + r) * ldy + f0;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      if (f0 + it * 128 < num_feat) {
+        float4 o = acc[it];
+        if (bias) {
+          const float4 b = ldg_f4(bias + f0 + it * 128);
+          o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y); o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(yrow + it * 128) = o;
+      }
+    }
+  }
+}
+
+template <int ITERS>
+static int launch_spmm_wide(const int* rowptr, const int* col, const float* w, const float* x, int64_t ldx,
+                            float* y, int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, int relu,
+                            cudaStream_t stream) {
+  dim3 grid((unsigned)ceil_div<int64_t>(num_rows, kRowsPerCta), (unsigned)ceil_div<int64_t>(num_feat, 128 * ITERS));
+  if (w)
+    spmm_wide_kernel<ITERS, true><<<grid, 256, 0, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias, (int)num_rows,
+                                                             (int)num_feat, relu);
+  else
+    spmm_wide_kernel<ITERS, false><<<grid, 256, 0, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias, (int)num_rows,
+                                                              (int)num_feat, relu);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+// ---- few long rows (pooling relations: every destination has many sources) ------------------------------
+// One CTA per row: its 8 warps stride the row's slots, each keeps full-width partial sums, and the partials are
+// combined in fixed warp order (deterministic; not the sequential CPU order, which pooled rows do not need).
+template <int ITERS, bool WEIGHTED>
+__global__ void __launch_bounds__(256) spmm_longrow_kernel(const int* __restrict__ rowptr,
+                                                           const int* __restrict__ col,
+                                                           const float* __restrict__ w,
+                                                           const float* __restrict__ x, int64_t ldx,
+                                                           float* __restrict__ y, int64_t ldy,
+                                                           const float* __restrict__ bias, int num_feat) {
+  __shared__ float4 part[8][ITERS * 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row = blockIdx.x;
+  const int f0 = blockIdx.y * (128 * ITERS) + lane * 4;
+  const int beg = rowptr[row], end = rowptr[row + 1];
+  float4 acc[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = beg + wid; s < end; s += 16) {
+    const bool two = s + 8 < end;
+    const int c0 = col[s], c1 = two ? col[s + 8] : c0;
+    const float w0 = WEIGHTED ? w[s] : 1.f, w1 = (WEIGHTED && two) ? w[s + 8] : 1.f;
+    float4 a[ITERS], b[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      if (f0 + it * 128 < num_feat) {
+        a[it] = ldg_f4(x + (int64_t)c0 * ldx + f0 + it * 128);
+        b[it] = ldg_f4(x + (int64_t)c1 * ldx + f0 + it * 128);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      if (f0 + it * 128 < num_feat) {
+        acc[it].x += w0 * a[it].x; acc[it].y += w0 * a[it].y; acc[it].z += w0 * a[it].z; acc[it].w += w0 * a[it].w;
+        if (two) {
+          acc[it].x += w1 * b[it].x; acc[it].y += w1 * b[it].y; acc[it].z += w1 * b[it].z; acc[it].w += w1 * b[it].w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) part[wid][it * 32 + lane] = acc[it];
+  __syncthreads();
+  for (int i = threadIdx.x; i < ITERS * 32; i += 256) {
+    const int f = blockIdx.y * (128 * ITERS) + (i / 32) * 128 + (i % 32) * 4;
+    if (f < num_feat) {
+      float4 t = part[0][i];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) { t.x += part[k][i].x; t.y += part[k][i].y; t.z += part[k][i].z; t.w += part[k][i].w; }
+      if (bias) { const float4 bb = ldg_f4(bias + f); t.x += bb.x; t.y += bb.y; t.z += bb.z; t.w += bb.w; }
+      *reinterpret_cast<float4*>(y + (int64_t)row * ldy + f) = t;
+    }
+  }
+}
+
+int spmm_long_rows(const int* rowptr, const int* col, const float* w, const float* x, int64_t ldx, float* y,
+                   int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, cudaStream_t stream) {
+  // caller guarantees the 128-bit path (num_feat % 4 == 0, 16-byte aligned rows)
+  if (num_rows == 0 || num_feat == 0) return GHSCN_OK;
+#define GHSCN_LONG(ITERS)                                                                                        \
+  do {                                                                                                           \
+    dim3 grid((unsigned)num_rows, (unsigned)ceil_div<int64_t>(num_feat, 128 * ITERS));                           \
+    if (w) spmm_longrow_kernel<ITERS, true><<<grid, 256, 0, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias,      \
+                                                                      (int)num_feat);                            \
+    else spmm_longrow_kernel<ITERS, false><<<grid, 256, 0, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias,       \
+                                                                     (int)num_feat);                             \
+  } while (0)
+  if (num_feat <= 128) GHSCN_LONG(1);
+  else if (num_feat <= 256) GHSCN_LONG(2);
+  else GHSCN_LONG(3);
+#undef GHSCN_LONG
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
 template <int VEC, int LPR, int ITERS>
 static int launch_spmm(const int* rowptr, const int* col, const float* w, const float* x, int64_t ldx, float* y,
                        int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, int relu,
@@ -152,6 +335,12 @@ static int dispatch_spmm(const int* rowptr, const int* col, const float* w, cons
                          int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, int relu,
                          cudaStream_t stream) {
   const int64_t nvec = ceil_div<int64_t>(num_feat, VEC);
+  if (VEC == 4 && nvec >= 32) {  // F >= 128 on the 128-bit path: CTA-staged indices, 4 slots in flight
+    if (nvec <= 32) return launch_spmm_wide<1>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+    if (nvec <= 64) return launch_spmm_wide<2>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+    if (nvec <= 96) return launch_spmm_wide<3>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+    return launch_spmm_wide<4>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+  }
 #define GHSCN_SPMM(LPR, ITERS) \
   return launch_spmm<VEC, LPR, ITERS>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream)
   if (nvec <= 4) GHSCN_SPMM(4, 1);
