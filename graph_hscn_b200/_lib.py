@@ -28,6 +28,8 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_csr_workspace_bytes": (SZ, [I64, I64, I32]),
     "ghscn_csr_build": (I32, [P, P, I64, I64, I32, P, P, P, P, SZ, P]),
     "ghscn_csr_add_loops": (I32, [P, P, P, I64, I64, P, P, P, P]),
+    "ghscn_split_tf32": (I32, [P, I64, P, P, P]),
+    "ghscn_split_tf32_cat": (I32, [P, I64, I64, I64, I64, I32, P, P]),
     "ghscn_colsum_workspace_bytes": (SZ, [I64, I64]),
     "ghscn_colsum": (I32, [P, I64, I64, I64, P, P, SZ, P]),
     "ghscn_virtual_csr": (I32, [P, P, P, P, P, I64, I64, I32] + [P] * 12 + [P]),
@@ -36,6 +38,8 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_edge_weights": (I32, [P, P, P, P, P, P, I64, I64, I32, I32, P, P]),
     "ghscn_loop_weights": (I32, [P, P, P, I64, I64, F32, P, P, P]),
     "ghscn_spmm": (I32, [P, P, P, P, I64, P, I64, P, I64, I64, I32, P]),
+    "ghscn_spmm_pool": (I32, [P, P, P, P, I64, P, I64, P, I64, I64, P]),
+    "ghscn_gat_scores": (I32, [P, P, P, P, F32, I64, P, P]),
     "ghscn_spmm_edge_grad": (I32, [P, P, P, P, I64, P, I64, I64, I64, I64, P, P]),
     "ghscn_segment_reduce": (I32, [P, I64, P, P, I64, I64, I32, P, I64, P]),
     "ghscn_segment_broadcast": (I32, [P, I64, P, P, I64, I64, I32, P, I64, P]),

@@ -154,6 +154,17 @@ int ghscn_row_dot(const float* x, int64_t ldx, const float* v, int64_t num_rows,
   return GHSCN_OK;
 }
 
+int ghscn_gat_scores(const int32_t* rowptr, const int32_t* col, const float* a_src, const float* a_dst,
+                     float negative_slope, int64_t num_rows, float* alpha, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_rows < ((int64_t)1 << 31));
+  if (num_rows == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(rowptr && col && a_src && alpha);
+  gat_scores_kernel<<<(unsigned)ceil_div<int64_t>(num_rows, 8), 256, 0, as_stream(stream)>>>(
+      rowptr, col, a_src, a_dst, negative_slope, (int)num_rows, alpha);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
 int ghscn_gat_pool_fwd(const int32_t* rowptr, const int32_t* col, const float* hs, int64_t ldhs,
                        const float* a_src, const float* a_dst, const float* bias, float negative_slope,
                        int64_t num_rows, int64_t num_feat, float* alpha, float* out, int64_t ldout,

@@ -168,6 +168,77 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
   }
 }
 
+// x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared) and lo = x - hi (exact in fp32).
+// Feeds the 3xTF32 tensor-core GEMM scheme: x.w ~= hi.hi + hi.lo + lo.hi, error ~2^-21 relative.
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, int64_t n,
+                                                         float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = ldg_f4(x + 4 * i);
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi + 4 * i) = h;
+    *reinterpret_cast<float4*>(lo + 4 * i) = l;
+  }
+  for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+// K-concatenated split: out[r, :] = [hi | hi | lo] (mode 0) or [hi | lo | hi] (mode 1) of x[r, :], rows
+// num_rows..num_rows_padded-1 zero.  With A in mode 0 and W in mode 1, ONE TF32 GEMM over the 3K-long reduction
+// computes x_hi.W_hi + x_hi.W_lo + x_lo.W_hi, i.e. the 3xTF32 product, in a single pass over the output.
+template <int VEC>
+__global__ void __launch_bounds__(256) split_tf32_cat_kernel(const float* __restrict__ x, int64_t ldx,
+                                                             int64_t num_rows, int64_t num_rows_padded, int K,
+                                                             int mode, float* __restrict__ out) {
+  const int kv = K / VEC;
+  const int64_t total = num_rows_padded * kv;
+  const int64_t ldo = 3 * (int64_t)K;
+  const int o1 = K, o2 = 2 * K;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / kv;
+    const int c = (int)(idx - r * kv) * VEC;
+    float v[VEC], h[VEC], l[VEC];
+    if (r < num_rows) {
+      if (VEC == 4) {
+        const float4 q = ldg_f4(x + r * ldx + c);
+        v[0] = q.x; v[1 % VEC] = q.y; v[2 % VEC] = q.z; v[3 % VEC] = q.w;
+      } else {
+        v[0] = __ldg(x + r * ldx + c);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[k] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      h[k] = __uint_as_float(__float_as_uint(v[k]) & 0xffffe000u);
+      l[k] = v[k] - h[k];
+    }
+    float* o = out + r * ldo + c;
+    if (VEC == 4) {
+      const float4 hh = make_float4(h[0], h[1 % VEC], h[2 % VEC], h[3 % VEC]);
+      const float4 ll = make_float4(l[0], l[1 % VEC], l[2 % VEC], l[3 % VEC]);
+      *reinterpret_cast<float4*>(o) = hh;
+      *reinterpret_cast<float4*>(o + o1) = mode == 0 ? hh : ll;
+      *reinterpret_cast<float4*>(o + o2) = mode == 0 ? ll : hh;
+    } else {
+      o[0] = h[0];
+      o[o1] = mode == 0 ? h[0] : l[0];
+      o[o2] = mode == 0 ? l[0] : h[0];
+    }
+  }
+}
+
 static inline bool aligned16(const void* a, const void* b) {
   return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) % 16) == 0;
 }
@@ -212,6 +283,38 @@ int ghscn_segment_broadcast(const float* dy, int64_t lddy, const int32_t* ptr, c
   else
     segment_broadcast_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(dy, lddy, ptr, perm, (int)num_segments,
                                                                         (int)num_feat, mean, dx, lddx);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+int ghscn_split_tf32(const float* x, int64_t n, float* hi, float* lo, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(n >= 0 && (n == 0 || (x && hi && lo)));
+  if (n == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) |
+                  reinterpret_cast<uintptr_t>(lo)) % 16) == 0);
+  const int64_t blocks = ceil_div<int64_t>(ceil_div<int64_t>(n, 4), 256);
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  split_tf32_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(x, n, hi, lo);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+int ghscn_split_tf32_cat(const float* x, int64_t ldx, int64_t num_rows, int64_t num_rows_padded, int64_t num_cols,
+                         int32_t mode, float* out, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_rows_padded >= num_rows && num_cols >= 0 && (mode == 0 || mode == 1));
+  GHSCN_REQUIRE(num_cols < ((int64_t)1 << 24));
+  if (num_rows_padded == 0 || num_cols == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(out && (num_rows == 0 || (x && ldx >= num_cols)));
+  const bool vec4 = num_cols % 4 == 0 && ldx % 4 == 0 && aligned16(x, out);
+  const int64_t work = num_rows_padded * (num_cols / (vec4 ? 4 : 1));
+  const int64_t cap = (int64_t)kNumSMs * 16, blocks = ceil_div<int64_t>(work, 256);
+  const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+  if (vec4)
+    split_tf32_cat_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(x, ldx, num_rows, num_rows_padded, (int)num_cols,
+                                                                   mode, out);
+  else
+    split_tf32_cat_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, ldx, num_rows, num_rows_padded, (int)num_cols,
+                                                                   mode, out);
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }

@@ -396,6 +396,19 @@ int ghscn_spmm(const int32_t* rowptr, const int32_t* col, const float* w, const 
   return dispatch_spmm<1>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, as_stream(stream));
 }
 
+int ghscn_spmm_pool(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, int64_t ldx, float* y,
+                    int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && ldx >= num_feat && ldy >= num_feat);
+  if (num_rows == 0 || num_feat == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(rowptr && col && x && y);
+  const bool vec4 = (num_feat % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                      reinterpret_cast<uintptr_t>(bias)) % 16 == 0);
+  if (vec4 && num_feat >= 64 && num_rows <= 65535)
+    return spmm_long_rows(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, as_stream(stream));
+  return ghscn_spmm(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, 0, stream);
+}
+
 int ghscn_spmm_edge_grad(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* x,
                          int64_t ldx, const float* dy, int64_t lddy, int64_t num_rows, int64_t num_feat,
                          int64_t num_edges, float* dw_edge, ghscn_stream_t stream) {

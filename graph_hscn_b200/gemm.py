@@ -1,0 +1,123 @@
+"""Dense projections (x W^T + b) of the layers: fp32-accurate GEMMs on the tensor cores via 3xTF32.
+
+The reference's `nn.Linear`s are host-side PyTorch code by the north_star's split (library GEMMs, not a
+hand-written kernel), but at h=300 they dominate the step (profiles/r1b: 47 % of the kernel time as fp32 SIMT
+sgemm).  Plain TF32 breaks the 1e-5 parity bar; the 3xTF32 split keeps fp32-level accuracy on the tensor pipe:
+
+    x = x_hi + x_lo,  W = W_hi + W_lo        (hi: low 13 mantissa bits cleared, exact in TF32; lo = rest)
+    x W^T ~= x_hi W_hi^T + x_hi W_lo^T + x_lo W_hi^T           (dropped lo.lo term ~ 2^-22 relative)
+
+A hand-written kernel (ghscn_split_tf32_cat) writes the operands K-concatenated -- A_cat = [hi | hi | lo],
+W_cat = [hi | lo | hi] -- so ONE library TF32 GEMM over the 3K-long reduction yields the three-term sum with a
+single pass over the output.  Weight gradients reduce over all N rows; tensor-core accumulation error grows
+with the reduction length, so they are computed per chunk of `DW_CHUNK` rows (batched GEMM) and the chunk
+results are added in fp32.  Mode "fp32" keeps plain cuBLAS fp32 (TF32 off).
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from ._lib import lib
+from .structure import _p, _stream
+
+_MODE = "3xtf32"
+MIN_ROWS, MIN_DIM = 4096, 64      # below this the GEMM is latency/bandwidth-bound: plain fp32 is as fast
+DW_CHUNK = 1024
+
+
+def set_gemm_mode(mode: str) -> None:
+    global _MODE
+    if mode not in ("fp32", "3xtf32"):
+        raise ValueError(mode)
+    _MODE = mode
+
+
+def gemm_mode() -> str:
+    return _MODE
+
+
+@contextmanager
+def _tf32():
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def split_tf32(x: Tensor) -> Tuple[Tensor, Tensor]:
+    x = x.contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    lib().call("ghscn_split_tf32", _p(x), x.numel(), _p(hi), _p(lo), _stream())
+    return hi, lo
+
+
+def split_cat(x: Tensor, mode: int, pad_rows_to: int = 1) -> Tensor:
+    """[rows_padded, 3K]: mode 0 -> [hi | hi | lo], mode 1 -> [hi | lo | hi]; padding rows are zero."""
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    n, k = x.shape
+    n_pad = (n + pad_rows_to - 1) // pad_rows_to * pad_rows_to
+    out = torch.empty((n_pad, 3 * k), dtype=torch.float32, device=x.device)
+    lib().call("ghscn_split_tf32_cat", _p(x), x.stride(0), n, n_pad, k, mode, _p(out), _stream())
+    return out
+
+
+class _Linear3xTF32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor]):
+        n, k = x.shape
+        a_cat = split_cat(x, 0, DW_CHUNK)                        # [Npad, 3K] = [xh | xh | xl]
+        w_cat = split_cat(weight, 1)                             # [out, 3K]  = [wh | wl | wh]
+        with _tf32():
+            if bias is not None:
+                y = torch.addmm(bias, a_cat[:n], w_cat.t())
+            else:
+                y = torch.mm(a_cat[:n], w_cat.t())
+        ctx.save_for_backward(a_cat, weight)
+        ctx.n, ctx.k, ctx.has_bias = n, k, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        a_cat, weight = ctx.saved_tensors
+        n, k = ctx.n, ctx.k
+        m = weight.size(0)
+        dx = dw = db = None
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need_dx or need_dw:
+            d_cat = split_cat(dy, 0, DW_CHUNK)                   # [Npad, 3m] = [dh | dh | dl]
+        if need_dx:
+            wh, wl = split_tf32(weight)
+            w_rows = torch.cat([wh, wl, wh], dim=0)              # [3m, K]: dX = [dh|dh|dl] . [wh; wl; wh]
+            with _tf32():
+                dx = torch.mm(d_cat[:n], w_rows)
+        if need_dw:
+            c = a_cat.size(0) // DW_CHUNK
+            a3 = a_cat.view(c, DW_CHUNK, 3 * k)
+            d3 = d_cat.view(c, DW_CHUNK, 3 * m)
+            dh, dl = d3[:, :, :m].transpose(1, 2), d3[:, :, 2 * m:].transpose(1, 2)
+            xh, xl = a3[:, :, :k], a3[:, :, 2 * k:]
+            with _tf32():
+                part = torch.bmm(dh, xh)
+                part.baddbmm_(dh, xl)
+                part.baddbmm_(dl, xh)
+            dw = part.sum(0)                                     # fp32 adds across chunks
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            from . import ops
+            db = ops.colsum(dy.contiguous())
+        return dx, dw, db
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+    """F.linear with fp32-level accuracy; large CUDA problems run as 3xTF32 on the tensor cores."""
+    if (_MODE == "3xtf32" and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
+            and x.size(0) >= MIN_ROWS and min(weight.shape) >= MIN_DIM):
+        return _Linear3xTF32.apply(x, weight, bias)
+    return F.linear(x, weight, bias)

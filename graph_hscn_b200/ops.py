@@ -270,6 +270,61 @@ def _gat_backward(ctx, dout, _dalpha, _das, _dad):
 torch.library.register_autograd("ghscn::gat_pool", _gat_backward, setup_context=_gat_setup)
 
 
+class GatPoolInputWidth(torch.autograd.Function):
+    """GATConv forward with the pooled sum taken at the INPUT width:
+        out_i = sum_s alpha_s (x_s W_src^T) + b = (sum_s alpha_s x_s) W_src^T + b,   a_src = x (W_src^T att_src)
+    so the [N,F]x[F,H] projection of every source node disappears from the forward (N >> number of destination
+    rows for the local -> virtual pool).  The backward -- never reached in HSCN training, where the virtual branch
+    is dead w.r.t. the loss -- materialises hs = x W_src^T and reuses the K5 backward kernels."""
+
+    @staticmethod
+    def forward(ctx, x_src, x_dst, w_src, w_dst, att_src, att_dst, bias, slope, rowptr, col, rowptr_t, col_t, map_t):
+        from . import gemm
+        x_src = _rowmajor(x_src)
+        V = rowptr.numel() - 1
+        dev = x_src.device
+        L, st = lib(), _stream()
+        a_src = row_dot(x_src, att_src @ w_src)
+        if x_dst is not None:
+            x_dst = _rowmajor(x_dst)
+            a_dst = row_dot(x_dst, att_dst @ w_dst)
+        else:
+            a_dst = None
+        alpha = torch.zeros(col.numel(), dtype=torch.float32, device=dev)
+        L.call("ghscn_gat_scores", _p(rowptr), _p(col), _p(a_src), _p(a_dst), float(slope), V, _p(alpha), st)
+        Fin = x_src.size(1)
+        pooled = torch.empty((V, Fin), dtype=torch.float32, device=dev)
+        L.call("ghscn_spmm_pool", _p(rowptr), _p(col), _p(alpha), _p(x_src), x_src.stride(0), _p(pooled), Fin, None,
+               V, Fin, st)
+        out = gemm.linear(pooled, w_src, bias)
+        ctx.slope = slope
+        ctx.save_for_backward(x_src, x_dst, w_src, w_dst, att_src, att_dst, alpha, a_src, a_dst, rowptr, col, rowptr_t,
+                              col_t, map_t)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x_src, x_dst, w_src, w_dst, att_src, att_dst, alpha, a_src, a_dst, rowptr, col, rowptr_t, col_t,
+         map_t) = ctx.saved_tensors
+        dout = dout.contiguous()
+        hs = x_src @ w_src.t()
+        dhs, da_src, da_dst = gat_pool_bwd(rowptr, col, rowptr_t, col_t, map_t, hs, a_src, a_dst, alpha, att_src, dout,
+                                           ctx.slope)
+        dx_src = dhs @ w_src
+        dw_src = dhs.t() @ x_src
+        datt_src = da_src @ hs
+        dx_dst = dw_dst = datt_dst = None
+        if x_dst is not None:
+            hd = x_dst @ w_dst.t()
+            dhd = da_dst.unsqueeze(1) * att_dst.unsqueeze(0)
+            dx_dst = dhd @ w_dst
+            dw_dst = dhd.t() @ x_dst
+            datt_dst = da_dst @ hd
+        dbias = colsum(dout) if ctx.has_bias else None
+        return (dx_src, dx_dst, dw_src, dw_dst, datt_src, datt_dst, dbias, None, None, None, None, None, None)
+
+
 # =============================================================================================
 # K6  fused MinCUT pool
 # =============================================================================================

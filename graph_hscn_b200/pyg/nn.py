@@ -21,6 +21,7 @@ import torch.nn.functional as F
 from torch import Tensor
 from torch.nn.parameter import UninitializedParameter
 
+from .. import gemm, ops
 from ..structure import _require_cuda, structure_cache
 
 
@@ -61,12 +62,16 @@ class Linear(nn.Module):
                 bound = 1.0 / math.sqrt(self.weight.size(1)) if self.weight.size(1) > 0 else 0.0
                 nn.init.uniform_(self.bias, -bound, bound)
 
-    def forward(self, x: Tensor) -> Tensor:
+    def materialize(self, in_channels: int, device) -> None:
+        """Resolve a lazy `in_channels=-1` weight (PyG does this in a forward pre-hook)."""
         if isinstance(self.weight, UninitializedParameter):
-            self.in_channels = x.size(-1)
-            self.weight.materialize((self.out_channels, self.in_channels), device=x.device)
+            self.in_channels = in_channels
+            self.weight.materialize((self.out_channels, self.in_channels), device=device)
             self.reset_parameters()
-        return F.linear(x, self.weight, self.bias)
+
+    def forward(self, x: Tensor) -> Tensor:
+        self.materialize(x.size(-1), x.device)
+        return gemm.linear(x, self.weight, self.bias)
 
     def extra_repr(self) -> str:
         return f"{self.in_channels}, {self.out_channels}, bias={self.bias is not None}"
@@ -204,22 +209,28 @@ class GATConv(MessagePassing):
         if edge_attr is not None:
             raise NotImplementedError("GATConv edge features are not on the reference's path")
         if isinstance(x, Tensor):
-            hs = self.lin_src(x)
-            hd = hs
+            x_src = x_dst = x
         else:
             x_src, x_dst = x
-            hs = self.lin_src(x_src)
-            hd = self.lin_dst(x_dst) if x_dst is not None else None
-        _require_cuda(hs, edge_index)
-        n_src = hs.size(0)
-        n_dst = hd.size(0) if hd is not None else (size[1] if size is not None else n_src)
+        _require_cuda(x_src, edge_index)
+        if x_src.dtype != torch.float32:
+            x_src = x_src.float()
+        self.lin_src.materialize(x_src.size(-1), x_src.device)
+        if x_dst is not None:
+            if x_dst.dtype != torch.float32:
+                x_dst = x_dst.float()
+            self.lin_dst.materialize(x_dst.size(-1), x_dst.device)
+        n_src = x_src.size(0)
+        n_dst = x_dst.size(0) if x_dst is not None else (size[1] if size is not None else n_src)
         if self.add_self_loops and n_src != n_dst:
             raise NotImplementedError("add_self_loops on a bipartite relation is not on the reference's path")
         st = structure_cache().graph(edge_index, n_src, n_dst, self.add_self_loops)
         d, s = st.by_dst, st.by_src
-        out, *_ = torch.ops.ghscn.gat_pool(d.rowptr, d.col, s.rowptr, s.col, st.slot_map_t, hs, hd,
-                                            self.att_src.view(-1), self.att_dst.view(-1), self.bias,
-                                            float(self.negative_slope))
+        # attention scores from x (W^T att) and the pooled sum at the input width: no [N,F]x[F,H] projection
+        out = ops.GatPoolInputWidth.apply(
+            x_src, x_dst, self.lin_src.weight, self.lin_dst.weight if x_dst is not None else None,
+            self.att_src.view(-1), self.att_dst.view(-1), self.bias, float(self.negative_slope),
+            d.rowptr, d.col, s.rowptr, s.col, st.slot_map_t)
         return out
 
 

@@ -108,6 +108,11 @@ GHSCN_API int ghscn_loop_weights(const int64_t* row, const int64_t* colidx, cons
 GHSCN_API int ghscn_spmm(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, int64_t ldx,
                          float* y, int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat,
                          int32_t relu, ghscn_stream_t stream);
+/* Same contraction for pooling relations (few destination rows, many sources each, e.g. local -> virtual):
+ * one CTA per row, fixed-order (deterministic) combination of 8 partial sums instead of the sequential order. */
+GHSCN_API int ghscn_spmm_pool(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, int64_t ldx,
+                              float* y, int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat,
+                              ghscn_stream_t stream);
 /* d(edge weight)[s] = <dy[row(s),:], x[col[s],:]> written at the ORIGINAL edge position perm[s]
  * (entries for appended loops, perm >= num_edges, are skipped).  perm == NULL writes dw_edge[s]. */
 GHSCN_API int ghscn_spmm_edge_grad(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* x,
@@ -132,6 +137,15 @@ GHSCN_API size_t ghscn_colsum_workspace_bytes(int64_t num_rows, int64_t num_feat
 GHSCN_API int ghscn_colsum(const float* x, int64_t ldx, int64_t num_rows, int64_t num_feat, float* out,
                            void* workspace, size_t workspace_bytes, ghscn_stream_t stream);
 
+/* hi/lo split for the 3xTF32 GEMM scheme used by the layers' dense projections (x W^T of GCNConv / GATConv /
+ * Linear): hi = x with the low 13 mantissa bits cleared (exact in TF32), lo = x - hi.  16-byte aligned buffers. */
+GHSCN_API int ghscn_split_tf32(const float* x, int64_t n, float* hi, float* lo, ghscn_stream_t stream);
+/* K-concatenated form: out[r,:] (3*num_cols wide) = [hi | hi | lo] (mode 0) or [hi | lo | hi] (mode 1) of row r;
+ * rows num_rows..num_rows_padded-1 are zero.  A in mode 0 times W in mode 1 over the 3K-long reduction is the
+ * 3xTF32 product x_hi.W_hi + x_hi.W_lo + x_lo.W_hi in ONE tensor-core GEMM. */
+GHSCN_API int ghscn_split_tf32_cat(const float* x, int64_t ldx, int64_t num_rows, int64_t num_rows_padded,
+                                   int64_t num_cols, int32_t mode, float* out, ghscn_stream_t stream);
+
 /* ---- K5: bipartite GAT cluster pool (local -> virtual) ---------------------------------------
  * Replaces GATConv((-1,-1), H, add_self_loops=False) on ("local","to","virtual")
  * (model/hscn.py:85-87,118-125).  SURVEY 8a row a9, Appendix A.8.  heads = 1.
@@ -142,6 +156,10 @@ GHSCN_API int ghscn_colsum(const float* x, int64_t ldx, int64_t num_rows, int64_
  */
 GHSCN_API int ghscn_row_dot(const float* x, int64_t ldx, const float* v, int64_t num_rows, int64_t num_feat,
                             float* out, ghscn_stream_t stream);
+/* alpha[s] only (segment softmax of the leaky-relu scores); the pooled sum can then run at the INPUT width:
+ * sum_s alpha_s (x_s W^T) = (sum_s alpha_s x_s) W^T, which removes the [N,F]x[F,H] projection of all local nodes. */
+GHSCN_API int ghscn_gat_scores(const int32_t* rowptr, const int32_t* col, const float* a_src, const float* a_dst,
+                               float negative_slope, int64_t num_rows, float* alpha, ghscn_stream_t stream);
 GHSCN_API int ghscn_gat_pool_fwd(const int32_t* rowptr, const int32_t* col, const float* hs, int64_t ldhs,
                                  const float* a_src, const float* a_dst, const float* bias, float negative_slope,
                                  int64_t num_rows, int64_t num_feat, float* alpha, float* out, int64_t ldout,

@@ -60,6 +60,36 @@ def test_virtual_csr_equals_sort(cuda, padded, K):
     _same(st_vv.by_src, build_csr(vv[0], vv[1], V, False))
 
 
+def test_linear_3xtf32_is_fp32_accurate(cuda):
+    """The 3xTF32 tensor-core projection must be as accurate as a plain fp32 GEMM (parity bar 1e-5)."""
+    from graph_hscn_b200 import gemm
+    from tests.util import rel_err
+    g = torch.Generator().manual_seed(6)
+    n, k, m = 4096, 300, 300
+    x = (torch.randn(n, k, generator=g) * 3).to(cuda).requires_grad_()
+    w = (torch.randn(m, k, generator=g) / 17).to(cuda).requires_grad_()
+    b = torch.randn(m, generator=g).to(cuda).requires_grad_()
+    gy = torch.randn(n, m, generator=g).to(cuda)
+    hi, lo = gemm.split_tf32(x.detach())
+    assert torch.equal(hi + lo, x.detach()) and bool(((hi.view(torch.int32) & 0x1FFF) == 0).all())
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    gx, gw, gb = torch.autograd.grad(ref, (x, w, b), gy.double())
+    gemm.set_gemm_mode("3xtf32")
+    y = gemm.linear(x, w, b)
+    dx, dw, db = torch.autograd.grad(y, (x, w, b), gy)
+    gemm.set_gemm_mode("fp32")
+    y32 = gemm.linear(x, w, b)
+    dx32, dw32, db32 = torch.autograd.grad(y32, (x, w, b), gy)
+    gemm.set_gemm_mode("3xtf32")
+    for name, a, a32, r in [("y", y, y32, ref), ("dx", dx, dx32, gx), ("dw", dw, dw32, gw), ("db", db, db32, gb)]:
+        e3, e32 = rel_err(a, r.float()), rel_err(a32, r.float())
+        assert e3 < 2e-6, f"{name}: 3xTF32 error {e3:.2e} (plain fp32 {e32:.2e})"
+    torch.backends.cuda.matmul.allow_tf32 = True          # plain TF32 would NOT meet the bar
+    ytf = torch.nn.functional.linear(x, w, b)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    assert rel_err(ytf, ref.float()) > 1e-5
+
+
 def test_colsum_matches_torch(cuda):
     g = torch.Generator().manual_seed(5)
     for n, f in [(1, 4), (18269, 300), (1000, 10), (65, 33)]:
