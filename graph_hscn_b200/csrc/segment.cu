@@ -192,9 +192,11 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 
-// K-concatenated split: out[r, :] = [hi | hi | lo] (mode 0) or [hi | lo | hi] (mode 1) of x[r, :], rows
+// K-concatenated split: out[r, :] = [lo | hi | hi] (mode 0) or [hi | lo | hi] (mode 1) of x[r, :], rows
 // num_rows..num_rows_padded-1 zero.  With A in mode 0 and W in mode 1, ONE TF32 GEMM over the 3K-long reduction
-// computes x_hi.W_hi + x_hi.W_lo + x_lo.W_hi, i.e. the 3xTF32 product, in a single pass over the output.
+// computes x_lo.W_hi + x_hi.W_lo + x_hi.W_hi, i.e. the 3xTF32 product, in a single pass over the output.  The
+// two small cross terms come FIRST in the reduction so that the tensor core's accumulator is still small when
+// they are added (its additions are not correctly rounded; adding them after the big term loses them).
 template <int VEC>
 __global__ void __launch_bounds__(256) split_tf32_cat_kernel(const float* __restrict__ x, int64_t ldx,
                                                              int64_t num_rows, int64_t num_rows_padded, int K,
@@ -228,13 +230,13 @@ __global__ void __launch_bounds__(256) split_tf32_cat_kernel(const float* __rest
     if (VEC == 4) {
       const float4 hh = make_float4(h[0], h[1 % VEC], h[2 % VEC], h[3 % VEC]);
       const float4 ll = make_float4(l[0], l[1 % VEC], l[2 % VEC], l[3 % VEC]);
-      *reinterpret_cast<float4*>(o) = hh;
+      *reinterpret_cast<float4*>(o) = mode == 0 ? ll : hh;
       *reinterpret_cast<float4*>(o + o1) = mode == 0 ? hh : ll;
-      *reinterpret_cast<float4*>(o + o2) = mode == 0 ? ll : hh;
+      *reinterpret_cast<float4*>(o + o2) = hh;
     } else {
-      o[0] = h[0];
+      o[0] = mode == 0 ? l[0] : h[0];
       o[o1] = mode == 0 ? h[0] : l[0];
-      o[o2] = mode == 0 ? l[0] : h[0];
+      o[o2] = h[0];
     }
   }
 }

@@ -7,9 +7,10 @@ sgemm).  Plain TF32 breaks the 1e-5 parity bar; the 3xTF32 split keeps fp32-leve
     x = x_hi + x_lo,  W = W_hi + W_lo        (hi: low 13 mantissa bits cleared, exact in TF32; lo = rest)
     x W^T ~= x_hi W_hi^T + x_hi W_lo^T + x_lo W_hi^T           (dropped lo.lo term ~ 2^-22 relative)
 
-A hand-written kernel (ghscn_split_tf32_cat) writes the operands K-concatenated -- A_cat = [hi | hi | lo],
+A hand-written kernel (ghscn_split_tf32_cat) writes the operands K-concatenated -- A_cat = [lo | hi | hi],
 W_cat = [hi | lo | hi] -- so ONE library TF32 GEMM over the 3K-long reduction yields the three-term sum with a
-single pass over the output.  Weight gradients reduce over all N rows; tensor-core accumulation error grows
+single pass over the output; the two small cross terms lead the reduction so they are accumulated while the
+tensor core's (not correctly rounded) accumulator is still small.  Weight gradients reduce over all N rows; tensor-core accumulation error grows
 with the reduction length, so they are computed per chunk of `DW_CHUNK` rows (batched GEMM) and the chunk
 results are added in fp32.  Mode "fp32" keeps plain cuBLAS fp32 (TF32 off).
 """
@@ -59,7 +60,7 @@ def split_tf32(x: Tensor) -> Tuple[Tensor, Tensor]:
 
 
 def split_cat(x: Tensor, mode: int, pad_rows_to: int = 1) -> Tensor:
-    """[rows_padded, 3K]: mode 0 -> [hi | hi | lo], mode 1 -> [hi | lo | hi]; padding rows are zero."""
+    """[rows_padded, 3K]: mode 0 -> [lo | hi | hi], mode 1 -> [hi | lo | hi]; padding rows are zero."""
     if x.stride(1) != 1:
         x = x.contiguous()
     n, k = x.shape
@@ -73,7 +74,7 @@ class _Linear3xTF32(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor]):
         n, k = x.shape
-        a_cat = split_cat(x, 0, DW_CHUNK)                        # [Npad, 3K] = [xh | xh | xl]
+        a_cat = split_cat(x, 0, DW_CHUNK)                        # [Npad, 3K] = [xl | xh | xh]
         w_cat = split_cat(weight, 1)                             # [out, 3K]  = [wh | wl | wh]
         with _tf32():
             if bias is not None:
@@ -92,22 +93,22 @@ class _Linear3xTF32(torch.autograd.Function):
         dx = dw = db = None
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if need_dx or need_dw:
-            d_cat = split_cat(dy, 0, DW_CHUNK)                   # [Npad, 3m] = [dh | dh | dl]
+            d_cat = split_cat(dy, 0, DW_CHUNK)                   # [Npad, 3m] = [dl | dh | dh]
         if need_dx:
             wh, wl = split_tf32(weight)
-            w_rows = torch.cat([wh, wl, wh], dim=0)              # [3m, K]: dX = [dh|dh|dl] . [wh; wl; wh]
+            w_rows = torch.cat([wh, wl, wh], dim=0)              # [3m, K]: dX = [dl|dh|dh] . [wh; wl; wh]
             with _tf32():
                 dx = torch.mm(d_cat[:n], w_rows)
         if need_dw:
             c = a_cat.size(0) // DW_CHUNK
             a3 = a_cat.view(c, DW_CHUNK, 3 * k)
             d3 = d_cat.view(c, DW_CHUNK, 3 * m)
-            dh, dl = d3[:, :, :m].transpose(1, 2), d3[:, :, 2 * m:].transpose(1, 2)
-            xh, xl = a3[:, :, :k], a3[:, :, 2 * k:]
+            dl, dh = d3[:, :, :m].transpose(1, 2), d3[:, :, 2 * m:].transpose(1, 2)
+            xl, xh = a3[:, :, :k], a3[:, :, 2 * k:]
             with _tf32():
-                part = torch.bmm(dh, xh)
+                part = torch.bmm(dl, xh)
                 part.baddbmm_(dh, xl)
-                part.baddbmm_(dl, xh)
+                part.baddbmm_(dh, xh)
             dw = part.sum(0)                                     # fp32 adds across chunks
         if ctx.has_bias and ctx.needs_input_grad[2]:
             from . import ops

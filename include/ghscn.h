@@ -140,9 +140,9 @@ GHSCN_API int ghscn_colsum(const float* x, int64_t ldx, int64_t num_rows, int64_
 /* hi/lo split for the 3xTF32 GEMM scheme used by the layers' dense projections (x W^T of GCNConv / GATConv /
  * Linear): hi = x with the low 13 mantissa bits cleared (exact in TF32), lo = x - hi.  16-byte aligned buffers. */
 GHSCN_API int ghscn_split_tf32(const float* x, int64_t n, float* hi, float* lo, ghscn_stream_t stream);
-/* K-concatenated form: out[r,:] (3*num_cols wide) = [hi | hi | lo] (mode 0) or [hi | lo | hi] (mode 1) of row r;
+/* K-concatenated form: out[r,:] (3*num_cols wide) = [lo | hi | hi] (mode 0) or [hi | lo | hi] (mode 1) of row r;
  * rows num_rows..num_rows_padded-1 are zero.  A in mode 0 times W in mode 1 over the 3K-long reduction is the
- * 3xTF32 product x_hi.W_hi + x_hi.W_lo + x_lo.W_hi in ONE tensor-core GEMM. */
+ * 3xTF32 product x_lo.W_hi + x_hi.W_lo + x_hi.W_hi (small terms first) in ONE tensor-core GEMM. */
 GHSCN_API int ghscn_split_tf32_cat(const float* x, int64_t ldx, int64_t num_rows, int64_t num_rows_padded,
                                    int64_t num_cols, int32_t mode, float* out, ghscn_stream_t stream);
 
