@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) segment_broadcast_kernel(const float* __r
 
 // ---- column sum (bias gradients: db = sum_rows dY) ---------------------------------------------------
 // Stage 1: CTA (rows chunk, 128-column tile) -> partial[chunk, :];  stage 2: fixed-order sum over chunks.
-constexpr int kColsumRows = 64;  // rows per CTA (8 per warp)
+constexpr int kColsumRows = 256;  // rows per CTA (32 per warp)
 
 template <int VEC>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int64_t ldx,

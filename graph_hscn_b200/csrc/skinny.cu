@@ -1,0 +1,203 @@
+// Tall-skinny dense projections: y = x W^T + b with a tiny input width (K <= 32), N in the tens of thousands.
+// These are the raw-feature layers of the reference (9 OGB atom features -> hidden: GCNConv layer 1 at
+// model/hscn.py:88-93, GraphConv lin_rel / lin_root at model/hscn.py:32-34, the SCN cluster MLP at
+// model/hscn.py:50-54).  They are pure HBM streaming problems (read or write one [N, M] matrix once, ~50 MFLOP),
+// which a tiled SIMT GEMM handles poorly (7-36 us each in profiles/r1d); here each is one pass at memory speed.
+//   fwd : y[n,m]  = sum_k x[n,k] W[m,k] + b[m]          W^T staged in shared memory, warp per row, lanes over m
+//   dW  : dW[m,k] = sum_n dY[n,m] x[n,k]                two-stage fixed-order reduction over 128-row chunks
+//   dX  : dx[n,k] = sum_m dY[n,m] W[m,k]                warp per row, lanes over k
+#include "common.cuh"
+
+namespace ghscn {
+
+constexpr int kSkinnyMaxK = 32;
+constexpr int kDwRows = 128;
+
+__global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict__ x, int64_t ldx,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         int num_rows, int K, int M, float* __restrict__ y,
+                                                         int64_t ldy) {
+  extern __shared__ float wt[];  // [K][M] (transposed: consecutive lanes read consecutive m)
+  for (int i = threadIdx.x; i < K * M; i += blockDim.x) {
+    const int m = i / K, k = i - m * K;
+    wt[k * M + m] = w[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < num_rows; n += warps) {
+    const float xv = lane < K ? __ldg(x + (int64_t)n * ldx + lane) : 0.f;
+    for (int m = lane; m < M; m += 32) {
+      float acc = bias ? __ldg(bias + m) : 0.f;
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) acc = fmaf(__shfl_sync(kFullMask, xv, k), wt[k * M + m], acc);
+      y[(int64_t)n * ldy + m] = acc;
+    }
+  }
+}
+
+// partial[chunk][m][k] = sum over the chunk's rows of dY[n,m] x[n,k]; thread owns one m, K register accumulators.
+template <int KMAX>
+__global__ void __launch_bounds__(128) skinny_dw_partial_kernel(const float* __restrict__ dy, int64_t lddy,
+                                                                const float* __restrict__ x, int64_t ldx,
+                                                                int num_rows, int K, int M,
+                                                                float* __restrict__ partial) {
+  __shared__ float xs[kDwRows * KMAX];
+  const int r0 = blockIdx.y * kDwRows;
+  const int rows = min(kDwRows, num_rows - r0);
+  for (int i = threadIdx.x; i < rows * K; i += blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    xs[r * KMAX + k] = __ldg(x + (int64_t)(r0 + r) * ldx + k);
+  }
+  __syncthreads();
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float acc[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  const float* dp = dy + (int64_t)r0 * lddy + m;
+  int r = 0;
+  for (; r + 3 < rows; r += 4) {
+    const float d0 = __ldg(dp + (int64_t)r * lddy), d1 = __ldg(dp + (int64_t)(r + 1) * lddy);
+    const float d2 = __ldg(dp + (int64_t)(r + 2) * lddy), d3 = __ldg(dp + (int64_t)(r + 3) * lddy);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        acc[k] = fmaf(d0, xs[r * KMAX + k], acc[k]);
+        acc[k] = fmaf(d1, xs[(r + 1) * KMAX + k], acc[k]);
+        acc[k] = fmaf(d2, xs[(r + 2) * KMAX + k], acc[k]);
+        acc[k] = fmaf(d3, xs[(r + 3) * KMAX + k], acc[k]);
+      }
+    }
+  }
+  for (; r < rows; ++r) {
+    const float d0 = __ldg(dp + (int64_t)r * lddy);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) acc[k] = fmaf(d0, xs[r * KMAX + k], acc[k]);
+  }
+  float* out = partial + ((int64_t)blockIdx.y * M + m) * K;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (k < K) out[k] = acc[k];
+}
+
+// out[i] = sum_c partial[c][i]; one CTA per 32 outputs, 8 warps stride the chunks, fixed-order combine.
+__global__ void __launch_bounds__(256) chunk_sum_kernel(const float* __restrict__ partial, int num_chunks,
+                                                        int64_t width, float* __restrict__ out) {
+  __shared__ float part[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+  float t0 = 0.f, t1 = 0.f;
+  if (i < width) {
+    int c = wid;
+    for (; c + 8 < num_chunks; c += 16) {
+      t0 += partial[(int64_t)c * width + i];
+      t1 += partial[(int64_t)(c + 8) * width + i];
+    }
+    if (c < num_chunks) t0 += partial[(int64_t)c * width + i];
+  }
+  part[wid][lane] = t0 + t1;
+  __syncthreads();
+  if (wid == 0 && i < width) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    out[i] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) skinny_dx_kernel(const float* __restrict__ dy, int64_t lddy,
+                                                        const float* __restrict__ w, int num_rows, int K, int M,
+                                                        float* __restrict__ dx, int64_t lddx) {
+  extern __shared__ float ws[];  // [M][K] as given
+  for (int i = threadIdx.x; i < K * M; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < num_rows; n += warps) {
+    float acc = 0.f;
+    for (int m0 = 0; m0 < M; m0 += 32) {
+      const float dv = (m0 + lane < M) ? __ldg(dy + (int64_t)n * lddy + m0 + lane) : 0.f;
+      const int mm = min(32, M - m0);
+      for (int j = 0; j < mm; ++j) {
+        const float d = __shfl_sync(kFullMask, dv, j);
+        if (lane < K) acc = fmaf(d, ws[(m0 + j) * K + lane], acc);
+      }
+    }
+    if (lane < K) dx[(int64_t)n * lddx + lane] = acc;
+  }
+}
+
+}  // namespace ghscn
+
+using namespace ghscn;
+
+extern "C" {
+
+int ghscn_skinny_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias, int64_t num_rows,
+                            int64_t in_feat, int64_t out_feat, float* y, int64_t ldy, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_rows >= 0 && in_feat > 0 && out_feat > 0 && num_rows < ((int64_t)1 << 31));
+  if (in_feat > kSkinnyMaxK || in_feat * out_feat * 4 > 96 * 1024) return GHSCN_E_UNSUPPORTED;
+  if (num_rows == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(x && w && y && ldx >= in_feat && ldy >= out_feat);
+  const size_t shm = (size_t)in_feat * out_feat * 4;
+  if (shm > 48 * 1024)
+    cudaFuncSetAttribute(skinny_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  const int64_t want = ceil_div<int64_t>(num_rows, 8 * 4);  // ~4 rows per warp
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  skinny_fwd_kernel<<<(unsigned)(want < cap ? (want > 0 ? want : 1) : cap), 256, shm, as_stream(stream)>>>(
+      x, ldx, w, bias, (int)num_rows, (int)in_feat, (int)out_feat, y, ldy);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+size_t ghscn_skinny_dw_workspace_bytes(int64_t num_rows, int64_t in_feat, int64_t out_feat) {
+  if (num_rows < 0 || in_feat < 0 || out_feat < 0) return 0;
+  return (size_t)ceil_div<int64_t>(num_rows > 0 ? num_rows : 1, kDwRows) * in_feat * out_feat * 4 + 256;
+}
+
+int ghscn_skinny_linear_dw(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t num_rows,
+                           int64_t in_feat, int64_t out_feat, float* dw, void* workspace, size_t workspace_bytes,
+                           ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(num_rows >= 0 && in_feat > 0 && out_feat > 0 && num_rows < ((int64_t)1 << 31));
+  if (in_feat > kSkinnyMaxK) return GHSCN_E_UNSUPPORTED;
+  GHSCN_REQUIRE(dw && (num_rows == 0 || (dy && x && lddy >= out_feat && ldx >= in_feat)));
+  if (workspace == nullptr || workspace_bytes < ghscn_skinny_dw_workspace_bytes(num_rows, in_feat, out_feat))
+    return GHSCN_E_WORKSPACE;
+  cudaStream_t stream = as_stream(stream_);
+  const int chunks = (int)ceil_div<int64_t>(num_rows, kDwRows);
+  if (chunks > 65535) return GHSCN_E_UNSUPPORTED;
+  float* partial = static_cast<float*>(workspace);
+  const int K = (int)in_feat, M = (int)out_feat;
+  if (chunks > 0) {
+    dim3 grid((unsigned)ceil_div(M, 128), (unsigned)chunks);
+    if (K <= 16)
+      skinny_dw_partial_kernel<16><<<grid, 128, 0, stream>>>(dy, lddy, x, ldx, (int)num_rows, K, M, partial);
+    else
+      skinny_dw_partial_kernel<32><<<grid, 128, 0, stream>>>(dy, lddy, x, ldx, (int)num_rows, K, M, partial);
+  }
+  const int64_t width = (int64_t)M * K;
+  chunk_sum_kernel<<<(unsigned)ceil_div<int64_t>(width, 32), 256, 0, stream>>>(partial, chunks, width, dw);
+  GHSCN_LAUNCH_CHECK_N(chunks > 0 ? 2 : 1);
+  return GHSCN_OK;
+}
+
+int ghscn_skinny_linear_dx(const float* dy, int64_t lddy, const float* w, int64_t num_rows, int64_t in_feat,
+                           int64_t out_feat, float* dx, int64_t lddx, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_rows >= 0 && in_feat > 0 && out_feat > 0 && num_rows < ((int64_t)1 << 31));
+  if (in_feat > kSkinnyMaxK || in_feat * out_feat * 4 > 96 * 1024) return GHSCN_E_UNSUPPORTED;
+  if (num_rows == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(dy && w && dx && lddy >= out_feat && lddx >= in_feat);
+  const size_t shm = (size_t)in_feat * out_feat * 4;
+  if (shm > 48 * 1024)
+    cudaFuncSetAttribute(skinny_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  const int64_t want = ceil_div<int64_t>(num_rows, 8 * 4);
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  skinny_dx_kernel<<<(unsigned)(want < cap ? (want > 0 ? want : 1) : cap), 256, shm, as_stream(stream)>>>(
+      dy, lddy, w, (int)num_rows, (int)in_feat, (int)out_feat, dx, lddx);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+}  // extern "C"

@@ -116,8 +116,53 @@ class _Linear3xTF32(torch.autograd.Function):
         return dx, dw, db
 
 
+class _LinearSkinny(torch.autograd.Function):
+    """y = x W^T + b for a tiny input width (<= 32) and many rows: hand-written streaming kernels (csrc/skinny.cu)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor]):
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        weight = weight.contiguous()
+        n, k = x.shape
+        m = weight.size(0)
+        y = torch.empty((n, m), dtype=torch.float32, device=x.device)
+        lib().call("ghscn_skinny_linear_fwd", _p(x), x.stride(0), _p(weight), _p(bias), n, k, m, _p(y), m, _stream())
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, k = x.shape
+        m = weight.size(0)
+        L, st = lib(), _stream()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((n, k), dtype=torch.float32, device=x.device)
+            L.call("ghscn_skinny_linear_dx", _p(dy), m, _p(weight), n, k, m, _p(dx), k, st)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((m, k), dtype=torch.float32, device=x.device)
+            ws_bytes = L.query("ghscn_skinny_dw_workspace_bytes", n, k, m)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            L.call("ghscn_skinny_linear_dw", _p(dy), m, _p(x), x.stride(0), n, k, m, _p(dw), _p(ws), ws_bytes, st)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            from . import ops
+            db = ops.colsum(dy)
+        return dx, dw, db
+
+
+SKINNY_MAX_IN, SKINNY_MIN_ROWS = 32, 2048
+
+
 def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
-    """F.linear with fp32-level accuracy; large CUDA problems run as 3xTF32 on the tensor cores."""
+    """F.linear with fp32-level accuracy: tall-skinny problems (raw-feature layers) stream through hand-written
+    kernels, large square ones run as 3xTF32 on the tensor cores, everything else is plain cuBLAS fp32."""
+    if (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.size(0) >= SKINNY_MIN_ROWS
+            and weight.size(1) <= SKINNY_MAX_IN and weight.numel() * 4 <= 96 * 1024):
+        return _LinearSkinny.apply(x, weight, bias)
     if (_MODE == "3xtf32" and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
             and x.size(0) >= MIN_ROWS and min(weight.shape) >= MIN_DIM):
         return _Linear3xTF32.apply(x, weight, bias)

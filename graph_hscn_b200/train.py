@@ -73,6 +73,22 @@ class FlatGradients:
     def zero(self) -> None:
         self.flat.zero_()
 
+    def flatten_parameters(self) -> Tensor:
+        """Re-home the live parameters as views of ONE flat fp32 leaf whose .grad is the flat gradient buffer:
+        the optimizer step becomes a single elementwise kernel over one tensor (AdamW is elementwise and all
+        parameters share one group, so this is the same update as per-parameter AdamW)."""
+        flat_p = torch.empty_like(self.flat)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            flat_p[off:off + n].copy_(p.data.reshape(-1))
+            p.data = flat_p[off:off + n].view_as(p)
+            off += n
+        flat_p.requires_grad_(True)
+        flat_p.grad = self.flat
+        self.flat_param = flat_p
+        return flat_p
+
     def all_reduce_mean(self, world: Optional[int] = None, group=None) -> None:
         if not (dist.is_available() and dist.is_initialized()):
             return
@@ -172,8 +188,8 @@ class GraphHSCNStep:
         kw = dict(lr=cfg.lr, weight_decay=cfg.weight_decay)
         if self.device.type == "cuda":
             kw.update(fused=True, capturable=True)
-        self.scn_opt = torch.optim.AdamW(self.scn_grads.params, **kw)
-        self.hscn_opt = torch.optim.AdamW(self.hscn_grads.params, **kw)
+        self.scn_opt = torch.optim.AdamW([self.scn_grads.flatten_parameters()], **kw)
+        self.hscn_opt = torch.optim.AdamW([self.hscn_grads.flatten_parameters()], **kw)
         structure_cache().clear()
 
     def _cast(self, x: Tensor) -> Tensor:

@@ -146,6 +146,20 @@ GHSCN_API int ghscn_split_tf32(const float* x, int64_t n, float* hi, float* lo, 
 GHSCN_API int ghscn_split_tf32_cat(const float* x, int64_t ldx, int64_t num_rows, int64_t num_rows_padded,
                                    int64_t num_cols, int32_t mode, float* out, ghscn_stream_t stream);
 
+/* Tall-skinny projections y = x W^T + b with in_feat <= 32 (the 9 raw atom features -> hidden layers:
+ * GCNConv layer 1, GraphConv lin_rel/lin_root, the SCN cluster MLP).  One streaming pass each, fp32 FMA.
+ *   fwd: y [N,out];  dw: dW[out,in] = dY^T x (two-stage fixed-order reduction);  dx: dx [N,in] = dY W. */
+GHSCN_API int ghscn_skinny_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias,
+                                      int64_t num_rows, int64_t in_feat, int64_t out_feat, float* y, int64_t ldy,
+                                      ghscn_stream_t stream);
+GHSCN_API size_t ghscn_skinny_dw_workspace_bytes(int64_t num_rows, int64_t in_feat, int64_t out_feat);
+GHSCN_API int ghscn_skinny_linear_dw(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t num_rows,
+                                     int64_t in_feat, int64_t out_feat, float* dw, void* workspace,
+                                     size_t workspace_bytes, ghscn_stream_t stream);
+GHSCN_API int ghscn_skinny_linear_dx(const float* dy, int64_t lddy, const float* w, int64_t num_rows,
+                                     int64_t in_feat, int64_t out_feat, float* dx, int64_t lddx,
+                                     ghscn_stream_t stream);
+
 /* ---- K5: bipartite GAT cluster pool (local -> virtual) ---------------------------------------
  * Replaces GATConv((-1,-1), H, add_self_loops=False) on ("local","to","virtual")
  * (model/hscn.py:85-87,118-125).  SURVEY 8a row a9, Appendix A.8.  heads = 1.
