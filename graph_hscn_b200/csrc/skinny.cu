@@ -4,14 +4,14 @@
 // model/hscn.py:50-54).  They are pure HBM streaming problems (read or write one [N, M] matrix once, ~50 MFLOP),
 // which a tiled SIMT GEMM handles poorly (7-36 us each in profiles/r1d); here each is one pass at memory speed.
 //   fwd : y[n,m]  = sum_k x[n,k] W[m,k] + b[m]          W^T staged in shared memory, warp per row, lanes over m
-//   dW  : dW[m,k] = sum_n dY[n,m] x[n,k]                two-stage fixed-order reduction over 128-row chunks
+//   dW  : dW[m,k] = sum_n dY[n,m] x[n,k]                two-stage fixed-order reduction over 256-row chunks
 //   dX  : dx[n,k] = sum_m dY[n,m] W[m,k]                warp per row, lanes over k
 #include "common.cuh"
 
 namespace ghscn {
 
 constexpr int kSkinnyMaxK = 32;
-constexpr int kDwRows = 128;
+constexpr int kDwRows = 256;
 
 __global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict__ x, int64_t ldx,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
@@ -27,22 +27,33 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < num_rows; n += warps) {
     const float xv = lane < K ? __ldg(x + (int64_t)n * ldx + lane) : 0.f;
-    for (int m = lane; m < M; m += 32) {
-      float acc = bias ? __ldg(bias + m) : 0.f;
+    for (int m0 = 0; m0 < M; m0 += 32) {  // warp-uniform trip count: every lane takes part in the shuffles
+      const int m = m0 + lane;
+      const bool on = m < M;
+      float acc = (on && bias) ? __ldg(bias + m) : 0.f;
 #pragma unroll 4
-      for (int k = 0; k < K; ++k) acc = fmaf(__shfl_sync(kFullMask, xv, k), wt[k * M + m], acc);
-      y[(int64_t)n * ldy + m] = acc;
+      for (int k = 0; k < K; ++k) {
+        const float xk = __shfl_sync(kFullMask, xv, k);
+        if (on) acc = fmaf(xk, wt[k * M + m], acc);
+      }
+      if (on) y[(int64_t)n * ldy + m] = acc;
     }
   }
 }
 
-// partial[chunk][m][k] = sum over the chunk's rows of dY[n,m] x[n,k]; thread owns one m, K register accumulators.
+// partial[chunk][m][k] = sum over the chunk's rows of dY[n,m] x[n,k].  CTA = (32-column tile of m, chunk of
+// kDwRows rows): lanes own m, the 8 warps stride the rows (8 dY loads in flight per lane), K register
+// accumulators per thread, fixed-order combine of the 8 warps in shared memory.
 template <int KMAX>
-__global__ void __launch_bounds__(128) skinny_dw_partial_kernel(const float* __restrict__ dy, int64_t lddy,
+__global__ void __launch_bounds__(256) skinny_dw_partial_kernel(const float* __restrict__ dy, int64_t lddy,
                                                                 const float* __restrict__ x, int64_t ldx,
                                                                 int num_rows, int K, int M,
                                                                 float* __restrict__ partial) {
-  __shared__ float xs[kDwRows * KMAX];
+  constexpr int kBuf = (kDwRows * KMAX > 8 * 32 * (KMAX + 1)) ? kDwRows * KMAX : 8 * 32 * (KMAX + 1);
+  __shared__ float buf[kBuf];                                  // x rows first, then reused for the combine
+  float* xs = buf;
+  float (*red)[32][KMAX + 1] = reinterpret_cast<float (*)[32][KMAX + 1]>(buf);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int r0 = blockIdx.y * kDwRows;
   const int rows = min(kDwRows, num_rows - r0);
   for (int i = threadIdx.x; i < rows * K; i += blockDim.x) {
@@ -50,36 +61,46 @@ __global__ void __launch_bounds__(128) skinny_dw_partial_kernel(const float* __r
     xs[r * KMAX + k] = __ldg(x + (int64_t)(r0 + r) * ldx + k);
   }
   __syncthreads();
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
+  const int m = blockIdx.x * 32 + lane;
+  const bool on = m < M;
   float acc[KMAX];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
-  const float* dp = dy + (int64_t)r0 * lddy + m;
-  int r = 0;
-  for (; r + 3 < rows; r += 4) {
-    const float d0 = __ldg(dp + (int64_t)r * lddy), d1 = __ldg(dp + (int64_t)(r + 1) * lddy);
-    const float d2 = __ldg(dp + (int64_t)(r + 2) * lddy), d3 = __ldg(dp + (int64_t)(r + 3) * lddy);
+  if (on) {
+    const float* dp = dy + (int64_t)r0 * lddy + m;
+    int r = wid;
+    for (; r + 56 < rows; r += 64) {
+      float d[8];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < K) {
-        acc[k] = fmaf(d0, xs[r * KMAX + k], acc[k]);
-        acc[k] = fmaf(d1, xs[(r + 1) * KMAX + k], acc[k]);
-        acc[k] = fmaf(d2, xs[(r + 2) * KMAX + k], acc[k]);
-        acc[k] = fmaf(d3, xs[(r + 3) * KMAX + k], acc[k]);
-      }
+      for (int u = 0; u < 8; ++u) d[u] = __ldg(dp + (int64_t)(r + 8 * u) * lddy);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) acc[k] = fmaf(d[u], xs[(r + 8 * u) * KMAX + k], acc[k]);
+    }
+    for (; r < rows; r += 8) {
+      const float d0 = __ldg(dp + (int64_t)r * lddy);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) acc[k] = fmaf(d0, xs[r * KMAX + k], acc[k]);
     }
   }
-  for (; r < rows; ++r) {
-    const float d0 = __ldg(dp + (int64_t)r * lddy);
+  __syncthreads();  // every warp is done with xs before the buffer is reused
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-      if (k < K) acc[k] = fmaf(d0, xs[r * KMAX + k], acc[k]);
+  for (int k = 0; k < KMAX; ++k) red[wid][lane][k] = acc[k];
+  __syncthreads();
+  // 32 x K outputs of this CTA, combined over the 8 warps in fixed order
+  for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) {
+    const int l = i / K, k = i - l * K;
+    const int mm = blockIdx.x * 32 + l;
+    if (mm < M) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][l][k];
+      partial[((int64_t)blockIdx.y * M + mm) * K + k] = t;
+    }
   }
-  float* out = partial + ((int64_t)blockIdx.y * M + m) * K;
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k)
-    if (k < K) out[k] = acc[k];
 }
 
 // out[i] = sum_c partial[c][i]; one CTA per 32 outputs, 8 warps stride the chunks, fixed-order combine.
@@ -171,11 +192,11 @@ int ghscn_skinny_linear_dw(const float* dy, int64_t lddy, const float* x, int64_
   float* partial = static_cast<float*>(workspace);
   const int K = (int)in_feat, M = (int)out_feat;
   if (chunks > 0) {
-    dim3 grid((unsigned)ceil_div(M, 128), (unsigned)chunks);
+    dim3 grid((unsigned)ceil_div(M, 32), (unsigned)chunks);
     if (K <= 16)
-      skinny_dw_partial_kernel<16><<<grid, 128, 0, stream>>>(dy, lddy, x, ldx, (int)num_rows, K, M, partial);
+      skinny_dw_partial_kernel<16><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, (int)num_rows, K, M, partial);
     else
-      skinny_dw_partial_kernel<32><<<grid, 128, 0, stream>>>(dy, lddy, x, ldx, (int)num_rows, K, M, partial);
+      skinny_dw_partial_kernel<32><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, (int)num_rows, K, M, partial);
   }
   const int64_t width = (int64_t)M * K;
   chunk_sum_kernel<<<(unsigned)ceil_div<int64_t>(width, 32), 256, 0, stream>>>(partial, chunks, width, dw);

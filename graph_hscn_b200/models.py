@@ -47,11 +47,17 @@ class MPNN(nn.Module):
             self.bns = nn.ModuleList(nn.BatchNorm1d(hidden_channels) for _ in range(num_layers - 1))
             self.lns = nn.ModuleList(nn.LayerNorm(hidden_channels) for _ in range(num_layers - 1))
         self.activation, self.dropout = activation, dropout
+        # operator sets that can run the ReLU of `F.relu(conv(x))` inside the aggregation kernel (same values)
+        self._fused = bool(getattr(self.ops, "fused_relu", False)) and all(
+            hasattr(c, "fuse_relu") for c in self.conv_layers[:-1])
+        if self._fused:
+            for c in self.conv_layers[:-1]:
+                c.fuse_relu = True
 
     def forward(self, batch) -> Tensor:
         h, edge_index, graph_of_node = batch.x, batch.edge_index, batch.batch
         for i, conv in enumerate(self.conv_layers[:-1]):
-            h = F.relu(conv(h, edge_index))
+            h = conv(h, edge_index) if self._fused else F.relu(conv(h, edge_index))
             if self.use_batch_norm:
                 h = self.bns[i](h)
             if self.use_layer_norm:
@@ -125,10 +131,19 @@ class HSCN(nn.Module):
             }, aggr="sum") for _ in range(num_layers))
         self.lin_1 = o.Linear(hidden_channels, hidden_channels)
         self.lin_2 = o.Linear(hidden_channels, num_classes)
+        # "local" receives only the l->l GCN, so its `.relu()` can run in that layer's aggregation epilogue
+        self._fused_local = False
+        if getattr(o, "fused_relu", False):
+            lls = [c.convs["local__to__local"] for c in self.convs]
+            if all(hasattr(c, "fuse_relu") for c in lls):
+                for c in lls:
+                    c.fuse_relu = True
+                self._fused_local = True
 
     def forward(self, x_dict: Dict[str, Tensor], edge_index_dict, batch) -> Tensor:
         for conv in self.convs:
-            x_dict = {k: v.relu() for k, v in conv(x_dict, edge_index_dict).items()}
+            x_dict = {k: (v if (self._fused_local and k == "local") else v.relu())
+                      for k, v in conv(x_dict, edge_index_dict).items()}
         pooled = self.ops.global_mean_pool(x_dict["local"], batch["local"].batch)
         return self.lin_2(self.activation(self.lin_1(pooled)))
 

@@ -84,25 +84,30 @@ def _(rowptr, col, x, dy, num_slots):
 
 @_custom_op("ghscn::spmm", mutates_args=(), device_types="cuda")
 def spmm(rowptr: Tensor, col: Tensor, w: Optional[Tensor], rowptr_t: Tensor, col_t: Tensor,
-         w_t: Optional[Tensor], x: Tensor, bias: Optional[Tensor]) -> Tensor:
-    """y = A_w x (+ bias); rows of (rowptr, col) are destinations, (rowptr_t, col_t) is the transpose."""
-    return spmm_raw(rowptr, col, w, x, bias, rowptr.numel() - 1, False)
+         w_t: Optional[Tensor], x: Tensor, bias: Optional[Tensor], relu: bool = False) -> Tensor:
+    """y = act(A_w x + bias); rows of (rowptr, col) are destinations, (rowptr_t, col_t) is the transpose;
+    act = ReLU when `relu` (fused into the kernel's epilogue), identity otherwise."""
+    return spmm_raw(rowptr, col, w, x, bias, rowptr.numel() - 1, relu)
 
 
 @spmm.register_fake
-def _(rowptr, col, w, rowptr_t, col_t, w_t, x, bias):
+def _(rowptr, col, w, rowptr_t, col_t, w_t, x, bias, relu=False):
     return x.new_empty((rowptr.numel() - 1, x.size(1)))
 
 
 def _spmm_setup(ctx, inputs, output):
-    rowptr, col, w, rowptr_t, col_t, w_t, x, bias = inputs
+    rowptr, col, w, rowptr_t, col_t, w_t, x, bias, relu = inputs
     ctx.has_bias = bias is not None
+    ctx.relu = relu
     ctx.w_needs_grad = w is not None and w.requires_grad
-    ctx.save_for_backward(rowptr, col, rowptr_t, col_t, w_t, x if ctx.w_needs_grad else None)
+    ctx.save_for_backward(rowptr, col, rowptr_t, col_t, w_t, x if ctx.w_needs_grad else None,
+                          output if relu else None)
 
 
 def _spmm_backward(ctx, dy):
-    rowptr, col, rowptr_t, col_t, w_t, x = ctx.saved_tensors
+    rowptr, col, rowptr_t, col_t, w_t, x, y = ctx.saved_tensors
+    if ctx.relu:
+        dy = torch.where(y > 0, dy, torch.zeros((), dtype=dy.dtype, device=dy.device))
     dy = dy.contiguous()
     dx = dw = dbias = None
     if ctx.needs_input_grad[6]:
@@ -111,7 +116,7 @@ def _spmm_backward(ctx, dy):
         dw = spmm_edge_grad(rowptr, col, x, dy, col.numel())
     if ctx.has_bias and ctx.needs_input_grad[7]:
         dbias = colsum(dy)
-    return None, None, dw, None, None, None, dx, dbias
+    return None, None, dw, None, None, None, dx, dbias, None
 
 
 torch.library.register_autograd("ghscn::spmm", _spmm_backward, setup_context=_spmm_setup)

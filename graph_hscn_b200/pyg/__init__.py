@@ -25,7 +25,7 @@ __all__ = ["GATConv", "GCNConv", "GINConv", "GraphConv", "HeteroConv", "Linear",
 def namespace() -> types.SimpleNamespace:
     """The operator set the mirror models (graph_hscn_b200.models) are parameterised with."""
     return types.SimpleNamespace(
-        name="ghscn-b200", GCNConv=GCNConv, GATConv=GATConv, GINConv=GINConv, GraphConv=GraphConv,
+        name="ghscn-b200", fused_relu=True, GCNConv=GCNConv, GATConv=GATConv, GINConv=GINConv, GraphConv=GraphConv,
         HeteroConv=HeteroConv, Linear=Linear, Sequential=Sequential, MessagePassing=MessagePassing,
         dense_mincut_pool=dense_mincut_pool, mincut_pool_ragged=mincut_pool_ragged, to_dense_adj=to_dense_adj,
         global_mean_pool=global_mean_pool, scatter_mean=scatter_mean, gcn_norm=gcn_norm)

@@ -83,8 +83,8 @@ class MessagePassing(nn.Module):
 
 def _aggregate(x_src: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor], num_dst: int,
                normalize: bool = False, improved: bool = False, add_self_loops: bool = False,
-               bias: Optional[Tensor] = None) -> Tensor:
-    """out[i] = sum_{e: col_e = i} w_e * x_src[row_e] (+ bias): CSR lookup + K2 SpMM."""
+               bias: Optional[Tensor] = None, relu: bool = False) -> Tensor:
+    """out[i] = act(sum_{e: col_e = i} w_e * x_src[row_e] + bias): CSR lookup + K2 SpMM (ReLU in its epilogue)."""
     _require_cuda(x_src, edge_index)
     st = structure_cache().graph(edge_index, x_src.size(0), num_dst, add_self_loops)
     w_param = None
@@ -99,7 +99,7 @@ def _aggregate(x_src: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor],
     d, s = st.by_dst, st.by_src
     if x_src.dtype != torch.float32:
         x_src = x_src.float()
-    return torch.ops.ghscn.spmm(d.rowptr, d.col, w, s.rowptr, s.col, w_t, x_src, bias)
+    return torch.ops.ghscn.spmm(d.rowptr, d.col, w, s.rowptr, s.col, w_t, x_src, bias, relu)
 
 
 class GCNConv(MessagePassing):
@@ -117,6 +117,9 @@ class GCNConv(MessagePassing):
             self.bias = nn.Parameter(torch.zeros(out_channels))
         else:
             self.register_parameter("bias", None)
+        # extension (not in PyG): a caller that applies ReLU right after this layer may set this flag and skip
+        # its own ReLU; the activation then runs in the aggregation kernel's epilogue (same values)
+        self.fuse_relu = False
 
     def reset_parameters(self) -> None:
         self.lin.reset_parameters()
@@ -127,7 +130,7 @@ class GCNConv(MessagePassing):
         h = self.lin(x)
         return _aggregate(h, edge_index, edge_weight, x.size(0), normalize=self.normalize,
                           improved=self.improved, add_self_loops=self.add_self_loops and self.normalize,
-                          bias=self.bias)
+                          bias=self.bias, relu=self.fuse_relu)
 
 
 class GraphConv(MessagePassing):
