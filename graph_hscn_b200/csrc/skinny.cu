@@ -222,3 +222,45 @@ int ghscn_skinny_linear_dx(const float* dy, int64_t lddy, const float* w, int64_
 }
 
 }  // extern "C"
+
+// ---- AdamW on one flat fp32 parameter buffer (train/train.py:94 `optimizer.step()`, OPTIM_DICT["adamW"]) -----------
+// torch.optim.AdamW's update, elementwise, with the step count kept on the device so the launch is CUDA-graph
+// capturable:  p *= 1 - lr*wd;  m = lerp(m, g, 1-b1);  v = b2*v + (1-b2)*g*g;
+//              p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+namespace ghscn {
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                    float lr, float b1, float b2, float eps, float wd,
+                                                    float* __restrict__ step) {
+  const float t = step[0] + 1.0f;  // every thread reads the old value; thread 0 of block 0 publishes t at the end
+  const float bc1 = 1.0f - powf(b1, t);
+  const float bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+  const float step_size = lr / bc1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i];
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
+    const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+__global__ void adamw_bump_kernel(float* step) { step[0] += 1.0f; }
+}  // namespace ghscn
+
+extern "C" int ghscn_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
+                                ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(n >= 0 && step && (n == 0 || (param && grad && exp_avg && exp_avg_sq)));
+  cudaStream_t stream = ghscn::as_stream(stream_);
+  if (n > 0) {
+    const int64_t blocks = ghscn::ceil_div<int64_t>(n, 256 * 4), cap = (int64_t)ghscn::kNumSMs * 8;
+    ghscn::adamw_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(
+        param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step);
+  }
+  ghscn::adamw_bump_kernel<<<1, 1, 0, stream>>>(step);
+  GHSCN_LAUNCH_CHECK_N(n > 0 ? 2 : 1);
+  return GHSCN_OK;
+}

@@ -107,7 +107,7 @@ def _spmm_setup(ctx, inputs, output):
 def _spmm_backward(ctx, dy):
     rowptr, col, rowptr_t, col_t, w_t, x, y = ctx.saved_tensors
     if ctx.relu:
-        dy = torch.where(y > 0, dy, torch.zeros((), dtype=dy.dtype, device=dy.device))
+        dy = torch.ops.aten.threshold_backward(dy, y, 0.0)      # dy * (y > 0), one vectorised pass
     dy = dy.contiguous()
     dx = dw = dbias = None
     if ctx.needs_input_grad[6]:

@@ -99,6 +99,30 @@ class FlatGradients:
         self.flat.mul_(1.0 / world)
 
 
+class FlatAdamW:
+    """torch.optim.AdamW semantics on one flat parameter buffer, one kernel per step (ghscn_adamw_step); the step
+    counter lives on the device, so `step()` is CUDA-graph capturable."""
+
+    def __init__(self, flat_param: Tensor, flat_grad: Tensor, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2):
+        self.p, self.g = flat_param, flat_grad
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(flat_grad)
+        self.exp_avg_sq = torch.zeros_like(flat_grad)
+        self.step_count = torch.zeros(1, dtype=torch.float32, device=flat_grad.device)
+        self.state = {0: {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count}}
+
+    def step(self) -> None:
+        from ._lib import lib
+        from .structure import _p, _stream
+        lib().call("ghscn_adamw_step", _p(self.p), _p(self.g), _p(self.exp_avg), _p(self.exp_avg_sq), self.p.numel(),
+                   float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd),
+                   _p(self.step_count), _stream())
+
+    def zero_grad(self) -> None:
+        self.g.zero_()
+
+
 def live_parameter_names(module: nn.Module, loss: Tensor) -> List[str]:
     """Names of the parameters reachable from `loss` (consistent on all ranks for the same model)."""
     named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
@@ -187,9 +211,11 @@ class GraphHSCNStep:
         self.hscn_grads = FlatGradients(self.hscn, hscn_live)
         kw = dict(lr=cfg.lr, weight_decay=cfg.weight_decay)
         if self.device.type == "cuda":
-            kw.update(fused=True, capturable=True)
-        self.scn_opt = torch.optim.AdamW([self.scn_grads.flatten_parameters()], **kw)
-        self.hscn_opt = torch.optim.AdamW([self.hscn_grads.flatten_parameters()], **kw)
+            self.scn_opt = FlatAdamW(self.scn_grads.flatten_parameters().detach(), self.scn_grads.flat, **kw)
+            self.hscn_opt = FlatAdamW(self.hscn_grads.flatten_parameters().detach(), self.hscn_grads.flat, **kw)
+        else:
+            self.scn_opt = torch.optim.AdamW([self.scn_grads.flatten_parameters()], **kw)
+            self.hscn_opt = torch.optim.AdamW([self.hscn_grads.flatten_parameters()], **kw)
         structure_cache().clear()
 
     def _cast(self, x: Tensor) -> Tensor:

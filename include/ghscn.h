@@ -160,6 +160,13 @@ GHSCN_API int ghscn_skinny_linear_dx(const float* dy, int64_t lddy, const float*
                                      int64_t in_feat, int64_t out_feat, float* dx, int64_t lddx,
                                      ghscn_stream_t stream);
 
+/* AdamW (torch.optim.AdamW semantics) on one flat fp32 parameter buffer; `step` is a device float holding the
+ * number of steps taken so far and is incremented by the call, so it can be captured in a CUDA graph.
+ * Replaces the per-tensor optimizer launches of train/train.py:94 for the flat-buffer training step. */
+GHSCN_API int ghscn_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                               float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
+                               ghscn_stream_t stream);
+
 /* ---- K5: bipartite GAT cluster pool (local -> virtual) ---------------------------------------
  * Replaces GATConv((-1,-1), H, add_self_loops=False) on ("local","to","virtual")
  * (model/hscn.py:85-87,118-125).  SURVEY 8a row a9, Appendix A.8.  heads = 1.

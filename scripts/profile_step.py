@@ -30,7 +30,8 @@ agg, cnt = collections.defaultdict(float), collections.Counter()
 first, last = None, None
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:
-        name = re.sub(r"\(.*", "", e.name)[:95]
+        name = re.sub(r"\(anonymous namespace\)::", "", e.name)
+        name = re.sub(r"\(.*", "", name)[:95]
         if "FillFunctor<unsigned char>" in e.name or "Memset" in e.name and e.device_time > 30:
             continue
         agg[name] += e.device_time / REPS
