@@ -5,6 +5,8 @@
 // register accumulators for ITERS column chunks, so every feature row touched is read with
 // coalesced 128-bit loads and the per-row neighbour sum is sequential in slot (= edge) order with
 // separate multiply and add roundings -- the order and rounding of CPU scatter_add_.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ghscn {
@@ -221,6 +223,157 @@ __global__ void __launch_bounds__(256, 2) spmm_wide_kernel(const int* __restrict
   }
 }
 
+// ---- wide rows, TMA bulk-copy gather (sm_100a: cp.async.bulk + mbarrier, SASS UBLKCP) -----------------------------
+// Same CTA-staged indices as above, but the feature rows themselves are fetched by the TMA engine: every warp owns
+// a private ring of kBulkStages shared-memory row buffers, each guarded by an mbarrier.  A source row x[col[s],:]
+// is one contiguous, 16-byte aligned span of 4F bytes, so one `cp.async.bulk.shared::cluster.global` per slot
+// moves it without touching registers; the warp keeps kBulkStages rows (~9.6 KB at F=300) in flight, reads a
+// landed row with conflict-free 128-bit shared loads, accumulates in slot order with unfused mul/add (identical
+// arithmetic to the register path), then re-arms the same stage for the slot kBulkStages ahead.  No cross-warp
+// synchronisation after the index staging; ~150 KB of gather traffic in flight per SM at 2 CTAs/SM.
+constexpr int kBulkStages = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+template <int ITERS, bool WEIGHTED>
+__global__ void __launch_bounds__(256, 2) spmm_bulk_kernel(const int* __restrict__ rowptr,
+                                                           const int* __restrict__ col,
+                                                           const float* __restrict__ w,
+                                                           const float* __restrict__ x, int64_t ldx,
+                                                           float* __restrict__ y, int64_t ldy,
+                                                           const float* __restrict__ bias, int num_rows,
+                                                           int num_feat, int relu) {
+  extern __shared__ __align__(128) unsigned char ring[];  // [8 warps][kBulkStages][row_bytes]
+  __shared__ __align__(8) unsigned long long bars[8 * kBulkStages];
+  __shared__ int s_rowptr[kRowsPerCta + 1];
+  __shared__ int s_col[kSlotCap];
+  __shared__ float s_w[kSlotCap];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int row0 = blockIdx.x * kRowsPerCta;
+  const int nrows = min(kRowsPerCta, num_rows - row0);
+  const uint32_t row_bytes = (uint32_t)num_feat * 4u;
+  if (tid < 8 * kBulkStages) mbar_init(smem_u32(&bars[tid]), 1);
+  if (tid <= nrows) s_rowptr[tid] = rowptr[row0 + tid];
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const int sbeg = s_rowptr[0];
+  const int staged = min(s_rowptr[nrows] - sbeg, kSlotCap);
+  for (int i = tid; i < staged; i += 256) {
+    s_col[i] = col[sbeg + i];
+    if (WEIGHTED) s_w[i] = w[sbeg + i];
+  }
+  __syncthreads();
+
+  unsigned char* my_ring = ring + (size_t)wid * kBulkStages * row_bytes;
+  const uint32_t bar0 = smem_u32(&bars[wid * kBulkStages]);
+  // issue cursor (runs kBulkStages slots ahead of the consume cursor); warp-uniform
+  int ir = wid, is = (ir < nrows) ? s_rowptr[ir] - sbeg : 0;
+  int issued = 0;
+  auto issue_next = [&]() -> bool {   // lane 0 arms the stage and launches one row copy
+    while (ir < nrows && is >= s_rowptr[ir + 1] - sbeg) {
+      ir += 8;
+      if (ir < nrows) is = s_rowptr[ir] - sbeg;
+    }
+    if (ir >= nrows) return false;
+    const int stage = issued % kBulkStages;
+    if (lane == 0) {
+      const int c = is < kSlotCap ? s_col[is] : col[sbeg + is];
+      const uint32_t bar = bar0 + stage * 8;
+      mbar_arrive_expect_tx(bar, row_bytes);
+      bulk_g2s(smem_u32(my_ring + (size_t)stage * row_bytes), x + (int64_t)c * ldx, row_bytes, bar);
+    }
+    ++is;
+    ++issued;
+    return true;
+  };
+  for (int k = 0; k < kBulkStages; ++k)
+    if (!issue_next()) break;
+
+  int consumed = 0;
+  for (int r = wid; r < nrows; r += 8) {
+    const int beg = s_rowptr[r] - sbeg, end = s_rowptr[r + 1] - sbeg;
+    float4 acc[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = beg; s < end; ++s) {
+      const int stage = consumed % kBulkStages;
+      mbar_wait(bar0 + stage * 8, (uint32_t)(consumed / kBulkStages) & 1u);
+      const float wv = WEIGHTED ? (s < kSlotCap ? s_w[s] : w[sbeg + s]) : 1.f;
+      const float4* src = reinterpret_cast<const float4*>(my_ring + (size_t)stage * row_bytes);
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        if ((it * 32 + lane) * 4 < num_feat) {
+          const float4 v = src[it * 32 + lane];
+          if (WEIGHTED) {
+            acc[it].x = mul_then_add(acc[it].x, wv, v.x); acc[it].y = mul_then_add(acc[it].y, wv, v.y);
+            acc[it].z = mul_then_add(acc[it].z, wv, v.z); acc[it].w = mul_then_add(acc[it].w, wv, v.w);
+          } else {
+            acc[it].x = __fadd_rn(acc[it].x, v.x); acc[it].y = __fadd_rn(acc[it].y, v.y);
+            acc[it].z = __fadd_rn(acc[it].z, v.z); acc[it].w = __fadd_rn(acc[it].w, v.w);
+          }
+        }
+      }
+      ++consumed;
+      __syncwarp();     // every lane has read this stage before the TMA engine may overwrite it
+      issue_next();
+    }
+    float* yrow = y + (int64_t)(row0 + r) * ldy;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int f = (it * 32 + lane) * 4;
+      if (f < num_feat) {
+        float4 o = acc[it];
+        if (bias) {
+          const float4 b = ldg_f4(bias + f);
+          o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y); o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(yrow + f) = o;
+      }
+    }
+  }
+}
+
+template <int ITERS>
+static int launch_spmm_bulk(const int* rowptr, const int* col, const float* w, const float* x, int64_t ldx,
+                            float* y, int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, int relu,
+                            cudaStream_t stream) {
+  const size_t shm = (size_t)8 * kBulkStages * num_feat * 4;
+  dim3 grid((unsigned)ceil_div<int64_t>(num_rows, kRowsPerCta));
+  if (w) {
+    cudaFuncSetAttribute(spmm_bulk_kernel<ITERS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+    spmm_bulk_kernel<ITERS, true><<<grid, 256, shm, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias, (int)num_rows,
+                                                               (int)num_feat, relu);
+  } else {
+    cudaFuncSetAttribute(spmm_bulk_kernel<ITERS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+    spmm_bulk_kernel<ITERS, false><<<grid, 256, shm, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias, (int)num_rows,
+                                                                (int)num_feat, relu);
+  }
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
 template <int ITERS>
 static int launch_spmm_wide(const int* rowptr, const int* col, const float* w, const float* x, int64_t ldx,
                             float* y, int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, int relu,
@@ -335,6 +488,16 @@ static int dispatch_spmm(const int* rowptr, const int* col, const float* w, cons
                          int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, int relu,
                          cudaStream_t stream) {
   const int64_t nvec = ceil_div<int64_t>(num_feat, VEC);
+  static const bool use_bulk = [] {
+    const char* e = getenv("GHSCN_SPMM_PATH");  // "wide" forces the register-gather variant (A/B measurements)
+    return !(e && e[0] == 'w');
+  }();
+  if (VEC == 4 && nvec >= 32 && nvec <= 128 && use_bulk) {  // 128 <= F <= 512: TMA bulk-copy gather
+    if (nvec <= 32) return launch_spmm_bulk<1>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+    if (nvec <= 64) return launch_spmm_bulk<2>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+    if (nvec <= 96) return launch_spmm_bulk<3>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+    return launch_spmm_bulk<4>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+  }
   if (VEC == 4 && nvec >= 32) {  // F >= 128 on the 128-bit path: CTA-staged indices, 4 slots in flight
     if (nvec <= 32) return launch_spmm_wide<1>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
     if (nvec <= 64) return launch_spmm_wide<2>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);

@@ -25,4 +25,5 @@ def cuda(built_lib):
         pytest.skip("no CUDA device")
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
+    import graph_hscn_b200.ops  # noqa: F401  (registers torch.ops.ghscn.*)
     return torch.device("cuda:0")
