@@ -374,6 +374,135 @@ static int launch_spmm_bulk(const int* rowptr, const int* col, const float* w, c
   return GHSCN_OK;
 }
 
+// ---- wide rows, cp.async (LDGSTS) gather: deep per-lane prefetch without registers ----------------------------------
+// Each lane copies exactly the 16-byte chunks it will later read (chunk it*32+lane of a row), one commit group per
+// slot, kAsyncStages slots ahead, into a warp-private shared-memory ring.  Consumption only needs
+// cp.async.wait_group (a lane waits for its own copies), no barrier and no shuffle; arithmetic and order are the
+// same unfused slot-order accumulation as the register path.
+constexpr int kAsyncStages = 10;
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int ITERS, bool WEIGHTED>
+__global__ void __launch_bounds__(256, 2) spmm_async_kernel(const int* __restrict__ rowptr,
+                                                            const int* __restrict__ col,
+                                                            const float* __restrict__ w,
+                                                            const float* __restrict__ x, int64_t ldx,
+                                                            float* __restrict__ y, int64_t ldy,
+                                                            const float* __restrict__ bias, int num_rows,
+                                                            int num_feat, int relu) {
+  extern __shared__ __align__(128) unsigned char ring[];  // [8 warps][kAsyncStages][row_bytes]
+  __shared__ int s_rowptr[kRowsPerCta + 1];
+  __shared__ int s_col[kSlotCap];
+  __shared__ float s_w[kSlotCap];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int row0 = blockIdx.x * kRowsPerCta;
+  const int nrows = min(kRowsPerCta, num_rows - row0);
+  const uint32_t row_bytes = (uint32_t)num_feat * 4u;
+  if (tid <= nrows) s_rowptr[tid] = rowptr[row0 + tid];
+  __syncthreads();
+  const int sbeg = s_rowptr[0];
+  const int staged = min(s_rowptr[nrows] - sbeg, kSlotCap);
+  for (int i = tid; i < staged; i += 256) {
+    s_col[i] = col[sbeg + i];
+    if (WEIGHTED) s_w[i] = w[sbeg + i];
+  }
+  __syncthreads();
+
+  unsigned char* my_ring = ring + (size_t)wid * kAsyncStages * row_bytes;
+  const uint32_t ring_u32 = smem_u32(my_ring);
+  int ir = wid, is = (ir < nrows) ? s_rowptr[ir] - sbeg : 0;   // issue cursor, warp-uniform
+  int issued = 0;
+  auto issue_next = [&]() {   // always commits one group (possibly empty) so the pending count stays constant
+    while (ir < nrows && is >= s_rowptr[ir + 1] - sbeg) {
+      ir += 8;
+      if (ir < nrows) is = s_rowptr[ir] - sbeg;
+    }
+    if (ir < nrows) {
+      const int c = is < kSlotCap ? s_col[is] : col[sbeg + is];
+      const float* src = x + (int64_t)c * ldx;
+      const uint32_t dst = ring_u32 + (uint32_t)(issued % kAsyncStages) * row_bytes;
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int f = (it * 32 + lane) * 4;
+        if (f < num_feat) cp_async_16(dst + f * 4, src + f);
+      }
+      ++is;
+      ++issued;
+    }
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int k = 0; k < kAsyncStages - 1; ++k) issue_next();
+
+  int consumed = 0;
+  for (int r = wid; r < nrows; r += 8) {
+    const int beg = s_rowptr[r] - sbeg, end = s_rowptr[r + 1] - sbeg;
+    float4 acc[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = beg; s < end; ++s) {
+      issue_next();                             // keep kAsyncStages groups outstanding ...
+      cp_async_wait<kAsyncStages - 1>();        // ... and wait for the oldest one (this slot)
+      const float wv = WEIGHTED ? (s < kSlotCap ? s_w[s] : w[sbeg + s]) : 1.f;
+      const float4* src = reinterpret_cast<const float4*>(my_ring + (size_t)(consumed % kAsyncStages) * row_bytes);
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        if ((it * 32 + lane) * 4 < num_feat) {
+          const float4 v = src[it * 32 + lane];   // the chunk this very lane copied
+          if (WEIGHTED) {
+            acc[it].x = mul_then_add(acc[it].x, wv, v.x); acc[it].y = mul_then_add(acc[it].y, wv, v.y);
+            acc[it].z = mul_then_add(acc[it].z, wv, v.z); acc[it].w = mul_then_add(acc[it].w, wv, v.w);
+          } else {
+            acc[it].x = __fadd_rn(acc[it].x, v.x); acc[it].y = __fadd_rn(acc[it].y, v.y);
+            acc[it].z = __fadd_rn(acc[it].z, v.z); acc[it].w = __fadd_rn(acc[it].w, v.w);
+          }
+        }
+      }
+      ++consumed;
+    }
+    float* yrow = y + (int64_t)(row0 + r) * ldy;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int f = (it * 32 + lane) * 4;
+      if (f < num_feat) {
+        float4 o = acc[it];
+        if (bias) {
+          const float4 b = ldg_f4(bias + f);
+          o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y); o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(yrow + f) = o;
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int ITERS>
+static int launch_spmm_async(const int* rowptr, const int* col, const float* w, const float* x, int64_t ldx,
+                             float* y, int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, int relu,
+                             cudaStream_t stream) {
+  const size_t shm = (size_t)8 * kAsyncStages * num_feat * 4;
+  dim3 grid((unsigned)ceil_div<int64_t>(num_rows, kRowsPerCta));
+  if (w) {
+    cudaFuncSetAttribute(spmm_async_kernel<ITERS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+    spmm_async_kernel<ITERS, true><<<grid, 256, shm, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias, (int)num_rows,
+                                                                (int)num_feat, relu);
+  } else {
+    cudaFuncSetAttribute(spmm_async_kernel<ITERS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+    spmm_async_kernel<ITERS, false><<<grid, 256, shm, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias, (int)num_rows,
+                                                                 (int)num_feat, relu);
+  }
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
 template <int ITERS>
 static int launch_spmm_wide(const int* rowptr, const int* col, const float* w, const float* x, int64_t ldx,
                             float* y, int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, int relu,
@@ -488,11 +617,21 @@ static int dispatch_spmm(const int* rowptr, const int* col, const float* w, cons
                          int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, int relu,
                          cudaStream_t stream) {
   const int64_t nvec = ceil_div<int64_t>(num_feat, VEC);
-  static const bool use_bulk = [] {
-    const char* e = getenv("GHSCN_SPMM_PATH");  // "wide" forces the register-gather variant (A/B measurements)
-    return !(e && e[0] == 'w');
+  // gather engine for 128 <= F <= 512, selectable for A/B measurements (scripts/spmm_ceiling.py):
+  //   'w' register gather with CTA-staged indices (default: fastest on molecule-like graphs, 13.5 us at
+  //       N=18,269 F=300 vs 15.0 us for 'a' and 18.3 us for 'b', CUDA-graph replay over 438 MB of operands)
+  //   'a' cp.async ring, 'b' TMA bulk copies (both win only at ~1 slot per row: 10.0 / 9.7 us vs 12.8 us)
+  static const char path = [] {
+    const char* e = getenv("GHSCN_SPMM_PATH");
+    return (e && (e[0] == 'a' || e[0] == 'b')) ? e[0] : 'w';
   }();
-  if (VEC == 4 && nvec >= 32 && nvec <= 128 && use_bulk) {  // 128 <= F <= 512: TMA bulk-copy gather
+  if (VEC == 4 && nvec >= 32 && nvec <= 128 && path == 'a') {
+    if (nvec <= 32) return launch_spmm_async<1>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+    if (nvec <= 64) return launch_spmm_async<2>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+    if (nvec <= 96) return launch_spmm_async<3>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+    return launch_spmm_async<4>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+  }
+  if (VEC == 4 && nvec >= 32 && nvec <= 128 && path == 'b') {
     if (nvec <= 32) return launch_spmm_bulk<1>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
     if (nvec <= 64) return launch_spmm_bulk<2>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
     if (nvec <= 96) return launch_spmm_bulk<3>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
