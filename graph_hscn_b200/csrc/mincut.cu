@@ -39,6 +39,183 @@ __device__ __forceinline__ void csr_times_s(const int* __restrict__ rowptr, cons
   }
 }
 
+// ---- register-tiled contractions over the graph's nodes -----------------------------------------------------------
+// C[m, c] (+)= sum_i A[i*lda + m] * B[i*ldb + c],  m < M, c < Nc, i < n.   A (the S tile) usually lives in shared
+// memory, B is S / AS (shared) or the graph's X rows (global, coalesced along c).  Each thread owns a TM x TN tile of
+// C: per node it reads TM + TN values for TM*TN FMAs (vs 2 reads per FMA in a scalar loop); consecutive threads
+// take consecutive column tiles of the same row tile, so A reads are warp broadcasts and B reads are contiguous.
+template <int TM, int TN>
+__device__ __forceinline__ void atb_tiled(const float* __restrict__ A, int lda, int M, const float* __restrict__ B,
+                                          int64_t ldb, int Nc, int n, float* __restrict__ C, int64_t ldc) {
+  const int mt = ceil_div(M, TM), ct = ceil_div(Nc, TN);
+  const int tiles = mt * ct;
+  // few tiles (small K): `split` adjacent lanes share one tile, each taking every split-th node, then a shuffle
+  // reduction -- keeps the whole CTA busy instead of a handful of threads walking all n nodes alone
+  int split = 1;
+  while (split < 32 && tiles * split * 2 <= (int)blockDim.x) split *= 2;
+  const bool vec_b = (TN == 4) && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  const int work = tiles * split;
+  for (int t0 = 0; t0 < work; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    const bool active = t < work;
+    const int tile = active ? t / split : 0, sub = t % split;
+    const int m0 = (tile / ct) * TM, c0 = (tile % ct) * TN;
+    float acc[TM][TN];
+#pragma unroll
+    for (int a = 0; a < TM; ++a)
+#pragma unroll
+      for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+    const bool full = (m0 + TM <= M) && (c0 + TN <= Nc);
+    if (active) {
+      if (full && vec_b) {
+        int i = sub;
+        for (; i + 3 * split < n; i += 4 * split) {   // 4 nodes in flight per lane
+          float4 q[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const float4*>(B + (int64_t)(i + u * split) * ldb + c0);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float bv[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+            for (int a = 0; a < TM; ++a) {
+              const float av = A[(i + u * split) * lda + m0 + a];
+#pragma unroll
+              for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av, bv[b % 4], acc[a][b]);
+            }
+          }
+        }
+        for (; i < n; i += split) {
+          const float4 q = *reinterpret_cast<const float4*>(B + (int64_t)i * ldb + c0);
+          const float bv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int a = 0; a < TM; ++a) {
+            const float av = A[i * lda + m0 + a];
+#pragma unroll
+            for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av, bv[b % 4], acc[a][b]);
+          }
+        }
+      } else {
+        for (int i = sub; i < n; i += split) {
+          float av[TM], bv[TN];
+#pragma unroll
+          for (int a = 0; a < TM; ++a) av[a] = (m0 + a < M) ? A[i * lda + m0 + a] : 0.f;
+#pragma unroll
+          for (int b = 0; b < TN; ++b) bv[b] = (c0 + b < Nc) ? B[(int64_t)i * ldb + c0 + b] : 0.f;
+#pragma unroll
+          for (int a = 0; a < TM; ++a)
+#pragma unroll
+            for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+        }
+      }
+    }
+    for (int off = split >> 1; off > 0; off >>= 1) {   // warp-uniform: split is the same for every thread
+#pragma unroll
+      for (int a = 0; a < TM; ++a)
+#pragma unroll
+        for (int b = 0; b < TN; ++b) acc[a][b] += __shfl_xor_sync(kFullMask, acc[a][b], off);
+    }
+    if (active && sub == 0) {
+#pragma unroll
+      for (int a = 0; a < TM; ++a)
+#pragma unroll
+        for (int b = 0; b < TN; ++b)
+          if (m0 + a < M && c0 + b < Nc) C[(int64_t)(m0 + a) * ldc + c0 + b] = acc[a][b];
+    }
+  }
+}
+
+// D[i, c] = sum_l P[i*ldp + l] * Q[l*ldq + c] (+ D if accumulate); the [n,K] x [K,K] products of the backward.
+template <int TR, int TN>
+__device__ __forceinline__ void ab_tiled(const float* __restrict__ P, int ldp, int n, const float* __restrict__ Q,
+                                         int ldq, int Kred, int Nc, float scale, float* __restrict__ D, int ldd,
+                                         bool accumulate) {
+  const int rt = ceil_div(n, TR), ct = ceil_div(Nc, TN);
+  for (int t = threadIdx.x; t < rt * ct; t += blockDim.x) {
+    const int r0 = (t / ct) * TR, c0 = (t % ct) * TN;
+    float acc[TR][TN];
+#pragma unroll
+    for (int a = 0; a < TR; ++a)
+#pragma unroll
+      for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+    for (int l = 0; l < Kred; ++l) {
+      float pv[TR], qv[TN];
+#pragma unroll
+      for (int a = 0; a < TR; ++a) pv[a] = (r0 + a < n) ? P[(r0 + a) * ldp + l] : 0.f;
+#pragma unroll
+      for (int b = 0; b < TN; ++b) qv[b] = (c0 + b < Nc) ? Q[l * ldq + c0 + b] : 0.f;
+#pragma unroll
+      for (int a = 0; a < TR; ++a)
+#pragma unroll
+        for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(pv[a], qv[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < TR; ++a)
+#pragma unroll
+      for (int b = 0; b < TN; ++b)
+        if (r0 + a < n && c0 + b < Nc) {
+          float* d = D + (r0 + a) * ldd + c0 + b;
+          *d = accumulate ? (*d + scale * acc[a][b]) : scale * acc[a][b];
+        }
+  }
+}
+
+// D[i, c] (+)= scale * sum_h P[i*ldp + h] * Q[c*ldq + h]: both operands reduce along their contiguous dimension
+// (x g_out^T over the features, AS Gamma^T over the clusters); 128-bit loads along h when alignment allows.
+template <int TR, int TN>
+__device__ __forceinline__ void abt_tiled(const float* __restrict__ P, int64_t ldp, int n, const float* __restrict__ Q,
+                                          int64_t ldq, int Nc, int Kred, float scale, float* __restrict__ D, int ldd,
+                                          bool accumulate) {
+  const int rt = ceil_div(n, TR), ct = ceil_div(Nc, TN);
+  const bool vec = (Kred % 4 == 0) && (ldp % 4 == 0) && (ldq % 4 == 0) &&
+                   (((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(Q)) & 15) == 0);
+  for (int t = threadIdx.x; t < rt * ct; t += blockDim.x) {
+    const int r0 = (t / ct) * TR, c0 = (t % ct) * TN;
+    float acc[TR][TN];
+#pragma unroll
+    for (int a = 0; a < TR; ++a)
+#pragma unroll
+      for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+    if (vec) {
+      for (int h = 0; h < Kred; h += 4) {
+        float4 pv[TR], qv[TN];
+#pragma unroll
+        for (int a = 0; a < TR; ++a)
+          pv[a] = (r0 + a < n) ? *reinterpret_cast<const float4*>(P + (int64_t)(r0 + a) * ldp + h)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int b = 0; b < TN; ++b)
+          qv[b] = (c0 + b < Nc) ? *reinterpret_cast<const float4*>(Q + (int64_t)(c0 + b) * ldq + h)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < TR; ++a)
+#pragma unroll
+          for (int b = 0; b < TN; ++b)
+            acc[a][b] += pv[a].x * qv[b].x + pv[a].y * qv[b].y + pv[a].z * qv[b].z + pv[a].w * qv[b].w;
+      }
+    } else {
+      for (int h = 0; h < Kred; ++h) {
+        float pv[TR], qv[TN];
+#pragma unroll
+        for (int a = 0; a < TR; ++a) pv[a] = (r0 + a < n) ? P[(int64_t)(r0 + a) * ldp + h] : 0.f;
+#pragma unroll
+        for (int b = 0; b < TN; ++b) qv[b] = (c0 + b < Nc) ? Q[(int64_t)(c0 + b) * ldq + h] : 0.f;
+#pragma unroll
+        for (int a = 0; a < TR; ++a)
+#pragma unroll
+          for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(pv[a], qv[b], acc[a][b]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < TR; ++a)
+#pragma unroll
+      for (int b = 0; b < TN; ++b)
+        if (r0 + a < n && c0 + b < Nc) {
+          float* d = D + (r0 + a) * ldd + c0 + b;
+          *d = accumulate ? (*d + scale * acc[a][b]) : scale * acc[a][b];
+        }
+  }
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
     const float* __restrict__ logits, int64_t ldz, const float* __restrict__ x, int64_t ldx,
@@ -59,32 +236,59 @@ __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
   float* AS = SMEM ? smem + (size_t)n_cap * K : as_ws + (int64_t)base * K;
   float* deg = SMEM ? smem + 2 * (size_t)n_cap * K : smem;
 
-  // A. S = softmax(logits / temp), one warp per node row
-  for (int i = wid; i < n; i += nwarps) {
-    const float* zr = logits + (int64_t)(base + i) * ldz;
-    float m = -INFINITY;
-    for (int k = lane; k < K; k += 32) {
-      const float z = temp != 1.0f ? __fdiv_rn(zr[k], temp) : zr[k];
-      m = fmaxf(m, z);
+  // A. S = softmax(logits / temp).  Small K: one thread per node row (all rows of the graph in flight at once);
+  //    large K: one warp per row.  Row degrees (row sums of A) by one thread per row.
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int beg = rowptr[base + i], end = rowptr[base + i + 1];
+    float d = (float)(end - beg);
+    if (adj_val) {
+      d = 0.f;
+      for (int s = beg; s < end; ++s) d += adj_val[s];
     }
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float z = temp != 1.0f ? __fdiv_rn(zr[k], temp) : zr[k];
-      const float p = expf(z - m);
-      S[i * K + k] = p;
-      sum += p;
+    deg[i] = d;
+  }
+  if (K <= 32) {
+    for (int i = tid; i < n; i += blockDim.x) {
+      const float* zr = logits + (int64_t)(base + i) * ldz;
+      float z[32];
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < K) { z[k] = temp != 1.0f ? __fdiv_rn(zr[k], temp) : zr[k]; m = fmaxf(m, z[k]); }
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < K) { z[k] = expf(z[k] - m); sum += z[k]; }
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < K) {
+          const float p = __fdiv_rn(z[k], sum);
+          S[i * K + k] = p;
+          if (SMEM) Sg[i * K + k] = p;
+        }
     }
-    sum = warp_sum(sum);
-    for (int k = lane; k < K; k += 32) {
-      const float p = __fdiv_rn(S[i * K + k], sum);
-      S[i * K + k] = p;
-      if (SMEM) Sg[i * K + k] = p;
-    }
-    if (lane == 0) {
-      float d = 0.f;
-      for (int s = rowptr[base + i]; s < rowptr[base + i + 1]; ++s) d += adj_value(adj_val, s);
-      deg[i] = d;
+  } else {
+    for (int i = wid; i < n; i += nwarps) {
+      const float* zr = logits + (int64_t)(base + i) * ldz;
+      float m = -INFINITY;
+      for (int k = lane; k < K; k += 32) {
+        const float z = temp != 1.0f ? __fdiv_rn(zr[k], temp) : zr[k];
+        m = fmaxf(m, z);
+      }
+      m = warp_max(m);
+      float sum = 0.f;
+      for (int k = lane; k < K; k += 32) {
+        const float z = temp != 1.0f ? __fdiv_rn(zr[k], temp) : zr[k];
+        const float p = expf(z - m);
+        S[i * K + k] = p;
+        sum += p;
+      }
+      sum = warp_sum(sum);
+      for (int k = lane; k < K; k += 32) {
+        const float p = __fdiv_rn(S[i * K + k], sum);
+        S[i * K + k] = p;
+        if (SMEM) Sg[i * K + k] = p;
+      }
     }
   }
   __syncthreads();
@@ -105,38 +309,10 @@ __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
 
   float* ssg = ss_raw + (int64_t)g * K * K;
   float* oag = adj_raw + (int64_t)g * K * K;
-  for (int p = tid; p < K * K; p += blockDim.x) {
-    const int k = p / K, l = p - k * K;
-    float ss = 0.f, oa = 0.f;
-    for (int i = 0; i < n; ++i) {
-      const float sk = S[i * K + k];
-      ss += sk * S[i * K + l];
-      oa += sk * AS[i * K + l];
-    }
-    ssg[p] = ss;
-    oag[p] = oa;
-  }
-  if (out != nullptr) {
-    constexpr int KC = 8;
-    float* og = out + (int64_t)g * K * H;
-    const int chunks = ceil_div(K, KC);
-    for (int item = tid; item < chunks * H; item += blockDim.x) {
-      const int kc = (item / H) * KC, h = item % H;
-      float acc[KC];
-#pragma unroll
-      for (int j = 0; j < KC; ++j) acc[j] = 0.f;
-      const float* xp = x + (int64_t)base * ldx + h;
-      for (int i = 0; i < n; ++i) {
-        const float xv = __ldg(xp + (int64_t)i * ldx);
-#pragma unroll
-        for (int j = 0; j < KC; ++j)
-          if (kc + j < K) acc[j] += S[i * K + kc + j] * xv;
-      }
-#pragma unroll
-      for (int j = 0; j < KC; ++j)
-        if (kc + j < K) og[(int64_t)(kc + j) * H + h] = acc[j];
-    }
-  }
+  atb_tiled<4, 4>(S, K, K, S, K, K, n, ssg, K);    // S^T S
+  atb_tiled<4, 4>(S, K, K, AS, K, K, n, oag, K);   // S^T (A S)
+  if (out != nullptr)                               // S^T X, X streamed from global memory
+    atb_tiled<8, 4>(S, K, K, x + (int64_t)base * ldx, ldx, H, n, out + (int64_t)g * K * H, H);
   __syncthreads();  // ssg / oag visible to the whole CTA
 
   // D. losses and the normalised coarse adjacency
@@ -292,27 +468,22 @@ __global__ void __launch_bounds__(1024) mincut_bwd_kernel(
   const bool diag_only = (g_out_adj == nullptr);
   const float gdiag = -gmc / den;
   const float* gog = g_out ? g_out + (int64_t)g * K * H : nullptr;
-  for (int e = tid; e < n * K; e += blockDim.x) {
-    const int i = e / K, k = e - i * K;
-    float v;
-    if (diag_only) {
-      v = gdiag * (AS[e] + ATS[e]);
-    } else {
-      v = 0.f;
-      for (int l = 0; l < K; ++l) v += AS[i * K + l] * Gam[k * K + l] + ATS[i * K + l] * Gam[l * K + k];
-    }
-    v += cden * 2.f * deg[i] * Sr[e];
-    float o = 0.f;
-    for (int l = 0; l < K; ++l) o += Sr[i * K + l] * Gsym[l * K + k];
-    v += o;
-    if (gog) {
-      const float* xr = x + (int64_t)(base + i) * ldx;
-      const float* gr = gog + (int64_t)k * H;
-      float acc = 0.f;
-      for (int h = 0; h < H; ++h) acc += __ldg(xr + h) * __ldg(gr + h);
-      v += acc;
-    }
-    dS[e] = v;
+  // dS = [mincut trace / out_adj chain] + [den term] + [ortho] + [out term], as tiled small GEMMs
+  if (diag_only) {
+    for (int e = tid; e < n * K; e += blockDim.x)
+      dS[e] = gdiag * (AS[e] + ATS[e]) + cden * 2.f * deg[e / K] * Sr[e];
+  } else {
+    abt_tiled<4, 4>(AS, K, n, Gam, K, K, K, 1.f, dS, K, false);          // AS  Gamma^T
+    __syncthreads();
+    ab_tiled<4, 4>(ATS, K, n, Gam, K, K, K, 1.f, dS, K, true);           // A^T S Gamma
+    __syncthreads();
+    for (int e = tid; e < n * K; e += blockDim.x) dS[e] += cden * 2.f * deg[e / K] * Sr[e];
+  }
+  __syncthreads();
+  ab_tiled<4, 4>(Sr, K, n, Gsym, K, K, K, 1.f, dS, K, true);             // S (G' + G'^T) go
+  if (gog) {
+    __syncthreads();
+    abt_tiled<4, 4>(x + (int64_t)base * ldx, ldx, n, gog, H, K, H, 1.f, dS, K, true);   // x g_out^T
   }
   __syncthreads();
   // softmax backward, one warp per node row
@@ -327,12 +498,36 @@ __global__ void __launch_bounds__(1024) mincut_bwd_kernel(
     }
   }
   if (d_x != nullptr) {
-    for (int e = tid; e < n * H; e += blockDim.x) {
-      const int i = e / H, h = e - i * H;
-      float acc = 0.f;
-      if (gog)
-        for (int k = 0; k < K; ++k) acc += Sr[i * K + k] * __ldg(gog + (int64_t)k * H + h);
-      d_x[(int64_t)(base + i) * lddx + h] = acc;
+    float* dxg = d_x + (int64_t)base * lddx;
+    if (gog) {
+      // dX = S g_out: [n,K] x [K,H]; thread tile 4 rows x 4 columns, columns contiguous
+      const int rt = ceil_div(n, 4), ct = ceil_div(H, 4);
+      for (int t = tid; t < rt * ct; t += blockDim.x) {
+        const int r0 = (t / ct) * 4, c0 = (t % ct) * 4;
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        for (int k = 0; k < K; ++k) {
+          float sv[4], gv[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) sv[a] = (r0 + a < n) ? Sr[(r0 + a) * K + k] : 0.f;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) gv[b] = (c0 + b < H) ? __ldg(gog + (int64_t)k * H + c0 + b) : 0.f;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(sv[a], gv[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (r0 + a < n && c0 + b < H) dxg[(int64_t)(r0 + a) * lddx + c0 + b] = acc[a][b];
+      }
+    } else {
+      for (int e = tid; e < n * H; e += blockDim.x) dxg[(int64_t)(e / H) * lddx + e % H] = 0.f;
     }
   }
 }

@@ -104,11 +104,12 @@ class _Linear3xTF32(torch.autograd.Function):
             a3 = a_cat.view(c, DW_CHUNK, 3 * k)
             d3 = d_cat.view(c, DW_CHUNK, 3 * m)
             dl, dh = d3[:, :, :m].transpose(1, 2), d3[:, :, 2 * m:].transpose(1, 2)
-            xl, xh = a3[:, :, :k], a3[:, :, 2 * k:]
             with _tf32():
-                part = torch.bmm(dl, xh)
-                part.baddbmm_(dh, xl)
-                part.baddbmm_(dh, xh)
+                # dh^T [xl | xh] in ONE batched GEMM (a_cat = [xl | xh | xh]), then the dl^T xh cross term
+                both = torch.bmm(dh, a3[:, :, :2 * k])               # [c, m, 2k] = [dh^T xl | dh^T xh]
+                part = torch.bmm(dl, a3[:, :, 2 * k:])               # small cross term first
+            part = part + both[:, :, :k]
+            part = part + both[:, :, k:]
             dw = part.sum(0)                                     # fp32 adds across chunks
         if ctx.has_bias and ctx.needs_input_grad[2]:
             from . import ops
