@@ -393,7 +393,11 @@ int ghscn_gcn_deg_inv_sqrt(const int32_t* rowptr, const int32_t* perm, const flo
 int ghscn_edge_weights(const int32_t* rowptr, const int32_t* col, const int32_t* perm, const float* edge_weight,
                        const float* loop_weight, const float* dis, int64_t num_edges, int64_t num_rows,
                        int32_t normalize, int32_t rows_are_dst, float* w, ghscn_stream_t stream) {
-  GHSCN_REQUIRE(rowptr && col && perm && w && num_rows >= 0 && num_edges >= 0);
+  GHSCN_REQUIRE(rowptr && num_rows >= 0 && num_edges >= 0);
+  if (col == nullptr || perm == nullptr || w == nullptr) {
+    GHSCN_REQUIRE(num_edges == 0);  // an empty relation has zero-sized slot arrays (null device pointers)
+    return GHSCN_OK;
+  }
   GHSCN_REQUIRE(!normalize || dis != nullptr);
   if (num_rows == 0) return GHSCN_OK;
   edge_weights_kernel<<<ceil_div<int64_t>(num_rows, 256), 256, 0, as_stream(stream)>>>(

@@ -158,7 +158,7 @@ int ghscn_gat_scores(const int32_t* rowptr, const int32_t* col, const float* a_s
                      float negative_slope, int64_t num_rows, float* alpha, ghscn_stream_t stream) {
   GHSCN_REQUIRE(num_rows >= 0 && num_rows < ((int64_t)1 << 31));
   if (num_rows == 0) return GHSCN_OK;
-  GHSCN_REQUIRE(rowptr && col && a_src && alpha);
+  GHSCN_REQUIRE(rowptr && a_src);  // col / alpha are zero-sized for an empty relation
   gat_scores_kernel<<<(unsigned)ceil_div<int64_t>(num_rows, 8), 256, 0, as_stream(stream)>>>(
       rowptr, col, a_src, a_dst, negative_slope, (int)num_rows, alpha);
   GHSCN_LAUNCH_CHECK();
@@ -171,7 +171,7 @@ int ghscn_gat_pool_fwd(const int32_t* rowptr, const int32_t* col, const float* h
                        ghscn_stream_t stream) {
   GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && num_rows < ((int64_t)1 << 31));
   if (num_rows == 0) return GHSCN_OK;
-  GHSCN_REQUIRE(rowptr && col && hs && a_src && alpha && out && ldhs >= num_feat && ldout >= num_feat);
+  GHSCN_REQUIRE(rowptr && hs && a_src && out && ldhs >= num_feat && ldout >= num_feat);
   gat_scores_kernel<<<(unsigned)ceil_div<int64_t>(num_rows, 8), 256, 0, as_stream(stream)>>>(
       rowptr, col, a_src, a_dst, negative_slope, (int)num_rows, alpha);
   GHSCN_LAUNCH_CHECK();

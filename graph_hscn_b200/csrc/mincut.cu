@@ -561,7 +561,7 @@ int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x, int64_t l
   GHSCN_REQUIRE(num_graphs < ((int64_t)1 << 31) && num_nodes < ((int64_t)1 << 31));
   if (num_clusters > kMaxClusters) return GHSCN_E_UNSUPPORTED;
   if (num_graphs == 0) return GHSCN_OK;
-  GHSCN_REQUIRE(logits && ptr && rowptr && col && s_soft && ss_raw && adj_raw && stats && losses);
+  GHSCN_REQUIRE(logits && ptr && rowptr && s_soft && ss_raw && adj_raw && stats && losses);
   GHSCN_REQUIRE(ldz >= num_clusters && (out == nullptr || (x != nullptr && ldx >= num_feat)));
   GHSCN_REQUIRE(max_nodes_per_graph > 0);
   cudaStream_t stream = as_stream(stream_);
@@ -600,7 +600,7 @@ int ghscn_mincut_bwd(const float* s_soft, const float* x, int64_t ldx, const int
   GHSCN_REQUIRE(num_graphs >= 0 && num_nodes >= 0 && num_clusters > 0 && num_feat >= 0);
   if (num_clusters > kMaxClusters) return GHSCN_E_UNSUPPORTED;
   if (num_graphs == 0) return GHSCN_OK;
-  GHSCN_REQUIRE(s_soft && ptr && rowptr && col && rowptr_t && col_t && ss_raw && adj_raw && stats && d_logits);
+  GHSCN_REQUIRE(s_soft && ptr && rowptr && rowptr_t && ss_raw && adj_raw && stats && d_logits);
   GHSCN_REQUIRE(lddz >= num_clusters && max_nodes_per_graph > 0);
   GHSCN_REQUIRE((g_out == nullptr && d_x == nullptr) || x != nullptr);
   cudaStream_t stream = as_stream(stream_);

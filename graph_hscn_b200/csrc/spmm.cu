@@ -689,7 +689,7 @@ int ghscn_spmm(const int32_t* rowptr, const int32_t* col, const float* w, const 
   GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && ldx >= num_feat && ldy >= num_feat);
   GHSCN_REQUIRE(num_rows < ((int64_t)1 << 31) && num_feat < ((int64_t)1 << 24));
   if (num_rows == 0 || num_feat == 0) return GHSCN_OK;
-  GHSCN_REQUIRE(rowptr && col && x && y);
+  GHSCN_REQUIRE(rowptr && x && y);  // col may be null for an empty relation (zero slots)
   const bool vec4 = (num_feat % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                       reinterpret_cast<uintptr_t>(bias)) % 16 == 0);
@@ -702,7 +702,7 @@ int ghscn_spmm_pool(const int32_t* rowptr, const int32_t* col, const float* w, c
                     int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, ghscn_stream_t stream) {
   GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && ldx >= num_feat && ldy >= num_feat);
   if (num_rows == 0 || num_feat == 0) return GHSCN_OK;
-  GHSCN_REQUIRE(rowptr && col && x && y);
+  GHSCN_REQUIRE(rowptr && x && y);  // col may be null for an empty relation (zero slots)
   const bool vec4 = (num_feat % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                       reinterpret_cast<uintptr_t>(bias)) % 16 == 0);
@@ -716,7 +716,7 @@ int ghscn_spmm_edge_grad(const int32_t* rowptr, const int32_t* col, const int32_
                          int64_t num_edges, float* dw_edge, ghscn_stream_t stream) {
   GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && num_edges >= 0);
   if (num_rows == 0) return GHSCN_OK;
-  GHSCN_REQUIRE(rowptr && col && x && dy && dw_edge);
+  GHSCN_REQUIRE(rowptr && x && dy && (dw_edge || num_edges == 0));
   spmm_edge_grad_kernel<<<(unsigned)ceil_div<int64_t>(num_rows, 8), 256, 0, as_stream(stream)>>>(
       rowptr, col, perm, x, ldx, dy, lddy, (int)num_rows, (int)num_feat, num_edges, dw_edge);
   GHSCN_LAUNCH_CHECK();
