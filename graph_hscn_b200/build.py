@@ -29,6 +29,9 @@ NVCC_FLAGS = [
 ]
 
 
+EXTRA = os.environ.get("GHSCN_NVCC_EXTRA", "").split()   # e.g. -DGHSCN_WIDE_ROWS=32 for tuning experiments
+
+
 def _sources():
     return sorted(CSRC.glob("*.cu"))
 
@@ -38,7 +41,7 @@ def _fingerprint() -> str:
     for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [REPO_ROOT / "include" / "ghscn.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + EXTRA).encode())
     return h.hexdigest()
 
 
@@ -54,7 +57,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     fp = _fingerprint()
     if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == fp:
         return LIB_PATH
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", str(REPO_ROOT / "include"), "-I", str(CSRC),
+    cmd = [find_nvcc(), *NVCC_FLAGS, *EXTRA, "-I", str(REPO_ROOT / "include"), "-I", str(CSRC),
            "-o", str(LIB_PATH), *map(str, _sources())]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     (LIB_DIR / "build.log").write_text(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)

@@ -138,21 +138,28 @@ __global__ void __launch_bounds__(256) spmm_kernel(const int* __restrict__ rowpt
 // gather with ~3 slots per row needs to approach HBM/L2 bandwidth.
 constexpr int kRowsPerCta = 64;
 constexpr int kSlotCap = 1024;
+#ifndef GHSCN_WIDE_ROWS
+#define GHSCN_WIDE_ROWS 64
+#endif
+#ifndef GHSCN_WIDE_MINBLOCKS
+#define GHSCN_WIDE_MINBLOCKS 2
+#endif
+constexpr int kWideRows = GHSCN_WIDE_ROWS;   // rows per CTA of the register-gather kernel (tuned: see profiles/README)
 
 template <int ITERS, bool WEIGHTED>
-__global__ void __launch_bounds__(256, 2) spmm_wide_kernel(const int* __restrict__ rowptr,
+__global__ void __launch_bounds__(256, GHSCN_WIDE_MINBLOCKS) spmm_wide_kernel(const int* __restrict__ rowptr,
                                                            const int* __restrict__ col,
                                                            const float* __restrict__ w,
                                                            const float* __restrict__ x, int64_t ldx,
                                                            float* __restrict__ y, int64_t ldy,
                                                            const float* __restrict__ bias, int num_rows,
                                                            int num_feat, int relu) {
-  __shared__ int s_rowptr[kRowsPerCta + 1];
+  __shared__ int s_rowptr[kWideRows + 1];
   __shared__ int s_col[kSlotCap];
   __shared__ float s_w[kSlotCap];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int row0 = blockIdx.x * kRowsPerCta;
-  const int nrows = min(kRowsPerCta, num_rows - row0);
+  const int row0 = blockIdx.x * kWideRows;
+  const int nrows = min(kWideRows, num_rows - row0);
   if (tid <= nrows) s_rowptr[tid] = rowptr[row0 + tid];
   __syncthreads();
   const int sbeg = s_rowptr[0];
@@ -507,7 +514,7 @@ template <int ITERS>
 static int launch_spmm_wide(const int* rowptr, const int* col, const float* w, const float* x, int64_t ldx,
                             float* y, int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, int relu,
                             cudaStream_t stream) {
-  dim3 grid((unsigned)ceil_div<int64_t>(num_rows, kRowsPerCta), (unsigned)ceil_div<int64_t>(num_feat, 128 * ITERS));
+  dim3 grid((unsigned)ceil_div<int64_t>(num_rows, kWideRows), (unsigned)ceil_div<int64_t>(num_feat, 128 * ITERS));
   if (w)
     spmm_wide_kernel<ITERS, true><<<grid, 256, 0, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias, (int)num_rows,
                                                              (int)num_feat, relu);
