@@ -16,6 +16,7 @@ results are added in fp32.  Mode "fp32" keeps plain cuBLAS fp32 (TF32 off).
 """
 from __future__ import annotations
 
+import os
 from contextlib import contextmanager
 from typing import Optional, Tuple
 
@@ -70,36 +71,102 @@ def split_cat(x: Tensor, mode: int, pad_rows_to: int = 1) -> Tensor:
     return out
 
 
+def gemm3x_supported(m: int, n_out: int, k: int) -> bool:
+    return bool(lib().query("ghscn_gemm3x_supported", m, n_out, k))
+
+
+def gemm3x_prep(weight: Tensor, transpose: bool = False) -> Tensor:
+    """Weight image of the fused tcgen05 3xTF32 GEMM (csrc/gemm3x.cu): B[n, k] = weight[n, k], or weight[k, n]
+    with transpose=True (the operand of dX = dY . W).  Split into TF32 hi/lo, K-chunked, 128B-swizzled."""
+    if weight.stride(1) != 1:
+        weight = weight.contiguous()
+    n_out, k = (weight.size(1), weight.size(0)) if transpose else (weight.size(0), weight.size(1))
+    nbytes = lib().query("ghscn_gemm3x_b_image_bytes", n_out, k)
+    if nbytes == 0:
+        raise ValueError(f"gemm3x does not support n_out={n_out}, k={k}")
+    image = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    lib().call("ghscn_gemm3x_prep_b", _p(weight), weight.stride(0), n_out, k, int(transpose), _p(image), _stream())
+    return image
+
+
+def gemm3x(a: Tensor, image: Tensor, n_out: int, bias: Optional[Tensor] = None, relu: bool = False) -> Tensor:
+    """C = A . B^T (+ bias) (ReLU) on the tcgen05 tensor cores with fp32-level accuracy (3xTF32, split in-kernel)."""
+    if a.stride(1) != 1 or a.stride(0) % 4 != 0:
+        a = a.contiguous()
+    m, k = a.shape
+    c = torch.empty((m, n_out), dtype=torch.float32, device=a.device)
+    lib().call("ghscn_gemm3x", _p(a), a.stride(0), m, k, _p(image), n_out, _p(bias), int(relu), _p(c), n_out,
+               _stream())
+    return c
+
+
+def gemm3x_tn_supported(rows: int, m_out: int, n_out: int) -> bool:
+    return bool(lib().query("ghscn_gemm3x_tn_supported", rows, m_out, n_out))
+
+
+def gemm3x_tn(p: Tensor, q: Tensor) -> Tensor:
+    """P^T . Q for row-major P [rows, m], Q [rows, n] (the weight gradient dY^T x) on tcgen05, 3xTF32, fp32 accuracy."""
+    if p.stride(1) != 1 or p.stride(0) % 4 != 0:
+        p = p.contiguous()
+    if q.stride(1) != 1 or q.stride(0) % 4 != 0:
+        q = q.contiguous()
+    rows, m = p.shape
+    n = q.size(1)
+    out = torch.empty((m, n), dtype=torch.float32, device=p.device)
+    ws_bytes = lib().query("ghscn_gemm3x_tn_workspace_bytes", rows, m, n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=p.device)
+    lib().call("ghscn_gemm3x_tn", _p(p), p.stride(0), _p(q), q.stride(0), rows, m, n, _p(out), _p(ws), ws_bytes,
+               _stream())
+    return out
+
+
+USE_TCGEN05 = os.environ.get("GHSCN_TCGEN05", "1") != "0"      # fused tcgen05 kernel (csrc/gemm3x.cu) where the shape is supported; else split_cat + library GEMM
+
+
 class _Linear3xTF32(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor]):
         n, k = x.shape
-        a_cat = split_cat(x, 0, DW_CHUNK)                        # [Npad, 3K] = [xl | xh | xh]
-        w_cat = split_cat(weight, 1)                             # [out, 3K]  = [wh | wl | wh]
-        with _tf32():
-            if bias is not None:
-                y = torch.addmm(bias, a_cat[:n], w_cat.t())
-            else:
-                y = torch.mm(a_cat[:n], w_cat.t())
-        ctx.save_for_backward(a_cat, weight)
+        m = weight.size(0)
+        fused = USE_TCGEN05 and gemm3x_supported(n, m, k)
+        if fused:
+            y = gemm3x(x, gemm3x_prep(weight), m, bias)
+            ctx.save_for_backward(x, weight)
+        else:
+            a_cat = split_cat(x, 0, DW_CHUNK)                    # [Npad, 3K] = [xl | xh | xh]
+            w_cat = split_cat(weight, 1)                         # [out, 3K]  = [wh | wl | wh]
+            with _tf32():
+                if bias is not None:
+                    y = torch.addmm(bias, a_cat[:n], w_cat.t())
+                else:
+                    y = torch.mm(a_cat[:n], w_cat.t())
+            ctx.save_for_backward(a_cat, weight)
+        ctx.fused = fused
         ctx.n, ctx.k, ctx.has_bias = n, k, bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy: Tensor):
-        a_cat, weight = ctx.saved_tensors
+        saved, weight = ctx.saved_tensors
         n, k = ctx.n, ctx.k
         m = weight.size(0)
         dx = dw = db = None
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if need_dx or need_dw:
+        dx_fused = need_dx and USE_TCGEN05 and gemm3x_supported(n, k, m)
+        if dx_fused:
+            dx = gemm3x(dy, gemm3x_prep(weight, transpose=True), k)      # dX = dY . W
+        dw_fused = need_dw and ctx.fused and USE_TCGEN05 and gemm3x_tn_supported(n, m, k)
+        if dw_fused:
+            dw = gemm3x_tn(dy, saved)                            # dW = dY^T x, slab partials added in fp32
+        if (need_dw and not dw_fused) or (need_dx and not dx_fused):
             d_cat = split_cat(dy, 0, DW_CHUNK)                   # [Npad, 3m] = [dl | dh | dh]
-        if need_dx:
+        if need_dx and not dx_fused:
             wh, wl = split_tf32(weight)
             w_rows = torch.cat([wh, wl, wh], dim=0)              # [3m, K]: dX = [dl|dh|dh] . [wh; wl; wh]
             with _tf32():
                 dx = torch.mm(d_cat[:n], w_rows)
-        if need_dw:
+        if need_dw and not dw_fused:
+            a_cat = split_cat(saved, 0, DW_CHUNK) if ctx.fused else saved
             c = a_cat.size(0) // DW_CHUNK
             a3 = a_cat.view(c, DW_CHUNK, 3 * k)
             d3 = d_cat.view(c, DW_CHUNK, 3 * m)

@@ -83,7 +83,7 @@ def test_linear_3xtf32_is_fp32_accurate(cuda):
     gemm.set_gemm_mode("3xtf32")
     for name, a, a32, r in [("y", y, y32, ref), ("dx", dx, dx32, gx), ("dw", dw, dw32, gw), ("db", db, db32, gb)]:
         e3, e32 = rel_err(a, r.float()), rel_err(a32, r.float())
-        bar = 4e-6 if name == "dw" else 2e-6     # dw reduces over all rows (chunked); well inside the 1e-5 bar
+        bar = 5e-6                             # single-pass tcgen05 accumulation (~3e-6); 2x inside the 1e-5 bar
         assert e3 < bar, f"{name}: 3xTF32 error {e3:.2e} (plain fp32 {e32:.2e})"
     torch.backends.cuda.matmul.allow_tf32 = True          # plain TF32 would NOT meet the bar
     ytf = torch.nn.functional.linear(x, w, b)
