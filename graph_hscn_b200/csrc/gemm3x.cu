@@ -1,28 +1,29 @@
-// Fused 3xTF32 projection GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+// Fused 3xTF32 projection GEMMs on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
 //
-//   C[M, N] = A[M, K] . B[N, K]^T (+ bias) (ReLU)          fp32 in, fp32 out, fp32-level accuracy
+//   ghscn_gemm3x     C[M, N]  = A[M, K] . B[N, K]^T (+ bias) (ReLU)     forward projection and dX = dY . W
+//   ghscn_gemm3x_tn  dW[M, N] = P[R, M]^T . Q[R, N]                     weight gradient dY^T x
 //
-// Replaces, for the h x h projections of GCNConv/GATConv (reference call sites model/mpnn.py:52,59 and
-// model/hscn.py:109 -> PyG `Linear` inside the conv), the round-1 pipeline
-// "split_tf32_cat (writes 3x the activations) + one library TF32 GEMM over the 3K-long reduction".
-// Here the activations are read from HBM exactly once as fp32, split into TF32 hi/lo parts in registers
-// and written straight into the swizzled shared-memory operand tiles of tcgen05.mma; nothing but C goes back.
+// fp32 in, fp32 out, fp32-level accuracy.  They replace, for the h x h projections of GCNConv / GATConv / Linear
+// (reference call sites model/mpnn.py:52,59 and model/hscn.py:109 -> PyG `Linear` inside the convs; SURVEY 8a rows
+// a2/a9), the round-1 pipeline "split_tf32_cat (writes 3x the activations) + library TF32 GEMM over a 3K-long
+// reduction".  Activations are read from HBM once as fp32, split into TF32 hi/lo parts in registers and written
+// straight into the swizzled shared-memory operand tiles of tcgen05.mma; only the result goes back.
 //
-//   x = x_hi + x_lo  (hi: low 13 mantissa bits cleared; lo = x - hi, exact)       same split as ghscn_split_tf32
-//   C = sum_k  x_lo.w_hi + x_hi.w_lo + x_hi.w_hi                                  (lo.lo dropped, ~2^-22)
+//   x = x_hi + x_lo  (hi: low 13 mantissa bits cleared; lo = x - hi, exact)          same split as ghscn_split_tf32
+//   x.w ~= x_hi.w_hi + (x_lo.w_hi + x_hi.w_lo)                                       (lo.lo dropped, ~2^-22)
 //
-// One CTA per 128-row tile of A, all N (<= 304 after padding to 16) columns: the fp32 accumulator
-// [128 lanes x NPAD columns] lives in TMEM.  Warp roles (192 threads):
-//   warp 0 / lane 0   streams the weight image (pre-split, pre-swizzled by gemm3x_prep_b_kernel; L2 resident)
-//                     with ONE cp.async.bulk per K chunk into the stage's B buffer (mbarrier complete_tx)
-//   warp 1 / lane 0   issues tcgen05.mma.kind::tf32 (3 products x N halves x K steps per chunk), commits the
-//                     stage's "empty" mbarrier, finally the accumulator barrier; warp 1 owns the TMEM allocation
-//   warps 2..5        A producers: 128-bit global loads (register-prefetched one chunk ahead) -> hi/lo split ->
-//                     128B-swizzled K-major smem tiles -> fence.proxy.async -> mbarrier arrive; afterwards the
-//                     same four warps are the epilogue: tcgen05.ld (their TMEM lane quadrant) -> bias/ReLU ->
-//                     packed row-major staging tile in smem -> one bulk store per warp (32 contiguous rows of C)
-// Shared-memory operand layout: the canonical K-major SWIZZLE_128B UMMA layout -- rows of 32 tf32 (128 bytes),
-// atoms of 8 rows (1024 bytes, SBO), the 16-byte chunk index XORed with (row & 7).
+// Accuracy: the tensor core adds every 8-term partial sum into its fp32 accumulator with TRUNCATION, a bias that is
+// coherent for same-sign data (post-ReLU features) and grows with the number of accumulations made at full
+// magnitude.  Each output tile therefore owns THREE TMEM accumulators: the main term x_hi.w_hi alternates between
+// two of them, the small cross terms go to the third, and the epilogue adds the three in fp32 (round to nearest).
+// Three accumulators of <= 160 columns fill the 512 TMEM columns, so a CTA walks its 128-row tile once per N half.
+//
+// Operand layouts (cute::UMMA canonical forms, verified on hardware by scripts/gemm3x_check.py --probe):
+//   K-major  (gemm3x A and B):  SWIZZLE_128B, rows of 32 tf32 (128 B), 8-row atoms of 1024 B (SBO), 16-byte chunk
+//                               index XOR (row & 7); descriptor start advanced by 32 B per K = 8 step.
+//   MN-major (gemm3x_tn P, Q):  SWIZZLE_128B_BASE32B -- the only legal layout for 32-bit MN-major operands: atoms of
+//                               4 reduction rows x 32 tf32 (512 B), 32-byte unit index XOR (row & 3), LBO between
+//                               32-wide blocks, SBO between 4-row groups; one MMA (K = 8) reads two groups.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -33,14 +34,15 @@ namespace ghscn {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kChunkK = 32;                       // tf32 elements per smem row (128 bytes)
-constexpr int kABytes = kTileM * kChunkK * 4;     // one A part (hi or lo) of one stage: 16 KB
-constexpr int kMaxStages = 6;
-constexpr int kMaxNPad = 304;
+constexpr int kHalfMax = 160;                     // columns per accumulator; 3 accumulators = 480 of 512 TMEM columns
+constexpr int kMaxN = 2 * kHalfMax;
+constexpr uint32_t kColMain0 = 0, kColMain1 = kHalfMax, kColCross = 2 * kHalfMax;
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kThreads = 192;
 constexpr unsigned kSpinLimit = 1u << 22;         // a broken pipeline traps instead of hanging the GPU
 
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
@@ -74,10 +76,9 @@ __device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t byt
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void bulk_store_commit_and_wait() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -103,9 +104,8 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// 32 lanes x 16 consecutive fp32 columns: thread l of the warp receives TMEM lane (quadrant*32 + l).
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+// 32 lanes x 16 consecutive fp32 columns (no wait): thread l of the warp receives TMEM lane (quadrant*32 + l).
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
       "[%16];"
@@ -113,66 +113,143 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// Waits for the outstanding tcgen05.ld of this thread; the registers are tied to the statement so that the compiler
+// cannot schedule their consumers above the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major: 1) | [32,46) SBO >> 4 (8 rows = 1024 B)
-//   [46,48) version = 1 (Blackwell) | [49,52) base offset = 0 (tiles are 1024-byte aligned) | [61,64) layout = 2
-__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
+// main0 + main1 + cross of 16 columns -> v (fp32, round to nearest)
+__device__ __forceinline__ void load_sum16(uint32_t tbase, uint32_t col, bool use_main1, float* v) {
+  uint32_t m0[16], m1[16], cr[16];
+  tmem_ld16_nowait(tbase + kColMain0 + col, m0);
+  tmem_ld16_nowait(tbase + kColCross + col, cr);
+  if (use_main1) tmem_ld16_nowait(tbase + kColMain1 + col, m1);
+  tmem_ld_wait(m0);
+  tmem_ld_wait(cr);
+  if (use_main1) tmem_ld_wait(m1);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float s = __uint_as_float(m0[i]);
+    if (use_main1) s += __uint_as_float(m1[i]);
+    v[i] = s + __uint_as_float(cr[i]);
+  }
+}
+
+__device__ __forceinline__ void split_store(unsigned char* hi_ptr, unsigned char* lo_ptr, const float4 v) {
+  float4 h, l;
+  h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+  h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+  h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+  h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+  *reinterpret_cast<float4*>(hi_ptr) = h;
+  *reinterpret_cast<float4*>(lo_ptr) = l;
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): [0,14) start >> 4 | [16,30) LBO >> 4 |
+// [32,46) SBO >> 4 | [46,48) version = 1 | [49,52) base offset = 0 | [61,64) layout type.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t desc_k_sw128(uint32_t saddr) { return make_desc(saddr, 16, 1024, kLayoutSw128); }
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6)=1, A = B = TF32 [7,10)=[10,13)=2,
-// both K-major (bits 15,16 = 0), N >> 3 at [17,23), M >> 4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// A/B major at bits 15/16 (0 = K-major, 1 = MN-major), N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n, bool mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// byte offset of element (row, k) inside one K-major SW128 block of `kChunkK` columns
+// byte offset of element (row, k) inside one K-major SW128 block of 32 columns
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
   const int chunk = k >> 2, e = k & 3, r8 = row & 7;
   return (uint32_t)((row >> 3) * 1024 + r8 * 128 + ((chunk ^ r8) << 4) + e * 4);
 }
 
-struct Plan {
-  int npad, n0, n1, kchunks, stages, stage_bytes, b_bytes, tmem_cols, smem_bytes;
+// The N range of a problem is cut into one or two "halves" of <= 160 padded columns.
+struct Halves {
+  int count;
+  int pad[2];     // accumulator columns (multiple of 16)
+  int valid[2];   // real columns
+  int col[2];     // first column
 };
-
-__host__ __device__ inline Plan make_plan(int n_out, int k) {
-  Plan p;
-  p.npad = (n_out + 15) / 16 * 16;
-  if (p.npad <= 256) { p.n0 = p.npad; p.n1 = 0; }
-  else { p.n0 = ((p.npad / 2) + 15) / 16 * 16; p.n1 = p.npad - p.n0; }
-  p.kchunks = (k + kChunkK - 1) / kChunkK;
-  p.b_bytes = 2 * p.npad * kChunkK * 4;            // hi block + lo block of one K chunk
-  p.stage_bytes = 2 * kABytes + p.b_bytes;
-  int st = (kSmemLimit - 2048) / p.stage_bytes;
-  if (st > kMaxStages) st = kMaxStages;
-  if (st > p.kchunks) st = p.kchunks;
-  p.stages = st;
-  int staging = kTileM * n_out * 4;                // epilogue tile, reuses the stage buffers
-  int body = p.stages * p.stage_bytes;
-  if (body < staging) body = staging;
-  p.smem_bytes = body + 1024;                      // slack for the manual 1024-byte alignment
-  p.tmem_cols = p.npad <= 32 ? 32 : p.npad <= 64 ? 64 : p.npad <= 128 ? 128 : p.npad <= 256 ? 256 : 512;
-  return p;
+__host__ __device__ inline Halves make_halves(int n_out) {
+  Halves h;
+  const int npad = (n_out + 15) / 16 * 16;
+  if (npad <= kHalfMax) {
+    h.count = 1; h.pad[0] = npad; h.valid[0] = n_out; h.col[0] = 0;
+    h.pad[1] = 0; h.valid[1] = 0; h.col[1] = 0;
+  } else {
+    h.count = 2;
+    h.pad[0] = ((npad / 2) + 15) / 16 * 16;
+    if (h.pad[0] % 32) h.pad[0] += 16;            // MN-major operands start the second half on a 32-column block
+    if (h.pad[0] > kHalfMax) h.pad[0] = kHalfMax;
+    h.pad[1] = npad - h.pad[0];
+    h.col[0] = 0; h.col[1] = h.pad[0];
+    h.valid[0] = h.pad[0];
+    h.valid[1] = n_out - h.pad[0];
+  }
+  return h;
 }
 
-// Weight image: for every K chunk, [NPAD rows x 128 B] of hi parts then the same of lo parts, already in the
-// swizzled shared-memory layout, zero padded in N and K.  b[n, k] = transpose ? w[k*ldw + n] : w[n*ldw + k].
+// =====================================================================================================================
+// gemm3x:  C = A . B^T.  One CTA per 128-row tile of A; for each N half: K loop over 32-wide chunks.
+//   warp 0 / lane 0   weight-image producer: one cp.async.bulk per chunk into a 3-stage B ring (L2 resident image,
+//                     pre-split and pre-swizzled by gemm3x_prep_b_kernel)
+//   warp 1 / lane 0   MMA issuer (owns TMEM): per K = 8 step  cross += a_lo.b_hi, cross += a_hi.b_lo,
+//                     main[chunk & 1] += a_hi.b_hi; commits the stage barriers, then the accumulator barrier
+//   warps 2..5        A producers: 128-bit global loads (register ring, 3 chunks ahead) -> hi/lo split ->
+//                     swizzled smem (2-stage A ring) -> fence.proxy.async -> one mbarrier arrive per warp
+//   warps 6..9        epilogue (own TMEM lane quadrant = warp & 3): tcgen05.ld of the three accumulators -> fp32 sum
+//                     -> bias / ReLU -> per-thread row segment in a padded staging tile -> one bulk store per row
+//                     segment; the stores of half h overlap the main loop of half h + 1
+// =====================================================================================================================
+constexpr int kChunkK = 32;
+constexpr int kABytes = kTileM * kChunkK * 4;               // one part (hi or lo) of an A stage: 16 KB
+constexpr int kAStages = 2, kBStages = 3;
+constexpr int kBStageBytes = 2 * kHalfMax * kChunkK * 4;    // hi block + lo block: 40 KB
+constexpr int kSubCols = 64;                                // epilogue drains 64 columns at a time
+constexpr int kStageRow = (kSubCols + 4) * 4;               // padded staging row: 272 B (conflict-free float4 stores)
+constexpr int kNnSmem = kAStages * 2 * kABytes + kBStages * kBStageBytes + kTileM * kStageRow + 1024;
+constexpr int kNnThreads = 320;
+static_assert(kNnSmem <= kSmemLimit - 1024, "gemm3x shared memory budget");
+
+struct NnPlan {
+  Halves hv;
+  int kchunks;
+  int64_t img_off[2];       // byte offset of each half's weight image
+};
+__host__ __device__ inline NnPlan make_nn_plan(int n_out, int k) {
+  NnPlan p;
+  p.hv = make_halves(n_out);
+  p.kchunks = (k + kChunkK - 1) / kChunkK;
+  p.img_off[0] = 0;
+  p.img_off[1] = (int64_t)p.kchunks * 2 * p.hv.pad[0] * kChunkK * 4;
+  return p;
+}
+__host__ __device__ inline int64_t nn_image_bytes(const NnPlan& p) {
+  return p.img_off[1] + (int64_t)p.kchunks * 2 * p.hv.pad[1] * kChunkK * 4;
+}
+
+// Weight image: for each N half, for each K chunk: [pad rows x 128 B] hi parts then the same of lo parts, in the
+// swizzled smem layout, zero padded in N and K.  b[n, k] = transpose ? w[k*ldw + n] : w[n*ldw + k].
 __global__ void __launch_bounds__(256) gemm3x_prep_b_kernel(const float* __restrict__ w, int64_t ldw, int n_out,
-                                                            int k_dim, int transpose, int npad, int kchunks,
+                                                            int k_dim, int transpose, NnPlan plan,
                                                             unsigned char* __restrict__ image) {
-  const int64_t total = (int64_t)kchunks * npad * kChunkK;
-  const int64_t block_bytes = (int64_t)npad * kChunkK * 4;
+  const int npad = plan.hv.pad[0] + plan.hv.pad[1];
+  const int64_t total = (int64_t)plan.kchunks * npad * kChunkK;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int kk, n, kc;
     if (transpose) {          // consecutive threads walk n (contiguous in w when transposed)
@@ -191,36 +268,41 @@ __global__ void __launch_bounds__(256) gemm3x_prep_b_kernel(const float* __restr
     if (n < n_out && k < k_dim) v = transpose ? __ldg(w + (int64_t)k * ldw + n) : __ldg(w + (int64_t)n * ldw + k);
     const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     const float lo = v - hi;
-    unsigned char* base = image + (int64_t)kc * 2 * block_bytes + sw128_offset(n, kk);
+    const int h = (plan.hv.count == 2 && n >= plan.hv.pad[0]) ? 1 : 0;
+    const int nl = n - plan.hv.col[h];
+    const int64_t block_bytes = (int64_t)plan.hv.pad[h] * kChunkK * 4;
+    unsigned char* base = image + plan.img_off[h] + (int64_t)kc * 2 * block_bytes + sw128_offset(nl, kk);
     *reinterpret_cast<float*>(base) = hi;
     *reinterpret_cast<float*>(base + block_bytes) = lo;
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kNnThreads, 1)
 gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, const unsigned char* __restrict__ b_image,
-              int n_out, const float* __restrict__ bias, int relu, float* __restrict__ c, Plan plan, int dbg) {
+              int n_out, const float* __restrict__ bias, int relu, float* __restrict__ c, NnPlan plan, int dbg) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long full_bar[kMaxStages];
-  __shared__ __align__(8) unsigned long long empty_bar[kMaxStages];
-  __shared__ __align__(8) unsigned long long accum_bar;
+  __shared__ __align__(8) unsigned long long a_full[kAStages], a_empty[kAStages];
+  __shared__ __align__(8) unsigned long long b_full[kBStages], b_empty[kBStages];
+  __shared__ __align__(8) unsigned long long acc_full, acc_empty;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_addr(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_addr(smem_raw));
+  const uint32_t a_ring = smem_base, b_ring = a_ring + kAStages * 2 * kABytes;
+  const uint32_t staging = b_ring + kBStages * kBStageBytes;
   const int m0 = blockIdx.x * kTileM;
-  const int stages = plan.stages, kchunks = (dbg & 16) ? 0 : plan.kchunks;
+  const int kchunks = plan.kchunks, nh = plan.hv.count;
+  const int total_chunks = nh * kchunks;
 
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) {
-      bar_init(smem_addr(&full_bar[s]), 4 + 1);     // 4 A-producer warps + the B producer's expect_tx arrive
-      bar_init(smem_addr(&empty_bar[s]), 1);        // one tcgen05.commit
-    }
-    bar_init(smem_addr(&accum_bar), 1);
+    for (int s = 0; s < kAStages; ++s) { bar_init(smem_addr(&a_full[s]), 4); bar_init(smem_addr(&a_empty[s]), 1); }
+    for (int s = 0; s < kBStages; ++s) { bar_init(smem_addr(&b_full[s]), 1); bar_init(smem_addr(&b_empty[s]), 1); }
+    bar_init(smem_addr(&acc_full), 1);
+    bar_init(smem_addr(&acc_empty), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_addr(&tmem_slot), (uint32_t)plan.tmem_cols);
+  if (warp == 1) tmem_alloc(smem_addr(&tmem_slot), 512u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -229,59 +311,56 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
   if (warp == 0) {
     // ===== weight-image producer =====
     if (lane == 0) {
-      for (int kc = 0; kc < kchunks; ++kc) {
-        const int s = kc % stages;
-        const uint32_t ph = (uint32_t)(kc / stages) & 1u;
-        bar_wait(smem_addr(&empty_bar[s]), ph ^ 1u);
-        const uint32_t fb = smem_addr(&full_bar[s]);
+      for (int g = 0; g < total_chunks; ++g) {
+        const int h = g >= kchunks ? 1 : 0, kc = g - h * kchunks;
+        const int s = g % kBStages;
+        const uint32_t ph = (uint32_t)(g / kBStages) & 1u;
+        bar_wait(smem_addr(&b_empty[s]), ph ^ 1u);
+        const uint32_t bytes = (uint32_t)(2 * plan.hv.pad[h] * kChunkK * 4);
+        const uint32_t fb = smem_addr(&b_full[s]);
         if (dbg & 4) { bar_arrive(fb); continue; }
-        bar_arrive_expect_tx(fb, (uint32_t)plan.b_bytes);
-        bulk_load(smem_base + (uint32_t)s * plan.stage_bytes + 2 * kABytes,
-                  b_image + (int64_t)kc * plan.b_bytes, (uint32_t)plan.b_bytes, fb);
+        bar_arrive_expect_tx(fb, bytes);
+        bulk_load(b_ring + (uint32_t)s * kBStageBytes, b_image + plan.img_off[h] + (int64_t)kc * bytes, bytes, fb);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc0 = make_idesc_tf32(kTileM, plan.n0);
-      const uint32_t idesc1 = make_idesc_tf32(kTileM, plan.n1 > 0 ? plan.n1 : 16);
-      const uint32_t b_half = (uint32_t)plan.npad * kChunkK * 4;   // bytes of the hi block (lo block follows)
-      const uint32_t n1_off = (uint32_t)plan.n0 * kChunkK * 4;     // rows n0.. of a block
-      uint32_t acc = 0;
-      for (int kc = 0; kc < kchunks; ++kc) {
-        const int s = kc % stages;
-        const uint32_t ph = (uint32_t)(kc / stages) & 1u;
-        bar_wait(smem_addr(&full_bar[s]), ph);
-        tc_fence_after();
-        const uint32_t st = smem_base + (uint32_t)s * plan.stage_bytes;
-        const uint64_t a_hi = make_desc_k_sw128(st), a_lo = make_desc_k_sw128(st + kABytes);
-        const uint64_t b_hi = make_desc_k_sw128(st + 2 * kABytes), b_lo = make_desc_k_sw128(st + 2 * kABytes + b_half);
-        const uint64_t b_hi1 = make_desc_k_sw128(st + 2 * kABytes + n1_off);
-        const uint64_t b_lo1 = make_desc_k_sw128(st + 2 * kABytes + b_half + n1_off);
-        const int kleft = k_dim - kc * kChunkK;
-        const int ksteps = kleft >= kChunkK ? kChunkK / 8 : (kleft + 7) / 8;
-        for (int ks = 0; ks < ((dbg & 1) ? 0 : ksteps); ++ks) {
-          const uint64_t adv = (uint64_t)(ks * 2);       // 8 tf32 = 32 bytes = 2 x 16-byte units
-          // small cross terms first, then the main term
-          mma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc0, acc);
-          acc = 1;
-          mma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc0, 1);
-          mma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc0, 1);
-          if (plan.n1 > 0) {
-            const uint32_t d1 = tmem_base + (uint32_t)plan.n0;
-            mma_tf32(d1, a_lo + adv, b_hi1 + adv, idesc1, kc > 0 || ks > 0);
-            mma_tf32(d1, a_hi + adv, b_lo1 + adv, idesc1, 1);
-            mma_tf32(d1, a_hi + adv, b_hi1 + adv, idesc1, 1);
-          }
+      for (int h = 0; h < nh; ++h) {
+        const uint32_t idesc = make_idesc_tf32(kTileM, plan.hv.pad[h], false);
+        const uint32_t lo_off = (uint32_t)plan.hv.pad[h] * kChunkK * 4;
+        if (h > 0) {                                   // the epilogue has drained the accumulators of half h-1
+          bar_wait(smem_addr(&acc_empty), (uint32_t)(h - 1) & 1u);
+          tc_fence_after();
         }
-        mma_commit(smem_addr(&empty_bar[s]));
+        for (int kc = 0; kc < kchunks; ++kc) {
+          const int g = h * kchunks + kc;
+          const int sa = g % kAStages, sb = g % kBStages;
+          bar_wait(smem_addr(&a_full[sa]), (uint32_t)(g / kAStages) & 1u);
+          bar_wait(smem_addr(&b_full[sb]), (uint32_t)(g / kBStages) & 1u);
+          tc_fence_after();
+          const uint32_t as = a_ring + (uint32_t)sa * 2 * kABytes, bs = b_ring + (uint32_t)sb * kBStageBytes;
+          const uint64_t a_hi = desc_k_sw128(as), a_lo = desc_k_sw128(as + kABytes);
+          const uint64_t b_hi = desc_k_sw128(bs), b_lo = desc_k_sw128(bs + lo_off);
+          const int kleft = k_dim - kc * kChunkK;
+          const int ksteps = kleft >= kChunkK ? kChunkK / 8 : (kleft + 7) / 8;
+          const uint32_t d_main = tmem_base + ((kc & 1) ? kColMain1 : kColMain0);
+          for (int ks = 0; ks < ((dbg & 1) ? 0 : ksteps); ++ks) {
+            const uint64_t adv = (uint64_t)(ks * 2);   // 8 tf32 = 32 bytes = 2 x 16-byte units
+            mma_tf32(tmem_base + kColCross, a_lo + adv, b_hi + adv, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+            mma_tf32(tmem_base + kColCross, a_hi + adv, b_lo + adv, idesc, 1u);
+            mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (kc > 1 || ks > 0) ? 1u : 0u);
+          }
+          mma_commit(smem_addr(&a_empty[sa]));
+          mma_commit(smem_addr(&b_empty[sb]));
+        }
+        mma_commit(smem_addr(&acc_full));
       }
-      mma_commit(smem_addr(&accum_bar));
     }
     __syncwarp();
-  } else {
-    // ===== A producers (warps 2..5), then epilogue =====
+  } else if (warp < 6) {
+    // ===== A producers (warps 2..5) =====
     const int t = tid - 64;                 // 0..127
     const int cq = t & 7;                   // 16-byte chunk of the 128-byte row
     const int r0 = t >> 3;                  // rows r0 + 16 j
@@ -289,7 +368,8 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
     const uint32_t row_off = (uint32_t)((r0 >> 3) * 1024 + r8 * 128 + ((cq ^ r8) << 4));
     constexpr int kDepth = 3;               // K chunks of A in flight per thread (register ring)
     float4 ring[kDepth][8];
-    auto load_chunk = [&](int kc, float4* dst) {
+    auto load_chunk = [&](int g, float4* dst) {
+      const int kc = g >= kchunks ? g - kchunks : g;
       const int k = kc * kChunkK + cq * 4;
       const bool kvalid = k < k_dim && !(dbg & 2);
 #pragma unroll
@@ -300,123 +380,114 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
     };
 #pragma unroll
     for (int d = 0; d < kDepth; ++d)
-      if (d < kchunks) load_chunk(d, ring[d]);
-    for (int kb = 0; kb < kchunks; kb += kDepth) {
+      if (d < total_chunks) load_chunk(d, ring[d]);
+    for (int gb = 0; gb < total_chunks; gb += kDepth) {
 #pragma unroll
       for (int d = 0; d < kDepth; ++d) {
-        const int kc = kb + d;
-        if (kc < kchunks) {
-          const int s = kc % stages;
-          const uint32_t ph = (uint32_t)(kc / stages) & 1u;
-          bar_wait(smem_addr(&empty_bar[s]), ph ^ 1u);
-          unsigned char* st = smem_gen + (size_t)s * plan.stage_bytes + row_off;
+        const int g = gb + d;
+        if (g < total_chunks) {
+          const int s = g % kAStages;
+          bar_wait(smem_addr(&a_empty[s]), ((uint32_t)(g / kAStages) & 1u) ^ 1u);
+          unsigned char* st = smem_gen + (size_t)s * 2 * kABytes + row_off;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 v = ring[d][j];
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-            *reinterpret_cast<float4*>(st + j * 2048) = h;              // rows +16 = two 8-row atoms
-            *reinterpret_cast<float4*>(st + kABytes + j * 2048) = l;
-          }
-          fence_proxy_async();                      // every writer: generic-proxy stores -> async proxy (tcgen05.mma)
+          for (int j = 0; j < 8; ++j)                    // rows +16 = two 8-row atoms = 2048 B
+            if (!(dbg & 8)) split_store(st + j * 2048, st + kABytes + j * 2048, ring[d][j]);
+          if (!(dbg & 16)) fence_proxy_async();          // generic-proxy stores -> async proxy (tcgen05.mma)
           __syncwarp();
-          if (lane == 0) bar_arrive(smem_addr(&full_bar[s]));   // one arrive per warp: 128 arrives cost ~1 us/chunk
-          if (kc + kDepth < kchunks) load_chunk(kc + kDepth, ring[d]);
+          if (lane == 0) bar_arrive(smem_addr(&a_full[s]));
+          if (g + kDepth < total_chunks) load_chunk(g + kDepth, ring[d]);
         }
       }
     }
-
-    // ----- epilogue: TMEM -> registers -> packed [rows, n_out] tile in smem -> bulk store -----
-    bar_wait(smem_addr(&accum_bar), 0);
-    tc_fence_after();
+  } else {
+    // ===== epilogue (warps 6..9) =====
     const int quad = warp & 3;                                  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;                           // tile row == TMEM lane
-    float* srow = reinterpret_cast<float*>(smem_gen) + (size_t)row * n_out;
     const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
-    for (int c0 = 0; c0 < ((dbg & 8) ? 16 : n_out); c0 += 16) {
-      float v[16];
-      tmem_ld16(tbase + (uint32_t)c0, v);
+    unsigned char* srow = smem_gen + (staging - smem_base) + (size_t)row * kStageRow;
+    const uint32_t srow_addr = staging + (uint32_t)row * kStageRow;
+    const bool row_ok = m0 + row < m_rows;
+    const bool use_main1 = kchunks > 1;
+    for (int h = 0; h < nh; ++h) {
+      bar_wait(smem_addr(&acc_full), (uint32_t)h & 1u);
+      tc_fence_after();
+      const int hpad = plan.hv.pad[h], hvalid = plan.hv.valid[h], hcol = plan.hv.col[h];
+      for (int c0 = 0; c0 < hpad; c0 += kSubCols) {
+        bulk_wait_read();                                       // my previous row segment has left the staging row
+        const int ncols = min(kSubCols, hpad - c0);
+        for (int cc = 0; cc < ((dbg & 32) ? 0 : ncols); cc += 16) {
+          float v[16];
+          load_sum16(tbase, (uint32_t)(c0 + cc), use_main1, v);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int col = c0 + 4 * q;
-        if (col < n_out) {                                       // n_out % 4 == 0
-          float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          if (bias != nullptr) {
-            const float4 b = ldg_f4(bias + col);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          for (int q = 0; q < 4; ++q) {
+            const int lc = c0 + cc + 4 * q;                     // column inside the half
+            if (lc < hvalid) {
+              float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              if (bias != nullptr) {
+                const float4 b = ldg_f4(bias + hcol + lc);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              *reinterpret_cast<float4*>(srow + (cc + 4 * q) * 4) = o;
+            }
           }
-          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          *reinterpret_cast<float4*>(srow + col) = o;
         }
+        if (c0 + kSubCols >= hpad) {                            // accumulators fully read: release them to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) bar_arrive(smem_addr(&acc_empty));
+        }
+        const int nvalid = min(ncols, hvalid - c0);
+        if (row_ok && nvalid > 0 && !(dbg & 64)) {
+          fence_proxy_async();
+          bulk_store(c + (int64_t)(m0 + row) * n_out + hcol + c0, srow_addr, (uint32_t)nvalid * 4u);
+        }
+        bulk_commit();
       }
     }
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-      int rows = m_rows - (m0 + quad * 32);
-      rows = rows > 32 ? 32 : rows;
-      if (rows > 0 && !(dbg & 32)) {
-        bulk_store(c + (int64_t)(m0 + quad * 32) * n_out, smem_base + (uint32_t)(quad * 32 * n_out * 4),
-                   (uint32_t)(rows * n_out * 4));
-        bulk_store_commit_and_wait();
-      }
-    }
+    bulk_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)plan.tmem_cols);
+    tmem_dealloc(tmem_base, 512u);
   }
 }
 
-
 // =====================================================================================================================
-// Weight-gradient GEMM  dW[M, N] = P[R, M]^T . Q[R, N]   (P = dY, Q = X; the reduction runs over the R node rows).
-//
-// Both operands are "MN-major" for the tensor core (the reduction index is the slow one in memory).  For 32-bit
-// MN-major operands the only UMMA layout is SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom): an atom is
-// 4 reduction rows x 32 tf32 (128 B) of M/N = 512 B, the 32-byte unit index of a row is XORed with (row & 3);
-// atoms of consecutive 32-wide M/N blocks are LBO apart, atoms of consecutive 4-row groups SBO apart, and one
-// tcgen05.mma (K = 8) reads two row groups.  128-bit global loads along M/N map onto 16-byte halves of the
-// swizzle units, so no transposition is needed.
-// Grid = (M tiles of 128) x (row slabs): every CTA reduces its slab of rows into a [128 x NPAD] TMEM accumulator and
-// writes an fp32 partial; gemm3x_tn_reduce_kernel adds the slab partials in fixed order (deterministic, and the
-// tensor core's truncating accumulator never sees more than kSlabRows rows).
-constexpr int kTnGroups = 2;                       // 8-row reduction groups per pipeline stage (16 rows)
-constexpr int kTnRows = 8 * kTnGroups;
+// gemm3x_tn:  dW[M, N] = P[R, M]^T . Q[R, N]  (P = dY, Q = x; the reduction runs over the R node rows).
+// Grid = (M tiles of 128 x N halves, row slabs).  Every CTA reduces its slab into the three accumulators and writes an
+// fp32 partial; gemm3x_tn_reduce_kernel adds the slab partials in slab order (deterministic).
+//   warp 0 / lane 0   MMA issuer (owns TMEM)
+//   warps 1..8        producers: P slice [16 rows x 128] and Q slice [16 rows x <=160] per stage, 128-bit loads along
+//                     M/N land on 16-byte halves of the swizzle units (no transposition); per-thread item geometry is
+//                     hoisted out of the loop; register ring 4 stages ahead.  Afterwards the same warps drain TMEM.
+// =====================================================================================================================
+constexpr int kTnRows = 16;                        // reduction rows per pipeline stage (two K = 8 MMAs)
 constexpr int kTnProducers = 256;                  // warps 1..8
 constexpr int kTnThreads = 32 + kTnProducers;
-constexpr int kTnMaxStages = 8;
-constexpr int kSlabRows = 384;                     // upper bound of rows reduced inside one accumulator
+constexpr int kTnABlocks = 4, kTnBBlocks = kHalfMax / 32;                 // 32-wide M/N blocks per operand
+constexpr int kTnAPart = (kTnRows / 4) * kTnABlocks * 512;                 // 8 KB  (hi or lo)
+constexpr int kTnBPart = (kTnRows / 4) * kTnBBlocks * 512;                 // 10 KB
+constexpr int kTnStageBytes = 2 * kTnAPart + 2 * kTnBPart;                 // 36 KB
+constexpr int kTnStages = 6;
+constexpr int kTnSmem = kTnStages * kTnStageBytes + 1024;
+constexpr int kSlabRows = 768;                     // upper bound of rows reduced inside one set of accumulators
+static_assert(kTnSmem <= kSmemLimit - 1024, "gemm3x_tn shared memory budget");
+static_assert(kTileM * (kHalfMax + 4) * 4 <= kTnStages * kTnStageBytes, "epilogue staging reuses the stage ring");
 
 struct TnPlan {
-  int npad, nblocks, n0, n1, stages, a_part, b_part, stage_bytes, smem_bytes, mtiles, nslabs, chunks_per_slab;
+  Halves hv;
+  int mtiles, nslabs, chunks_per_slab;
 };
-
 __host__ __device__ inline TnPlan make_tn_plan(int64_t rows, int m_out, int n_out) {
   TnPlan p;
-  p.npad = (n_out + 15) / 16 * 16;
-  p.nblocks = (p.npad + 31) / 32;
-  if (p.npad <= 256) { p.n0 = p.npad; p.n1 = 0; }
-  else { p.n0 = 160; p.n1 = p.npad - 160; }
-  p.a_part = kTnGroups * 2 * 4 * 512;              // per 4-row group: 128 M values = 4 blocks of 512 B
-  p.b_part = kTnGroups * 2 * p.nblocks * 512;
-  p.stage_bytes = 2 * p.a_part + 2 * p.b_part;
-  int st = (kSmemLimit - 2048) / p.stage_bytes;
-  if (st > kTnMaxStages) st = kTnMaxStages;
-  p.stages = st;
-  int staging = kTileM * n_out * 4;
-  int body = p.stages * p.stage_bytes;
-  if (body < staging) body = staging;
-  p.smem_bytes = body + 1024;
+  p.hv = make_halves(n_out);
   p.mtiles = (m_out + kTileM - 1) / kTileM;
   const int64_t chunks = (rows + kTnRows - 1) / kTnRows;
-  int64_t nslabs = kNumSMs / p.mtiles;             // one wave when the slabs are short enough
+  int64_t nslabs = kNumSMs / (p.mtiles * p.hv.count);                      // one wave when the slabs are short enough
   const int64_t min_slabs = (rows + kSlabRows - 1) / kSlabRows;
   if (nslabs < min_slabs) nslabs = min_slabs;
   if (nslabs > chunks) nslabs = chunks;
@@ -426,19 +497,8 @@ __host__ __device__ inline TnPlan make_tn_plan(int64_t rows, int m_out, int n_ou
   return p;
 }
 
-// MN-major SWIZZLE_128B_BASE32B descriptor (layout type 1): LBO = byte distance between 32-element M/N blocks,
-// SBO = between 4-row groups of the reduction dimension.
-__device__ __forceinline__ uint64_t make_desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(lbo >> 4) << 16;
-  d |= (uint64_t)(sbo >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)1 << 61;
-  return d;
-}
-// byte offset of the 16-byte unit `f4` (4 consecutive M/N values) of reduction row `rr` inside an operand part
-// laid out as [4-row group][32-wide block][512 B atom]
+// byte offset of the 16-byte unit `f4` (4 consecutive M/N values) of reduction row `rr` inside an operand part laid
+// out as [4-row group][32-wide block][512 B atom]
 __device__ __forceinline__ uint32_t mn_offset(int rr, int f4, int nblocks) {
   const int kg = rr >> 2, k4 = rr & 3, c16 = f4 & 7;
   return (uint32_t)((kg * nblocks + (f4 >> 3)) * 512 + k4 * 128 + (((c16 >> 1) ^ k4) << 5) + ((c16 & 1) << 4));
@@ -446,26 +506,26 @@ __device__ __forceinline__ uint32_t mn_offset(int rr, int f4, int nblocks) {
 
 __global__ void __launch_bounds__(kTnThreads, 1)
 gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __restrict__ qmat, int64_t ldq, int rows,
-                 int m_out, int n_out, float* __restrict__ partial, TnPlan plan) {
+                 int m_out, int n_out, float* __restrict__ partial, TnPlan plan, int dbg) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long full_bar[kTnMaxStages];
-  __shared__ __align__(8) unsigned long long empty_bar[kTnMaxStages];
+  __shared__ __align__(8) unsigned long long full_bar[kTnStages], empty_bar[kTnStages];
   __shared__ __align__(8) unsigned long long accum_bar;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_addr(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_addr(smem_raw));
-  const int m0 = blockIdx.x * kTileM;
+  const int nh = plan.hv.count;
+  const int mt = blockIdx.x / nh, h = blockIdx.x - mt * nh;
+  const int m0 = mt * kTileM;
+  const int hpad = plan.hv.pad[h], hvalid = plan.hv.valid[h], hcol = plan.hv.col[h];
   const int slab = blockIdx.y;
-  const int stages = plan.stages;
   const int chunk0 = slab * plan.chunks_per_slab;
-  const int total_chunks = (rows + kTnRows - 1) / kTnRows;
-  int nchunks = total_chunks - chunk0;
+  int nchunks = (rows + kTnRows - 1) / kTnRows - chunk0;
   if (nchunks > plan.chunks_per_slab) nchunks = plan.chunks_per_slab;
 
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) {
+    for (int s = 0; s < kTnStages; ++s) {
       bar_init(smem_addr(&full_bar[s]), kTnProducers / 32);
       bar_init(smem_addr(&empty_bar[s]), 1);
     }
@@ -481,38 +541,24 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
   if (warp == 0) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t mn = (1u << 15) | (1u << 16);             // A and B are MN-major
-      const uint32_t idesc0 = make_idesc_tf32(kTileM, plan.n0) | mn;
-      const uint32_t idesc1 = make_idesc_tf32(kTileM, plan.n1 > 0 ? plan.n1 : 16) | mn;
-      const uint32_t a_sbo = 4 * 512, b_sbo = (uint32_t)plan.nblocks * 512;   // one 4-row group of all blocks
-      const uint32_t n1_off = (uint32_t)(plan.n0 / 32) * 512;
+      const uint32_t idesc = make_idesc_tf32(kTileM, hpad, true);
+      constexpr uint32_t a_sbo = kTnABlocks * 512, b_sbo = kTnBBlocks * 512;   // one 4-row group of all blocks
       for (int c = 0; c < nchunks; ++c) {
-        const int s = c % stages;
-        const uint32_t ph = (uint32_t)(c / stages) & 1u;
-        bar_wait(smem_addr(&full_bar[s]), ph);
+        const int s = c % kTnStages;
+        bar_wait(smem_addr(&full_bar[s]), (uint32_t)(c / kTnStages) & 1u);
         tc_fence_after();
-        const uint32_t st = smem_base + (uint32_t)s * plan.stage_bytes;
-        const uint32_t a_hi = st, a_lo = st + plan.a_part;
-        const uint32_t b_hi = st + 2 * plan.a_part, b_lo = b_hi + plan.b_part;
+        const uint32_t st = smem_base + (uint32_t)s * kTnStageBytes;
+        const uint32_t a_hi = st, a_lo = st + kTnAPart, b_hi = st + 2 * kTnAPart, b_lo = b_hi + kTnBPart;
 #pragma unroll
-        for (int g = 0; g < kTnGroups; ++g) {          // 8 reduction rows = two 4-row groups per MMA
+        for (int g = 0; g < ((dbg & 1) ? 0 : kTnRows / 8); ++g) {        // 8 reduction rows = two 4-row groups per MMA
           const uint32_t ao = g * 2 * a_sbo, bo = g * 2 * b_sbo;
-          const uint64_t dah = make_desc_mn_sw128_32b(a_hi + ao, 512, a_sbo);
-          const uint64_t dal = make_desc_mn_sw128_32b(a_lo + ao, 512, a_sbo);
-          const uint64_t dbh = make_desc_mn_sw128_32b(b_hi + bo, 512, b_sbo);
-          const uint64_t dbl = make_desc_mn_sw128_32b(b_lo + bo, 512, b_sbo);
-          const uint32_t acc = (c > 0 || g > 0) ? 1u : 0u;
-          mma_tf32(tmem_base, dal, dbh, idesc0, acc);
-          mma_tf32(tmem_base, dah, dbl, idesc0, 1);
-          mma_tf32(tmem_base, dah, dbh, idesc0, 1);
-          if (plan.n1 > 0) {
-            const uint32_t d1 = tmem_base + (uint32_t)plan.n0;
-            const uint64_t dbh1 = make_desc_mn_sw128_32b(b_hi + bo + n1_off, 512, b_sbo);
-            const uint64_t dbl1 = make_desc_mn_sw128_32b(b_lo + bo + n1_off, 512, b_sbo);
-            mma_tf32(d1, dal, dbh1, idesc1, acc);
-            mma_tf32(d1, dah, dbl1, idesc1, 1);
-            mma_tf32(d1, dah, dbh1, idesc1, 1);
-          }
+          const uint64_t dah = make_desc(a_hi + ao, 512, a_sbo, kLayoutSw128Base32);
+          const uint64_t dal = make_desc(a_lo + ao, 512, a_sbo, kLayoutSw128Base32);
+          const uint64_t dbh = make_desc(b_hi + bo, 512, b_sbo, kLayoutSw128Base32);
+          const uint64_t dbl = make_desc(b_lo + bo, 512, b_sbo, kLayoutSw128Base32);
+          mma_tf32(tmem_base + kColCross, dal, dbh, idesc, (c > 0 || g > 0) ? 1u : 0u);
+          mma_tf32(tmem_base + kColCross, dah, dbl, idesc, 1u);
+          mma_tf32(tmem_base + (g ? kColMain1 : kColMain0), dah, dbh, idesc, c > 0 ? 1u : 0u);
         }
         mma_commit(smem_addr(&empty_bar[s]));
       }
@@ -520,39 +566,45 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
     }
     __syncwarp();
   } else {
-    // ===== producers (warps 1..8): P slice [16 rows x 128] and Q [16 rows x NPAD] per chunk, then epilogue =====
+    // ===== producers =====
     const int t = tid - 32;                          // 0..255
-    constexpr int kAItems = kTnRows * 32 / kTnProducers;          // float4 items of P per thread and chunk (2)
-    const int q4 = plan.npad / 4;                    // float4 per row of Q (zero padded)
-    const int b_items = kTnRows * q4;                // <= 16 * 76
-    constexpr int kBMax = (kTnRows * (kMaxNPad / 4) + kTnProducers - 1) / kTnProducers;   // 5
-    constexpr int kDepth = 4;                        // chunks of global loads in flight per thread (register ring)
-    float4 ra[kDepth][kAItems], rb[kDepth][kBMax];
+    constexpr int kAItems = kTnRows * 32 / kTnProducers;                                   // 2 float4 of P per thread
+    constexpr int kBItems = (kTnRows * (kHalfMax / 4) + kTnProducers - 1) / kTnProducers;  // <= 3 float4 of Q
+    constexpr int kDepth = 4;
+    const int q4 = hpad / 4;                         // float4 per row of the Q slice (zero padded to hpad)
+    // chunk-invariant geometry of this thread's items
+    uint32_t a_soff[kAItems], b_soff[kBItems];
+    int64_t a_goff[kAItems], b_goff[kBItems];
+    int a_rr[kAItems], b_rr[kBItems];
+    bool a_ok[kAItems], b_ok[kBItems];
+#pragma unroll
+    for (int i = 0; i < kAItems; ++i) {
+      const int item = t + i * kTnProducers, rr = item >> 5, f4 = item & 31;
+      a_rr[i] = rr;
+      a_soff[i] = mn_offset(rr, f4, kTnABlocks);
+      a_goff[i] = (int64_t)rr * ldp + m0 + f4 * 4;
+      a_ok[i] = m0 + f4 * 4 < m_out;
+    }
+#pragma unroll
+    for (int i = 0; i < kBItems; ++i) {
+      const int item = t + i * kTnProducers, rr = item / q4, f4 = item - rr * q4;
+      const bool in = item < kTnRows * q4;
+      b_rr[i] = in ? rr : 0;
+      b_soff[i] = in ? 2 * kTnAPart + mn_offset(rr, f4, kTnBBlocks) : 0xffffffffu;
+      b_goff[i] = (int64_t)rr * ldq + hcol + f4 * 4;
+      b_ok[i] = in && f4 * 4 < hvalid;
+    }
+    float4 ra[kDepth][kAItems], rb[kDepth][kBItems];
     auto load_chunk = [&](int c, float4* da, float4* db) {
       const int r_base = (chunk0 + c) * kTnRows;
+      const float* pb = pmat + (int64_t)r_base * ldp;
+      const float* qb = qmat + (int64_t)r_base * ldq;
 #pragma unroll
-      for (int i = 0; i < kAItems; ++i) {
-        const int item = t + i * kTnProducers;       // row = item / 32, f4 = item % 32
-        const int r = r_base + (item >> 5), col = m0 + (item & 31) * 4;
-        da[i] = (r < rows && col < m_out) ? ldg_f4(pmat + (int64_t)r * ldp + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int i = 0; i < kAItems; ++i)
+        da[i] = (a_ok[i] && r_base + a_rr[i] < rows && !(dbg & 2)) ? ldg_f4(pb + a_goff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < kBMax; ++i) {
-        const int item = t + i * kTnProducers;
-        const int rr = item / q4, f4 = item - rr * q4;
-        const int r = r_base + rr, col = f4 * 4;
-        db[i] = (item < b_items && r < rows && col < n_out) ? ldg_f4(qmat + (int64_t)r * ldq + col)
-                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto split_store = [&](unsigned char* hi_base, uint32_t part, uint32_t off, const float4 v) {
-      float4 h, l;
-      h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-      h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-      h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-      h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-      *reinterpret_cast<float4*>(hi_base + off) = h;
-      *reinterpret_cast<float4*>(hi_base + part + off) = l;
+      for (int i = 0; i < kBItems; ++i)
+        db[i] = (b_ok[i] && r_base + b_rr[i] < rows && !(dbg & 2)) ? ldg_f4(qb + b_goff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
 #pragma unroll
     for (int d = 0; d < kDepth; ++d)
@@ -562,25 +614,16 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
       for (int d = 0; d < kDepth; ++d) {
         const int c = cb + d;
         if (c < nchunks) {
-          const int s = c % stages;
-          const uint32_t ph = (uint32_t)(c / stages) & 1u;
-          bar_wait(smem_addr(&empty_bar[s]), ph ^ 1u);
-          unsigned char* st = smem_gen + (size_t)s * plan.stage_bytes;
+          const int s = c % kTnStages;
+          bar_wait(smem_addr(&empty_bar[s]), ((uint32_t)(c / kTnStages) & 1u) ^ 1u);
+          unsigned char* st = smem_gen + (size_t)s * kTnStageBytes;
 #pragma unroll
-          for (int i = 0; i < kAItems; ++i) {
-            const int item = t + i * kTnProducers;
-            const int rr = item >> 5, f4 = item & 31;    // row in chunk, 16-byte unit along M
-            split_store(st, (uint32_t)plan.a_part, mn_offset(rr, f4, 4), ra[d][i]);
-          }
+          for (int i = 0; i < kAItems; ++i)
+            if (!(dbg & 8)) split_store(st + a_soff[i], st + kTnAPart + a_soff[i], ra[d][i]);
 #pragma unroll
-          for (int i = 0; i < kBMax; ++i) {
-            const int item = t + i * kTnProducers;
-            if (item < b_items) {
-              const int rr = item / q4, f4 = item - rr * q4;
-              split_store(st + 2 * plan.a_part, (uint32_t)plan.b_part, mn_offset(rr, f4, plan.nblocks), rb[d][i]);
-            }
-          }
-          fence_proxy_async();
+          for (int i = 0; i < kBItems; ++i)
+            if (b_soff[i] != 0xffffffffu && !(dbg & 8)) split_store(st + b_soff[i], st + kTnBPart + b_soff[i], rb[d][i]);
+          if (!(dbg & 16)) fence_proxy_async();
           __syncwarp();
           if (lane == 0) bar_arrive(smem_addr(&full_bar[s]));
           if (c + kDepth < nchunks) load_chunk(c + kDepth, ra[d], rb[d]);
@@ -588,20 +631,21 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
       }
     }
 
-    // ----- epilogue: two warps per TMEM lane quadrant, each takes half of the 16-column groups -----
+    // ----- epilogue: two warps per TMEM lane quadrant, each takes every other 16-column group -----
     bar_wait(smem_addr(&accum_bar), 0);
     tc_fence_after();
     const int quad = warp & 3;
     const int half = (warp - 1) >> 2;                // warps 1..4 -> 0, warps 5..8 -> 1
     const int row = quad * 32 + lane;
-    float* srow = reinterpret_cast<float*>(smem_gen) + (size_t)row * n_out;
+    const int sstride = hvalid + ((hvalid & 4) ? 0 : 4);       // floats; odd multiple of 4 words: conflict-free float4
+    float* srow = reinterpret_cast<float*>(smem_gen) + (size_t)row * sstride;
     const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int groups = (n_out + 15) / 16;
+    const int groups = (hvalid + 15) / 16;
     for (int gi = half; gi < groups; gi += 2) {
       const int c0 = gi * 16;
       float v[16];
       if (nchunks > 0) {
-        tmem_ld16(tbase + (uint32_t)c0, v);
+        load_sum16(tbase, (uint32_t)c0, true, v);
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -609,20 +653,18 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int col = c0 + 4 * q;
-        if (col < n_out)
+        if (col < hvalid)
           *reinterpret_cast<float4*>(srow + col) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
     }
     fence_proxy_async();
-    asm volatile("bar.sync 1, %0;" ::"n"(kTnProducers) : "memory");      // both column halves of every row are staged
-    if (half == 0 && lane == 0) {
-      int nrow = m_out - (m0 + quad * 32);
-      nrow = nrow > 32 ? 32 : nrow;
-      if (nrow > 0) {
-        float* dst = partial + ((int64_t)slab * m_out + (m0 + quad * 32)) * n_out;
-        bulk_store(dst, smem_base + (uint32_t)(quad * 32 * n_out * 4), (uint32_t)(nrow * n_out * 4));
-        bulk_store_commit_and_wait();
-      }
+    asm volatile("bar.sync 1, %0;" ::"n"(kTnProducers) : "memory");      // both column sets of every row are staged
+    // one bulk store per output row segment (hvalid contiguous floats of partial[slab][m0 + row, hcol ...])
+    if (half == 0 && m0 + row < m_out) {
+      float* dst = partial + ((int64_t)slab * m_out + (m0 + row)) * n_out + hcol;
+      bulk_store(dst, smem_base + (uint32_t)(row * sstride * 4), (uint32_t)(hvalid * 4));
+      bulk_commit();
+      bulk_wait_all();
     }
   }
 
@@ -658,15 +700,14 @@ extern "C" {
 int ghscn_gemm3x_supported(int64_t m, int64_t n_out, int64_t k) {
   if (m <= 0 || n_out < 16 || k < 8) return 0;
   if ((n_out % 4) != 0 || (k % 4) != 0) return 0;
-  if ((n_out + 15) / 16 * 16 > kMaxNPad) return 0;
+  if (n_out > kMaxN) return 0;
   if (m > (int64_t)INT32_MAX - kTileM || k > (1 << 20)) return 0;
   return 1;
 }
 
 size_t ghscn_gemm3x_b_image_bytes(int64_t n_out, int64_t k) {
   if (!ghscn_gemm3x_supported(kTileM, n_out, k)) return 0;
-  const Plan p = make_plan((int)n_out, (int)k);
-  return (size_t)p.kchunks * (size_t)p.b_bytes;
+  return (size_t)nn_image_bytes(make_nn_plan((int)n_out, (int)k));
 }
 
 int ghscn_gemm3x_prep_b(const float* w, int64_t ldw, int64_t n_out, int64_t k, int32_t transpose, void* image,
@@ -674,11 +715,11 @@ int ghscn_gemm3x_prep_b(const float* w, int64_t ldw, int64_t n_out, int64_t k, i
   GHSCN_REQUIRE(w != nullptr && image != nullptr);
   if (!ghscn_gemm3x_supported(kTileM, n_out, k)) return GHSCN_E_UNSUPPORTED;
   GHSCN_REQUIRE(ldw >= (transpose ? n_out : k));
-  const Plan p = make_plan((int)n_out, (int)k);
-  const int64_t total = (int64_t)p.kchunks * p.npad * kChunkK;
+  const NnPlan p = make_nn_plan((int)n_out, (int)k);
+  const int64_t total = (int64_t)p.kchunks * (p.hv.pad[0] + p.hv.pad[1]) * kChunkK;
   const int64_t blocks = ceil_div<int64_t>(total, 256);
   gemm3x_prep_b_kernel<<<(unsigned)(blocks < 4 * kNumSMs ? blocks : 4 * kNumSMs), 256, 0, as_stream(stream)>>>(
-      w, ldw, (int)n_out, (int)k, transpose, p.npad, p.kchunks, static_cast<unsigned char*>(image));
+      w, ldw, (int)n_out, (int)k, transpose, p, static_cast<unsigned char*>(image));
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }
@@ -691,18 +732,18 @@ int ghscn_gemm3x(const float* a, int64_t lda, int64_t m, int64_t k, const void* 
   if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(c) & 15) ||
       (reinterpret_cast<uintptr_t>(b_image) & 15) || (bias && (reinterpret_cast<uintptr_t>(bias) & 15)))
     return GHSCN_E_UNSUPPORTED;
-  const Plan p = make_plan((int)n_out, (int)k);
+  const NnPlan p = make_nn_plan((int)n_out, (int)k);
   static bool attr_set = false;
-  static int dbg = 0;   // GHSCN_GEMM3X_DEBUG: timing experiments only (1 no MMA, 2 no A loads, 4 no B loads, 8 short epilogue)
+  static int dbg = 0;   // GHSCN_GEMM3X_DEBUG: timing experiments only (results are wrong when set)
   if (!attr_set) {
     const char* ev = getenv("GHSCN_GEMM3X_DEBUG");
     dbg = ev ? atoi(ev) : 0;
-    cudaError_t e = cudaFuncSetAttribute(gemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit - 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNnSmem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const unsigned grid = (unsigned)ceil_div<int64_t>(m, kTileM);
-  gemm3x_kernel<<<grid, kThreads, p.smem_bytes, as_stream(stream)>>>(
+  gemm3x_kernel<<<grid, kNnThreads, kNnSmem, as_stream(stream)>>>(
       a, lda, (int)m, (int)k, static_cast<const unsigned char*>(b_image), (int)n_out, bias, relu, c, p, dbg);
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
@@ -711,7 +752,7 @@ int ghscn_gemm3x(const float* a, int64_t lda, int64_t m, int64_t k, const void* 
 int ghscn_gemm3x_tn_supported(int64_t rows, int64_t m_out, int64_t n_out) {
   if (rows <= 0 || rows > (int64_t)INT32_MAX - 64 || m_out < 4 || n_out < 16) return 0;
   if ((m_out % 4) != 0 || (n_out % 4) != 0) return 0;
-  if ((n_out + 15) / 16 * 16 > kMaxNPad || m_out > 4096) return 0;
+  if (n_out > kMaxN || m_out > 4096) return 0;
   return 1;
 }
 
@@ -732,14 +773,17 @@ int ghscn_gemm3x_tn(const float* p_mat, int64_t ldp, const float* q_mat, int64_t
   const TnPlan p = make_tn_plan(rows, (int)m_out, (int)n_out);
   if (workspace_bytes < (size_t)p.nslabs * (size_t)m_out * (size_t)n_out * sizeof(float)) return GHSCN_E_WORKSPACE;
   static bool attr_set = false;
+  static int dbg = 0;   // GHSCN_GEMM3X_DEBUG: timing experiments only
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm3x_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit - 1024);
+    const char* ev = getenv("GHSCN_GEMM3X_DEBUG");
+    dbg = ev ? atoi(ev) : 0;
+    cudaError_t e = cudaFuncSetAttribute(gemm3x_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTnSmem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   float* partial = p.nslabs == 1 ? out : static_cast<float*>(workspace);
-  gemm3x_tn_kernel<<<dim3((unsigned)p.mtiles, (unsigned)p.nslabs), kTnThreads, p.smem_bytes, as_stream(stream)>>>(
-      p_mat, ldp, q_mat, ldq, (int)rows, (int)m_out, (int)n_out, partial, p);
+  gemm3x_tn_kernel<<<dim3((unsigned)(p.mtiles * p.hv.count), (unsigned)p.nslabs), kTnThreads, kTnSmem,
+                     as_stream(stream)>>>(p_mat, ldp, q_mat, ldq, (int)rows, (int)m_out, (int)n_out, partial, p, dbg);
   GHSCN_LAUNCH_CHECK();
   if (p.nslabs > 1) {
     const int64_t elems4 = m_out * n_out / 4;

@@ -151,10 +151,10 @@ GHSCN_API int ghscn_split_tf32_cat(const float* x, int64_t ldx, int64_t num_rows
  * GCNConv / GATConv / Linear (PyG `Linear` inside the convs called at model/mpnn.py:52,59 and model/hscn.py:109;
  * SURVEY 8a rows a2, a9) and their input gradients.  A is read once as fp32 and split into TF32 hi/lo parts
  * in-kernel; the weights are split and laid out once per step by ghscn_gemm3x_prep_b:
- *   image = for each 32-wide K chunk: [npad x 32] hi parts, [npad x 32] lo parts, K-major, 128B-swizzled,
- *           zero padded (npad = n_out rounded up to 16), ghscn_gemm3x_b_image_bytes() bytes, 16-byte aligned;
+ *   image = for each N half (<= 160 columns), for each 32-wide K chunk: [pad x 32] hi parts, [pad x 32] lo parts,
+ *           K-major, 128B-swizzled, zero padded, ghscn_gemm3x_b_image_bytes() bytes, 16-byte aligned;
  *   b[n, k] = transpose ? w[k*ldw + n] : w[n*ldw + k]   (transpose = 1 gives dX = dY . W from W[out,in]).
- * Supported (ghscn_gemm3x_supported() != 0): n_out % 4 == 0, 16 <= n_out <= 304, k % 4 == 0, k >= 8;
+ * Supported (ghscn_gemm3x_supported() != 0): n_out % 4 == 0, 16 <= n_out <= 320, k % 4 == 0, k >= 8;
  * ghscn_gemm3x additionally needs ldc == n_out, lda % 4 == 0 and 16-byte aligned a, c, bias. */
 GHSCN_API int ghscn_gemm3x_supported(int64_t m, int64_t n_out, int64_t k);
 GHSCN_API size_t ghscn_gemm3x_b_image_bytes(int64_t n_out, int64_t k);
@@ -164,9 +164,9 @@ GHSCN_API int ghscn_gemm3x(const float* a, int64_t lda, int64_t m, int64_t k, co
                            const float* bias, int32_t relu, float* c, int64_t ldc, ghscn_stream_t stream);
 
 /* Weight gradient of the same projections: out[m_out, n_out] = P[rows, m_out]^T . Q[rows, n_out] (P = dY, Q = x),
- * 3xTF32 on tcgen05 with both operands MN-major, split in-kernel.  The rows are cut into slabs of <= 384; each
- * (128-row tile of out, slab) CTA writes an fp32 partial into `workspace`, then the partials are added in slab
- * order (deterministic).  Supported: m_out % 4 == 0, n_out % 4 == 0, 16 <= n_out <= 304, ld % 4 == 0, 16-byte
+ * 3xTF32 on tcgen05 with both operands MN-major, split in-kernel.  The rows are cut into slabs of <= 768; each
+ * (128 x <=160 tile of out, slab) CTA writes an fp32 partial into `workspace`, then the partials are added in slab
+ * order (deterministic).  Supported: m_out % 4 == 0, n_out % 4 == 0, 16 <= n_out <= 320, ld % 4 == 0, 16-byte
  * aligned pointers. */
 GHSCN_API int ghscn_gemm3x_tn_supported(int64_t rows, int64_t m_out, int64_t n_out);
 GHSCN_API size_t ghscn_gemm3x_tn_workspace_bytes(int64_t rows, int64_t m_out, int64_t n_out);
