@@ -26,7 +26,6 @@
 //                               32-wide blocks, SBO between 4-row groups; one MMA (K = 8) reads two groups.
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -91,18 +90,24 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::tf32, issued by ONE thread for the CTA.
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::tf32.  Called by ALL 32 lanes of the (convergent) MMA warp with
+// warp-uniform operands; elect.sync picks the issuing lane.  Written this way the compiler keeps the descriptors in
+// uniform registers and emits back-to-back UTCHMMA; issuing from inside `if (lane == 0)` wraps every MMA in an
+// ELECT / BRA.U.ANY lane loop (~90 cycles per MMA, more than an N = 160 MMA takes to execute).
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "{\n\t.reg .pred pe, pa;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, pa;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// All previously issued MMAs of this thread arrive on `bar` once they have completed (implies fence::before).
+// All previously issued MMAs arrive on `bar` once they have completed (implies fence::before).  Convergent warp.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns (no wait): thread l of the warp receives TMEM lane (quadrant*32 + l).
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
@@ -208,13 +213,13 @@ __host__ __device__ inline Halves make_halves(int n_out) {
 // gemm3x:  C = A . B^T.  One CTA per 128-row tile of A; for each N half: K loop over 32-wide chunks.
 //   warp 0 / lane 0   weight-image producer: one cp.async.bulk per chunk into a 3-stage B ring (L2 resident image,
 //                     pre-split and pre-swizzled by gemm3x_prep_b_kernel)
-//   warp 1 / lane 0   MMA issuer (owns TMEM): per K = 8 step  cross += a_lo.b_hi, cross += a_hi.b_lo,
+//   warp 1            MMA issuer, convergent (owns TMEM): per K = 8 step  cross += a_lo.b_hi, cross += a_hi.b_lo,
 //                     main[chunk & 1] += a_hi.b_hi; commits the stage barriers, then the accumulator barrier
 //   warps 2..5        A producers: 128-bit global loads (register ring, 3 chunks ahead) -> hi/lo split ->
 //                     swizzled smem (2-stage A ring) -> fence.proxy.async -> one mbarrier arrive per warp
 //   warps 6..9        epilogue (own TMEM lane quadrant = warp & 3): tcgen05.ld of the three accumulators -> fp32 sum
-//                     -> bias / ReLU -> per-thread row segment in a padded staging tile -> one bulk store per row
-//                     segment; the stores of half h overlap the main loop of half h + 1
+//                     -> bias / ReLU -> per-warp padded staging tile -> coalesced 128-bit global stores; the stores of
+//                     half h overlap the main loop of half h + 1
 // =====================================================================================================================
 constexpr int kChunkK = 32;
 constexpr int kABytes = kTileM * kChunkK * 4;               // one part (hi or lo) of an A stage: 16 KB
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(256) gemm3x_prep_b_kernel(const float* __restr
 
 __global__ void __launch_bounds__(kNnThreads, 1)
 gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, const unsigned char* __restrict__ b_image,
-              int n_out, const float* __restrict__ bias, int relu, float* __restrict__ c, NnPlan plan, int dbg) {
+              int n_out, const float* __restrict__ bias, int relu, float* __restrict__ c, NnPlan plan) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long a_full[kAStages], a_empty[kAStages];
   __shared__ __align__(8) unsigned long long b_full[kBStages], b_empty[kBStages];
@@ -318,15 +323,14 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
         bar_wait(smem_addr(&b_empty[s]), ph ^ 1u);
         const uint32_t bytes = (uint32_t)(2 * plan.hv.pad[h] * kChunkK * 4);
         const uint32_t fb = smem_addr(&b_full[s]);
-        if (dbg & 4) { bar_arrive(fb); continue; }
         bar_arrive_expect_tx(fb, bytes);
         bulk_load(b_ring + (uint32_t)s * kBStageBytes, b_image + plan.img_off[h] + (int64_t)kc * bytes, bytes, fb);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (all 32 lanes run the loop; elect.sync inside mma_tf32 / mma_commit) =====
+    {
       for (int h = 0; h < nh; ++h) {
         const uint32_t idesc = make_idesc_tf32(kTileM, plan.hv.pad[h], false);
         const uint32_t lo_off = (uint32_t)plan.hv.pad[h] * kChunkK * 4;
@@ -346,7 +350,7 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
           const int kleft = k_dim - kc * kChunkK;
           const int ksteps = kleft >= kChunkK ? kChunkK / 8 : (kleft + 7) / 8;
           const uint32_t d_main = tmem_base + ((kc & 1) ? kColMain1 : kColMain0);
-          for (int ks = 0; ks < ((dbg & 1) ? 0 : ksteps); ++ks) {
+          for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t adv = (uint64_t)(ks * 2);   // 8 tf32 = 32 bytes = 2 x 16-byte units
             mma_tf32(tmem_base + kColCross, a_lo + adv, b_hi + adv, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
             mma_tf32(tmem_base + kColCross, a_hi + adv, b_lo + adv, idesc, 1u);
@@ -371,7 +375,7 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
     auto load_chunk = [&](int g, float4* dst) {
       const int kc = g >= kchunks ? g - kchunks : g;
       const int k = kc * kChunkK + cq * 4;
-      const bool kvalid = k < k_dim && !(dbg & 2);
+      const bool kvalid = k < k_dim;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int r = m0 + r0 + 16 * j;
@@ -391,8 +395,8 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
           unsigned char* st = smem_gen + (size_t)s * 2 * kABytes + row_off;
 #pragma unroll
           for (int j = 0; j < 8; ++j)                    // rows +16 = two 8-row atoms = 2048 B
-            if (!(dbg & 8)) split_store(st + j * 2048, st + kABytes + j * 2048, ring[d][j]);
-          if (!(dbg & 16)) fence_proxy_async();          // generic-proxy stores -> async proxy (tcgen05.mma)
+            split_store(st + j * 2048, st + kABytes + j * 2048, ring[d][j]);
+          fence_proxy_async();                           // generic-proxy stores -> async proxy (tcgen05.mma)
           __syncwarp();
           if (lane == 0) bar_arrive(smem_addr(&a_full[s]));
           if (g + kDepth < total_chunks) load_chunk(g + kDepth, ring[d]);
@@ -404,18 +408,17 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
     const int quad = warp & 3;                                  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;                           // tile row == TMEM lane
     const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
-    unsigned char* srow = smem_gen + (staging - smem_base) + (size_t)row * kStageRow;
-    const uint32_t srow_addr = staging + (uint32_t)row * kStageRow;
-    const bool row_ok = m0 + row < m_rows;
+    unsigned char* swarp = smem_gen + (staging - smem_base) + (size_t)quad * 32 * kStageRow;   // this warp's 32 rows
+    unsigned char* srow = swarp + (size_t)lane * kStageRow;
     const bool use_main1 = kchunks > 1;
+    const int hl = lane & 15, rsel = lane >> 4;                 // store phase: half-warp per row, 16 float4 lanes
     for (int h = 0; h < nh; ++h) {
       bar_wait(smem_addr(&acc_full), (uint32_t)h & 1u);
       tc_fence_after();
       const int hpad = plan.hv.pad[h], hvalid = plan.hv.valid[h], hcol = plan.hv.col[h];
       for (int c0 = 0; c0 < hpad; c0 += kSubCols) {
-        bulk_wait_read();                                       // my previous row segment has left the staging row
         const int ncols = min(kSubCols, hpad - c0);
-        for (int cc = 0; cc < ((dbg & 32) ? 0 : ncols); cc += 16) {
+        for (int cc = 0; cc < ncols; cc += 16) {
           float v[16];
           load_sum16(tbase, (uint32_t)(c0 + cc), use_main1, v);
 #pragma unroll
@@ -437,15 +440,22 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
           __syncwarp();
           if (lane == 0) bar_arrive(smem_addr(&acc_empty));
         }
-        const int nvalid = min(ncols, hvalid - c0);
-        if (row_ok && nvalid > 0 && !(dbg & 64)) {
-          fence_proxy_async();
-          bulk_store(c + (int64_t)(m0 + row) * n_out + hcol + c0, srow_addr, (uint32_t)nvalid * 4u);
+        __syncwarp();                                           // staging rows of this warp are complete
+        // coalesced 128-bit stores, two rows (up to 256 contiguous bytes each) per instruction.  Per-row bulk
+        // stores were measured at ~27 cycles per request per SM and dropped.
+        const int nf4 = min(ncols, hvalid - c0) / 4;            // float4 per row segment (<= 16)
+        if (hl < nf4) {
+#pragma unroll 4
+          for (int r = rsel; r < 32; r += 2) {
+            const int grow = m0 + quad * 32 + r;
+            if (grow < m_rows)
+              *reinterpret_cast<float4*>(c + (int64_t)grow * n_out + hcol + c0 + hl * 4) =
+                  *reinterpret_cast<const float4*>(swarp + (size_t)r * kStageRow + hl * 16);
+          }
         }
-        bulk_commit();
+        __syncwarp();                                           // reads done before the next sub-tile overwrites
       }
     }
-    bulk_wait_all();
   }
 
   tc_fence_before();
@@ -460,7 +470,7 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
 // gemm3x_tn:  dW[M, N] = P[R, M]^T . Q[R, N]  (P = dY, Q = x; the reduction runs over the R node rows).
 // Grid = (M tiles of 128 x N halves, row slabs).  Every CTA reduces its slab into the three accumulators and writes an
 // fp32 partial; gemm3x_tn_reduce_kernel adds the slab partials in slab order (deterministic).
-//   warp 0 / lane 0   MMA issuer (owns TMEM)
+//   warp 0            MMA issuer, convergent (owns TMEM)
 //   warps 1..8        producers: P slice [16 rows x 128] and Q slice [16 rows x <=160] per stage, 128-bit loads along
 //                     M/N land on 16-byte halves of the swizzle units (no transposition); per-thread item geometry is
 //                     hoisted out of the loop; register ring 4 stages ahead.  Afterwards the same warps drain TMEM.
@@ -506,7 +516,7 @@ __device__ __forceinline__ uint32_t mn_offset(int rr, int f4, int nblocks) {
 
 __global__ void __launch_bounds__(kTnThreads, 1)
 gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __restrict__ qmat, int64_t ldq, int rows,
-                 int m_out, int n_out, float* __restrict__ partial, TnPlan plan, int dbg) {
+                 int m_out, int n_out, float* __restrict__ partial, TnPlan plan) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[kTnStages], empty_bar[kTnStages];
   __shared__ __align__(8) unsigned long long accum_bar;
@@ -539,8 +549,8 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (all 32 lanes run the loop; elect.sync inside mma_tf32 / mma_commit) =====
+    {
       const uint32_t idesc = make_idesc_tf32(kTileM, hpad, true);
       constexpr uint32_t a_sbo = kTnABlocks * 512, b_sbo = kTnBBlocks * 512;   // one 4-row group of all blocks
       for (int c = 0; c < nchunks; ++c) {
@@ -550,7 +560,7 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
         const uint32_t st = smem_base + (uint32_t)s * kTnStageBytes;
         const uint32_t a_hi = st, a_lo = st + kTnAPart, b_hi = st + 2 * kTnAPart, b_lo = b_hi + kTnBPart;
 #pragma unroll
-        for (int g = 0; g < ((dbg & 1) ? 0 : kTnRows / 8); ++g) {        // 8 reduction rows = two 4-row groups per MMA
+        for (int g = 0; g < kTnRows / 8; ++g) {        // 8 reduction rows = two 4-row groups per MMA
           const uint32_t ao = g * 2 * a_sbo, bo = g * 2 * b_sbo;
           const uint64_t dah = make_desc(a_hi + ao, 512, a_sbo, kLayoutSw128Base32);
           const uint64_t dal = make_desc(a_lo + ao, 512, a_sbo, kLayoutSw128Base32);
@@ -601,10 +611,10 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
       const float* qb = qmat + (int64_t)r_base * ldq;
 #pragma unroll
       for (int i = 0; i < kAItems; ++i)
-        da[i] = (a_ok[i] && r_base + a_rr[i] < rows && !(dbg & 2)) ? ldg_f4(pb + a_goff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        da[i] = (a_ok[i] && r_base + a_rr[i] < rows) ? ldg_f4(pb + a_goff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < kBItems; ++i)
-        db[i] = (b_ok[i] && r_base + b_rr[i] < rows && !(dbg & 2)) ? ldg_f4(qb + b_goff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        db[i] = (b_ok[i] && r_base + b_rr[i] < rows) ? ldg_f4(qb + b_goff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
 #pragma unroll
     for (int d = 0; d < kDepth; ++d)
@@ -618,12 +628,11 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
           bar_wait(smem_addr(&empty_bar[s]), ((uint32_t)(c / kTnStages) & 1u) ^ 1u);
           unsigned char* st = smem_gen + (size_t)s * kTnStageBytes;
 #pragma unroll
-          for (int i = 0; i < kAItems; ++i)
-            if (!(dbg & 8)) split_store(st + a_soff[i], st + kTnAPart + a_soff[i], ra[d][i]);
+          for (int i = 0; i < kAItems; ++i) split_store(st + a_soff[i], st + kTnAPart + a_soff[i], ra[d][i]);
 #pragma unroll
           for (int i = 0; i < kBItems; ++i)
-            if (b_soff[i] != 0xffffffffu && !(dbg & 8)) split_store(st + b_soff[i], st + kTnBPart + b_soff[i], rb[d][i]);
-          if (!(dbg & 16)) fence_proxy_async();
+            if (b_soff[i] != 0xffffffffu) split_store(st + b_soff[i], st + kTnBPart + b_soff[i], rb[d][i]);
+          fence_proxy_async();
           __syncwarp();
           if (lane == 0) bar_arrive(smem_addr(&full_bar[s]));
           if (c + kDepth < nchunks) load_chunk(c + kDepth, ra[d], rb[d]);
@@ -657,14 +666,17 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
           *reinterpret_cast<float4*>(srow + col) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
     }
-    fence_proxy_async();
     asm volatile("bar.sync 1, %0;" ::"n"(kTnProducers) : "memory");      // both column sets of every row are staged
-    // one bulk store per output row segment (hvalid contiguous floats of partial[slab][m0 + row, hcol ...])
-    if (half == 0 && m0 + row < m_out) {
-      float* dst = partial + ((int64_t)slab * m_out + (m0 + row)) * n_out + hcol;
-      bulk_store(dst, smem_base + (uint32_t)(row * sstride * 4), (uint32_t)(hvalid * 4));
-      bulk_commit();
-      bulk_wait_all();
+    // coalesced stores: each warp writes 16 rows of its quadrant, hvalid contiguous floats per row
+    const int nf4 = hvalid / 4;
+    for (int r = 0; r < 16; ++r) {
+      const int trow = quad * 32 + half * 16 + r;
+      if (m0 + trow < m_out) {
+        float* dst = partial + ((int64_t)slab * m_out + (m0 + trow)) * n_out + hcol;
+        const float* src = reinterpret_cast<const float*>(smem_gen) + (size_t)trow * sstride;
+        for (int f = lane; f < nf4; f += 32)
+          *reinterpret_cast<float4*>(dst + f * 4) = *reinterpret_cast<const float4*>(src + f * 4);
+      }
     }
   }
 
@@ -734,17 +746,14 @@ int ghscn_gemm3x(const float* a, int64_t lda, int64_t m, int64_t k, const void* 
     return GHSCN_E_UNSUPPORTED;
   const NnPlan p = make_nn_plan((int)n_out, (int)k);
   static bool attr_set = false;
-  static int dbg = 0;   // GHSCN_GEMM3X_DEBUG: timing experiments only (results are wrong when set)
   if (!attr_set) {
-    const char* ev = getenv("GHSCN_GEMM3X_DEBUG");
-    dbg = ev ? atoi(ev) : 0;
     cudaError_t e = cudaFuncSetAttribute(gemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNnSmem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const unsigned grid = (unsigned)ceil_div<int64_t>(m, kTileM);
   gemm3x_kernel<<<grid, kNnThreads, kNnSmem, as_stream(stream)>>>(
-      a, lda, (int)m, (int)k, static_cast<const unsigned char*>(b_image), (int)n_out, bias, relu, c, p, dbg);
+      a, lda, (int)m, (int)k, static_cast<const unsigned char*>(b_image), (int)n_out, bias, relu, c, p);
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }
@@ -773,17 +782,14 @@ int ghscn_gemm3x_tn(const float* p_mat, int64_t ldp, const float* q_mat, int64_t
   const TnPlan p = make_tn_plan(rows, (int)m_out, (int)n_out);
   if (workspace_bytes < (size_t)p.nslabs * (size_t)m_out * (size_t)n_out * sizeof(float)) return GHSCN_E_WORKSPACE;
   static bool attr_set = false;
-  static int dbg = 0;   // GHSCN_GEMM3X_DEBUG: timing experiments only
   if (!attr_set) {
-    const char* ev = getenv("GHSCN_GEMM3X_DEBUG");
-    dbg = ev ? atoi(ev) : 0;
     cudaError_t e = cudaFuncSetAttribute(gemm3x_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTnSmem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   float* partial = p.nslabs == 1 ? out : static_cast<float*>(workspace);
   gemm3x_tn_kernel<<<dim3((unsigned)(p.mtiles * p.hv.count), (unsigned)p.nslabs), kTnThreads, kTnSmem,
-                     as_stream(stream)>>>(p_mat, ldp, q_mat, ldq, (int)rows, (int)m_out, (int)n_out, partial, p, dbg);
+                     as_stream(stream)>>>(p_mat, ldp, q_mat, ldq, (int)rows, (int)m_out, (int)n_out, partial, p);
   GHSCN_LAUNCH_CHECK();
   if (p.nslabs > 1) {
     const int64_t elems4 = m_out * n_out / 4;
