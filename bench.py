@@ -324,7 +324,7 @@ def run_product(args, rank: int, local_rank: int, world: int) -> None:
             "config": {"workload": WORKLOAD, "graphs_per_gpu": GRAPHS_PER_GPU, "nodes_per_gpu": int(batch.x.size(0)),
                        "edges_per_gpu": int(batch.edge_index.size(1)), "parallelism": f"dp{world} by graph",
                        "execution": "one CUDA graph per step (padded virtual-node layout)",
-                       "l2": "flushed between timed steps (256 MiB write)", "gemm": "3xTF32 tensor-core projections (split kernel + one library TF32 GEMM), fp32 accuracy; skinny layers hand-written"},
+                       "l2": "flushed between timed steps (256 MiB write)", "gemm": "h x h projections: hand-written tcgen05/TMEM 3xTF32 kernels (fused hi/lo split, 3 accumulators), fp32-level accuracy; skinny layers hand-written; small virtual-node GEMMs cuBLAS fp32"},
             "e2e": {"value": total_graphs / (e2e_ms * 1e-3), "unit": "graphs/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": step.h2d_bytes, "d2h_bytes_per_step": 12},
             "gpu_launches": int(launches_per_step * args.steps),

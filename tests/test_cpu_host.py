@@ -233,3 +233,26 @@ def test_shard_range_covers_all_graphs():
     w = [1] * 50 + [9] * 50
     r = [shard_range(100, k, 2, w) for k in range(2)]
     assert r[0][1] > 50 and r[0][1] == r[1][0] and r[1][1] == 100
+
+
+def test_gemm3x_shape_rules_without_a_gpu(built_lib):
+    """ghscn_gemm3x_supported / *_bytes are host-only: shape rules of the tcgen05 GEMMs (include/ghscn.h)."""
+    from graph_hscn_b200._lib import lib
+    L = lib()
+    assert L.query("ghscn_gemm3x_supported", 18269, 300, 300) == 1
+    assert L.query("ghscn_gemm3x_supported", 18269, 320, 300) == 1
+    assert L.query("ghscn_gemm3x_supported", 18269, 324, 300) == 0      # more than two 160-column halves
+    assert L.query("ghscn_gemm3x_supported", 18269, 302, 300) == 0      # n_out % 4
+    assert L.query("ghscn_gemm3x_supported", 18269, 300, 9) == 0        # k % 4 (raw atom features: skinny kernels)
+    assert L.query("ghscn_gemm3x_supported", 0, 300, 300) == 0
+    # weight image: per N half, per 32-wide K chunk, hi + lo blocks of pad x 128 bytes; 300 -> halves 160 + 144
+    assert L.query("ghscn_gemm3x_b_image_bytes", 300, 300) == 10 * 2 * (160 + 144) * 128
+    assert L.query("ghscn_gemm3x_b_image_bytes", 64, 64) == 2 * 2 * 64 * 128
+    assert L.query("ghscn_gemm3x_b_image_bytes", 400, 300) == 0
+    assert L.query("ghscn_gemm3x_tn_supported", 18269, 300, 300) == 1
+    assert L.query("ghscn_gemm3x_tn_supported", 18269, 300, 324) == 0
+    ws = L.query("ghscn_gemm3x_tn_workspace_bytes", 18269, 300, 300)
+    assert ws % (300 * 300 * 4) == 0 and 1 <= ws // (300 * 300 * 4) <= 64   # one fp32 partial per row slab
+    # null pointers are rejected before anything is launched
+    assert L._fns["ghscn_gemm3x"](None, 300, 128, 300, None, 300, None, 0, None, 300, None) == -1
+    assert L._fns["ghscn_gemm3x_tn"](None, 300, None, 300, 128, 300, 300, None, None, 0, None) == -1
