@@ -27,7 +27,7 @@ def main():
         cnt[n] += 1
         tot += us(r)
     mine = sum(v for n, v in agg.items() if "ghscn" in n)
-    gemm = sum(v for n, v in agg.items() if re.search(r"gemm|cutlass|splitK|gemv", n, re.I))
+    gemm = sum(v for n, v in agg.items() if "ghscn" not in n and re.search(r"gemm|cutlass|splitK|gemv", n, re.I))
     out = [f"source: {path}", f"kernels in one step: {len(seg)}   sum of kernel time: {tot:.1f} us (cold-cache, serialised)",
            f"hand-written ghscn kernels: {mine:.1f} us ({100 * mine / tot:.1f}%)   cuBLAS GEMM: {gemm:.1f} us "
            f"({100 * gemm / tot:.1f}%)   other torch: {tot - mine - gemm:.1f} us ({100 * (tot - mine - gemm) / tot:.1f}%)", ""]

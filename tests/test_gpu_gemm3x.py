@@ -54,7 +54,7 @@ def test_gemm3x_tn_matches_fp64(cuda, rows, m, n):
 
 def test_gemm3x_same_sign_data_has_no_truncation_bias(cuda):
     """Post-ReLU features are all >= 0: a single TMEM accumulator truncates coherently (3e-6 .. 1e-4 after the weight
-    gradient); the three-accumulator scheme must stay at fp32 level."""
+    gradient); the three-accumulator scheme must stay at fp32 level (cuBLAS fp32 itself is at ~1e-6 here)."""
     from graph_hscn_b200 import gemm
     g = torch.Generator(device="cuda").manual_seed(11)
     x = torch.rand(9000, 300, device=cuda, generator=g) * 5            # all positive
@@ -62,8 +62,8 @@ def test_gemm3x_same_sign_data_has_no_truncation_bias(cuda):
     dy = torch.rand(9000, 300, device=cuda, generator=g)
     y = gemm.gemm3x(x, gemm.gemm3x_prep(w), 300)
     dw = gemm.gemm3x_tn(dy, x)
-    assert _rel(y, x.double() @ w.double().t()) < 1e-6
-    assert _rel(dw, dy.double().t() @ x.double()) < 1e-6
+    ey, edw = _rel(y, x.double() @ w.double().t()), _rel(dw, dy.double().t() @ x.double())
+    assert ey < 2e-6 and edw < 2e-6, f"same-sign inputs: y {ey:.2e}, dW {edw:.2e}"
 
 
 def test_gemm3x_layout_probes_are_bit_exact(cuda):
