@@ -484,7 +484,7 @@ constexpr int kTnBPart = (kTnRows / 4) * kTnBBlocks * 512;                 // 10
 constexpr int kTnStageBytes = 2 * kTnAPart + 2 * kTnBPart;                 // 36 KB
 constexpr int kTnStages = 6;
 constexpr int kTnSmem = kTnStages * kTnStageBytes + 1024;
-constexpr int kSlabRows = 768;                     // upper bound of rows reduced inside one set of accumulators
+constexpr int kSlabRows = 1024;                    // upper bound of rows reduced inside one set of accumulators
 static_assert(kTnSmem <= kSmemLimit - 1024, "gemm3x_tn shared memory budget");
 static_assert(kTileM * (kHalfMax + 4) * 4 <= kTnStages * kTnStageBytes, "epilogue staging reuses the stage ring");
 

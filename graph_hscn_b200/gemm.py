@@ -89,15 +89,47 @@ def gemm3x_prep(weight: Tensor, transpose: bool = False) -> Tensor:
     return image
 
 
-def gemm3x(a: Tensor, image: Tensor, n_out: int, bias: Optional[Tensor] = None, relu: bool = False) -> Tensor:
+def gemm3x(a: Tensor, image: Tensor, n_out: int, bias: Optional[Tensor] = None, relu: bool = False,
+           out: Optional[Tensor] = None) -> Tensor:
     """C = A . B^T (+ bias) (ReLU) on the tcgen05 tensor cores with fp32-level accuracy (3xTF32, split in-kernel)."""
     if a.stride(1) != 1 or a.stride(0) % 4 != 0:
         a = a.contiguous()
     m, k = a.shape
-    c = torch.empty((m, n_out), dtype=torch.float32, device=a.device)
+    c = torch.empty((m, n_out), dtype=torch.float32, device=a.device) if out is None else out
     lib().call("ghscn_gemm3x", _p(a), a.stride(0), m, k, _p(image), n_out, _p(bias), int(relu), _p(c), n_out,
                _stream())
     return c
+
+
+TILE_ROWS, NUM_SMS, MAX_TAIL_TILES = 128, 148, 24
+
+
+def wave_rows(n: int) -> int:
+    """Rows the tcgen05 kernel should take so that its 128-row tiles fill whole waves of the 148 SMs.  One CTA per
+    SM and ~30 us per CTA regardless of its work: a last wave of a few tiles (the typical Peptides batch has
+    19.3 k nodes = 151 tiles) would double the kernel time, so up to MAX_TAIL_TILES trailing tiles go to a
+    plain fp32 GEMM instead (~9 us for ~1 k rows)."""
+    tiles = (n + TILE_ROWS - 1) // TILE_ROWS
+    waves, tail = divmod(tiles, NUM_SMS)
+    if 1 <= waves <= 2 and 0 < tail <= MAX_TAIL_TILES:
+        return waves * NUM_SMS * TILE_ROWS
+    return n
+
+
+def linear_rows(a: Tensor, weight_nk: Tensor, image: Tensor, n_out: int, bias: Optional[Tensor], transposed: bool):
+    """a . B^T with B[n, k] = weight (or weight^T when `transposed`): whole waves on tcgen05, tail rows on cuBLAS fp32."""
+    m = a.size(0)
+    r = wave_rows(m)
+    if r == m:
+        return gemm3x(a, image, n_out, bias)
+    y = torch.empty((m, n_out), dtype=torch.float32, device=a.device)
+    gemm3x(a[:r], image, n_out, bias, out=y[:r])
+    b_kn = weight_nk if transposed else weight_nk.t()          # [k, n_out]
+    if bias is not None:
+        torch.addmm(bias, a[r:], b_kn, out=y[r:])
+    else:
+        torch.mm(a[r:], b_kn, out=y[r:])
+    return y
 
 
 def gemm3x_tn_supported(rows: int, m_out: int, n_out: int) -> bool:
@@ -130,7 +162,7 @@ class _Linear3xTF32(torch.autograd.Function):
         m = weight.size(0)
         fused = USE_TCGEN05 and gemm3x_supported(n, m, k)
         if fused:
-            y = gemm3x(x, gemm3x_prep(weight), m, bias)
+            y = linear_rows(x, weight, gemm3x_prep(weight), m, bias, transposed=False)
             ctx.save_for_backward(x, weight)
         else:
             a_cat = split_cat(x, 0, DW_CHUNK)                    # [Npad, 3K] = [xl | xh | xh]
@@ -154,7 +186,7 @@ class _Linear3xTF32(torch.autograd.Function):
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dx_fused = need_dx and USE_TCGEN05 and gemm3x_supported(n, k, m)
         if dx_fused:
-            dx = gemm3x(dy, gemm3x_prep(weight, transpose=True), k)      # dX = dY . W
+            dx = linear_rows(dy, weight, gemm3x_prep(weight, transpose=True), k, None, transposed=True)   # dX = dY . W
         dw_fused = need_dw and ctx.fused and USE_TCGEN05 and gemm3x_tn_supported(n, m, k)
         if dw_fused:
             dw = gemm3x_tn(dy, saved)                            # dW = dY^T x, slab partials added in fp32

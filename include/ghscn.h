@@ -164,7 +164,7 @@ GHSCN_API int ghscn_gemm3x(const float* a, int64_t lda, int64_t m, int64_t k, co
                            const float* bias, int32_t relu, float* c, int64_t ldc, ghscn_stream_t stream);
 
 /* Weight gradient of the same projections: out[m_out, n_out] = P[rows, m_out]^T . Q[rows, n_out] (P = dY, Q = x),
- * 3xTF32 on tcgen05 with both operands MN-major, split in-kernel.  The rows are cut into slabs of <= 768; each
+ * 3xTF32 on tcgen05 with both operands MN-major, split in-kernel.  The rows are cut into slabs of <= 1024; each
  * (128 x <=160 tile of out, slab) CTA writes an fp32 partial into `workspace`, then the partials are added in slab
  * order (deterministic).  Supported: m_out % 4 == 0, n_out % 4 == 0, 16 <= n_out <= 320, ld % 4 == 0, 16-byte
  * aligned pointers. */

@@ -101,6 +101,15 @@ def test_linear_uses_the_tcgen05_kernels_and_falls_back_for_unsupported_shapes(c
     y.sum().backward()
     # prep + gemm3x (fwd), prep + gemm3x (dX), gemm3x_tn (dW): five C-ABI calls, no split_cat
     assert lib().launches - before == 5
+    # 151 tiles = one wave of 148 + 3: the trailing rows go to a plain fp32 GEMM, results stay at fp32 level
+    assert gemm.wave_rows(19300) == 148 * 128 and gemm.wave_rows(18269) == 18269 and gemm.wave_rows(150000) == 150000
+    xb = torch.randn(19300, 300, device=cuda, requires_grad=True)
+    yb = gemm.linear(xb, w, None)
+    gy = torch.randn_like(yb)
+    dxb, dwb = torch.autograd.grad(yb, (xb, w), gy)
+    assert _rel(yb, xb.detach().double() @ w.detach().double().t()) < 2e-6
+    assert _rel(dxb, gy.double() @ w.detach().double()) < 2e-6
+    assert _rel(dwb, gy.double().t() @ xb.detach().double()) < 2e-6
     wide = torch.randn(512, 300, device=cuda)                        # n_out = 512 > 320: library 3xTF32 path
     assert not gemm.gemm3x_supported(5000, 512, 300)
     ref = x.detach().double() @ wide.double().t()
