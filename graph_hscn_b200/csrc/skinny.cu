@@ -4,14 +4,15 @@
 // model/hscn.py:50-54).  They are pure HBM streaming problems (read or write one [N, M] matrix once, ~50 MFLOP),
 // which a tiled SIMT GEMM handles poorly (7-36 us each in profiles/r1d); here each is one pass at memory speed.
 //   fwd : y[n,m]  = sum_k x[n,k] W[m,k] + b[m]          W^T staged in shared memory, warp per row, lanes over m
-//   dW  : dW[m,k] = sum_n dY[n,m] x[n,k]                two-stage fixed-order reduction over 256-row chunks
+//   dW  : dW[m,k] = sum_n dY[n,m] x[n,k]                two-stage fixed-order reduction over 512-row chunks
 //   dX  : dx[n,k] = sum_m dY[n,m] W[m,k]                warp per row, lanes over k
 #include "common.cuh"
 
 namespace ghscn {
 
 constexpr int kSkinnyMaxK = 32;
-constexpr int kDwRows = 256;
+constexpr int kDwRowFloats = 8192;                            // smem floats for the staged x rows of one chunk
+__host__ __device__ constexpr int dw_rows(int kmax) { return kDwRowFloats / kmax; }   // 512 rows (K <= 16) / 256
 
 __global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict__ x, int64_t ldx,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
@@ -41,6 +42,73 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict
   }
 }
 
+// Register-resident variant for K <= 12 (the 9 raw atom features): lane l owns the outputs m = l + 32 j and keeps
+// their J x K weights in registers, so a row costs K shuffles + J*K FMAs and no shared-memory traffic (the smem
+// version issues one LDS per FMA and sits on the LSU limit at ~2.5 TB/s of output).
+template <int J>
+__global__ void __launch_bounds__(256) skinny_fwd_reg_kernel(const float* __restrict__ x, int64_t ldx,
+                                                             const float* __restrict__ w,
+                                                             const float* __restrict__ bias, int num_rows, int K,
+                                                             int M, float* __restrict__ y, int64_t ldy) {
+  constexpr int KR = 12;
+  extern __shared__ float wt[];  // [K][M]: staged once per CTA with coalesced loads, then read conflict-free
+  for (int i = threadIdx.x; i < K * M; i += blockDim.x) {
+    const int m = i / K, k = i - m * K;
+    wt[k * M + m] = w[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  float wr[J][KR], br[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int m = lane + 32 * j;
+    br[j] = (m < M && bias) ? __ldg(bias + m) : 0.f;
+#pragma unroll
+    for (int k = 0; k < KR; ++k) wr[j][k] = (m < M && k < K) ? wt[k * M + m] : 0.f;
+  }
+  const int warps = (gridDim.x * blockDim.x) >> 5;     // row stride between a warp's consecutive rows
+  // x rows are fetched in groups of 4, one group ahead of the FMAs: with a single row per warp in flight the
+  // kernel is latency-bound (1.6 TB/s of output)
+  constexpr int G = 4;
+  int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  float xa[G], xb[G];
+  auto load_group = [&](int base, float* xx) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int r = base + g * warps;
+      xx[g] = (r < num_rows && lane < K) ? __ldg(x + (int64_t)r * ldx + lane) : 0.f;
+    }
+  };
+  auto compute_group = [&](int base, const float* xx) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int r = base + g * warps;
+      if (r < num_rows) {
+        float acc[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[j] = br[j];
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+          const float xk = __shfl_sync(kFullMask, xx[g], k);    // lanes >= K hold 0: padded k contribute nothing
+#pragma unroll
+          for (int j = 0; j < J; ++j) acc[j] = fmaf(xk, wr[j][k], acc[j]);
+        }
+        float* yr = y + (int64_t)r * ldy + lane;
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+          if (lane + 32 * j < M) yr[32 * j] = acc[j];
+      }
+    }
+  };
+  load_group(n, xa);
+  for (; n < num_rows; n += 2 * G * warps) {
+    load_group(n + G * warps, xb);
+    compute_group(n, xa);
+    load_group(n + 2 * G * warps, xa);
+    compute_group(n + G * warps, xb);
+  }
+}
+
 // partial[chunk][m][k] = sum over the chunk's rows of dY[n,m] x[n,k].  CTA = (32-column tile of m, chunk of
 // kDwRows rows): lanes own m, the 8 warps stride the rows (8 dY loads in flight per lane), K register
 // accumulators per thread, fixed-order combine of the 8 warps in shared memory.
@@ -49,16 +117,17 @@ __global__ void __launch_bounds__(256) skinny_dw_partial_kernel(const float* __r
                                                                 const float* __restrict__ x, int64_t ldx,
                                                                 int num_rows, int K, int M,
                                                                 float* __restrict__ partial) {
+  constexpr int kDwRows = dw_rows(KMAX);
   constexpr int kBuf = (kDwRows * KMAX > 8 * 32 * (KMAX + 1)) ? kDwRows * KMAX : 8 * 32 * (KMAX + 1);
-  __shared__ float buf[kBuf];                                  // x rows first, then reused for the combine
+  __shared__ __align__(16) float buf[kBuf];                    // x rows first, then reused for the combine
   float* xs = buf;
   float (*red)[32][KMAX + 1] = reinterpret_cast<float (*)[32][KMAX + 1]>(buf);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int r0 = blockIdx.y * kDwRows;
   const int rows = min(kDwRows, num_rows - r0);
-  for (int i = threadIdx.x; i < rows * K; i += blockDim.x) {
-    const int r = i / K, k = i - r * K;
-    xs[r * KMAX + k] = __ldg(x + (int64_t)(r0 + r) * ldx + k);
+  for (int i = threadIdx.x; i < rows * KMAX; i += blockDim.x) {   // columns K..KMAX-1 are zero padding
+    const int r = i / KMAX, k = i - r * KMAX;
+    xs[r * KMAX + k] = k < K ? __ldg(x + (int64_t)(r0 + r) * ldx + k) : 0.f;
   }
   __syncthreads();
   const int m = blockIdx.x * 32 + lane;
@@ -74,16 +143,35 @@ __global__ void __launch_bounds__(256) skinny_dw_partial_kernel(const float* __r
 #pragma unroll
       for (int u = 0; u < 8; ++u) d[u] = __ldg(dp + (int64_t)(r + 8 * u) * lddy);
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < 8; ++u) {
+        // the x row is a warp-wide broadcast: 128-bit shared loads (ceil(K/4) instead of K per row) keep the
+        // kernel off the LSU limit (9 scalar LDS per 128 B of dY capped it at ~1.2 TB/s)
+        const float4* xr = reinterpret_cast<const float4*>(xs + (r + 8 * u) * KMAX);
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k)
-          if (k < K) acc[k] = fmaf(d[u], xs[(r + 8 * u) * KMAX + k], acc[k]);
+        for (int q = 0; q < KMAX / 4; ++q) {
+          if (4 * q < K) {
+            const float4 xv = xr[q];
+            acc[4 * q + 0] = fmaf(d[u], xv.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(d[u], xv.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(d[u], xv.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(d[u], xv.w, acc[4 * q + 3]);
+          }
+        }
+      }
     }
     for (; r < rows; r += 8) {
       const float d0 = __ldg(dp + (int64_t)r * lddy);
+      const float4* xr = reinterpret_cast<const float4*>(xs + r * KMAX);
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < K) acc[k] = fmaf(d0, xs[r * KMAX + k], acc[k]);
+      for (int q = 0; q < KMAX / 4; ++q) {
+        if (4 * q < K) {
+          const float4 xv = xr[q];
+          acc[4 * q + 0] = fmaf(d0, xv.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(d0, xv.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(d0, xv.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(d0, xv.w, acc[4 * q + 3]);
+        }
+      }
     }
   }
   __syncthreads();  // every warp is done with xs before the buffer is reused
@@ -99,6 +187,77 @@ __global__ void __launch_bounds__(256) skinny_dw_partial_kernel(const float* __r
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += red[w][l][k];
       partial[((int64_t)blockIdx.y * M + mm) * K + k] = t;
+    }
+  }
+}
+
+// Register-resident dW for K <= 16 (M <= 128) / K <= 12 (M <= 320): one CTA per chunk of rows and per 160 columns
+// (lane l owns m = m0 + l + 32 j, J x K accumulators in registers), so x is staged nowhere and read once, dY rows are read as full
+// contiguous rows (J coalesced 128-byte loads per warp and row, the next row prefetched), and the only shared-memory
+// traffic is the fixed-order combine of the 8 warps at the end.  partial[chunk][m][k].
+template <int J, int KR>
+__global__ void __launch_bounds__(256) skinny_dw_rows_kernel(const float* __restrict__ dy, int64_t lddy,
+                                                             const float* __restrict__ x, int64_t ldx,
+                                                             int num_rows, int K, int M, int rows_per_cta,
+                                                             float* __restrict__ partial) {
+  __shared__ float red[8][32][KR + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int rows = min(rows_per_cta, num_rows - r0);
+  const int m0 = blockIdx.y * (32 * J);                       // this CTA's column range: m0 + lane + 32 j
+  float acc[J][KR];
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+#pragma unroll
+    for (int k = 0; k < KR; ++k) acc[j][k] = 0.f;
+  constexpr int D = 2;                                        // rows in flight ahead of the FMAs
+  float dq[D][J], xq[D];
+  auto load_row = [&](int r, float* dd, float& xx) {
+    if (r < rows) {
+      const float* dp = dy + (int64_t)(r0 + r) * lddy + m0 + lane;
+#pragma unroll
+      for (int j = 0; j < J; ++j) dd[j] = (m0 + lane + 32 * j < M) ? __ldg(dp + 32 * j) : 0.f;
+      xx = lane < K ? __ldg(x + (int64_t)(r0 + r) * ldx + lane) : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < J; ++j) dd[j] = 0.f;
+      xx = 0.f;
+    }
+  };
+#pragma unroll
+  for (int q = 0; q < D; ++q) load_row(wid + 8 * q, dq[q], xq[q]);
+  for (int rb = wid; rb < rows; rb += 8 * D) {
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+      float d[J];
+      const float xv = xq[q];
+#pragma unroll
+      for (int j = 0; j < J; ++j) d[j] = dq[q][j];
+      load_row(rb + 8 * (q + D), dq[q], xq[q]);
+#pragma unroll
+      for (int k = 0; k < KR; ++k) {
+        const float xk = __shfl_sync(kFullMask, xv, k);     // lanes >= K hold 0; rows past the end are zeros
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[j][k] = fmaf(d[j], xk, acc[j][k]);
+      }
+    }
+  }
+  // fixed-order combine of the 8 warps, one 32-column group at a time
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < KR; ++k) red[wid][lane][k] = acc[j][k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) {
+      const int l = i / K, k = i - l * K;
+      const int m = m0 + l + 32 * j;
+      if (m < M) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][l][k];
+        partial[((int64_t)blockIdx.x * M + m) * K + k] = t;
+      }
     }
   }
 }
@@ -162,12 +321,31 @@ int ghscn_skinny_linear_fwd(const float* x, int64_t ldx, const float* w, const f
   if (in_feat > kSkinnyMaxK || in_feat * out_feat * 4 > 96 * 1024) return GHSCN_E_UNSUPPORTED;
   if (num_rows == 0) return GHSCN_OK;
   GHSCN_REQUIRE(x && w && y && ldx >= in_feat && ldy >= out_feat);
+  const int64_t want = ceil_div<int64_t>(num_rows, 8 * 4);  // ~4 rows per warp
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  const unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+  if (in_feat <= 12 && out_feat <= 320) {
+    const int j = (int)ceil_div<int64_t>(out_feat, 32);
+    // the weights live in registers: keep the grid at the resident CTA count so that they are loaded once per SM
+    const int64_t resident = (int64_t)kNumSMs * (j <= 2 ? 4 : (j <= 4 ? 2 : 1));
+    const int64_t want_r = ceil_div<int64_t>(num_rows, 8 * 8);
+    const unsigned grid_r = (unsigned)(want_r < resident ? (want_r > 0 ? want_r : 1) : resident);
+    const size_t shm_r = (size_t)in_feat * out_feat * 4;
+#define GHSCN_SKINNY_REG(J)                                                                              \
+  skinny_fwd_reg_kernel<J><<<grid_r, 256, shm_r, as_stream(stream)>>>(x, ldx, w, bias, (int)num_rows,    \
+                                                                      (int)in_feat, (int)out_feat, y, ldy)
+    if (j <= 1) GHSCN_SKINNY_REG(1);
+    else if (j <= 2) GHSCN_SKINNY_REG(2);
+    else if (j <= 4) GHSCN_SKINNY_REG(4);
+    else GHSCN_SKINNY_REG(10);
+#undef GHSCN_SKINNY_REG
+    GHSCN_LAUNCH_CHECK();
+    return GHSCN_OK;
+  }
   const size_t shm = (size_t)in_feat * out_feat * 4;
   if (shm > 48 * 1024)
     cudaFuncSetAttribute(skinny_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  const int64_t want = ceil_div<int64_t>(num_rows, 8 * 4);  // ~4 rows per warp
-  const int64_t cap = (int64_t)kNumSMs * 8;
-  skinny_fwd_kernel<<<(unsigned)(want < cap ? (want > 0 ? want : 1) : cap), 256, shm, as_stream(stream)>>>(
+  skinny_fwd_kernel<<<grid, 256, shm, as_stream(stream)>>>(
       x, ldx, w, bias, (int)num_rows, (int)in_feat, (int)out_feat, y, ldy);
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
@@ -175,7 +353,9 @@ int ghscn_skinny_linear_fwd(const float* x, int64_t ldx, const float* w, const f
 
 size_t ghscn_skinny_dw_workspace_bytes(int64_t num_rows, int64_t in_feat, int64_t out_feat) {
   if (num_rows < 0 || in_feat < 0 || out_feat < 0) return 0;
-  return (size_t)ceil_div<int64_t>(num_rows > 0 ? num_rows : 1, kDwRows) * in_feat * out_feat * 4 + 256;
+  int64_t chunks = ceil_div<int64_t>(num_rows > 0 ? num_rows : 1, dw_rows(in_feat <= 16 ? 16 : 32));
+  if (chunks < kNumSMs) chunks = kNumSMs;                    // the register-resident variant uses up to one chunk per SM
+  return (size_t)chunks * in_feat * out_feat * 4 + 256;
 }
 
 int ghscn_skinny_linear_dw(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t num_rows,
@@ -187,16 +367,33 @@ int ghscn_skinny_linear_dw(const float* dy, int64_t lddy, const float* x, int64_
   if (workspace == nullptr || workspace_bytes < ghscn_skinny_dw_workspace_bytes(num_rows, in_feat, out_feat))
     return GHSCN_E_WORKSPACE;
   cudaStream_t stream = as_stream(stream_);
-  const int chunks = (int)ceil_div<int64_t>(num_rows, kDwRows);
-  if (chunks > 65535) return GHSCN_E_UNSUPPORTED;
   float* partial = static_cast<float*>(workspace);
   const int K = (int)in_feat, M = (int)out_feat;
-  if (chunks > 0) {
-    dim3 grid((unsigned)ceil_div(M, 32), (unsigned)chunks);
-    if (K <= 16)
-      skinny_dw_partial_kernel<16><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, (int)num_rows, K, M, partial);
-    else
-      skinny_dw_partial_kernel<32><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, (int)num_rows, K, M, partial);
+  int chunks;
+  if (K <= 16 && num_rows > 0 && (M <= 128 || (K <= 12 && M <= 320))) {
+    int rows_per_cta = (int)ceil_div<int64_t>(num_rows, kNumSMs);
+    rows_per_cta = (rows_per_cta + 15) / 16 * 16;
+    if (rows_per_cta < 64) rows_per_cta = 64;
+    chunks = (int)ceil_div<int64_t>(num_rows, rows_per_cta);
+    const int j = ceil_div(M, 32);
+#define GHSCN_SKINNY_DW(J, KR, NY)                                                                       \
+  skinny_dw_rows_kernel<J, KR><<<dim3((unsigned)chunks, NY), 256, 0, stream>>>(dy, lddy, x, ldx, (int)num_rows, K, M, \
+                                                                             rows_per_cta, partial)
+    if (j <= 1) GHSCN_SKINNY_DW(1, 16, 1);
+    else if (j <= 2) GHSCN_SKINNY_DW(2, 16, 1);
+    else if (j <= 4) GHSCN_SKINNY_DW(4, 16, 1);
+    else GHSCN_SKINNY_DW(5, 12, (unsigned)ceil_div(j, 5));     // 160 columns per CTA: ~100 registers, 2 CTAs per SM
+#undef GHSCN_SKINNY_DW
+  } else {
+    chunks = (int)ceil_div<int64_t>(num_rows, dw_rows(in_feat <= 16 ? 16 : 32));
+    if (chunks > 65535) return GHSCN_E_UNSUPPORTED;
+    if (chunks > 0) {
+      dim3 grid((unsigned)ceil_div(M, 32), (unsigned)chunks);
+      if (K <= 16)
+        skinny_dw_partial_kernel<16><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, (int)num_rows, K, M, partial);
+      else
+        skinny_dw_partial_kernel<32><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, (int)num_rows, K, M, partial);
+    }
   }
   const int64_t width = (int64_t)M * K;
   chunk_sum_kernel<<<(unsigned)ceil_div<int64_t>(width, 32), 256, 0, stream>>>(partial, chunks, width, dw);
