@@ -11,6 +11,9 @@ Dense GEMMs (x @ W^T) stay on cuBLAS fp32 through F.linear (TF32 off: parity is 
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import math
 from collections import defaultdict
 from typing import Callable, Dict, List, Optional, Tuple, Union
@@ -237,6 +240,18 @@ class GATConv(MessagePassing):
         return out
 
 
+PARALLEL_BRANCHES = os.environ.get("GHSCN_PARALLEL_BRANCHES", "1") != "0"
+_SIDE_STREAMS: Dict[Tuple[str, int], List["torch.cuda.Stream"]] = {}
+
+
+def _side_streams(device: torch.device, n: int):
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    pool = _SIDE_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
 class HeteroConv(nn.Module):
     """Runs one conv per relation in `edge_index_dict` order and sums per destination type (A.9)."""
 
@@ -248,35 +263,60 @@ class HeteroConv(nn.Module):
     def forward(self, x_dict: Dict[str, Tensor], edge_index_dict: Dict[Tuple[str, str, str], Tensor]
                 ) -> Dict[str, Tensor]:
         outs: Dict[str, List[Tensor]] = defaultdict(list)
+        dsts: List[str] = []
+        for edge_type in edge_index_dict:
+            if "__".join(edge_type) in self.convs and edge_type[2] not in dsts:
+                dsts.append(edge_type[2])
+        # The relations of different destination types are independent (l->l feeds "local"; v->v and l->v feed
+        # "virtual"): each destination type gets its own CUDA stream, forked from and joined back to the caller's
+        # stream, so the small virtual-node kernels overlap the large local ones (also inside a captured CUDA
+        # graph, where the fork/join become graph dependencies).  The relations are still visited in
+        # `edge_index_dict` order (lazy parameters initialise in PyG's order) and run the same kernels: results
+        # are bit-identical to the serial schedule (scripts/parallel_branch_check.py).
+        streams = None
+        if PARALLEL_BRANCHES and len(dsts) > 1 and all(t.is_cuda for t in x_dict.values()):
+            main = torch.cuda.current_stream()
+            sides = _side_streams(main.device, len(dsts) - 1)
+            streams = {dsts[0]: main}
+            for i, dst in enumerate(dsts[1:]):
+                sides[i].wait_stream(main)
+                streams[dst] = sides[i]
         for edge_type, edge_index in edge_index_dict.items():
             src, _, dst = edge_type
             key = "__".join(edge_type)
             if key not in self.convs:
                 continue
             conv = self.convs[key]
-            if src == dst:
-                out = conv(x_dict[src], edge_index)
-            else:
-                out = conv((x_dict[src], x_dict[dst]), edge_index)
+            with torch.cuda.stream(streams[dst]) if streams is not None else contextlib.nullcontext():
+                if src == dst:
+                    out = conv(x_dict[src], edge_index)
+                else:
+                    out = conv((x_dict[src], x_dict[dst]), edge_index)
             outs[dst].append(out)
         result: Dict[str, Tensor] = {}
         for key, xs in outs.items():
-            if self.aggr in ("sum", "add"):
-                acc = xs[0]
-                for t in xs[1:]:      # == torch.stack(xs).sum(0) for <= 2 terms; left-to-right beyond
-                    acc = acc + t
-                result[key] = acc
-            elif self.aggr == "mean":
-                result[key] = torch.stack(xs, 0).mean(0)
-            elif self.aggr == "max":
-                result[key] = torch.stack(xs, 0).max(0)[0]
-            elif self.aggr == "min":
-                result[key] = torch.stack(xs, 0).min(0)[0]
-            elif self.aggr == "cat":
-                result[key] = torch.cat(xs, -1)
-            else:
-                result[key] = torch.stack(xs, 1)
+            with torch.cuda.stream(streams[key]) if streams is not None else contextlib.nullcontext():
+                result[key] = self._aggregate(xs)
+        if streams is not None:
+            for dst in dsts[1:]:
+                main.wait_stream(streams[dst])
         return result
+
+    def _aggregate(self, xs: List[Tensor]) -> Tensor:
+        if self.aggr in ("sum", "add"):
+            acc = xs[0]
+            for t in xs[1:]:      # == torch.stack(xs).sum(0) for <= 2 terms; left-to-right beyond
+                acc = acc + t
+            return acc
+        if self.aggr == "mean":
+            return torch.stack(xs, 0).mean(0)
+        if self.aggr == "max":
+            return torch.stack(xs, 0).max(0)[0]
+        if self.aggr == "min":
+            return torch.stack(xs, 0).min(0)[0]
+        if self.aggr == "cat":
+            return torch.cat(xs, -1)
+        return torch.stack(xs, 1)
 
 
 class Sequential(nn.Module):
