@@ -34,8 +34,8 @@ def assign_clusters(s_soft: Tensor) -> Tensor:
 
 
 def build_hetero_batch(x_raw: Tensor, edge_index: Tensor, batch: Tensor, clusters: Tensor, num_clusters: int,
-                       y: Optional[Tensor] = None, padded: bool = False, num_graphs: Optional[int] = None
-                       ) -> HeteroBatch:
+                       y: Optional[Tensor] = None, padded: bool = False, num_graphs: Optional[int] = None,
+                       x_float: Optional[Tensor] = None) -> HeteroBatch:
     """x_raw: int64 (OGB atoms) or float32 [N,F]; clusters: int32 [N] from `assign_clusters`."""
     _require_cuda(x_raw, edge_index, batch, clusters)
     seg = structure_cache().segments(batch, num_graphs)
@@ -70,7 +70,10 @@ def build_hetero_batch(x_raw: Tensor, edge_index: Tensor, batch: Tensor, cluster
                st)
         virt_ptr = voff.long()
     local = out["local"]
-    local.x = ops.cast_i64_f32(x_raw) if x_raw.dtype == torch.int64 else x_raw
+    if x_float is not None:          # already cast by the caller (on ITS stream: see train.GraphHSCNStep)
+        local.x = x_float
+    else:
+        local.x = ops.cast_i64_f32(x_raw) if x_raw.dtype == torch.int64 else x_raw
     if y is not None:
         local.y = y
     local.batch, local.ptr = batch, ptr.long()

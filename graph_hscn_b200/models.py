@@ -141,11 +141,35 @@ class HSCN(nn.Module):
                 self._fused_local = True
 
     def forward(self, x_dict: Dict[str, Tensor], edge_index_dict, batch) -> Tensor:
+        # Operator sets whose HeteroConv runs the destination types on parallel CUDA streams (`last_streams`) keep
+        # every type's tensors on its own stream across the layers: the "virtual" branch never feeds "local"
+        # (model/hscn.py:84-94 has no virtual->local relation), so the caller's stream only waits for it once, at the
+        # end -- or not at all when `defer_branch_join` is set and the training step joins after its optimizer step.
+        streams = None
+        main = None
         for conv in self.convs:
-            x_dict = {k: (v if (self._fused_local and k == "local") else v.relu())
-                      for k, v in conv(x_dict, edge_index_dict).items()}
+            if hasattr(conv, "defer_join"):
+                conv.defer_join = True
+            out = conv(x_dict, edge_index_dict)
+            streams = getattr(conv, "last_streams", None)
+            if streams is not None and main is None:
+                main = torch.cuda.current_stream()
+            x_dict = {}
+            for k, v in out.items():
+                if self._fused_local and k == "local":
+                    x_dict[k] = v
+                elif streams is not None:
+                    with torch.cuda.stream(streams[k]):
+                        x_dict[k] = v.relu()
+                else:
+                    x_dict[k] = v.relu()
         pooled = self.ops.global_mean_pool(x_dict["local"], batch["local"].batch)
-        return self.lin_2(self.activation(self.lin_1(pooled)))
+        pred = self.lin_2(self.activation(self.lin_1(pooled)))
+        if streams is not None and not getattr(self, "defer_branch_join", False):
+            for st in streams.values():
+                if st is not main:
+                    main.wait_stream(st)
+        return pred
 
 
 def criterion(loss_fn: str, pred: Tensor, true: Tensor):

@@ -244,6 +244,11 @@ PARALLEL_BRANCHES = os.environ.get("GHSCN_PARALLEL_BRANCHES", "1") != "0"
 _SIDE_STREAMS: Dict[Tuple[str, int], List["torch.cuda.Stream"]] = {}
 
 
+def branch_stream(device: torch.device, index: int = 0) -> "torch.cuda.Stream":
+    """The side stream HeteroConv uses for its (index + 2)-th destination type on `device`."""
+    return _side_streams(device, index + 1)[index]
+
+
 def _side_streams(device: torch.device, n: int):
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     pool = _SIDE_STREAMS.setdefault(key, [])
@@ -259,6 +264,10 @@ class HeteroConv(nn.Module):
         super().__init__()
         self.convs = nn.ModuleDict({"__".join(k): v for k, v in convs.items()})
         self.aggr = aggr
+        # set by a caller that keeps each destination type's tensors on its branch stream and joins later
+        # (models.HSCN / train.GraphHSCNStep); `last_streams` tells it which stream owns which output
+        self.defer_join = False
+        self.last_streams: Optional[Dict[str, "torch.cuda.Stream"]] = None
 
     def forward(self, x_dict: Dict[str, Tensor], edge_index_dict: Dict[Tuple[str, str, str], Tensor]
                 ) -> Dict[str, Tensor]:
@@ -297,7 +306,8 @@ class HeteroConv(nn.Module):
         for key, xs in outs.items():
             with torch.cuda.stream(streams[key]) if streams is not None else contextlib.nullcontext():
                 result[key] = self._aggregate(xs)
-        if streams is not None:
+        self.last_streams = streams
+        if streams is not None and not self.defer_join:
             for dst in dsts[1:]:
                 main.wait_stream(streams[dst])
         return result

@@ -137,6 +137,9 @@ def live_parameter_names(module: nn.Module, loss: Tensor) -> List[str]:
 # ---------------------------------------------------------------------------------------------
 # the step
 # ---------------------------------------------------------------------------------------------
+TWO_STREAMS = os.environ.get("GHSCN_TWO_STREAMS", "1") != "0"
+
+
 @dataclass
 class StepConfig:
     num_features: int = 9
@@ -199,7 +202,7 @@ class GraphHSCNStep:
             clusters = hetero.assign_clusters(torch.softmax(s, dim=-1))
         return hetero.build_hetero_batch(self.dev["x"], self.dev["edge_index"], self.dev["batch"], clusters,
                                          self.cfg.num_clusters, y=self.dev["y"], padded=self.padded,
-                                         num_graphs=self.B)
+                                         num_graphs=self.B, x_float=x_f)
 
     def _prepare(self) -> None:
         cfg = self.cfg
@@ -249,14 +252,62 @@ class GraphHSCNStep:
     def stage_hscn_update(self):
         self.hscn_opt.step()
 
+    def _step_serial(self, world: int) -> None:
+        st = self.stage_scn_backward()
+        self.scn_grads.all_reduce_mean(world)
+        self.stage_assign_and_hscn_backward(*st)
+        self.hscn_grads.all_reduce_mean(world)
+        self.stage_hscn_update()
+
+    def _step_two_streams(self, world: int) -> None:
+        """Same operations as `_step_serial`, scheduled on two CUDA streams.  The "local" half of the HSCN (l->l convs,
+        readout, loss, backward, AdamW) depends on neither the SCN stage nor the cluster assignment: only the
+        "virtual" branch does (model/hscn.py:84-94 has no virtual->local relation).  So the SCN step, the assignment
+        (K7) and the virtual branch run on the branch stream while the caller's stream runs the local half; the two
+        meet once, at the end of the step.  Everything both halves read is produced on the caller's stream BEFORE
+        the fork (float features, `ptr`, the plain CSR of the molecular graph); every kernel and its inputs are the
+        same as in the serial schedule, so results are bit-identical (tests/test_gpu_step.py)."""
+        from .pyg import nn as pnn
+        main = torch.cuda.current_stream()
+        side = pnn.branch_stream(self.device)
+        N = self.dev["x"].size(0)
+        x_f = self._cast(self.dev["x"])
+        structure_cache().segments(self.dev["batch"], self.B)
+        plain = structure_cache().graph(self.dev["edge_index"], N, N, False)
+        plain.by_dst, plain.by_src                               # built here, read by both streams
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.scn_grads.zero()
+            ei, ew, _, mc, ol = self._forward_scn(x_f)
+            (mc + ol).backward()
+            self.losses[0:1].copy_(mc.detach().view(1))
+            self.losses[1:2].copy_(ol.detach().view(1))
+            self.scn_grads.all_reduce_mean(world)
+            self.scn_opt.step()
+            hb = self._assign(x_f, ei, ew)
+        self.hscn_grads.zero()
+        self.hscn.defer_branch_join = True
+        try:
+            pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)
+        finally:
+            self.hscn.defer_branch_join = False
+        loss, _ = models.criterion(self.cfg.loss_fn, pred, hb["local"].y)
+        loss.backward()
+        self.losses[2:3].copy_(loss.detach().view(1))
+        self.hscn_grads.all_reduce_mean(world)
+        self.hscn_opt.step()
+        main.wait_stream(side)
+
+    def _step(self, world: int) -> None:
+        if TWO_STREAMS and self.device.type == "cuda":
+            self._step_two_streams(world)
+        else:
+            self._step_serial(world)
+
     def run_eager(self, world: int = 1) -> None:
         with structure_hints(**self.hints):
             structure_cache().clear()
-            st = self.stage_scn_backward()
-            self.scn_grads.all_reduce_mean(world)
-            self.stage_assign_and_hscn_backward(*st)
-            self.hscn_grads.all_reduce_mean(world)
-            self.stage_hscn_update()
+            self._step(world)
 
     # -- CUDA graph capture: static shapes (padded virtual layout), no host sync inside -------------------
     def capture(self, world: int = 1, warmup: int = 3) -> None:
@@ -271,11 +322,7 @@ class GraphHSCNStep:
         self.graph = torch.cuda.CUDAGraph()
         with capture_scope(), structure_hints(**self.hints):
             with torch.cuda.graph(self.graph):
-                st = self.stage_scn_backward()
-                self.scn_grads.all_reduce_mean(world)
-                self.stage_assign_and_hscn_backward(*st)
-                self.hscn_grads.all_reduce_mean(world)
-                self.stage_hscn_update()
+                self._step(world)
 
     def run(self, world: int = 1) -> None:
         if self.graph is not None:

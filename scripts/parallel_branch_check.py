@@ -4,13 +4,15 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from graph_hscn_b200.pyg import nn as pnn
+from graph_hscn_b200 import train as gtrain
 from graph_hscn_b200.train import GraphHSCNStep, StepConfig
 
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda:0")
 
-def run(parallel, captured, steps=5):
+def run(parallel, captured, steps=12):
     pnn.PARALLEL_BRANCHES = parallel
+    gtrain.TWO_STREAMS = parallel
     torch.manual_seed(0)
     step = GraphHSCNStep(StepConfig(), bench.make_batch(0), dev, padded=True)
     if captured:

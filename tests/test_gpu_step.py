@@ -74,29 +74,31 @@ def test_padded_captured_replay_equals_compact_eager(cuda):
 
 
 def test_parallel_branch_schedule_is_bit_identical(cuda):
-    """HeteroConv runs the "virtual"-destination relations on a side stream (fork/join inside the CUDA graph):
-    same kernels, same order per destination type -> parameters after 4 steps must equal the serial schedule bit for
-    bit, eager and captured."""
+    """The step runs the SCN stage + cluster assignment + the "virtual" HeteroConv branch on a side stream and the
+    "local" half of the HSCN on the caller's stream (fork/join inside the CUDA graph): same kernels, same inputs ->
+    parameters after several steps must equal the serial schedule bit for bit, eager and captured."""
     from graph_hscn_b200 import synthetic
+    from graph_hscn_b200 import train as gtrain
     from graph_hscn_b200.pyg import nn as pnn
     from graph_hscn_b200.train import GraphHSCNStep, StepConfig
 
     def run(parallel, captured):
-        old = pnn.PARALLEL_BRANCHES
-        pnn.PARALLEL_BRANCHES = parallel
+        old = pnn.PARALLEL_BRANCHES, gtrain.TWO_STREAMS
+        pnn.PARALLEL_BRANCHES = gtrain.TWO_STREAMS = parallel
         try:
             torch.manual_seed(0)
             step = GraphHSCNStep(StepConfig(hidden=64), synthetic.peptides_batch(16, seed=5), cuda, padded=True)
-            n = 4
+            n = 6
             if captured:
                 step.capture(warmup=2)
                 n -= 2
             for _ in range(n):
                 step.run()
             torch.cuda.synchronize()
-            return step.hscn_grads.flat_param.detach().clone(), step.losses.clone()
+            return (torch.cat([step.hscn_grads.flat_param.detach(), step.scn_grads.flat_param.detach()]).clone(),
+                    step.losses.clone())
         finally:
-            pnn.PARALLEL_BRANCHES = old
+            pnn.PARALLEL_BRANCHES, gtrain.TWO_STREAMS = old
 
     for captured in (False, True):
         (p0, l0), (p1, l1) = run(False, captured), run(True, captured)
