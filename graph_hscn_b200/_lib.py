@@ -28,11 +28,14 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_csr_workspace_bytes": (SZ, [I64, I64, I32]),
     "ghscn_csr_build": (I32, [P, P, I64, I64, I32, P, P, P, P, SZ, P]),
     "ghscn_csr_add_loops": (I32, [P, P, P, I64, I64, P, P, P, P]),
+    "ghscn_csr_blocked_smem_bytes": (SZ, [I64, I64]),
+    "ghscn_csr_build_blocked": (I32, [P, P, I64, P, I64, I64, I64, I64, P, P, P, P, P, P, P, P]),
     "ghscn_split_tf32": (I32, [P, I64, P, P, P]),
     "ghscn_split_tf32_cat": (I32, [P, I64, I64, I64, I64, I32, P, P]),
     "ghscn_gemm3x_supported": (I32, [I64, I64, I64]),
     "ghscn_gemm3x_b_image_bytes": (SZ, [I64, I64]),
     "ghscn_gemm3x_prep_b": (I32, [P, I64, I64, I64, I32, P, P]),
+    "ghscn_gemm3x_set_trace": (I32, [P]),
     "ghscn_gemm3x": (I32, [P, I64, I64, I64, P, I64, P, I32, P, I64, P]),
     "ghscn_gemm3x_tn_supported": (I32, [I64, I64, I64]),
     "ghscn_gemm3x_tn_workspace_bytes": (SZ, [I64, I64, I64]),

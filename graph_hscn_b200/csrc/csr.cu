@@ -282,6 +282,145 @@ __global__ void csr_add_loops_kernel(const int* __restrict__ rowptr, const int* 
   perm2[o] = num_edges + r;
 }
 
+
+// ---- K1 fast path: block-diagonal edge lists (PyG collate output) ---------------------------------------------
+// A collated mini-batch stores its edges graph-major and no edge leaves its graph, so the stable sort
+// by (key, edge id) decomposes into independent per-graph counting sorts.  One CTA per graph builds BOTH
+// orientations in shared memory: 32-ary search for the graph's edge range -> per-node counts (smem atomics) ->
+// block scan -> unordered bucket fill -> rank of every edge inside its bucket by edge id (what stability means) ->
+// final slots.  Output is bit-identical to two ghscn_csr_build calls (tests/test_gpu_structures.py).
+constexpr int kBlkThreads = 256;
+
+// First e in [0, num_edges) with src[e] >= target (src is graph-major, so the predicate is monotone); one warp.
+__device__ int64_t warp_lower_bound(const int64_t* __restrict__ src, int64_t num_edges, int64_t target) {
+  const int lane = threadIdx.x & 31;
+  int64_t lo = 0, hi = num_edges;
+  while (hi > lo) {
+    const int64_t span = hi - lo, step = (span + 31) / 32;
+    const int64_t probe = lo + min(span, (int64_t)(lane + 1) * step) - 1;
+    const int below = __popc(__ballot_sync(kFullMask, src[probe] < target));   // monotone: a prefix of the lanes
+    const int64_t new_lo = lo + min(span, (int64_t)below * step);
+    if (below < 32) hi = lo + min(span, (int64_t)(below + 1) * step) - 1;
+    lo = new_lo;
+  }
+  return lo;
+}
+
+// Exclusive scan of cnt[0..n) into off[0..n] (off[n] = total) by the whole CTA; `wtot` holds >= 32 ints.
+__device__ void block_exclusive_scan(const int* __restrict__ cnt, int* __restrict__ off, int n, int* wtot) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const int per = ceil_div(n, (int)blockDim.x);
+  const int beg = min(n, tid * per), end = min(n, beg + per);
+  int sum = 0;
+  for (int i = beg; i < end; ++i) sum += cnt[i];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(kFullMask, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wtot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const int t = lane < nw ? wtot[lane] : 0;
+    int ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(kFullMask, ti, o);
+      if (lane >= o) ti += v;
+    }
+    wtot[lane] = ti - t;
+  }
+  __syncthreads();
+  int run = wtot[wid] + incl - sum;
+  for (int i = beg; i < end; ++i) { off[i] = run; run += cnt[i]; }
+  if (tid == blockDim.x - 1) off[n] = run;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBlkThreads)
+csr_blocked_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t num_edges,
+                   const int* __restrict__ ptr, int num_graphs, int num_nodes, int max_nodes, int max_edges,
+                   int* __restrict__ rowptr_d, int* __restrict__ col_d, int* __restrict__ perm_d,
+                   int* __restrict__ rowptr_s, int* __restrict__ col_s, int* __restrict__ perm_s,
+                   int* __restrict__ status) {
+  extern __shared__ int blk_sm[];
+  int* off_d = blk_sm;                    // [max_nodes + 1] row offsets by destination (graph-local)
+  int* off_s = off_d + max_nodes + 1;     // [max_nodes + 1] ... by source
+  int* cur_d = off_s + max_nodes + 1;     // [max_nodes] counts, then fill cursors
+  int* cur_s = cur_d + max_nodes;
+  int* key_d = cur_s + max_nodes;         // [max_edges] local destination of every edge of the graph
+  int* key_s = key_d + max_edges;         // [max_edges] local source
+  int* tmp_d = key_s + max_edges;         // [max_edges] bucket-ordered (unstable) local edge ids
+  int* tmp_s = tmp_d + max_edges;
+  __shared__ int wtot[32];
+  __shared__ int64_t range[2];
+
+  const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+  const int n0 = ptr[g], n1 = ptr[g + 1], n = n1 - n0;
+  if (warp == 0) {
+    const int64_t v = warp_lower_bound(src, num_edges, n0);
+    if (tid == 0) range[0] = v;
+  } else if (warp == 1) {
+    const int64_t v = warp_lower_bound(src, num_edges, n1);
+    if (tid == 32) range[1] = v;
+  }
+  for (int i = tid; i < n && i < max_nodes; i += kBlkThreads) { cur_d[i] = 0; cur_s[i] = 0; }
+  __syncthreads();
+  const int64_t e0 = range[0];
+  const int ne = (int)(range[1] - e0);
+  if (g == num_graphs - 1)                 // rows after the last graph (none in a collated batch) are empty
+    for (int r = n1 + tid; r <= num_nodes; r += kBlkThreads) { rowptr_d[r] = (int)num_edges; rowptr_s[r] = (int)num_edges; }
+  if (n > max_nodes || ne > max_edges || n < 0) {      // the caller's bounds do not hold: report, write nothing
+    if (tid == 0) atomicOr(status, 1);
+    return;
+  }
+  bool bad = false;
+  for (int e = tid; e < ne; e += kBlkThreads) {
+    const int64_t s = src[e0 + e] - n0, d = dst[e0 + e] - n0;
+    const bool ok = s >= 0 && s < n && d >= 0 && d < n;          // an edge leaving its graph: not block diagonal
+    bad |= !ok;
+    key_s[e] = ok ? (int)s : -1;
+    key_d[e] = ok ? (int)d : -1;
+    if (ok) { atomicAdd(&cur_s[(int)s], 1); atomicAdd(&cur_d[(int)d], 1); }
+  }
+  if (bad) atomicOr(status, 2);
+  __syncthreads();
+  block_exclusive_scan(cur_d, off_d, n, wtot);
+  block_exclusive_scan(cur_s, off_s, n, wtot);
+  for (int i = tid; i < n; i += kBlkThreads) {
+    cur_d[i] = off_d[i];
+    cur_s[i] = off_s[i];
+    rowptr_d[n0 + i] = (int)e0 + off_d[i];
+    rowptr_s[n0 + i] = (int)e0 + off_s[i];
+  }
+  __syncthreads();
+  for (int e = tid; e < ne; e += kBlkThreads) {
+    const int d = key_d[e], s = key_s[e];
+    if (d >= 0) { tmp_d[atomicAdd(&cur_d[d], 1)] = e; tmp_s[atomicAdd(&cur_s[s], 1)] = e; }
+  }
+  __syncthreads();
+  const int placed = off_d[n];            // == ne unless an edge was rejected
+  for (int t = tid; t < placed; t += kBlkThreads) {
+    {
+      const int e = tmp_d[t], r = key_d[e], a = off_d[r], b = off_d[r + 1];
+      int rank = 0;
+      for (int u = a; u < b; ++u) rank += (tmp_d[u] < e) ? 1 : 0;
+      const int64_t o = e0 + a + rank;
+      perm_d[o] = (int)e0 + e;
+      col_d[o] = n0 + key_s[e];
+    }
+    {
+      const int e = tmp_s[t], r = key_s[e], a = off_s[r], b = off_s[r + 1];
+      int rank = 0;
+      for (int u = a; u < b; ++u) rank += (tmp_s[u] < e) ? 1 : 0;
+      const int64_t o = e0 + a + rank;
+      perm_s[o] = (int)e0 + e;
+      col_s[o] = n0 + key_d[e];
+    }
+  }
+}
+
 }  // namespace ghscn
 
 using namespace ghscn;
@@ -429,6 +568,32 @@ int ghscn_csr_add_loops(const int32_t* rowptr, const int32_t* col, const int32_t
   GHSCN_REQUIRE(rowptr && rowptr2 && (num_rows + num_edges == 0 || (col2 && perm2)) && (num_edges == 0 || (col && perm)));
   csr_add_loops_kernel<<<(unsigned)ceil_div<int64_t>(num_rows + 1, 256), 256, 0, as_stream(stream)>>>(
       rowptr, col, perm, (int)num_rows, (int)num_edges, rowptr2, col2, perm2);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+size_t ghscn_csr_blocked_smem_bytes(int64_t max_nodes_per_graph, int64_t max_edges_per_graph) {
+  if (max_nodes_per_graph < 0 || max_edges_per_graph < 0) return 0;
+  return (size_t)(4 * max_nodes_per_graph + 2 + 4 * max_edges_per_graph) * sizeof(int);
+}
+
+int ghscn_csr_build_blocked(const int64_t* src, const int64_t* dst, int64_t num_edges, const int32_t* ptr,
+                            int64_t num_graphs, int64_t num_nodes, int64_t max_nodes_per_graph,
+                            int64_t max_edges_per_graph, int32_t* rowptr_dst, int32_t* col_dst, int32_t* perm_dst,
+                            int32_t* rowptr_src, int32_t* col_src, int32_t* perm_src, int32_t* status,
+                            ghscn_stream_t stream) {
+  GHSCN_REQUIRE(src && dst && ptr && rowptr_dst && col_dst && perm_dst && rowptr_src && col_src && perm_src && status);
+  GHSCN_REQUIRE(num_edges > 0 && num_graphs > 0 && num_nodes > 0 && max_nodes_per_graph > 0 && max_edges_per_graph > 0);
+  GHSCN_REQUIRE(num_edges < ((int64_t)1 << 31) && num_nodes < ((int64_t)1 << 31) - 1 && num_graphs < ((int64_t)1 << 31));
+  const size_t smem = ghscn_csr_blocked_smem_bytes(max_nodes_per_graph, max_edges_per_graph);
+  if (smem > 200 * 1024) return GHSCN_E_UNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(csr_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  csr_blocked_kernel<<<(unsigned)num_graphs, kBlkThreads, smem, as_stream(stream)>>>(
+      src, dst, num_edges, ptr, (int)num_graphs, (int)num_nodes, (int)max_nodes_per_graph, (int)max_edges_per_graph,
+      rowptr_dst, col_dst, perm_dst, rowptr_src, col_src, perm_src, status);
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }

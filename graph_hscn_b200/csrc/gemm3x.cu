@@ -32,6 +32,38 @@
 namespace ghscn {
 namespace {
 
+// Pipeline timeline of CTA (0,0) for scripts/gemm3x_trace.py: clock() stamps kept in shared memory (a stamp is one
+// CS2R + STS) and dumped at kernel exit.  Compiled in only with -DGHSCN_GEMM3X_TRACE.
+#ifdef GHSCN_GEMM3X_TRACE
+__device__ long long* g_trace = nullptr;
+constexpr int kTraceSlots = 1024;
+#define GHSCN_TR_DECL __shared__ unsigned int s_trace[kTraceSlots];
+#define GHSCN_TR_INIT                                                                          \
+  do {                                                                                         \
+    for (int i_ = threadIdx.x; i_ < kTraceSlots; i_ += blockDim.x) s_trace[i_] = 0u;           \
+  } while (0)
+#define GHSCN_TR(slot)                                                                         \
+  do {                                                                                         \
+    if ((threadIdx.x & 31) == 0 && (slot) < kTraceSlots) s_trace[(slot)] = (unsigned int)clock(); \
+  } while (0)
+#define GHSCN_TR_DUMP                                                                          \
+  do {                                                                                         \
+    __syncthreads();                                                                           \
+    if (g_trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0)                              \
+      for (int i_ = threadIdx.x; i_ < kTraceSlots; i_ += blockDim.x) g_trace[i_] = s_trace[i_]; \
+  } while (0)
+#define GHSCN_TR1(slot)                                                                        \
+  do {                                                                                         \
+    if ((slot) < kTraceSlots) s_trace[(slot)] = (unsigned int)clock();                         \
+  } while (0)
+#else
+#define GHSCN_TR1(slot) do { } while (0)
+#define GHSCN_TR_DECL
+#define GHSCN_TR_INIT do { } while (0)
+#define GHSCN_TR(slot) do { } while (0)
+#define GHSCN_TR_DUMP do { } while (0)
+#endif
+
 constexpr int kTileM = 128;
 constexpr int kHalfMax = 160;                     // columns per accumulator; 3 accumulators = 480 of 512 TMEM columns
 constexpr int kMaxN = 2 * kHalfMax;
@@ -215,9 +247,9 @@ __host__ __device__ inline Halves make_halves(int n_out) {
 //                     pre-split and pre-swizzled by gemm3x_prep_b_kernel)
 //   warp 1            MMA issuer, convergent (owns TMEM): per K = 8 step  cross += a_lo.b_hi, cross += a_hi.b_lo,
 //                     main[chunk & 1] += a_hi.b_hi; commits the stage barriers, then the accumulator barrier
-//   warps 2..5        A producers: 128-bit global loads (register ring, 3 chunks ahead) -> hi/lo split ->
-//                     swizzled smem (2-stage A ring) -> fence.proxy.async -> one mbarrier arrive per warp
-//   warps 6..9        epilogue (own TMEM lane quadrant = warp & 3): tcgen05.ld of the three accumulators -> fp32 sum
+//   warps 2..7        A producers, each owning whole K chunks: 128-bit global loads of the chunk (all in flight) ->
+//                     hi/lo split -> swizzled smem (2-stage A ring) -> fence.proxy.async -> mbarrier arrive
+//   warps 8..11       epilogue (own TMEM lane quadrant = warp & 3): tcgen05.ld of the three accumulators -> fp32 sum
 //                     -> bias / ReLU -> per-warp padded staging tile -> coalesced 128-bit global stores; the stores of
 //                     half h overlap the main loop of half h + 1
 // =====================================================================================================================
@@ -228,7 +260,8 @@ constexpr int kBStageBytes = 2 * kHalfMax * kChunkK * 4;    // hi block + lo blo
 constexpr int kSubCols = 64;                                // epilogue drains 64 columns at a time
 constexpr int kStageRow = (kSubCols + 4) * 4;               // padded staging row: 272 B (conflict-free float4 stores)
 constexpr int kNnSmem = kAStages * 2 * kABytes + kBStages * kBStageBytes + kTileM * kStageRow + 1024;
-constexpr int kNnThreads = 320;
+constexpr int kNnProducerWarps = 6;
+constexpr int kNnThreads = 32 * (2 + kNnProducerWarps + 4);
 static_assert(kNnSmem <= kSmemLimit - 1024, "gemm3x shared memory budget");
 
 struct NnPlan {
@@ -290,6 +323,9 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
   __shared__ __align__(8) unsigned long long b_full[kBStages], b_empty[kBStages];
   __shared__ __align__(8) unsigned long long acc_full, acc_empty;
   __shared__ uint32_t tmem_slot;
+  __shared__ volatile int a_turn;                   // next chunk whose producer may test its stage's empty barrier
+  GHSCN_TR_DECL
+  GHSCN_TR_INIT;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_addr(smem_raw) + 1023u) & ~1023u;
@@ -299,12 +335,16 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
   const int m0 = blockIdx.x * kTileM;
   const int kchunks = plan.kchunks, nh = plan.hv.count;
   const int total_chunks = nh * kchunks;
+  // Every CTA streams the SAME weight image; walking it in lock step makes ~148 SMs hit the same few L2 slices at
+  // once.  CTA b therefore starts at K chunk b mod kchunks (a sum: any chunk order is valid, and it is fixed per tile).
+  const int rot = (int)(blockIdx.x % (unsigned)kchunks);
 
   if (tid == 0) {
-    for (int s = 0; s < kAStages; ++s) { bar_init(smem_addr(&a_full[s]), 4); bar_init(smem_addr(&a_empty[s]), 1); }
+    for (int s = 0; s < kAStages; ++s) { bar_init(smem_addr(&a_full[s]), 1); bar_init(smem_addr(&a_empty[s]), 1); }
     for (int s = 0; s < kBStages; ++s) { bar_init(smem_addr(&b_full[s]), 1); bar_init(smem_addr(&b_empty[s]), 1); }
     bar_init(smem_addr(&acc_full), 1);
     bar_init(smem_addr(&acc_empty), 4);
+    a_turn = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_addr(&tmem_slot), 512u);
@@ -317,10 +357,12 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
     // ===== weight-image producer =====
     if (lane == 0) {
       for (int g = 0; g < total_chunks; ++g) {
-        const int h = g >= kchunks ? 1 : 0, kc = g - h * kchunks;
+        const int h = g >= kchunks ? 1 : 0, kc = (g - h * kchunks + rot) % kchunks;
         const int s = g % kBStages;
         const uint32_t ph = (uint32_t)(g / kBStages) & 1u;
+        if (g < 50) GHSCN_TR1(300 + 2 * g);
         bar_wait(smem_addr(&b_empty[s]), ph ^ 1u);
+        if (g < 50) GHSCN_TR1(301 + 2 * g);
         const uint32_t bytes = (uint32_t)(2 * plan.hv.pad[h] * kChunkK * 4);
         const uint32_t fb = smem_addr(&b_full[s]);
         bar_arrive_expect_tx(fb, bytes);
@@ -338,23 +380,27 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
           bar_wait(smem_addr(&acc_empty), (uint32_t)(h - 1) & 1u);
           tc_fence_after();
         }
-        for (int kc = 0; kc < kchunks; ++kc) {
-          const int g = h * kchunks + kc;
+        for (int pos = 0; pos < kchunks; ++pos) {
+          const int g = h * kchunks + pos;
+          const int kc = (pos + rot) % kchunks;
           const int sa = g % kAStages, sb = g % kBStages;
+          GHSCN_TR(3 * g);
           bar_wait(smem_addr(&a_full[sa]), (uint32_t)(g / kAStages) & 1u);
+          GHSCN_TR(3 * g + 1);
           bar_wait(smem_addr(&b_full[sb]), (uint32_t)(g / kBStages) & 1u);
+          GHSCN_TR(3 * g + 2);
           tc_fence_after();
           const uint32_t as = a_ring + (uint32_t)sa * 2 * kABytes, bs = b_ring + (uint32_t)sb * kBStageBytes;
           const uint64_t a_hi = desc_k_sw128(as), a_lo = desc_k_sw128(as + kABytes);
           const uint64_t b_hi = desc_k_sw128(bs), b_lo = desc_k_sw128(bs + lo_off);
           const int kleft = k_dim - kc * kChunkK;
           const int ksteps = kleft >= kChunkK ? kChunkK / 8 : (kleft + 7) / 8;
-          const uint32_t d_main = tmem_base + ((kc & 1) ? kColMain1 : kColMain0);
+          const uint32_t d_main = tmem_base + ((pos & 1) ? kColMain1 : kColMain0);
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t adv = (uint64_t)(ks * 2);   // 8 tf32 = 32 bytes = 2 x 16-byte units
-            mma_tf32(tmem_base + kColCross, a_lo + adv, b_hi + adv, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+            mma_tf32(tmem_base + kColCross, a_lo + adv, b_hi + adv, idesc, (pos > 0 || ks > 0) ? 1u : 0u);
             mma_tf32(tmem_base + kColCross, a_hi + adv, b_lo + adv, idesc, 1u);
-            mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (kc > 1 || ks > 0) ? 1u : 0u);
+            mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (pos > 1 || ks > 0) ? 1u : 0u);
           }
           mma_commit(smem_addr(&a_empty[sa]));
           mma_commit(smem_addr(&b_empty[sb]));
@@ -363,48 +409,47 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
-    // ===== A producers (warps 2..5) =====
-    const int t = tid - 64;                 // 0..127
-    const int cq = t & 7;                   // 16-byte chunk of the 128-byte row
-    const int r0 = t >> 3;                  // rows r0 + 16 j
-    const int r8 = r0 & 7;
-    const uint32_t row_off = (uint32_t)((r0 >> 3) * 1024 + r8 * 128 + ((cq ^ r8) << 4));
-    constexpr int kDepth = 3;               // K chunks of A in flight per thread (register ring)
-    float4 ring[kDepth][8];
-    auto load_chunk = [&](int g, float4* dst) {
-      const int kc = g >= kchunks ? g - kchunks : g;
+  } else if (warp < 2 + kNnProducerWarps) {
+    // ===== A producers (warps 2..7): every warp owns whole K chunks (g = pw, pw + 6, ...) =====
+    // All 32 float4 of the chunk a lane is responsible for are loaded at once; after the split + stores no global
+    // load of this thread is outstanding, so fence.proxy.async is cheap, and the other five warps keep their
+    // chunks' loads in flight meanwhile (see the note in gemm3x_tn_kernel).
+    const int pw = warp - 2;
+    const int cq = lane & 7;                // 16-byte chunk of the 128-byte row
+    const int rsub = lane >> 3;             // rows rsub + 4 j
+    for (int g = pw; g < total_chunks; g += kNnProducerWarps) {
+      const int kc = ((g >= kchunks ? g - kchunks : g) + rot) % kchunks;
       const int k = kc * kChunkK + cq * 4;
       const bool kvalid = k < k_dim;
+      const float* ap = a + (int64_t)(m0 + rsub) * lda + k;
+      float4 v[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = m0 + r0 + 16 * j;
-        dst[j] = (kvalid && r < m_rows) ? ldg_f4(a + (int64_t)r * lda + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 32; ++j)
+        v[j] = (kvalid && m0 + rsub + 4 * j < m_rows) ? ldg_f4(ap + (int64_t)(4 * j) * lda)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int s = g % kAStages;
+      // Producers test the empty barriers in chunk order (a_turn): a parity wait is only meaningful when the waiter
+      // is at most one phase behind, and the owner of chunk g - kAStages has passed its wait by now.
+      GHSCN_TR(100 + 4 * g);
+      while (a_turn != g) { }
+      bar_wait(smem_addr(&a_empty[s]), ((uint32_t)(g / kAStages) & 1u) ^ 1u);
+      GHSCN_TR(100 + 4 * g + 1);
+      __syncwarp();
+      if (lane == 0) a_turn = g + 1;
+      unsigned char* st = smem_gen + (size_t)s * 2 * kABytes;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t off = sw128_offset(rsub + 4 * j, cq * 4);
+        split_store(st + off, st + kABytes + off, v[j]);
       }
-    };
-#pragma unroll
-    for (int d = 0; d < kDepth; ++d)
-      if (d < total_chunks) load_chunk(d, ring[d]);
-    for (int gb = 0; gb < total_chunks; gb += kDepth) {
-#pragma unroll
-      for (int d = 0; d < kDepth; ++d) {
-        const int g = gb + d;
-        if (g < total_chunks) {
-          const int s = g % kAStages;
-          bar_wait(smem_addr(&a_empty[s]), ((uint32_t)(g / kAStages) & 1u) ^ 1u);
-          unsigned char* st = smem_gen + (size_t)s * 2 * kABytes + row_off;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)                    // rows +16 = two 8-row atoms = 2048 B
-            split_store(st + j * 2048, st + kABytes + j * 2048, ring[d][j]);
-          fence_proxy_async();                           // generic-proxy stores -> async proxy (tcgen05.mma)
-          __syncwarp();
-          if (lane == 0) bar_arrive(smem_addr(&a_full[s]));
-          if (g + kDepth < total_chunks) load_chunk(g + kDepth, ring[d]);
-        }
-      }
+      GHSCN_TR(100 + 4 * g + 2);
+      fence_proxy_async();                             // generic-proxy stores -> async proxy (tcgen05.mma)
+      __syncwarp();
+      if (lane == 0) bar_arrive(smem_addr(&a_full[s]));
+      GHSCN_TR(100 + 4 * g + 3);
     }
   } else {
-    // ===== epilogue (warps 6..9) =====
+    // ===== epilogue (warps 8..11) =====
     const int quad = warp & 3;                                  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;                           // tile row == TMEM lane
     const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -413,7 +458,9 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
     const bool use_main1 = kchunks > 1;
     const int hl = lane & 15, rsel = lane >> 4;                 // store phase: half-warp per row, 16 float4 lanes
     for (int h = 0; h < nh; ++h) {
+      if (quad == 0) GHSCN_TR(400 + 4 * h);
       bar_wait(smem_addr(&acc_full), (uint32_t)h & 1u);
+      if (quad == 0) GHSCN_TR(401 + 4 * h);
       tc_fence_after();
       const int hpad = plan.hv.pad[h], hvalid = plan.hv.valid[h], hcol = plan.hv.col[h];
       for (int c0 = 0; c0 < hpad; c0 += kSubCols) {
@@ -439,6 +486,7 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
           tc_fence_before();
           __syncwarp();
           if (lane == 0) bar_arrive(smem_addr(&acc_empty));
+          if (quad == 0) GHSCN_TR(402 + 4 * h);
         }
         __syncwarp();                                           // staging rows of this warp are complete
         // coalesced 128-bit stores, two rows (up to 256 contiguous bytes each) per instruction.  Per-row bulk
@@ -460,10 +508,12 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
 
   tc_fence_before();
   __syncthreads();
+  if (warp == 8) GHSCN_TR(410);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
   }
+  GHSCN_TR_DUMP;
 }
 
 // =====================================================================================================================
@@ -521,6 +571,9 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
   __shared__ __align__(8) unsigned long long full_bar[kTnStages], empty_bar[kTnStages];
   __shared__ __align__(8) unsigned long long accum_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ volatile int turn;                     // next chunk whose producer may test its stage's empty barrier
+  GHSCN_TR_DECL
+  GHSCN_TR_INIT;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_addr(smem_raw) + 1023u) & ~1023u;
@@ -536,10 +589,11 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
 
   if (tid == 0) {
     for (int s = 0; s < kTnStages; ++s) {
-      bar_init(smem_addr(&full_bar[s]), kTnProducers / 32);
+      bar_init(smem_addr(&full_bar[s]), 1);            // the one producer warp that owns the stage's chunk
       bar_init(smem_addr(&empty_bar[s]), 1);
     }
     bar_init(smem_addr(&accum_bar), 1);
+    turn = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(smem_addr(&tmem_slot), 512u);
@@ -555,7 +609,9 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
       constexpr uint32_t a_sbo = kTnABlocks * 512, b_sbo = kTnBBlocks * 512;   // one 4-row group of all blocks
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % kTnStages;
+        GHSCN_TR(2 * c);
         bar_wait(smem_addr(&full_bar[s]), (uint32_t)(c / kTnStages) & 1u);
+        GHSCN_TR(2 * c + 1);
         tc_fence_after();
         const uint32_t st = smem_base + (uint32_t)s * kTnStageBytes;
         const uint32_t a_hi = st, a_lo = st + kTnAPart, b_hi = st + 2 * kTnAPart, b_lo = b_hi + kTnBPart;
@@ -576,72 +632,63 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
     }
     __syncwarp();
   } else {
-    // ===== producers =====
-    const int t = tid - 32;                          // 0..255
-    constexpr int kAItems = kTnRows * 32 / kTnProducers;                                   // 2 float4 of P per thread
-    constexpr int kBItems = (kTnRows * (kHalfMax / 4) + kTnProducers - 1) / kTnProducers;  // <= 3 float4 of Q
-    constexpr int kDepth = 4;
-    const int q4 = hpad / 4;                         // float4 per row of the Q slice (zero padded to hpad)
-    // chunk-invariant geometry of this thread's items
-    uint32_t a_soff[kAItems], b_soff[kBItems];
-    int64_t a_goff[kAItems], b_goff[kBItems];
-    int a_rr[kAItems], b_rr[kBItems];
-    bool a_ok[kAItems], b_ok[kBItems];
-#pragma unroll
-    for (int i = 0; i < kAItems; ++i) {
-      const int item = t + i * kTnProducers, rr = item >> 5, f4 = item & 31;
-      a_rr[i] = rr;
-      a_soff[i] = mn_offset(rr, f4, kTnABlocks);
-      a_goff[i] = (int64_t)rr * ldp + m0 + f4 * 4;
-      a_ok[i] = m0 + f4 * 4 < m_out;
-    }
-#pragma unroll
-    for (int i = 0; i < kBItems; ++i) {
-      const int item = t + i * kTnProducers, rr = item / q4, f4 = item - rr * q4;
-      const bool in = item < kTnRows * q4;
-      b_rr[i] = in ? rr : 0;
-      b_soff[i] = in ? 2 * kTnAPart + mn_offset(rr, f4, kTnBBlocks) : 0xffffffffu;
-      b_goff[i] = (int64_t)rr * ldq + hcol + f4 * 4;
-      b_ok[i] = in && f4 * 4 < hvalid;
-    }
-    float4 ra[kDepth][kAItems], rb[kDepth][kBItems];
-    auto load_chunk = [&](int c, float4* da, float4* db) {
+    // ===== producers: every warp owns whole stages (chunk pw, pw + 8, ...) =====
+    // A warp loads ALL operand data of its chunk into registers (36 float4 per lane, every load in flight at once),
+    // then splits and stores it and only then executes fence.proxy.async: the fence waits for the thread's
+    // outstanding global loads, and here there are none left, while the other seven warps have their chunks'
+    // loads in flight.  (A register-prefetch ring inside the fencing thread is drained by every fence: that
+    // version ran at one memory latency per chunk.)
+    const int pw = warp - 1;                         // 0..7
+    constexpr int kQ4 = kHalfMax / 4;                // float4 slots per Q row (padded to 160 columns)
+    constexpr int kAItems = kTnRows;                 // P: one row per item, lane = float4 column     (16)
+    constexpr int kBItems = kTnRows * kQ4 / 32;      // Q: item = lane + 32 i -> (row, float4 column) (20)
+    const bool a_col_ok = m0 + lane * 4 < m_out;
+    for (int c = pw; c < nchunks; c += kTnProducers / 32) {
       const int r_base = (chunk0 + c) * kTnRows;
-      const float* pb = pmat + (int64_t)r_base * ldp;
-      const float* qb = qmat + (int64_t)r_base * ldq;
+      const float* pb = pmat + (int64_t)r_base * ldp + m0 + lane * 4;
+      const float* qb = qmat + (int64_t)r_base * ldq + hcol;
+      float4 va[kAItems], vb[kBItems];
 #pragma unroll
       for (int i = 0; i < kAItems; ++i)
-        da[i] = (a_ok[i] && r_base + a_rr[i] < rows) ? ldg_f4(pb + a_goff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        va[i] = (a_col_ok && r_base + i < rows) ? ldg_f4(pb + (int64_t)i * ldp) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < kBItems; ++i)
-        db[i] = (b_ok[i] && r_base + b_rr[i] < rows) ? ldg_f4(qb + b_goff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
+      for (int i = 0; i < kBItems; ++i) {
+        const int item = lane + 32 * i, rr = item / kQ4, f4 = item - rr * kQ4;
+        vb[i] = (f4 * 4 < hvalid && r_base + rr < rows) ? ldg_f4(qb + (int64_t)rr * ldq + f4 * 4)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const int s = c % kTnStages;
+      if (pw == 0) GHSCN_TR(200 + 5 * (c / 8));
+      while (turn != c) { }                          // empty barriers are tested in chunk order (parity waits must
+      bar_wait(smem_addr(&empty_bar[s]), ((uint32_t)(c / kTnStages) & 1u) ^ 1u);   // be at most one phase behind)
+      __syncwarp();
+      if (lane == 0) turn = c + 1;
+      if (pw == 0) GHSCN_TR(200 + 5 * (c / 8) + 1);
+      unsigned char* st = smem_gen + (size_t)s * kTnStageBytes;
 #pragma unroll
-    for (int d = 0; d < kDepth; ++d)
-      if (d < nchunks) load_chunk(d, ra[d], rb[d]);
-    for (int cb = 0; cb < nchunks; cb += kDepth) {
+      for (int i = 0; i < kAItems; ++i) {
+        const uint32_t off = mn_offset(i, lane, kTnABlocks);
+        split_store(st + off, st + kTnAPart + off, va[i]);
+      }
 #pragma unroll
-      for (int d = 0; d < kDepth; ++d) {
-        const int c = cb + d;
-        if (c < nchunks) {
-          const int s = c % kTnStages;
-          bar_wait(smem_addr(&empty_bar[s]), ((uint32_t)(c / kTnStages) & 1u) ^ 1u);
-          unsigned char* st = smem_gen + (size_t)s * kTnStageBytes;
-#pragma unroll
-          for (int i = 0; i < kAItems; ++i) split_store(st + a_soff[i], st + kTnAPart + a_soff[i], ra[d][i]);
-#pragma unroll
-          for (int i = 0; i < kBItems; ++i)
-            if (b_soff[i] != 0xffffffffu) split_store(st + b_soff[i], st + kTnBPart + b_soff[i], rb[d][i]);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) bar_arrive(smem_addr(&full_bar[s]));
-          if (c + kDepth < nchunks) load_chunk(c + kDepth, ra[d], rb[d]);
+      for (int i = 0; i < kBItems; ++i) {
+        const int item = lane + 32 * i, rr = item / kQ4, f4 = item - rr * kQ4;
+        if (f4 * 4 < hpad) {
+          const uint32_t off = 2 * kTnAPart + mn_offset(rr, f4, kTnBBlocks);
+          split_store(st + off, st + kTnBPart + off, vb[i]);
         }
       }
+      if (pw == 0) GHSCN_TR(200 + 5 * (c / 8) + 2);
+      fence_proxy_async();
+      if (pw == 0) GHSCN_TR(200 + 5 * (c / 8) + 3);
+      __syncwarp();
+      if (lane == 0) bar_arrive(smem_addr(&full_bar[s]));
+      if (pw == 0) GHSCN_TR(200 + 5 * (c / 8) + 4);
     }
 
     // ----- epilogue: two warps per TMEM lane quadrant, each takes every other 16-column group -----
     bar_wait(smem_addr(&accum_bar), 0);
+    if (pw == 0) GHSCN_TR(500);
     tc_fence_after();
     const int quad = warp & 3;
     const int half = (warp - 1) >> 2;                // warps 1..4 -> 0, warps 5..8 -> 1
@@ -680,12 +727,14 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
     }
   }
 
+  if (warp == 1) GHSCN_TR(510);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
   }
+  GHSCN_TR_DUMP;
 }
 
 // out[e] = sum_s partial[s][e], slabs added in index order (deterministic).
@@ -734,6 +783,16 @@ int ghscn_gemm3x_prep_b(const float* w, int64_t ldw, int64_t n_out, int64_t k, i
       w, ldw, (int)n_out, (int)k, transpose, p, static_cast<unsigned char*>(image));
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
+}
+
+int ghscn_gemm3x_set_trace(void* device_buffer) {
+#ifdef GHSCN_GEMM3X_TRACE
+  long long* p = static_cast<long long*>(device_buffer);
+  return (int)cudaMemcpyToSymbol(g_trace, &p, sizeof(p));
+#else
+  (void)device_buffer;
+  return GHSCN_E_UNSUPPORTED;
+#endif
 }
 
 int ghscn_gemm3x(const float* a, int64_t lda, int64_t m, int64_t k, const void* b_image, int64_t n_out,

@@ -112,6 +112,7 @@ class GraphStructure:
         self._keep: list = []
         self._parent: Optional["GraphStructure"] = None   # set by StructureCache.alias
         self._plain: Optional["GraphStructure"] = None    # loop-free edge list: derive instead of sorting again
+        self._blocks: Optional["EdgeBlocks"] = None       # collated batch: per-graph counting sort, no radix passes
 
     @property
     def num_edges(self) -> int:
@@ -133,8 +134,30 @@ class GraphStructure:
                    _stream())
         return CSR(rowptr, col, perm, R, E, E + R)
 
+    def _build_blocked(self) -> None:
+        """K1 fast path: both orientations in ONE launch, one CTA per graph (ghscn_csr_build_blocked)."""
+        b = self._blocks
+        E, N, dev = self.num_edges, self.num_dst, self.edge_index.device
+        rp, ep = (N + 1 + 63) // 64 * 64, (E + 63) // 64 * 64         # 256-byte aligned sub-arrays of one buffer
+        out = torch.empty(2 * rp + 4 * ep, dtype=torch.int32, device=dev)
+        rp_d, rp_s = out[:N + 1], out[rp:rp + N + 1]
+        col_d, perm_d, col_s, perm_s = (out[2 * rp + i * ep:2 * rp + i * ep + E] for i in range(4))
+        lib().call("ghscn_csr_build_blocked", _p(self.edge_index[0]), _p(self.edge_index[1]), E, _p(b.ptr),
+                   b.num_graphs, N, b.max_nodes, b.max_edges, _p(rp_d), _p(col_d), _p(perm_d), _p(rp_s), _p(col_s),
+                   _p(perm_s), _p(b.status), _stream())
+        self._by_dst = CSR(rp_d, col_d, perm_d, N, E, E)
+        self._by_src = CSR(rp_s, col_s, perm_s, N, E, E)
+
+    def _blocked_ok(self) -> bool:
+        b = self._blocks
+        if b is None or self.add_self_loops or self.num_src != self.num_dst or self.num_edges == 0:
+            return False
+        return lib().query("ghscn_csr_blocked_smem_bytes", b.max_nodes, b.max_edges) <= 200 * 1024
+
     @property
     def by_dst(self) -> CSR:
+        if self._by_dst is None and self._blocked_ok():
+            self._build_blocked()
         if self._by_dst is None and self._parent is not None:
             self._by_dst = self._as_plain(self._parent.by_dst)
         if self._by_dst is None and self._plain is not None:
@@ -145,6 +168,8 @@ class GraphStructure:
 
     @property
     def by_src(self) -> CSR:
+        if self._by_src is None and self._blocked_ok():
+            self._build_blocked()
         if self._by_src is None and self._parent is not None:
             self._by_src = self._as_plain(self._parent.by_src)
         if self._by_src is None and self._plain is not None:
@@ -222,6 +247,30 @@ class Segments:
     max_rows: int = 0              # max rows of any segment (0 = unknown)
 
 
+@dataclass
+class EdgeBlocks:
+    """Collate-time knowledge about an edge list: edges are stored graph-major and stay inside their graph."""
+    ptr: Tensor                    # int32 [B+1] node ranges
+    num_graphs: int
+    max_nodes: int                 # max nodes of any graph
+    max_edges: int                 # max edges of any graph
+    status: Tensor                 # int32 [1], non-zero if a kernel found the promise broken
+
+
+def edge_blocks_from_batch(edge_index: Tensor, batch: Tensor, num_graphs: Optional[int] = None
+                           ) -> Optional[Tuple[int, int]]:
+    """(max nodes per graph, max edges per graph) if `edge_index` is block diagonal and graph-major w.r.t. the
+    sorted `batch` vector, else None.  Reads the result back (host sync): collate time / eager mode only."""
+    if edge_index.numel() == 0 or batch.numel() == 0:
+        return None
+    g_src, g_dst = batch[edge_index[0]], batch[edge_index[1]]
+    ok = bool((g_src == g_dst).all()) and bool((g_src[1:] >= g_src[:-1]).all()) and bool((batch[1:] >= batch[:-1]).all())
+    if not ok:
+        return None
+    B = int(num_graphs) if num_graphs is not None else int(batch[-1]) + 1
+    return int(torch.bincount(batch, minlength=B).max()), int(torch.bincount(g_src, minlength=B).max())
+
+
 class StructureCache:
     """Memoises structures by tensor identity; the cached entry pins the index tensor."""
 
@@ -229,7 +278,27 @@ class StructureCache:
         self.capacity = capacity
         self._graphs: "OrderedDict[tuple, GraphStructure]" = OrderedDict()
         self._segments: "OrderedDict[tuple, Tuple[Tensor, Segments]]" = OrderedDict()
+        self._blocks: "OrderedDict[tuple, EdgeBlocks]" = OrderedDict()
+        self._status: Dict[int, Tensor] = {}
         self.builds = 0
+
+    def blocked_status(self, device) -> Tensor:
+        """Device flag OR-ed by ghscn_csr_build_blocked when its preconditions do not hold (0 = fine)."""
+        idx = torch.device(device).index or 0
+        if idx not in self._status:
+            self._status[idx] = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._status[idx]
+
+    def register_blocks(self, edge_index: Tensor, ptr: Tensor, num_graphs: int, max_nodes: int, max_edges: int
+                        ) -> EdgeBlocks:
+        """Promise that `edge_index` is the collated edge list of the graphs delimited by `ptr`: its CSRs are then
+        built by the per-graph kernel (one launch) instead of the radix passes."""
+        b = EdgeBlocks(ptr if ptr.dtype == torch.int32 else ptr.to(torch.int32), int(num_graphs), int(max_nodes),
+                       int(max_edges), self.blocked_status(edge_index.device))
+        self._blocks[self._key(edge_index)] = b
+        while len(self._blocks) > self.capacity:
+            self._blocks.popitem(last=False)
+        return b
 
     @staticmethod
     def _key(t: Tensor, *extra) -> tuple:
@@ -238,12 +307,15 @@ class StructureCache:
     def clear(self) -> None:
         self._graphs.clear()
         self._segments.clear()
+        self._blocks.clear()
 
     def graph(self, edge_index: Tensor, num_src: int, num_dst: int, add_self_loops: bool = False) -> GraphStructure:
         key = self._key(edge_index, int(num_src), int(num_dst), bool(add_self_loops))
         st = self._graphs.get(key)
         if st is None:
             st = GraphStructure(edge_index, num_src, num_dst, add_self_loops)
+            if not add_self_loops:
+                st._blocks = self._blocks.get(self._key(edge_index))
             if add_self_loops and self._known_loop_free(edge_index):
                 st._plain = self.graph(edge_index, num_src, num_dst, False)
             self._graphs[key] = st

@@ -28,7 +28,7 @@ from torch.nn.parameter import UninitializedParameter
 
 from . import hetero, models, ops
 from .data import Batch
-from .structure import capture_scope, structure_cache, structure_hints
+from .structure import capture_scope, edge_blocks_from_batch, structure_cache, structure_hints
 
 
 # ---------------------------------------------------------------------------------------------
@@ -167,6 +167,9 @@ class GraphHSCNStep:
         counts = host_batch.ptr[1:] - host_batch.ptr[:-1]
         self.hints = dict(num_graphs=self.B, batch_sorted=1, max_nodes_per_graph=int(counts.max()),
                           no_self_loops=int(not bool((host_batch.edge_index[0] == host_batch.edge_index[1]).any())))
+        # collate-time fact: edges are graph-major and block diagonal -> per-graph CSR kernel (K1 fast path)
+        blocks = edge_blocks_from_batch(host_batch.edge_index, host_batch.batch, self.B)
+        self.max_edges_per_graph = blocks[1] if blocks is not None and os.environ.get("GHSCN_BLOCKED_CSR", "1") != "0" else 0
         # pinned host staging + static device buffers (inputs are re-copied every step in the e2e path)
         self.host = {k: host_batch[k].contiguous().pin_memory() if device.type == "cuda" else host_batch[k]
                      for k in ("x", "edge_index", "batch", "y")}
@@ -225,6 +228,12 @@ class GraphHSCNStep:
             self.hscn_opt = torch.optim.AdamW([self.hscn_grads.flatten_parameters()], **kw)
         structure_cache().clear()
 
+    def _register_blocks(self) -> None:
+        if self.max_edges_per_graph and self.device.type == "cuda":
+            seg = structure_cache().segments(self.dev["batch"], self.B)
+            structure_cache().register_blocks(self.dev["edge_index"], seg.ptr, self.B,
+                                              self.hints["max_nodes_per_graph"], self.max_edges_per_graph)
+
     def _cast(self, x: Tensor) -> Tensor:
         if x.dtype == torch.int64 and x.is_cuda:
             return ops.cast_i64_f32(x)
@@ -233,6 +242,7 @@ class GraphHSCNStep:
     # -- the three stages; `sync_grads` hooks the data-parallel all-reduce in between ------------------
     def stage_scn_backward(self):
         self.scn_grads.zero()
+        self._register_blocks()
         x_f = self._cast(self.dev["x"])
         ei, ew, _, mc, ol = self._forward_scn(x_f)
         (mc + ol).backward()
@@ -273,6 +283,7 @@ class GraphHSCNStep:
         N = self.dev["x"].size(0)
         x_f = self._cast(self.dev["x"])
         structure_cache().segments(self.dev["batch"], self.B)
+        self._register_blocks()
         plain = structure_cache().graph(self.dev["edge_index"], N, N, False)
         plain.by_dst, plain.by_src                               # built here, read by both streams
         side.wait_stream(main)

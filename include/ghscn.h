@@ -71,6 +71,21 @@ GHSCN_API int ghscn_csr_add_loops(const int32_t* rowptr, const int32_t* col, con
                                   int64_t num_edges, int32_t* rowptr2, int32_t* col2, int32_t* perm2,
                                   ghscn_stream_t stream);
 
+/* K1 fast path for collated mini-batches (edges are stored graph-major and never leave their graph).
+ * One CTA per graph builds BOTH orientations of the plain (loop-free handling: none added, none dropped) CSR in
+ * shared memory; results are bit-identical to ghscn_csr_build(dst, src, ...) and ghscn_csr_build(src, dst, ...).
+ *   ptr [num_graphs+1]   node ranges of the graphs (ghscn_batch_to_ptr)
+ *   max_*_per_graph      upper bounds the caller knows from collate time (they size the shared memory)
+ *   status               device int32, caller-zeroed: bit 0 = a bound was exceeded, bit 1 = an edge leaves its
+ *                        graph; outputs are unspecified when it is non-zero
+ * GHSCN_E_UNSUPPORTED when the per-graph working set exceeds 200 KB of shared memory (use ghscn_csr_build). */
+GHSCN_API size_t ghscn_csr_blocked_smem_bytes(int64_t max_nodes_per_graph, int64_t max_edges_per_graph);
+GHSCN_API int ghscn_csr_build_blocked(const int64_t* src, const int64_t* dst, int64_t num_edges, const int32_t* ptr,
+                                      int64_t num_graphs, int64_t num_nodes, int64_t max_nodes_per_graph,
+                                      int64_t max_edges_per_graph, int32_t* rowptr_dst, int32_t* col_dst,
+                                      int32_t* perm_dst, int32_t* rowptr_src, int32_t* col_src, int32_t* perm_src,
+                                      int32_t* status, ghscn_stream_t stream);
+
 /* sorted `batch` vector -> ptr[num_graphs+1] (PyG collate convention). */
 GHSCN_API int ghscn_batch_to_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs, int32_t* ptr,
                                  ghscn_stream_t stream);
@@ -160,6 +175,9 @@ GHSCN_API int ghscn_gemm3x_supported(int64_t m, int64_t n_out, int64_t k);
 GHSCN_API size_t ghscn_gemm3x_b_image_bytes(int64_t n_out, int64_t k);
 GHSCN_API int ghscn_gemm3x_prep_b(const float* w, int64_t ldw, int64_t n_out, int64_t k, int32_t transpose,
                                   void* image, ghscn_stream_t stream);
+/* debug builds only (-DGHSCN_GEMM3X_TRACE): device buffer (>= 1024 int64) receiving clock() stamps of the pipeline
+ * events of CTA (0,0) of the tcgen05 kernels; NULL switches it off.  GHSCN_E_UNSUPPORTED in normal builds. */
+GHSCN_API int ghscn_gemm3x_set_trace(void* device_buffer);
 GHSCN_API int ghscn_gemm3x(const float* a, int64_t lda, int64_t m, int64_t k, const void* b_image, int64_t n_out,
                            const float* bias, int32_t relu, float* c, int64_t ldc, ghscn_stream_t stream);
 

@@ -256,3 +256,19 @@ def test_gemm3x_shape_rules_without_a_gpu(built_lib):
     # null pointers are rejected before anything is launched
     assert L._fns["ghscn_gemm3x"](None, 300, 128, 300, None, 300, None, 0, None, 300, None) == -1
     assert L._fns["ghscn_gemm3x_tn"](None, 300, None, 300, 128, 300, 300, None, None, 0, None) == -1
+
+
+def test_edge_blocks_from_batch_accepts_only_collated_edge_lists():
+    """Host-side gate of the K1 fast path: graph-major, block-diagonal edge lists only."""
+    import torch
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.structure import edge_blocks_from_batch
+    b = synthetic.peptides_batch(6, seed=3)
+    counts = b.ptr[1:] - b.ptr[:-1]
+    got = edge_blocks_from_batch(b.edge_index, b.batch, 6)
+    assert got == (int(counts.max()), int(torch.bincount(b.batch[b.edge_index[0]], minlength=6).max()))
+    crossing = b.edge_index.clone()
+    crossing[1, 0] = int(b.ptr[3])                      # first edge now ends in graph 3
+    assert edge_blocks_from_batch(crossing, b.batch, 6) is None
+    assert edge_blocks_from_batch(b.edge_index.flip(1), b.batch, 6) is None      # graph-minor order
+    assert edge_blocks_from_batch(b.edge_index[:, :0], b.batch, 6) is None

@@ -145,3 +145,75 @@ def test_skinny_linear_fwd_bwd(cuda, k, m):
     gx, gw, gb = torch.autograd.grad(ref, (x, w, b), gy.double())
     for name, a, r in [("y", y, ref), ("dx", dx, gx), ("dw", dw, gw), ("db", db, gb)]:
         assert rel_err(a, r.float()) < 2e-6, name
+
+
+def _collated(sizes, degree, gen, shuffle_within=True):
+    """Collated edge list (graph-major, block diagonal) of random graphs with the given node counts."""
+    parts, batch, off = [], [], 0
+    for g, n in enumerate(sizes):
+        e = int(n * degree)
+        if n > 0 and e > 0:
+            ei = torch.randint(0, n, (2, e), generator=gen)
+            if not shuffle_within:
+                ei = ei[:, torch.argsort(ei[1], stable=True)]
+            parts.append(ei + off)
+        batch += [g] * n
+        off += n
+    return torch.cat(parts, 1), torch.tensor(batch, dtype=torch.long)
+
+
+@pytest.mark.parametrize("case", ["peptides", "ragged", "dense_rows", "voc"])
+def test_blocked_csr_equals_radix_sort(cuda, case):
+    """K1 fast path (one CTA per graph, both orientations) == two stable radix sorts, bit for bit."""
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.structure import StructureCache, build_csr, edge_blocks_from_batch
+    g = torch.Generator().manual_seed(11)
+    if case == "peptides":
+        b = synthetic.peptides_batch(128, seed=5)
+        ei, batch = b.edge_index, b.batch
+    elif case == "ragged":          # empty graphs, single nodes, edge-free graphs, duplicates and self loops
+        ei, batch = _collated([5, 0, 1, 300, 0, 2, 64, 1, 444, 3], 2.5, g)
+        keep = (batch[ei[0]] != 6)                       # graph 6 keeps its nodes but loses every edge
+        ei = ei[:, keep]
+    elif case == "dense_rows":      # stars: one destination collects hundreds of edges (rank loop, long rows)
+        ei, batch = _collated([200, 333, 50], 6.0, g)
+        ei[1, ei[1] < 200] = 7
+    else:
+        ei, batch = _collated([int(v) for v in torch.randint(395, 501, (32,), generator=g)], 5.66, g)
+    B = int(batch.max()) + 1
+    N = batch.numel()
+    blocks = edge_blocks_from_batch(ei, batch, B)
+    assert blocks is not None
+    ei_d, batch_d = ei.to(cuda), batch.to(cuda)
+    cache = StructureCache()
+    seg = cache.segments(batch_d, B)
+    cache.register_blocks(ei_d, seg.ptr, B, blocks[0], blocks[1])
+    st = cache.graph(ei_d, N, N, False)
+    assert st._blocks is not None
+    _same(st.by_dst, build_csr(ei_d[1], ei_d[0], N, False))
+    _same(st.by_src, build_csr(ei_d[0], ei_d[1], N, False))
+    assert int(cache.blocked_status(cuda)) == 0
+    assert int(st.by_dst.rowptr[-1]) == ei.size(1)
+
+
+def test_blocked_csr_reports_broken_promises(cuda):
+    from graph_hscn_b200.structure import StructureCache, edge_blocks_from_batch
+    g = torch.Generator().manual_seed(12)
+    ei, batch = _collated([40, 50, 60], 3.0, g)
+    bad = ei.clone()
+    bad[1, 5] = 100                                       # an edge of graph 0 pointing into graph 2
+    assert edge_blocks_from_batch(bad, batch, 3) is None  # the host-side check refuses it
+    assert edge_blocks_from_batch(ei.flip(1), batch, 3) is None          # not graph-major
+    cache = StructureCache()
+    seg = cache.segments(batch.to(cuda), 3)
+    cache.blocked_status(cuda).zero_()
+    bad_d = bad.to(cuda)
+    cache.register_blocks(bad_d, seg.ptr, 3, 60, 180)                    # a false promise: the kernel flags it
+    cache.graph(bad_d, 150, 150, False).by_dst
+    assert int(cache.blocked_status(cuda)) & 2
+    cache.blocked_status(cuda).zero_()
+    ok = ei.to(cuda)
+    cache.register_blocks(ok, seg.ptr, 3, 60, 10)                        # bound too small
+    cache.graph(ok, 150, 150, False).by_dst
+    assert int(cache.blocked_status(cuda)) & 1
+    cache.blocked_status(cuda).zero_()
