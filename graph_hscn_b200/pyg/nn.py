@@ -241,6 +241,7 @@ class GATConv(MessagePassing):
 
 
 PARALLEL_BRANCHES = os.environ.get("GHSCN_PARALLEL_BRANCHES", "1") != "0"
+PARALLEL_RELATIONS = os.environ.get("GHSCN_PARALLEL_RELATIONS", "1") != "0"
 _SIDE_STREAMS: Dict[Tuple[str, int], List["torch.cuda.Stream"]] = {}
 
 
@@ -290,13 +291,34 @@ class HeteroConv(nn.Module):
             for i, dst in enumerate(dsts[1:]):
                 sides[i].wait_stream(main)
                 streams[dst] = sides[i]
+        # Relations that share a destination type (v->v and l->v) are independent up to the final sum: the first one
+        # runs on the destination's stream, every further one on a stream of its own that waits for the caller's
+        # stream and for the destination's stream as they stand now (its inputs), and is joined before the sum.
+        rel_streams: Dict[Tuple[str, str, str], "torch.cuda.Stream"] = {}
+        joins: Dict[str, List["torch.cuda.Stream"]] = defaultdict(list)
+        if streams is not None:
+            extra = len(dsts) - 1
+            for edge_type in edge_index_dict:
+                if "__".join(edge_type) not in self.convs:
+                    continue
+                dst = edge_type[2]
+                if not PARALLEL_RELATIONS or all(t[2] != dst for t in rel_streams):
+                    rel_streams[edge_type] = streams[dst]
+                    continue
+                r = _side_streams(main.device, extra + 1)[extra]
+                extra += 1
+                r.wait_stream(main)
+                if streams[dst] is not main:
+                    r.wait_stream(streams[dst])
+                rel_streams[edge_type] = r
+                joins[dst].append(r)
         for edge_type, edge_index in edge_index_dict.items():
             src, _, dst = edge_type
             key = "__".join(edge_type)
             if key not in self.convs:
                 continue
             conv = self.convs[key]
-            with torch.cuda.stream(streams[dst]) if streams is not None else contextlib.nullcontext():
+            with torch.cuda.stream(rel_streams[edge_type]) if streams is not None else contextlib.nullcontext():
                 if src == dst:
                     out = conv(x_dict[src], edge_index)
                 else:
@@ -305,6 +327,8 @@ class HeteroConv(nn.Module):
         result: Dict[str, Tensor] = {}
         for key, xs in outs.items():
             with torch.cuda.stream(streams[key]) if streams is not None else contextlib.nullcontext():
+                for r in joins[key]:
+                    streams[key].wait_stream(r)
                 result[key] = self._aggregate(xs)
         self.last_streams = streams
         if streams is not None and not self.defer_join:
