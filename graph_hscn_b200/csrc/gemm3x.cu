@@ -248,18 +248,16 @@ __host__ __device__ inline Halves make_halves(int n_out) {
 //   warp 1            MMA issuer, convergent (owns TMEM): per K = 8 step  cross += a_lo.b_hi, cross += a_hi.b_lo,
 //                     main[chunk & 1] += a_hi.b_hi; commits the stage barriers, then the accumulator barrier
 //   warps 2..7        A producers, each owning whole K chunks: 128-bit global loads of the chunk (all in flight) ->
-//                     hi/lo split -> swizzled smem (2-stage A ring) -> fence.proxy.async -> mbarrier arrive
-//   warps 8..11       epilogue (own TMEM lane quadrant = warp & 3): tcgen05.ld of the three accumulators -> fp32 sum
-//                     -> bias / ReLU -> per-warp padded staging tile -> coalesced 128-bit global stores; the stores of
-//                     half h overlap the main loop of half h + 1
+//                     hi/lo split -> swizzled smem (3-stage A ring) -> fence.proxy.async -> mbarrier arrive
+//   warps 8..11       epilogue (own TMEM lane quadrant = warp & 3): tcgen05.ld of 32 columns of the three accumulators
+//                     per round -> fp32 sum -> bias / ReLU -> 128-bit global stores (one full line per lane and round);
+//                     the stores of half h overlap the main loop of half h + 1
 // =====================================================================================================================
 constexpr int kChunkK = 32;
 constexpr int kABytes = kTileM * kChunkK * 4;               // one part (hi or lo) of an A stage: 16 KB
-constexpr int kAStages = 2, kBStages = 3;
+constexpr int kAStages = 3, kBStages = 3;
 constexpr int kBStageBytes = 2 * kHalfMax * kChunkK * 4;    // hi block + lo block: 40 KB
-constexpr int kSubCols = 64;                                // epilogue drains 64 columns at a time
-constexpr int kStageRow = (kSubCols + 4) * 4;               // padded staging row: 272 B (conflict-free float4 stores)
-constexpr int kNnSmem = kAStages * 2 * kABytes + kBStages * kBStageBytes + kTileM * kStageRow + 1024;
+constexpr int kNnSmem = kAStages * 2 * kABytes + kBStages * kBStageBytes + 1024;
 constexpr int kNnProducerWarps = 6;
 constexpr int kNnThreads = 32 * (2 + kNnProducerWarps + 4);
 static_assert(kNnSmem <= kSmemLimit - 1024, "gemm3x shared memory budget");
@@ -331,7 +329,6 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
   const uint32_t smem_base = (smem_addr(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_addr(smem_raw));
   const uint32_t a_ring = smem_base, b_ring = a_ring + kAStages * 2 * kABytes;
-  const uint32_t staging = b_ring + kBStages * kBStageBytes;
   const int m0 = blockIdx.x * kTileM;
   const int kchunks = plan.kchunks, nh = plan.hv.count;
   const int total_chunks = nh * kchunks;
@@ -450,58 +447,73 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
     }
   } else {
     // ===== epilogue (warps 8..11) =====
+    // Each lane owns one tile row (= TMEM lane).  Per round: the tcgen05.ld of 32 columns of all three accumulators are
+    // issued together and waited for once (one ld + wait round trip costs ~300 cycles whatever its width), summed in
+    // fp32, and written straight to global memory: 32 columns are one full 128-byte line per lane.  The accumulators
+    // are handed back to the MMA warp right after the last wait, before the last stores.
     const int quad = warp & 3;                                  // TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;                           // tile row == TMEM lane
+    const int grow = m0 + quad * 32 + lane;                     // tile row == TMEM lane
     const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
-    unsigned char* swarp = smem_gen + (staging - smem_base) + (size_t)quad * 32 * kStageRow;   // this warp's 32 rows
-    unsigned char* srow = swarp + (size_t)lane * kStageRow;
     const bool use_main1 = kchunks > 1;
-    const int hl = lane & 15, rsel = lane >> 4;                 // store phase: half-warp per row, 16 float4 lanes
+    float* crow = c + (int64_t)grow * n_out;
     for (int h = 0; h < nh; ++h) {
       if (quad == 0) GHSCN_TR(400 + 4 * h);
       bar_wait(smem_addr(&acc_full), (uint32_t)h & 1u);
       if (quad == 0) GHSCN_TR(401 + 4 * h);
       tc_fence_after();
       const int hpad = plan.hv.pad[h], hvalid = plan.hv.valid[h], hcol = plan.hv.col[h];
-      for (int c0 = 0; c0 < hpad; c0 += kSubCols) {
-        const int ncols = min(kSubCols, hpad - c0);
-        for (int cc = 0; cc < ncols; cc += 16) {
-          float v[16];
-          load_sum16(tbase, (uint32_t)(c0 + cc), use_main1, v);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int lc = c0 + cc + 4 * q;                     // column inside the half
-            if (lc < hvalid) {
-              float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-              if (bias != nullptr) {
-                const float4 b = ldg_f4(bias + hcol + lc);
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-              }
-              if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              *reinterpret_cast<float4*>(srow + (cc + 4 * q) * 4) = o;
-            }
-          }
+      for (int c0 = 0; c0 < hpad; c0 += 32) {
+        const bool second = c0 + 16 < hpad;
+        uint32_t a0[16], a1[16], ac[16], b0[16], b1[16], bc[16];
+        tmem_ld16_nowait(tbase + kColMain0 + (uint32_t)c0, a0);
+        tmem_ld16_nowait(tbase + kColCross + (uint32_t)c0, ac);
+        if (use_main1) tmem_ld16_nowait(tbase + kColMain1 + (uint32_t)c0, a1);
+        if (second) {
+          tmem_ld16_nowait(tbase + kColMain0 + (uint32_t)(c0 + 16), b0);
+          tmem_ld16_nowait(tbase + kColCross + (uint32_t)(c0 + 16), bc);
+          if (use_main1) tmem_ld16_nowait(tbase + kColMain1 + (uint32_t)(c0 + 16), b1);
         }
-        if (c0 + kSubCols >= hpad) {                            // accumulators fully read: release them to the MMA warp
+        tmem_ld_wait(a0);
+        tmem_ld_wait(ac);
+        if (use_main1) tmem_ld_wait(a1);
+        if (second) {
+          tmem_ld_wait(b0);
+          tmem_ld_wait(bc);
+          if (use_main1) tmem_ld_wait(b1);
+        }
+        if (c0 + 32 >= hpad) {                                  // accumulators fully read: release them to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) bar_arrive(smem_addr(&acc_empty));
           if (quad == 0) GHSCN_TR(402 + 4 * h);
         }
-        __syncwarp();                                           // staging rows of this warp are complete
-        // coalesced 128-bit stores, two rows (up to 256 contiguous bytes each) per instruction.  Per-row bulk
-        // stores were measured at ~27 cycles per request per SM and dropped.
-        const int nf4 = min(ncols, hvalid - c0) / 4;            // float4 per row segment (<= 16)
-        if (hl < nf4) {
-#pragma unroll 4
-          for (int r = rsel; r < 32; r += 2) {
-            const int grow = m0 + quad * 32 + r;
-            if (grow < m_rows)
-              *reinterpret_cast<float4*>(c + (int64_t)grow * n_out + hcol + c0 + hl * 4) =
-                  *reinterpret_cast<const float4*>(swarp + (size_t)r * kStageRow + hl * 16);
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          if (part == 1 && !second) break;
+          const uint32_t* pm0 = part ? b0 : a0;
+          const uint32_t* pm1 = part ? b1 : a1;
+          const uint32_t* pcr = part ? bc : ac;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int lc = c0 + 16 * part + 4 * q;              // column inside the half
+            if (lc < hvalid) {
+              float v[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float t = __uint_as_float(pm0[4 * q + i]);
+                if (use_main1) t += __uint_as_float(pm1[4 * q + i]);
+                v[i] = t + __uint_as_float(pcr[4 * q + i]);
+              }
+              float4 o = make_float4(v[0], v[1], v[2], v[3]);
+              if (bias != nullptr) {
+                const float4 b = ldg_f4(bias + hcol + lc);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              if (grow < m_rows) *reinterpret_cast<float4*>(crow + hcol + lc) = o;
+            }
           }
         }
-        __syncwarp();                                           // reads done before the next sub-tile overwrites
       }
     }
   }
