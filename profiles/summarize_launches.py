@@ -1,8 +1,8 @@
 """Summarises an `ncu --metrics gpu__time_duration.sum --csv` launch list into per-step kernel shares.
 
 usage: python profiles/summarize_launches.py gpurun_out/launches.csv [out.txt]
-A step is delimited by every second ghscn::cast_i64_f32_kernel launch (the step casts the raw atom
-features twice: SCN input and HSCN local features).  Times under ncu are cold-cache and serialised:
+A step is delimited by consecutive ghscn::cast_i64_f32_kernel launches (the step casts the raw atom
+features once, as its first kernel; profiles up to r1f came from a version that cast twice per step).  Times under ncu are cold-cache and serialised:
 compare SHARES, not absolutes.
 """
 import collections
@@ -17,7 +17,7 @@ def main():
         rows = list(csv.DictReader(l for l in f if not l.startswith("==")))
     names = [r["Kernel Name"] for r in rows]
     starts = [i for i, n in enumerate(names) if "cast_i64_f32" in n]
-    s0, s1 = starts[-6], starts[-4]          # one full CUDA-graph replay from the timed region
+    s0, s1 = starts[-3], starts[-2]          # one full CUDA-graph replay from the timed region
     seg = rows[s0:s1]
     us = lambda r: float(r["Metric Value"].replace(",", "")) / 1000.0
     agg, cnt, tot = {}, collections.Counter(), 0.0
