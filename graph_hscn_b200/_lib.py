@@ -74,6 +74,7 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_virtual_edges": (I32, [P, P, P, P, I64, I64, I64, P, P, I64, P, P]),
     "ghscn_virtual_compact": (I32, [P, P, P, I64, I64, I64, P, P, P]),
     "ghscn_cast_i64_f32": (I32, [P, I64, P, P]),
+    "ghscn_scn_forward": (I32, [P, P, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, I32, P, P, P, P, P]),
 }
 
 

@@ -216,6 +216,27 @@ class _Linear3xTF32(torch.autograd.Function):
         return dx, dw, db
 
 
+def skinny_dx(dy: Tensor, weight: Tensor) -> Tensor:
+    """dx[n,k] = sum_m dy[n,m] W[m,k] for a tiny k (hand-written streaming kernel)."""
+    n, m = dy.shape
+    k = weight.size(1)
+    dx = torch.empty((n, k), dtype=torch.float32, device=dy.device)
+    lib().call("ghscn_skinny_linear_dx", _p(dy), m, _p(weight), n, k, m, _p(dx), k, _stream())
+    return dx
+
+
+def skinny_dw(dy: Tensor, x: Tensor) -> Tensor:
+    """dW[m,k] = sum_n dy[n,m] x[n,k] (two-stage fixed-order reduction: deterministic)."""
+    n, m = dy.shape
+    k = x.size(1)
+    L = lib()
+    dw = torch.empty((m, k), dtype=torch.float32, device=dy.device)
+    ws_bytes = L.query("ghscn_skinny_dw_workspace_bytes", n, k, m)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dy.device)
+    L.call("ghscn_skinny_linear_dw", _p(dy), m, _p(x), x.stride(0), n, k, m, _p(dw), _p(ws), ws_bytes, _stream())
+    return dw
+
+
 class _LinearSkinny(torch.autograd.Function):
     """y = x W^T + b for a tiny input width (<= 32) and many rows: hand-written streaming kernels (csrc/skinny.cu)."""
 

@@ -11,6 +11,7 @@ reference's quirks.  tests/golden pins mirror == u
 """
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace
 from typing import Callable, Dict, List, Optional, Sequence
 
@@ -88,6 +89,20 @@ class SCN(nn.Module):
             self.mlp.append(o.Linear(width, units))
             self.mlp.append(ACTIVATIONS[mlp_act.lower()])
         self.mlp.append(o.Linear(width, num_clusters))
+        # one GraphConv + activation + one Linear is what main.py:101-106 builds: operator sets that offer it run
+        # that chain as one fused launch (same values within fp32 rounding; tests/test_gpu_parity.py)
+        self._fusable = (len(mp_units) == 1 and len(mlp_units) == 0 and mp_act.lower() in ("elu", "relu", "tanh", "identity")
+                         and hasattr(o, "scn_logits_fused"))
+        self._act_name = mp_act.lower()
+        self.fuse = os.environ.get("GHSCN_FUSED_SCN", "1") != "0"
+
+    def logits(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor]) -> Tensor:
+        """s = mlp(mp(x, edge_index, edge_weight))  (model/hscn.py:57-60)."""
+        if self._fusable and self.fuse:
+            s = self.ops.scn_logits_fused(x, edge_index, edge_weight, self.mp.module_0, self._act_name, self.mlp[0])
+            if s is not None:
+                return s
+        return self.mlp(self.mp(x, edge_index, edge_weight))
 
     def forward(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor]):
         """One graph per call, as train_clustering.py:44-47 drives it."""
@@ -101,8 +116,12 @@ class SCN(nn.Module):
     def forward_batched(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor], batch: Tensor):
         """Throughput form: the whole `batch`/`ptr` mini-batch in one launch (losses are batch means)."""
         o = self.ops
-        h = self.mp(x, edge_index, edge_weight)
-        s = self.mlp(h)
+        if self._fusable and self.fuse:
+            s = self.logits(x, edge_index, edge_weight)
+            h = x                       # the pooled features are not computed (want_out=False): only the shape matters
+        else:
+            h = self.mp(x, edge_index, edge_weight)
+            s = self.mlp(h)
         _, _, mc_loss, o_loss = o.mincut_pool_ragged(h, edge_index, s, batch, want_out=False, want_adj=False)
         return s, mc_loss, o_loss
 

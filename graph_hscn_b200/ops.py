@@ -9,6 +9,8 @@ from __future__ import annotations
 
 from typing import List, Optional, Tuple
 
+import os
+
 import torch
 from torch import Tensor
 
@@ -17,6 +19,20 @@ from .structure import _p, _stream
 
 _custom_op = torch.library.custom_op
 _STATS_STRIDE = 8
+
+
+PARALLEL_BACKWARD = os.environ.get("GHSCN_PARALLEL_BACKWARD", "1") != "0"
+_AUX_STREAMS: dict = {}
+
+
+def _aux_stream(device: torch.device) -> "torch.cuda.Stream":
+    """One auxiliary stream per (device, current stream): independent side work inside a backward function."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    st = _AUX_STREAMS.get(key)
+    if st is None:
+        st = _AUX_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
 
 
 def _rowmajor(x: Tensor) -> Tensor:
@@ -110,16 +126,86 @@ def _spmm_backward(ctx, dy):
         dy = torch.ops.aten.threshold_backward(dy, y, 0.0)      # dy * (y > 0), one vectorised pass
     dy = dy.contiguous()
     dx = dw = dbias = None
+    want_bias = ctx.has_bias and ctx.needs_input_grad[7]
+    # The bias gradient (a column sum of dy) and the transposed aggregation both only read dy: the column sum runs on
+    # an auxiliary stream, forked here and joined before returning (graph-capturable; same kernels, same results).
+    side = main = None
+    if want_bias and ctx.needs_input_grad[6] and PARALLEL_BACKWARD and dy.is_cuda:
+        main = torch.cuda.current_stream()
+        side = _aux_stream(dy.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            dbias = colsum(dy)
     if ctx.needs_input_grad[6]:
         dx = spmm_raw(rowptr_t, col_t, w_t, dy, None, rowptr_t.numel() - 1, False)
     if ctx.w_needs_grad:
         dw = spmm_edge_grad(rowptr, col, x, dy, col.numel())
-    if ctx.has_bias and ctx.needs_input_grad[7]:
+    if side is not None:
+        main.wait_stream(side)
+    elif want_bias:
         dbias = colsum(dy)
     return None, None, dw, None, None, None, dx, dbias, None
 
 
 torch.library.register_autograd("ghscn::spmm", _spmm_backward, setup_context=_spmm_setup)
+
+
+# =============================================================================================
+# fused SCN node pipeline: GraphConv aggregation + lin_rel + lin_root + activation + cluster Linear
+# =============================================================================================
+SCN_ACTS = {"identity": 0, "elu": 1, "relu": 2, "tanh": 3}
+SCN_LIMITS = (16, 32, 32)          # f_in, units, clusters handled by ghscn_scn_forward
+
+
+class ScnNodeForward(torch.autograd.Function):
+    """logits = W_out act(W_rel (A_w x) + b_rel + W_root x) + b_out in ONE launch (csrc/scn.cu); `x` and the structure
+    carry no gradient (raw atom features, gcn_norm weights: train/train_clustering.py:37-47).  The backward is the
+    chain of the separate operators' backwards, on the saved agg / pre / h."""
+
+    @staticmethod
+    def forward(ctx, x, rowptr, col, w, w_rel, b_rel, w_root, w_out, b_out, act: int):
+        n, f = x.shape
+        u, k = w_rel.size(0), w_out.size(0)
+        dev = x.device
+        need = any(ctx.needs_input_grad[4:9])          # (grad mode is off inside Function.forward: ask the context)
+        agg = torch.empty((n, f), dtype=torch.float32, device=dev) if need else None
+        pre = torch.empty((n, u), dtype=torch.float32, device=dev) if need else None
+        h = torch.empty((n, u), dtype=torch.float32, device=dev) if need else None
+        logits = torch.empty((n, k), dtype=torch.float32, device=dev)
+        lib().call("ghscn_scn_forward", _p(rowptr), _p(col), _p(w), _p(x), x.stride(0), n, f, u, k,
+                   _p(w_rel), _p(b_rel), _p(w_root), _p(w_out), _p(b_out), int(act),
+                   _p(agg), _p(pre), _p(h), _p(logits), _stream())
+        ctx.save_for_backward(x, agg, pre, h, w_out)
+        ctx.act = int(act)
+        ctx.has = (b_rel is not None, b_out is not None)
+        return logits
+
+    @staticmethod
+    def backward(ctx, ds):
+        from .gemm import skinny_dw, skinny_dx
+        x, agg, pre, h, w_out = ctx.saved_tensors
+        ds = ds.contiguous()
+        d_wout = skinny_dw(ds, h)
+        d_bout = colsum(ds) if ctx.has[1] else None
+        dh = skinny_dx(ds, w_out.contiguous())
+        if ctx.act == 1:
+            dpre = torch.ops.aten.elu_backward(dh, 1.0, 1.0, 1.0, False, pre)
+        elif ctx.act == 2:
+            dpre = torch.ops.aten.threshold_backward(dh, pre, 0.0)
+        elif ctx.act == 3:
+            dpre = dh * (1.0 - h * h)
+        else:
+            dpre = dh
+        d_wrel = skinny_dw(dpre, agg)
+        d_brel = colsum(dpre) if ctx.has[0] else None
+        d_wroot = skinny_dw(dpre, x)
+        return None, None, None, None, d_wrel, d_brel, d_wroot, d_wout, d_bout, None
+
+
+def scn_node_forward(x: Tensor, rowptr: Tensor, col: Tensor, w: Optional[Tensor], w_rel: Tensor,
+                     b_rel: Optional[Tensor], w_root: Tensor, w_out: Tensor, b_out: Optional[Tensor], act: str) -> Tensor:
+    return ScnNodeForward.apply(x, rowptr, col, w, w_rel.contiguous(), b_rel, w_root.contiguous(),
+                                w_out.contiguous(), b_out, SCN_ACTS[act])
 
 
 # =============================================================================================

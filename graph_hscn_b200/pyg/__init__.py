@@ -14,7 +14,8 @@ import types
 from ..data import Batch, Data, DataLoader, HeteroBatch, HeteroData
 from . import functional, nn
 from .functional import (SparseAdj, dense_mincut_pool, gcn_norm, global_add_pool, global_mean_pool,
-                         mincut_pool_ragged, scatter, scatter_add, scatter_mean, scatter_sum, to_dense_adj)
+                         mincut_pool_ragged, scatter, scatter_add, scatter_mean, scatter_sum, scn_logits_fused,
+                         to_dense_adj)
 from .nn import (GATConv, GCNConv, GINConv, GraphConv, HeteroConv, Linear, MessagePassing, Sequential)
 
 __all__ = ["GATConv", "GCNConv", "GINConv", "GraphConv", "HeteroConv", "Linear", "MessagePassing", "Sequential",
@@ -28,7 +29,8 @@ def namespace() -> types.SimpleNamespace:
         name="ghscn-b200", fused_relu=True, GCNConv=GCNConv, GATConv=GATConv, GINConv=GINConv, GraphConv=GraphConv,
         HeteroConv=HeteroConv, Linear=Linear, Sequential=Sequential, MessagePassing=MessagePassing,
         dense_mincut_pool=dense_mincut_pool, mincut_pool_ragged=mincut_pool_ragged, to_dense_adj=to_dense_adj,
-        global_mean_pool=global_mean_pool, scatter_mean=scatter_mean, gcn_norm=gcn_norm)
+        global_mean_pool=global_mean_pool, scatter_mean=scatter_mean, gcn_norm=gcn_norm,
+        scn_logits_fused=scn_logits_fused)
 
 
 def build_modules(ns: types.SimpleNamespace, data_mod=None) -> dict:

@@ -258,3 +258,27 @@ def scatter(src: Tensor, index: Tensor, dim: int = -1, out: Optional[Tensor] = N
     if reduce == "mean":
         return scatter_mean(src, index, dim, out, dim_size)
     raise NotImplementedError(f"scatter reduce={reduce!r} is not on the reference's path")
+
+
+def scn_logits_fused(x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor], conv, act: str, out_lin
+                     ) -> Optional[Tensor]:
+    """Cluster logits of SCN(mp_units=[U]) -- GraphConv `conv`, activation `act`, Linear `out_lin`
+    (model/hscn.py:30-45,57-60) -- in one launch (ghscn_scn_forward); None when the shape or dtype is outside the
+    fused kernel's range (the caller then runs the separate operators)."""
+    from .. import ops
+    from ..structure import structure_cache
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and act in ops.SCN_ACTS):
+        return None
+    if edge_weight is not None and edge_weight.requires_grad:
+        return None
+    f, u, k = x.size(1), conv.out_channels, out_lin.out_channels
+    if f > ops.SCN_LIMITS[0] or u > ops.SCN_LIMITS[1] or k > ops.SCN_LIMITS[2]:
+        return None
+    if conv.lin_rel.weight.size(1) != f or conv.lin_root.weight.size(1) != f or out_lin.weight.size(1) != u:
+        return None
+    st = structure_cache().graph(edge_index, x.size(0), x.size(0), False)
+    w, _, _ = st.weights(edge_weight, normalize=False, need_transpose=False)
+    d = st.by_dst
+    xs = x if x.stride(1) == 1 else x.contiguous()
+    return ops.scn_node_forward(xs, d.rowptr, d.col, w, conv.lin_rel.weight, conv.lin_rel.bias, conv.lin_root.weight,
+                                out_lin.weight, out_lin.bias, act)

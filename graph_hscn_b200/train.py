@@ -201,7 +201,7 @@ class GraphHSCNStep:
 
     def _assign(self, x_f: Tensor, ei: Tensor, ew: Tensor):
         with torch.no_grad():
-            s = self.scn.mlp(self.scn.mp(x_f, ei, ew))
+            s = self.scn.logits(x_f, ei, ew)
             clusters = hetero.assign_clusters(torch.softmax(s, dim=-1))
         return hetero.build_hetero_batch(self.dev["x"], self.dev["edge_index"], self.dev["batch"], clusters,
                                          self.cfg.num_clusters, y=self.dev["y"], padded=self.padded,

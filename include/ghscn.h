@@ -249,6 +249,19 @@ GHSCN_API int ghscn_gat_pool_bwd_src(const int32_t* rowptr_t, const int32_t* col
 GHSCN_API int ghscn_slot_map(const int32_t* perm, const int32_t* perm_t, int64_t nnz, int64_t num_items,
                              int32_t* scratch_pos, int32_t* map_t, ghscn_stream_t stream);
 
+/* ---- fused node pipeline of the spectral-clustering net ----------------------------------------
+ * Replaces, for SCN(mp_units=[U]) (model/hscn.py:30-45,57-60; main.py:101-106), the chain
+ * GraphConv.propagate -> lin_rel -> + lin_root -> activation -> Linear that the reference runs as six launches,
+ * once per training forward and once per cluster assignment (train/train_clustering.py:44,64-66):
+ *   agg = A_w x (rows of (rowptr, col) are destinations; w NULL = unit weights; slot order, unfused mul+add),
+ *   pre = W_rel agg + b_rel + W_root x,  h = act(pre) (0 identity, 1 ELU, 2 ReLU, 3 tanh),  logits = W_out h + b_out.
+ * agg [N,f_in], pre [N,units], h [N,units] are written for the backward when non-NULL; logits [N,clusters].
+ * GHSCN_E_UNSUPPORTED beyond f_in <= 16, units <= 32, clusters <= 32 (callers then run the separate operators). */
+GHSCN_API int ghscn_scn_forward(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, int64_t ldx,
+                                int64_t num_nodes, int64_t f_in, int64_t units, int64_t clusters, const float* w_rel,
+                                const float* b_rel, const float* w_root, const float* w_out, const float* b_out,
+                                int32_t act, float* agg, float* pre, float* h, float* logits, ghscn_stream_t stream);
+
 /* ---- K6: fused MinCUT pool, one CTA per graph --------------------------------------------------
  * Replaces to_dense_adj + dense_mincut_pool (model/hscn.py:61-63).  SURVEY 8a rows a4, a5,
  * Appendix A.6/A.7.  The adjacency is consumed as the batch CSR whose ROWS ARE edge_index[0]

@@ -429,6 +429,41 @@ def test_scn_per_graph_and_batched(cuda):
         assert_close(p2.grad, p1.grad, 20 * RTOL, f"SCN batched grad {n1}")
 
 
+@pytest.mark.parametrize("act,units,K", [("elu", 16, 10), ("relu", 32, 32), ("tanh", 8, 5), ("identity", 16, 10)])
+def test_scn_fused_node_pipeline(cuda, act, units, K):
+    """ghscn_scn_forward (GraphConv aggregation + lin_rel + lin_root + activation + cluster Linear in one launch)
+    against the separate operators of this package and against the CPU oracle, values and parameter gradients."""
+    from graph_hscn_b200 import models
+    o, p = _oracle(), _product()
+    ref, tst = _to_dev(lambda: models.SCN([units], act, 9, K, ops=o), lambda: models.SCN([units], act, 9, K, ops=p),
+                       cuda, lambda m, d: None)
+    assert tst._fusable and not ref._fusable
+    b = _peptide_batch(12, seed=33)
+    N = b.x.size(0)
+    g = torch.Generator().manual_seed(units)
+    up = torch.randn(N, K, generator=g)
+    ei_r, w_r = o.gcn_norm(b.edge_index, None, N, add_self_loops=True)
+    ei_t, w_t = p.gcn_norm(b.edge_index.to(cuda), None, N, add_self_loops=True)
+    x_t = b.x.float().to(cuda)
+    s_r = ref.logits(b.x.float(), ei_r, w_r)
+    (s_r * up).sum().backward()
+    got = {}
+    for fuse in (True, False):
+        tst.zero_grad(set_to_none=True)
+        tst.fuse = fuse
+        s_t = tst.logits(x_t, ei_t, w_t)
+        (s_t * up.to(cuda)).sum().backward()
+        got[fuse] = (s_t.detach().clone(), {n: q.grad.detach().clone() for n, q in tst.named_parameters()})
+    assert_close(got[True][0], got[False][0], 2e-6, "fused vs separate logits")
+    assert_close(got[True][0], s_r, RTOL, "fused logits vs oracle")
+    for n, q in ref.named_parameters():
+        assert_close(got[True][1][n], got[False][1][n], RTOL, f"fused vs separate grad {n}")
+        assert_close(got[True][1][n], q.grad, 10 * RTOL, f"fused grad {n} vs oracle")
+    with torch.no_grad():                                  # the assignment pass: nothing saved, same logits
+        tst.fuse = True
+        assert torch.equal(tst.logits(x_t, ei_t, w_t), got[True][0])
+
+
 def test_hscn_model_fwd_bwd(cuda):
     """Config #2 shape at reduced width: 3-relation HeteroConv (GAT l->v, GCN l->l, GCN v->v)."""
     from graph_hscn_b200 import hetero, models
