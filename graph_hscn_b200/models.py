@@ -113,8 +113,10 @@ class SCN(nn.Module):
         _, _, mc_loss, o_loss = o.dense_mincut_pool(h, adj, s)
         return torch.softmax(s, dim=-1), mc_loss, o_loss, adj
 
-    def forward_batched(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor], batch: Tensor):
-        """Throughput form: the whole `batch`/`ptr` mini-batch in one launch (losses are batch means)."""
+    def forward_batched(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor], batch: Tensor,
+                        losses_tensor: bool = False):
+        """Throughput form: the whole `batch`/`ptr` mini-batch in one launch (losses are batch means).
+        -> (s, mincut_loss, ortho_loss), or (s, losses[2]) with `losses_tensor` (CUDA operator set only)."""
         o = self.ops
         if self._fusable and self.fuse:
             s = self.logits(x, edge_index, edge_weight)
@@ -122,6 +124,9 @@ class SCN(nn.Module):
         else:
             h = self.mp(x, edge_index, edge_weight)
             s = self.mlp(h)
+        if losses_tensor:
+            _, _, both = o.mincut_pool_ragged(h, edge_index, s, batch, want_out=False, want_adj=False, losses_tensor=True)
+            return s, both
         _, _, mc_loss, o_loss = o.mincut_pool_ragged(h, edge_index, s, batch, want_out=False, want_adj=False)
         return s, mc_loss, o_loss
 

@@ -491,6 +491,7 @@ def _mincut_setup(ctx, inputs, output):
     out, out_adj, losses, s_soft, ss_raw, adj_raw, stats = output
     ctx.temp, ctx.max_nodes, ctx.want = temp, max_nodes, (want_out, want_adj)
     ctx.num_feat = x.size(1)
+    ctx.set_materialize_grads(False)       # unused outputs (s_soft, raw K x K blocks, stats) arrive as None, not as zero fills
     ctx.save_for_backward(s_soft, x, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, ss_raw, adj_raw, stats)
 
 

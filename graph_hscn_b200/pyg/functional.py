@@ -146,9 +146,11 @@ def _ptr_for(batch: Optional[Tensor], num_nodes: int, device) -> Tuple[Tensor, i
 
 def mincut_pool_ragged(x: Tensor, edge_index: Tensor, s: Tensor, batch: Optional[Tensor] = None,
                        edge_attr: Optional[Tensor] = None, temp: float = 1.0, want_out: bool = True,
-                       want_adj: bool = True) -> Tuple[Optional[Tensor], Optional[Tensor], Tensor, Tensor]:
+                       want_adj: bool = True, losses_tensor: bool = False):
     """Batched MinCUT pool on the ragged (`batch`/`ptr`) layout: one CTA per graph, no [B,n,n] tensor.
-    Equivalent to to_dense_batch + to_dense_adj(batch) + dense_mincut_pool(mask) in PyG."""
+    Equivalent to to_dense_batch + to_dense_adj(batch) + dense_mincut_pool(mask) in PyG.
+    -> (out, out_adj, mincut_loss, ortho_loss), or with `losses_tensor` (out, out_adj, losses[2]) so that a caller
+    that only adds the two losses does not pay for two select/scatter round trips in autograd."""
     _require_cuda(x, edge_index, s)
     N = s.size(0)
     ptr, B, max_nodes = _ptr_for(batch, N, s.device)
@@ -161,6 +163,8 @@ def mincut_pool_ragged(x: Tensor, edge_index: Tensor, s: Tensor, batch: Optional
     out, out_adj, losses, *_ = torch.ops.ghscn.mincut_pool(
         s, x, ptr, rows.rowptr, rows.col, val, cols.rowptr, cols.col, val_t, float(temp), int(max_nodes),
         bool(want_out), bool(want_adj))
+    if losses_tensor:
+        return (out if want_out else None), (out_adj if want_adj else None), losses
     return (out if want_out else None), (out_adj if want_adj else None), losses[0], losses[1]
 
 

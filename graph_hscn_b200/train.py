@@ -289,10 +289,10 @@ class GraphHSCNStep:
         side.wait_stream(main)
         with torch.cuda.stream(side):
             self.scn_grads.zero()
-            ei, ew, _, mc, ol = self._forward_scn(x_f)
-            (mc + ol).backward()
-            self.losses[0:1].copy_(mc.detach().view(1))
-            self.losses[1:2].copy_(ol.detach().view(1))
+            ei, ew = self.ns.gcn_norm(self.dev["edge_index"], None, N, add_self_loops=True)
+            _, both = self.scn.forward_batched(x_f, ei, ew, self.dev["batch"], losses_tensor=True)
+            both.sum().backward()                        # == (mincut + ortho).backward(), one reduction instead of
+            self.losses[0:2].copy_(both.detach())        # two select/scatter round trips
             self.scn_grads.all_reduce_mean(world)
             self.scn_opt.step()
             hb = self._assign(x_f, ei, ew)
