@@ -21,7 +21,7 @@ _custom_op = torch.library.custom_op
 _STATS_STRIDE = 8
 
 
-PARALLEL_BACKWARD = os.environ.get("GHSCN_PARALLEL_BACKWARD", "1") != "0"
+PARALLEL_AUX = os.environ.get("GHSCN_PARALLEL_AUX", "1") != "0"
 _AUX_STREAMS: dict = {}
 
 
@@ -130,7 +130,7 @@ def _spmm_backward(ctx, dy):
     # The bias gradient (a column sum of dy) and the transposed aggregation both only read dy: the column sum runs on
     # an auxiliary stream, forked here and joined before returning (graph-capturable; same kernels, same results).
     side = main = None
-    if want_bias and ctx.needs_input_grad[6] and PARALLEL_BACKWARD and dy.is_cuda:
+    if want_bias and ctx.needs_input_grad[6] and PARALLEL_AUX and dy.is_cuda:
         main = torch.cuda.current_stream()
         side = _aux_stream(dy.device)
         side.wait_stream(main)
@@ -375,12 +375,22 @@ class GatPoolInputWidth(torch.autograd.Function):
         V = rowptr.numel() - 1
         dev = x_src.device
         L, st = lib(), _stream()
-        a_src = row_dot(x_src, att_src @ w_src)
+        side = None
         if x_dst is not None:
             x_dst = _rowmajor(x_dst)
-            a_dst = row_dot(x_dst, att_dst @ w_dst)
+            if PARALLEL_AUX and x_src.is_cuda:      # the two score halves are independent: a_dst on an aux stream
+                main = torch.cuda.current_stream()
+                side = _aux_stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    a_dst = row_dot(x_dst, att_dst @ w_dst)
+            else:
+                a_dst = row_dot(x_dst, att_dst @ w_dst)
         else:
             a_dst = None
+        a_src = row_dot(x_src, att_src @ w_src)
+        if side is not None:
+            main.wait_stream(side)
         alpha = torch.zeros(col.numel(), dtype=torch.float32, device=dev)
         L.call("ghscn_gat_scores", _p(rowptr), _p(col), _p(a_src), _p(a_dst), float(slope), V, _p(alpha), st)
         Fin = x_src.size(1)

@@ -53,8 +53,11 @@ def gcn_norm(edge_index: Tensor, edge_weight: Optional[Tensor] = None, num_nodes
             new_index = edge_index
         w_coo = torch.empty(M, dtype=torch.float32, device=edge_index.device)
         w_coo[d.perm.long()] = w
-        if add_self_loops:   # layers called with (new_index, w_coo) reuse this CSR instead of sorting again
-            structure_cache().alias(new_index, st)
+        if add_self_loops:   # layers called with (new_index, w_coo) reuse this CSR instead of sorting again ...
+            view = structure_cache().alias(new_index, st)
+            # ... and its per-slot weights: w_coo gathered back to slot order is `w` itself
+            view._weights[((w_coo.data_ptr(), w_coo._version), False, False)] = dict(
+                w=w, w_t=None, dis=None, lw=None, ew=w_coo, unit=False)
         return new_index, w_coo
     nnz = int(d.rowptr[-1].item())
     # back to PyG's COO order: slot s holds item perm[s]; items = kept edges (in order) then loops
