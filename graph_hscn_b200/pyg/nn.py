@@ -182,15 +182,13 @@ class GINConv(MessagePassing):
 
 
 class GATConv(MessagePassing):
-    """Single-head graph attention.  The bipartite form GATConv((-1,-1), C,
-    add_self_loops=False) on ("local","to","virtual") is the reference's cluster pool."""
+    """Graph attention.  The bipartite single-head form GATConv((-1,-1), C, add_self_loops=False)
+    on ("local","to","virtual") is the reference's cluster pool; heads > 1 run head by head on the same kernels."""
 
     def __init__(self, in_channels: Union[int, Tuple[int, int]], out_channels: int, heads: int = 1,
                  concat: bool = True, negative_slope: float = 0.2, dropout: float = 0.0,
                  add_self_loops: bool = True, bias: bool = True, **kwargs):
         super().__init__()
-        if heads != 1:
-            raise NotImplementedError("heads > 1 is not on the reference's path (SURVEY 8f rank 3)")
         if dropout != 0.0:
             raise NotImplementedError("attention dropout is not on the reference's path")
         self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
@@ -233,11 +231,22 @@ class GATConv(MessagePassing):
         st = structure_cache().graph(edge_index, n_src, n_dst, self.add_self_loops)
         d, s = st.by_dst, st.by_src
         # attention scores from x (W^T att) and the pooled sum at the input width: no [N,F]x[F,H] projection
-        out = ops.GatPoolInputWidth.apply(
-            x_src, x_dst, self.lin_src.weight, self.lin_dst.weight if x_dst is not None else None,
-            self.att_src.view(-1), self.att_dst.view(-1), self.bias, float(self.negative_slope),
-            d.rowptr, d.col, s.rowptr, s.col, st.slot_map_t)
-        return out
+        if self.heads == 1:
+            return ops.GatPoolInputWidth.apply(
+                x_src, x_dst, self.lin_src.weight, self.lin_dst.weight if x_dst is not None else None,
+                self.att_src.view(-1), self.att_dst.view(-1), self.bias, float(self.negative_slope),
+                d.rowptr, d.col, s.rowptr, s.col, st.slot_map_t)
+        # heads > 1 (never built by the reference's configs): every head is the single-head operator
+        # on its own row block of lin_src / lin_dst and its own attention vectors, over the same structure
+        C, outs = self.out_channels, []
+        for h in range(self.heads):
+            rows = slice(h * C, (h + 1) * C)
+            outs.append(ops.GatPoolInputWidth.apply(
+                x_src, x_dst, self.lin_src.weight[rows], self.lin_dst.weight[rows] if x_dst is not None else None,
+                self.att_src[0, h], self.att_dst[0, h], None, float(self.negative_slope),
+                d.rowptr, d.col, s.rowptr, s.col, st.slot_map_t))
+        out = torch.cat(outs, dim=1) if self.concat else torch.stack(outs, dim=1).mean(dim=1)
+        return out + self.bias if self.bias is not None else out
 
 
 PARALLEL_BRANCHES = os.environ.get("GHSCN_PARALLEL_BRANCHES", "1") != "0"

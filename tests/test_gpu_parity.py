@@ -231,6 +231,38 @@ def test_gat_homogeneous_self_loops(cuda):
     assert_close(tst(x.to(cuda), ei.to(cuda)), ref(x, ei), RTOL, "GAT homogeneous")
 
 
+@pytest.mark.parametrize("concat", [True, False])
+def test_gat_multi_head_fwd_bwd(cuda, concat):
+    """heads = 3: bipartite and homogeneous forms against the oracle, values and gradients."""
+    o, p = _oracle(), _product()
+    g = torch.Generator().manual_seed(10)
+    N, V, fi, C, heads = 900, 60, 9, 16, 3
+    lv = torch.stack([torch.arange(N), torch.randint(0, V, (N,), generator=g)])
+    xl = torch.randn(N, fi, generator=g)
+    xv = torch.randn(V, fi, generator=g)
+    ref, tst = _to_dev(lambda: o.GATConv((-1, -1), C, heads=heads, concat=concat, add_self_loops=False),
+                       lambda: p.GATConv((-1, -1), C, heads=heads, concat=concat, add_self_loops=False), cuda,
+                       lambda m, d: m((xl.to(d), xv.to(d)), lv.to(d)))
+    xlr, xvr = xl.clone().requires_grad_(), xv.clone().requires_grad_()
+    xlt, xvt = xl.to(cuda).requires_grad_(), xv.to(cuda).requires_grad_()
+    yr, yt = ref((xlr, xvr), lv), tst((xlt, xvt), lv.to(cuda))
+    assert yt.shape == yr.shape == (V, heads * C if concat else C)
+    assert_close(yt, yr, RTOL, "multi-head GAT out")
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    yt.backward(gy.to(cuda))
+    assert_close(xlt.grad, xlr.grad, 2 * RTOL, "multi-head GAT dx_local")
+    assert_close(xvt.grad, xvr.grad, 2 * RTOL, "multi-head GAT dx_virtual")
+    for name in ["lin_src.weight", "lin_dst.weight", "att_src", "att_dst", "bias"]:
+        assert_close(dict(tst.named_parameters())[name].grad, dict(ref.named_parameters())[name].grad, 2 * RTOL,
+                     f"multi-head GAT d{name}")
+    ei = random_edge_index(300, 300, 1200, g)
+    x = torch.randn(300, fi, generator=g)
+    ref2, tst2 = _to_dev(lambda: o.GATConv(fi, C, heads=heads, concat=concat),
+                         lambda: p.GATConv(fi, C, heads=heads, concat=concat), cuda, lambda m, d: None)
+    assert_close(tst2(x.to(cuda), ei.to(cuda)), ref2(x, ei), RTOL, "multi-head GAT homogeneous")
+
+
 # ------------------------------------------------------------------------------------------- K6
 def _peptide_batch(num_graphs, seed):
     from graph_hscn_b200 import synthetic
