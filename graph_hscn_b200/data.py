@@ -249,7 +249,34 @@ class Batch(Data):
         out["batch"] = torch.repeat_interleave(torch.arange(len(data_list), dtype=torch.long), counts)
         out["ptr"] = ptr
         out["num_graphs"] = len(data_list)
+        # collate-time facts the device side would otherwise need a host sync for (structure.py): the largest graph,
+        # and -- edges are concatenated graph-major with node offsets added, so the batch is block diagonal -- the
+        # largest per-graph edge count, which sizes the per-graph CSR kernel (K1 fast path)
+        out["max_nodes_per_graph"] = int(counts.max()) if len(data_list) else 0
+        if len(data_list) and all("edge_index" in d for d in data_list):
+            out["max_edges_per_graph"] = max(int(d["edge_index"].size(1)) for d in data_list)
         return out
+
+    def to(self, device, non_blocking: bool = False) -> "Batch":
+        out = super().to(device, non_blocking=non_blocking)
+        out.register_structures()
+        return out
+
+    def register_structures(self) -> bool:
+        """Tell the structure cache what collate knows about this (CUDA-resident) batch: `ptr` (no sortedness
+        check, no `batch.max()` sync) and that the edge list is block diagonal and graph-major (K1 fast path).
+        `to(device)` calls it; call it again after `structure_cache().clear()`."""
+        ei, b, ptr = self.edge_index, self.batch, self.ptr
+        if not (ei is not None and ei.is_cuda and b is not None and ptr is not None and "max_edges_per_graph" in self
+                and "num_graphs" in self):
+            return False
+        from .structure import structure_cache
+        cache = structure_cache()
+        seg = cache.register_segments(b, ptr, int(self["num_graphs"]), int(self["max_nodes_per_graph"]))
+        if int(self["max_edges_per_graph"]) > 0 and int(self["max_nodes_per_graph"]) > 0:
+            cache.register_blocks(ei, seg.ptr, int(self["num_graphs"]), int(self["max_nodes_per_graph"]),
+                                  int(self["max_edges_per_graph"]))
+        return True
 
     def to_data_list(self) -> List[Data]:
         ptr, B = self.ptr, int(self.num_graphs)

@@ -176,6 +176,7 @@ def model_steps():
 
     def step(i):
         structure_cache().clear()
+        bd.register_structures()                 # collate-time facts: ptr, block-diagonal edge list (K1 fast path)
         opt.zero_grad(set_to_none=False)
         loss, _ = models.criterion("cross_entropy", m(bd), bd.y)
         loss.backward()

@@ -272,3 +272,16 @@ def test_edge_blocks_from_batch_accepts_only_collated_edge_lists():
     assert edge_blocks_from_batch(crossing, b.batch, 6) is None
     assert edge_blocks_from_batch(b.edge_index.flip(1), b.batch, 6) is None      # graph-minor order
     assert edge_blocks_from_batch(b.edge_index[:, :0], b.batch, 6) is None
+
+
+def test_collate_records_block_bounds():
+    """Batch.from_data_list keeps the collate-time facts the per-graph CSR kernel needs (no device sync later)."""
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.data import Batch
+    graphs = synthetic.peptides_graphs(7, seed=2)
+    b = Batch.from_data_list(graphs)
+    assert b.max_nodes_per_graph == max(g.num_nodes for g in graphs)
+    assert b.max_edges_per_graph == max(g.edge_index.size(1) for g in graphs)
+    back = b.to_data_list()
+    assert len(back) == 7 and all("max_edges_per_graph" not in g for g in back)
+    assert Batch.from_data_list(back).max_edges_per_graph == b.max_edges_per_graph

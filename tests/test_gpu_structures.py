@@ -217,3 +217,24 @@ def test_blocked_csr_reports_broken_promises(cuda):
     cache.graph(ok, 150, 150, False).by_dst
     assert int(cache.blocked_status(cuda)) & 1
     cache.blocked_status(cuda).zero_()
+
+
+def test_batch_to_device_registers_the_fast_csr_path(cuda):
+    """A collated Batch moved to the GPU builds its CSRs with the per-graph kernel; the convs see the same numbers."""
+    from graph_hscn_b200 import pyg, synthetic
+    from graph_hscn_b200.structure import build_csr, structure_cache
+    structure_cache().clear()
+    structure_cache().blocked_status(cuda).zero_()
+    b = synthetic.peptides_batch(20, seed=41).to(cuda)
+    N = b.x.size(0)
+    st = structure_cache().graph(b.edge_index, N, N, False)
+    assert st._blocks is not None and st._blocks.max_edges == b.max_edges_per_graph
+    _same(st.by_dst, build_csr(b.edge_index[1], b.edge_index[0], N, False))
+    _same(st.by_src, build_csr(b.edge_index[0], b.edge_index[1], N, False))
+    assert int(structure_cache().blocked_status(cuda)) == 0
+    torch.manual_seed(0)
+    conv = pyg.GCNConv(9, 32).to(cuda)
+    y_fast = conv(b.x.float(), b.edge_index)
+    ei_plain = b.edge_index.clone()                      # an unregistered copy of the same edges: radix path
+    assert structure_cache().graph(ei_plain, N, N, True)._plain._blocks is None
+    assert torch.equal(conv(b.x.float(), ei_plain), y_fast)
