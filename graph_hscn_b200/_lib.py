@@ -38,6 +38,7 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_gemm3x_set_trace": (I32, [P]),
     "ghscn_gemm3x": (I32, [P, I64, I64, I64, P, I64, P, I32, P, I64, P]),
     "ghscn_gemm3x_tn_supported": (I32, [I64, I64, I64]),
+    "ghscn_gemm3x_tn_segmented": (I32, [P, I64, P, I64, P, I64, I64, I64, I64, P, I64, I64, P]),
     "ghscn_gemm3x_tn_workspace_bytes": (SZ, [I64, I64, I64]),
     "ghscn_gemm3x_tn": (I32, [P, I64, P, I64, I64, I64, I64, P, P, SZ, P]),
     "ghscn_skinny_linear_fwd": (I32, [P, I64, P, P, I64, I64, I64, P, I64, P]),

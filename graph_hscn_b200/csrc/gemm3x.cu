@@ -576,9 +576,11 @@ __device__ __forceinline__ uint32_t mn_offset(int rr, int f4, int nblocks) {
   return (uint32_t)((kg * nblocks + (f4 >> 3)) * 512 + k4 * 128 + (((c16 >> 1) ^ k4) << 5) + ((c16 & 1) << 4));
 }
 
+template <bool kSegmented>
 __global__ void __launch_bounds__(kTnThreads, 1)
 gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __restrict__ qmat, int64_t ldq, int rows,
-                 int m_out, int n_out, float* __restrict__ partial, TnPlan plan) {
+                 int m_out, int n_out, float* __restrict__ partial, TnPlan plan, const int* __restrict__ seg_ptr,
+                 int64_t out_slab_stride, int64_t ldo) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[kTnStages], empty_bar[kTnStages];
   __shared__ __align__(8) unsigned long long accum_bar;
@@ -594,10 +596,20 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
   const int mt = blockIdx.x / nh, h = blockIdx.x - mt * nh;
   const int m0 = mt * kTileM;
   const int hpad = plan.hv.pad[h], hvalid = plan.hv.valid[h], hcol = plan.hv.col[h];
+  // blockIdx.y is a row slab of ONE product (dW: equal slabs, partials reduced afterwards) or, with `seg_ptr`, one
+  // segment of a batch of independent products (MinCUT S^T X per graph: rows seg_ptr[g] .. seg_ptr[g+1]-1).
   const int slab = blockIdx.y;
-  const int chunk0 = slab * plan.chunks_per_slab;
-  int nchunks = (rows + kTnRows - 1) / kTnRows - chunk0;
-  if (nchunks > plan.chunks_per_slab) nchunks = plan.chunks_per_slab;
+  int row_begin, row_end, nchunks;
+  if (kSegmented) {
+    row_begin = seg_ptr[slab];
+    row_end = seg_ptr[slab + 1];
+    nchunks = max(0, (row_end - row_begin + kTnRows - 1) / kTnRows);
+  } else {
+    const int chunk0 = slab * plan.chunks_per_slab;
+    row_begin = chunk0 * kTnRows;
+    row_end = rows;
+    nchunks = min((rows + kTnRows - 1) / kTnRows - chunk0, plan.chunks_per_slab);
+  }
 
   if (tid == 0) {
     for (int s = 0; s < kTnStages; ++s) {
@@ -656,17 +668,17 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
     constexpr int kBItems = kTnRows * kQ4 / 32;      // Q: item = lane + 32 i -> (row, float4 column) (20)
     const bool a_col_ok = m0 + lane * 4 < m_out;
     for (int c = pw; c < nchunks; c += kTnProducers / 32) {
-      const int r_base = (chunk0 + c) * kTnRows;
+      const int r_base = row_begin + c * kTnRows;
       const float* pb = pmat + (int64_t)r_base * ldp + m0 + lane * 4;
       const float* qb = qmat + (int64_t)r_base * ldq + hcol;
       float4 va[kAItems], vb[kBItems];
 #pragma unroll
       for (int i = 0; i < kAItems; ++i)
-        va[i] = (a_col_ok && r_base + i < rows) ? ldg_f4(pb + (int64_t)i * ldp) : make_float4(0.f, 0.f, 0.f, 0.f);
+        va[i] = (a_col_ok && r_base + i < row_end) ? ldg_f4(pb + (int64_t)i * ldp) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < kBItems; ++i) {
         const int item = lane + 32 * i, rr = item / kQ4, f4 = item - rr * kQ4;
-        vb[i] = (f4 * 4 < hvalid && r_base + rr < rows) ? ldg_f4(qb + (int64_t)rr * ldq + f4 * 4)
+        vb[i] = (f4 * 4 < hvalid && r_base + rr < row_end) ? ldg_f4(qb + (int64_t)rr * ldq + f4 * 4)
                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const int s = c % kTnStages;
@@ -731,7 +743,8 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
     for (int r = 0; r < 16; ++r) {
       const int trow = quad * 32 + half * 16 + r;
       if (m0 + trow < m_out) {
-        float* dst = partial + ((int64_t)slab * m_out + (m0 + trow)) * n_out + hcol;
+        float* dst = kSegmented ? partial + (int64_t)slab * out_slab_stride + (int64_t)(m0 + trow) * ldo + hcol
+                                : partial + ((int64_t)slab * m_out + (m0 + trow)) * n_out + hcol;
         const float* src = reinterpret_cast<const float*>(smem_gen) + (size_t)trow * sstride;
         for (int f = lane; f < nf4; f += 32)
           *reinterpret_cast<float4*>(dst + f * 4) = *reinterpret_cast<const float4*>(src + f * 4);
@@ -854,13 +867,14 @@ int ghscn_gemm3x_tn(const float* p_mat, int64_t ldp, const float* q_mat, int64_t
   if (workspace_bytes < (size_t)p.nslabs * (size_t)m_out * (size_t)n_out * sizeof(float)) return GHSCN_E_WORKSPACE;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm3x_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTnSmem);
+    cudaError_t e = cudaFuncSetAttribute(gemm3x_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTnSmem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   float* partial = p.nslabs == 1 ? out : static_cast<float*>(workspace);
-  gemm3x_tn_kernel<<<dim3((unsigned)(p.mtiles * p.hv.count), (unsigned)p.nslabs), kTnThreads, kTnSmem,
-                     as_stream(stream)>>>(p_mat, ldp, q_mat, ldq, (int)rows, (int)m_out, (int)n_out, partial, p);
+  gemm3x_tn_kernel<false><<<dim3((unsigned)(p.mtiles * p.hv.count), (unsigned)p.nslabs), kTnThreads, kTnSmem,
+                            as_stream(stream)>>>(p_mat, ldp, q_mat, ldq, (int)rows, (int)m_out, (int)n_out, partial, p,
+                                                 nullptr, 0, 0);
   GHSCN_LAUNCH_CHECK();
   if (p.nslabs > 1) {
     const int64_t elems4 = m_out * n_out / 4;
@@ -868,6 +882,35 @@ int ghscn_gemm3x_tn(const float* p_mat, int64_t ldp, const float* q_mat, int64_t
         partial, elems4, p.nslabs, out);
     GHSCN_LAUNCH_CHECK();
   }
+  return GHSCN_OK;
+}
+
+int ghscn_gemm3x_tn_segmented(const float* p_mat, int64_t ldp, const float* q_mat, int64_t ldq,
+                              const int32_t* seg_ptr, int64_t num_segments, int64_t max_segment_rows, int64_t m_out,
+                              int64_t n_out, float* out, int64_t ldo, int64_t out_segment_stride,
+                              ghscn_stream_t stream) {
+  GHSCN_REQUIRE(p_mat != nullptr && q_mat != nullptr && out != nullptr && seg_ptr != nullptr);
+  GHSCN_REQUIRE(num_segments >= 0 && max_segment_rows >= 0);
+  if (num_segments == 0) return GHSCN_OK;
+  if (!ghscn_gemm3x_tn_supported(1, m_out, n_out) || num_segments > 65535) return GHSCN_E_UNSUPPORTED;
+  if (max_segment_rows > kSlabRows) return GHSCN_E_UNSUPPORTED;      // accuracy: accumulations per TMEM accumulator
+  if ((ldp % 4) != 0 || (ldq % 4) != 0 || (ldo % 4) != 0 || (out_segment_stride % 4) != 0 || ldp < m_out ||
+      ldq < n_out || ldo < n_out)
+    return GHSCN_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(p_mat) & 15) || (reinterpret_cast<uintptr_t>(q_mat) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15))
+    return GHSCN_E_UNSUPPORTED;
+  TnPlan p;
+  p.hv = make_halves((int)n_out);
+  p.mtiles = (int)((m_out + kTileM - 1) / kTileM);
+  p.nslabs = (int)num_segments;
+  p.chunks_per_slab = 0;
+  cudaError_t e = cudaFuncSetAttribute(gemm3x_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTnSmem);
+  if (e != cudaSuccess) return (int)e;
+  gemm3x_tn_kernel<true><<<dim3((unsigned)(p.mtiles * p.hv.count), (unsigned)num_segments), kTnThreads, kTnSmem,
+                           as_stream(stream)>>>(p_mat, ldp, q_mat, ldq, 0, (int)m_out, (int)n_out, out, p, seg_ptr,
+                                                out_segment_stride, ldo);
+  GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }
 

@@ -152,6 +152,35 @@ def gemm3x_tn(p: Tensor, q: Tensor) -> Tensor:
     return out
 
 
+SEG_MAX_ROWS, SEG_COL_BLOCK = 1024, 256
+
+
+def gemm3x_tn_segmented_supported(m_out: int, n_out: int, max_rows: int, num_segments: int) -> bool:
+    return (USE_TCGEN05 and m_out % 4 == 0 and n_out % 4 == 0 and m_out >= 4 and n_out >= 16 and m_out <= 4096
+            and 0 < max_rows <= SEG_MAX_ROWS and 0 < num_segments <= 65535)
+
+
+def gemm3x_tn_segmented(p: Tensor, q: Tensor, ptr: Tensor, max_rows: int, out: Optional[Tensor] = None) -> Tensor:
+    """out[g] = p[rows_g]^T q[rows_g] for the row segments of `ptr` (int32 [B+1]) on the tcgen05 tensor cores with
+    fp32-level accuracy; q wider than 320 columns is processed in column blocks of 256."""
+    if p.stride(1) != 1 or p.stride(0) % 4 != 0:
+        p = p.contiguous()
+    if q.stride(1) != 1 or q.stride(0) % 4 != 0:
+        q = q.contiguous()
+    B, m, n = ptr.numel() - 1, p.size(1), q.size(1)
+    if out is None:
+        out = torch.empty((B, m, n), dtype=torch.float32, device=p.device)
+    L, st = lib(), _stream()
+    blocks = [(0, n)] if n <= 320 else [(c, min(SEG_COL_BLOCK, n - c)) for c in range(0, n, SEG_COL_BLOCK)]
+    if blocks[-1][1] < 16 and len(blocks) > 1:          # keep the last block >= 16 columns wide
+        (c0, w0), (c1, w1) = blocks[-2], blocks[-1]
+        blocks[-2:] = [(c0, w0 - 16), (c0 + w0 - 16, w1 + 16)]
+    for c, wdt in blocks:
+        L.call("ghscn_gemm3x_tn_segmented", _p(p), p.stride(0), q.data_ptr() + 4 * c, q.stride(0), _p(ptr), B,
+               int(max_rows), m, wdt, out.data_ptr() + 4 * c, n, m * n, st)
+    return out
+
+
 USE_TCGEN05 = os.environ.get("GHSCN_TCGEN05", "1") != "0"      # fused tcgen05 kernel (csrc/gemm3x.cu) where the shape is supported; else split_cat + library GEMM
 
 

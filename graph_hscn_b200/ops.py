@@ -153,6 +153,7 @@ torch.library.register_autograd("ghscn::spmm", _spmm_backward, setup_context=_sp
 # =============================================================================================
 # fused SCN node pipeline: GraphConv aggregation + lin_rel + lin_root + activation + cluster Linear
 # =============================================================================================
+MINCUT_TC_MIN_K = int(os.environ.get("GHSCN_MINCUT_TC_MIN_K", "64"))
 SCN_ACTS = {"identity": 0, "elu": 1, "relu": 2, "tanh": 3}
 SCN_LIMITS = (16, 32, 32)          # f_in, units, clusters handled by ghscn_scn_forward
 
@@ -480,10 +481,18 @@ def mincut_pool(logits: Tensor, x: Tensor, ptr: Tensor, rowptr: Tensor, col: Ten
     L = lib()
     ws_bytes = L.query("ghscn_mincut_workspace_bytes", N, B, K)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    # The pooled features S^T X are dense-bound once K >= 64 (profiles/r1_sweeps.md: ~9 TFLOP/s on the SIMT pipes):
+    # there the fused kernel skips them and the per-graph contraction runs on the tcgen05 tensor cores (3xTF32,
+    # fp32-level accuracy) over the same `ptr` segments.  Below that the path is HBM/latency-bound and stays fused.
+    from . import gemm
+    tc_out = (want_out and K >= MINCUT_TC_MIN_K and N > 0
+              and gemm.gemm3x_tn_segmented_supported(K, H, max_nodes, B))
     L.call("ghscn_mincut_fwd", _p(logits), logits.stride(0), _p(x), x.stride(0), _p(ptr), _p(rowptr), _p(col),
-           _p(adj_val), float(temp), B, N, K, H, max_nodes, _p(s_soft), _p(out) if want_out else None,
+           _p(adj_val), float(temp), B, N, K, H, max_nodes, _p(s_soft), _p(out) if (want_out and not tc_out) else None,
            _p(out_adj) if want_adj else None, _p(ss_raw), _p(adj_raw), _p(stats), _p(losses), _p(ws), ws_bytes,
            _stream())
+    if tc_out:
+        gemm.gemm3x_tn_segmented(s_soft, x, ptr, max_nodes, out=out)
     return out, out_adj, losses, s_soft, ss_raw, adj_raw, stats
 
 

@@ -192,6 +192,16 @@ GHSCN_API int ghscn_gemm3x_tn(const float* p_mat, int64_t ldp, const float* q_ma
                               int64_t m_out, int64_t n_out, float* out, void* workspace, size_t workspace_bytes,
                               ghscn_stream_t stream);
 
+/* Batch of independent products out[g] = P[rows_g]^T . Q[rows_g] over the row segments seg_ptr[g] .. seg_ptr[g+1]-1
+ * (one CTA per segment x M tile x N half, same kernel as ghscn_gemm3x_tn).  This is the pooled-feature contraction
+ * S^T X of dense_mincut_pool (model/hscn.py:63) per graph of a `ptr` batch, used where it is
+ * dense-bound (K >= 64, profiles/r1_sweeps.md).  out[g] is [m_out, n_out] with row stride ldo at
+ * out + g * out_segment_stride; empty segments give zeros.  max_segment_rows <= 1024 (accuracy bound per accumulator). */
+GHSCN_API int ghscn_gemm3x_tn_segmented(const float* p_mat, int64_t ldp, const float* q_mat, int64_t ldq,
+                                        const int32_t* seg_ptr, int64_t num_segments, int64_t max_segment_rows,
+                                        int64_t m_out, int64_t n_out, float* out, int64_t ldo,
+                                        int64_t out_segment_stride, ghscn_stream_t stream);
+
 /* Tall-skinny projections y = x W^T + b with in_feat <= 32 (the 9 raw atom features -> hidden layers:
  * GCNConv layer 1, GraphConv lin_rel/lin_root, the SCN cluster MLP).  One streaming pass each, fp32 FMA.
  *   fwd: y [N,out];  dw: dW[out,in] = dY^T x (two-stage fixed-order reduction);  dx: dx [N,in] = dY W. */

@@ -269,7 +269,7 @@ def _peptide_batch(num_graphs, seed):
     return synthetic.peptides_batch(num_graphs, seed=seed)
 
 
-@pytest.mark.parametrize("K,H", [(10, 16), (4, 64), (32, 40), (128, 24)])
+@pytest.mark.parametrize("K,H", [(10, 16), (4, 64), (32, 40), (128, 24), (64, 300), (128, 512), (68, 332)])
 def test_mincut_ragged_fwd_bwd(cuda, K, H):
     o, p = _oracle(), _product()
     b = _peptide_batch(6, seed=K)
