@@ -159,6 +159,132 @@ def vocsp():
     emit()
 
 
+# ----------------------------------------------------------------------- per-kernel roofline at the bench shape
+def kernel_table():
+    """Every kernel family of SURVEY 8a at the config #2 shape (B = 128 Peptides graphs, h = 300, K = 10), timed alone:
+    20 back-to-back calls in one CUDA graph, so launch gaps are excluded but nothing else overlaps."""
+    from graph_hscn_b200 import gemm, hetero, ops
+    from graph_hscn_b200.structure import StructureCache, build_csr, edge_blocks_from_batch
+    emit("## Per-kernel roofline at the bench shape (config #2: B = 128, h = 300, K = 10), each kernel timed alone\n")
+    b = synthetic.peptides_batch(128, seed=1236)
+    N, E, B, H, K, F = b.x.size(0), b.edge_index.size(1), 128, 300, 10, 9
+    emit(f"N = {N} nodes, E = {E} directed edges, V = B*K = {B * K} virtual slots; peak = measured HBM copy {PEAK:.0f} GB/s\n")
+    emit("| kernel (SURVEY 8a row) | us | algorithmic MB | GB/s | frac of HBM peak | note |")
+    emit("|---|---|---|---|---|---|")
+    ei, batch, x_raw = b.edge_index.to(dev), b.batch.to(dev), b.x.to(dev)
+    counts = b.ptr[1:] - b.ptr[:-1]
+    hints = dict(num_graphs=B, batch_sorted=1, max_nodes_per_graph=int(counts.max()), no_self_loops=1)
+    blocks = edge_blocks_from_batch(b.edge_index, b.batch, B)
+
+    def row(name, us, by, note=""):
+        emit(f"| {name} | {us:.1f} | {by / 1e6:.2f} | {by / us / 1e3:.0f} | {by / us / 1e3 / PEAK:.3f} | {note} |")
+
+    with structure_hints(**hints):
+        cache = StructureCache()
+        seg = cache.segments(batch, B)
+
+        def k1_fast(i):
+            c = StructureCache()
+            c.register_blocks(ei, seg.ptr, B, *blocks)
+            c.graph(ei, N, N, False).by_dst
+        row("K1 CSR, per-graph fast path, both orientations (a1)", graph_time(k1_fast), 16 * E + 8 * (N + 1) + 16 * E,
+            "one launch; latency-bound (128 CTAs, 7 dependent phases)")
+
+        def k1_radix(i):
+            build_csr(ei[1], ei[0], N, False)
+            build_csr(ei[0], ei[1], N, False)
+        row("K1 CSR, general radix path, both orientations (a1)", graph_time(k1_radix), 2 * (16 * E + 4 * (N + 1) + 8 * E),
+            "16 launches")
+        st = structure_cache().graph(ei, N, N, True)
+        d, t = st.by_dst, st.by_src
+
+        def k1b(i):
+            st._weights.clear()
+            st.weights(None, normalize=True, need_transpose=False)
+        row("K1b gcn_norm on the CSR: deg^-1/2 + slot weights (a1)", graph_time(k1b), 12 * d.num_items + 8 * N, "2 launches")
+        w, w_t, _ = st.weights(None, normalize=True)
+        nset = 8
+        xs = [torch.randn(N, H, device=dev) for _ in range(nset)]
+        ys = [torch.empty(N, H, device=dev) for _ in range(nset)]
+        L = lib()
+
+        def k2(i):
+            L.call("ghscn_spmm", _p(d.rowptr), _p(d.col), _p(w), _p(xs[i % nset]), H, _p(ys[i % nset]), H, None, N, H, 1,
+                   _stream())
+        row("K2 SpMM h = 300 + ReLU epilogue (a2)", graph_time(k2), 4 * H * 2 * N + 8 * d.num_items + 4 * (N + 1),
+            "latency-bound: DRAM traffic = algorithmic (ncu), 16 warps/SM")
+        xf = ops.cast_i64_f32(x_raw)
+
+        def k3(i):
+            L.call("ghscn_spmm", _p(d.rowptr), _p(d.col), _p(w), _p(xf), F, _p(ys[i % nset]), F, None, N, F, 0, _stream())
+        row("K3 SpMM at input width 9 (GraphConv, a3)", graph_time(k3), 4 * F * 2 * N + 8 * d.num_items + 4 * (N + 1))
+
+        def k4(i):
+            torch.ops.ghscn.segment_reduce(xs[i % nset], seg.ptr, None, True)
+        row("K4 segment mean [N,300] -> [B,300] (a10)", graph_time(k4), 4 * H * (N + B))
+        clusters = (torch.arange(N, device=dev) % K).int()
+        hb = hetero.build_hetero_batch(x_raw, ei, batch, clusters, K, padded=True, num_graphs=B)
+        lv = hb["local", "to", "virtual"].edge_index
+        V = hb["virtual"].x.size(0)
+        gat = pyg.GATConv((-1, -1), H, add_self_loops=False).to(dev)
+        xv = torch.randn(V, H, device=dev)
+        with torch.no_grad():
+            gat((xs[0], xv), lv)
+
+            def k5(i):
+                gat((xs[i % nset], xv), lv)
+            row("K5 GAT cluster pool l->v at width 300, forward (a9)", graph_time(k5), 4 * H * N + 12 * N + 4 * H * V * 2,
+                "scores + segment softmax + pooled sum at input width + [V,300]x[300,300] GEMM")
+        s_log = torch.randn(N, K, device=dev)
+        ei1, _ = pyg.gcn_norm(ei, None, N, add_self_loops=True)
+
+        def k6f(i):
+            pyg.mincut_pool_ragged(xs[i % nset], ei1, s_log, batch, want_out=False, want_adj=False)
+        E1 = ei1.size(1)
+        row("K6 MinCUT losses forward, K = 10 (a4/a5; what hscn.py:63 keeps)", graph_time(k6f),
+            4 * N * K * 2 + 4 * (N + 1) + 4 * E1 + B * (8 * K * K + 32), "latency-bound: one CTA per graph, ~10 barrier phases")
+
+        def k6o(i):
+            pyg.mincut_pool_ragged(xs[i % nset], ei1, s_log, batch)
+        row("K6 MinCUT forward with pooled features and adjacency, K = 10, H = 300", graph_time(k6o),
+            4 * N * K * 2 + 4 * N * H + 4 * (N + 1) + 4 * E1 + B * (4 * K * H + 8 * K * K + 32))
+        s_soft = torch.softmax(s_log, -1)
+
+        def k7(i):
+            cl = hetero.assign_clusters(s_soft)
+            hetero.build_hetero_batch(x_raw, ei, batch, cl, K, padded=True, num_graphs=B, x_float=xf)
+        row("K7 argmax + virtual nodes + l->v / v->v edges + their 4 CSRs (a6/a7)", graph_time(k7),
+            4 * N * K + 4 * N + 8 * F * N + 4 * F * B * K + 16 * N + 16 * N, "5 launches + torch glue")
+        scn = models.SCN([16], "elu", 9, K).to(dev)
+        ei_s, ew_s = pyg.gcn_norm(ei, None, N, add_self_loops=True)
+        with torch.no_grad():
+            def kscn(i):
+                scn.logits(xf, ei_s, ew_s)
+            row("SCN node pipeline (GraphConv 9->16 + ELU + Linear->10), logits only", graph_time(kscn),
+                4 * N * (F + K) + 8 * d.num_items + 4 * (N + 1))
+        wgt = torch.randn(H, H, device=dev) / H ** 0.5
+        img = gemm.gemm3x_prep(wgt)
+
+        def kg(i):
+            gemm.gemm3x(xs[i % nset], img, H, None, False, out=ys[i % nset])
+        us = graph_time(kg)
+        row("projection x W^T, h x h, tcgen05 3xTF32 (`gemm3x`)", us, 4 * N * 2 * H,
+            f"{3 * 2 * N * H * H / us / 1e6:.0f} TFLOP/s of tf32 MMA work; smem-bandwidth-bound main loop (DESIGN 4.1)")
+
+        def ktn(i):
+            gemm.gemm3x_tn(ys[i % nset], xs[i % nset])
+        us = graph_time(ktn)
+        row("weight gradient dY^T x, h x h, tcgen05 3xTF32 (`gemm3x_tn` + slab reduce)", us, 4 * N * 2 * H,
+            f"{3 * 2 * N * H * H / us / 1e6:.0f} TFLOP/s of tf32 MMA work")
+        w9 = torch.randn(H, F, device=dev)
+
+        def ksk(i):
+            gemm.linear(xf, w9, None)
+        row("projection 9 -> 300 (`skinny_fwd_reg`)", graph_time(ksk), 4 * N * (F + H))
+    structure_cache().clear()
+    emit()
+
+
 # ---------------------------------------------------------------------------------------- model steps #1, #3
 def model_steps():
     emit("## Config #1 (MPNN GCN L=5 h=300, B=128) and config #3 shape (Graph-HSCN step, B=1024, 11 targets, L1)\n")
@@ -207,8 +333,10 @@ def model_steps():
 
 if __name__ == "__main__":
     emit(f"# Round-1 sweeps on one B200 (measured HBM copy peak {PEAK:.0f} GB/s)\n")
-    which = os.environ.get("SWEEPS", "spmm,mincut,vocsp,models").split(",")
+    which = os.environ.get("SWEEPS", "kernels,spmm,mincut,vocsp,models").split(",")
     t0 = time.time()
+    if "kernels" in which:
+        kernel_table()
     if "spmm" in which:
         spmm_sweep()
     if "mincut" in which:
