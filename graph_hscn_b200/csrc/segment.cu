@@ -27,6 +27,20 @@ __global__ void __launch_bounds__(kSegWarps * 32) segment_reduce_kernel(const fl
   for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
   if (on) {
     int i = beg + wid;
+    if (VEC == 4) {      // four rows in flight per warp, added in row order (the order of the two-row loop below)
+      for (; i + 3 * kSegWarps < end; i += 4 * kSegWarps) {
+        float4 q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t r = perm ? perm[i + j * kSegWarps] : (i + j * kSegWarps);
+          q[j] = ldg_f4(x + r * ldx + f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[0] += q[j].x; acc[1 % VEC] += q[j].y; acc[2 % VEC] += q[j].z; acc[3 % VEC] += q[j].w;
+        }
+      }
+    }
     for (; i + kSegWarps < end; i += 2 * kSegWarps) {
       const int64_t r0 = perm ? perm[i] : i, r1 = perm ? perm[i + kSegWarps] : (i + kSegWarps);
       if (VEC == 4) {
@@ -70,12 +84,12 @@ __global__ void __launch_bounds__(256) segment_broadcast_kernel(const float* __r
                                                                 const int* __restrict__ perm, int num_segments,
                                                                 int num_feat, int mean, float* __restrict__ dx,
                                                                 int64_t lddx) {
+  // warp per output row: the segment search runs once per row (not once per element), the lanes stream the row
   const int nvec = num_feat / VEC;
-  const int64_t total = (int64_t)ptr[num_segments] * nvec;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int p = (int)(idx / nvec);
-    const int f = (int)(idx % nvec) * VEC;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int total_rows = ptr[num_segments];
+  for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < total_rows; p += nwarps) {
     int lo = 0, hi = num_segments;  // largest g with ptr[g] <= p
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
@@ -83,16 +97,18 @@ __global__ void __launch_bounds__(256) segment_broadcast_kernel(const float* __r
     }
     const float cnt = (float)max(ptr[lo + 1] - ptr[lo], 1);  // autograd of true_divide_: g / count
     const int64_t r = perm ? perm[p] : p;
-    const float* src = dy + (int64_t)lo * lddy + f;
-    float* dst = dx + r * lddx + f;
-    if (VEC == 4) {
-      float4 q = ldg_f4(src);
-      if (mean) {
-        q.x = __fdiv_rn(q.x, cnt); q.y = __fdiv_rn(q.y, cnt); q.z = __fdiv_rn(q.z, cnt); q.w = __fdiv_rn(q.w, cnt);
+    const float* src = dy + (int64_t)lo * lddy;
+    float* dst = dx + r * lddx;
+    for (int v = lane; v < nvec; v += 32) {
+      if (VEC == 4) {
+        float4 q = ldg_f4(src + v * 4);
+        if (mean) {
+          q.x = __fdiv_rn(q.x, cnt); q.y = __fdiv_rn(q.y, cnt); q.z = __fdiv_rn(q.z, cnt); q.w = __fdiv_rn(q.w, cnt);
+        }
+        *reinterpret_cast<float4*>(dst + v * 4) = q;
+      } else {
+        dst[v] = mean ? __fdiv_rn(__ldg(src + v), cnt) : __ldg(src + v);
       }
-      *reinterpret_cast<float4*>(dst) = q;
-    } else {
-      dst[0] = mean ? __fdiv_rn(__ldg(src), cnt) : __ldg(src);
     }
   }
 }
