@@ -171,49 +171,17 @@ __global__ void __launch_bounds__(256, GHSCN_WIDE_MINBLOCKS) spmm_wide_kernel(co
   __syncthreads();
   const int f0 = blockIdx.y * (128 * ITERS) + lane * 4;
 
-  for (int r = wid; r < nrows; r += 8) {
-    const int beg = s_rowptr[r] - sbeg, end = s_rowptr[r + 1] - sbeg;
-    float4 acc[ITERS];
+  // Every warp owns kWideRows / 8 CONSECUTIVE rows, i.e. one contiguous slot range, and walks it four slots at a time
+  // whatever rows they belong to: molecule-like graphs have ~2 slots per row, so batching per row would leave half of
+  // the loads unissued.  Slots are still accumulated strictly in slot order into their own row (a row is written out
+  // when the walk leaves it), so the arithmetic per row is unchanged.
+  constexpr int kRowsPerWarp = kWideRows / 8;
+  const int rbeg = wid * kRowsPerWarp, rend = min(nrows, rbeg + kRowsPerWarp);
+  if (rbeg >= nrows) return;
+  float4 acc[ITERS];
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = beg; s < end; s += 4) {
-      const int n4 = min(4, end - s);
-      float4 v[4][ITERS];
-      float wv[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < n4) {
-          const int slot = s + k;
-          const int c = slot < kSlotCap ? s_col[slot] : col[sbeg + slot];
-          wv[k] = WEIGHTED ? (slot < kSlotCap ? s_w[slot] : w[sbeg + slot]) : 1.f;
-          const float* xr = x + (int64_t)c * ldx + f0;
-#pragma unroll
-          for (int it = 0; it < ITERS; ++it)
-            if (f0 + it * 128 < num_feat) v[k][it] = ldg_f4(xr + it * 128);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < n4) {
-#pragma unroll
-          for (int it = 0; it < ITERS; ++it) {
-            if (f0 + it * 128 < num_feat) {
-              if (WEIGHTED) {
-                acc[it].x = mul_then_add(acc[it].x, wv[k], v[k][it].x);
-                acc[it].y = mul_then_add(acc[it].y, wv[k], v[k][it].y);
-                acc[it].z = mul_then_add(acc[it].z, wv[k], v[k][it].z);
-                acc[it].w = mul_then_add(acc[it].w, wv[k], v[k][it].w);
-              } else {
-                acc[it].x = __fadd_rn(acc[it].x, v[k][it].x);
-                acc[it].y = __fadd_rn(acc[it].y, v[k][it].y);
-                acc[it].z = __fadd_rn(acc[it].z, v[k][it].z);
-                acc[it].w = __fadd_rn(acc[it].w, v[k][it].w);
-              }
-            }
-          }
-        }
-      }
-    }
+  for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto flush = [&](int r) {
     float* yrow = y + (int64_t)(row0 + r) * ldy + f0;
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
@@ -226,8 +194,56 @@ __global__ void __launch_bounds__(256, GHSCN_WIDE_MINBLOCKS) spmm_wide_kernel(co
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         *reinterpret_cast<float4*>(yrow + it * 128) = o;
       }
+      acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  int r = rbeg;
+  int row_end = s_rowptr[r + 1] - sbeg;                       // first slot after the current row
+  const int s_first = s_rowptr[rbeg] - sbeg, s_last = s_rowptr[rend] - sbeg;
+  for (int s = s_first; s < s_last; s += 4) {
+    const int n4 = min(4, s_last - s);
+    float4 v[4][ITERS];
+    float wv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < n4) {
+        const int slot = s + k;
+        const int c = slot < kSlotCap ? s_col[slot] : col[sbeg + slot];
+        wv[k] = WEIGHTED ? (slot < kSlotCap ? s_w[slot] : w[sbeg + slot]) : 1.f;
+        const float* xr = x + (int64_t)c * ldx + f0;
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it)
+          if (f0 + it * 128 < num_feat) v[k][it] = ldg_f4(xr + it * 128);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < n4) {
+        while (s + k >= row_end) {                            // the walk leaves row r (and any empty rows after it)
+          flush(r);
+          ++r;
+          row_end = s_rowptr[r + 1] - sbeg;
+        }
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+          if (f0 + it * 128 < num_feat) {
+            if (WEIGHTED) {
+              acc[it].x = mul_then_add(acc[it].x, wv[k], v[k][it].x);
+              acc[it].y = mul_then_add(acc[it].y, wv[k], v[k][it].y);
+              acc[it].z = mul_then_add(acc[it].z, wv[k], v[k][it].z);
+              acc[it].w = mul_then_add(acc[it].w, wv[k], v[k][it].w);
+            } else {
+              acc[it].x = __fadd_rn(acc[it].x, v[k][it].x);
+              acc[it].y = __fadd_rn(acc[it].y, v[k][it].y);
+              acc[it].z = __fadd_rn(acc[it].z, v[k][it].z);
+              acc[it].w = __fadd_rn(acc[it].w, v[k][it].w);
+            }
+          }
+        }
+      }
     }
   }
+  for (; r < rend; ++r) flush(r);                             // the last row with slots and trailing empty rows
 }
 
 // ---- wide rows, TMA bulk-copy gather (sm_100a: cp.async.bulk + mbarrier, SASS UBLKCP) -----------------------------
