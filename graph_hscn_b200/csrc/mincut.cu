@@ -9,12 +9,22 @@
 //   4nK (logits) + 4nH (X, only if `out` is requested) + 4(n+1) + 4 nnz  ->  4nK (S) + 4KH + 8K^2 + 32.
 #include <math.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ghscn {
 
 // few graphs: one big CTA per graph keeps an SM busy; many graphs: several small CTAs per SM
-static inline int mincut_threads(int64_t num_graphs) { return num_graphs >= 4 * kNumSMs ? 256 : (num_graphs >= 2 * kNumSMs ? 512 : 1024); }
+static inline int mincut_threads(int64_t num_graphs) {
+  static const int forced = [] {                       // tuning experiments: GHSCN_MINCUT_THREADS=256|512|1024
+    const char* e = getenv("GHSCN_MINCUT_THREADS");
+    const int v = e ? atoi(e) : 0;
+    return (v == 128 || v == 256 || v == 512 || v == 1024) ? v : 0;
+  }();
+  if (forced) return forced;
+  return num_graphs >= 4 * kNumSMs ? 256 : (num_graphs >= 2 * kNumSMs ? 512 : 1024);
+}
 constexpr int kMaxClusters = 128;
 constexpr int kStatsStride = 8;  // per graph: num, den, ||SS||_F, ||R||_F (= ortho_g), mc_g, -, -, -
 constexpr size_t kSmemBudget = 200 * 1024;
