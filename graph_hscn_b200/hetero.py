@@ -27,6 +27,22 @@ VV = ("virtual", "to", "virtual")
 LV = ("local", "to", "virtual")
 
 
+_PADDED_LAYOUT: dict = {}
+
+
+def _padded_layout(B: int, K: int, dev) -> tuple:
+    """`batch` / `ptr` of the padded virtual layout (K slots per graph): constants of (B, K), built once per device
+    instead of five small launches per step."""
+    key = (B, K, dev.index if dev.index is not None else torch.cuda.current_device())
+    hit = _PADDED_LAYOUT.get(key)
+    if hit is None:
+        if torch.cuda.is_current_stream_capturing():       # first use inside a capture: do not cache pool memory
+            return torch.arange(B, device=dev).repeat_interleave(K), torch.arange(B + 1, device=dev) * K
+        hit = _PADDED_LAYOUT[key] = (torch.arange(B, device=dev).repeat_interleave(K),
+                                     torch.arange(B + 1, device=dev) * K)
+    return hit
+
+
 def assign_clusters(s_soft: Tensor) -> Tensor:
     """First-max cluster id per node (int32 [N]); bit-exact with `Tensor.max(1)[1]`."""
     _require_cuda(s_soft)
@@ -56,8 +72,7 @@ def build_hetero_batch(x_raw: Tensor, edge_index: Tensor, batch: Tensor, cluster
         L.call("ghscn_virtual_edges", _p(remap), _p(ptr), _p(num_virtual), None, B, N, K, _p(lv), _p(vv), vv_cap,
                None, st)
         virt_x = vx_pad
-        virt_batch = torch.arange(B, device=dev).repeat_interleave(K)
-        virt_ptr = torch.arange(B + 1, device=dev) * K
+        virt_batch, virt_ptr = _padded_layout(B, K, dev)
     else:
         V, E_vv = torch.stack([voff[-1], eoff[-1]]).tolist()      # the one host sync of the compact layout
         vv_cap = E_vv
