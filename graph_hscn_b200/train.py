@@ -75,6 +75,14 @@ class FlatGradients:
     def zero(self) -> None:
         self.flat.zero_()
 
+    def backward_into(self, loss: Tensor) -> None:
+        """`loss.backward()` for the live parameters, with the gradients written straight into the flat buffer: the
+        autograd engine hands the finished gradients over (`torch.autograd.grad`) and ONE multi-tensor copy places them,
+        instead of one `grad += g` kernel per parameter interleaved with the backward chain (and no zero fill before).
+        Every value is the one `backward()` would have accumulated onto a zeroed buffer."""
+        grads = torch.autograd.grad(loss, self.params)
+        torch._foreach_copy_([p.grad for p in self.params], list(grads))
+
     def flatten_parameters(self) -> Tensor:
         """Re-home the live parameters as views of ONE flat fp32 leaf whose .grad is the flat gradient buffer:
         the optimizer step becomes a single elementwise kernel over one tensor (AdamW is elementwise and all
@@ -288,22 +296,20 @@ class GraphHSCNStep:
         plain.by_dst, plain.by_src                               # built here, read by both streams
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            self.scn_grads.zero()
             ei, ew = self.ns.gcn_norm(self.dev["edge_index"], None, N, add_self_loops=True)
             _, both = self.scn.forward_batched(x_f, ei, ew, self.dev["batch"], losses_tensor=True)
-            both.sum().backward()                        # == (mincut + ortho).backward(), one reduction instead of
+            self.scn_grads.backward_into(both.sum())     # == (mincut + ortho).backward(), one reduction instead of
             self.losses[0:2].copy_(both.detach())        # two select/scatter round trips
             self.scn_grads.all_reduce_mean(world)
             self.scn_opt.step()
             hb = self._assign(x_f, ei, ew)
-        self.hscn_grads.zero()
         self.hscn.defer_branch_join = True
         try:
             pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)
         finally:
             self.hscn.defer_branch_join = False
         loss, _ = models.criterion(self.cfg.loss_fn, pred, hb["local"].y)
-        loss.backward()
+        self.hscn_grads.backward_into(loss)
         self.losses[2:3].copy_(loss.detach().view(1))
         self.hscn_grads.all_reduce_mean(world)
         self.hscn_opt.step()
