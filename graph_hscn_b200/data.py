@@ -253,8 +253,16 @@ class Batch(Data):
         # and -- edges are concatenated graph-major with node offsets added, so the batch is block diagonal -- the
         # largest per-graph edge count, which sizes the per-graph CSR kernel (K1 fast path)
         out["max_nodes_per_graph"] = int(counts.max()) if len(data_list) else 0
-        if len(data_list) and all("edge_index" in d for d in data_list):
-            out["max_edges_per_graph"] = max(int(d["edge_index"].size(1)) for d in data_list)
+        if len(data_list) and all("edge_index" in d for d in data_list) and out["edge_index"].numel():
+            # verified here, once, on the host: every edge stays inside its graph (a Data object with an out-of-range
+            # index would break that); batches that fail keep the general radix path
+            from .structure import edge_blocks_from_batch
+            try:
+                blocks = edge_blocks_from_batch(out["edge_index"], out["batch"], len(data_list))
+            except (IndexError, RuntimeError):
+                blocks = None
+            if blocks is not None:
+                out["max_edges_per_graph"] = blocks[1]
         return out
 
     def to(self, device, non_blocking: bool = False) -> "Batch":

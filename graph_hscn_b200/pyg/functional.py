@@ -276,8 +276,8 @@ def scn_logits_fused(x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor
     from ..structure import structure_cache
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and act in ops.SCN_ACTS):
         return None
-    if edge_weight is not None and edge_weight.requires_grad:
-        return None
+    if x.requires_grad or (edge_weight is not None and edge_weight.requires_grad):
+        return None             # the fused op differentiates w.r.t. the parameters only
     f, u, k = x.size(1), conv.out_channels, out_lin.out_channels
     if f > ops.SCN_LIMITS[0] or u > ops.SCN_LIMITS[1] or k > ops.SCN_LIMITS[2]:
         return None

@@ -285,3 +285,15 @@ def test_collate_records_block_bounds():
     back = b.to_data_list()
     assert len(back) == 7 and all("max_edges_per_graph" not in g for g in back)
     assert Batch.from_data_list(back).max_edges_per_graph == b.max_edges_per_graph
+
+
+def test_collate_refuses_block_bounds_for_edges_leaving_their_graph():
+    """A Data object whose edge index points outside its own node range must not enable the per-graph CSR kernel."""
+    import torch
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.data import Batch
+    graphs = synthetic.peptides_graphs(4, seed=5)
+    graphs[1].edge_index = graphs[1].edge_index.clone()
+    graphs[1].edge_index[1, 0] = graphs[1].num_nodes + 3          # lands in the next graph after collate
+    b = Batch.from_data_list(graphs)
+    assert "max_edges_per_graph" not in b and b.max_nodes_per_graph > 0
