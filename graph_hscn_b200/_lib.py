@@ -76,6 +76,8 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_virtual_compact": (I32, [P, P, P, I64, I64, I64, P, P, P]),
     "ghscn_cast_i64_f32": (I32, [P, I64, P, P]),
     "ghscn_scn_forward": (I32, [P, P, P, P, I64, I64, I64, I64, I64, P, P, P, P, P, I32, P, P, P, P, P]),
+    "ghscn_scn_backward_workspace_bytes": (SZ, [I64, I64, I64, I64]),
+    "ghscn_scn_backward": (I32, [P, P, P, P, P, I64, I64, I64, I64, I64, P, I32, P, P, SZ, P]),
 }
 
 

@@ -87,6 +87,139 @@ scn_forward_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, 
   }
 }
 
+
+// ---- backward of the node pipeline w.r.t. its parameters ---------------------------------------------------------
+//   dh = ds W_out,  dpre = dh * act'(pre),
+//   dW_out = ds^T h, db_out = colsum(ds), dW_rel = dpre^T agg, db_rel = colsum(dpre), dW_root = dpre^T x.
+// One thread per node forms the node's outer products; every product is summed over the warp with shuffles, over the
+// CTA's warps in warp order and over the CTAs in CTA order by the second kernel: a fixed order, hence deterministic.
+// Replaces three two-stage dW kernels, two column sums, a dX kernel and the activation backward (12 launches).
+constexpr int kScnBwdThreads = 256;
+
+__host__ __device__ inline int scn_grad_count(int f_in, int units, int clusters) {
+  return clusters * units + clusters + 2 * units * f_in + units;
+}
+
+template <int F, int U, int KC>
+__global__ void __launch_bounds__(kScnBwdThreads)
+scn_backward_kernel(const float* __restrict__ ds, const float* __restrict__ h, const float* __restrict__ pre,
+                    const float* __restrict__ agg, const float* __restrict__ x, int64_t ldx, int num_nodes, int f_in,
+                    int units, int clusters, const float* __restrict__ w_out, int act, float* __restrict__ partial) {
+  constexpr int kWarps = kScnBwdThreads / 32;
+  extern __shared__ float scn_sm[];                      // [kWarps][count] warp partials, then W_out [KC][U]
+  const int count = scn_grad_count(f_in, units, clusters);
+  float* s_part = scn_sm;
+  float* s_wout = scn_sm + kWarps * count;
+  for (int i = threadIdx.x; i < KC * U; i += blockDim.x) {
+    const int c = i / U, u = i - c * U;
+    s_wout[i] = (c < clusters && u < units) ? w_out[c * units + u] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = n < num_nodes;
+  float dsv[KC], hv[U], dpre[U], av[F], xv[F];
+#pragma unroll
+  for (int c = 0; c < KC; ++c) dsv[c] = (on && c < clusters) ? ds[(int64_t)n * clusters + c] : 0.f;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const bool ok = on && u < units;
+    hv[u] = ok ? h[(int64_t)n * units + u] : 0.f;
+    const float p = ok ? pre[(int64_t)n * units + u] : 0.f;
+    float dh = 0.f;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) dh = fmaf(dsv[c], s_wout[c * U + u], dh);
+    float g;
+    switch (act) {
+      case 1: g = p > 0.f ? dh : dh * expf(p); break;      // ELU'(p) = exp(p) for p <= 0
+      case 2: g = p > 0.f ? dh : 0.f; break;
+      case 3: g = dh * (1.f - hv[u] * hv[u]); break;
+      default: g = dh;
+    }
+    dpre[u] = ok ? g : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < F; ++k) {
+    const bool ok = on && k < f_in;
+    av[k] = ok ? agg[(int64_t)n * f_in + k] : 0.f;
+    xv[k] = ok ? __ldg(x + (int64_t)n * ldx + k) : 0.f;
+  }
+  float* mine = s_part + wid * count;
+  int o = 0;
+  // layout of the gradient vector: dW_out [K,U] | db_out [K] | dW_rel [U,F] | db_rel [U] | dW_root [U,F]
+#pragma unroll
+  for (int c = 0; c < KC; ++c) {
+    if (c < clusters) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u < units) {
+          const float t = warp_sum(dsv[c] * hv[u]);
+          if (lane == 0) mine[o + c * units + u] = t;
+        }
+      }
+    }
+  }
+  o += clusters * units;
+#pragma unroll
+  for (int c = 0; c < KC; ++c) {
+    if (c < clusters) {
+      const float t = warp_sum(dsv[c]);
+      if (lane == 0) mine[o + c] = t;
+    }
+  }
+  o += clusters;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (u < units) {
+#pragma unroll
+      for (int k = 0; k < F; ++k) {
+        if (k < f_in) {
+          const float t = warp_sum(dpre[u] * av[k]);
+          if (lane == 0) mine[o + u * f_in + k] = t;
+        }
+      }
+    }
+  }
+  o += units * f_in;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (u < units) {
+      const float t = warp_sum(dpre[u]);
+      if (lane == 0) mine[o + u] = t;
+    }
+  }
+  o += units;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (u < units) {
+#pragma unroll
+      for (int k = 0; k < F; ++k) {
+        if (k < f_in) {
+          const float t = warp_sum(dpre[u] * xv[k]);
+          if (lane == 0) mine[o + u * f_in + k] = t;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += s_part[w * count + i];
+    partial[(int64_t)blockIdx.x * count + i] = t;
+  }
+}
+
+// grads[i] = sum over CTAs, in CTA order
+__global__ void __launch_bounds__(256) scn_backward_reduce_kernel(const float* __restrict__ partial, int num_ctas,
+                                                                  int count, float* __restrict__ grads) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float t = 0.f;
+  for (int b = 0; b < num_ctas; ++b) t += partial[(int64_t)b * count + i];
+  grads[i] = t;
+}
+
 }  // namespace ghscn
 
 using namespace ghscn;
@@ -113,6 +246,52 @@ int ghscn_scn_forward(const int32_t* rowptr, const int32_t* col, const float* w,
   else if (units <= 16) GHSCN_SCN_LAUNCH(16, 16);
   else GHSCN_SCN_LAUNCH(16, 32);
 #undef GHSCN_SCN_LAUNCH
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+size_t ghscn_scn_backward_workspace_bytes(int64_t num_nodes, int64_t f_in, int64_t units, int64_t clusters) {
+  if (num_nodes < 0 || f_in < 1 || units < 1 || clusters < 1) return 0;
+  const int64_t ctas = ceil_div<int64_t>(num_nodes > 0 ? num_nodes : 1, kScnBwdThreads);
+  return (size_t)ctas * (size_t)scn_grad_count((int)f_in, (int)units, (int)clusters) * sizeof(float);
+}
+
+int ghscn_scn_backward(const float* ds, const float* h, const float* pre, const float* agg, const float* x, int64_t ldx,
+                       int64_t num_nodes, int64_t f_in, int64_t units, int64_t clusters, const float* w_out,
+                       int32_t act, float* grads, void* workspace, size_t workspace_bytes, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_nodes >= 0 && num_nodes < ((int64_t)1 << 31));
+  if (f_in < 1 || f_in > kScnMaxF || units < 1 || units > kScnMaxU || clusters < 1 || clusters > kScnMaxK ||
+      act < 0 || act > 3)
+    return GHSCN_E_UNSUPPORTED;
+  GHSCN_REQUIRE(grads != nullptr);
+  const int count = scn_grad_count((int)f_in, (int)units, (int)clusters);
+  cudaStream_t st = as_stream(stream);
+  if (num_nodes == 0) {
+    cudaError_t e = cudaMemsetAsync(grads, 0, (size_t)count * sizeof(float), st);
+    return e == cudaSuccess ? GHSCN_OK : (int)e;
+  }
+  GHSCN_REQUIRE(ds && h && pre && agg && x && w_out && workspace && ldx >= f_in);
+  if (workspace_bytes < ghscn_scn_backward_workspace_bytes(num_nodes, f_in, units, clusters)) return GHSCN_E_WORKSPACE;
+  const unsigned ctas = (unsigned)ceil_div<int64_t>(num_nodes, kScnBwdThreads);
+  float* partial = static_cast<float*>(workspace);
+#define GHSCN_SCN_BWD(F, U, KC)                                                                                      \
+  do {                                                                                                               \
+    const size_t shm = ((size_t)(kScnBwdThreads / 32) * count + (size_t)(KC) * (U)) * sizeof(float);                  \
+    if (shm > 48 * 1024) {                                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(scn_backward_kernel<F, U, KC>,                                            \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);                   \
+      if (e != cudaSuccess) return (int)e;                                                                           \
+    }                                                                                                                \
+    scn_backward_kernel<F, U, KC><<<ctas, kScnBwdThreads, shm, st>>>(ds, h, pre, agg, x, ldx, (int)num_nodes,         \
+                                                                     (int)f_in, (int)units, (int)clusters, w_out,    \
+                                                                     act, partial);                                  \
+  } while (0)
+  if (f_in <= 9 && units <= 16 && clusters <= 16) GHSCN_SCN_BWD(9, 16, 16);
+  else if (units <= 16) GHSCN_SCN_BWD(16, 16, 32);
+  else GHSCN_SCN_BWD(16, 32, 32);
+#undef GHSCN_SCN_BWD
+  GHSCN_LAUNCH_CHECK();
+  scn_backward_reduce_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(partial, (int)ctas, count, grads);
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }

@@ -154,6 +154,7 @@ torch.library.register_autograd("ghscn::spmm", _spmm_backward, setup_context=_sp
 # fused SCN node pipeline: GraphConv aggregation + lin_rel + lin_root + activation + cluster Linear
 # =============================================================================================
 MINCUT_TC_MIN_K = int(os.environ.get("GHSCN_MINCUT_TC_MIN_K", "64"))
+FUSED_SCN_BACKWARD = os.environ.get("GHSCN_FUSED_SCN_BACKWARD", "1") != "0"
 SCN_ACTS = {"identity": 0, "elu": 1, "relu": 2, "tanh": 3}
 SCN_LIMITS = (16, 32, 32)          # f_in, units, clusters handled by ghscn_scn_forward
 
@@ -183,9 +184,22 @@ class ScnNodeForward(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, ds):
-        from .gemm import skinny_dw, skinny_dx
         x, agg, pre, h, w_out = ctx.saved_tensors
         ds = ds.contiguous()
+        if FUSED_SCN_BACKWARD:
+            # one launch + a fixed-order reduction instead of three dW kernels, two column sums, dX and act'
+            n, f = x.shape
+            u, k = w_out.size(1), w_out.size(0)
+            L = lib()
+            grads = torch.empty(k * u + k + 2 * u * f + u, dtype=torch.float32, device=x.device)
+            ws_bytes = L.query("ghscn_scn_backward_workspace_bytes", n, f, u, k)
+            ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=x.device)
+            L.call("ghscn_scn_backward", _p(ds), _p(h), _p(pre), _p(agg), _p(x), x.stride(0), n, f, u, k,
+                   _p(w_out.contiguous()), ctx.act, _p(grads), _p(ws), ws_bytes, _stream())
+            d_wout, d_bout, d_wrel, d_brel, d_wroot = torch.split(grads, [k * u, k, u * f, u, u * f])
+            return (None, None, None, None, d_wrel.view(u, f), d_brel if ctx.has[0] else None, d_wroot.view(u, f),
+                    d_wout.view(k, u), d_bout if ctx.has[1] else None, None)
+        from .gemm import skinny_dw, skinny_dx
         d_wout = skinny_dw(ds, h)
         d_bout = colsum(ds) if ctx.has[1] else None
         dh = skinny_dx(ds, w_out.contiguous())

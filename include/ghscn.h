@@ -272,6 +272,17 @@ GHSCN_API int ghscn_scn_forward(const int32_t* rowptr, const int32_t* col, const
                                 const float* b_rel, const float* w_root, const float* w_out, const float* b_out,
                                 int32_t act, float* agg, float* pre, float* h, float* logits, ghscn_stream_t stream);
 
+/* Parameter gradients of the pipeline above from ds = d loss / d logits and the saved agg / pre / h (the reference's
+ * autograd chain through Linear, the activation and GraphConv's two Linears; train/train_clustering.py:48-50):
+ *   grads = [ dW_out [clusters,units] | db_out [clusters] | dW_rel [units,f_in] | db_rel [units] | dW_root [units,f_in] ]
+ * summed over the nodes in a fixed order (warp shuffles, warps in order, CTAs in order): deterministic.  x and the
+ * graph structure get no gradient.  workspace: ghscn_scn_backward_workspace_bytes(). */
+GHSCN_API size_t ghscn_scn_backward_workspace_bytes(int64_t num_nodes, int64_t f_in, int64_t units, int64_t clusters);
+GHSCN_API int ghscn_scn_backward(const float* ds, const float* h, const float* pre, const float* agg, const float* x,
+                                 int64_t ldx, int64_t num_nodes, int64_t f_in, int64_t units, int64_t clusters,
+                                 const float* w_out, int32_t act, float* grads, void* workspace, size_t workspace_bytes,
+                                 ghscn_stream_t stream);
+
 /* ---- K6: fused MinCUT pool, one CTA per graph --------------------------------------------------
  * Replaces to_dense_adj + dense_mincut_pool (model/hscn.py:61-63).  SURVEY 8a rows a4, a5,
  * Appendix A.6/A.7.  The adjacency is consumed as the batch CSR whose ROWS ARE edge_index[0]

@@ -480,12 +480,19 @@ def test_scn_fused_node_pipeline(cuda, act, units, K):
     s_r = ref.logits(b.x.float(), ei_r, w_r)
     (s_r * up).sum().backward()
     got = {}
-    for fuse in (True, False):
+    from graph_hscn_b200 import ops as gops
+    for fuse in (True, False, "chain"):                    # fused fwd + fused bwd | separate operators | fused fwd + op chain bwd
         tst.zero_grad(set_to_none=True)
-        tst.fuse = fuse
-        s_t = tst.logits(x_t, ei_t, w_t)
-        (s_t * up.to(cuda)).sum().backward()
+        tst.fuse = bool(fuse)
+        gops.FUSED_SCN_BACKWARD = fuse is True
+        try:
+            s_t = tst.logits(x_t, ei_t, w_t)
+            (s_t * up.to(cuda)).sum().backward()
+        finally:
+            gops.FUSED_SCN_BACKWARD = True
         got[fuse] = (s_t.detach().clone(), {n: q.grad.detach().clone() for n, q in tst.named_parameters()})
+    for n in got[True][1]:
+        assert_close(got[True][1][n], got["chain"][1][n], RTOL, f"fused backward vs operator chain, grad {n}")
     assert_close(got[True][0], got[False][0], 2e-6, "fused vs separate logits")
     assert_close(got[True][0], s_r, RTOL, "fused logits vs oracle")
     for n, q in ref.named_parameters():
