@@ -297,3 +297,26 @@ def test_collate_refuses_block_bounds_for_edges_leaving_their_graph():
     graphs[1].edge_index[1, 0] = graphs[1].num_nodes + 3          # lands in the next graph after collate
     b = Batch.from_data_list(graphs)
     assert "max_edges_per_graph" not in b and b.max_nodes_per_graph > 0
+
+
+def test_flat_gradients_backward_into_equals_backward():
+    """FlatGradients.backward_into (autograd.grad + one multi-tensor copy) == zero the flat buffer + loss.backward()."""
+    import torch
+    from graph_hscn_b200.train import FlatGradients
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+    shared = torch.nn.Linear(3, 3)                       # used twice: its gradient has two contributions
+    mod = torch.nn.ModuleList([net, shared])
+    fg = FlatGradients(mod)
+    x = torch.randn(11, 5)
+
+    def loss():
+        y = net(x)
+        return (shared(shared(y)) ** 2).mean()
+    fg.flat.fill_(123.0)                                 # stale content must be overwritten, not accumulated onto
+    fg.backward_into(loss())
+    got = fg.flat.clone()
+    fg.zero()
+    loss().backward()
+    assert torch.equal(got, fg.flat)
+    assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in fg.params)     # still views of the flat buffer
