@@ -67,6 +67,8 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_mincut_workspace_bytes": (SZ, [I64, I64, I64]),
     "ghscn_mincut_fwd": (I32, [P, I64, P, I64, P, P, P, P, F32, I64, I64, I64, I64, I32,
                                P, P, P, P, P, P, P, P, SZ, P]),
+    "ghscn_mincut_fwd_phase": (I32, [P, I64, P, I64, P, P, P, P, F32, I64, I64, I64, I64, I32,
+                                     P, P, P, P, P, P, P, P, SZ, P, I32]),
     "ghscn_mincut_bwd": (I32, [P, P, I64, P, P, P, P, P, P, P, F32, I64, I64, I64, I64, I32,
                                P, P, P, P, P, P, P, I64, P, I64, P, SZ, P]),
     "ghscn_cluster_argmax": (I32, [P, I64, I64, I64, P, P]),

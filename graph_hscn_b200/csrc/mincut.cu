@@ -232,7 +232,10 @@ __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
     const int* __restrict__ ptr, const int* __restrict__ rowptr, const int* __restrict__ col,
     const float* __restrict__ adj_val, float temp, int K, int H, int n_cap, float* __restrict__ s_soft,
     float* __restrict__ out, float* __restrict__ out_adj, float* __restrict__ ss_raw,
-    float* __restrict__ adj_raw, float* __restrict__ stats, float* __restrict__ as_ws) {
+    float* __restrict__ adj_raw, float* __restrict__ stats, float* __restrict__ as_ws, int phase) {
+  // phase 0: everything.  phase 1: S, A S, the two traces (num, den -> stats) and nothing else: the K x K and K x H
+  // contractions are then done by ghscn_gemm3x_tn_segmented on the tensor cores (dense-bound for K >= 64), and
+  // phase 2 finishes from ss_raw / adj_raw: norms, orthogonality loss, normalised coarse adjacency.
   extern __shared__ float smem[];
   __shared__ float red[32];
   __shared__ float dk[kMaxClusters];
@@ -246,6 +249,8 @@ __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
   float* AS = SMEM ? smem + (size_t)n_cap * K : as_ws + (int64_t)base * K;
   float* deg = SMEM ? smem + 2 * (size_t)n_cap * K : smem;
 
+  float num = 0.f, den = 0.f;
+  if (phase != 2) {
   // A. S = softmax(logits / temp).  Small K: one thread per node row (all rows of the graph in flight at once);
   //    large K: one warp per row.  Row degrees (row sums of A) by one thread per row.
   for (int i = tid; i < n; i += blockDim.x) {
@@ -314,16 +319,30 @@ __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
     pnum += sv * AS[e];
     pden += deg[e / K] * sv * sv;
   }
-  const float num = block_sum(pnum, red);
-  const float den = block_sum(pden, red);
+  num = block_sum(pnum, red);
+  den = block_sum(pden, red);
+  }  // phase != 2
+  if (phase == 1) {
+    if (tid == 0) {
+      float* st = stats + (int64_t)g * kStatsStride;
+      st[0] = num; st[1] = den;
+    }
+    return;
+  }
+  if (phase == 2) {
+    num = stats[(int64_t)g * kStatsStride];
+    den = stats[(int64_t)g * kStatsStride + 1];
+  }
 
   float* ssg = ss_raw + (int64_t)g * K * K;
   float* oag = adj_raw + (int64_t)g * K * K;
-  atb_tiled<4, 4>(S, K, K, S, K, K, n, ssg, K);    // S^T S
-  atb_tiled<4, 4>(S, K, K, AS, K, K, n, oag, K);   // S^T (A S)
-  if (out != nullptr)                               // S^T X, X streamed from global memory
-    atb_tiled<8, 4>(S, K, K, x + (int64_t)base * ldx, ldx, H, n, out + (int64_t)g * K * H, H);
-  __syncthreads();  // ssg / oag visible to the whole CTA
+  if (phase == 0) {
+    atb_tiled<4, 4>(S, K, K, S, K, K, n, ssg, K);    // S^T S
+    atb_tiled<4, 4>(S, K, K, AS, K, K, n, oag, K);   // S^T (A S)
+    if (out != nullptr)                               // S^T X, X streamed from global memory
+      atb_tiled<8, 4>(S, K, K, x + (int64_t)base * ldx, ldx, H, n, out + (int64_t)g * K * H, H);
+    __syncthreads();  // ssg / oag visible to the whole CTA
+  }
 
   // D. losses and the normalised coarse adjacency
   float pf = 0.f;
@@ -561,12 +580,12 @@ size_t ghscn_mincut_workspace_bytes(int64_t num_nodes, int64_t num_graphs, int64
   return (size_t)3 * num_nodes * num_clusters * 4 + 256;
 }
 
-int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x, int64_t ldx, const int32_t* ptr,
+static int mincut_fwd_impl(const float* logits, int64_t ldz, const float* x, int64_t ldx, const int32_t* ptr,
                      const int32_t* rowptr, const int32_t* col, const float* adj_val, float temp,
                      int64_t num_graphs, int64_t num_nodes, int64_t num_clusters, int64_t num_feat,
                      int32_t max_nodes_per_graph, float* s_soft, float* out, float* out_adj, float* ss_raw,
                      float* adj_raw, float* stats, float* losses, void* workspace, size_t workspace_bytes,
-                     ghscn_stream_t stream_) {
+                     ghscn_stream_t stream_, int phase) {
   GHSCN_REQUIRE(num_graphs >= 0 && num_nodes >= 0 && num_clusters > 0 && num_feat >= 0);
   GHSCN_REQUIRE(num_graphs < ((int64_t)1 << 31) && num_nodes < ((int64_t)1 << 31));
   if (num_clusters > kMaxClusters) return GHSCN_E_UNSUPPORTED;
@@ -577,7 +596,8 @@ int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x, int64_t l
   cudaStream_t stream = as_stream(stream_);
   const int K = (int)num_clusters, H = (int)num_feat, n_cap = max_nodes_per_graph;
   const int threads = mincut_threads(num_graphs);
-  const bool smem = fwd_smem_bytes(n_cap, K, true) <= kSmemBudget;
+  // the split phases exchange S and A S through HBM (s_soft, workspace): they use the workspace variant
+  const bool smem = phase == 0 && fwd_smem_bytes(n_cap, K, true) <= kSmemBudget;
   const size_t shm = fwd_smem_bytes(n_cap, K, smem);
   if (shm > kSmemBudget) return GHSCN_E_UNSUPPORTED;
   float* as_ws = nullptr;
@@ -589,15 +609,38 @@ int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x, int64_t l
     cudaFuncSetAttribute(mincut_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
     mincut_fwd_kernel<true><<<(unsigned)num_graphs, threads, shm, stream>>>(
         logits, ldz, x, ldx, ptr, rowptr, col, adj_val, temp, K, H, n_cap, s_soft, out, out_adj, ss_raw, adj_raw,
-        stats, as_ws);
+        stats, as_ws, phase);
   } else {
     mincut_fwd_kernel<false><<<(unsigned)num_graphs, threads, shm, stream>>>(
         logits, ldz, x, ldx, ptr, rowptr, col, adj_val, temp, K, H, n_cap, s_soft, out, out_adj, ss_raw, adj_raw,
-        stats, as_ws);
+        stats, as_ws, phase);
+  }
+  if (phase == 1) {
+    GHSCN_LAUNCH_CHECK();
+    return GHSCN_OK;
   }
   mincut_reduce_losses_kernel<<<1, 256, 0, stream>>>(stats, (int)num_graphs, losses);
   GHSCN_LAUNCH_CHECK_N(2);
   return GHSCN_OK;
+}
+
+int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x, int64_t ldx, const int32_t* ptr,
+                     const int32_t* rowptr, const int32_t* col, const float* adj_val, float temp,
+                     int64_t num_graphs, int64_t num_nodes, int64_t num_clusters, int64_t num_feat,
+                     int32_t max_nodes_per_graph, float* s_soft, float* out, float* out_adj, float* ss_raw,
+                     float* adj_raw, float* stats, float* losses, void* workspace, size_t workspace_bytes,
+                     ghscn_stream_t stream_) {
+  return mincut_fwd_impl(logits, ldz, x, ldx, ptr, rowptr, col, adj_val, temp, num_graphs, num_nodes, num_clusters, num_feat, max_nodes_per_graph, s_soft, out, out_adj, ss_raw, adj_raw, stats, losses, workspace, workspace_bytes, stream_, 0);
+}
+
+int ghscn_mincut_fwd_phase(const float* logits, int64_t ldz, const float* x, int64_t ldx, const int32_t* ptr,
+                     const int32_t* rowptr, const int32_t* col, const float* adj_val, float temp,
+                     int64_t num_graphs, int64_t num_nodes, int64_t num_clusters, int64_t num_feat,
+                     int32_t max_nodes_per_graph, float* s_soft, float* out, float* out_adj, float* ss_raw,
+                     float* adj_raw, float* stats, float* losses, void* workspace, size_t workspace_bytes,
+                     ghscn_stream_t stream_, int32_t phase) {
+  if (phase < 0 || phase > 2) return GHSCN_E_INVALID;
+  return mincut_fwd_impl(logits, ldz, x, ldx, ptr, rowptr, col, adj_val, temp, num_graphs, num_nodes, num_clusters, num_feat, max_nodes_per_graph, s_soft, out, out_adj, ss_raw, adj_raw, stats, losses, workspace, workspace_bytes, stream_, phase);
 }
 
 int ghscn_mincut_bwd(const float* s_soft, const float* x, int64_t ldx, const int32_t* ptr, const int32_t* rowptr,

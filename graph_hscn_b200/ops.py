@@ -154,6 +154,7 @@ torch.library.register_autograd("ghscn::spmm", _spmm_backward, setup_context=_sp
 # fused SCN node pipeline: GraphConv aggregation + lin_rel + lin_root + activation + cluster Linear
 # =============================================================================================
 MINCUT_TC_MIN_K = int(os.environ.get("GHSCN_MINCUT_TC_MIN_K", "64"))
+MINCUT_TC_KK = os.environ.get("GHSCN_MINCUT_TC_KK", "1") != "0"      # S^T S and S^T A S on the tensor cores too
 FUSED_SCN_BACKWARD = os.environ.get("GHSCN_FUSED_SCN_BACKWARD", "1") != "0"
 SCN_ACTS = {"identity": 0, "elu": 1, "relu": 2, "tanh": 3}
 SCN_LIMITS = (16, 32, 32)          # f_in, units, clusters handled by ghscn_scn_forward
@@ -499,12 +500,24 @@ def mincut_pool(logits: Tensor, x: Tensor, ptr: Tensor, rowptr: Tensor, col: Ten
     # there the fused kernel skips them and the per-graph contraction runs on the tcgen05 tensor cores (3xTF32,
     # fp32-level accuracy) over the same `ptr` segments.  Below that the path is HBM/latency-bound and stays fused.
     from . import gemm
-    tc_out = (want_out and K >= MINCUT_TC_MIN_K and N > 0
-              and gemm.gemm3x_tn_segmented_supported(K, H, max_nodes, B))
-    L.call("ghscn_mincut_fwd", _p(logits), logits.stride(0), _p(x), x.stride(0), _p(ptr), _p(rowptr), _p(col),
-           _p(adj_val), float(temp), B, N, K, H, max_nodes, _p(s_soft), _p(out) if (want_out and not tc_out) else None,
-           _p(out_adj) if want_adj else None, _p(ss_raw), _p(adj_raw), _p(stats), _p(losses), _p(ws), ws_bytes,
-           _stream())
+    big_k = K >= MINCUT_TC_MIN_K and N > 0
+    tc_out = want_out and big_k and gemm.gemm3x_tn_segmented_supported(K, H, max_nodes, B)
+    tc_kk = (big_k and MINCUT_TC_KK and gemm.gemm3x_tn_segmented_supported(K, K, max_nodes, B)
+             and (tc_out or not want_out) and ws_bytes >= N * K * 4)
+    args = (_p(logits), logits.stride(0), _p(x), x.stride(0), _p(ptr), _p(rowptr), _p(col), _p(adj_val), float(temp),
+            B, N, K, H, max_nodes, _p(s_soft), _p(out) if (want_out and not tc_out) else None,
+            _p(out_adj) if want_adj else None, _p(ss_raw), _p(adj_raw), _p(stats), _p(losses), _p(ws), ws_bytes,
+            _stream())
+    if tc_kk:                               # S, A S and the traces; then every contraction on the tensor cores
+        L.call("ghscn_mincut_fwd_phase", *args, 1)
+        a_s = ws[:N * K * 4].view(torch.float32).view(N, K)
+        gemm.gemm3x_tn_segmented(s_soft, s_soft, ptr, max_nodes, out=ss_raw)
+        gemm.gemm3x_tn_segmented(s_soft, a_s, ptr, max_nodes, out=adj_raw)
+        if tc_out:
+            gemm.gemm3x_tn_segmented(s_soft, x, ptr, max_nodes, out=out)
+        L.call("ghscn_mincut_fwd_phase", *args, 2)
+        return out, out_adj, losses, s_soft, ss_raw, adj_raw, stats
+    L.call("ghscn_mincut_fwd", *args)
     if tc_out:
         gemm.gemm3x_tn_segmented(s_soft, x, ptr, max_nodes, out=out)
     return out, out_adj, losses, s_soft, ss_raw, adj_raw, stats

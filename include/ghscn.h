@@ -303,6 +303,17 @@ GHSCN_API int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x,
                                int32_t max_nodes_per_graph, float* s_soft, float* out, float* out_adj,
                                float* ss_raw, float* adj_raw, float* stats, float* losses /*[2]*/,
                                void* workspace, size_t workspace_bytes, ghscn_stream_t stream);
+/* The same forward in two phases around ghscn_gemm3x_tn_segmented, for the dense-bound corner (K >= 64):
+ *   phase 1  S = softmax, A S (-> workspace, [N,K] fp32), the traces num / den (-> stats); no contraction;
+ *   caller   ss_raw = S^T S, adj_raw = S^T (A S), out = S^T X per graph on the tensor cores;
+ *   phase 2  norms, orthogonality loss, normalised coarse adjacency from ss_raw / adj_raw, then the loss means.
+ * phase 0 == ghscn_mincut_fwd.  Arguments as above; out is ignored by phases 1 and 2. */
+GHSCN_API int ghscn_mincut_fwd_phase(const float* logits, int64_t ldz, const float* x, int64_t ldx, const int32_t* ptr,
+                                     const int32_t* rowptr, const int32_t* col, const float* adj_val, float temp,
+                                     int64_t num_graphs, int64_t num_nodes, int64_t num_clusters, int64_t num_feat,
+                                     int32_t max_nodes_per_graph, float* s_soft, float* out, float* out_adj,
+                                     float* ss_raw, float* adj_raw, float* stats, float* losses /*[2]*/,
+                                     void* workspace, size_t workspace_bytes, ghscn_stream_t stream, int32_t phase);
 GHSCN_API int ghscn_mincut_bwd(const float* s_soft, const float* x, int64_t ldx, const int32_t* ptr,
                                const int32_t* rowptr, const int32_t* col, const float* adj_val,
                                const int32_t* rowptr_t, const int32_t* col_t, const float* adj_val_t, float temp,
