@@ -179,10 +179,30 @@ class GraphHSCNStep:
         blocks = edge_blocks_from_batch(host_batch.edge_index, host_batch.batch, self.B)
         self.max_edges_per_graph = blocks[1] if blocks is not None and os.environ.get("GHSCN_BLOCKED_CSR", "1") != "0" else 0
         # pinned host staging + static device buffers (inputs are re-copied every step in the e2e path)
-        self.host = {k: host_batch[k].contiguous().pin_memory() if device.type == "cuda" else host_batch[k]
-                     for k in ("x", "edge_index", "batch", "y")}
-        self.dev = {k: torch.empty_like(v, device=device) for k, v in self.host.items()}
-        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        src = {k: host_batch[k].contiguous() for k in ("x", "edge_index", "batch", "y")}
+        if device.type == "cuda":
+            # ONE pinned staging buffer and ONE device buffer hold all four inputs (256-byte aligned sub-ranges), so
+            # the per-step upload is a single host-to-device copy; `host[k]` / `dev[k]` are typed views into them
+            offs, total = {}, 0
+            for k, v in src.items():
+                offs[k] = total
+                total += (v.numel() * v.element_size() + 255) // 256 * 256
+            self._host_buf = torch.empty(max(total, 256), dtype=torch.uint8).pin_memory()
+            self._dev_buf = torch.empty(max(total, 256), dtype=torch.uint8, device=device)
+
+            def view(buf, k, v):
+                nbytes = v.numel() * v.element_size()
+                return buf[offs[k]:offs[k] + nbytes].view(v.dtype).view(v.shape)
+            self.host = {k: view(self._host_buf, k, v) for k, v in src.items()}
+            for k, v in src.items():
+                self.host[k].copy_(v)
+            self.dev = {k: view(self._dev_buf, k, v) for k, v in src.items()}
+            self.h2d_bytes = int(self._host_buf.numel())
+        else:
+            self._host_buf = self._dev_buf = None
+            self.host = src
+            self.dev = {k: torch.empty_like(v, device=device) for k, v in self.host.items()}
+            self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
         torch.manual_seed(seed)
         self.scn = models.SCN(list(cfg.scn_units), cfg.scn_act, cfg.num_features, cfg.num_clusters, ops=self.ns).to(device)
         self.hscn = models.HSCN("GAT", "GCN", "GCN", models.ACTIVATIONS[cfg.activation], cfg.num_features, cfg.hidden,
@@ -195,6 +215,9 @@ class GraphHSCNStep:
 
     # -- host <-> device ---------------------------------------------------------------------------
     def upload(self) -> None:
+        if self._dev_buf is not None:
+            self._dev_buf.copy_(self._host_buf, non_blocking=True)
+            return
         for k, v in self.host.items():
             self.dev[k].copy_(v, non_blocking=True)
 
