@@ -320,3 +320,25 @@ def test_flat_gradients_backward_into_equals_backward():
     loss().backward()
     assert torch.equal(got, fg.flat)
     assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in fg.params)     # still views of the flat buffer
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu(built_lib):
+    """Per-graph CSR build, fused SCN pipeline, segmented tcgen05 contraction, split MinCUT forward: argument and
+    shape errors are reported before any launch (runs on the CPU-only build box)."""
+    from graph_hscn_b200._lib import GhscnError, lib
+    L = lib()
+    assert L.query("ghscn_csr_blocked_smem_bytes", 444, 920) == (4 * 444 + 2 + 4 * 920) * 4
+    assert L.query("ghscn_scn_backward_workspace_bytes", 18269, 9, 16, 10) == 72 * 474 * 4
+    with pytest.raises(GhscnError, match="invalid"):
+        L.call("ghscn_csr_build_blocked", None, None, 10, None, 1, 10, 10, 10, None, None, None, None, None, None,
+               None, None)
+    with pytest.raises(GhscnError, match="unsupported"):      # 17 input features: outside the fused kernel's range
+        L.call("ghscn_scn_forward", None, None, None, None, 17, 100, 17, 16, 10, None, None, None, None, None, 1,
+               None, None, None, None, None)
+    with pytest.raises(GhscnError, match="unsupported"):      # activation id out of range
+        L.call("ghscn_scn_backward", None, None, None, None, None, 9, 100, 9, 16, 10, None, 7, None, None, 0, None)
+    with pytest.raises(GhscnError, match="invalid"):
+        L.call("ghscn_gemm3x_tn_segmented", None, 64, None, 300, None, 4, 100, 64, 300, None, 300, 64 * 300, None)
+    with pytest.raises(GhscnError, match="invalid"):          # phase out of range
+        L.call("ghscn_mincut_fwd_phase", None, 0, None, 0, None, None, None, None, 1.0, 1, 1, 10, 1, 1,
+               None, None, None, None, None, None, None, None, 0, None, 3)
