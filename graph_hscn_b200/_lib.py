@@ -46,6 +46,9 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_skinny_linear_dw": (I32, [P, I64, P, I64, I64, I64, I64, P, P, SZ, P]),
     "ghscn_skinny_linear_dx": (I32, [P, I64, P, I64, I64, I64, P, I64, P]),
     "ghscn_adamw_step": (I32, [P, P, P, P, I64, F32, F32, F32, F32, F32, P, P]),
+    "ghscn_adamw_step_scaled": (I32, [P, P, P, P, I64, F32, F32, F32, F32, F32, P, P, P]),
+    "ghscn_grad_clip_workspace_bytes": (SZ, [I64]),
+    "ghscn_grad_clip_scale": (I32, [P, I64, F32, P, SZ, P, P]),
     "ghscn_colsum_workspace_bytes": (SZ, [I64, I64]),
     "ghscn_colsum": (I32, [P, I64, I64, I64, P, P, SZ, P]),
     "ghscn_virtual_csr": (I32, [P, P, P, P, P, I64, I64, I32] + [P] * 12 + [P]),

@@ -243,6 +243,15 @@ __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
   const int base = ptr[g];
   const int n = ptr[g + 1] - base;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x / 32;
+  if (n > n_cap || n < 0) {
+    // the caller's max-nodes-per-graph hint sized the shared tiles and is too small for this graph: poison the
+    // graph's losses (NaN propagates to the batch means) instead of writing past the tiles
+    if (tid == 0 && phase != 1) {
+      float* st = stats + (int64_t)g * kStatsStride;
+      st[3] = NAN; st[4] = NAN;
+    }
+    return;
+  }
 
   float* Sg = s_soft + (int64_t)base * K;
   float* S = SMEM ? smem : Sg;
@@ -399,7 +408,7 @@ __global__ void __launch_bounds__(1024) mincut_bwd_kernel(
     const float* __restrict__ s_soft, const float* __restrict__ x, int64_t ldx, const int* __restrict__ ptr,
     const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ adj_val,
     const int* __restrict__ rowptr_t, const int* __restrict__ col_t, const float* __restrict__ adj_val_t,
-    float temp, int B, int K, int H, int n_cap, const float* __restrict__ ss_raw,
+    float temp, int B, int N, int K, int H, int n_cap, const float* __restrict__ ss_raw,
     const float* __restrict__ adj_raw, const float* __restrict__ stats, const float* __restrict__ g_out,
     const float* __restrict__ g_out_adj, const float* __restrict__ g_losses, float* __restrict__ d_logits,
     int64_t lddz, float* __restrict__ d_x, int64_t lddx, float* __restrict__ ws) {
@@ -411,6 +420,19 @@ __global__ void __launch_bounds__(1024) mincut_bwd_kernel(
   const int n = ptr[g + 1] - base;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x / 32;
   const size_t nk_cap = (size_t)n_cap * K;
+  if (g == B - 1) {
+    // rows past the last graph (padding rows of a bucketed batch: `ptr` may cover fewer than N rows) get zero
+    // gradients, so callers never see unwritten memory
+    const int tail0 = ptr[B];
+    for (int64_t e = (int64_t)tail0 * K + tid; e < (int64_t)N * K; e += blockDim.x)
+      d_logits[(e / K) * lddz + e % K] = 0.f;
+    if (d_x != nullptr)
+      for (int64_t e = (int64_t)tail0 * H + tid; e < (int64_t)N * H; e += blockDim.x) d_x[(e / H) * lddx + e % H] = 0.f;
+  }
+  if (n > n_cap || n < 0) {                       // stale max-nodes hint: poison the gradient, touch nothing else
+    if (tid == 0 && n > 0) d_logits[(int64_t)base * lddz] = NAN;
+    return;
+  }
 
   // shared layout: [Gsym K*K][Gam K*K][deg n_cap] (+ [S][AS][ATS][dS] when SMEM)
   float* Gsym = smem;
@@ -670,13 +692,13 @@ int ghscn_mincut_bwd(const float* s_soft, const float* x, int64_t ldx, const int
   if (smem) {
     cudaFuncSetAttribute(mincut_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
     mincut_bwd_kernel<true><<<(unsigned)num_graphs, threads, shm, stream>>>(
-        s_soft, x, ldx, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, temp, (int)num_graphs, K, H, n_cap,
-        ss_raw, adj_raw, stats, g_out, g_out_adj, g_losses, d_logits, lddz, d_x, lddx, ws);
+        s_soft, x, ldx, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, temp, (int)num_graphs, (int)num_nodes, K,
+        H, n_cap, ss_raw, adj_raw, stats, g_out, g_out_adj, g_losses, d_logits, lddz, d_x, lddx, ws);
   } else {
     cudaFuncSetAttribute(mincut_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
     mincut_bwd_kernel<false><<<(unsigned)num_graphs, threads, shm, stream>>>(
-        s_soft, x, ldx, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, temp, (int)num_graphs, K, H, n_cap,
-        ss_raw, adj_raw, stats, g_out, g_out_adj, g_losses, d_logits, lddz, d_x, lddx, ws);
+        s_soft, x, ldx, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, temp, (int)num_graphs, (int)num_nodes, K,
+        H, n_cap, ss_raw, adj_raw, stats, g_out, g_out_adj, g_losses, d_logits, lddz, d_x, lddx, ws);
   }
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;

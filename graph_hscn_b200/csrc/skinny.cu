@@ -428,14 +428,15 @@ namespace ghscn {
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                     float lr, float b1, float b2, float eps, float wd,
-                                                    float* __restrict__ step) {
-  const float t = step[0] + 1.0f;  // every thread reads the old value; thread 0 of block 0 publishes t at the end
+                                                    float* __restrict__ step, const float* __restrict__ grad_scale) {
+  const float t = step[0] + 1.0f;  // every thread reads the old value; a separate 1-thread kernel publishes t
   const float bc1 = 1.0f - powf(b1, t);
   const float bc2_sqrt = sqrtf(1.0f - powf(b2, t));
   const float step_size = lr / bc1;
+  const float gs = grad_scale ? grad_scale[0] : 1.0f;   // clip_grad_norm coefficient (== g.mul_(coef) beforehand)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float gi = g[i];
+    const float gi = grad_scale ? g[i] * gs : g[i];
     float pi = p[i] * (1.0f - lr * wd);
     const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
     const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
@@ -445,19 +446,70 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 __global__ void adamw_bump_kernel(float* step) { step[0] += 1.0f; }
+
+// ---- clip_grad_norm (train/train.py:92-93) over the flat gradient buffer ------------------------------------------
+// total = ||g||_2 as a fixed-order two-stage sum of squares (deterministic); coef = min(1, max_norm / (total + 1e-6)),
+// torch.nn.utils.clip_grad_norm_'s formula.  out[0] = total, out[1] = coef; the AdamW kernel applies coef.
+constexpr int kClipCtas = 148;
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, int64_t n,
+                                                            float* __restrict__ partial) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) acc = fmaf(g[i], g[i], acc);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(256) clip_coef_kernel(const float* __restrict__ partial, int count, float max_norm,
+                                                        float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) acc += partial[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    const float total = sqrtf(acc);
+    const float coef = max_norm / (total + 1e-6f);
+    out[0] = total;
+    out[1] = coef < 1.0f ? coef : 1.0f;
+  }
+}
 }  // namespace ghscn
 
-extern "C" int ghscn_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                                float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
-                                ghscn_stream_t stream_) {
+extern "C" size_t ghscn_grad_clip_workspace_bytes(int64_t n) {
+  (void)n;
+  return (size_t)ghscn::kClipCtas * sizeof(float);
+}
+
+extern "C" int ghscn_grad_clip_scale(const float* grad, int64_t n, float max_norm, void* workspace,
+                                     size_t workspace_bytes, float* out, ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(n >= 0 && out && max_norm > 0.f && (n == 0 || grad));
+  if (workspace == nullptr || workspace_bytes < ghscn_grad_clip_workspace_bytes(n)) return GHSCN_E_WORKSPACE;
+  cudaStream_t stream = ghscn::as_stream(stream_);
+  float* partial = static_cast<float*>(workspace);
+  ghscn::sumsq_partial_kernel<<<ghscn::kClipCtas, 256, 0, stream>>>(grad, n, partial);
+  ghscn::clip_coef_kernel<<<1, 256, 0, stream>>>(partial, ghscn::kClipCtas, max_norm, out);
+  GHSCN_LAUNCH_CHECK_N(2);
+  return GHSCN_OK;
+}
+
+extern "C" int ghscn_adamw_step_scaled(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                       float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
+                                       const float* grad_scale, ghscn_stream_t stream_) {
   GHSCN_REQUIRE(n >= 0 && step && (n == 0 || (param && grad && exp_avg && exp_avg_sq)));
   cudaStream_t stream = ghscn::as_stream(stream_);
   if (n > 0) {
     const int64_t blocks = ghscn::ceil_div<int64_t>(n, 256 * 4), cap = (int64_t)ghscn::kNumSMs * 8;
     ghscn::adamw_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(
-        param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step);
+        param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale);
   }
   ghscn::adamw_bump_kernel<<<1, 1, 0, stream>>>(step);
   GHSCN_LAUNCH_CHECK_N(n > 0 ? 2 : 1);
   return GHSCN_OK;
+}
+
+extern "C" int ghscn_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
+                                ghscn_stream_t stream_) {
+  return ghscn_adamw_step_scaled(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step,
+                                 nullptr, stream_);
 }

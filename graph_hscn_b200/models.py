@@ -114,9 +114,11 @@ class SCN(nn.Module):
         return torch.softmax(s, dim=-1), mc_loss, o_loss, adj
 
     def forward_batched(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor], batch: Tensor,
-                        losses_tensor: bool = False):
+                        losses_tensor: bool = False, num_graphs: Optional[int] = None):
         """Throughput form: the whole `batch`/`ptr` mini-batch in one launch (losses are batch means).
-        -> (s, mincut_loss, ortho_loss), or (s, losses[2]) with `losses_tensor` (CUDA operator set only)."""
+        -> (s, mincut_loss, ortho_loss), or (s, losses[2]) with `losses_tensor` (CUDA operator set only).
+        `num_graphs` restricts the losses to the first that many graphs (trailing padding graphs of a bucketed
+        batch, train.GraphHSCNStep; CUDA operator set only)."""
         o = self.ops
         if self._fusable and self.fuse:
             s = self.logits(x, edge_index, edge_weight)
@@ -124,10 +126,12 @@ class SCN(nn.Module):
         else:
             h = self.mp(x, edge_index, edge_weight)
             s = self.mlp(h)
+        kw = {} if num_graphs is None else {"num_graphs": num_graphs}
         if losses_tensor:
-            _, _, both = o.mincut_pool_ragged(h, edge_index, s, batch, want_out=False, want_adj=False, losses_tensor=True)
+            _, _, both = o.mincut_pool_ragged(h, edge_index, s, batch, want_out=False, want_adj=False,
+                                              losses_tensor=True, **kw)
             return s, both
-        _, _, mc_loss, o_loss = o.mincut_pool_ragged(h, edge_index, s, batch, want_out=False, want_adj=False)
+        _, _, mc_loss, o_loss = o.mincut_pool_ragged(h, edge_index, s, batch, want_out=False, want_adj=False, **kw)
         return s, mc_loss, o_loss
 
 
@@ -174,7 +178,11 @@ class HSCN(nn.Module):
         for conv in self.convs:
             if hasattr(conv, "defer_join"):
                 conv.defer_join = True
-            out = conv(x_dict, edge_index_dict)
+            try:
+                out = conv(x_dict, edge_index_dict)
+            finally:
+                if hasattr(conv, "defer_join"):
+                    conv.defer_join = False
             streams = getattr(conv, "last_streams", None)
             if streams is not None and main is None:
                 main = torch.cuda.current_stream()

@@ -136,6 +136,7 @@ def _spmm_backward(ctx, dy):
         side.wait_stream(main)
         with torch.cuda.stream(side):
             dbias = colsum(dy)
+        dbias.record_stream(main)           # allocated on the auxiliary stream, consumed on the caller's
     if ctx.needs_input_grad[6]:
         dx = spmm_raw(rowptr_t, col_t, w_t, dy, None, rowptr_t.numel() - 1, False)
     if ctx.w_needs_grad:
@@ -400,6 +401,7 @@ class GatPoolInputWidth(torch.autograd.Function):
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     a_dst = row_dot(x_dst, att_dst @ w_dst)
+                a_dst.record_stream(main)
             else:
                 a_dst = row_dot(x_dst, att_dst @ w_dst)
         else:

@@ -12,7 +12,8 @@ import sys
 import types
 
 from ..data import Batch, Data, DataLoader, HeteroBatch, HeteroData
-from . import functional, nn
+from . import _device, functional, nn
+from ._device import auto_device, set_auto_device
 from .functional import (SparseAdj, dense_mincut_pool, gcn_norm, global_add_pool, global_mean_pool,
                          mincut_pool_ragged, scatter, scatter_add, scatter_mean, scatter_sum, scn_logits_fused,
                          to_dense_adj)
@@ -20,7 +21,7 @@ from .nn import (GATConv, GCNConv, GINConv, GraphConv, HeteroConv, Linear, Messa
 
 __all__ = ["GATConv", "GCNConv", "GINConv", "GraphConv", "HeteroConv", "Linear", "MessagePassing", "Sequential",
            "dense_mincut_pool", "gcn_norm", "global_add_pool", "global_mean_pool", "mincut_pool_ragged", "scatter",
-           "scatter_add", "scatter_mean", "scatter_sum", "to_dense_adj", "SparseAdj", "install", "namespace"]
+           "scatter_add", "scatter_mean", "scatter_sum", "to_dense_adj", "SparseAdj", "install", "namespace", "set_auto_device", "auto_device"]
 
 
 def namespace() -> types.SimpleNamespace:
@@ -67,8 +68,13 @@ def build_modules(ns: types.SimpleNamespace, data_mod=None) -> dict:
             "torch_geometric.loader": loader, "torch_scatter": scatter_mod}
 
 
-def install(ns: types.SimpleNamespace = None) -> None:
-    """Make `import torch_geometric...` / `import torch_scatter` resolve to this package."""
+def install(ns: types.SimpleNamespace = None, auto_device: bool = True) -> None:
+    """Make `import torch_geometric...` / `import torch_scatter` resolve to this package.  `auto_device` (default on
+    for the drop-in route) lets the operators accept the CPU tensors the reference hands them at
+    train/train_clustering.py:37-43 (gcn_norm before `.to(device)`) and on its MPNN path (train/train.py:78-81):
+    they are staged to the GPU, computed there and returned on the input's device (pyg/_device.py)."""
+    if ns is None:
+        set_auto_device(auto_device)
     ns = ns or namespace()
     if not hasattr(ns, "scatter"):
         ns.scatter, ns.scatter_add = scatter, scatter_add

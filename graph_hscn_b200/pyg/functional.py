@@ -17,6 +17,7 @@ from torch import Tensor
 
 from .. import ops
 from .._lib import lib
+from . import _device
 from ..structure import (GraphStructure, Segments, _capturing, _p, _require_cuda, _stream, current_hints,
                          structure_cache)
 
@@ -29,7 +30,17 @@ def gcn_norm(edge_index: Tensor, edge_weight: Optional[Tensor] = None, num_nodes
              dtype: Optional[torch.dtype] = None) -> Tuple[Tensor, Tensor]:
     """Returns PyG's (edge_index', edge_weight') in PyG's edge order (original non-loop edges, then the
     N appended loops).  The layers never call this -- they consume the CSR directly -- it exists for the
-    reference's direct call (train_clustering.py:37) and is computed by the same kernels."""
+    reference's direct call (train_clustering.py:37) and is computed by the same kernels.  The reference calls it
+    on CPU tensors (before `data.to(device)`): with auto-device staging they are copied to the GPU, the kernels run
+    there and both results come back on the input's device (pyg/_device.py)."""
+    dev, back = _device.plan(edge_index, edge_weight)
+    if dev is not None:
+        edge_index, edge_weight = _device.index_to_dev(edge_index, dev), _device.to_dev(edge_weight, dev)
+    return _device.back_to(_gcn_norm_cuda(edge_index, edge_weight, num_nodes, improved, add_self_loops, flow), back)
+
+
+def _gcn_norm_cuda(edge_index: Tensor, edge_weight: Optional[Tensor], num_nodes: Optional[int], improved: bool,
+                   add_self_loops: bool, flow: str) -> Tuple[Tensor, Tensor]:
     _require_cuda(edge_index, edge_weight)
     if flow != "source_to_target":
         raise NotImplementedError("only flow='source_to_target' is on the reference's path")
@@ -79,6 +90,10 @@ class SparseAdj:
 
     def __init__(self, edge_index: Tensor, batch: Optional[Tensor], edge_attr: Optional[Tensor],
                  max_num_nodes: Optional[int]):
+        dev, self._back = _device.plan(edge_index, batch, edge_attr)
+        if dev is not None:
+            edge_index, batch = _device.index_to_dev(edge_index, dev), _device.index_to_dev(batch, dev)
+            edge_attr = _device.to_dev(edge_attr, dev)
         self.edge_index, self.batch, self.edge_attr, self.max_num_nodes = edge_index, batch, edge_attr, max_num_nodes
         self._dense: Optional[Tensor] = None
 
@@ -103,7 +118,7 @@ class SparseAdj:
             keep = (i1 < n_max) & (i2 < n_max)
             flat = torch.zeros(B * n_max * n_max, dtype=val.dtype, device=ei.device)
             flat.index_add_(0, (i0 * n_max * n_max + i1 * n_max + i2)[keep], val[keep])
-            self._dense = flat.view(B, n_max, n_max)
+            self._dense = _device.back_to(flat.view(B, n_max, n_max), self._back)
         return self._dense
 
     def size(self, dim: Optional[int] = None):
@@ -125,7 +140,6 @@ class SparseAdj:
 
 def to_dense_adj(edge_index: Tensor, batch: Optional[Tensor] = None, edge_attr: Optional[Tensor] = None,
                  max_num_nodes: Optional[int] = None) -> SparseAdj:
-    _require_cuda(edge_index)
     return SparseAdj(edge_index, batch, edge_attr, max_num_nodes)
 
 
@@ -149,14 +163,18 @@ def _ptr_for(batch: Optional[Tensor], num_nodes: int, device) -> Tuple[Tensor, i
 
 def mincut_pool_ragged(x: Tensor, edge_index: Tensor, s: Tensor, batch: Optional[Tensor] = None,
                        edge_attr: Optional[Tensor] = None, temp: float = 1.0, want_out: bool = True,
-                       want_adj: bool = True, losses_tensor: bool = False):
+                       want_adj: bool = True, losses_tensor: bool = False, num_graphs: Optional[int] = None):
     """Batched MinCUT pool on the ragged (`batch`/`ptr`) layout: one CTA per graph, no [B,n,n] tensor.
     Equivalent to to_dense_batch + to_dense_adj(batch) + dense_mincut_pool(mask) in PyG.
     -> (out, out_adj, mincut_loss, ortho_loss), or with `losses_tensor` (out, out_adj, losses[2]) so that a caller
-    that only adds the two losses does not pay for two select/scatter round trips in autograd."""
+    that only adds the two losses does not pay for two select/scatter round trips in autograd.
+    `num_graphs` pools only the first that many graphs of the batch (the rest -- trailing padding graphs of a
+    bucketed batch -- get no output rows, no share of the loss means and zero gradients)."""
     _require_cuda(x, edge_index, s)
     N = s.size(0)
     ptr, B, max_nodes = _ptr_for(batch, N, s.device)
+    if num_graphs is not None and num_graphs < B:
+        ptr, B = ptr[:num_graphs + 1], int(num_graphs)
     st = structure_cache().graph(edge_index, N, N, False)
     rows, cols = st.by_src, st.by_dst   # rows of A are edge_index[0]
     val = val_t = None
@@ -174,6 +192,14 @@ def mincut_pool_ragged(x: Tensor, edge_index: Tensor, s: Tensor, batch: Optional
 def dense_mincut_pool(x: Tensor, adj, s: Tensor, mask: Optional[Tensor] = None, temp: float = 1.0
                       ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """PyG signature and returns: (out [B,K,H], out_adj [B,K,K], mincut_loss, ortho_loss)."""
+    dev, back = _device.plan(x, s, adj if isinstance(adj, Tensor) else adj.edge_index, mask)
+    if dev is not None:
+        x, s, mask = _device.to_dev(x, dev), _device.to_dev(s, dev), _device.to_dev(mask, dev)
+        adj = _device.to_dev(adj, dev)          # a SparseAdj staged its own tensors when it was built
+    return _device.back_to(_dense_mincut_pool_cuda(x, adj, s, mask, temp), back)
+
+
+def _dense_mincut_pool_cuda(x: Tensor, adj, s: Tensor, mask: Optional[Tensor], temp: float):
     _require_cuda(x, s)
     if isinstance(adj, SparseAdj) and x.dim() == 2 and mask is None:
         return mincut_pool_ragged(x, adj.edge_index, s, adj.batch, adj.edge_attr, temp)
@@ -210,6 +236,9 @@ def dense_mincut_pool(x: Tensor, adj, s: Tensor, mask: Optional[Tensor] = None, 
 # readout  
 # ---------------------------------------------------------------------------------------------
 def _segment(x: Tensor, index: Tensor, size: Optional[int], mean: bool) -> Tensor:
+    dev, back = _device.plan(x, index)
+    if dev is not None:
+        return _device.back_to(_segment(_device.to_dev(x, dev), _device.index_to_dev(index, dev), size, mean), back)
     _require_cuda(x, index)
     squeeze = x.dim() == 1
     x2 = x.unsqueeze(1) if squeeze else x

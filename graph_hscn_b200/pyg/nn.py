@@ -7,7 +7,10 @@ state_dicts interchange with a real PyG install:
   GraphConv lin_rel.{weight,bias}, lin_root.weight                 model/hscn.py:32-34,40-41
   GATConv   lin_src/lin_dst.weight, att_src/att_dst [1,H,C], bias  model/hscn.py:85-87
   HeteroConv convs.<src__rel__dst>.*                               model/hscn.py:83-96,109
-Dense GEMMs (x @ W^T) stay on cuBLAS fp32 through F.linear (TF32 off: parity is 1e-5).
+Dense projections (x @ W^T) go through gemm.linear: hand-written tcgen05 3xTF32 kernels for the h x h layers,
+streaming kernels for the tall-skinny ones, fp32 library GEMM otherwise (TF32 off: parity is 1e-5).
+CPU tensors / CPU-resident parameters are staged to the GPU when auto-device staging is on (pyg/_device.py:
+the reference's MPNN path, train/train.py:78-81, never moves its model or batches); otherwise they raise.
 """
 from __future__ import annotations
 
@@ -26,6 +29,7 @@ from torch.nn.parameter import UninitializedParameter
 
 from .. import gemm, ops
 from ..structure import _require_cuda, structure_cache
+from . import _device
 
 
 def glorot(t: Optional[Tensor]) -> None:
@@ -74,6 +78,10 @@ class Linear(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         self.materialize(x.size(-1), x.device)
+        dev, back = _device.plan(x, self.weight)
+        if dev is not None:
+            y = gemm.linear(_device.to_dev(x, dev), _device.to_dev(self.weight, dev), _device.to_dev(self.bias, dev))
+            return _device.back_to(y, back)
         return gemm.linear(x, self.weight, self.bias)
 
     def extra_repr(self) -> str:
@@ -130,10 +138,16 @@ class GCNConv(MessagePassing):
             nn.init.zeros_(self.bias)
 
     def forward(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor] = None) -> Tensor:
+        dev, back = _device.plan(x, edge_index, edge_weight, self.bias)
+        bias = self.bias
+        if dev is not None:
+            x, edge_weight, bias = _device.to_dev(x, dev), _device.to_dev(edge_weight, dev), _device.to_dev(bias, dev)
+            edge_index = _device.index_to_dev(edge_index, dev)
         h = self.lin(x)
-        return _aggregate(h, edge_index, edge_weight, x.size(0), normalize=self.normalize,
-                          improved=self.improved, add_self_loops=self.add_self_loops and self.normalize,
-                          bias=self.bias, relu=self.fuse_relu)
+        out = _aggregate(h, edge_index, edge_weight, x.size(0), normalize=self.normalize,
+                         improved=self.improved, add_self_loops=self.add_self_loops and self.normalize,
+                         bias=bias, relu=self.fuse_relu)
+        return _device.back_to(out, back)
 
 
 class GraphConv(MessagePassing):
@@ -153,11 +167,15 @@ class GraphConv(MessagePassing):
     def forward(self, x, edge_index: Tensor, edge_weight: Optional[Tensor] = None, size=None) -> Tensor:
         if isinstance(x, Tensor):
             x = (x, x)
+        dev, back = _device.plan(x[0], x[1], edge_index, edge_weight)
+        if dev is not None:
+            x = (_device.to_dev(x[0], dev), _device.to_dev(x[1], dev))
+            edge_index, edge_weight = _device.index_to_dev(edge_index, dev), _device.to_dev(edge_weight, dev)
         n_dst = x[1].size(0) if x[1] is not None else (size[1] if size is not None else x[0].size(0))
         out = self.lin_rel(_aggregate(x[0], edge_index, edge_weight, n_dst))
         if x[1] is not None:
             out = out + self.lin_root(x[1])
-        return out
+        return _device.back_to(out, back)
 
 
 class GINConv(MessagePassing):
@@ -175,10 +193,14 @@ class GINConv(MessagePassing):
     def forward(self, x, edge_index: Tensor, size=None) -> Tensor:
         if isinstance(x, Tensor):
             x = (x, x)
+        dev, back = _device.plan(x[0], x[1], edge_index)
+        if dev is not None:
+            x = (_device.to_dev(x[0], dev), _device.to_dev(x[1], dev))
+            edge_index = _device.index_to_dev(edge_index, dev)
         out = _aggregate(x[0], edge_index, None, x[1].size(0))
         if x[1] is not None:
-            out = out + (1 + self.eps) * x[1]
-        return self.nn(out)
+            out = out + (1 + _device.to_dev(self.eps, out.device)) * x[1]
+        return _device.back_to(self.nn(out), back)
 
 
 class GATConv(MessagePassing):
@@ -216,6 +238,25 @@ class GATConv(MessagePassing):
             x_src = x_dst = x
         else:
             x_src, x_dst = x
+        dev, back = _device.plan(x_src, x_dst, edge_index, self.att_src)
+        if dev is not None:
+            return _device.back_to(self._forward_staged(x, x_src, x_dst, edge_index, size, dev), back)
+        return self._forward_cuda(x_src, x_dst, edge_index, size, None)
+
+    def _params(self, dev=None):
+        ls, ld = self.lin_src.weight, self.lin_dst.weight
+        p = dict(w_src=ls, w_dst=ld, att_src=self.att_src, att_dst=self.att_dst, bias=self.bias)
+        return p if dev is None else {k: _device.to_dev(v, dev) for k, v in p.items()}
+
+    def _forward_staged(self, x, x_src, x_dst, edge_index, size, dev):
+        self.lin_src.materialize(x_src.size(-1), x_src.device)
+        if x_dst is not None:
+            self.lin_dst.materialize(x_dst.size(-1), x_dst.device)
+        xs = _device.to_dev(x_src, dev)
+        xd = xs if x_dst is x_src else _device.to_dev(x_dst, dev)
+        return self._forward_cuda(xs, xd, _device.index_to_dev(edge_index, dev), size, self._params(dev))
+
+    def _forward_cuda(self, x_src, x_dst, edge_index, size, prm) -> Tensor:
         _require_cuda(x_src, edge_index)
         if x_src.dtype != torch.float32:
             x_src = x_src.float()
@@ -224,6 +265,9 @@ class GATConv(MessagePassing):
             if x_dst.dtype != torch.float32:
                 x_dst = x_dst.float()
             self.lin_dst.materialize(x_dst.size(-1), x_dst.device)
+        if prm is None:
+            prm = self._params()
+        w_src, w_dst, att_src, att_dst, bias = (prm[k] for k in ("w_src", "w_dst", "att_src", "att_dst", "bias"))
         n_src = x_src.size(0)
         n_dst = x_dst.size(0) if x_dst is not None else (size[1] if size is not None else n_src)
         if self.add_self_loops and n_src != n_dst:
@@ -233,8 +277,8 @@ class GATConv(MessagePassing):
         # attention scores from x (W^T att) and the pooled sum at the input width: no [N,F]x[F,H] projection
         if self.heads == 1:
             return ops.GatPoolInputWidth.apply(
-                x_src, x_dst, self.lin_src.weight, self.lin_dst.weight if x_dst is not None else None,
-                self.att_src.view(-1), self.att_dst.view(-1), self.bias, float(self.negative_slope),
+                x_src, x_dst, w_src, w_dst if x_dst is not None else None,
+                att_src.view(-1), att_dst.view(-1), bias, float(self.negative_slope),
                 d.rowptr, d.col, s.rowptr, s.col, st.slot_map_t)
         # heads > 1 (never built by the reference's configs): every head is the single-head operator
         # on its own row block of lin_src / lin_dst and its own attention vectors, over the same structure
@@ -242,11 +286,11 @@ class GATConv(MessagePassing):
         for h in range(self.heads):
             rows = slice(h * C, (h + 1) * C)
             outs.append(ops.GatPoolInputWidth.apply(
-                x_src, x_dst, self.lin_src.weight[rows], self.lin_dst.weight[rows] if x_dst is not None else None,
-                self.att_src[0, h], self.att_dst[0, h], None, float(self.negative_slope),
+                x_src, x_dst, w_src[rows], w_dst[rows] if x_dst is not None else None,
+                att_src[0, h], att_dst[0, h], None, float(self.negative_slope),
                 d.rowptr, d.col, s.rowptr, s.col, st.slot_map_t))
         out = torch.cat(outs, dim=1) if self.concat else torch.stack(outs, dim=1).mean(dim=1)
-        return out + self.bias if self.bias is not None else out
+        return out + bias if bias is not None else out
 
 
 PARALLEL_BRANCHES = os.environ.get("GHSCN_PARALLEL_BRANCHES", "1") != "0"
@@ -257,6 +301,31 @@ _SIDE_STREAMS: Dict[Tuple[str, int], List["torch.cuda.Stream"]] = {}
 def branch_stream(device: torch.device, index: int = 0) -> "torch.cuda.Stream":
     """The side stream HeteroConv uses for its (index + 2)-th destination type on `device`."""
     return _side_streams(device, index + 1)[index]
+
+
+_FORKED: Dict[Tuple[str, int], List["torch.cuda.Stream"]] = {}
+
+
+def _forked(device: torch.device, stream: "torch.cuda.Stream") -> None:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    lst = _FORKED.setdefault(key, [])
+    if all(s is not stream for s in lst):
+        lst.append(stream)
+
+
+def take_forked_streams(device: torch.device) -> List["torch.cuda.Stream"]:
+    """Side streams HeteroConv has forked on `device` since the last call (and forgets them).  A caller that defers
+    the joins (train.GraphHSCNStep) waits for exactly these at the end of its step -- inside a CUDA-graph capture
+    only streams that took part in the capture may be waited for."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    return _FORKED.pop(key, [])
+
+
+def _uses(t, stream) -> None:
+    """Tells the caching allocator that `t` is read on `stream` (a no-op for the stream that allocated it): the block
+    is not recycled under the reader, eagerly (event-deferred free) or inside a capture (free deferred to its end)."""
+    if isinstance(t, Tensor) and t.is_cuda:
+        t.record_stream(stream)
 
 
 def _side_streams(device: torch.device, n: int):
@@ -299,6 +368,7 @@ class HeteroConv(nn.Module):
             streams = {dsts[0]: main}
             for i, dst in enumerate(dsts[1:]):
                 sides[i].wait_stream(main)
+                _forked(main.device, sides[i])
                 streams[dst] = sides[i]
         # Relations that share a destination type (v->v and l->v) are independent up to the final sum: the first one
         # runs on the destination's stream, every further one on a stream of its own that waits for the caller's
@@ -317,6 +387,7 @@ class HeteroConv(nn.Module):
                 r = _side_streams(main.device, extra + 1)[extra]
                 extra += 1
                 r.wait_stream(main)
+                _forked(main.device, r)
                 if streams[dst] is not main:
                     r.wait_stream(streams[dst])
                 rel_streams[edge_type] = r
@@ -327,11 +398,16 @@ class HeteroConv(nn.Module):
             if key not in self.convs:
                 continue
             conv = self.convs[key]
+            if streams is not None:          # inputs produced on another stream are read on this relation's stream
+                _uses(x_dict[src], rel_streams[edge_type])
+                _uses(x_dict[dst], rel_streams[edge_type])
             with torch.cuda.stream(rel_streams[edge_type]) if streams is not None else contextlib.nullcontext():
                 if src == dst:
                     out = conv(x_dict[src], edge_index)
                 else:
                     out = conv((x_dict[src], x_dict[dst]), edge_index)
+            if streams is not None:
+                _uses(out, streams[dst])     # summed on the destination type's stream
             outs[dst].append(out)
         result: Dict[str, Tensor] = {}
         for key, xs in outs.items():

@@ -98,6 +98,8 @@ def build_csr(key: Tensor, other: Tensor, num_rows: int, add_self_loops: bool = 
 class GraphStructure:
     """Both orientations of one relation's edge set plus cached per-slot weights."""
 
+    MAX_WEIGHT_SETS = 8      # distinct (edge_weight tensor, normalize, improved) combinations kept per structure
+
     def __init__(self, edge_index: Tensor, num_src: int, num_dst: int, add_self_loops: bool = False):
         _require_cuda(edge_index)
         if add_self_loops and num_src != num_dst:
@@ -107,7 +109,7 @@ class GraphStructure:
         self.add_self_loops = bool(add_self_loops)
         self._by_dst: Optional[CSR] = None
         self._by_src: Optional[CSR] = None
-        self._weights: Dict[tuple, Tuple[Optional[Tensor], Optional[Tensor], Optional[Tensor]]] = {}
+        self._weights: "OrderedDict[tuple, dict]" = OrderedDict()    # small LRU: entries pin w / w_t / dis
         self._slot_map_t: Optional[Tensor] = None
         self._keep: list = []
         self._parent: Optional["GraphStructure"] = None   # set by StructureCache.alias
@@ -228,6 +230,10 @@ class GraphStructure:
                        d.num_edges, d.num_rows, int(normalize), 1, _p(w), st)
                 ent = dict(w=w, w_t=None, dis=dis, lw=lw, ew=edge_weight, unit=False)
             self._weights[key] = ent
+            while len(self._weights) > self.MAX_WEIGHT_SETS:
+                self._weights.popitem(last=False)
+        else:
+            self._weights.move_to_end(key)
         if need_transpose and not ent["unit"] and ent["w_t"] is None:
             s = self.by_src
             w_t = torch.empty(s.num_items, dtype=torch.float32, device=dev)
@@ -255,6 +261,7 @@ class EdgeBlocks:
     max_nodes: int                 # max nodes of any graph
     max_edges: int                 # max edges of any graph
     status: Tensor                 # int32 [1], non-zero if a kernel found the promise broken
+    index: Optional[Tensor] = None # the edge list the promise was made for: pinned, so its address cannot be recycled
 
 
 def edge_blocks_from_batch(edge_index: Tensor, batch: Tensor, num_graphs: Optional[int] = None
@@ -289,12 +296,21 @@ class StructureCache:
             self._status[idx] = torch.zeros(1, dtype=torch.int32, device=device)
         return self._status[idx]
 
+    def check_blocked_status(self, device) -> None:
+        """Host read of the flag (one sync; never inside a capture): raises when a per-graph CSR build found its
+        promise broken -- the CSR slots of that batch were left unwritten, nothing computed from them is valid."""
+        flag = int(self.blocked_status(device).item())
+        if flag:
+            self.blocked_status(device).zero_()
+            raise RuntimeError(f"ghscn_csr_build_blocked: the block-diagonal / graph-major promise registered for an "
+                               f"edge list did not hold (status {flag}); rebuild the batch without register_blocks")
+
     def register_blocks(self, edge_index: Tensor, ptr: Tensor, num_graphs: int, max_nodes: int, max_edges: int
                         ) -> EdgeBlocks:
         """Promise that `edge_index` is the collated edge list of the graphs delimited by `ptr`: its CSRs are then
         built by the per-graph kernel (one launch) instead of the radix passes."""
         b = EdgeBlocks(ptr if ptr.dtype == torch.int32 else ptr.to(torch.int32), int(num_graphs), int(max_nodes),
-                       int(max_edges), self.blocked_status(edge_index.device))
+                       int(max_edges), self.blocked_status(edge_index.device), edge_index)
         self._blocks[self._key(edge_index)] = b
         while len(self._blocks) > self.capacity:
             self._blocks.popitem(last=False)
@@ -315,7 +331,7 @@ class StructureCache:
         if st is None:
             st = GraphStructure(edge_index, num_src, num_dst, add_self_loops)
             if not add_self_loops:
-                st._blocks = self._blocks.get(self._key(edge_index))
+                st._blocks = self._blocks.get(self._key(edge_index))     # the entry pins its tensor: same key == same tensor
             if add_self_loops and self._known_loop_free(edge_index):
                 st._plain = self.graph(edge_index, num_src, num_dst, False)
             self._graphs[key] = st

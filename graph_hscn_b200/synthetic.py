@@ -72,6 +72,30 @@ def peptides_graphs(num_graphs: int, seed: int = 1234, task: str = "func",
     return out
 
 
+def _peptide_size(rng: np.random.Generator) -> int:
+    return int(np.clip(np.rint(rng.normal(150.94, 60.0)), 8, 444))
+
+
+def peptides_graph_size(seed: int, index: int) -> int:
+    """Node count of `peptides_graph(seed, index)` without building it (data-parallel ranks balance a global batch
+    by size and then generate only their own graphs)."""
+    return _peptide_size(np.random.default_rng([int(seed), int(index)]))
+
+
+def peptides_graph(seed: int, index: int, task: str = "func") -> Data:
+    """Graph `index` of the global batch `seed`: same distribution as `peptides_graphs`, but every graph has its own
+    random stream, so any subset can be generated independently and identically on every rank."""
+    rng = np.random.default_rng([int(seed), int(index)])
+    n = _peptide_size(rng)
+    ei = _peptide_edges(n, rng)
+    x = np.stack([rng.integers(0, r, size=n) for r in ATOM_FEATURE_RANGES], axis=1).astype(np.int64)
+    if task == "func":
+        y = (rng.random((1, 10)) < 0.15).astype(np.float32)
+    else:
+        y = rng.normal(0.0, 1.0, size=(1, 11)).astype(np.float32)
+    return Data(x=torch.from_numpy(x), edge_index=torch.from_numpy(ei), y=torch.from_numpy(y))
+
+
 def vocsp_graphs(num_graphs: int, seed: int = 1238, num_classes: int = 21) -> List[Data]:
     """PascalVOC-SP-shaped graphs: n in [395,500], ~2.83 links/node within index distance 16, symmetrised."""
     rng = np.random.default_rng(seed)

@@ -1,4 +1,4 @@
-"""Graph-HSCN training step on one B200 (optionally CUDA-graph captured) and its data-parallel form.
+"""Graph-HSCN training step on one B200 (CUDA-graph captured per shape bucket) and its data-parallel form.
 
 One step = one pass of the hot path over one `batch`/`ptr` mini-batch (BASELINE config #2):
     1. SCN stage   -- gcn_norm(add_self_loops) -> GraphConv stack -> logits -> fused MinCUT losses,
@@ -6,14 +6,25 @@ One step = one pass of the hot path over one `batch`/`ptr` mini-batch (BASELINE 
     2. assignment  -- SCN forward with the updated weights, softmax, first-max cluster id
                       (train_clustering.py:57-69) and on-device virtual-node construction
                       (loader/hetero_data.py:42-87)
-    3. HSCN stage  -- 3-relation HeteroConv stack, mean readout, 2 linears, loss, backward, AdamW step
-                      (train/train.py:73-95)
-Data parallelism: graphs are independent, so ranks take disjoint contiguous graph
-ranges and exchange nothing in forward/backward; one NCCL all-reduce of a single flat fp32 gradient
-buffer per model per step averages the gradients (the reference has no distributed code).
+    3. HSCN stage  -- 3-relation HeteroConv stack, mean readout, 2 linears, loss, backward,
+                      [clip_grad_norm], AdamW step every `batch_accumulation` batches (train/train.py:73-95)
+
+Variable-shape batches (train/train.py:73 iterates a DataLoader): a CUDA graph needs static shapes, so every batch is
+padded into a *bucket* (`BucketPolicy`): node count rounded up to a multiple of `node_step`, edge count to a multiple
+of `edge_step`.  The padding is `D` trailing DUMMY GRAPHS -- real, well-formed graphs (zero features, zero labels,
+a chain of edges among the pad nodes) appended after the B real ones -- so every structure kernel sees an ordinary
+block-diagonal, graph-major batch of B + D graphs.  The losses look at the first B graphs only (MinCUT runs on
+`ptr[:B+1]`; the task loss on `pred[:B]`), so the dummy rows carry exactly zero gradient and no real row ever reads
+them.  One CUDA graph is captured per bucket on first use and replayed afterwards (`GraphHSCNStep.load/run`).
+
+Data parallelism: graphs are independent, so ranks take disjoint sets of graphs and exchange nothing
+in forward/backward; one NCCL all-reduce of a single flat fp32 gradient buffer per model per optimizer step sums the
+gradients, each rank's contribution weighted by its share of the global graph count (the reference has no
+distributed code).
 """
 from __future__ import annotations
 
+import math
 import os
 
 from dataclasses import dataclass
@@ -36,7 +47,8 @@ from .structure import capture_scope, edge_blocks_from_batch, structure_cache, s
 # ---------------------------------------------------------------------------------------------
 def shard_range(num_graphs: int, rank: int, world: int, weights: Optional[Sequence[int]] = None) -> Tuple[int, int]:
     """Contiguous graph range [lo, hi) of `rank`.  With `weights` (nodes or edges per graph) the cut points
-    balance the summed weight instead of the graph count (SURVEY 8e "balance by sum n_g")."""
+    balance the summed weight instead of the graph count (SURVEY 8e "balance by sum n_g"); the ranks then hold
+    different graph counts and must pass them to `FlatGradients.all_reduce_mean(local_graphs=, global_graphs=)`."""
     if weights is None:
         base, rem = divmod(num_graphs, world)
         lo = rank * base + min(rank, rem)
@@ -50,6 +62,19 @@ def shard_range(num_graphs: int, rank: int, world: int, weights: Optional[Sequen
     for i in range(1, len(cuts)):
         cuts[i] = max(cuts[i], cuts[i - 1])
     return cuts[rank], cuts[rank + 1]
+
+
+def balanced_partition(sizes: Sequence[int], world: int) -> List[List[int]]:
+    """Splits graph indices into `world` groups of EQUAL COUNT (up to one) and nearly equal summed size: graphs are
+    exchangeable inside a mini-batch (every loss is a mean over graphs), so any equal-count split is a valid
+    data-parallel sharding, and equal counts keep the mean of the rank means equal to the batch mean.  Largest graphs
+    first, dealt in snake order (0..W-1, W-1..0, ...); each group is returned in ascending index order."""
+    order = sorted(range(len(sizes)), key=lambda i: (-int(sizes[i]), i))
+    groups: List[List[int]] = [[] for _ in range(world)]
+    for pos, idx in enumerate(order):
+        rnd, k = divmod(pos, world)
+        groups[k if rnd % 2 == 0 else world - 1 - k].append(idx)
+    return [sorted(g) for g in groups]
 
 
 class FlatGradients:
@@ -75,13 +100,17 @@ class FlatGradients:
     def zero(self) -> None:
         self.flat.zero_()
 
-    def backward_into(self, loss: Tensor) -> None:
+    def backward_into(self, loss: Tensor, accumulate: bool = False) -> None:
         """`loss.backward()` for the live parameters, with the gradients written straight into the flat buffer: the
         autograd engine hands the finished gradients over (`torch.autograd.grad`) and ONE multi-tensor copy places them,
         instead of one `grad += g` kernel per parameter interleaved with the backward chain (and no zero fill before).
-        Every value is the one `backward()` would have accumulated onto a zeroed buffer."""
+        Every value is the one `backward()` would have accumulated onto a zeroed buffer; with `accumulate` the
+        gradients are added to what the buffer holds (train/train.py:87-89, `batch_accumulation` > 1)."""
         grads = torch.autograd.grad(loss, self.params)
-        torch._foreach_copy_([p.grad for p in self.params], list(grads))
+        if accumulate:
+            torch._foreach_add_([p.grad for p in self.params], list(grads))
+        else:
+            torch._foreach_copy_([p.grad for p in self.params], list(grads))
 
     def flatten_parameters(self) -> Tensor:
         """Re-home the live parameters as views of ONE flat fp32 leaf whose .grad is the flat gradient buffer:
@@ -99,13 +128,19 @@ class FlatGradients:
         self.flat_param = flat_p
         return flat_p
 
-    def all_reduce_mean(self, world: Optional[int] = None, group=None) -> None:
+    def all_reduce_mean(self, world: Optional[int] = None, group=None, local_graphs: Optional[int] = None,
+                        global_graphs: Optional[int] = None) -> None:
+        """Gradient of the GLOBAL batch mean from the per-rank batch-mean gradients.  Every rank's loss is a mean over
+        its own graphs, so its gradient is weighted by local_graphs / global_graphs before the SUM all-reduce; with
+        equal shards (the default, counts omitted) that weight is 1 / world."""
         if not (dist.is_available() and dist.is_initialized()):
             return
         world = world or dist.get_world_size(group)
         if world == 1:
             return
-        if os.environ.get("GHSCN_SKIP_ALLREDUCE") == "1":      # timing experiments only: WRONG gradients
+        if local_graphs is not None and global_graphs:
+            self.flat.mul_(float(local_graphs) / float(global_graphs))
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             return
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         self.flat.mul_(1.0 / world)
@@ -113,7 +148,10 @@ class FlatGradients:
 
 class FlatAdamW:
     """torch.optim.AdamW semantics on one flat parameter buffer, one kernel per step (ghscn_adamw_step); the step
-    counter lives on the device, so `step()` is CUDA-graph capturable."""
+    counter lives on the device, so `step()` is CUDA-graph capturable.  `clip_grad_norm(max_norm)` is
+    `nn.utils.clip_grad_norm_` (train/train.py:92-93) over the same flat buffer: a fixed-order two-stage sum of
+    squares leaves the clip coefficient in a device scalar that the next `step()` multiplies into every gradient as it
+    reads it, instead of one norm kernel per parameter, a stack, and one multiply per parameter."""
 
     def __init__(self, flat_param: Tensor, flat_grad: Tensor, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2):
@@ -123,13 +161,32 @@ class FlatAdamW:
         self.exp_avg_sq = torch.zeros_like(flat_grad)
         self.step_count = torch.zeros(1, dtype=torch.float32, device=flat_grad.device)
         self.state = {0: {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count}}
+        self.clip = torch.ones(2, dtype=torch.float32, device=flat_grad.device)      # (total norm, clip coefficient)
+        self._clip_ws: Optional[Tensor] = None
+        self._use_clip = False
+
+    def clip_grad_norm(self, max_norm: float = 1.0) -> Tensor:
+        """-> device tensor [2] = (total 2-norm, coefficient min(1, max_norm / (norm + 1e-6))); applied by `step()`."""
+        from ._lib import lib
+        from .structure import _p, _stream
+        L = lib()
+        n = self.g.numel()
+        if self._clip_ws is None:
+            self._clip_ws = torch.empty(max(L.query("ghscn_grad_clip_workspace_bytes", n), 4), dtype=torch.uint8,
+                                        device=self.g.device)
+        L.call("ghscn_grad_clip_scale", _p(self.g), n, float(max_norm), _p(self._clip_ws), self._clip_ws.numel(),
+               _p(self.clip), _stream())
+        self._use_clip = True
+        return self.clip
 
     def step(self) -> None:
         from ._lib import lib
         from .structure import _p, _stream
-        lib().call("ghscn_adamw_step", _p(self.p), _p(self.g), _p(self.exp_avg), _p(self.exp_avg_sq), self.p.numel(),
-                   float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd),
-                   _p(self.step_count), _stream())
+        scale = self.clip[1:] if self._use_clip else None
+        lib().call("ghscn_adamw_step_scaled", _p(self.p), _p(self.g), _p(self.exp_avg), _p(self.exp_avg_sq),
+                   self.p.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                   float(self.wd), _p(self.step_count), _p(scale), _stream())
+        self._use_clip = False
 
     def zero_grad(self) -> None:
         self.g.zero_()
@@ -140,6 +197,172 @@ def live_parameter_names(module: nn.Module, loss: Tensor) -> List[str]:
     named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
     grads = torch.autograd.grad(loss, [p for _, p in named], allow_unused=True, retain_graph=False)
     return [n for (n, _), g in zip(named, grads) if g is not None]
+
+
+# ---------------------------------------------------------------------------------------------
+# shape buckets
+# ---------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class BucketPolicy:
+    """Static-shape buckets for variable-size mini-batches.  `max_*_per_graph` are dataset-level caps on one graph
+    (444 nodes / 906 directed edges for the Peptides shape); they bound the dummy graphs too, so the per-graph
+    kernels (blocked CSR, MinCUT) keep the shared-memory footprint they have on the real graphs."""
+    max_nodes_per_graph: int
+    max_edges_per_graph: int
+    node_step: int = 256
+    edge_step: int = 512
+    min_pad_nodes: int = 2          # a dummy graph needs two nodes to carry pad edges without self loops
+
+    @property
+    def eff_edge_step(self) -> int:
+        return max(1, min(self.edge_step, self.max_edges_per_graph))
+
+    @property
+    def dummy_graphs(self) -> int:
+        return max(1, math.ceil((self.node_step + self.min_pad_nodes - 1) / max(self.max_nodes_per_graph, 2)))
+
+    def bucket(self, num_nodes: int, num_edges: int) -> Tuple[int, int]:
+        n_cap = math.ceil((num_nodes + self.min_pad_nodes) / self.node_step) * self.node_step
+        es = self.eff_edge_step
+        return n_cap, math.ceil(num_edges / es) * es
+
+    @staticmethod
+    def for_batches(batches: Sequence[Batch], node_step: int = 256, edge_step: int = 512) -> "BucketPolicy":
+        """Caps measured over a set of collated batches (a stand-in for dataset statistics)."""
+        mn = max(int(b["max_nodes_per_graph"]) for b in batches)
+        me = 0
+        for b in batches:
+            if "max_edges_per_graph" in b:
+                me = max(me, int(b["max_edges_per_graph"]))
+            else:
+                me = max(me, int(torch.bincount(b.batch[b.edge_index[0]], minlength=int(b.num_graphs)).max()))
+        return BucketPolicy(max(mn, 2), max(me, 2), node_step, edge_step)
+
+
+@dataclass(frozen=True)
+class _Shape:
+    """Everything a captured graph bakes in."""
+    n_cap: int
+    e_cap: int
+    graphs: int                 # B real graphs
+    dummies: int                # D trailing dummy graphs
+    max_nodes: int
+    max_edges: int              # 0: no block-diagonal promise (general radix CSR path)
+    no_self_loops: bool
+
+
+class StagedBatch:
+    """One mini-batch packed for upload: x | edge_index | batch | y in ONE pinned host buffer (256-byte aligned
+    sub-ranges, padded to its bucket), so the per-step upload is a single host-to-device copy."""
+
+    def __init__(self, shape: _Shape, buf: Tensor, views: Dict[str, Tensor], num_nodes: int, num_edges: int):
+        self.shape, self.buf, self.views = shape, buf, views
+        self.num_nodes, self.num_edges = num_nodes, num_edges        # real (unpadded) sizes
+        self.device_copy: Optional[Tensor] = None                    # set by GraphHSCNStep.make_resident
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.buf.numel())
+
+
+def _layout(shape: _Shape, x_like: Tensor, y_like: Tensor) -> Tuple[Dict[str, tuple], int]:
+    """name -> (byte offset, dtype, shape) of the packed buffer; total bytes."""
+    bt = shape.graphs + shape.dummies
+    specs = {"x": (x_like.dtype, (shape.n_cap,) + tuple(x_like.shape[1:])),
+             "edge_index": (torch.int64, (2, shape.e_cap)),
+             "batch": (torch.int64, (shape.n_cap,)),
+             "y": (y_like.dtype, (bt,) + tuple(y_like.shape[1:]))}
+    out, total = {}, 0
+    for k, (dt, shp) in specs.items():
+        nbytes = int(torch.empty((), dtype=dt).element_size()) * int(math.prod(shp))
+        out[k] = (total, dt, shp)
+        total += (nbytes + 255) // 256 * 256
+    return out, max(total, 256)
+
+
+def _views(buf: Tensor, layout: Dict[str, tuple]) -> Dict[str, Tensor]:
+    out = {}
+    for k, (off, dt, shp) in layout.items():
+        nbytes = int(torch.empty((), dtype=dt).element_size()) * int(math.prod(shp))
+        out[k] = buf[off:off + nbytes].view(dt).view(shp)
+    return out
+
+
+def _fill_dummies(views: Dict[str, Tensor], shape: _Shape, n_real: int, e_real: int) -> None:
+    """Writes the D trailing dummy graphs: zero features / labels, pad nodes split over the dummy graphs (each within
+    the per-graph caps), pad edges as (a, a+1), (a+1, a) pairs walking along the first dummy graphs' nodes."""
+    B, D = shape.graphs, shape.dummies
+    pn, pe = shape.n_cap - n_real, shape.e_cap - e_real
+    views["x"][n_real:].zero_()
+    views["y"][B:].zero_()
+    sizes, left = [], pn
+    for _ in range(D):
+        take = min(left, shape.max_nodes)
+        sizes.append(take)
+        left -= take
+    if left:
+        raise ValueError(f"{pn} pad nodes do not fit {D} dummy graphs of <= {shape.max_nodes} nodes")
+    views["batch"][n_real:] = torch.repeat_interleave(torch.arange(B, B + D), torch.tensor(sizes))
+    ei = views["edge_index"]
+    pos, base = e_real, n_real
+    for sz in sizes:
+        if pe <= 0:
+            break
+        if sz < 2:
+            base += sz
+            continue
+        take = min(pe, shape.max_edges) if shape.max_edges else pe
+        k = torch.arange(take)
+        a = base + (k // 2) % (sz - 1)
+        fwd = (k % 2 == 0)
+        ei[0, pos:pos + take] = torch.where(fwd, a, a + 1)
+        ei[1, pos:pos + take] = torch.where(fwd, a + 1, a)
+        pos, pe, base = pos + take, pe - take, base + sz
+    if pe > 0:
+        raise ValueError(f"pad edges do not fit the dummy graphs (left {pe})")
+
+
+def shape_for(batch: Batch, policy: Optional[BucketPolicy], use_blocks: bool = True) -> _Shape:
+    """The static shape a collated batch runs under: its bucket (with a policy) or its exact sizes (without)."""
+    N, E, B = int(batch.x.size(0)), int(batch.edge_index.size(1)), int(batch.num_graphs)
+    loop_free = not bool((batch.edge_index[0] == batch.edge_index[1]).any())
+    max_n = int(batch["max_nodes_per_graph"]) if "max_nodes_per_graph" in batch else int(
+        (batch.ptr[1:] - batch.ptr[:-1]).max())
+    max_e = 0
+    if use_blocks:
+        if "max_edges_per_graph" in batch:                  # verified by Batch.from_data_list at collate time
+            max_e = int(batch["max_edges_per_graph"])
+        else:
+            blocks = edge_blocks_from_batch(batch.edge_index, batch.batch, B)
+            max_e = blocks[1] if blocks is not None else 0
+    if policy is None:
+        return _Shape(N, E, B, 0, max_n, max_e, loop_free)
+    if max_n > policy.max_nodes_per_graph or max_e > policy.max_edges_per_graph:
+        raise ValueError(f"batch has a graph with {max_n} nodes / {max_e} edges, above the policy's caps "
+                         f"({policy.max_nodes_per_graph} / {policy.max_edges_per_graph})")
+    n_cap, e_cap = policy.bucket(N, E)
+    return _Shape(n_cap, e_cap, B, policy.dummy_graphs, policy.max_nodes_per_graph,
+                  policy.max_edges_per_graph if max_e else 0, loop_free)
+
+
+def stage_batch(batch: Batch, policy: Optional[BucketPolicy], pin: bool = False, use_blocks: bool = True
+                ) -> StagedBatch:
+    """Packs one collated batch (x, edge_index, batch, y) into a single host buffer of its bucket's size; the padding
+    is written as trailing dummy graphs (`_fill_dummies`)."""
+    shape = shape_for(batch, policy, use_blocks)
+    layout, nbytes = _layout(shape, batch.x, batch.y)
+    buf = torch.empty(nbytes, dtype=torch.uint8)
+    if pin:
+        buf = buf.pin_memory()
+    v = _views(buf, layout)
+    N, E = int(batch.x.size(0)), int(batch.edge_index.size(1))
+    v["x"][:N].copy_(batch.x)
+    v["edge_index"][:, :E].copy_(batch.edge_index)
+    v["batch"][:N].copy_(batch.batch)
+    v["y"][:shape.graphs].copy_(batch.y)
+    if shape.dummies:
+        _fill_dummies(v, shape, N, E)
+    return StagedBatch(shape, buf, v, N, E)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -161,92 +384,218 @@ class StepConfig:
     loss_fn: str = "cross_entropy"
     lr: float = 1e-3
     weight_decay: float = 5e-4
+    clip_grad_norm: bool = False        # train/train.py:92-93 (max_norm 1.0)
+    batch_accumulation: int = 1         # train/train.py:89-91: optimizer step every this many batches (HSCN stage)
+
+
+class _Runner:
+    """Static device buffers + captured CUDA graphs of one shape bucket."""
+
+    def __init__(self, shape: _Shape, layout: Dict[str, tuple], nbytes: int, device: torch.device):
+        self.shape = shape
+        if device.type == "cuda":
+            self.dev_buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self.dev = _views(self.dev_buf, layout)
+        else:
+            self.dev_buf = None
+            self.dev = {k: torch.empty(shp, dtype=dt) for k, (off, dt, shp) in layout.items()}
+        self.hints = dict(num_graphs=shape.graphs + shape.dummies, batch_sorted=1, max_nodes_per_graph=shape.max_nodes,
+                          no_self_loops=int(shape.no_self_loops))
+        self.graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
 
 
 class GraphHSCNStep:
-    """Owns the two models, their optimizers and static device buffers for one batch shape."""
+    """Owns the two models, their optimizers, and per-bucket static device buffers + CUDA graphs.
+
+        step = GraphHSCNStep(cfg, first_batch, device, policy=BucketPolicy(...))
+        for batch in loader:                       # variable-shape batches
+            step.load(batch)                       # pack (pinned) + upload + select the bucket
+            step.run()                             # replays the bucket's graph (captured on first use)
+            losses = step.download()
+
+    Without a policy the single "bucket" has the first batch's exact shape (no padding, D = 0)."""
 
     def __init__(self, cfg: StepConfig, host_batch: Batch, device: torch.device, op_ns: Optional[SimpleNamespace] = None,
-                 seed: int = 0, padded: bool = True):
+                 seed: int = 0, padded: bool = True, policy: Optional[BucketPolicy] = None, auto_capture: bool = False):
         from . import pyg
-        self.cfg, self.device, self.padded = cfg, device, padded
+        self.cfg, self.device, self.padded, self.policy = cfg, device, padded, policy
         self.ns = op_ns or pyg.namespace()
         self.B = int(host_batch.num_graphs)
-        counts = host_batch.ptr[1:] - host_batch.ptr[:-1]
-        self.hints = dict(num_graphs=self.B, batch_sorted=1, max_nodes_per_graph=int(counts.max()),
-                          no_self_loops=int(not bool((host_batch.edge_index[0] == host_batch.edge_index[1]).any())))
-        # collate-time fact (SURVEY 8b): edges are graph-major and block diagonal -> per-graph CSR kernel (K1 fast path)
-        blocks = edge_blocks_from_batch(host_batch.edge_index, host_batch.batch, self.B)
-        self.max_edges_per_graph = blocks[1] if blocks is not None and os.environ.get("GHSCN_BLOCKED_CSR", "1") != "0" else 0
-        # pinned host staging + static device buffers (inputs are re-copied every step in the e2e path)
-        src = {k: host_batch[k].contiguous() for k in ("x", "edge_index", "batch", "y")}
-        if device.type == "cuda":
-            # ONE pinned staging buffer and ONE device buffer hold all four inputs (256-byte aligned sub-ranges), so
-            # the per-step upload is a single host-to-device copy; `host[k]` / `dev[k]` are typed views into them
-            offs, total = {}, 0
-            for k, v in src.items():
-                offs[k] = total
-                total += (v.numel() * v.element_size() + 255) // 256 * 256
-            self._host_buf = torch.empty(max(total, 256), dtype=torch.uint8).pin_memory()
-            self._dev_buf = torch.empty(max(total, 256), dtype=torch.uint8, device=device)
-
-            def view(buf, k, v):
-                nbytes = v.numel() * v.element_size()
-                return buf[offs[k]:offs[k] + nbytes].view(v.dtype).view(v.shape)
-            self.host = {k: view(self._host_buf, k, v) for k, v in src.items()}
-            for k, v in src.items():
-                self.host[k].copy_(v)
-            self.dev = {k: view(self._dev_buf, k, v) for k, v in src.items()}
-            self.h2d_bytes = int(self._host_buf.numel())
-        else:
-            self._host_buf = self._dev_buf = None
-            self.host = src
-            self.dev = {k: torch.empty_like(v, device=device) for k, v in self.host.items()}
-            self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.auto_capture = auto_capture and device.type == "cuda" and padded
+        self.world = 1
+        self._use_blocks = os.environ.get("GHSCN_BLOCKED_CSR", "1") != "0"
+        self._runners: Dict[_Shape, _Runner] = {}
+        self._pool = None
+        self._x_like, self._y_like = host_batch.x[:0], host_batch.y[:0]
+        self._copy_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        self._slots: List[Optional[Tensor]] = [None, None]      # device staging buffers of the prefetch pipeline
+        self._slot_events: List[Optional["torch.cuda.Event"]] = [None, None]
+        self._next_slot = 0
+        self._micro = 0                                         # batches since the last HSCN optimizer step
+        self._warmed: set = set()                               # step variants that have run eagerly at least once
+        self._loss_ring: Optional[List[Tensor]] = None
+        self._loss_slot = 0
         torch.manual_seed(seed)
         self.scn = models.SCN(list(cfg.scn_units), cfg.scn_act, cfg.num_features, cfg.num_clusters, ops=self.ns).to(device)
         self.hscn = models.HSCN("GAT", "GCN", "GCN", models.ACTIVATIONS[cfg.activation], cfg.num_features, cfg.hidden,
                                 cfg.num_classes, cfg.num_layers, ops=self.ns).to(device)
         self.losses = torch.zeros(3, dtype=torch.float32, device=device)     # mincut, ortho, task
         self.losses_host = torch.zeros(3, dtype=torch.float32).pin_memory() if device.type == "cuda" else torch.zeros(3)
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.staged = self.stage(host_batch)
+        self.runner = self._runner_for(self.staged.shape)
         self.upload()
         self._prepare()
 
+    # -- compatibility views of the current bucket -------------------------------------------------------------
+    @property
+    def dev(self) -> Dict[str, Tensor]:
+        return self.runner.dev
+
+    @property
+    def host(self) -> Dict[str, Tensor]:
+        return self.staged.views
+
+    @property
+    def hints(self) -> Dict[str, int]:
+        return self.runner.hints
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.staged.nbytes
+
+    @property
+    def graph(self):
+        return self.runner.graphs.get(self._variant())
+
+    @property
+    def num_buckets(self) -> int:
+        return len(self._runners)
+
+    @property
+    def num_graphs_captured(self) -> int:
+        return sum(len(r.graphs) for r in self._runners.values())
+
+    # -- host side: pack a batch into its bucket -------------------------------------------------------------------
+    def stage(self, batch: Batch) -> StagedBatch:
+        """Host-side packing of one collated batch into a pinned buffer of its bucket's size (padding = dummy graphs)."""
+        if int(batch.num_graphs) != self.B:
+            raise ValueError(f"this step was built for {self.B} graphs per batch, got {int(batch.num_graphs)}")
+        return stage_batch(batch, self.policy, pin=self.device.type == "cuda", use_blocks=self._use_blocks)
+
+    def _runner_for(self, shape: _Shape) -> _Runner:
+        r = self._runners.get(shape)
+        if r is None:
+            layout, nbytes = _layout(shape, self._x_like, self._y_like)
+            r = self._runners[shape] = _Runner(shape, layout, nbytes, self.device)
+        return r
+
     # -- host <-> device ---------------------------------------------------------------------------
+    def load(self, batch) -> StagedBatch:
+        """Packs (unless already a StagedBatch), selects the bucket and uploads on the current stream."""
+        staged = batch if isinstance(batch, StagedBatch) else self.stage(batch)
+        self.select(staged)
+        self.upload()
+        return staged
+
+    def select(self, staged: StagedBatch) -> None:
+        self.staged = staged
+        self.runner = self._runner_for(staged.shape)
+
     def upload(self) -> None:
-        if self._dev_buf is not None:
-            self._dev_buf.copy_(self._host_buf, non_blocking=True)
+        """Host -> device copy of the current staged batch into its bucket's static buffer (current stream)."""
+        r = self.runner
+        if r.dev_buf is not None:
+            r.dev_buf.copy_(self.staged.buf, non_blocking=True)
             return
-        for k, v in self.host.items():
-            self.dev[k].copy_(v, non_blocking=True)
+        for k, v in self.staged.views.items():
+            r.dev[k].copy_(v)
+
+    def make_resident(self, staged: StagedBatch) -> StagedBatch:
+        """Keeps a device copy of the packed batch (benchmarks with inputs already in HBM)."""
+        staged.device_copy = staged.buf.to(self.device)
+        return staged
+
+    def select_resident(self, staged: StagedBatch) -> None:
+        """Device -> device copy of a resident batch into its bucket's static buffer."""
+        self.select(staged)
+        self.runner.dev_buf.copy_(staged.device_copy, non_blocking=True)
+
+    def prefetch(self, staged: StagedBatch) -> int:
+        """Starts the H2D copy of a LATER step's batch on the copy stream (double-buffered device staging slots): it
+        overlaps the step that is running.  -> slot to hand to `select_prefetched`."""
+        slot = self._next_slot
+        self._next_slot ^= 1
+        cur = torch.cuda.current_stream()
+        buf = self._slots[slot]
+        if buf is None or buf.numel() < staged.nbytes:
+            buf = self._slots[slot] = torch.empty(max(staged.nbytes, 1 << 22), dtype=torch.uint8, device=self.device)
+        self._copy_stream.wait_stream(cur)          # the slot's previous consumer (a D2D on `cur`) must be done
+        with torch.cuda.stream(self._copy_stream):
+            buf[:staged.nbytes].copy_(staged.buf, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._slot_events[slot] = ev
+        return slot
+
+    def select_prefetched(self, staged: StagedBatch, slot: int) -> None:
+        self.select(staged)
+        torch.cuda.current_stream().wait_event(self._slot_events[slot])
+        self.runner.dev_buf.copy_(self._slots[slot][:staged.nbytes], non_blocking=True)
 
     def download(self) -> Tensor:
         self.losses_host.copy_(self.losses, non_blocking=True)
         return self.losses_host
 
+    def download_async(self) -> Tuple[Tensor, Optional["torch.cuda.Event"]]:
+        """D2H read of the three losses into one of two alternating pinned buffers; -> (host tensor, event to wait
+        for).  Lets a training loop read step t's losses while step t+1 is already running."""
+        if self.device.type != "cuda":
+            return self.download(), None
+        if self._loss_ring is None:
+            self._loss_ring = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._loss_slot ^= 1
+        host = self._loss_ring[self._loss_slot]
+        host.copy_(self.losses, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return host, ev
+
     # -- one-time preparation: materialise lazy parameters, find live parameters, build optimizers ------
     def _forward_scn(self, x_f: Tensor):
-        ei, ew = self.ns.gcn_norm(self.dev["edge_index"], None, x_f.size(0), add_self_loops=True)
-        return (ei, ew) + tuple(self.scn.forward_batched(x_f, ei, ew, self.dev["batch"]))
+        d = self.runner.dev
+        ei, ew = self.ns.gcn_norm(d["edge_index"], None, x_f.size(0), add_self_loops=True)
+        return (ei, ew) + tuple(self._scn_losses(x_f, ei, ew))
+
+    def _scn_losses(self, x_f, ei, ew, losses_tensor: bool = False):
+        # with dummy graphs the MinCUT losses are taken over the B real graphs only
+        real = self.B if self.runner.shape.dummies else None
+        return self.scn.forward_batched(x_f, ei, ew, self.runner.dev["batch"], losses_tensor=losses_tensor,
+                                        num_graphs=real)
 
     def _assign(self, x_f: Tensor, ei: Tensor, ew: Tensor):
+        d, shape = self.runner.dev, self.runner.shape
         with torch.no_grad():
             s = self.scn.logits(x_f, ei, ew)
             clusters = hetero.assign_clusters(torch.softmax(s, dim=-1))
-        return hetero.build_hetero_batch(self.dev["x"], self.dev["edge_index"], self.dev["batch"], clusters,
-                                         self.cfg.num_clusters, y=self.dev["y"], padded=self.padded,
-                                         num_graphs=self.B, x_float=x_f)
+        return hetero.build_hetero_batch(d["x"], d["edge_index"], d["batch"], clusters,
+                                         self.cfg.num_clusters, y=d["y"], padded=self.padded,
+                                         num_graphs=shape.graphs + shape.dummies, x_float=x_f)
+
+    def _task_loss(self, pred: Tensor, y: Tensor) -> Tensor:
+        if self.runner.shape.dummies:               # the dummy graphs' rows carry no loss and no gradient
+            pred, y = pred[:self.B], y[:self.B]
+        return models.criterion(self.cfg.loss_fn, pred, y)[0]
 
     def _prepare(self) -> None:
         cfg = self.cfg
         with structure_hints(**self.hints):
+            self._register_blocks()
             x_f = self._cast(self.dev["x"])
             ei, ew, _, mc, ol = self._forward_scn(x_f)
             scn_live = live_parameter_names(self.scn, mc + ol)
             hb = self._assign(x_f, ei, ew)
             pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)            # materialises lazy weights
-            loss, _ = models.criterion(cfg.loss_fn, pred, hb["local"].y)
+            loss = self._task_loss(pred, hb["local"].y)
             hscn_live = live_parameter_names(self.hscn, loss)
         self.scn_grads = FlatGradients(self.scn, scn_live)
         self.hscn_grads = FlatGradients(self.hscn, hscn_live)
@@ -260,67 +609,76 @@ class GraphHSCNStep:
         structure_cache().clear()
 
     def _register_blocks(self) -> None:
-        if self.max_edges_per_graph and self.device.type == "cuda":
-            seg = structure_cache().segments(self.dev["batch"], self.B)
-            structure_cache().register_blocks(self.dev["edge_index"], seg.ptr, self.B,
-                                              self.hints["max_nodes_per_graph"], self.max_edges_per_graph)
+        shape = self.runner.shape
+        if shape.max_edges and self.device.type == "cuda":
+            d = self.runner.dev
+            seg = structure_cache().segments(d["batch"], shape.graphs + shape.dummies)
+            structure_cache().register_blocks(d["edge_index"], seg.ptr, shape.graphs + shape.dummies, shape.max_nodes,
+                                              shape.max_edges)
 
     def _cast(self, x: Tensor) -> Tensor:
         if x.dtype == torch.int64 and x.is_cuda:
             return ops.cast_i64_f32(x)
         return x.float()
 
-    # -- the three stages; `sync_grads` hooks the data-parallel all-reduce in between ------------------
-    def stage_scn_backward(self):
-        self.scn_grads.zero()
+    # -- optimizer-side pieces shared by both schedules ---------------------------------------------------
+    def _variant(self) -> tuple:
+        """(accumulate onto the HSCN gradient buffer, take the HSCN optimizer step) for the batch about to run."""
+        acc = max(int(self.cfg.batch_accumulation), 1)
+        return (self._micro > 0, self._micro + 1 >= acc)
+
+    def _hscn_update(self, world: int) -> None:
+        self.hscn_grads.all_reduce_mean(world)
+        if self.cfg.clip_grad_norm:
+            if isinstance(self.hscn_opt, FlatAdamW):
+                self.hscn_opt.clip_grad_norm(1.0)
+            else:
+                nn.utils.clip_grad_norm_(self.hscn_grads.params, 1.0)
+        self.hscn_opt.step()
+
+    # -- the three stages ---------------------------------------------------------------------------------
+    def _step_serial(self, world: int, accumulate: bool, update: bool) -> None:
         self._register_blocks()
         x_f = self._cast(self.dev["x"])
         ei, ew, _, mc, ol = self._forward_scn(x_f)
-        (mc + ol).backward()
+        self.scn_grads.backward_into(mc + ol)
         self.losses[0:1].copy_(mc.detach().view(1))
         self.losses[1:2].copy_(ol.detach().view(1))
-        return x_f, ei, ew
-
-    def stage_assign_and_hscn_backward(self, x_f, ei, ew):
+        self.scn_grads.all_reduce_mean(world)
         self.scn_opt.step()
         hb = self._assign(x_f, ei, ew)
-        self.hscn_grads.zero()
         pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)
-        loss, _ = models.criterion(self.cfg.loss_fn, pred, hb["local"].y)
-        loss.backward()
+        loss = self._task_loss(pred, hb["local"].y)
+        self.hscn_grads.backward_into(loss, accumulate=accumulate)
         self.losses[2:3].copy_(loss.detach().view(1))
+        if update:
+            self._hscn_update(world)
 
-    def stage_hscn_update(self):
-        self.hscn_opt.step()
-
-    def _step_serial(self, world: int) -> None:
-        st = self.stage_scn_backward()
-        self.scn_grads.all_reduce_mean(world)
-        self.stage_assign_and_hscn_backward(*st)
-        self.hscn_grads.all_reduce_mean(world)
-        self.stage_hscn_update()
-
-    def _step_two_streams(self, world: int) -> None:
+    def _step_two_streams(self, world: int, accumulate: bool, update: bool) -> None:
         """Same operations as `_step_serial`, scheduled on two CUDA streams.  The "local" half of the HSCN (l->l convs,
         readout, loss, backward, AdamW) depends on neither the SCN stage nor the cluster assignment: only the
         "virtual" branch does (model/hscn.py:84-94 has no virtual->local relation).  So the SCN step, the assignment
         (K7) and the virtual branch run on the branch stream while the caller's stream runs the local half; the two
         meet once, at the end of the step.  Everything both halves read is produced on the caller's stream BEFORE
         the fork (float features, `ptr`, the plain CSR of the molecular graph); every kernel and its inputs are the
-        same as in the serial schedule, so results are bit-identical (tests/test_gpu_step.py)."""
+        same as in the serial schedule, so results are bit-identical (tests/test_gpu_step.py).  The deferred join is
+        valid because nothing on the caller's stream reads a virtual-branch tensor; tensors that cross streams are
+        marked with `record_stream` (pyg/nn.py), so the allocator cannot recycle them under a reader."""
         from .pyg import nn as pnn
         main = torch.cuda.current_stream()
         side = pnn.branch_stream(self.device)
-        N = self.dev["x"].size(0)
-        x_f = self._cast(self.dev["x"])
-        structure_cache().segments(self.dev["batch"], self.B)
+        pnn.take_forked_streams(self.device)                     # forget forks of earlier (already joined) work
+        d, shape = self.runner.dev, self.runner.shape
+        N = d["x"].size(0)
+        x_f = self._cast(d["x"])
+        structure_cache().segments(d["batch"], shape.graphs + shape.dummies)
         self._register_blocks()
-        plain = structure_cache().graph(self.dev["edge_index"], N, N, False)
+        plain = structure_cache().graph(d["edge_index"], N, N, False)
         plain.by_dst, plain.by_src                               # built here, read by both streams
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            ei, ew = self.ns.gcn_norm(self.dev["edge_index"], None, N, add_self_loops=True)
-            _, both = self.scn.forward_batched(x_f, ei, ew, self.dev["batch"], losses_tensor=True)
+            ei, ew = self.ns.gcn_norm(d["edge_index"], None, N, add_self_loops=True)
+            _, both = self._scn_losses(x_f, ei, ew, losses_tensor=True)
             self.scn_grads.backward_into(both.sum())     # == (mincut + ortho).backward(), one reduction instead of
             self.losses[0:2].copy_(both.detach())        # two select/scatter round trips
             self.scn_grads.all_reduce_mean(world)
@@ -331,41 +689,111 @@ class GraphHSCNStep:
             pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)
         finally:
             self.hscn.defer_branch_join = False
-        loss, _ = models.criterion(self.cfg.loss_fn, pred, hb["local"].y)
-        self.hscn_grads.backward_into(loss)
+        loss = self._task_loss(pred, hb["local"].y)
+        self.hscn_grads.backward_into(loss, accumulate=accumulate)
         self.losses[2:3].copy_(loss.detach().view(1))
-        self.hscn_grads.all_reduce_mean(world)
-        self.hscn_opt.step()
+        if update:
+            self._hscn_update(world)
         main.wait_stream(side)
+        for st in pnn.take_forked_streams(self.device):          # every stream the HeteroConv layers forked
+            if st is not side:
+                main.wait_stream(st)
 
-    def _step(self, world: int) -> None:
+    def _step(self, world: int, variant: Optional[tuple] = None) -> None:
+        accumulate, update = variant if variant is not None else self._variant()
         if TWO_STREAMS and self.device.type == "cuda":
-            self._step_two_streams(world)
+            self._step_two_streams(world, accumulate, update)
         else:
-            self._step_serial(world)
+            self._step_serial(world, accumulate, update)
 
-    def run_eager(self, world: int = 1) -> None:
+    def _advance(self) -> None:
+        self._micro = 0 if self._variant()[1] else self._micro + 1
+
+    def predict(self) -> Tensor:
+        """HSCN logits [B, C] of the current batch with the current weights (no gradient, no update): the forward of
+        train/train.py:115-123 `eval_epoch`.  Eager; the cluster assignment comes from the current SCN weights."""
+        d = self.runner.dev
+        with torch.no_grad(), structure_hints(**self.hints):
+            structure_cache().clear()
+            self._register_blocks()
+            x_f = self._cast(d["x"])
+            ei, ew = self.ns.gcn_norm(d["edge_index"], None, x_f.size(0), add_self_loops=True)
+            hb = self._assign(x_f, ei, ew)
+            pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)
+        return pred[:self.B]
+
+    def _snapshot(self):
+        opts = [o for o in (self.scn_opt, self.hscn_opt) if isinstance(o, FlatAdamW)]
+        return [t.clone() for o in opts for t in (o.p, o.g, o.exp_avg, o.exp_avg_sq, o.step_count)] + [self.losses.clone()]
+
+    def _restore(self, snap) -> None:
+        opts = [o for o in (self.scn_opt, self.hscn_opt) if isinstance(o, FlatAdamW)]
+        dst = [t for o in opts for t in (o.p, o.g, o.exp_avg, o.exp_avg_sq, o.step_count)] + [self.losses]
+        for t, v in zip(dst, snap):
+            t.copy_(v)
+
+    def _dry_run(self, world: int, variant: tuple) -> None:
+        """One eager step whose effects are rolled back (parameters, gradients, optimizer state, losses): loads every
+        kernel / library handle the step uses, so a capture that follows never meets a lazy initialisation."""
+        snap = self._snapshot()
         with structure_hints(**self.hints):
             structure_cache().clear()
-            self._step(world)
+            self._step(world, variant)
+        self._restore(snap)
+        torch.cuda.synchronize()
+        self._warmed.add(variant)
+
+    def run_eager(self, world: int = 1) -> None:
+        variant = self._variant()
+        with structure_hints(**self.hints):
+            structure_cache().clear()
+            self._step(world, variant)
+        self._warmed.add(variant)
+        self._advance()
 
     # -- CUDA graph capture: static shapes (padded virtual layout), no host sync inside -------------------
-    def capture(self, world: int = 1, warmup: int = 3) -> None:
+    def capture(self, world: int = 1, warmup: int = 3, variant: Optional[tuple] = None) -> None:
+        """Captures the current bucket's graph for `variant` (default: the variant of the batch about to run).
+        `warmup` eager steps run first (they are real training steps on the current batch)."""
         assert self.device.type == "cuda" and self.padded, "capture needs CUDA and the padded virtual layout"
+        self.world = world
+        variant = variant or self._variant()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.run_eager(world)
+                with structure_hints(**self.hints):
+                    structure_cache().clear()
+                    self._step(world, variant)
+            if warmup:
+                self._warmed.add(variant)
+            elif variant not in self._warmed:
+                self._dry_run(world, variant)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
+        structure_cache().check_blocked_status(self.device)     # the per-graph CSR promise held on real data
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        g = torch.cuda.CUDAGraph()
         with capture_scope(), structure_hints(**self.hints):
-            with torch.cuda.graph(self.graph):
-                self._step(world)
+            with torch.cuda.graph(g, pool=self._pool):
+                self._step(world, variant)
+        self.runner.graphs[variant] = g
 
     def run(self, world: int = 1) -> None:
-        if self.graph is not None:
-            self.graph.replay()
+        variant = self._variant()
+        g = self.runner.graphs.get(variant)
+        if g is None and self.auto_capture:
+            # first batch of this bucket: capture without warm-up steps (warm-up would train on the batch more than
+            # once; the very first capture does one rolled-back dry run instead)
+            self.capture(world or self.world, warmup=0, variant=variant)
+            g = self.runner.graphs[variant]
+        if g is not None:
+            g.replay()
+            self._advance()
         else:
             self.run_eager(world)
+
+    def release_graphs(self) -> None:
+        for r in self._runners.values():
+            r.graphs.clear()

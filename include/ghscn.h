@@ -13,8 +13,11 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host;
  *   - the caller (PyTorch) owns every buffer; the library never allocates,
- *     frees, synchronises or keeps global state; all work is enqueued on
- *     `stream` and is CUDA-graph-capture safe;
+ *     frees or synchronises, and keeps no state that a result depends on; all
+ *     work is enqueued on `stream` and is CUDA-graph-capture safe.  The only
+ *     process-wide state is instrumentation: the monotonic launch counter
+ *     (ghscn_launch_count) and the optional pipeline-trace buffer of debug
+ *     builds (ghscn_gemm3x_set_trace);
  *   - feature matrices are row-major fp32 with an explicit leading dimension
  *     (elements); index arrays produced by this library are int32, index
  *     arrays received from PyTorch (edge_index, batch) are int64;
@@ -222,6 +225,17 @@ GHSCN_API int ghscn_skinny_linear_dx(const float* dy, int64_t lddy, const float*
 GHSCN_API int ghscn_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                                float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
                                ghscn_stream_t stream);
+/* Same update with every gradient multiplied by the device scalar grad_scale[0] as it is read (NULL = 1): the
+ * clip coefficient of ghscn_grad_clip_scale, i.e. `clip_grad_norm_` followed by `optimizer.step()`. */
+GHSCN_API int ghscn_adamw_step_scaled(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                      float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
+                                      const float* grad_scale, ghscn_stream_t stream);
+/* nn.utils.clip_grad_norm(model.parameters(), max_norm) of train/train.py:92-93 over the flat gradient buffer:
+ * out[0] = total 2-norm (fixed-order two-stage reduction, deterministic), out[1] = min(1, max_norm / (out[0] + 1e-6)).
+ * The gradients themselves are not modified; pass out + 1 as grad_scale to ghscn_adamw_step_scaled. */
+GHSCN_API size_t ghscn_grad_clip_workspace_bytes(int64_t n);
+GHSCN_API int ghscn_grad_clip_scale(const float* grad, int64_t n, float max_norm, void* workspace,
+                                    size_t workspace_bytes, float* out, ghscn_stream_t stream);
 
 /* ---- K5: bipartite GAT cluster pool (local -> virtual) ---------------------------------------
  * Replaces GATConv((-1,-1), H, add_self_loops=False) on ("local","to","virtual")

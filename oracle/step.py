@@ -40,6 +40,8 @@ class OracleStep:
         self.scn_opt = torch.optim.AdamW(self.scn.parameters(), **kw)
         self.hscn_opt = torch.optim.AdamW(self.hscn.parameters(), **kw)
         self.losses = [0.0, 0.0, 0.0]
+        self._micro = 0
+        self.hscn_opt.zero_grad()
 
     def _scn_train(self) -> None:
         o, b = self.ns, self.batch
@@ -56,7 +58,8 @@ class OracleStep:
             _, mc, ol = self.scn.forward_batched(b.x.float(), ei, ew, b.batch)
             (mc + ol).backward()
             self.scn_opt.step()
-        self.losses[0], self.losses[1] = float(mc), float(ol)
+        self.losses[0], self.losses[1] = float(mc.detach()), float(ol.detach())
+        self.scn_grads = {n: p.grad.detach().clone() for n, p in self.scn.named_parameters() if p.grad is not None}
 
     def _clusters(self) -> list:
         out = []
@@ -83,9 +86,20 @@ class OracleStep:
     def run(self) -> None:
         self._scn_train()
         hb = self._hetero(self._clusters())
-        self.hscn_opt.zero_grad()
         pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)
         loss, _ = models.criterion(self.cfg.loss_fn, pred, hb["local"].y)
         loss.backward()
-        self.hscn_opt.step()
-        self.losses[2] = float(loss)
+        self.pred = pred.detach()
+        self.grads = {n: p.grad.detach().clone() for n, p in self.hscn.named_parameters() if p.grad is not None}
+        self._micro += 1
+        if self._micro % max(int(getattr(self.cfg, "batch_accumulation", 1)), 1) == 0:     # train/train.py:89-95
+            if getattr(self.cfg, "clip_grad_norm", False):
+                torch.nn.utils.clip_grad_norm_(self.hscn.parameters(), 1.0)
+            self.hscn_opt.step()
+            self.hscn_opt.zero_grad()
+        self.losses[2] = float(loss.detach())
+
+    def set_batch(self, host_batch: Batch) -> None:
+        """Next mini-batch of the loader (variable shapes are free on the CPU path)."""
+        self.batch = host_batch
+        self.graphs = host_batch.to_data_list()

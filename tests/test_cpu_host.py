@@ -342,3 +342,97 @@ def test_new_entry_points_validate_arguments_without_a_gpu(built_lib):
     with pytest.raises(GhscnError, match="invalid"):          # phase out of range
         L.call("ghscn_mincut_fwd_phase", None, 0, None, 0, None, None, None, None, 1.0, 1, 1, 10, 1, 1,
                None, None, None, None, None, None, None, None, 0, None, 3)
+    assert L.query("ghscn_grad_clip_workspace_bytes", 277_000) == 148 * 4
+    with pytest.raises(GhscnError, match="workspace"):        # clip_grad_norm: workspace too small
+        L.call("ghscn_grad_clip_scale", None, 0, 1.0, None, 0, ctypes.c_void_p(8), None)
+    with pytest.raises(GhscnError, match="invalid"):          # max_norm must be positive
+        L.call("ghscn_grad_clip_scale", None, 0, 0.0, ctypes.c_void_p(8), 1024, ctypes.c_void_p(8), None)
+    with pytest.raises(GhscnError, match="invalid"):          # scaled AdamW without a step counter
+        L.call("ghscn_adamw_step_scaled", None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 0.0, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------ round 2 host logic
+def test_bucket_padding_builds_wellformed_dummy_graphs():
+    """train.stage_batch pads a batch into its bucket with trailing dummy graphs: still sorted `batch`, block-diagonal
+    graph-major loop-free edges, per-graph caps respected, real rows untouched."""
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.structure import edge_blocks_from_batch
+    from graph_hscn_b200.train import BucketPolicy, stage_batch
+    batches = [synthetic.peptides_batch(12, seed=s) for s in (1, 2, 3, 4)]
+    pol = BucketPolicy.for_batches(batches, node_step=64, edge_step=128)
+    seen = set()
+    for b in batches:
+        st = stage_batch(b, pol)
+        sh, v = st.shape, st.views
+        N, E = b.x.size(0), b.edge_index.size(1)
+        assert sh.n_cap % 64 == 0 and sh.n_cap >= N + 2 and sh.n_cap - N <= 64 + 2
+        assert sh.e_cap % pol.eff_edge_step == 0 and 0 <= sh.e_cap - E < pol.eff_edge_step
+        assert sh.graphs == 12 and sh.dummies == pol.dummy_graphs
+        assert torch.equal(v["x"][:N], b.x) and torch.equal(v["edge_index"][:, :E], b.edge_index)
+        assert torch.equal(v["batch"][:N], b.batch) and torch.equal(v["y"][:12], b.y)
+        assert not v["x"][N:].any() and not v["y"][12:].any()
+        bt = v["batch"]
+        assert bool((bt[1:] >= bt[:-1]).all()) and int(bt[-1]) <= 12 + sh.dummies - 1 and int(bt[N]) >= 12
+        ei = v["edge_index"]
+        assert int(ei.min()) >= 0 and int(ei.max()) < sh.n_cap and not bool((ei[0] == ei[1]).any())
+        blocks = edge_blocks_from_batch(ei, bt, 12 + sh.dummies)
+        assert blocks is not None and blocks[0] <= sh.max_nodes and blocks[1] <= sh.max_edges
+        seen.add((sh.n_cap, sh.e_cap))
+    assert len(seen) >= 2                                   # different sizes land in different buckets
+    exact = stage_batch(batches[0], None)
+    assert exact.shape.dummies == 0 and exact.shape.n_cap == batches[0].x.size(0)
+
+
+def test_dummy_graphs_do_not_change_losses_or_gradients():
+    """The padded batch (B real + D dummy graphs, loss over the first B graphs) gives the gradients of the unpadded
+    batch: run on the CPU oracle operators with the MPNN as the local chain of the HSCN."""
+    from graph_hscn_b200 import models, synthetic
+    from graph_hscn_b200.data import Batch
+    from graph_hscn_b200.train import BucketPolicy, stage_batch
+    from oracle.namespace import namespace
+    b = synthetic.peptides_batch(6, seed=9)
+    st = stage_batch(b, BucketPolicy.for_batches([b], node_step=32, edge_step=64))
+    v = st.views
+    torch.manual_seed(0)
+    m = models.MPNN("gcn", torch.relu, 9, 24, 10, 3, ops=namespace())
+    b.x = b.x.float()
+    loss, _ = models.criterion("cross_entropy", m(b), b.y)
+    want = torch.autograd.grad(loss, list(m.parameters()))
+    pb = Batch(x=v["x"].float(), edge_index=v["edge_index"], y=v["y"])
+    pb.batch = v["batch"]
+    pred = m(pb)
+    assert pred.size(0) == 6 + st.shape.dummies
+    loss_p, _ = models.criterion("cross_entropy", pred[:6], v["y"][:6])
+    got = torch.autograd.grad(loss_p, list(m.parameters()))
+    assert abs(loss_p.item() - loss.item()) <= 1e-6 * abs(loss.item())
+    for a, c in zip(got, want):
+        assert float((a - c).abs().max()) <= 1e-6 * float(c.abs().max().clamp_min(1e-12))
+
+
+def test_balanced_partition_equal_counts_and_sizes():
+    from graph_hscn_b200.train import balanced_partition
+    rng = np.random.default_rng(0)
+    sizes = np.clip(np.rint(rng.normal(151, 60, size=1024)), 8, 444).astype(int).tolist()
+    groups = balanced_partition(sizes, 8)
+    assert sorted(i for g in groups for i in g) == list(range(1024))
+    assert all(len(g) == 128 for g in groups)
+    sums = [sum(sizes[i] for i in g) for g in groups]
+    assert (max(sums) - min(sums)) / (sum(sums) / 8) < 0.01          # node counts within 1 % across ranks
+    uneven = balanced_partition(sizes[:10], 4)
+    assert sorted(len(g) for g in uneven) == [2, 2, 3, 3]
+
+
+def test_device_staging_plan_without_a_gpu():
+    """pyg/_device.py: strict mode raises on CPU tensors; auto mode plans a CUDA staging (no CPU fallback)."""
+    from graph_hscn_b200.pyg import _device
+    x = torch.zeros(3, 2)
+    assert not _device.auto_device()
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        _device.plan(x)
+    _device.set_auto_device(True)
+    try:
+        if not torch.cuda.is_available():
+            with pytest.raises(RuntimeError, match="no CPU fallback"):
+                _device.plan(x)
+    finally:
+        _device.set_auto_device(False)

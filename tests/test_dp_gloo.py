@@ -33,7 +33,7 @@ def _loss_on(model, graphs):
     return loss
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, uneven=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -43,6 +43,13 @@ def _worker(rank, world, port, q):
         graphs = synthetic.peptides_graphs(8, seed=5)
         model = _build()
         flat = FlatGradients(model)
+        if uneven:      # node-balanced cut points: the ranks hold different graph counts (5 + 3 here)
+            lo, hi = (0, 5) if rank == 0 else (5, 8)
+            flat.zero()
+            _loss_on(model, graphs[lo:hi]).backward()
+            flat.all_reduce_mean(local_graphs=hi - lo, global_graphs=len(graphs))
+            q.put((rank, flat.flat.clone(), (lo, hi)))
+            return
         lo, hi = shard_range(len(graphs), rank, world)
         flat.zero()
         _loss_on(model, graphs[lo:hi]).backward()
@@ -80,6 +87,30 @@ def test_two_rank_allreduce_equals_full_batch():
     graphs = synthetic.peptides_graphs(8, seed=5)
     model = _build()
     _loss_on(model, graphs).backward()                      # BCE mean over 8 graphs == mean of the two shard means
+    full = torch.cat([p.grad.flatten() for p in model.parameters()])
+    assert rel_err(got[0][1], full) < 1e-5
+
+
+def test_two_rank_allreduce_with_uneven_shards_weights_by_graph_count():
+    """Node-balanced shards hold different graph counts: each rank's batch-mean gradient is weighted by its share of
+    the global graph count before the SUM all-reduce (a plain mean over ranks would be wrong)."""
+    from graph_hscn_b200 import synthetic
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got.sort(key=lambda t: t[0])
+    assert got[0][2] == (0, 5) and got[1][2] == (5, 8)
+    assert torch.equal(got[0][1], got[1][1])
+    graphs = synthetic.peptides_graphs(8, seed=5)
+    model = _build()
+    _loss_on(model, graphs).backward()
     full = torch.cat([p.grad.flatten() for p in model.parameters()])
     assert rel_err(got[0][1], full) < 1e-5
 

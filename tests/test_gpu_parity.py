@@ -345,6 +345,81 @@ def test_dense_mincut_pool_single_graph_api(cuda):
         assert_close(a, b_, RTOL, "dense " + nm)
 
 
+def test_mincut_voc_sp_shape_vs_oracle(cuda):
+    """BASELINE config #4 shape (n ~ 395-500, avg degree ~5.7, K=32, H=256): four sampled graphs, all four outputs
+    and both gradients against the oracle's dense PyG recipe."""
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.data import Batch
+    o, p = _oracle(), _product()
+    b = Batch.from_data_list(synthetic.vocsp_graphs(4, seed=1238))
+    g = torch.Generator().manual_seed(4)
+    N, K, H = b.x.size(0), 32, 256
+    assert 4 * 395 <= N <= 4 * 500
+    ei, _ = o.gcn_norm(b.edge_index, None, N, add_self_loops=True)
+    x = torch.randn(N, H, generator=g)
+    s = torch.randn(N, K, generator=g)
+    xr, sr = x.clone().requires_grad_(), s.clone().requires_grad_()
+    xt, st_ = x.to(cuda).requires_grad_(), s.to(cuda).requires_grad_()
+    out_r, adj_r, mc_r, or_r = o.mincut_pool_ragged(xr, ei, sr, b.batch)
+    out_t, adj_t, mc_t, or_t = p.mincut_pool_ragged(xt, ei.to(cuda), st_, b.batch.to(cuda))
+    for a, c, nm in [(out_t, out_r, "out"), (adj_t, adj_r, "out_adj"), (mc_t, mc_r, "mc"), (or_t, or_r, "ortho")]:
+        assert_close(a, c, RTOL, "VOC-SP mincut " + nm)
+    go = torch.randn(out_r.shape, generator=g)
+    (mc_r + or_r + (out_r * go).sum() * 0.01).backward()
+    (mc_t + or_t + (out_t * go.to(cuda)).sum() * 0.01).backward()
+    assert_close(st_.grad, sr.grad, 5 * RTOL, "VOC-SP mincut d logits")
+    assert_close(xt.grad, xr.grad, 5 * RTOL, "VOC-SP mincut d x")
+
+
+@pytest.mark.parametrize("train_eps", [False, True])
+def test_ginconv_fwd_bwd(cuda, train_eps):
+    """GINConv is listed in CONV_DICT (config/config.py:19-23): out = nn((1 + eps) x_i + sum_j x_j)."""
+    import torch.nn as nn
+    o, p = _oracle(), _product()
+    g = torch.Generator().manual_seed(12)
+    n, e, fi, fo = 700, 2600, 9, 24
+    ei = random_edge_index(n, n, e, g)
+    x = torch.randn(n, fi, generator=g)
+
+    def mlp(ns):
+        return nn.Sequential(ns.Linear(fi, 32), nn.ReLU(), ns.Linear(32, fo))
+    ref, tst = _to_dev(lambda: o.GINConv(mlp(o), eps=0.3, train_eps=train_eps),
+                       lambda: p.GINConv(mlp(p), eps=0.3, train_eps=train_eps), cuda, lambda m, d: None)
+    xr, xt = x.clone().requires_grad_(), x.to(cuda).requires_grad_()
+    yr, yt = ref(xr, ei), tst(xt, ei.to(cuda))
+    assert_close(yt, yr, RTOL, "GIN out")
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    yt.backward(gy.to(cuda))
+    assert_close(xt.grad, xr.grad, 2 * RTOL, "GIN dx")
+    for (nm, a), (_, c) in zip(tst.named_parameters(), ref.named_parameters()):
+        assert_close(a.grad, c.grad, 2 * RTOL, f"GIN d{nm}")
+
+
+def test_adamw_kernel_matches_torch_adamw(cuda):
+    """ghscn_adamw_step (flat buffer, device step counter) vs torch.optim.AdamW over 5 steps at 1e-6."""
+    from graph_hscn_b200.train import FlatAdamW
+    g = torch.Generator().manual_seed(13)
+    n = 277_001
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+    p = p0.to(cuda)
+    grad = torch.empty(n, device=cuda)
+    mine = FlatAdamW(p, grad, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+    for step in range(5):
+        gr = torch.randn(n, generator=g) * (10.0 ** (step - 2))
+        ref.grad = gr.clone()
+        opt.step()
+        grad.copy_(gr)
+        mine.step()
+    assert_close(p, ref.detach(), 1e-6, "parameters after 5 AdamW steps")
+    st = opt.state[ref]
+    assert_close(mine.exp_avg, st["exp_avg"], 1e-6, "exp_avg")
+    assert_close(mine.exp_avg_sq, st["exp_avg_sq"], 1e-6, "exp_avg_sq")
+    assert float(mine.step_count) == 5.0
+
+
 # ------------------------------------------------------------------------------------------- K7
 @pytest.mark.parametrize("K", [4, 10, 32])
 @pytest.mark.parametrize("int_feats", [True, False])

@@ -103,3 +103,142 @@ def test_parallel_branch_schedule_is_bit_identical(cuda):
     for captured in (False, True):
         (p0, l0), (p1, l1) = run(False, captured), run(True, captured)
         assert torch.equal(p0, p1) and torch.equal(l0, l1), f"captured={captured}"
+
+
+# ------------------------------------------------------------------------------------------------ round 2
+def _flat_named(grads):
+    return dict(zip(grads.names, (p.grad for p in grads.params)))
+
+
+def test_bench_configuration_step_matches_oracle(cuda):
+    """The benchmark's own configuration -- StepConfig() (h=300, K=10, 3 layers), the Peptides-func batch of seed 1236
+    (128 graphs), bucketed padding, ONE captured two-stream CUDA graph -- against the CPU oracle step on the same
+    batch and weights: losses, HSCN logits, live gradients of both models, cluster-id agreement."""
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.train import BucketPolicy, GraphHSCNStep, StepConfig
+    from oracle.step import OracleStep
+    batch = synthetic.peptides_batch(128, seed=1236, task="func")
+    cfg = StepConfig()
+    ostep = OracleStep(cfg, batch, seed=0)
+    pstep = GraphHSCNStep(cfg, batch, cuda, padded=True, policy=BucketPolicy.for_batches([batch]))
+    assert pstep.runner.shape.dummies >= 1 and pstep.runner.shape.n_cap > batch.x.size(0)
+    _sync_weights(pstep, ostep)
+    pred0 = pstep.predict()                       # HSCN logits before any update (independent of the clusters)
+    pstep.capture(warmup=0)
+    _sync_weights(pstep, ostep)                   # (the dry run is rolled back; load again to be explicit)
+    pstep.run()
+    got = pstep.download().clone()
+    torch.cuda.synchronize()
+    ostep.run()
+    want = torch.tensor(ostep.losses)
+    assert_close(got[:2], want[:2], RTOL, "mincut / ortho loss at the bench configuration")
+    assert_close(got[2:], want[2:], RTOL, "task loss at the bench configuration")
+    assert_close(pred0, ostep.pred, RTOL, "HSCN logits at the bench configuration")
+    for n, g in _flat_named(pstep.scn_grads).items():
+        assert_close(g, ostep.scn_grads[n], 1e-4, f"SCN gradient {n}")
+    live = _flat_named(pstep.hscn_grads)
+    assert set(live) == set(ostep.grads)
+    for n, g in live.items():
+        assert_close(g, ostep.grads[n], 1e-4, f"HSCN gradient {n}")
+    # cluster ids: bit-exact outside fp32 near-ties of the softmax; report the near-tie rate (SURVEY 7.2)
+    from graph_hscn_b200 import hetero
+    from graph_hscn_b200.structure import structure_hints
+    b = batch
+    ei, ew = ostep.ns.gcn_norm(b.edge_index, None, b.x.size(0), add_self_loops=True)
+    with torch.no_grad():
+        s_ref = torch.softmax(ostep.scn.logits(b.x.float(), ei, ew), dim=-1)
+    N = b.x.size(0)
+    with torch.no_grad(), structure_hints(**pstep.hints):
+        d = pstep.dev
+        x_f = pstep._cast(d["x"])
+        ei_d, ew_d = pstep.ns.gcn_norm(d["edge_index"], None, x_f.size(0), add_self_loops=True)
+        ids = hetero.assign_clusters(torch.softmax(pstep.scn.logits(x_f, ei_d, ew_d), dim=-1))[:N].cpu().long()
+    want_ids = s_ref.max(1)[1]
+    top2 = s_ref.topk(2, dim=1)[0]
+    near = (top2[:, 0] - top2[:, 1]) <= 1e-5
+    assert torch.equal(ids[~near], want_ids[~near])
+    rate, agree = float(near.float().mean()), float((ids == want_ids).float().mean())
+    print(f"bench configuration: near-tie rate {rate:.2e}, cluster-id agreement {agree:.6f} over {N} nodes")
+    assert agree > 0.999
+
+
+def test_bucketed_captured_steps_equal_exact_shape_eager_steps(cuda):
+    """Four different-sized batches through (a) exact shapes, eager, compact virtual layout and (b) bucketed padding
+    with dummy graphs, one captured graph per bucket: same losses every step and same weights at the end."""
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.train import BucketPolicy, GraphHSCNStep
+    batches = [synthetic.peptides_batch(10, seed=s) for s in (31, 32, 33, 31)]
+    pol = BucketPolicy.for_batches(batches, node_step=128, edge_step=256)
+    a = GraphHSCNStep(_cfg(), batches[0], cuda, padded=False, seed=3)
+    b = GraphHSCNStep(_cfg(), batches[0], cuda, padded=True, seed=3, policy=pol, auto_capture=True)
+    _sync_weights(b, a)
+    for i, bt in enumerate(batches):
+        a.load(bt)
+        a.run()
+        b.load(bt)
+        b.run()
+        la, lb = a.download().clone(), b.download().clone()
+        torch.cuda.synchronize()
+        assert_close(lb[:2], la[:2], 2e-5, f"SCN losses, step {i}")
+        assert rel_err(lb[2:], la[2:]) < 1e-4, f"task loss, step {i}"
+    assert 2 <= b.num_buckets <= 3 and b.num_graphs_captured == b.num_buckets     # batch 4 replays bucket 1's graph
+    for (n, p), (_, q) in zip(a.hscn.named_parameters(), b.hscn.named_parameters()):
+        assert rel_err(q, p) < 1e-3, f"HSCN param {n}"
+    for (n, p), (_, q) in zip(a.scn.named_parameters(), b.scn.named_parameters()):
+        assert rel_err(q, p) < 1e-4, f"SCN param {n}"
+
+
+def test_accumulation_and_clip_match_oracle_loop(cuda):
+    """train/train.py:87-95: gradients accumulate over `batch_accumulation` batches, are clipped to norm 1 and applied;
+    captured bucketed steps vs the CPU oracle's loop over the same three batches."""
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.train import BucketPolicy, GraphHSCNStep, StepConfig
+    from oracle.step import OracleStep
+    cfg = StepConfig(hidden=48, lr=1e-2, batch_accumulation=2, clip_grad_norm=True, loss_fn="l1", num_classes=11)
+    batches = [synthetic.peptides_batch(8, seed=s, task="struct") for s in (51, 52, 53, 54)]
+    ostep = OracleStep(cfg, batches[0], seed=0)
+    pstep = GraphHSCNStep(cfg, batches[0], cuda, padded=True, policy=BucketPolicy.for_batches(batches, 128, 256),
+                          auto_capture=True)
+    _sync_weights(pstep, ostep)
+    for i, bt in enumerate(batches):
+        ostep.set_batch(bt)
+        ostep.run()
+        pstep.load(bt)
+        pstep.run()
+        got = pstep.download().clone()
+        torch.cuda.synchronize()
+        assert_close(got[:2], torch.tensor(ostep.losses[:2]), 1e-4, f"SCN losses, step {i}")
+        assert rel_err(got[2:], torch.tensor(ostep.losses[2:])) < 1e-3, f"task loss, step {i}"
+    for (n, a), (_, b) in zip(pstep.hscn.named_parameters(), ostep.hscn.named_parameters()):
+        assert rel_err(a, b) < 2e-3, f"HSCN param {n} after two clipped, accumulated updates"
+
+
+def test_grad_clip_kernel_matches_torch(cuda):
+    from graph_hscn_b200.train import FlatAdamW
+    g = torch.Generator().manual_seed(3)
+    for scale in (1e-3, 10.0):
+        grad = (torch.randn(276_910, generator=g) * scale).to(cuda)
+        ref = torch.nn.Parameter(torch.zeros_like(grad))
+        ref.grad = grad.clone()
+        total = torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        opt = FlatAdamW(torch.zeros_like(grad), grad.clone())
+        out = opt.clip_grad_norm(1.0)
+        assert_close(out[0:1], total.view(1), 1e-6, "total norm")
+        assert_close(opt.g * out[1], ref.grad, 1e-6, "clipped gradient")
+
+
+def test_prefetch_pipeline_delivers_the_right_batch(cuda):
+    """Double-buffered H2D on the copy stream: the bucket's static buffer holds exactly the staged bytes."""
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.train import BucketPolicy, GraphHSCNStep
+    batches = [synthetic.peptides_batch(6, seed=s) for s in (61, 62, 63)]
+    step = GraphHSCNStep(_cfg(), batches[0], cuda, policy=BucketPolicy.for_batches(batches, 64, 128))
+    staged = [step.stage(b) for b in batches]
+    slot = step.prefetch(staged[0])
+    for i, st in enumerate(staged):
+        step.select_prefetched(st, slot)
+        if i + 1 < len(staged):
+            slot = step.prefetch(staged[i + 1])
+        torch.cuda.synchronize()
+        assert torch.equal(step.runner.dev_buf.cpu(), st.buf)
+        assert torch.equal(step.dev["x"][:st.num_nodes].cpu(), batches[i].x)
