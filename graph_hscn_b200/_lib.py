@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
 from pathlib import Path
 from typing import Dict, List, Tuple
 
@@ -18,6 +18,7 @@ P = c_void_p      # device pointer / stream
 I64 = c_int64
 I32 = c_int32
 F32 = c_float
+F64 = c_double
 SZ = c_size_t
 
 # name -> (restype, argtypes); must list every GHSCN_API symbol of include/ghscn.h
@@ -45,8 +46,8 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_skinny_dw_workspace_bytes": (SZ, [I64, I64, I64]),
     "ghscn_skinny_linear_dw": (I32, [P, I64, P, I64, I64, I64, I64, P, P, SZ, P]),
     "ghscn_skinny_linear_dx": (I32, [P, I64, P, I64, I64, I64, P, I64, P]),
-    "ghscn_adamw_step": (I32, [P, P, P, P, I64, F32, F32, F32, F32, F32, P, P]),
-    "ghscn_adamw_step_scaled": (I32, [P, P, P, P, I64, F32, F32, F32, F32, F32, P, P, P]),
+    "ghscn_adamw_step": (I32, [P, P, P, P, I64, F64, F64, F64, F64, F64, P, P]),
+    "ghscn_adamw_step_scaled": (I32, [P, P, P, P, I64, F64, F64, F64, F64, F64, P, P, P]),
     "ghscn_grad_clip_workspace_bytes": (SZ, [I64]),
     "ghscn_grad_clip_scale": (I32, [P, I64, F32, P, SZ, P, P]),
     "ghscn_colsum_workspace_bytes": (SZ, [I64, I64]),

@@ -427,7 +427,7 @@ using namespace ghscn;
 
 extern "C" {
 
-int ghscn_abi_version(void) { return 1; }
+int ghscn_abi_version(void) { return 2; }
 
 unsigned long long ghscn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

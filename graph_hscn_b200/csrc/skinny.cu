@@ -421,31 +421,37 @@ int ghscn_skinny_linear_dx(const float* dy, int64_t lddy, const float* w, int64_
 }  // extern "C"
 
 // ---- AdamW on one flat fp32 parameter buffer (train/train.py:94 `optimizer.step()`, OPTIM_DICT["adamW"]) -----------
-// torch.optim.AdamW's update, elementwise, with the step count kept on the device so the launch is CUDA-graph
-// capturable:  p *= 1 - lr*wd;  m = lerp(m, g, 1-b1);  v = b2*v + (1-b2)*g*g;
+// torch.optim.AdamW's (non-capturable, single-tensor) update, elementwise, with the step count kept on the device so
+// the launch is CUDA-graph capturable:  p *= 1 - lr*wd;  m = lerp(m, g, 1-b1);  v = b2*v + (1-b2)*g*g;
 //              p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 namespace ghscn {
+// state[0] = steps taken so far, state[1] = lr / (1 - b1^t), state[2] = sqrt(1 - b2^t) for the step being taken.
+// One thread advances the counter and derives the two bias-correction scalars in double precision, exactly as
+// torch.optim.AdamW's Python code does on the host; the elementwise kernel then only reads them.
+__global__ void adamw_prepare_kernel(float* __restrict__ state, double lr, double b1, double b2) {
+  const double t = (double)state[0] + 1.0;
+  state[0] = (float)t;
+  state[1] = (float)(lr / (1.0 - pow(b1, t)));
+  state[2] = (float)sqrt(1.0 - pow(b2, t));
+}
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                    float lr, float b1, float b2, float eps, float wd,
-                                                    float* __restrict__ step, const float* __restrict__ grad_scale) {
-  const float t = step[0] + 1.0f;  // every thread reads the old value; a separate 1-thread kernel publishes t
-  const float bc1 = 1.0f - powf(b1, t);
-  const float bc2_sqrt = sqrtf(1.0f - powf(b2, t));
-  const float step_size = lr / bc1;
+                                                    float decay, float omb1, float b2, float omb2, float eps,
+                                                    const float* __restrict__ state,
+                                                    const float* __restrict__ grad_scale) {
+  const float step_size = state[1], bc2_sqrt = state[2];
   const float gs = grad_scale ? grad_scale[0] : 1.0f;   // clip_grad_norm coefficient (== g.mul_(coef) beforehand)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
     const float gi = grad_scale ? g[i] * gs : g[i];
-    float pi = p[i] * (1.0f - lr * wd);
-    const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
-    const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
+    float pi = p[i] * decay;                                    // param.mul_(1 - lr * wd)
+    const float mi = m[i] + (gi - m[i]) * omb1;                 // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * b2 + omb2 * (gi * gi);              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= step_size * (mi / denom);
+    pi -= step_size * (mi / denom);                             // param.addcdiv_(exp_avg, denom, value=-step_size)
     p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
-__global__ void adamw_bump_kernel(float* step) { step[0] += 1.0f; }
 
 // ---- clip_grad_norm (train/train.py:92-93) over the flat gradient buffer ------------------------------------------
 // total = ||g||_2 as a fixed-order two-stage sum of squares (deterministic); coef = min(1, max_norm / (total + 1e-6)),
@@ -493,23 +499,25 @@ extern "C" int ghscn_grad_clip_scale(const float* grad, int64_t n, float max_nor
 }
 
 extern "C" int ghscn_adamw_step_scaled(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                                       float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
-                                       const float* grad_scale, ghscn_stream_t stream_) {
-  GHSCN_REQUIRE(n >= 0 && step && (n == 0 || (param && grad && exp_avg && exp_avg_sq)));
+                                       double lr, double beta1, double beta2, double eps, double weight_decay,
+                                       float* state, const float* grad_scale, ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(n >= 0 && state && (n == 0 || (param && grad && exp_avg && exp_avg_sq)));
   cudaStream_t stream = ghscn::as_stream(stream_);
+  ghscn::adamw_prepare_kernel<<<1, 1, 0, stream>>>(state, lr, beta1, beta2);
   if (n > 0) {
     const int64_t blocks = ghscn::ceil_div<int64_t>(n, 256 * 4), cap = (int64_t)ghscn::kNumSMs * 8;
+    // the hyper-parameter combinations are formed in double and rounded once, like the Python scalars torch passes
     ghscn::adamw_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(
-        param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale);
+        param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - lr * weight_decay), (float)(1.0 - beta1), (float)beta2,
+        (float)(1.0 - beta2), (float)eps, state, grad_scale);
   }
-  ghscn::adamw_bump_kernel<<<1, 1, 0, stream>>>(step);
   GHSCN_LAUNCH_CHECK_N(n > 0 ? 2 : 1);
   return GHSCN_OK;
 }
 
 extern "C" int ghscn_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                                float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
+                                double lr, double beta1, double beta2, double eps, double weight_decay, float* state,
                                 ghscn_stream_t stream_) {
-  return ghscn_adamw_step_scaled(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step,
+  return ghscn_adamw_step_scaled(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, state,
                                  nullptr, stream_);
 }

@@ -159,8 +159,9 @@ class FlatAdamW:
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.exp_avg = torch.zeros_like(flat_grad)
         self.exp_avg_sq = torch.zeros_like(flat_grad)
-        self.step_count = torch.zeros(1, dtype=torch.float32, device=flat_grad.device)
-        self.state = {0: {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count}}
+        self._state = torch.zeros(4, dtype=torch.float32, device=flat_grad.device)  # steps, lr/(1-b1^t), sqrt(1-b2^t)
+        self.step_count = self._state[0:1]
+        self.state = {0: {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self._state}}
         self.clip = torch.ones(2, dtype=torch.float32, device=flat_grad.device)      # (total norm, clip coefficient)
         self._clip_ws: Optional[Tensor] = None
         self._use_clip = False
@@ -185,7 +186,7 @@ class FlatAdamW:
         scale = self.clip[1:] if self._use_clip else None
         lib().call("ghscn_adamw_step_scaled", _p(self.p), _p(self.g), _p(self.exp_avg), _p(self.exp_avg_sq),
                    self.p.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                   float(self.wd), _p(self.step_count), _p(scale), _stream())
+                   float(self.wd), _p(self._state), _p(scale), _stream())
         self._use_clip = False
 
     def zero_grad(self) -> None:
@@ -724,11 +725,11 @@ class GraphHSCNStep:
 
     def _snapshot(self):
         opts = [o for o in (self.scn_opt, self.hscn_opt) if isinstance(o, FlatAdamW)]
-        return [t.clone() for o in opts for t in (o.p, o.g, o.exp_avg, o.exp_avg_sq, o.step_count)] + [self.losses.clone()]
+        return [t.clone() for o in opts for t in (o.p, o.g, o.exp_avg, o.exp_avg_sq, o._state)] + [self.losses.clone()]
 
     def _restore(self, snap) -> None:
         opts = [o for o in (self.scn_opt, self.hscn_opt) if isinstance(o, FlatAdamW)]
-        dst = [t for o in opts for t in (o.p, o.g, o.exp_avg, o.exp_avg_sq, o.step_count)] + [self.losses]
+        dst = [t for o in opts for t in (o.p, o.g, o.exp_avg, o.exp_avg_sq, o._state)] + [self.losses]
         for t, v in zip(dst, snap):
             t.copy_(v)
 

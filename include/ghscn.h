@@ -219,17 +219,20 @@ GHSCN_API int ghscn_skinny_linear_dx(const float* dy, int64_t lddy, const float*
                                      int64_t in_feat, int64_t out_feat, float* dx, int64_t lddx,
                                      ghscn_stream_t stream);
 
-/* AdamW (torch.optim.AdamW semantics) on one flat fp32 parameter buffer; `step` is a device float holding the
- * number of steps taken so far and is incremented by the call, so it can be captured in a CUDA graph.
+/* AdamW (torch.optim.AdamW semantics) on one flat fp32 parameter buffer.  `state` is THREE device floats owned by
+ * the caller and zero-initialised: state[0] = number of steps taken so far (incremented by the call), state[1..2] =
+ * the bias-correction scalars of the step being taken (derived on the device in double precision), so the call can be
+ * captured in a CUDA graph.  Hyper-parameters are doubles, like the Python scalars torch.optim forms them from
+ * (1 - beta2 in fp32 would be off by 1.3e-5 relative).
  * Replaces the per-tensor optimizer launches of train/train.py:94 for the flat-buffer training step. */
 GHSCN_API int ghscn_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                               float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
+                               double lr, double beta1, double beta2, double eps, double weight_decay, float* state,
                                ghscn_stream_t stream);
 /* Same update with every gradient multiplied by the device scalar grad_scale[0] as it is read (NULL = 1): the
  * clip coefficient of ghscn_grad_clip_scale, i.e. `clip_grad_norm_` followed by `optimizer.step()`. */
 GHSCN_API int ghscn_adamw_step_scaled(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                                      float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
-                                      const float* grad_scale, ghscn_stream_t stream);
+                                      double lr, double beta1, double beta2, double eps, double weight_decay,
+                                      float* state, const float* grad_scale, ghscn_stream_t stream);
 /* nn.utils.clip_grad_norm(model.parameters(), max_norm) of train/train.py:92-93 over the flat gradient buffer:
  * out[0] = total 2-norm (fixed-order two-stage reduction, deterministic), out[1] = min(1, max_norm / (out[0] + 1e-6)).
  * The gradients themselves are not modified; pass out + 1 as grad_scale to ghscn_adamw_step_scaled. */

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 def test_library_loads_and_validates_arguments_without_a_gpu(built_lib):
     from graph_hscn_b200._lib import GhscnError, lib
     L = lib()
-    assert L.query("ghscn_abi_version") == 1
+    assert L.query("ghscn_abi_version") == 2
     assert L.error_string(0) == "ok" and "invalid" in L.error_string(-1)
     assert L.query("ghscn_csr_workspace_bytes", 1000, 100, 1) > 3 * 1100 * 4
     # argument errors are reported before anything is launched (negative sizes / null pointers)

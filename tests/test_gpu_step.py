@@ -13,6 +13,13 @@ def _cfg():
     return StepConfig(hidden=48, num_layers=3, num_clusters=10, lr=1e-2)
 
 
+def _read_losses(step):
+    """`download()` is an asynchronous D2H copy into pinned memory: wait for it before looking."""
+    host = step.download()
+    torch.cuda.synchronize()
+    return host.clone()
+
+
 def _sync_weights(dst_step, src_step):
     dst_step.scn.load_state_dict(src_step.scn.state_dict())
     dst_step.hscn.load_state_dict(src_step.hscn.state_dict())
@@ -28,8 +35,7 @@ def test_step_matches_oracle_step(cuda):
     _sync_weights(pstep, ostep)
     ostep.run()
     pstep.run_eager()
-    got = pstep.download()
-    torch.cuda.synchronize()
+    got = _read_losses(pstep)
     want = torch.tensor(ostep.losses)
     assert_close(got[:2], want[:2], RTOL, "mincut / ortho loss")
     # the task loss goes through hard cluster ids: allow for near-tie flips of the fp32 softmax argmax
@@ -63,8 +69,7 @@ def test_padded_captured_replay_equals_compact_eager(cuda):
         a.run_eager()
         b.upload()
         b.run()
-    la, lb = a.download().clone(), b.download().clone()
-    torch.cuda.synchronize()
+    la, lb = _read_losses(a), _read_losses(b)
     assert lib().query("ghscn_launch_count") > n0
     assert_close(lb, la, 1e-4, "losses after 3 steps: captured padded vs eager compact")
     for (n, p), (_, q) in zip(a.hscn.named_parameters(), b.hscn.named_parameters()):
@@ -127,8 +132,7 @@ def test_bench_configuration_step_matches_oracle(cuda):
     pstep.capture(warmup=0)
     _sync_weights(pstep, ostep)                   # (the dry run is rolled back; load again to be explicit)
     pstep.run()
-    got = pstep.download().clone()
-    torch.cuda.synchronize()
+    got = _read_losses(pstep)
     ostep.run()
     want = torch.tensor(ostep.losses)
     assert_close(got[:2], want[:2], RTOL, "mincut / ortho loss at the bench configuration")
@@ -177,8 +181,7 @@ def test_bucketed_captured_steps_equal_exact_shape_eager_steps(cuda):
         a.run()
         b.load(bt)
         b.run()
-        la, lb = a.download().clone(), b.download().clone()
-        torch.cuda.synchronize()
+        la, lb = _read_losses(a), _read_losses(b)
         assert_close(lb[:2], la[:2], 2e-5, f"SCN losses, step {i}")
         assert rel_err(lb[2:], la[2:]) < 1e-4, f"task loss, step {i}"
     assert 2 <= b.num_buckets <= 3 and b.num_graphs_captured == b.num_buckets     # batch 4 replays bucket 1's graph
@@ -205,8 +208,7 @@ def test_accumulation_and_clip_match_oracle_loop(cuda):
         ostep.run()
         pstep.load(bt)
         pstep.run()
-        got = pstep.download().clone()
-        torch.cuda.synchronize()
+        got = _read_losses(pstep)
         assert_close(got[:2], torch.tensor(ostep.losses[:2]), 1e-4, f"SCN losses, step {i}")
         assert rel_err(got[2:], torch.tensor(ostep.losses[2:])) < 1e-3, f"task loss, step {i}"
     for (n, a), (_, b) in zip(pstep.hscn.named_parameters(), ostep.hscn.named_parameters()):
