@@ -138,22 +138,28 @@ __global__ void __launch_bounds__(256) spmm_kernel(const int* __restrict__ rowpt
 // gather with ~3 slots per row needs to approach HBM/L2 bandwidth.
 constexpr int kRowsPerCta = 64;
 constexpr int kSlotCap = 1024;
+// Rows per CTA of the register-gather kernel: 8 rows per warp, ROWS / 8 warps per CTA.  Small CTAs (32 rows = 4
+// warps) let the register file hold 5 CTAs = 20 warps per SM instead of 2 x 8, and cut the grid into pieces fine
+// enough that a batch a few per cent larger does not fall off a wave boundary (64-row CTAs at 2 per SM: 296 slots,
+// so N = 18.3 k ran in one wave and N = 19.6 k in two -- 12.2 us vs 18.5 us, scripts/spmm_probe.py).
 #ifndef GHSCN_WIDE_ROWS
-#define GHSCN_WIDE_ROWS 64
+#define GHSCN_WIDE_ROWS 32
 #endif
-#ifndef GHSCN_WIDE_MINBLOCKS
-#define GHSCN_WIDE_MINBLOCKS 2
-#endif
-constexpr int kWideRows = GHSCN_WIDE_ROWS;   // rows per CTA of the register-gather kernel (tuned: see profiles/README)
+static inline int wide_rows() {
+  static const int v = [] {
+    const char* e = getenv("GHSCN_SPMM_ROWS");          // tuning experiments: 16 | 32 | 64
+    const int r = e ? atoi(e) : 0;
+    return (r == 16 || r == 32 || r == 64) ? r : GHSCN_WIDE_ROWS;
+  }();
+  return v;
+}
 
-template <int ITERS, bool WEIGHTED>
-__global__ void __launch_bounds__(256, GHSCN_WIDE_MINBLOCKS) spmm_wide_kernel(const int* __restrict__ rowptr,
-                                                           const int* __restrict__ col,
-                                                           const float* __restrict__ w,
-                                                           const float* __restrict__ x, int64_t ldx,
-                                                           float* __restrict__ y, int64_t ldy,
-                                                           const float* __restrict__ bias, int num_rows,
-                                                           int num_feat, int relu) {
+template <int ITERS, bool WEIGHTED, int ROWS>
+__global__ void __launch_bounds__(ROWS * 4, ROWS == 64 ? 2 : (ROWS == 32 ? 5 : 10))   // 16 / 20 / 20 warps per SM
+    spmm_wide_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ w,
+                     const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy,
+                     const float* __restrict__ bias, int num_rows, int num_feat, int relu) {
+  constexpr int kWideRows = ROWS, kThreads = ROWS * 4, kSlotCap = ROWS * 16;
   __shared__ int s_rowptr[kWideRows + 1];
   __shared__ int s_col[kSlotCap];
   __shared__ float s_w[kSlotCap];
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(256, GHSCN_WIDE_MINBLOCKS) spmm_wide_kernel(co
   __syncthreads();
   const int sbeg = s_rowptr[0];
   const int staged = min(s_rowptr[nrows] - sbeg, kSlotCap);
-  for (int i = tid; i < staged; i += 256) {
+  for (int i = tid; i < staged; i += kThreads) {
     s_col[i] = col[sbeg + i];
     if (WEIGHTED) s_w[i] = w[sbeg + i];
   }
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(256, GHSCN_WIDE_MINBLOCKS) spmm_wide_kernel(co
   // whatever rows they belong to: molecule-like graphs have ~2 slots per row, so batching per row would leave half of
   // the loads unissued.  Slots are still accumulated strictly in slot order into their own row (a row is written out
   // when the walk leaves it), so the arithmetic per row is unchanged.
-  constexpr int kRowsPerWarp = kWideRows / 8;
+  constexpr int kRowsPerWarp = 8;                             // ROWS / 8 warps per CTA
   const int rbeg = wid * kRowsPerWarp, rend = min(nrows, rbeg + kRowsPerWarp);
   if (rbeg >= nrows) return;
   float4 acc[ITERS];
@@ -526,19 +532,30 @@ static int launch_spmm_async(const int* rowptr, const int* col, const float* w, 
   return GHSCN_OK;
 }
 
+template <int ITERS, int ROWS>
+static int launch_spmm_wide_rows(const int* rowptr, const int* col, const float* w, const float* x, int64_t ldx,
+                                 float* y, int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat,
+                                 int relu, cudaStream_t stream) {
+  dim3 grid((unsigned)ceil_div<int64_t>(num_rows, ROWS), (unsigned)ceil_div<int64_t>(num_feat, 128 * ITERS));
+  if (w)
+    spmm_wide_kernel<ITERS, true, ROWS><<<grid, ROWS * 4, 0, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias,
+                                                                       (int)num_rows, (int)num_feat, relu);
+  else
+    spmm_wide_kernel<ITERS, false, ROWS><<<grid, ROWS * 4, 0, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias,
+                                                                        (int)num_rows, (int)num_feat, relu);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
 template <int ITERS>
 static int launch_spmm_wide(const int* rowptr, const int* col, const float* w, const float* x, int64_t ldx,
                             float* y, int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat, int relu,
                             cudaStream_t stream) {
-  dim3 grid((unsigned)ceil_div<int64_t>(num_rows, kWideRows), (unsigned)ceil_div<int64_t>(num_feat, 128 * ITERS));
-  if (w)
-    spmm_wide_kernel<ITERS, true><<<grid, 256, 0, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias, (int)num_rows,
-                                                             (int)num_feat, relu);
-  else
-    spmm_wide_kernel<ITERS, false><<<grid, 256, 0, stream>>>(rowptr, col, w, x, ldx, y, ldy, bias, (int)num_rows,
-                                                              (int)num_feat, relu);
-  GHSCN_LAUNCH_CHECK();
-  return GHSCN_OK;
+  switch (wide_rows()) {
+    case 16: return launch_spmm_wide_rows<ITERS, 16>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+    case 64: return launch_spmm_wide_rows<ITERS, 64>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+    default: return launch_spmm_wide_rows<ITERS, 32>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, stream);
+  }
 }
 
 // ---- few long rows (pooling relations: every destination has many sources) ------------------------------

@@ -27,6 +27,13 @@ def time_spmm(ei, N, hidden=300, reps=40, nset=10, label=""):
     for i in range(nset):
         launch(i, _stream())
     torch.cuda.synchronize()
+    # correctness: against index_add_ in fp64 (weights w are per slot, sources col, destination = row of the slot)
+    dst = torch.repeat_interleave(torch.arange(N, device=dev), (d.rowptr[1:] - d.rowptr[:-1]).long())
+    ref = torch.zeros(N, hidden, device=dev, dtype=torch.float64)
+    nz = int(d.rowptr[-1])
+    ref.index_add_(0, dst, xs[0][d.col[:nz].long()].double() * w[:nz].double()[:, None])
+    err = float((ys[0].double() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-6, f"SpMM result wrong: {err}"
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         s = _stream()
