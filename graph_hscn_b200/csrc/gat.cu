@@ -126,6 +126,118 @@ __global__ void __launch_bounds__(256) gat_pool_bwd_src_kernel(const int* __rest
   }
 }
 
+// ---- fused attention pool at the input width (forward) -------------------------------------------------------------
+// GATConv((-1,-1), H, heads=1, add_self_loops=False) on local -> virtual is linear in the source features once the
+// attention coefficients are known:  out_v = (sum_s alpha_s x_s) W_src^T + b,  a_src = x . (W_src^T att_src),
+// a_dst = x_dst . (W_dst^T att_dst).  One warp per destination (virtual) row does the whole pool in ONE pass over its
+// members' rows: score, leaky-relu, ONLINE softmax (running max / rescaled sums, exact in exact arithmetic) and the
+// weighted feature sum, with the feature loads of 4 members in flight.  Replaces row_dot x2, gat_scores, a zero fill
+// and the long-row SpMM (5 launches, ~36 us per layer at the bench shape); reads x_src once (HBM-bound: 4 F N bytes).
+// u_src / u_dst are the two folded attention vectors (ghscn_gat_fold_attention).
+template <int VEC, int ITERS>
+__global__ void __launch_bounds__(256) gat_pool_fused_kernel(const int* __restrict__ rowptr,
+                                                             const int* __restrict__ col,
+                                                             const float* __restrict__ x_src, int64_t ldxs,
+                                                             const float* __restrict__ x_dst, int64_t ldxd,
+                                                             const float* __restrict__ u_src,
+                                                             const float* __restrict__ u_dst, float slope,
+                                                             int num_rows, int num_feat, float* __restrict__ pooled,
+                                                             int64_t ldp) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= num_rows) return;
+  constexpr int W = VEC * ITERS;
+  auto load_row = [&](const float* p, float (&dst)[W]) {
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = (it * 32 + lane) * VEC;
+      if constexpr (VEC == 4) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < num_feat) q = __ldg(reinterpret_cast<const float4*>(p + c));
+        dst[it * 4 + 0] = q.x; dst[it * 4 + 1] = q.y; dst[it * 4 + 2] = q.z; dst[it * 4 + 3] = q.w;
+      } else {
+        dst[it] = c < num_feat ? __ldg(p + c) : 0.f;
+      }
+    }
+  };
+  float us[W], ud[W], xd[W];
+  load_row(u_src, us);
+  float ad = 0.f;
+  if (x_dst != nullptr && u_dst != nullptr) {
+    load_row(u_dst, ud);
+    load_row(x_dst + (int64_t)row * ldxd, xd);
+#pragma unroll
+    for (int j = 0; j < W; ++j) ad = fmaf(xd[j], ud[j], ad);
+    ad = warp_sum(ad);
+  }
+  const int beg = rowptr[row], end = rowptr[row + 1];
+  float m = -INFINITY, ssum = 0.f, acc[W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) acc[j] = 0.f;
+  for (int s = beg; s < end; s += 4) {
+    const int n4 = min(4, end - s);
+    float v[4][W];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < n4) load_row(x_src + (int64_t)col[s + k] * ldxs, v[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < n4) {
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < W; ++j) d = fmaf(v[k][j], us[j], d);
+        d = warp_sum(d);
+        const float z = d + ad;
+        const float e = z > 0.f ? z : z * slope;
+        if (e > m) {                                     // warp-uniform: every lane holds the same e and m
+          const float sc = expf(m - e);                  // m = -inf on the first member: exp(-inf) = 0
+          ssum *= sc;
+#pragma unroll
+          for (int j = 0; j < W; ++j) acc[j] *= sc;
+          m = e;
+        }
+        const float p = expf(e - m);
+        ssum += p;
+#pragma unroll
+        for (int j = 0; j < W; ++j) acc[j] = fmaf(p, v[k][j], acc[j]);
+      }
+    }
+  }
+  const float inv = 1.0f / (ssum + 1e-16f);              // PyG softmax: + 1e-16 in the denominator
+  float* out = pooled + (int64_t)row * ldp;
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int c = (it * 32 + lane) * VEC;
+    if (c < num_feat) {
+      if constexpr (VEC == 4) {
+        *reinterpret_cast<float4*>(out + c) = make_float4(acc[it * 4] * inv, acc[it * 4 + 1] * inv,
+                                                          acc[it * 4 + 2] * inv, acc[it * 4 + 3] * inv);
+      } else {
+        out[c] = acc[it] * inv;
+      }
+    }
+  }
+}
+
+// u_src[f] = sum_h att_src[h] W_src[h, f],  u_dst[f] = sum_h att_dst[h] W_dst[h, f]   (W [H, F] row-major)
+__global__ void __launch_bounds__(128) gat_fold_attention_kernel(const float* __restrict__ w_src, int64_t ldws,
+                                                                 const float* __restrict__ att_src,
+                                                                 const float* __restrict__ w_dst, int64_t ldwd,
+                                                                 const float* __restrict__ att_dst, int H, int Fs,
+                                                                 int Fd, float* __restrict__ u_src,
+                                                                 float* __restrict__ u_dst) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool dst_side = blockIdx.y == 1;
+  const float* w = dst_side ? w_dst : w_src;
+  const float* att = dst_side ? att_dst : att_src;
+  const int64_t ld = dst_side ? ldwd : ldws;
+  const int F = dst_side ? Fd : Fs;
+  if (w == nullptr || f >= F) return;
+  float acc = 0.f;
+  for (int h = 0; h < H; ++h) acc = fmaf(att[h], w[(int64_t)h * ld + f], acc);
+  (dst_side ? u_dst : u_src)[f] = acc;
+}
+
 // map_t[t] = slot (in the by-destination structure) of the edge sitting in transposed slot t.
 __global__ void slot_pos_kernel(const int* __restrict__ perm, int64_t nnz, int* __restrict__ pos) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,6 +294,56 @@ int ghscn_gat_pool_fwd(const int32_t* rowptr, const int32_t* col, const float* h
   if (vec4 && num_feat >= 64 && num_rows <= 65535)
     return spmm_long_rows(rowptr, col, alpha, hs, ldhs, out, ldout, bias, num_rows, num_feat, as_stream(stream));
   return ghscn_spmm(rowptr, col, alpha, hs, ldhs, out, ldout, bias, num_rows, num_feat, 0, stream);
+}
+
+int ghscn_gat_fold_attention(const float* w_src, int64_t ldws, const float* att_src, const float* w_dst, int64_t ldwd,
+                             const float* att_dst, int64_t out_feat, int64_t src_feat, int64_t dst_feat, float* u_src,
+                             float* u_dst, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(out_feat > 0 && src_feat > 0 && dst_feat >= 0 && w_src && att_src && u_src && ldws >= src_feat);
+  GHSCN_REQUIRE(w_dst == nullptr || (att_dst && u_dst && ldwd >= dst_feat && dst_feat > 0));
+  const int64_t fmax = src_feat > dst_feat ? src_feat : dst_feat;
+  dim3 grid((unsigned)ceil_div<int64_t>(fmax, 128), w_dst ? 2u : 1u);
+  gat_fold_attention_kernel<<<grid, 128, 0, as_stream(stream)>>>(w_src, ldws, att_src, w_dst, ldwd, att_dst,
+                                                                 (int)out_feat, (int)src_feat, (int)dst_feat, u_src,
+                                                                 u_dst);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+int ghscn_gat_pool_fused_supported(int64_t num_feat, int64_t ldxs, int64_t ldp) {
+  if (num_feat <= 0) return 0;
+  if (num_feat <= 32) return 1;
+  return num_feat % 4 == 0 && ldxs % 4 == 0 && ldp % 4 == 0 && num_feat <= 512;
+}
+
+int ghscn_gat_pool_fused_fwd(const int32_t* rowptr, const int32_t* col, const float* x_src, int64_t ldxs,
+                             const float* x_dst, int64_t ldxd, const float* u_src, const float* u_dst,
+                             float negative_slope, int64_t num_rows, int64_t num_feat, float* pooled, int64_t ldp,
+                             ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_feat > 0 && num_rows < ((int64_t)1 << 31));
+  if (num_rows == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(rowptr && x_src && u_src && pooled && ldxs >= num_feat && ldp >= num_feat);
+  GHSCN_REQUIRE((x_dst == nullptr) == (u_dst == nullptr) && (x_dst == nullptr || ldxd >= num_feat));
+  cudaStream_t stream = as_stream(stream_);
+  const unsigned blocks = (unsigned)ceil_div<int64_t>(num_rows, 8);
+#define GHSCN_POOL_LAUNCH(VEC, ITERS)                                                                          \
+  gat_pool_fused_kernel<VEC, ITERS><<<blocks, 256, 0, stream>>>(rowptr, col, x_src, ldxs, x_dst, ldxd, u_src,  \
+                                                                u_dst, negative_slope, (int)num_rows,          \
+                                                                (int)num_feat, pooled, ldp)
+  const bool vec4 = num_feat % 4 == 0 && ldxs % 4 == 0 && ldp % 4 == 0 && (x_dst == nullptr || ldxd % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(x_src) | reinterpret_cast<uintptr_t>(x_dst) |
+                      reinterpret_cast<uintptr_t>(pooled) | reinterpret_cast<uintptr_t>(u_src) |
+                      reinterpret_cast<uintptr_t>(u_dst)) % 16 == 0);
+  if (num_feat <= 32) GHSCN_POOL_LAUNCH(1, 1);
+  else if (!vec4) return GHSCN_E_UNSUPPORTED;
+  else if (num_feat <= 128) GHSCN_POOL_LAUNCH(4, 1);
+  else if (num_feat <= 256) GHSCN_POOL_LAUNCH(4, 2);
+  else if (num_feat <= 384) GHSCN_POOL_LAUNCH(4, 3);
+  else if (num_feat <= 512) GHSCN_POOL_LAUNCH(4, 4);
+  else return GHSCN_E_UNSUPPORTED;
+#undef GHSCN_POOL_LAUNCH
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
 }
 
 int ghscn_gat_pool_bwd_scores(const int32_t* rowptr, const int32_t* col, const float* hs, int64_t ldhs,

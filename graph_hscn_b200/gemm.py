@@ -304,16 +304,82 @@ class _LinearSkinny(torch.autograd.Function):
         return dx, dw, db
 
 
+SMALL_ACTS = {"identity": 0, None: 0, "elu": 1, "relu": 2, "tanh": 3}
+SMALL_LINEAR = os.environ.get("GHSCN_SMALL_LINEAR", "1") != "0"
+
+
+class _LinearSmall(torch.autograd.Function):
+    """y = act(x W^T + b) for problems of 10^2..10^3 rows (graph-level head, virtual-node projections): one fp32 FMA
+    tile kernel per product (csrc/dense_small.cu) instead of a library GEMM + bias epilogue + activation kernel each;
+    the backward folds act'(y) into the operand loads of dW / db / dx."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], act: int):
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        if weight.stride(1) != 1:
+            weight = weight.contiguous()
+        n, k = x.shape
+        m = weight.size(0)
+        y = torch.empty((n, m), dtype=torch.float32, device=x.device)
+        lib().call("ghscn_small_linear_fwd", _p(x), x.stride(0), _p(weight), weight.stride(0), _p(bias), int(act),
+                   n, k, m, _p(y), m, _stream())
+        ctx.save_for_backward(x, weight, y if act else None)
+        ctx.act, ctx.has_bias = int(act), bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, weight, y = ctx.saved_tensors
+        if dy.stride(1) != 1:
+            dy = dy.contiguous()
+        n, k = x.shape
+        m = weight.size(0)
+        L, st = lib(), _stream()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((n, k), dtype=torch.float32, device=x.device)
+            L.call("ghscn_small_linear_dx", _p(dy), dy.stride(0), _p(y), m, ctx.act, _p(weight), weight.stride(0),
+                   n, k, m, _p(dx), k, st)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty((m, k), dtype=torch.float32, device=x.device)
+            db = torch.empty(m, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            ws_bytes = L.query("ghscn_small_linear_dw_workspace_bytes", n, k, m)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+            L.call("ghscn_small_linear_dw", _p(dy), dy.stride(0), _p(y), m, ctx.act, _p(x), x.stride(0), n, k, m,
+                   _p(dw), _p(db), _p(ws), ws_bytes, st)
+        return dx, dw, db, None
+
+
+SMALL_MAX_ROWS = 4096
+
+
+def small_linear_ok(x: Tensor, weight: Tensor) -> bool:
+    return (SMALL_LINEAR and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and weight.is_cuda
+            and 0 < x.size(0) < SMALL_MAX_ROWS and weight.dim() == 2)
+
+
+def linear_act(x: Tensor, weight: Tensor, bias: Optional[Tensor], act: Optional[str]) -> Optional[Tensor]:
+    """act(x W^T + b) in one launch when the problem is small enough for the tile kernels; None otherwise (the caller
+    then applies the activation itself after `linear`)."""
+    if act not in SMALL_ACTS or not small_linear_ok(x, weight):
+        return None
+    return _LinearSmall.apply(x, weight, bias, SMALL_ACTS[act])
+
+
 SKINNY_MAX_IN, SKINNY_MIN_ROWS = 32, 2048
 
 
 def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None) -> Tensor:
     """F.linear with fp32-level accuracy: tall-skinny problems (raw-feature layers) stream through hand-written
-    kernels, large square ones run as 3xTF32 on the tensor cores, everything else is plain cuBLAS fp32."""
+    kernels, large square ones run as 3xTF32 on the tensor cores, problems of < 4 k rows (graph-level head, virtual
+    nodes) through the fp32 tile kernels, everything else is plain cuBLAS fp32."""
     if (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.size(0) >= SKINNY_MIN_ROWS
             and weight.size(1) <= SKINNY_MAX_IN and weight.numel() * 4 <= 96 * 1024):
         return _LinearSkinny.apply(x, weight, bias)
     if (_MODE == "3xtf32" and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
             and x.size(0) >= MIN_ROWS and min(weight.shape) >= MIN_DIM):
         return _Linear3xTF32.apply(x, weight, bias)
+    if small_linear_ok(x, weight):
+        return _LinearSmall.apply(x, weight, bias, 0)
     return F.linear(x, weight, bias)

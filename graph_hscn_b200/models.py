@@ -160,13 +160,17 @@ class HSCN(nn.Module):
         self.lin_1 = o.Linear(hidden_channels, hidden_channels)
         self.lin_2 = o.Linear(hidden_channels, num_classes)
         # "local" receives only the l->l GCN, so its `.relu()` can run in that layer's aggregation epilogue
-        self._fused_local = False
+        self._fused_local = self._fused_virtual = False
         if getattr(o, "fused_relu", False):
             lls = [c.convs["local__to__local"] for c in self.convs]
             if all(hasattr(c, "fuse_relu") for c in lls):
                 for c in lls:
                     c.fuse_relu = True
                 self._fused_local = True
+            if all(hasattr(c, "fuse_relu_dst") for c in self.convs):      # "virtual": ReLU inside the HeteroConv
+                for c in self.convs:
+                    c.fuse_relu_dst = {"virtual"}
+                self._fused_virtual = True
 
     def forward(self, x_dict: Dict[str, Tensor], edge_index_dict, batch) -> Tensor:
         # Operator sets whose HeteroConv runs the destination types on parallel CUDA streams (`last_streams`) keep
@@ -188,7 +192,7 @@ class HSCN(nn.Module):
                 main = torch.cuda.current_stream()
             x_dict = {}
             for k, v in out.items():
-                if self._fused_local and k == "local":
+                if (self._fused_local and k == "local") or (self._fused_virtual and k == "virtual"):
                     x_dict[k] = v
                 elif streams is not None:
                     with torch.cuda.stream(streams[k]):
@@ -196,7 +200,12 @@ class HSCN(nn.Module):
                 else:
                     x_dict[k] = v.relu()
         pooled = self.ops.global_mean_pool(x_dict["local"], batch["local"].batch)
-        pred = self.lin_2(self.activation(self.lin_1(pooled)))
+        hidden = None
+        if hasattr(self.ops, "linear_act"):          # bias + activation in the projection's epilogue (same values)
+            hidden = self.ops.linear_act(self.lin_1, pooled, self.activation)
+        if hidden is None:
+            hidden = self.activation(self.lin_1(pooled))
+        pred = self.lin_2(hidden)
         if streams is not None and not getattr(self, "defer_branch_join", False):
             for st in streams.values():
                 if st is not main:

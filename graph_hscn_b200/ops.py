@@ -606,3 +606,98 @@ def cast_i64_f32(x: Tensor) -> Tensor:
     out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
     lib().call("ghscn_cast_i64_f32", _p(x), x.numel(), _p(out), _stream())
     return out
+
+
+# =============================================================================================
+# task loss (loss.py:6-19) over the first `rows` graphs, one launch forward, none backward
+# =============================================================================================
+LOSS_MODES = {"cross_entropy": 0, "l1": 1}
+
+
+class GraphLoss(torch.autograd.Function):
+    """criterion(loss_fn, pred, true) for [B, C] float targets: mean BCE-with-logits or mean L1 over the first `rows`
+    rows (padding graphs behind them get zero gradient), the sigmoid score of train/train.py:82, and d loss / d pred,
+    all from ONE kernel; the backward only scales the stored gradient by the incoming scalar."""
+
+    @staticmethod
+    def forward(ctx, pred: Tensor, target: Tensor, rows: int, mode: int):
+        pred = _rowmajor(pred)
+        target = _rowmajor(target.float())
+        total, c = pred.shape
+        dev = pred.device
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        d_pred = torch.empty((total, c), dtype=torch.float32, device=dev)
+        score = torch.empty((total, c), dtype=torch.float32, device=dev)
+        lib().call("ghscn_graph_loss", _p(pred), pred.stride(0), _p(target), target.stride(0), int(rows), total, c,
+                   int(mode), _p(loss), _p(d_pred), _p(score), _stream())
+        ctx.save_for_backward(d_pred)
+        ctx.mark_non_differentiable(score)
+        return loss.view(()), score
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_score):
+        (d_pred,) = ctx.saved_tensors
+        return d_pred * g_loss, None, None, None
+
+
+def graph_loss(loss_fn: str, pred: Tensor, target: Tensor, rows: Optional[int] = None):
+    """-> (loss, sigmoid(pred[:rows])) like models.criterion / loss.py:6-19 (the [B, C] float-target forms)."""
+    rows = pred.size(0) if rows is None else int(rows)
+    loss, score = GraphLoss.apply(pred, target, rows, LOSS_MODES[loss_fn])
+    return loss, score[:rows]
+
+
+# =============================================================================================
+# fused "virtual" destination of the HeteroConv: v->v GCN + l->v GAT pool, summed (model/hscn.py:83-96)
+# =============================================================================================
+class VirtualLayerFused(torch.autograd.Function):
+    """out = [relu]( GCNConv_vv(x_v) + GATConv_lv((x_l, x_v)) ) computed at the INPUT width:
+        P = sum_s alpha_s x_l[s]            one-pass attention pool (ghscn_gat_pool_fused_fwd)
+        Q = A_hat_vv x_v                    GCN aggregation before the projection (linearity)
+        out = P W_src^T + b_gat + Q W_vv^T + b_vv          ONE small GEMM over the concatenated reduction
+    4 launches instead of ~16 per layer.  The backward (never reached in HSCN training: nothing downstream of the
+    virtual nodes feeds the loss, model/hscn.py:84-94) re-runs the two unfused, differentiable operators."""
+
+    @staticmethod
+    def forward(ctx, x_src, x_dst, w_src, w_dst, att_src, att_dst, b_gat, w_vv, b_vv, meta):
+        x_src, x_dst = _rowmajor(x_src), _rowmajor(x_dst)
+        V, F = x_dst.shape
+        H = w_src.size(0)
+        dev = x_src.device
+        L, st = lib(), _stream()
+        lvd, vvd, vv_w = meta["lv_by_dst"], meta["vv_by_dst"], meta["vv_w"]
+        w_src_c, w_dst_c, w_vv_c = w_src.contiguous(), w_dst.contiguous(), w_vv.contiguous()
+        u = torch.empty((2, F), dtype=torch.float32, device=dev)
+        L.call("ghscn_gat_fold_attention", _p(w_src_c), F, _p(att_src.contiguous()), _p(w_dst_c), F,
+               _p(att_dst.contiguous()), H, F, F, _p(u[0]), _p(u[1]), st)
+        pooled = torch.empty((V, F), dtype=torch.float32, device=dev)
+        L.call("ghscn_gat_pool_fused_fwd", _p(lvd.rowptr), _p(lvd.col), _p(x_src), x_src.stride(0), _p(x_dst),
+               x_dst.stride(0), _p(u[0]), _p(u[1]), float(meta["slope"]), V, F, _p(pooled), F, st)
+        agg = torch.empty((V, F), dtype=torch.float32, device=dev)
+        L.call("ghscn_spmm", _p(vvd.rowptr), _p(vvd.col), _p(vv_w), _p(x_dst), x_dst.stride(0), _p(agg), F, None, V, F,
+               0, st)
+        out = torch.empty((V, H), dtype=torch.float32, device=dev)
+        L.call("ghscn_small_linear2_fwd", _p(agg), F, _p(w_vv_c), F, _p(b_vv), F, _p(pooled), F, _p(w_src_c), F,
+               _p(b_gat), F, 2 if meta["relu"] else 0, V, H, _p(out), H, st)
+        ctx.meta = meta
+        ctx.save_for_backward(x_src, x_dst)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x_src, x_dst = ctx.saved_tensors
+        meta = ctx.meta
+        gat, gcn = meta["gat"], meta["gcn"]
+        with torch.enable_grad():
+            xs, xd = x_src.detach().requires_grad_(), x_dst.detach().requires_grad_()
+            out = gcn(xd, meta["vv_index"]) + gat._forward_cuda(xs, xd, meta["lv_index"], None, None)
+            if meta["relu"]:
+                out = out.relu()
+            params = [gat.lin_src.weight, gat.lin_dst.weight, gat.att_src, gat.att_dst, gat.bias, gcn.lin.weight,
+                      gcn.bias]
+            live = [p for p in params if p is not None]
+            grads = list(torch.autograd.grad(out, [xs, xd] + live, dout.contiguous(), allow_unused=True))
+        dxs, dxd = grads[0], grads[1]
+        it = iter(grads[2:])
+        pg = [next(it) if p is not None else None for p in params]
+        return (dxs, dxd, pg[0], pg[1], pg[2], pg[3], pg[4], pg[5], pg[6], None)

@@ -31,7 +31,7 @@ def namespace() -> types.SimpleNamespace:
         HeteroConv=HeteroConv, Linear=Linear, Sequential=Sequential, MessagePassing=MessagePassing,
         dense_mincut_pool=dense_mincut_pool, mincut_pool_ragged=mincut_pool_ragged, to_dense_adj=to_dense_adj,
         global_mean_pool=global_mean_pool, scatter_mean=scatter_mean, gcn_norm=gcn_norm,
-        scn_logits_fused=scn_logits_fused)
+        scn_logits_fused=scn_logits_fused, linear_act=functional.linear_act)
 
 
 def build_modules(ns: types.SimpleNamespace, data_mod=None) -> dict:

@@ -318,3 +318,19 @@ def scn_logits_fused(x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor
     xs = x if x.stride(1) == 1 else x.contiguous()
     return ops.scn_node_forward(xs, d.rowptr, d.col, w, conv.lin_rel.weight, conv.lin_rel.bias, conv.lin_root.weight,
                                 out_lin.weight, out_lin.bias, act)
+
+
+def linear_act(lin, x: Tensor, act) -> Optional[Tensor]:
+    """act(lin(x)) for a `Linear` module in one launch (bias and activation in the GEMM epilogue) when the operator
+    set can fuse it; None otherwise.  `act` is a callable from config/config.py:13-18 (F.relu, F.elu, torch.tanh)."""
+    import torch.nn.functional as F
+    from .. import gemm
+    name = {F.relu: "relu", torch.relu: "relu", F.elu: "elu", torch.tanh: "tanh", F.tanh: "tanh"}.get(act)
+    if isinstance(act, torch.nn.Identity):
+        name = "identity"
+    if name is None or not x.is_cuda or x.dim() != 2 or x.dtype != torch.float32:
+        return None
+    lin.materialize(x.size(-1), x.device)
+    if not lin.weight.is_cuda:
+        return None
+    return gemm.linear_act(x, lin.weight, lin.bias, name)

@@ -293,6 +293,7 @@ class GATConv(MessagePassing):
         return out + bias if bias is not None else out
 
 
+FUSED_VIRTUAL = os.environ.get("GHSCN_FUSED_VIRTUAL", "1") != "0"
 PARALLEL_BRANCHES = os.environ.get("GHSCN_PARALLEL_BRANCHES", "1") != "0"
 PARALLEL_RELATIONS = os.environ.get("GHSCN_PARALLEL_RELATIONS", "1") != "0"
 _SIDE_STREAMS: Dict[Tuple[str, int], List["torch.cuda.Stream"]] = {}
@@ -347,9 +348,69 @@ class HeteroConv(nn.Module):
         # (models.HSCN / train.GraphHSCNStep); `last_streams` tells it which stream owns which output
         self.defer_join = False
         self.last_streams: Optional[Dict[str, "torch.cuda.Stream"]] = None
+        # extension (not in PyG): destination types whose output the caller passes through ReLU right away; the
+        # activation then runs inside this layer (in the fused operator's epilogue where there is one; same values)
+        self.fuse_relu_dst: set = set()
+
+    def _fused_virtual_plan(self, x_dict, edge_index_dict):
+        """Destination types that receive exactly {GCNConv on dst->dst (normalised, no self loops), single-head bipartite
+        GATConv on src->dst (no self loops)} under aggr='sum' -- the reference's "virtual" type (model/hscn.py:83-96)
+        -- are computed by ONE fused operator (ops.VirtualLayerFused).  -> {dst: (vv_type, lv_type)}"""
+        if not FUSED_VIRTUAL or self.aggr not in ("sum", "add"):
+            return {}
+        by_dst: Dict[str, List[Tuple[str, str, str]]] = defaultdict(list)
+        for et in edge_index_dict:
+            if "__".join(et) in self.convs:
+                by_dst[et[2]].append(et)
+        plan = {}
+        lib_ = None
+        for dst, ets in by_dst.items():
+            if len(ets) != 2:
+                continue
+            same = [e for e in ets if e[0] == dst]
+            cross = [e for e in ets if e[0] != dst]
+            if len(same) != 1 or len(cross) != 1 or ets[0] != same[0]:      # sum order: dst->dst first, then src->dst
+                continue
+            gcn, gat = self.convs["__".join(same[0])], self.convs["__".join(cross[0])]
+            if not (isinstance(gcn, GCNConv) and isinstance(gat, GATConv)):
+                continue
+            if not (gcn.normalize and not gcn.add_self_loops and not gcn.improved and not gcn.fuse_relu
+                    and gat.heads == 1 and not gat.add_self_loops and gat.lin_src is not gat.lin_dst):
+                continue
+            xs, xd = x_dict.get(cross[0][0]), x_dict.get(dst)
+            if not (isinstance(xs, Tensor) and isinstance(xd, Tensor) and xs.is_cuda and xd.is_cuda
+                    and xs.dtype == torch.float32 and xd.dtype == torch.float32 and xs.dim() == 2 and xd.dim() == 2
+                    and xs.size(1) == xd.size(1) and xd.size(0) > 0):
+                continue
+            if lib_ is None:
+                from .._lib import lib as _lib
+                lib_ = _lib()
+            f = xs.size(1)
+            if not lib_.query("ghscn_gat_pool_fused_supported", f, xs.stride(0), f):
+                continue
+            plan[dst] = (same[0], cross[0])
+        return plan
+
+    def _fused_virtual(self, dst: str, vv_type, lv_type, x_dict, edge_index_dict, relu: bool) -> Tensor:
+        gcn, gat = self.convs["__".join(vv_type)], self.convs["__".join(lv_type)]
+        xs, xd = x_dict[lv_type[0]], x_dict[dst]
+        vv_index, lv_index = edge_index_dict[vv_type], edge_index_dict[lv_type]
+        gcn.lin.materialize(xd.size(-1), xd.device)                 # lazy parameters in PyG's (relation) order
+        gat.lin_src.materialize(xs.size(-1), xs.device)
+        gat.lin_dst.materialize(xd.size(-1), xd.device)
+        V = xd.size(0)
+        st_vv = structure_cache().graph(vv_index, V, V, False)
+        vv_w, _, _ = st_vv.weights(None, normalize=True, need_transpose=False)
+        st_lv = structure_cache().graph(lv_index, xs.size(0), V, False)
+        meta = dict(gat=gat, gcn=gcn, vv_index=vv_index, lv_index=lv_index, lv_by_dst=st_lv.by_dst,
+                    vv_by_dst=st_vv.by_dst, vv_w=vv_w, slope=gat.negative_slope, relu=bool(relu))
+        return ops.VirtualLayerFused.apply(xs, xd, gat.lin_src.weight, gat.lin_dst.weight, gat.att_src.view(-1),
+                                           gat.att_dst.view(-1), gat.bias, gcn.lin.weight, gcn.bias, meta)
 
     def forward(self, x_dict: Dict[str, Tensor], edge_index_dict: Dict[Tuple[str, str, str], Tensor]
                 ) -> Dict[str, Tensor]:
+        fused = self._fused_virtual_plan(x_dict, edge_index_dict)
+        fused_types = {et for pair in fused.values() for et in pair}
         outs: Dict[str, List[Tensor]] = defaultdict(list)
         dsts: List[str] = []
         for edge_type in edge_index_dict:
@@ -381,7 +442,7 @@ class HeteroConv(nn.Module):
                 if "__".join(edge_type) not in self.convs:
                     continue
                 dst = edge_type[2]
-                if not PARALLEL_RELATIONS or all(t[2] != dst for t in rel_streams):
+                if not PARALLEL_RELATIONS or edge_type in fused_types or all(t[2] != dst for t in rel_streams):
                     rel_streams[edge_type] = streams[dst]
                     continue
                 r = _side_streams(main.device, extra + 1)[extra]
@@ -392,10 +453,25 @@ class HeteroConv(nn.Module):
                     r.wait_stream(streams[dst])
                 rel_streams[edge_type] = r
                 joins[dst].append(r)
+        relu_done = set()
         for edge_type, edge_index in edge_index_dict.items():
             src, _, dst = edge_type
             key = "__".join(edge_type)
             if key not in self.convs:
+                continue
+            if edge_type in fused_types:
+                vv_type, lv_type = fused[dst]
+                if edge_type != lv_type:                 # run once, at the second (src -> dst) relation of the pair
+                    continue
+                if streams is not None:
+                    _uses(x_dict[src], streams[dst])
+                    _uses(x_dict[dst], streams[dst])
+                with torch.cuda.stream(streams[dst]) if streams is not None else contextlib.nullcontext():
+                    out = self._fused_virtual(dst, vv_type, lv_type, x_dict, edge_index_dict,
+                                              relu=dst in self.fuse_relu_dst)
+                if dst in self.fuse_relu_dst:
+                    relu_done.add(dst)
+                outs[dst].append(out)
                 continue
             conv = self.convs[key]
             if streams is not None:          # inputs produced on another stream are read on this relation's stream
@@ -415,6 +491,8 @@ class HeteroConv(nn.Module):
                 for r in joins[key]:
                     streams[key].wait_stream(r)
                 result[key] = self._aggregate(xs)
+                if key in self.fuse_relu_dst and key not in relu_done:
+                    result[key] = result[key].relu()
         self.last_streams = streams
         if streams is not None and not self.defer_join:
             for dst in dsts[1:]:

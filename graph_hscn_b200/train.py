@@ -583,7 +583,12 @@ class GraphHSCNStep:
                                          num_graphs=shape.graphs + shape.dummies, x_float=x_f)
 
     def _task_loss(self, pred: Tensor, y: Tensor) -> Tensor:
-        if self.runner.shape.dummies:               # the dummy graphs' rows carry no loss and no gradient
+        """criterion(loss_fn, pred, true) of train/train.py:82 over the B real graphs (the dummy graphs' rows carry no
+        loss and no gradient); on CUDA the loss, its gradient and the sigmoid score come from one kernel."""
+        if (pred.is_cuda and pred.dim() == 2 and y.dim() == 2 and self.cfg.loss_fn in ops.LOSS_MODES
+                and os.environ.get("GHSCN_FUSED_LOSS", "1") != "0"):
+            return ops.graph_loss(self.cfg.loss_fn, pred, y, rows=self.B)[0]
+        if self.runner.shape.dummies:
             pred, y = pred[:self.B], y[:self.B]
         return models.criterion(self.cfg.loss_fn, pred, y)[0]
 

@@ -240,6 +240,53 @@ GHSCN_API size_t ghscn_grad_clip_workspace_bytes(int64_t n);
 GHSCN_API int ghscn_grad_clip_scale(const float* grad, int64_t n, float max_norm, void* workspace,
                                     size_t workspace_bytes, float* out, ghscn_stream_t stream);
 
+/* Fused forward of the same operator at the INPUT width (linearity of the pool in the source features):
+ *   u_src = W_src^T att_src, u_dst = W_dst^T att_dst                     (ghscn_gat_fold_attention, W [out, in])
+ *   pooled[r,:] = sum_s softmax_s(leaky_relu(<x_src[col[s]], u_src> + <x_dst[r], u_dst>)) x_src[col[s],:]
+ * so that out = pooled W_src^T + bias is one small GEMM.  One warp per destination row, one pass over its members
+ * (online softmax), replaces ghscn_row_dot x2 + ghscn_gat_scores + ghscn_spmm_pool.  x_dst / u_dst may both be NULL.
+ * Supported widths: <= 32 (any alignment) or a multiple of 4 up to 512 with 16-byte aligned rows. */
+GHSCN_API int ghscn_gat_fold_attention(const float* w_src, int64_t ldws, const float* att_src, const float* w_dst,
+                                       int64_t ldwd, const float* att_dst, int64_t out_feat, int64_t src_feat,
+                                       int64_t dst_feat, float* u_src, float* u_dst, ghscn_stream_t stream);
+GHSCN_API int ghscn_gat_pool_fused_supported(int64_t num_feat, int64_t ldxs, int64_t ldp);
+GHSCN_API int ghscn_gat_pool_fused_fwd(const int32_t* rowptr, const int32_t* col, const float* x_src, int64_t ldxs,
+                                       const float* x_dst, int64_t ldxd, const float* u_src, const float* u_dst,
+                                       float negative_slope, int64_t num_rows, int64_t num_feat, float* pooled,
+                                       int64_t ldp, ghscn_stream_t stream);
+
+/* ---- small dense layers + task loss (readout head, virtual-node projections) --------------------------------------
+ * Replaces the library GEMM + bias + activation kernels of `lin_1`, activation, `lin_2` on the [B, H] graph embeddings
+ * (model/hscn.py:99-100,112) and of the virtual-node projections (model/hscn.py:85-93), problems of 10^2..10^3 rows.
+ * fp32 FMA tiles, fixed reduction order.  act: 0 none, 1 ELU, 2 ReLU, 3 tanh (config/config.py:13-18).
+ *   fwd: y = act(x W^T + bias)                     x [rows, in], W [out, in], y [rows, out]
+ *   dx : dx = (dy (.) act'(y_ref)) W               y_ref = the forward's output (NULL with act 0)
+ *   dw : dW = (dy (.) act'(y_ref))^T x, db = column sums of the same (db may be NULL); rows are split into <= 8 slabs
+ *        whose partials are added in slab order (workspace needed only then) */
+GHSCN_API int ghscn_small_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
+                                     int32_t act, int64_t num_rows, int64_t in_feat, int64_t out_feat, float* y,
+                                     int64_t ldy, ghscn_stream_t stream);
+/* y = act(x1 W1^T + bias1 + x2 W2^T + bias2): the sum of two layers with the same destination rows in one launch
+ * (HeteroConv's `sum` over the v->v GCN and the l->v GAT pool, model/hscn.py:83-96; biases may be NULL). */
+GHSCN_API int ghscn_small_linear2_fwd(const float* x1, int64_t ldx1, const float* w1, int64_t ldw1, const float* bias1,
+                                      int64_t in_feat1, const float* x2, int64_t ldx2, const float* w2, int64_t ldw2,
+                                      const float* bias2, int64_t in_feat2, int32_t act, int64_t num_rows,
+                                      int64_t out_feat, float* y, int64_t ldy, ghscn_stream_t stream);
+GHSCN_API int ghscn_small_linear_dx(const float* dy, int64_t lddy, const float* y_ref, int64_t ldy, int32_t act,
+                                    const float* w, int64_t ldw, int64_t num_rows, int64_t in_feat, int64_t out_feat,
+                                    float* dx, int64_t lddx, ghscn_stream_t stream);
+GHSCN_API size_t ghscn_small_linear_dw_workspace_bytes(int64_t num_rows, int64_t in_feat, int64_t out_feat);
+GHSCN_API int ghscn_small_linear_dw(const float* dy, int64_t lddy, const float* y_ref, int64_t ldy, int32_t act,
+                                    const float* x, int64_t ldx, int64_t num_rows, int64_t in_feat, int64_t out_feat,
+                                    float* dw, float* db, void* workspace, size_t workspace_bytes,
+                                    ghscn_stream_t stream);
+/* criterion(loss_fn, pred, true) of loss.py:6-19 over the first `rows` of `total_rows` rows (the rest are padding
+ * graphs): mode 0 = binary_cross_entropy_with_logits, mode 1 = l1_loss, mean reduction.  loss [1]; d_pred
+ * [total_rows, num_targets] = d loss / d pred (zero in the padding rows); score (may be NULL) = sigmoid(pred). */
+GHSCN_API int ghscn_graph_loss(const float* pred, int64_t ldp, const float* target, int64_t ldt, int64_t rows,
+                               int64_t total_rows, int64_t num_targets, int32_t mode, float* loss, float* d_pred,
+                               float* score, ghscn_stream_t stream);
+
 /* ---- K5: bipartite GAT cluster pool (local -> virtual) ---------------------------------------
  * Replaces GATConv((-1,-1), H, add_self_loops=False) on ("local","to","virtual")
  * (model/hscn.py:85-87,118-125).  SURVEY 8a row a9, Appendix A.8.  heads = 1.

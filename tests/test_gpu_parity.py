@@ -602,7 +602,8 @@ def test_hscn_model_fwd_bwd(cuda):
     xr = ref.convs[0](hb_cpu.x_dict, hb_cpu.edge_index_dict)
     xt = tst.convs[0](hb.x_dict, hb.edge_index_dict)
     assert set(xr) == set(xt) == {"local", "virtual"}
-    assert_close(xt["virtual"], xr["virtual"], RTOL, "HeteroConv virtual")
+    want_virtual = xr["virtual"].relu() if tst._fused_virtual else xr["virtual"]
+    assert_close(xt["virtual"], want_virtual, RTOL, "HeteroConv virtual")
     # the mirror model lets the l->l GCN apply the following ReLU in its aggregation epilogue
     want_local = xr["local"].relu() if tst._fused_local else xr["local"]
     assert_close(xt["local"], want_local, RTOL, "HeteroConv local")
@@ -615,6 +616,59 @@ def test_hscn_model_fwd_bwd(cuda):
             assert p2.grad is None or float(p2.grad.abs().max()) == 0.0, n1   # dead virtual branch
         else:
             assert_close(p2.grad, p1.grad, 10 * RTOL, f"HSCN grad {n1}")
+
+
+@pytest.mark.parametrize("width,fuse_relu", [(9, False), (48, True), (300, True)])
+def test_fused_virtual_layer_matches_unfused_and_oracle(cuda, width, fuse_relu):
+    """HeteroConv computes the "virtual" destination (v->v GCN + l->v GAT pool, summed) with ONE fused operator at the
+    input width: outputs vs the oracle's HeteroConv, and -- through the fused operator's backward -- the gradients of
+    every virtual-branch parameter and of both inputs."""
+    from graph_hscn_b200 import hetero
+    from graph_hscn_b200.pyg import nn as pnn
+    o, p = _oracle(), _product()
+    K, H = 10, 64
+    b = _peptide_batch(9, seed=17)
+    g = torch.Generator().manual_seed(width)
+    clusters = torch.randint(0, K, (b.x.size(0),), generator=g).int()
+    hb = hetero.build_hetero_batch(b.x.to(cuda), b.edge_index.to(cuda), b.batch.to(cuda), clusters.to(cuda), K)
+    hb_cpu = hb.to("cpu")
+    N, V = hb_cpu["local"].x.size(0), hb_cpu["virtual"].x.size(0)
+    xl, xv = torch.randn(N, width, generator=g), torch.randn(V, width, generator=g)
+
+    def build(ns):
+        return ns.HeteroConv({("local", "to", "virtual"): ns.GATConv((-1, -1), H, add_self_loops=False),
+                              ("local", "to", "local"): ns.GCNConv(-1, H, add_self_loops=False),
+                              ("virtual", "to", "virtual"): ns.GCNConv(-1, H, add_self_loops=False)}, aggr="sum")
+    ref, tst = _to_dev(lambda: build(o), lambda: build(p), cuda,
+                       lambda m, d: m({"local": xl.to(d), "virtual": xv.to(d)},
+                                      hb_cpu.edge_index_dict if d == "cpu" else hb.edge_index_dict))
+    if fuse_relu:
+        tst.fuse_relu_dst = {"virtual"}
+    xlr, xvr = xl.clone().requires_grad_(), xv.clone().requires_grad_()
+    xlt, xvt = xl.to(cuda).requires_grad_(), xv.to(cuda).requires_grad_()
+    assert tst._fused_virtual_plan({"local": xlt, "virtual": xvt}, hb.edge_index_dict), "fused path not taken"
+    yr = ref({"local": xlr, "virtual": xvr}, hb_cpu.edge_index_dict)["virtual"]
+    if fuse_relu:
+        yr = yr.relu()
+    yt = tst({"local": xlt, "virtual": xvt}, hb.edge_index_dict)["virtual"]
+    assert_close(yt, yr, RTOL, "fused virtual output")
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    yt.backward(gy.to(cuda))
+    assert_close(xlt.grad, xlr.grad, 5 * RTOL, "d x_local")
+    assert_close(xvt.grad, xvr.grad, 5 * RTOL, "d x_virtual")
+    for (n1, p1), (_, p2) in zip(ref.named_parameters(), tst.named_parameters()):
+        if "local__to__local" in n1:
+            continue
+        assert_close(p2.grad, p1.grad, 5 * RTOL, f"virtual-branch grad {n1}")
+    # and the unfused schedule gives the same numbers
+    old = pnn.FUSED_VIRTUAL
+    pnn.FUSED_VIRTUAL = False
+    try:
+        yu = tst({"local": xlt.detach(), "virtual": xvt.detach()}, hb.edge_index_dict)["virtual"]
+    finally:
+        pnn.FUSED_VIRTUAL = old
+    assert_close(yu, yt.detach(), RTOL, "fused vs unfused")
 
 
 def test_cpu_tensor_fails_loudly(cuda):

@@ -238,3 +238,53 @@ def test_batch_to_device_registers_the_fast_csr_path(cuda):
     ei_plain = b.edge_index.clone()                      # an unregistered copy of the same edges: radix path
     assert structure_cache().graph(ei_plain, N, N, True)._plain._blocks is None
     assert torch.equal(conv(b.x.float(), ei_plain), y_fast)
+
+
+@pytest.mark.parametrize("rows,k,m,act", [(129, 300, 300, "relu"), (129, 300, 10, None), (1290, 600, 300, "relu"),
+                                          (1027, 300, 300, "elu"), (7, 5, 3, "tanh"), (300, 18, 300, None)])
+def test_small_linear_fwd_bwd(cuda, rows, k, m, act):
+    """csrc/dense_small.cu (graph-level head, virtual-node projections) vs an fp64 torch reference: output, dx, dW, db
+    with the activation folded into the kernels."""
+    import torch.nn.functional as F
+    from graph_hscn_b200 import gemm
+    g = torch.Generator().manual_seed(rows + k)
+    x = torch.randn(rows, k, generator=g)
+    w = torch.randn(m, k, generator=g) / k ** 0.5
+    b = torch.randn(m, generator=g)
+    gy = torch.randn(rows, m, generator=g)
+    fn = {"relu": F.relu, "elu": F.elu, "tanh": torch.tanh, None: lambda t: t}[act]
+    xr, wr, br = (t.double().requires_grad_() for t in (x, w, b))
+    yr = fn(F.linear(xr, wr, br))
+    yr.backward(gy.double())
+    xt, wt, bt = (t.to(cuda).requires_grad_() for t in (x, w, b))
+    yt = gemm.linear_act(xt, wt, bt, act)
+    assert yt is not None
+    yt.backward(gy.to(cuda))
+    assert_close(yt, yr.float(), 2e-6, "small linear out")
+    assert_close(xt.grad, xr.grad.float(), 2e-6, "small linear dx")
+    assert_close(wt.grad, wr.grad.float(), 2e-6, "small linear dW")
+    assert_close(bt.grad, br.grad.float(), 2e-6, "small linear db")
+    # the plain dispatcher takes the same kernels for < 4 k rows
+    y2 = gemm.linear(x.to(cuda), w.to(cuda), b.to(cuda))
+    assert_close(y2, F.linear(x.double(), w.double(), b.double()).float(), 2e-6, "gemm.linear small path")
+
+
+@pytest.mark.parametrize("loss_fn,rows,total,c", [("cross_entropy", 128, 129, 10), ("l1", 1024, 1027, 11),
+                                                  ("cross_entropy", 5, 5, 3)])
+def test_graph_loss_matches_criterion(cuda, loss_fn, rows, total, c):
+    """Fused task loss (loss.py:6-19): value, sigmoid score and gradient vs models.criterion on the first `rows` rows;
+    padding rows get zero gradient."""
+    from graph_hscn_b200 import models, ops
+    g = torch.Generator().manual_seed(total)
+    pred = torch.randn(total, c, generator=g) * 3
+    y = (torch.rand(total, c, generator=g) < 0.3).float() if loss_fn == "cross_entropy" else torch.randn(total, c, generator=g)
+    pr = pred.clone().requires_grad_()
+    lr, sr = models.criterion(loss_fn, pr[:rows], y[:rows])
+    (lr * 1.7).backward()
+    pt = pred.to(cuda).requires_grad_()
+    lt, st_ = ops.graph_loss(loss_fn, pt, y.to(cuda), rows=rows)
+    (lt * 1.7).backward()
+    assert_close(lt, lr, 1e-6, "loss")
+    assert_close(st_, sr, 1e-6, "score")
+    assert_close(pt.grad, pr.grad, 1e-6, "d pred")
+    assert not pt.grad[rows:].any()
