@@ -143,10 +143,11 @@ __global__ void __launch_bounds__(256) gat_pool_fused_kernel(const int* __restri
                                                              const float* __restrict__ u_dst, float slope,
                                                              int num_rows, int num_feat, float* __restrict__ pooled,
                                                              int64_t ldp) {
-  const int lane = threadIdx.x & 31;
-  const int row = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
-  if (row >= num_rows) return;
   constexpr int W = VEC * ITERS;
+  constexpr int kLong = 32;                              // rows with more members are pooled by the whole CTA
+  extern __shared__ float part[];                        // [8 warps][2 + 32 * W]: (m, ssum, acc...) per warp
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * 8;
   auto load_row = [&](const float* p, float (&dst)[W]) {
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
@@ -160,82 +161,138 @@ __global__ void __launch_bounds__(256) gat_pool_fused_kernel(const int* __restri
       }
     }
   };
-  float us[W], ud[W], xd[W];
+  float us[W];
   load_row(u_src, us);
-  float ad = 0.f;
-  if (x_dst != nullptr && u_dst != nullptr) {
-    load_row(u_dst, ud);
-    load_row(x_dst + (int64_t)row * ldxd, xd);
+  // online-softmax pool of the members s = s_beg, s_beg + stride, ... < s_end of destination `row`
+  float m, ssum, acc[W];
+  auto pool = [&](int row, int s_beg, int s_end, int stride) {
+    float ad = 0.f;
+    if (x_dst != nullptr && u_dst != nullptr) {
+      float ud[W], xd[W];
+      load_row(u_dst, ud);
+      load_row(x_dst + (int64_t)row * ldxd, xd);
 #pragma unroll
-    for (int j = 0; j < W; ++j) ad = fmaf(xd[j], ud[j], ad);
-    ad = warp_sum(ad);
-  }
-  const int beg = rowptr[row], end = rowptr[row + 1];
-  float m = -INFINITY, ssum = 0.f, acc[W];
+      for (int j = 0; j < W; ++j) ad = fmaf(xd[j], ud[j], ad);
+      ad = warp_sum(ad);
+    }
+    m = -INFINITY;
+    ssum = 0.f;
 #pragma unroll
-  for (int j = 0; j < W; ++j) acc[j] = 0.f;
-  for (int s = beg; s < end; s += 4) {
-    const int n4 = min(4, end - s);
-    float v[4][W];
+    for (int j = 0; j < W; ++j) acc[j] = 0.f;
+    for (int s = s_beg; s < s_end; s += 4 * stride) {
+      float v[4][W];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (k < n4) load_row(x_src + (int64_t)col[s + k] * ldxs, v[k]);
+      for (int k = 0; k < 4; ++k)
+        if (s + k * stride < s_end) load_row(x_src + (int64_t)col[s + k * stride] * ldxs, v[k]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k < n4) {
-        float d = 0.f;
+      for (int k = 0; k < 4; ++k) {
+        if (s + k * stride < s_end) {
+          float d = 0.f;
 #pragma unroll
-        for (int j = 0; j < W; ++j) d = fmaf(v[k][j], us[j], d);
-        d = warp_sum(d);
-        const float z = d + ad;
-        const float e = z > 0.f ? z : z * slope;
-        if (e > m) {                                     // warp-uniform: every lane holds the same e and m
-          const float sc = expf(m - e);                  // m = -inf on the first member: exp(-inf) = 0
-          ssum *= sc;
+          for (int j = 0; j < W; ++j) d = fmaf(v[k][j], us[j], d);
+          d = warp_sum(d);
+          const float z = d + ad;
+          const float e = z > 0.f ? z : z * slope;
+          if (e > m) {                                   // warp-uniform: every lane holds the same e and m
+            const float sc = expf(m - e);                // m = -inf on the first member: exp(-inf) = 0
+            ssum *= sc;
 #pragma unroll
-          for (int j = 0; j < W; ++j) acc[j] *= sc;
-          m = e;
+            for (int j = 0; j < W; ++j) acc[j] *= sc;
+            m = e;
+          }
+          const float p = expf(e - m);
+          ssum += p;
+#pragma unroll
+          for (int j = 0; j < W; ++j) acc[j] = fmaf(p, v[k][j], acc[j]);
         }
-        const float p = expf(e - m);
-        ssum += p;
+      }
+    }
+  };
+  auto store = [&](int row, float inv) {
+    float* out = pooled + (int64_t)row * ldp;
 #pragma unroll
-        for (int j = 0; j < W; ++j) acc[j] = fmaf(p, v[k][j], acc[j]);
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = (it * 32 + lane) * VEC;
+      if (c < num_feat) {
+        if constexpr (VEC == 4) {
+          *reinterpret_cast<float4*>(out + c) = make_float4(acc[it * 4] * inv, acc[it * 4 + 1] * inv,
+                                                            acc[it * 4 + 2] * inv, acc[it * 4 + 3] * inv);
+        } else {
+          out[c] = acc[it] * inv;
+        }
+      }
+    }
+  };
+  // ---- short rows: one warp each, in one pass
+  {
+    const int row = row0 + wid;
+    if (row < num_rows) {
+      const int beg = rowptr[row], end = rowptr[row + 1];
+      if (end - beg <= kLong) {
+        pool(row, beg, end, 1);
+        store(row, 1.0f / (ssum + 1e-16f));              // PyG softmax: + 1e-16 in the denominator
       }
     }
   }
-  const float inv = 1.0f / (ssum + 1e-16f);              // PyG softmax: + 1e-16 in the denominator
-  float* out = pooled + (int64_t)row * ldp;
+  // ---- long rows (a cluster that swallowed most of its graph): the 8 warps take every 8th member each and their
+  //      (max, sum, weighted sum) partials are merged in warp order -- the log-sum-exp merge, deterministic
+  for (int r = 0; r < 8; ++r) {
+    const int row = row0 + r;
+    if (row >= num_rows) break;
+    const int beg = rowptr[row], end = rowptr[row + 1];
+    if (end - beg <= kLong) continue;                    // CTA-uniform
+    pool(row, beg + wid, end, 8);
+    float* mine = part + wid * (2 + 32 * W);
+    if (lane == 0) { mine[0] = m; mine[1] = ssum; }
 #pragma unroll
-  for (int it = 0; it < ITERS; ++it) {
-    const int c = (it * 32 + lane) * VEC;
-    if (c < num_feat) {
-      if constexpr (VEC == 4) {
-        *reinterpret_cast<float4*>(out + c) = make_float4(acc[it * 4] * inv, acc[it * 4 + 1] * inv,
-                                                          acc[it * 4 + 2] * inv, acc[it * 4 + 3] * inv);
-      } else {
-        out[c] = acc[it] * inv;
+    for (int j = 0; j < W; ++j) mine[2 + j * 32 + lane] = acc[j];
+    __syncthreads();
+    if (wid == 0) {
+      float mm = -INFINITY;
+      for (int w = 0; w < 8; ++w) mm = fmaxf(mm, part[w * (2 + 32 * W)]);
+      float tot = 0.f;
+#pragma unroll
+      for (int j = 0; j < W; ++j) acc[j] = 0.f;
+      for (int w = 0; w < 8; ++w) {
+        const float* pw = part + w * (2 + 32 * W);
+        const float sc = pw[1] > 0.f ? expf(pw[0] - mm) : 0.f;   // a warp without members holds (m = -inf, sum = 0)
+        tot = fmaf(pw[1], sc, tot);
+#pragma unroll
+        for (int j = 0; j < W; ++j) acc[j] = fmaf(pw[2 + j * 32 + lane], sc, acc[j]);
       }
+      store(row, 1.0f / (tot + 1e-16f));
     }
+    __syncthreads();
   }
 }
 
 // u_src[f] = sum_h att_src[h] W_src[h, f],  u_dst[f] = sum_h att_dst[h] W_dst[h, f]   (W [H, F] row-major)
-__global__ void __launch_bounds__(128) gat_fold_attention_kernel(const float* __restrict__ w_src, int64_t ldws,
+// CTA = 32 columns x 8 row groups: the 8 partial sums of a column are added in group order (deterministic).
+__global__ void __launch_bounds__(256) gat_fold_attention_kernel(const float* __restrict__ w_src, int64_t ldws,
                                                                  const float* __restrict__ att_src,
                                                                  const float* __restrict__ w_dst, int64_t ldwd,
                                                                  const float* __restrict__ att_dst, int H, int Fs,
                                                                  int Fd, float* __restrict__ u_src,
                                                                  float* __restrict__ u_dst) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float red[8][33];
+  const int fx = threadIdx.x & 31, hg = threadIdx.x >> 5;
+  const int f = blockIdx.x * 32 + fx;
   const bool dst_side = blockIdx.y == 1;
   const float* w = dst_side ? w_dst : w_src;
   const float* att = dst_side ? att_dst : att_src;
   const int64_t ld = dst_side ? ldwd : ldws;
   const int F = dst_side ? Fd : Fs;
-  if (w == nullptr || f >= F) return;
   float acc = 0.f;
-  for (int h = 0; h < H; ++h) acc = fmaf(att[h], w[(int64_t)h * ld + f], acc);
-  (dst_side ? u_dst : u_src)[f] = acc;
+  if (w != nullptr && f < F)
+    for (int h = hg; h < H; h += 8) acc = fmaf(__ldg(att + h), __ldg(w + (int64_t)h * ld + f), acc);
+  red[hg][fx] = acc;
+  __syncthreads();
+  if (hg == 0 && w != nullptr && f < F) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][fx];
+    (dst_side ? u_dst : u_src)[f] = t;
+  }
 }
 
 // map_t[t] = slot (in the by-destination structure) of the edge sitting in transposed slot t.
@@ -302,8 +359,8 @@ int ghscn_gat_fold_attention(const float* w_src, int64_t ldws, const float* att_
   GHSCN_REQUIRE(out_feat > 0 && src_feat > 0 && dst_feat >= 0 && w_src && att_src && u_src && ldws >= src_feat);
   GHSCN_REQUIRE(w_dst == nullptr || (att_dst && u_dst && ldwd >= dst_feat && dst_feat > 0));
   const int64_t fmax = src_feat > dst_feat ? src_feat : dst_feat;
-  dim3 grid((unsigned)ceil_div<int64_t>(fmax, 128), w_dst ? 2u : 1u);
-  gat_fold_attention_kernel<<<grid, 128, 0, as_stream(stream)>>>(w_src, ldws, att_src, w_dst, ldwd, att_dst,
+  dim3 grid((unsigned)ceil_div<int64_t>(fmax, 32), w_dst ? 2u : 1u);
+  gat_fold_attention_kernel<<<grid, 256, 0, as_stream(stream)>>>(w_src, ldws, att_src, w_dst, ldwd, att_dst,
                                                                  (int)out_feat, (int)src_feat, (int)dst_feat, u_src,
                                                                  u_dst);
   GHSCN_LAUNCH_CHECK();
@@ -327,9 +384,8 @@ int ghscn_gat_pool_fused_fwd(const int32_t* rowptr, const int32_t* col, const fl
   cudaStream_t stream = as_stream(stream_);
   const unsigned blocks = (unsigned)ceil_div<int64_t>(num_rows, 8);
 #define GHSCN_POOL_LAUNCH(VEC, ITERS)                                                                          \
-  gat_pool_fused_kernel<VEC, ITERS><<<blocks, 256, 0, stream>>>(rowptr, col, x_src, ldxs, x_dst, ldxd, u_src,  \
-                                                                u_dst, negative_slope, (int)num_rows,          \
-                                                                (int)num_feat, pooled, ldp)
+  gat_pool_fused_kernel<VEC, ITERS><<<blocks, 256, 8 * (2 + 32 * (VEC) * (ITERS)) * 4, stream>>>(              \
+      rowptr, col, x_src, ldxs, x_dst, ldxd, u_src, u_dst, negative_slope, (int)num_rows, (int)num_feat, pooled, ldp)
   const bool vec4 = num_feat % 4 == 0 && ldxs % 4 == 0 && ldp % 4 == 0 && (x_dst == nullptr || ldxd % 4 == 0) &&
                     ((reinterpret_cast<uintptr_t>(x_src) | reinterpret_cast<uintptr_t>(x_dst) |
                       reinterpret_cast<uintptr_t>(pooled) | reinterpret_cast<uintptr_t>(u_src) |

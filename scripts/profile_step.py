@@ -9,11 +9,12 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
-from graph_hscn_b200.train import GraphHSCNStep, StepConfig  # noqa: E402
+from graph_hscn_b200.train import BucketPolicy, GraphHSCNStep, StepConfig  # noqa: E402
 
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda:0")
-step = GraphHSCNStep(StepConfig(), bench.make_batch(0), dev, padded=True)
+batch = bench.make_batches(0, 1, count=int(os.environ.get("PROFILE_BATCH", "0")) + 1)[-1]
+step = GraphHSCNStep(StepConfig(), batch, dev, padded=True, policy=BucketPolicy(444, 1024))
 step.capture(warmup=3)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for _ in range(5):
