@@ -48,6 +48,7 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_skinny_linear_dx": (I32, [P, I64, P, I64, I64, I64, P, I64, P]),
     "ghscn_adamw_step": (I32, [P, P, P, P, I64, F64, F64, F64, F64, F64, P, P]),
     "ghscn_adamw_step_scaled": (I32, [P, P, P, P, I64, F64, F64, F64, F64, F64, P, P, P]),
+    "ghscn_gather_flat": (I32, [P, P, I32, P, P]),
     "ghscn_grad_clip_workspace_bytes": (SZ, [I64]),
     "ghscn_grad_clip_scale": (I32, [P, I64, F32, P, SZ, P, P]),
     "ghscn_small_linear_fwd": (I32, [P, I64, P, I64, P, I32, I64, I64, I64, P, I64, P]),
@@ -64,6 +65,9 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_edge_weights": (I32, [P, P, P, P, P, P, I64, I64, I32, I32, P, P]),
     "ghscn_loop_weights": (I32, [P, P, P, I64, I64, F32, P, P, P]),
     "ghscn_spmm": (I32, [P, P, P, P, I64, P, I64, P, I64, I64, I32, P]),
+    "ghscn_spmm_masked_supported": (I32, [I64, I64, I64, I64]),
+    "ghscn_spmm_masked": (I32, [P, P, P, P, I64, P, I64, P, I64, I64, I64, P]),
+    "ghscn_colsum_masked": (I32, [P, I64, P, I64, I64, I64, P, P, SZ, P]),
     "ghscn_spmm_pool": (I32, [P, P, P, P, I64, P, I64, P, I64, I64, P]),
     "ghscn_gat_scores": (I32, [P, P, P, P, F32, I64, P, P]),
     "ghscn_spmm_edge_grad": (I32, [P, P, P, P, I64, P, I64, I64, I64, I64, P, P]),

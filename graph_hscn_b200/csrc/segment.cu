@@ -120,7 +120,9 @@ constexpr int kColsumRows = 256;  // rows per CTA (32 per warp)
 template <int VEC>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int64_t ldx,
                                                              int num_rows, int num_feat,
-                                                             float* __restrict__ partial) {
+                                                             float* __restrict__ partial,
+                                                             const float* __restrict__ mask = nullptr,
+                                                             int64_t ldm = 0) {
   __shared__ float part[8][32 * VEC];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = (blockIdx.x * 32 + lane) * VEC;
@@ -135,10 +137,17 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
       const int r = r0 + k * 8 + wid;
       if (r < num_rows) {
         if (VEC == 4) {
-          const float4 a = ldg_f4(x + (int64_t)r * ldx + f);
+          float4 a = ldg_f4(x + (int64_t)r * ldx + f);
+          if (mask != nullptr) {                    // ReLU backward folded in: rows of x count where mask > 0
+            const float4 m = ldg_f4(mask + (int64_t)r * ldm + f);
+            a.x = m.x > 0.f ? a.x : 0.f; a.y = m.y > 0.f ? a.y : 0.f;
+            a.z = m.z > 0.f ? a.z : 0.f; a.w = m.w > 0.f ? a.w : 0.f;
+          }
           acc[0] += a.x; acc[1 % VEC] += a.y; acc[2 % VEC] += a.z; acc[3 % VEC] += a.w;
         } else {
-          acc[0] += __ldg(x + (int64_t)r * ldx + f);
+          float a = __ldg(x + (int64_t)r * ldx + f);
+          if (mask != nullptr && !(__ldg(mask + (int64_t)r * ldm + f) > 0.f)) a = 0.f;
+          acc[0] += a;
         }
       }
     }
@@ -344,9 +353,16 @@ size_t ghscn_colsum_workspace_bytes(int64_t num_rows, int64_t num_feat) {
 
 int ghscn_colsum(const float* x, int64_t ldx, int64_t num_rows, int64_t num_feat, float* out, void* workspace,
                  size_t workspace_bytes, ghscn_stream_t stream_) {
+  return ghscn_colsum_masked(x, ldx, nullptr, 0, num_rows, num_feat, out, workspace, workspace_bytes, stream_);
+}
+
+int ghscn_colsum_masked(const float* x, int64_t ldx, const float* mask, int64_t ldm, int64_t num_rows,
+                        int64_t num_feat, float* out, void* workspace, size_t workspace_bytes,
+                        ghscn_stream_t stream_) {
   GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && num_rows < ((int64_t)1 << 31) && num_feat < ((int64_t)1 << 24));
   if (num_feat == 0) return GHSCN_OK;
   GHSCN_REQUIRE(out && (num_rows == 0 || (x && ldx >= num_feat)));
+  GHSCN_REQUIRE(mask == nullptr || ldm >= num_feat);
   if (workspace_bytes < ghscn_colsum_workspace_bytes(num_rows, num_feat) || workspace == nullptr)
     return GHSCN_E_WORKSPACE;
   cudaStream_t stream = as_stream(stream_);
@@ -354,13 +370,14 @@ int ghscn_colsum(const float* x, int64_t ldx, int64_t num_rows, int64_t num_feat
   const int chunks = (int)ceil_div<int64_t>(num_rows, kColsumRows);
   if (chunks > 65535) return GHSCN_E_UNSUPPORTED;
   if (chunks > 0) {
-    const bool vec4 = num_feat % 4 == 0 && ldx % 4 == 0 && aligned16(x, x);
+    const bool vec4 = num_feat % 4 == 0 && ldx % 4 == 0 && aligned16(x, x) &&
+                      (mask == nullptr || (ldm % 4 == 0 && aligned16(mask, mask)));
     if (vec4) {
       dim3 grid((unsigned)ceil_div<int64_t>(num_feat, 128), (unsigned)chunks);
-      colsum_partial_kernel<4><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial);
+      colsum_partial_kernel<4><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial, mask, ldm);
     } else {
       dim3 grid((unsigned)ceil_div<int64_t>(num_feat, 32), (unsigned)chunks);
-      colsum_partial_kernel<1><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial);
+      colsum_partial_kernel<1><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial, mask, ldm);
     }
   }
   colsum_final_kernel<<<(unsigned)ceil_div<int64_t>(num_feat, 32), 256, 0, stream>>>(partial, chunks,

@@ -521,3 +521,61 @@ extern "C" int ghscn_adamw_step(float* param, const float* grad, float* exp_avg,
   return ghscn_adamw_step_scaled(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, state,
                                  nullptr, stream_);
 }
+
+// ---- gradients of many parameters -> one flat buffer ---------------------------------------------------------------
+// `torch.autograd.grad` hands the step its gradients as separate tensors; the flat-buffer optimizer / all-reduce wants
+// them back to back.  One launch copies up to 64 tensors: their device pointers and sizes travel as kernel arguments
+// (no device-side table to upload, so the call is CUDA-graph capturable and needs no host synchronisation).
+namespace ghscn {
+constexpr int kGatherMax = 64;
+struct GatherArgs {
+  const float* src[kGatherMax];
+  long long off[kGatherMax + 1];       // element offsets inside the flat destination (prefix sums)
+  int count;
+};
+__global__ void __launch_bounds__(256) gather_flat_kernel(GatherArgs a, float* __restrict__ dst) {
+  const long long total = a.off[a.count];
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total;
+       i += (long long)gridDim.x * blockDim.x * 4) {
+    int lo = 0, hi = a.count - 1;                     // tensor holding element i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (a.off[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long j = i + u;
+      if (j >= total) break;
+      while (j >= a.off[lo + 1]) ++lo;
+      dst[j] = a.src[lo][j - a.off[lo]];
+    }
+  }
+}
+}  // namespace ghscn
+
+extern "C" int ghscn_gather_flat(const float* const* srcs_host, const int64_t* numels_host, int32_t count, float* dst,
+                                 ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(count >= 0 && (count == 0 || (srcs_host && numels_host && dst)));
+  cudaStream_t stream = ghscn::as_stream(stream_);
+  int launches = 0;
+  int64_t base = 0;
+  for (int first = 0; first < count; first += ghscn::kGatherMax) {
+    ghscn::GatherArgs a;
+    a.count = count - first < ghscn::kGatherMax ? count - first : ghscn::kGatherMax;
+    a.off[0] = 0;
+    for (int i = 0; i < a.count; ++i) {
+      GHSCN_REQUIRE(numels_host[first + i] >= 0 && (numels_host[first + i] == 0 || srcs_host[first + i]));
+      a.src[i] = srcs_host[first + i];
+      a.off[i + 1] = a.off[i] + numels_host[first + i];
+    }
+    const long long total = a.off[a.count];
+    if (total > 0) {
+      const long long blocks = (total + 1023) / 1024;
+      ghscn::gather_flat_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, stream>>>(a, dst + base);
+      ++launches;
+    }
+    base += total;
+  }
+  if (launches) GHSCN_LAUNCH_CHECK_N(launches);
+  return GHSCN_OK;
+}

@@ -154,11 +154,14 @@ static inline int wide_rows() {
   return v;
 }
 
-template <int ITERS, bool WEIGHTED, int ROWS>
+// MASKED: every gathered row is multiplied by (mask[row] > 0) as it is read -- the backward of a ReLU that was fused
+// into the forward aggregation (dy (.) [y > 0]) without a separate pass over dy.
+template <int ITERS, bool WEIGHTED, int ROWS, bool MASKED = false>
 __global__ void __launch_bounds__(ROWS * 4, ROWS == 64 ? 2 : (ROWS == 32 ? 5 : 10))   // 16 / 20 / 20 warps per SM
     spmm_wide_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ w,
                      const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy,
-                     const float* __restrict__ bias, int num_rows, int num_feat, int relu) {
+                     const float* __restrict__ bias, int num_rows, int num_feat, int relu,
+                     const float* __restrict__ mask = nullptr, int64_t ldm = 0) {
   constexpr int kWideRows = ROWS, kThreads = ROWS * 4, kSlotCap = ROWS * 16;
   __shared__ int s_rowptr[kWideRows + 1];
   __shared__ int s_col[kSlotCap];
@@ -219,7 +222,16 @@ __global__ void __launch_bounds__(ROWS * 4, ROWS == 64 ? 2 : (ROWS == 32 ? 5 : 1
         const float* xr = x + (int64_t)c * ldx + f0;
 #pragma unroll
         for (int it = 0; it < ITERS; ++it)
-          if (f0 + it * 128 < num_feat) v[k][it] = ldg_f4(xr + it * 128);
+          if (f0 + it * 128 < num_feat) {
+            v[k][it] = ldg_f4(xr + it * 128);
+            if (MASKED) {
+              const float4 m = ldg_f4(mask + (int64_t)c * ldm + f0 + it * 128);
+              v[k][it].x = m.x > 0.f ? v[k][it].x : 0.f;
+              v[k][it].y = m.y > 0.f ? v[k][it].y : 0.f;
+              v[k][it].z = m.z > 0.f ? v[k][it].z : 0.f;
+              v[k][it].w = m.w > 0.f ? v[k][it].w : 0.f;
+            }
+          }
       }
     }
 #pragma unroll
@@ -558,6 +570,21 @@ static int launch_spmm_wide(const int* rowptr, const int* col, const float* w, c
   }
 }
 
+template <int ITERS>
+static int launch_spmm_wide_masked(const int* rowptr, const int* col, const float* w, const float* x, int64_t ldx,
+                                   const float* mask, int64_t ldm, float* y, int64_t ldy, int64_t num_rows,
+                                   int64_t num_feat, cudaStream_t stream) {
+  dim3 grid((unsigned)ceil_div<int64_t>(num_rows, 32), (unsigned)ceil_div<int64_t>(num_feat, 128 * ITERS));
+  if (w)
+    spmm_wide_kernel<ITERS, true, 32, true><<<grid, 128, 0, stream>>>(rowptr, col, w, x, ldx, y, ldy, nullptr,
+                                                                      (int)num_rows, (int)num_feat, 0, mask, ldm);
+  else
+    spmm_wide_kernel<ITERS, false, 32, true><<<grid, 128, 0, stream>>>(rowptr, col, w, x, ldx, y, ldy, nullptr,
+                                                                       (int)num_rows, (int)num_feat, 0, mask, ldm);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
 // ---- few long rows (pooling relations: every destination has many sources) ------------------------------
 // One CTA per row: its 8 warps stride the row's slots, each keeps full-width partial sums, and the partials are
 // combined in fixed warp order (deterministic; not the sequential CPU order, which pooled rows do not need).
@@ -736,6 +763,28 @@ int ghscn_spmm(const int32_t* rowptr, const int32_t* col, const float* w, const 
   if (vec4)
     return dispatch_spmm<4>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, as_stream(stream));
   return dispatch_spmm<1>(rowptr, col, w, x, ldx, y, ldy, bias, num_rows, num_feat, relu, as_stream(stream));
+}
+
+int ghscn_spmm_masked_supported(int64_t num_feat, int64_t ldx, int64_t ldm, int64_t ldy) {
+  return num_feat >= 128 && num_feat <= 512 && num_feat % 4 == 0 && ldx % 4 == 0 && ldm % 4 == 0 && ldy % 4 == 0;
+}
+
+int ghscn_spmm_masked(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, int64_t ldx,
+                      const float* mask, int64_t ldm, float* y, int64_t ldy, int64_t num_rows, int64_t num_feat,
+                      ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_feat > 0 && ldx >= num_feat && ldy >= num_feat && ldm >= num_feat);
+  GHSCN_REQUIRE(num_rows < ((int64_t)1 << 31));
+  if (!ghscn_spmm_masked_supported(num_feat, ldx, ldm, ldy)) return GHSCN_E_UNSUPPORTED;
+  if (num_rows == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(rowptr && x && y && mask);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(mask)) % 16 != 0)
+    return GHSCN_E_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  const int64_t nvec = num_feat / 4;
+  if (nvec <= 32) return launch_spmm_wide_masked<1>(rowptr, col, w, x, ldx, mask, ldm, y, ldy, num_rows, num_feat, st);
+  if (nvec <= 64) return launch_spmm_wide_masked<2>(rowptr, col, w, x, ldx, mask, ldm, y, ldy, num_rows, num_feat, st);
+  if (nvec <= 96) return launch_spmm_wide_masked<3>(rowptr, col, w, x, ldx, mask, ldm, y, ldy, num_rows, num_feat, st);
+  return launch_spmm_wide_masked<4>(rowptr, col, w, x, ldx, mask, ldm, y, ldy, num_rows, num_feat, st);
 }
 
 int ghscn_spmm_pool(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, int64_t ldx, float* y,

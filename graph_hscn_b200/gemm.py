@@ -101,6 +101,50 @@ def gemm3x(a: Tensor, image: Tensor, n_out: int, bias: Optional[Tensor] = None, 
     return c
 
 
+# ---- weight images computed ahead of their first use -----------------------------------------------------------
+# The image of a weight (TF32 hi/lo split, K-chunked, swizzled) depends on the parameters only, not on the batch: a
+# training step can build all of them on a side stream at its very beginning instead of ~4 us in front of every GEMM
+# on the critical chain.  `_Linear3xTF32` notes which weights take the tcgen05 path; `prefetch_images` serves them.
+_IMAGES: dict = {}            # (data_ptr, shape, transpose) -> (image, event)
+_FUSED_WEIGHTS: dict = {}     # data_ptr -> weight tensor seen on the tcgen05 path (forward and/or transposed use)
+
+
+def clear_images() -> None:
+    _IMAGES.clear()
+
+
+def prefetch_images(stream: "torch.cuda.Stream") -> int:
+    """Builds forward and transposed images of every weight known to take the tcgen05 path, on `stream`."""
+    if not _FUSED_WEIGHTS:
+        return 0
+    n = 0
+    with torch.cuda.stream(stream):
+        for w, uses in list(_FUSED_WEIGHTS.values()):
+            for transpose in sorted(uses):
+                img = gemm3x_prep(w, transpose=transpose)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                _IMAGES[(w.data_ptr(), tuple(w.shape), transpose)] = (img, ev)
+                n += 1
+    return n
+
+
+def _image(weight: Tensor, transpose: bool) -> Tensor:
+    key = (weight.data_ptr(), tuple(weight.shape), transpose)
+    ent = _FUSED_WEIGHTS.get(weight.data_ptr())
+    if ent is None:
+        _FUSED_WEIGHTS[weight.data_ptr()] = (weight.detach(), {transpose})
+    else:
+        ent[1].add(transpose)
+    hit = _IMAGES.get(key)
+    if hit is not None:
+        cur = torch.cuda.current_stream()
+        cur.wait_event(hit[1])
+        hit[0].record_stream(cur)
+        return hit[0]
+    return gemm3x_prep(weight, transpose=transpose)
+
+
 TILE_ROWS, NUM_SMS, MAX_TAIL_TILES = 128, 148, 24
 
 
@@ -191,7 +235,7 @@ class _Linear3xTF32(torch.autograd.Function):
         m = weight.size(0)
         fused = USE_TCGEN05 and gemm3x_supported(n, m, k)
         if fused:
-            y = linear_rows(x, weight, gemm3x_prep(weight), m, bias, transposed=False)
+            y = linear_rows(x, weight, _image(weight, False), m, bias, transposed=False)
             ctx.save_for_backward(x, weight)
         else:
             a_cat = split_cat(x, 0, DW_CHUNK)                    # [Npad, 3K] = [xl | xh | xh]
@@ -215,7 +259,7 @@ class _Linear3xTF32(torch.autograd.Function):
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dx_fused = need_dx and USE_TCGEN05 and gemm3x_supported(n, k, m)
         if dx_fused:
-            dx = linear_rows(dy, weight, gemm3x_prep(weight, transpose=True), k, None, transposed=True)   # dX = dY . W
+            dx = linear_rows(dy, weight, _image(weight, True), k, None, transposed=True)   # dX = dY . W
         dw_fused = need_dw and ctx.fused and USE_TCGEN05 and gemm3x_tn_supported(n, m, k)
         if dw_fused:
             dw = gemm3x_tn(dy, saved)                            # dW = dY^T x, slab partials added in fp32

@@ -65,6 +65,25 @@ def _(x):
     return x.new_empty((x.size(1),))
 
 
+@_custom_op("ghscn::colsum_masked", mutates_args=(), device_types="cuda")
+def colsum_masked(x: Tensor, mask: Tensor) -> Tensor:
+    """Column sums of x (.) [mask > 0] (bias gradient behind a fused ReLU) without materialising the product."""
+    x, mask = _rowmajor(x), _rowmajor(mask)
+    N, F = x.shape
+    out = torch.empty(F, dtype=torch.float32, device=x.device)
+    L = lib()
+    ws_bytes = L.query("ghscn_colsum_workspace_bytes", N, F)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    L.call("ghscn_colsum_masked", _p(x), x.stride(0), _p(mask), mask.stride(0), N, F, _p(out), _p(ws), ws_bytes,
+           _stream())
+    return out
+
+
+@colsum_masked.register_fake
+def _(x, mask):
+    return x.new_empty((x.size(1),))
+
+
 # =============================================================================================
 # K2/K3  SpMM
 # =============================================================================================
@@ -82,6 +101,26 @@ def spmm_raw(rowptr: Tensor, col: Tensor, w: Optional[Tensor], x: Tensor, bias: 
 @spmm_raw.register_fake
 def _(rowptr, col, w, x, bias, num_rows, relu):
     return x.new_empty((num_rows, x.size(1)))
+
+
+@_custom_op("ghscn::spmm_masked", mutates_args=(), device_types="cuda")
+def spmm_masked(rowptr: Tensor, col: Tensor, w: Optional[Tensor], x: Tensor, mask: Tensor, num_rows: int) -> Tensor:
+    """A_w (x (.) [mask > 0]): the rows of x are masked as they are gathered (ReLU backward fused into the transposed
+    aggregation)."""
+    x, mask = _rowmajor(x), _rowmajor(mask)
+    F = x.size(1)
+    y = torch.empty((num_rows, F), dtype=torch.float32, device=x.device)
+    lib().call("ghscn_spmm_masked", _p(rowptr), _p(col), _p(w), _p(x), x.stride(0), _p(mask), mask.stride(0), _p(y), F,
+               num_rows, F, _stream())
+    return y
+
+
+@spmm_masked.register_fake
+def _(rowptr, col, w, x, mask, num_rows):
+    return x.new_empty((num_rows, x.size(1)))
+
+
+FUSED_RELU_BACKWARD = os.environ.get("GHSCN_FUSED_RELU_BACKWARD", "1") != "0"
 
 
 @_custom_op("ghscn::spmm_edge_grad", mutates_args=(), device_types="cuda")
@@ -122,9 +161,13 @@ def _spmm_setup(ctx, inputs, output):
 
 def _spmm_backward(ctx, dy):
     rowptr, col, rowptr_t, col_t, w_t, x, y = ctx.saved_tensors
-    if ctx.relu:
-        dy = torch.ops.aten.threshold_backward(dy, y, 0.0)      # dy * (y > 0), one vectorised pass
     dy = dy.contiguous()
+    # ReLU backward: folded into the loads of the two consumers of dy (transposed aggregation, bias column sum) where
+    # the kernels support it, instead of a separate pass that reads dy and y and writes dy (.) [y > 0]
+    masked = (ctx.relu and FUSED_RELU_BACKWARD and not ctx.w_needs_grad and dy.is_cuda and dy.dim() == 2
+              and bool(lib().query("ghscn_spmm_masked_supported", dy.size(1), dy.stride(0), y.stride(0), dy.size(1))))
+    if ctx.relu and not masked:
+        dy = torch.ops.aten.threshold_backward(dy, y, 0.0)      # dy * (y > 0), one vectorised pass
     dx = dw = dbias = None
     want_bias = ctx.has_bias and ctx.needs_input_grad[7]
     # The bias gradient (a column sum of dy) and the transposed aggregation both only read dy: the column sum runs on
@@ -135,16 +178,19 @@ def _spmm_backward(ctx, dy):
         side = _aux_stream(dy.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            dbias = colsum(dy)
+            dbias = colsum_masked(dy, y) if masked else colsum(dy)
         dbias.record_stream(main)           # allocated on the auxiliary stream, consumed on the caller's
     if ctx.needs_input_grad[6]:
-        dx = spmm_raw(rowptr_t, col_t, w_t, dy, None, rowptr_t.numel() - 1, False)
+        if masked:
+            dx = spmm_masked(rowptr_t, col_t, w_t, dy, y, rowptr_t.numel() - 1)
+        else:
+            dx = spmm_raw(rowptr_t, col_t, w_t, dy, None, rowptr_t.numel() - 1, False)
     if ctx.w_needs_grad:
         dw = spmm_edge_grad(rowptr, col, x, dy, col.numel())
     if side is not None:
         main.wait_stream(side)
     elif want_bias:
-        dbias = colsum(dy)
+        dbias = colsum_masked(dy, y) if masked else colsum(dy)
     return None, None, dw, None, None, None, dx, dbias, None
 
 

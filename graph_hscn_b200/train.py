@@ -109,6 +109,17 @@ class FlatGradients:
         grads = torch.autograd.grad(loss, self.params)
         if accumulate:
             torch._foreach_add_([p.grad for p in self.params], list(grads))
+        elif self.flat.is_cuda and all(g.dtype == torch.float32 for g in grads):
+            # the parameters' gradient views tile the flat buffer in order: one gather launch (pointers travel as
+            # kernel arguments) instead of a multi-tensor copy that runs ~10 thread blocks for 1.1 MB
+            import ctypes
+            from ._lib import lib
+            from .structure import _p, _stream
+            gs = [g if g.is_contiguous() else g.contiguous() for g in grads]
+            n = len(gs)
+            ptrs = (ctypes.c_void_p * n)(*[g.data_ptr() for g in gs])
+            sizes = (ctypes.c_int64 * n)(*[g.numel() for g in gs])
+            lib().call("ghscn_gather_flat", ptrs, sizes, n, _p(self.flat), _stream())
         else:
             torch._foreach_copy_([p.grad for p in self.params], list(grads))
 
@@ -218,14 +229,24 @@ class BucketPolicy:
     def eff_edge_step(self) -> int:
         return max(1, min(self.edge_step, self.max_edges_per_graph))
 
+    max_pad_degree: int = 4         # pad edges per pad node: keeps the dummy graphs' rows as short as real ones
+
     @property
     def dummy_graphs(self) -> int:
-        return max(1, math.ceil((self.node_step + self.min_pad_nodes - 1) / max(self.max_nodes_per_graph, 2)))
+        worst = 2 * self.node_step + self.min_pad_nodes          # one extra node step when the pad edges need it
+        return max(1, math.ceil(worst / max(self.max_nodes_per_graph, 2)))
 
     def bucket(self, num_nodes: int, num_edges: int) -> Tuple[int, int]:
+        """-> (n_cap, e_cap).  The pad edges all land on the pad nodes (a dummy graph cannot borrow nodes from a real
+        one), so a bucket with many pad edges and few pad nodes would create rows hundreds of slots long -- one warp of
+        the row-parallel kernels would walk them alone (measured: +25 % on the aggregation kernel).  The node capacity
+        therefore grows by one more step whenever the pad edges would exceed `max_pad_degree` per pad node."""
         n_cap = math.ceil((num_nodes + self.min_pad_nodes) / self.node_step) * self.node_step
         es = self.eff_edge_step
-        return n_cap, math.ceil(num_edges / es) * es
+        e_cap = math.ceil(num_edges / es) * es
+        if e_cap - num_edges > self.max_pad_degree * (n_cap - num_nodes):
+            n_cap += self.node_step
+        return n_cap, e_cap
 
     @staticmethod
     def for_batches(batches: Sequence[Batch], node_step: int = 256, edge_step: int = 512) -> "BucketPolicy":
@@ -436,6 +457,7 @@ class GraphHSCNStep:
         self._warmed: set = set()                               # step variants that have run eagerly at least once
         self._loss_ring: Optional[List[Tensor]] = None
         self._loss_slot = 0
+        self._prep_stream = None
         torch.manual_seed(seed)
         self.scn = models.SCN(list(cfg.scn_units), cfg.scn_act, cfg.num_features, cfg.num_clusters, ops=self.ns).to(device)
         self.hscn = models.HSCN("GAT", "GCN", "GCN", models.ACTIVATIONS[cfg.activation], cfg.num_features, cfg.hidden,
@@ -659,6 +681,8 @@ class GraphHSCNStep:
         self.losses[2:3].copy_(loss.detach().view(1))
         if update:
             self._hscn_update(world)
+        if self._prep_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._prep_stream)
 
     def _step_two_streams(self, world: int, accumulate: bool, update: bool) -> None:
         """Same operations as `_step_serial`, scheduled on two CUDA streams.  The "local" half of the HSCN (l->l convs,
@@ -704,9 +728,23 @@ class GraphHSCNStep:
         for st in pnn.take_forked_streams(self.device):          # every stream the HeteroConv layers forked
             if st is not side:
                 main.wait_stream(st)
+        if self._prep_stream is not None:
+            main.wait_stream(self._prep_stream)
+
+    def _prefetch_weight_images(self) -> None:
+        """tcgen05 weight images of this step, built on a side stream right away (they depend on the parameters only)."""
+        from . import gemm
+        gemm.clear_images()
+        if self.device.type != "cuda" or os.environ.get("GHSCN_PREFETCH_IMAGES", "1") == "0":
+            return
+        if self._prep_stream is None:
+            self._prep_stream = torch.cuda.Stream(device=self.device)
+        self._prep_stream.wait_stream(torch.cuda.current_stream())
+        gemm.prefetch_images(self._prep_stream)
 
     def _step(self, world: int, variant: Optional[tuple] = None) -> None:
         accumulate, update = variant if variant is not None else self._variant()
+        self._prefetch_weight_images()
         if TWO_STREAMS and self.device.type == "cuda":
             self._step_two_streams(world, accumulate, update)
         else:

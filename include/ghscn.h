@@ -128,6 +128,13 @@ GHSCN_API int ghscn_spmm(const int32_t* rowptr, const int32_t* col, const float*
                          int32_t relu, ghscn_stream_t stream);
 /* Same contraction for pooling relations (few destination rows, many sources each, e.g. local -> virtual):
  * one CTA per row, fixed-order (deterministic) combination of 8 partial sums instead of the sequential order. */
+/* y = A_w (x (.) [mask > 0]): ghscn_spmm over rows of x that are masked as they are gathered -- the input gradient of
+ * `relu(GCNConv(...))` (model/mpnn.py:52, model/hscn.py:110) computed from dy and the layer's output in one pass
+ * (x = dy, mask = y, (rowptr, col, w) = the transposed structure).  128 <= num_feat <= 512, multiples of 4. */
+GHSCN_API int ghscn_spmm_masked_supported(int64_t num_feat, int64_t ldx, int64_t ldm, int64_t ldy);
+GHSCN_API int ghscn_spmm_masked(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, int64_t ldx,
+                                const float* mask, int64_t ldm, float* y, int64_t ldy, int64_t num_rows,
+                                int64_t num_feat, ghscn_stream_t stream);
 GHSCN_API int ghscn_spmm_pool(const int32_t* rowptr, const int32_t* col, const float* w, const float* x, int64_t ldx,
                               float* y, int64_t ldy, const float* bias, int64_t num_rows, int64_t num_feat,
                               ghscn_stream_t stream);
@@ -154,6 +161,11 @@ GHSCN_API int ghscn_segment_broadcast(const float* dy, int64_t lddy, const int32
 GHSCN_API size_t ghscn_colsum_workspace_bytes(int64_t num_rows, int64_t num_feat);
 GHSCN_API int ghscn_colsum(const float* x, int64_t ldx, int64_t num_rows, int64_t num_feat, float* out,
                            void* workspace, size_t workspace_bytes, ghscn_stream_t stream);
+/* Column sums of x (.) [mask > 0]: the bias gradient behind a ReLU that was fused into the forward aggregation
+ * (mask = that layer's output), without materialising the masked gradient.  mask NULL = ghscn_colsum. */
+GHSCN_API int ghscn_colsum_masked(const float* x, int64_t ldx, const float* mask, int64_t ldm, int64_t num_rows,
+                                  int64_t num_feat, float* out, void* workspace, size_t workspace_bytes,
+                                  ghscn_stream_t stream);
 
 /* hi/lo split for the 3xTF32 GEMM scheme used by the layers' dense projections (x W^T of GCNConv / GATConv /
  * Linear): hi = x with the low 13 mantissa bits cleared (exact in TF32), lo = x - hi.  16-byte aligned buffers. */
@@ -233,6 +245,11 @@ GHSCN_API int ghscn_adamw_step(float* param, const float* grad, float* exp_avg, 
 GHSCN_API int ghscn_adamw_step_scaled(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                                       double lr, double beta1, double beta2, double eps, double weight_decay,
                                       float* state, const float* grad_scale, ghscn_stream_t stream);
+/* dst = concatenation of `count` fp32 device tensors (pointer and element-count arrays live on the HOST and are
+ * consumed before the call returns): the gradients `loss.backward()` produced (train/train.py:87), laid out as the flat
+ * buffer that the one-kernel optimizer step and the data-parallel all-reduce work on. */
+GHSCN_API int ghscn_gather_flat(const float* const* srcs_host, const int64_t* numels_host, int32_t count, float* dst,
+                                ghscn_stream_t stream);
 /* nn.utils.clip_grad_norm(model.parameters(), max_norm) of train/train.py:92-93 over the flat gradient buffer:
  * out[0] = total 2-norm (fixed-order two-stage reduction, deterministic), out[1] = min(1, max_norm / (out[0] + 1e-6)).
  * The gradients themselves are not modified; pass out + 1 as grad_scale to ghscn_adamw_step_scaled. */

@@ -365,7 +365,8 @@ def test_bucket_padding_builds_wellformed_dummy_graphs():
         st = stage_batch(b, pol)
         sh, v = st.shape, st.views
         N, E = b.x.size(0), b.edge_index.size(1)
-        assert sh.n_cap % 64 == 0 and sh.n_cap >= N + 2 and sh.n_cap - N <= 64 + 2
+        assert sh.n_cap % 64 == 0 and sh.n_cap >= N + 2 and sh.n_cap - N <= 2 * 64 + 2
+        assert sh.e_cap - E <= pol.max_pad_degree * (sh.n_cap - N)
         assert sh.e_cap % pol.eff_edge_step == 0 and 0 <= sh.e_cap - E < pol.eff_edge_step
         assert sh.graphs == 12 and sh.dummies == pol.dummy_graphs
         assert torch.equal(v["x"][:N], b.x) and torch.equal(v["edge_index"][:, :E], b.edge_index)
