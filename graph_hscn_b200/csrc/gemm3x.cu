@@ -26,6 +26,7 @@
 //                               32-wide blocks, SBO between 4-row groups; one MMA (K = 8) reads two groups.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(256) gemm3x_prep_b_kernel(const float* __restr
 
 __global__ void __launch_bounds__(kNnThreads, 1)
 gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, const unsigned char* __restrict__ b_image,
-              int n_out, const float* __restrict__ bias, int relu, float* __restrict__ c, NnPlan plan) {
+              int n_out, const float* __restrict__ bias, int relu, float* __restrict__ c, NnPlan plan, int split) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long a_full[kAStages], a_empty[kAStages];
   __shared__ __align__(8) unsigned long long b_full[kBStages], b_empty[kBStages];
@@ -330,7 +331,12 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
   unsigned char* smem_gen = smem_raw + (smem_base - smem_addr(smem_raw));
   const uint32_t a_ring = smem_base, b_ring = a_ring + kAStages * 2 * kABytes;
   const int m0 = blockIdx.x * kTileM;
-  const int kchunks = plan.kchunks, nh = plan.hv.count;
+  // split != 0: gridDim.y = number of N halves and this CTA computes only half blockIdx.y of its row tile (half the
+  // work per CTA, twice the CTAs): used when the row tiles do not fill one wave of the 148 SMs exactly -- a problem of
+  // 156 tiles runs as 312 half CTAs in 3 waves of ~11 us instead of one wave of ~23 us plus a tail GEMM, and a small
+  // one (<= 74 tiles) finishes in half the time.  `hoff` maps the CTA-local half index to the problem's.
+  const int hoff = split ? (int)blockIdx.y : 0;
+  const int kchunks = plan.kchunks, nh = split ? 1 : plan.hv.count;
   const int total_chunks = nh * kchunks;
   // Every CTA streams the SAME weight image; walking it in lock step makes ~148 SMs hit the same few L2 slices at
   // once.  CTA b therefore starts at K chunk b mod kchunks (a sum: any chunk order is valid, and it is fixed per tile).
@@ -354,7 +360,7 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
     // ===== weight-image producer =====
     if (lane == 0) {
       for (int g = 0; g < total_chunks; ++g) {
-        const int h = g >= kchunks ? 1 : 0, kc = (g - h * kchunks + rot) % kchunks;
+        const int hl = g >= kchunks ? 1 : 0, h = hl + hoff, kc = (g - hl * kchunks + rot) % kchunks;
         const int s = g % kBStages;
         const uint32_t ph = (uint32_t)(g / kBStages) & 1u;
         if (g < 50) GHSCN_TR1(300 + 2 * g);
@@ -370,15 +376,16 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
   } else if (warp == 1) {
     // ===== MMA issuer (all 32 lanes run the loop; elect.sync inside mma_tf32 / mma_commit) =====
     {
-      for (int h = 0; h < nh; ++h) {
+      for (int hl = 0; hl < nh; ++hl) {
+        const int h = hl + hoff;
         const uint32_t idesc = make_idesc_tf32(kTileM, plan.hv.pad[h], false);
         const uint32_t lo_off = (uint32_t)plan.hv.pad[h] * kChunkK * 4;
-        if (h > 0) {                                   // the epilogue has drained the accumulators of half h-1
-          bar_wait(smem_addr(&acc_empty), (uint32_t)(h - 1) & 1u);
+        if (hl > 0) {                                  // the epilogue has drained the accumulators of half hl-1
+          bar_wait(smem_addr(&acc_empty), (uint32_t)(hl - 1) & 1u);
           tc_fence_after();
         }
         for (int pos = 0; pos < kchunks; ++pos) {
-          const int g = h * kchunks + pos;
+          const int g = hl * kchunks + pos;
           const int kc = (pos + rot) % kchunks;
           const int sa = g % kAStages, sb = g % kBStages;
           GHSCN_TR(3 * g);
@@ -456,10 +463,11 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
     const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
     const bool use_main1 = kchunks > 1;
     float* crow = c + (int64_t)grow * n_out;
-    for (int h = 0; h < nh; ++h) {
-      if (quad == 0) GHSCN_TR(400 + 4 * h);
-      bar_wait(smem_addr(&acc_full), (uint32_t)h & 1u);
-      if (quad == 0) GHSCN_TR(401 + 4 * h);
+    for (int hl = 0; hl < nh; ++hl) {
+      const int h = hl + hoff;
+      if (quad == 0) GHSCN_TR(400 + 4 * hl);
+      bar_wait(smem_addr(&acc_full), (uint32_t)hl & 1u);
+      if (quad == 0) GHSCN_TR(401 + 4 * hl);
       tc_fence_after();
       const int hpad = plan.hv.pad[h], hvalid = plan.hv.valid[h], hcol = plan.hv.col[h];
       for (int c0 = 0; c0 < hpad; c0 += 32) {
@@ -485,7 +493,7 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
           tc_fence_before();
           __syncwarp();
           if (lane == 0) bar_arrive(smem_addr(&acc_empty));
-          if (quad == 0) GHSCN_TR(402 + 4 * h);
+          if (quad == 0) GHSCN_TR(402 + 4 * hl);
         }
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
@@ -835,9 +843,18 @@ int ghscn_gemm3x(const float* a, int64_t lda, int64_t m, int64_t k, const void* 
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const unsigned grid = (unsigned)ceil_div<int64_t>(m, kTileM);
+  const unsigned tiles = (unsigned)ceil_div<int64_t>(m, kTileM);
+  // one CTA per row tile walks both N halves (A is re-read from L2 for the second) when the tiles fill exactly one
+  // wave; otherwise one CTA per (tile, half): see the note in the kernel
+  static const int force_split = [] {
+    const char* e = getenv("GHSCN_GEMM3X_SPLIT");       // tuning: 0 = never, 1 = always, unset = by wave count
+    return e ? atoi(e) : -1;
+  }();
+  int split = (p.hv.count == 2) && (tiles > (unsigned)kNumSMs || 2 * tiles <= (unsigned)kNumSMs);
+  if (force_split >= 0) split = force_split && p.hv.count == 2;
+  dim3 grid(tiles, split ? 2u : 1u);
   gemm3x_kernel<<<grid, kNnThreads, kNnSmem, as_stream(stream)>>>(
-      a, lda, (int)m, (int)k, static_cast<const unsigned char*>(b_image), (int)n_out, bias, relu, c, p);
+      a, lda, (int)m, (int)k, static_cast<const unsigned char*>(b_image), (int)n_out, bias, relu, c, p, split);
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }

@@ -146,6 +146,9 @@ def _image(weight: Tensor, transpose: bool) -> Tensor:
 
 
 TILE_ROWS, NUM_SMS, MAX_TAIL_TILES = 128, 148, 24
+# round 1 sent the tiles beyond whole waves to a library fp32 GEMM; the kernel now runs one CTA per (tile, N half) when
+# the tiles do not fill one wave exactly (csrc/gemm3x.cu), which keeps every row on the tensor cores
+TAIL_ON_LIBRARY = os.environ.get("GHSCN_GEMM_TAIL", "tcgen05") == "library"
 
 
 def wave_rows(n: int) -> int:
@@ -163,7 +166,7 @@ def wave_rows(n: int) -> int:
 def linear_rows(a: Tensor, weight_nk: Tensor, image: Tensor, n_out: int, bias: Optional[Tensor], transposed: bool):
     """a . B^T with B[n, k] = weight (or weight^T when `transposed`): whole waves on tcgen05, tail rows on cuBLAS fp32."""
     m = a.size(0)
-    r = wave_rows(m)
+    r = wave_rows(m) if TAIL_ON_LIBRARY else m
     if r == m:
         return gemm3x(a, image, n_out, bias)
     y = torch.empty((m, n_out), dtype=torch.float32, device=a.device)

@@ -120,7 +120,9 @@ def _(rowptr, col, w, x, mask, num_rows):
     return x.new_empty((num_rows, x.size(1)))
 
 
-FUSED_RELU_BACKWARD = os.environ.get("GHSCN_FUSED_RELU_BACKWARD", "1") != "0"
+# measured slower than the separate threshold pass at degree ~2 (the mask rows double the gather traffic, which is what
+# bounds the aggregation kernel: +17 us per step), so it is off by default; kept for graphs where rows are read once
+FUSED_RELU_BACKWARD = os.environ.get("GHSCN_FUSED_RELU_BACKWARD", "0") != "0"
 
 
 @_custom_op("ghscn::spmm_edge_grad", mutates_args=(), device_types="cuda")

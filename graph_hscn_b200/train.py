@@ -735,7 +735,9 @@ class GraphHSCNStep:
         """tcgen05 weight images of this step, built on a side stream right away (they depend on the parameters only)."""
         from . import gemm
         gemm.clear_images()
-        if self.device.type != "cuda" or os.environ.get("GHSCN_PREFETCH_IMAGES", "1") == "0":
+        # off by default: measured +8 us per step (the image kernels then compete with the first kernels of the local
+        # chain for SMs; in front of their GEMM they sit in that chain's idle launch gaps)
+        if self.device.type != "cuda" or os.environ.get("GHSCN_PREFETCH_IMAGES", "0") == "0":
             return
         if self._prep_stream is None:
             self._prep_stream = torch.cuda.Stream(device=self.device)
