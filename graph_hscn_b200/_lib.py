@@ -60,6 +60,7 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_colsum_workspace_bytes": (SZ, [I64, I64]),
     "ghscn_colsum": (I32, [P, I64, I64, I64, P, P, SZ, P]),
     "ghscn_virtual_csr": (I32, [P, P, P, P, P, I64, I64, I32] + [P] * 12 + [P]),
+    "ghscn_collate_batch": (I32, [P, P, I64, P, I64, P, P, I64, P]),
     "ghscn_batch_to_ptr": (I32, [P, I64, I64, P, P]),
     "ghscn_gcn_deg_inv_sqrt": (I32, [P, P, P, P, I64, I64, P, P]),
     "ghscn_edge_weights": (I32, [P, P, P, P, P, P, I64, I64, I32, I32, P, P]),

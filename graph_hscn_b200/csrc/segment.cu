@@ -270,6 +270,44 @@ static inline bool aligned16(const void* a, const void* b) {
   return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) % 16) == 0;
 }
 
+// ---- device-side collate (loader/loader.py:48-60 -> PyG `Batch.from_data_list`) ----------------------------------------
+// The host packs the graphs of a mini-batch back to back WITHOUT touching their indices (edge_index stays local to
+// each graph); one CTA per graph then derives what collate adds: the graph's node offset (prefix sum of the node
+// counts), `batch` (graph id per node) and the offset edge_index.  Replaces B small tensor adds + concatenations on
+// the host per batch.
+__global__ void __launch_bounds__(256) collate_batch_kernel(const int* __restrict__ node_counts,
+                                                            const int* __restrict__ edge_counts, int num_graphs,
+                                                            const long long* __restrict__ ei_local, long long e_cap,
+                                                            long long* __restrict__ ei_global,
+                                                            long long* __restrict__ batch, long long n_cap) {
+  __shared__ int red[32];
+  __shared__ int s_noff, s_eoff;
+  const int g = blockIdx.x;
+  int pn = 0, pe = 0;
+  for (int j = threadIdx.x; j < g; j += blockDim.x) { pn += node_counts[j]; pe += edge_counts[j]; }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  pn = warp_sum_i(pn);
+  if (lane == 0) red[wid] = pn;
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += red[w]; s_noff = t; }
+  __syncthreads();
+  pe = warp_sum_i(pe);
+  if (lane == 0) red[wid] = pe;
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += red[w]; s_eoff = t; }
+  __syncthreads();
+  const long long noff = s_noff, eoff = s_eoff;
+  const int n = node_counts[g], e = edge_counts[g];
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (noff + i < n_cap) batch[noff + i] = g;
+  for (int i = threadIdx.x; i < e; i += blockDim.x) {
+    if (eoff + i < e_cap) {
+      ei_global[eoff + i] = ei_local[eoff + i] + noff;
+      ei_global[e_cap + eoff + i] = ei_local[e_cap + eoff + i] + noff;
+    }
+  }
+}
+
 }  // namespace ghscn
 
 using namespace ghscn;
@@ -342,6 +380,21 @@ int ghscn_split_tf32_cat(const float* x, int64_t ldx, int64_t num_rows, int64_t 
   else
     split_tf32_cat_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, ldx, num_rows, num_rows_padded, (int)num_cols,
                                                                    mode, out);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+int ghscn_collate_batch(const int32_t* node_counts, const int32_t* edge_counts, int64_t num_graphs,
+                        const int64_t* edge_index_local, int64_t edge_capacity, int64_t* edge_index,
+                        int64_t* batch, int64_t node_capacity, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(num_graphs >= 0 && num_graphs <= 65535 && edge_capacity >= 0 && node_capacity >= 0);
+  if (num_graphs == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(node_counts && edge_counts && (edge_capacity == 0 || (edge_index_local && edge_index)) &&
+                (node_capacity == 0 || batch));
+  collate_batch_kernel<<<(unsigned)num_graphs, 256, 0, as_stream(stream)>>>(
+      node_counts, edge_counts, (int)num_graphs, reinterpret_cast<const long long*>(edge_index_local),
+      (long long)edge_capacity, reinterpret_cast<long long*>(edge_index), reinterpret_cast<long long*>(batch),
+      (long long)node_capacity);
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }

@@ -277,23 +277,30 @@ class StagedBatch:
     """One mini-batch packed for upload: x | edge_index | batch | y in ONE pinned host buffer (256-byte aligned
     sub-ranges, padded to its bucket), so the per-step upload is a single host-to-device copy."""
 
-    def __init__(self, shape: _Shape, buf: Tensor, views: Dict[str, Tensor], num_nodes: int, num_edges: int):
+    def __init__(self, shape: _Shape, buf: Tensor, views: Dict[str, Tensor], num_nodes: int, num_edges: int,
+                 raw: bool = False, upload_bytes: Optional[int] = None):
         self.shape, self.buf, self.views = shape, buf, views
         self.num_nodes, self.num_edges = num_nodes, num_edges        # real (unpadded) sizes
+        self.raw = raw                # True: edge_index holds per-graph LOCAL indices, `batch` is not filled --
+        #                               the device derives both from `counts` (ghscn_collate_batch)
+        self.upload_bytes = int(buf.numel()) if upload_bytes is None else int(upload_bytes)
         self.device_copy: Optional[Tensor] = None                    # set by GraphHSCNStep.make_resident
 
     @property
     def nbytes(self) -> int:
-        return int(self.buf.numel())
+        """Bytes that travel host -> device for this batch."""
+        return self.upload_bytes
 
 
 def _layout(shape: _Shape, x_like: Tensor, y_like: Tensor) -> Tuple[Dict[str, tuple], int]:
-    """name -> (byte offset, dtype, shape) of the packed buffer; total bytes."""
+    """name -> (byte offset, dtype, shape) of the packed buffer; total bytes.  `batch` comes last: a batch that is
+    collated on the device does not upload it (everything in front of it is the upload)."""
     bt = shape.graphs + shape.dummies
     specs = {"x": (x_like.dtype, (shape.n_cap,) + tuple(x_like.shape[1:])),
              "edge_index": (torch.int64, (2, shape.e_cap)),
-             "batch": (torch.int64, (shape.n_cap,)),
-             "y": (y_like.dtype, (bt,) + tuple(y_like.shape[1:]))}
+             "y": (y_like.dtype, (bt,) + tuple(y_like.shape[1:])),
+             "counts": (torch.int32, (2, bt)),                    # nodes per graph, edges per graph
+             "batch": (torch.int64, (shape.n_cap,))}
     out, total = {}, 0
     for k, (dt, shp) in specs.items():
         nbytes = int(torch.empty((), dtype=dt).element_size()) * int(math.prod(shp))
@@ -310,13 +317,11 @@ def _views(buf: Tensor, layout: Dict[str, tuple]) -> Dict[str, Tensor]:
     return out
 
 
-def _fill_dummies(views: Dict[str, Tensor], shape: _Shape, n_real: int, e_real: int) -> None:
-    """Writes the D trailing dummy graphs: zero features / labels, pad nodes split over the dummy graphs (each within
-    the per-graph caps), pad edges as (a, a+1), (a+1, a) pairs walking along the first dummy graphs' nodes."""
-    B, D = shape.graphs, shape.dummies
+def _dummy_plan(shape: _Shape, n_real: int, e_real: int) -> Tuple[List[int], List[int]]:
+    """(nodes, edges) of each of the D trailing dummy graphs: pad nodes fill the dummy graphs in order (each within the
+    per-graph cap), pad edges go to the first dummy graphs that have at least two nodes."""
+    D = shape.dummies
     pn, pe = shape.n_cap - n_real, shape.e_cap - e_real
-    views["x"][n_real:].zero_()
-    views["y"][B:].zero_()
     sizes, left = [], pn
     for _ in range(D):
         take = min(left, shape.max_nodes)
@@ -324,24 +329,39 @@ def _fill_dummies(views: Dict[str, Tensor], shape: _Shape, n_real: int, e_real: 
         left -= take
     if left:
         raise ValueError(f"{pn} pad nodes do not fit {D} dummy graphs of <= {shape.max_nodes} nodes")
-    views["batch"][n_real:] = torch.repeat_interleave(torch.arange(B, B + D), torch.tensor(sizes))
-    ei = views["edge_index"]
-    pos, base = e_real, n_real
+    edges = []
     for sz in sizes:
-        if pe <= 0:
-            break
-        if sz < 2:
-            base += sz
-            continue
-        take = min(pe, shape.max_edges) if shape.max_edges else pe
-        k = torch.arange(take)
-        a = base + (k // 2) % (sz - 1)
-        fwd = (k % 2 == 0)
-        ei[0, pos:pos + take] = torch.where(fwd, a, a + 1)
-        ei[1, pos:pos + take] = torch.where(fwd, a + 1, a)
-        pos, pe, base = pos + take, pe - take, base + sz
+        take = 0
+        if pe > 0 and sz >= 2:
+            take = min(pe, shape.max_edges) if shape.max_edges else pe
+        edges.append(take)
+        pe -= take
     if pe > 0:
         raise ValueError(f"pad edges do not fit the dummy graphs (left {pe})")
+    return sizes, edges
+
+
+def _fill_dummies(views: Dict[str, Tensor], shape: _Shape, n_real: int, e_real: int, local: bool = False) -> None:
+    """Writes the D trailing dummy graphs: zero features / labels, pad edges as (a, a+1), (a+1, a) pairs walking along
+    each dummy graph's nodes (global node ids, or ids local to the dummy graph with `local`)."""
+    B, D = shape.graphs, shape.dummies
+    sizes, edges = _dummy_plan(shape, n_real, e_real)
+    views["x"][n_real:].zero_()
+    views["y"][B:].zero_()
+    if not local:
+        views["batch"][n_real:] = torch.repeat_interleave(torch.arange(B, B + D), torch.tensor(sizes))
+    views["counts"][0, B:] = torch.tensor(sizes, dtype=torch.int32)
+    views["counts"][1, B:] = torch.tensor(edges, dtype=torch.int32)
+    ei = views["edge_index"]
+    pos, base = e_real, n_real
+    for sz, take in zip(sizes, edges):
+        if take:
+            k = torch.arange(take)
+            a = (0 if local else base) + (k // 2) % (sz - 1)
+            fwd = (k % 2 == 0)
+            ei[0, pos:pos + take] = torch.where(fwd, a, a + 1)
+            ei[1, pos:pos + take] = torch.where(fwd, a + 1, a)
+        pos, base = pos + take, base + sz
 
 
 def shape_for(batch: Batch, policy: Optional[BucketPolicy], use_blocks: bool = True) -> _Shape:
@@ -382,9 +402,64 @@ def stage_batch(batch: Batch, policy: Optional[BucketPolicy], pin: bool = False,
     v["edge_index"][:, :E].copy_(batch.edge_index)
     v["batch"][:N].copy_(batch.batch)
     v["y"][:shape.graphs].copy_(batch.y)
+    v["counts"][0, :shape.graphs] = (batch.ptr[1:] - batch.ptr[:-1]).to(torch.int32)
+    v["counts"][1, :shape.graphs] = torch.bincount(batch.batch[batch.edge_index[0]], minlength=shape.graphs).to(torch.int32)
     if shape.dummies:
         _fill_dummies(v, shape, N, E)
     return StagedBatch(shape, buf, v, N, E)
+
+
+def stage_graphs(graphs: Sequence, policy: Optional[BucketPolicy], pin: bool = False) -> StagedBatch:
+    """Collate WITHOUT the host-side index arithmetic (loader/loader.py:48-60): the graphs' x, LOCAL edge_index and y
+    are written back to back straight into one (pinned) staging buffer together with the per-graph node / edge
+    counts; `batch` and the offset edge_index are derived on the device (ghscn_collate_batch) after the upload.
+    Usable as a DataLoader `collate_fn` through `StagingCollate`."""
+    B = len(graphs)
+    nodes = torch.tensor([int(g.num_nodes) for g in graphs], dtype=torch.int64)
+    edges = torch.tensor([int(g.edge_index.size(1)) for g in graphs], dtype=torch.int64)
+    N, E = int(nodes.sum()), int(edges.sum())
+    max_n, max_e = int(nodes.max()), int(edges.max())
+    ei_local = torch.cat([g.edge_index for g in graphs], dim=1) if E else torch.zeros((2, 0), dtype=torch.int64)
+    if E:
+        bound = torch.repeat_interleave(nodes, edges)
+        if int(ei_local.min()) < 0 or bool((ei_local >= bound).any()):
+            raise ValueError("a graph has an edge that leaves it (edge_index out of range)")
+    loop_free = not bool((ei_local[0] == ei_local[1]).any())
+    if policy is None:
+        shape = _Shape(N, E, B, 0, max_n, max_e, loop_free)
+    else:
+        if max_n > policy.max_nodes_per_graph or max_e > policy.max_edges_per_graph:
+            raise ValueError(f"a graph has {max_n} nodes / {max_e} edges, above the policy's caps "
+                             f"({policy.max_nodes_per_graph} / {policy.max_edges_per_graph})")
+        n_cap, e_cap = policy.bucket(N, E)
+        shape = _Shape(n_cap, e_cap, B, policy.dummy_graphs, policy.max_nodes_per_graph,
+                       policy.max_edges_per_graph if max_e else 0, loop_free)
+    x0, y0 = graphs[0].x, graphs[0].y
+    layout, nbytes = _layout(shape, x0, y0)
+    buf = torch.empty(nbytes, dtype=torch.uint8)
+    if pin:
+        buf = buf.pin_memory()
+    v = _views(buf, layout)
+    torch.cat([g.x for g in graphs], dim=0, out=v["x"][:N])
+    v["edge_index"][:, :E].copy_(ei_local)
+    torch.cat([g.y for g in graphs], dim=0, out=v["y"][:B])
+    v["counts"][0, :B] = nodes.to(torch.int32)
+    v["counts"][1, :B] = edges.to(torch.int32)
+    if shape.dummies:
+        _fill_dummies(v, shape, N, E, local=True)
+    return StagedBatch(shape, buf, v, N, E, raw=True, upload_bytes=layout["batch"][0])
+
+
+class StagingCollate:
+    """`collate_fn` for torch's DataLoader: a list of graphs -> a StagedBatch in pinned memory, ready for
+    `GraphHSCNStep.load` (device-side collate).  The reference's counterpart is PyG's Python collate behind
+    `DataLoader(dataset, batch_size=...)` at loader/loader.py:48-60."""
+
+    def __init__(self, policy: Optional[BucketPolicy], pin: bool = True):
+        self.policy, self.pin = policy, pin
+
+    def __call__(self, graphs) -> StagedBatch:
+        return stage_graphs(list(graphs), self.policy, pin=self.pin)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -424,6 +499,17 @@ class _Runner:
         self.hints = dict(num_graphs=shape.graphs + shape.dummies, batch_sorted=1, max_nodes_per_graph=shape.max_nodes,
                           no_self_loops=int(shape.no_self_loops))
         self.graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
+        self._raw: Optional[Dict[str, Tensor]] = None
+
+    @property
+    def raw_dev(self) -> Dict[str, Tensor]:
+        """Tensors of a batch that is collated on the device: x / y / counts and the LOCAL edge list live in the
+        uploaded buffer, `edge_index` (offset) and `batch` are written by ghscn_collate_batch into their own buffers."""
+        if self._raw is None:
+            d = self.dev
+            self._raw = dict(x=d["x"], y=d["y"], counts=d["counts"], edge_index_local=d["edge_index"],
+                             edge_index=torch.empty_like(d["edge_index"]), batch=torch.empty_like(d["batch"]))
+        return self._raw
 
 
 class GraphHSCNStep:
@@ -472,7 +558,7 @@ class GraphHSCNStep:
     # -- compatibility views of the current bucket -------------------------------------------------------------
     @property
     def dev(self) -> Dict[str, Tensor]:
-        return self.runner.dev
+        return self.runner.raw_dev if self.staged.raw else self.runner.dev
 
     @property
     def host(self) -> Dict[str, Tensor]:
@@ -505,6 +591,13 @@ class GraphHSCNStep:
             raise ValueError(f"this step was built for {self.B} graphs per batch, got {int(batch.num_graphs)}")
         return stage_batch(batch, self.policy, pin=self.device.type == "cuda", use_blocks=self._use_blocks)
 
+    def stage_graphs(self, graphs: Sequence) -> StagedBatch:
+        """Packs a list of graphs without host-side collate arithmetic; `batch` / offset edge_index are derived on the
+        device at the start of the step (see `stage_graphs`)."""
+        if len(graphs) != self.B:
+            raise ValueError(f"this step was built for {self.B} graphs per batch, got {len(graphs)}")
+        return stage_graphs(graphs, self.policy, pin=self.device.type == "cuda")
+
     def _runner_for(self, shape: _Shape) -> _Runner:
         r = self._runners.get(shape)
         if r is None:
@@ -528,20 +621,21 @@ class GraphHSCNStep:
         """Host -> device copy of the current staged batch into its bucket's static buffer (current stream)."""
         r = self.runner
         if r.dev_buf is not None:
-            r.dev_buf.copy_(self.staged.buf, non_blocking=True)
+            n = self.staged.nbytes                  # a device-collated batch does not upload `batch`
+            r.dev_buf[:n].copy_(self.staged.buf[:n], non_blocking=True)
             return
         for k, v in self.staged.views.items():
             r.dev[k].copy_(v)
 
     def make_resident(self, staged: StagedBatch) -> StagedBatch:
         """Keeps a device copy of the packed batch (benchmarks with inputs already in HBM)."""
-        staged.device_copy = staged.buf.to(self.device)
+        staged.device_copy = staged.buf[:staged.nbytes].to(self.device)
         return staged
 
     def select_resident(self, staged: StagedBatch) -> None:
         """Device -> device copy of a resident batch into its bucket's static buffer."""
         self.select(staged)
-        self.runner.dev_buf.copy_(staged.device_copy, non_blocking=True)
+        self.runner.dev_buf[:staged.nbytes].copy_(staged.device_copy, non_blocking=True)
 
     def prefetch(self, staged: StagedBatch) -> int:
         """Starts the H2D copy of a LATER step's batch on the copy stream (double-buffered device staging slots): it
@@ -554,7 +648,7 @@ class GraphHSCNStep:
             buf = self._slots[slot] = torch.empty(max(staged.nbytes, 1 << 22), dtype=torch.uint8, device=self.device)
         self._copy_stream.wait_stream(cur)          # the slot's previous consumer (a D2D on `cur`) must be done
         with torch.cuda.stream(self._copy_stream):
-            buf[:staged.nbytes].copy_(staged.buf, non_blocking=True)
+            buf[:staged.nbytes].copy_(staged.buf[:staged.nbytes], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         self._slot_events[slot] = ev
@@ -563,7 +657,7 @@ class GraphHSCNStep:
     def select_prefetched(self, staged: StagedBatch, slot: int) -> None:
         self.select(staged)
         torch.cuda.current_stream().wait_event(self._slot_events[slot])
-        self.runner.dev_buf.copy_(self._slots[slot][:staged.nbytes], non_blocking=True)
+        self.runner.dev_buf[:staged.nbytes].copy_(self._slots[slot][:staged.nbytes], non_blocking=True)
 
     def download(self) -> Tensor:
         self.losses_host.copy_(self.losses, non_blocking=True)
@@ -585,18 +679,18 @@ class GraphHSCNStep:
 
     # -- one-time preparation: materialise lazy parameters, find live parameters, build optimizers ------
     def _forward_scn(self, x_f: Tensor):
-        d = self.runner.dev
+        d = self.dev
         ei, ew = self.ns.gcn_norm(d["edge_index"], None, x_f.size(0), add_self_loops=True)
         return (ei, ew) + tuple(self._scn_losses(x_f, ei, ew))
 
     def _scn_losses(self, x_f, ei, ew, losses_tensor: bool = False):
         # with dummy graphs the MinCUT losses are taken over the B real graphs only
         real = self.B if self.runner.shape.dummies else None
-        return self.scn.forward_batched(x_f, ei, ew, self.runner.dev["batch"], losses_tensor=losses_tensor,
+        return self.scn.forward_batched(x_f, ei, ew, self.dev["batch"], losses_tensor=losses_tensor,
                                         num_graphs=real)
 
     def _assign(self, x_f: Tensor, ei: Tensor, ew: Tensor):
-        d, shape = self.runner.dev, self.runner.shape
+        d, shape = self.dev, self.runner.shape
         with torch.no_grad():
             s = self.scn.logits(x_f, ei, ew)
             clusters = hetero.assign_clusters(torch.softmax(s, dim=-1))
@@ -617,6 +711,7 @@ class GraphHSCNStep:
     def _prepare(self) -> None:
         cfg = self.cfg
         with structure_hints(**self.hints):
+            self._collate_on_device()
             self._register_blocks()
             x_f = self._cast(self.dev["x"])
             ei, ew, _, mc, ol = self._forward_scn(x_f)
@@ -639,7 +734,7 @@ class GraphHSCNStep:
     def _register_blocks(self) -> None:
         shape = self.runner.shape
         if shape.max_edges and self.device.type == "cuda":
-            d = self.runner.dev
+            d = self.dev
             seg = structure_cache().segments(d["batch"], shape.graphs + shape.dummies)
             structure_cache().register_blocks(d["edge_index"], seg.ptr, shape.graphs + shape.dummies, shape.max_nodes,
                                               shape.max_edges)
@@ -653,7 +748,7 @@ class GraphHSCNStep:
     def _variant(self) -> tuple:
         """(accumulate onto the HSCN gradient buffer, take the HSCN optimizer step) for the batch about to run."""
         acc = max(int(self.cfg.batch_accumulation), 1)
-        return (self._micro > 0, self._micro + 1 >= acc)
+        return (self._micro > 0, self._micro + 1 >= acc, bool(self.staged.raw))
 
     def _hscn_update(self, world: int) -> None:
         self.hscn_grads.all_reduce_mean(world)
@@ -698,7 +793,7 @@ class GraphHSCNStep:
         main = torch.cuda.current_stream()
         side = pnn.branch_stream(self.device)
         pnn.take_forked_streams(self.device)                     # forget forks of earlier (already joined) work
-        d, shape = self.runner.dev, self.runner.shape
+        d, shape = self.dev, self.runner.shape
         N = d["x"].size(0)
         x_f = self._cast(d["x"])
         structure_cache().segments(d["batch"], shape.graphs + shape.dummies)
@@ -745,12 +840,24 @@ class GraphHSCNStep:
         gemm.prefetch_images(self._prep_stream)
 
     def _step(self, world: int, variant: Optional[tuple] = None) -> None:
-        accumulate, update = variant if variant is not None else self._variant()
+        accumulate, update = (variant if variant is not None else self._variant())[:2]
         self._prefetch_weight_images()
+        self._collate_on_device()
         if TWO_STREAMS and self.device.type == "cuda":
             self._step_two_streams(world, accumulate, update)
         else:
             self._step_serial(world, accumulate, update)
+
+    def _collate_on_device(self) -> None:
+        """`batch` and the offset edge_index of a raw-staged batch (loader/loader.py:48-60 on the device)."""
+        if not self.staged.raw:
+            return
+        from ._lib import lib
+        from .structure import _p, _stream
+        d, shape = self.runner.raw_dev, self.runner.shape
+        g = shape.graphs + shape.dummies
+        lib().call("ghscn_collate_batch", _p(d["counts"][0]), _p(d["counts"][1]), g, _p(d["edge_index_local"]),
+                   shape.e_cap, _p(d["edge_index"]), _p(d["batch"]), shape.n_cap, _stream())
 
     def _advance(self) -> None:
         self._micro = 0 if self._variant()[1] else self._micro + 1
@@ -758,9 +865,10 @@ class GraphHSCNStep:
     def predict(self) -> Tensor:
         """HSCN logits [B, C] of the current batch with the current weights (no gradient, no update): the forward of
         train/train.py:115-123 `eval_epoch`.  Eager; the cluster assignment comes from the current SCN weights."""
-        d = self.runner.dev
         with torch.no_grad(), structure_hints(**self.hints):
             structure_cache().clear()
+            self._collate_on_device()
+            d = self.dev
             self._register_blocks()
             x_f = self._cast(d["x"])
             ei, ew = self.ns.gcn_norm(d["edge_index"], None, x_f.size(0), add_self_loops=True)

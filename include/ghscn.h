@@ -89,6 +89,14 @@ GHSCN_API int ghscn_csr_build_blocked(const int64_t* src, const int64_t* dst, in
                                       int32_t* perm_dst, int32_t* rowptr_src, int32_t* col_src, int32_t* perm_src,
                                       int32_t* status, ghscn_stream_t stream);
 
+/* Device-side collate (loader/loader.py:48-60, `Batch.from_data_list`): the host packs the graphs of a mini-batch back
+ * to back with their LOCAL edge indices ([2, edge_capacity], row r at edge_index_local + r * edge_capacity) and one
+ * node / edge count per graph; this call writes `batch` (graph id of every node) and the offset edge_index.  The counts
+ * must sum to node_capacity / edge_capacity (padding graphs included). */
+GHSCN_API int ghscn_collate_batch(const int32_t* node_counts, const int32_t* edge_counts, int64_t num_graphs,
+                                  const int64_t* edge_index_local, int64_t edge_capacity, int64_t* edge_index,
+                                  int64_t* batch, int64_t node_capacity, ghscn_stream_t stream);
+
 /* sorted `batch` vector -> ptr[num_graphs+1] (PyG collate convention). */
 GHSCN_API int ghscn_batch_to_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs, int32_t* ptr,
                                  ghscn_stream_t stream);

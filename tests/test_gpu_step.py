@@ -244,3 +244,53 @@ def test_prefetch_pipeline_delivers_the_right_batch(cuda):
         torch.cuda.synchronize()
         assert torch.equal(step.runner.dev_buf.cpu(), st.buf)
         assert torch.equal(step.dev["x"][:st.num_nodes].cpu(), batches[i].x)
+
+
+def test_device_collate_equals_host_collate(cuda):
+    """loader/loader.py:48-60 on the device: graphs packed with LOCAL edge indices + per-graph counts, `batch` and the
+    offset edge_index derived by ghscn_collate_batch -- bit-identical to Batch.from_data_list, and the step computes
+    the same losses from either staging."""
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.data import Batch
+    from graph_hscn_b200.train import BucketPolicy, GraphHSCNStep, StagingCollate
+    graphs = synthetic.peptides_graphs(10, seed=71)
+    host = Batch.from_data_list(graphs)
+    pol = BucketPolicy.for_batches([host], node_step=128, edge_step=256)
+    a = GraphHSCNStep(_cfg(), host, cuda, padded=True, seed=3, policy=pol)
+    b = GraphHSCNStep(_cfg(), host, cuda, padded=True, seed=3, policy=pol)
+    _sync_weights(b, a)
+    raw = StagingCollate(pol, pin=True)(graphs)
+    assert raw.raw and raw.nbytes < a.staged.nbytes                  # `batch` is not uploaded
+    b.load(raw)
+    b.predict()                                                      # runs the device collate
+    torch.cuda.synchronize()
+    N, E = host.x.size(0), host.edge_index.size(1)
+    assert torch.equal(b.dev["batch"].cpu(), a.staged.views["batch"])
+    assert torch.equal(b.dev["edge_index"].cpu(), a.staged.views["edge_index"])
+    assert torch.equal(b.dev["edge_index"][:, :E].cpu(), host.edge_index) and torch.equal(b.dev["batch"][:N].cpu(), host.batch)
+    for st in (a, b):
+        st.capture(warmup=0)
+    for _ in range(2):
+        a.run()
+        b.run()
+    la, lb = _read_losses(a), _read_losses(b)
+    assert torch.equal(la, lb), "device-collated and host-collated batches must give bit-identical steps"
+
+
+def test_staging_collate_in_a_dataloader(cuda):
+    """`DataLoader(dataset, batch_size, collate_fn=StagingCollate(policy))` feeds the bucketed step directly."""
+    from torch.utils.data import DataLoader as TorchLoader
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.data import Batch
+    from graph_hscn_b200.train import BucketPolicy, GraphHSCNStep, StagingCollate
+    graphs = synthetic.peptides_graphs(24, seed=72)
+    pol = BucketPolicy(444, 1024, node_step=128, edge_step=256)
+    step = GraphHSCNStep(_cfg(), Batch.from_data_list(graphs[:8]), cuda, policy=pol, auto_capture=True)
+    seen = 0
+    for staged in TorchLoader(graphs, batch_size=8, collate_fn=StagingCollate(pol, pin=True)):
+        step.load(staged)
+        step.run()
+        losses = _read_losses(step)
+        assert torch.isfinite(losses).all()
+        seen += 1
+    assert seen == 3 and step.num_graphs_captured >= 1
