@@ -57,6 +57,8 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_small_linear_dw_workspace_bytes": (SZ, [I64, I64, I64]),
     "ghscn_small_linear_dw": (I32, [P, I64, P, I64, I32, P, I64, I64, I64, I64, P, P, P, SZ, P]),
     "ghscn_graph_loss": (I32, [P, I64, P, I64, I64, I64, I64, I32, P, P, P, P]),
+    "ghscn_relu_dropout_fwd": (I32, [P, I64, F32, P, P, P]),
+    "ghscn_relu_dropout_bwd": (I32, [P, P, I64, F32, P, P]),
     "ghscn_colsum_workspace_bytes": (SZ, [I64, I64]),
     "ghscn_colsum": (I32, [P, I64, I64, I64, P, P, SZ, P]),
     "ghscn_virtual_csr": (I32, [P, P, P, P, P, I64, I64, I32] + [P] * 12 + [P]),
@@ -78,9 +80,9 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_gat_pool_fwd": (I32, [P, P, P, I64, P, P, P, F32, I64, I64, P, P, I64, P]),
     "ghscn_gat_pool_bwd_scores": (I32, [P, P, P, I64, P, P, P, P, I64, F32, I64, I64, P, P, P]),
     "ghscn_gat_pool_bwd_src": (I32, [P, P, P, P, P, P, I64, P, I64, I64, P, I64, P, P]),
-    "ghscn_gat_fold_attention": (I32, [P, I64, P, P, I64, P, I64, I64, I64, P, P, P]),
+    "ghscn_gat_fold_attention": (I32, [P, I64, P, P, I64, P, I64, I64, I64, I64, P, P, P]),
     "ghscn_gat_pool_fused_supported": (I32, [I64, I64, I64]),
-    "ghscn_gat_pool_fused_fwd": (I32, [P, P, P, I64, P, I64, P, P, F32, I64, I64, P, I64, P]),
+    "ghscn_gat_pool_fused_fwd": (I32, [P, P, P, I64, P, I64, P, P, F32, I64, I64, I64, P, I64, P]),
     "ghscn_slot_map": (I32, [P, P, I64, I64, P, P, P]),
     "ghscn_mincut_workspace_bytes": (SZ, [I64, I64, I64]),
     "ghscn_mincut_fwd": (I32, [P, I64, P, I64, P, P, P, P, F32, I64, I64, I64, I64, I32,

@@ -148,6 +148,10 @@ __global__ void __launch_bounds__(256) gat_pool_fused_kernel(const int* __restri
   extern __shared__ float part[];                        // [8 warps][2 + 32 * W]: (m, ssum, acc...) per warp
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int row0 = blockIdx.x * 8;
+  // attention head = blockIdx.y: its own folded vectors and its own [num_rows, num_feat] slab of `pooled`
+  u_src += (int64_t)blockIdx.y * num_feat;
+  if (u_dst != nullptr) u_dst += (int64_t)blockIdx.y * num_feat;
+  pooled += (int64_t)blockIdx.y * num_rows * ldp;
   auto load_row = [&](const float* p, float (&dst)[W]) {
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
@@ -278,10 +282,14 @@ __global__ void __launch_bounds__(256) gat_fold_attention_kernel(const float* __
   const int fx = threadIdx.x & 31, hg = threadIdx.x >> 5;
   const int f = blockIdx.x * 32 + fx;
   const bool dst_side = blockIdx.y == 1;
-  const float* w = dst_side ? w_dst : w_src;
-  const float* att = dst_side ? att_dst : att_src;
+  const int head = blockIdx.z;                       // head h uses rows h*H .. h*H+H-1 of W and of att
   const int64_t ld = dst_side ? ldwd : ldws;
+  const float* w = dst_side ? w_dst : w_src;
+  if (w != nullptr) w += (int64_t)head * H * ld;
+  const float* att = (dst_side ? att_dst : att_src) + (int64_t)head * H;
   const int F = dst_side ? Fd : Fs;
+  if (u_src != nullptr) u_src += (int64_t)head * Fs;
+  if (u_dst != nullptr) u_dst += (int64_t)head * Fd;
   float acc = 0.f;
   if (w != nullptr && f < F)
     for (int h = hg; h < H; h += 8) acc = fmaf(__ldg(att + h), __ldg(w + (int64_t)h * ld + f), acc);
@@ -354,12 +362,13 @@ int ghscn_gat_pool_fwd(const int32_t* rowptr, const int32_t* col, const float* h
 }
 
 int ghscn_gat_fold_attention(const float* w_src, int64_t ldws, const float* att_src, const float* w_dst, int64_t ldwd,
-                             const float* att_dst, int64_t out_feat, int64_t src_feat, int64_t dst_feat, float* u_src,
-                             float* u_dst, ghscn_stream_t stream) {
+                             const float* att_dst, int64_t out_feat, int64_t src_feat, int64_t dst_feat, int64_t heads,
+                             float* u_src, float* u_dst, ghscn_stream_t stream) {
   GHSCN_REQUIRE(out_feat > 0 && src_feat > 0 && dst_feat >= 0 && w_src && att_src && u_src && ldws >= src_feat);
+  GHSCN_REQUIRE(heads >= 1 && heads <= 64);
   GHSCN_REQUIRE(w_dst == nullptr || (att_dst && u_dst && ldwd >= dst_feat && dst_feat > 0));
   const int64_t fmax = src_feat > dst_feat ? src_feat : dst_feat;
-  dim3 grid((unsigned)ceil_div<int64_t>(fmax, 32), w_dst ? 2u : 1u);
+  dim3 grid((unsigned)ceil_div<int64_t>(fmax, 32), w_dst ? 2u : 1u, (unsigned)heads);
   gat_fold_attention_kernel<<<grid, 256, 0, as_stream(stream)>>>(w_src, ldws, att_src, w_dst, ldwd, att_dst,
                                                                  (int)out_feat, (int)src_feat, (int)dst_feat, u_src,
                                                                  u_dst);
@@ -375,14 +384,14 @@ int ghscn_gat_pool_fused_supported(int64_t num_feat, int64_t ldxs, int64_t ldp) 
 
 int ghscn_gat_pool_fused_fwd(const int32_t* rowptr, const int32_t* col, const float* x_src, int64_t ldxs,
                              const float* x_dst, int64_t ldxd, const float* u_src, const float* u_dst,
-                             float negative_slope, int64_t num_rows, int64_t num_feat, float* pooled, int64_t ldp,
-                             ghscn_stream_t stream_) {
-  GHSCN_REQUIRE(num_rows >= 0 && num_feat > 0 && num_rows < ((int64_t)1 << 31));
+                             float negative_slope, int64_t num_rows, int64_t num_feat, int64_t heads, float* pooled,
+                             int64_t ldp, ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_feat > 0 && num_rows < ((int64_t)1 << 31) && heads >= 1 && heads <= 64);
   if (num_rows == 0) return GHSCN_OK;
   GHSCN_REQUIRE(rowptr && x_src && u_src && pooled && ldxs >= num_feat && ldp >= num_feat);
   GHSCN_REQUIRE((x_dst == nullptr) == (u_dst == nullptr) && (x_dst == nullptr || ldxd >= num_feat));
   cudaStream_t stream = as_stream(stream_);
-  const unsigned blocks = (unsigned)ceil_div<int64_t>(num_rows, 8);
+  const dim3 blocks((unsigned)ceil_div<int64_t>(num_rows, 8), (unsigned)heads);
 #define GHSCN_POOL_LAUNCH(VEC, ITERS)                                                                          \
   gat_pool_fused_kernel<VEC, ITERS><<<blocks, 256, 8 * (2 + 32 * (VEC) * (ITERS)) * 4, stream>>>(              \
       rowptr, col, x_src, ldxs, x_dst, ldxd, u_src, u_dst, negative_slope, (int)num_rows, (int)num_feat, pooled, ldp)

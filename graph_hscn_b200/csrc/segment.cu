@@ -308,6 +308,50 @@ __global__ void __launch_bounds__(256) collate_batch_kernel(const int* __restric
   }
 }
 
+// ---- ReLU + dropout in one pass (model/mpnn.py:57-58: `F.dropout(self.activation(x), p, training)`) -------------------
+// Philox4x32-10 keyed by a (seed, call counter) pair that lives on the device, so a captured CUDA graph draws a fresh
+// mask on every replay; the element index is the Philox counter.  No mask tensor: a dropped element and a negative
+// pre-activation both leave y = 0, so the backward is  dx = (y > 0) ? dy / (1 - p) : 0  from the output alone.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__global__ void __launch_bounds__(256) relu_dropout_fwd_kernel(const float* __restrict__ x, long long n, float p,
+                                                               const unsigned long long* __restrict__ state,
+                                                               float* __restrict__ y) {
+  const unsigned long long seed = state[0], call = state[1];
+  const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+  const float scale = 1.0f / (1.0f - p);
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g * 4 < n;
+       g += (long long)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((unsigned)g, (unsigned)(g >> 32), (unsigned)call, (unsigned)(call >> 32)), key);
+    const unsigned rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = g * 4 + u;
+      if (i < n) {
+        const float uni = (float)(rr[u] >> 8) * (1.0f / 16777216.0f);      // [0, 1)
+        const float v = fmaxf(x[i], 0.f);
+        y[i] = uni >= p ? v * scale : 0.f;
+      }
+    }
+  }
+}
+__global__ void relu_dropout_bump_kernel(unsigned long long* state) { state[1] += 1ull; }
+__global__ void __launch_bounds__(256) relu_dropout_bwd_kernel(const float* __restrict__ dy,
+                                                               const float* __restrict__ y, long long n, float scale,
+                                                               float* __restrict__ dx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = y[i] > 0.f ? dy[i] * scale : 0.f;
+}
+
 }  // namespace ghscn
 
 using namespace ghscn;
@@ -395,6 +439,29 @@ int ghscn_collate_batch(const int32_t* node_counts, const int32_t* edge_counts, 
       node_counts, edge_counts, (int)num_graphs, reinterpret_cast<const long long*>(edge_index_local),
       (long long)edge_capacity, reinterpret_cast<long long*>(edge_index), reinterpret_cast<long long*>(batch),
       (long long)node_capacity);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+int ghscn_relu_dropout_fwd(const float* x, int64_t n, float p, uint64_t* state, float* y, ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(n >= 0 && p >= 0.f && p < 1.f && state && (n == 0 || (x && y)));
+  cudaStream_t stream = as_stream(stream_);
+  if (n > 0) {
+    const int64_t want = ceil_div<int64_t>(ceil_div<int64_t>(n, 4), 256), cap = (int64_t)kNumSMs * 16;
+    relu_dropout_fwd_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(
+        x, (long long)n, p, reinterpret_cast<const unsigned long long*>(state), y);
+  }
+  relu_dropout_bump_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<unsigned long long*>(state));
+  GHSCN_LAUNCH_CHECK_N(n > 0 ? 2 : 1);
+  return GHSCN_OK;
+}
+
+int ghscn_relu_dropout_bwd(const float* dy, const float* y, int64_t n, float p, float* dx, ghscn_stream_t stream) {
+  GHSCN_REQUIRE(n >= 0 && p >= 0.f && p < 1.f && (n == 0 || (dy && y && dx)));
+  if (n == 0) return GHSCN_OK;
+  const int64_t want = ceil_div<int64_t>(n, 256 * 4), cap = (int64_t)kNumSMs * 16;
+  relu_dropout_bwd_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(
+      dy, y, (long long)n, 1.0f / (1.0f - p), dx);
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }

@@ -63,7 +63,11 @@ class MPNN(nn.Module):
                 h = self.bns[i](h)
             if self.use_layer_norm:
                 h = self.lns[i](h)
-            h = F.dropout(self.activation(h), p=self.dropout, training=self.training)
+            if (self.dropout > 0 and self.training and self.activation in (F.relu, torch.relu)
+                    and hasattr(self.ops, "relu_dropout")):
+                h = self.ops.relu_dropout(h, self.dropout, True)        # activation + dropout in one pass
+            else:
+                h = F.dropout(self.activation(h), p=self.dropout, training=self.training)
         h = self.conv_layers[-1](h, edge_index)
         return self.ops.scatter_mean(h, graph_of_node, dim=0)
 

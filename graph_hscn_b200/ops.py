@@ -717,10 +717,10 @@ class VirtualLayerFused(torch.autograd.Function):
         w_src_c, w_dst_c, w_vv_c = w_src.contiguous(), w_dst.contiguous(), w_vv.contiguous()
         u = torch.empty((2, F), dtype=torch.float32, device=dev)
         L.call("ghscn_gat_fold_attention", _p(w_src_c), F, _p(att_src.contiguous()), _p(w_dst_c), F,
-               _p(att_dst.contiguous()), H, F, F, _p(u[0]), _p(u[1]), st)
+               _p(att_dst.contiguous()), H, F, F, 1, _p(u[0]), _p(u[1]), st)
         pooled = torch.empty((V, F), dtype=torch.float32, device=dev)
         L.call("ghscn_gat_pool_fused_fwd", _p(lvd.rowptr), _p(lvd.col), _p(x_src), x_src.stride(0), _p(x_dst),
-               x_dst.stride(0), _p(u[0]), _p(u[1]), float(meta["slope"]), V, F, _p(pooled), F, st)
+               x_dst.stride(0), _p(u[0]), _p(u[1]), float(meta["slope"]), V, F, 1, _p(pooled), F, st)
         agg = torch.empty((V, F), dtype=torch.float32, device=dev)
         L.call("ghscn_spmm", _p(vvd.rowptr), _p(vvd.col), _p(vv_w), _p(x_dst), x_dst.stride(0), _p(agg), F, None, V, F,
                0, st)
@@ -749,3 +749,104 @@ class VirtualLayerFused(torch.autograd.Function):
         it = iter(grads[2:])
         pg = [next(it) if p is not None else None for p in params]
         return (dxs, dxd, pg[0], pg[1], pg[2], pg[3], pg[4], pg[5], pg[6], None)
+
+
+# =============================================================================================
+# ReLU + dropout in one pass (model/mpnn.py:57-58), no mask tensor
+# =============================================================================================
+_DROPOUT_STATE: dict = {}
+
+
+def dropout_state(device: torch.device) -> Tensor:
+    """{seed, call counter} of the fused dropout on `device` (int64 [2] on the device; seeded from torch.initial_seed()
+    on first use -- `manual_seed` before that makes runs reproducible; captured graphs advance the counter themselves)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _DROPOUT_STATE.get(idx)
+    if st is None:
+        st = _DROPOUT_STATE[idx] = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64,
+                                                device=device)
+    return st
+
+
+class ReluDropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, p: float):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        lib().call("ghscn_relu_dropout_fwd", _p(x), x.numel(), float(p), _p(dropout_state(x.device)), _p(y), _stream())
+        ctx.save_for_backward(y)
+        ctx.p = float(p)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        lib().call("ghscn_relu_dropout_bwd", _p(dy), _p(y), dy.numel(), ctx.p, _p(dx), _stream())
+        return dx, None
+
+
+def relu_dropout(x: Tensor, p: float, training: bool = True) -> Tensor:
+    """F.dropout(F.relu(x), p, training) (model/mpnn.py:57-58 with the ReLU activation); one kernel, no mask tensor."""
+    if not training or p <= 0.0:
+        return torch.relu(x)
+    if not (x.is_cuda and x.dtype == torch.float32) or p >= 1.0:
+        return torch.nn.functional.dropout(torch.relu(x), p=p, training=True)
+    return ReluDropout.apply(x, float(p))
+
+
+# =============================================================================================
+# multi-head GATConv forward in one pool launch for all heads (SURVEY 8f rank 3)
+# =============================================================================================
+class GatMultiHead(torch.autograd.Function):
+    """GATConv(heads = h) forward: the attention vectors of all heads are folded in one launch, ALL heads are pooled at
+    the input width in one launch (grid.y = head), then one small projection per head writes its column block of the
+    concatenated output.  The backward re-runs the head-by-head differentiable operators (`meta["unfused"]`)."""
+
+    @staticmethod
+    def forward(ctx, x_src, x_dst, w_src, w_dst, att_src, att_dst, meta):
+        x_src = _rowmajor(x_src)
+        heads, C = meta["heads"], meta["out_channels"]
+        V, F = meta["num_dst"], x_src.size(1)
+        dev = x_src.device
+        L, st = lib(), _stream()
+        d = meta["by_dst"]
+        w_src_c = w_src.contiguous()
+        has_dst = x_dst is not None
+        if has_dst:
+            x_dst = _rowmajor(x_dst)
+            w_dst_c = w_dst.contiguous()
+        u = torch.empty((2, heads, F), dtype=torch.float32, device=dev)
+        L.call("ghscn_gat_fold_attention", _p(w_src_c), F, _p(att_src.contiguous()),
+               _p(w_dst_c) if has_dst else None, F, _p(att_dst.contiguous()) if has_dst else None, C, F,
+               F if has_dst else 0, heads, _p(u[0]), _p(u[1]) if has_dst else None, st)
+        pooled = torch.empty((heads, V, F), dtype=torch.float32, device=dev)
+        L.call("ghscn_gat_pool_fused_fwd", _p(d.rowptr), _p(d.col), _p(x_src), x_src.stride(0),
+               _p(x_dst) if has_dst else None, x_dst.stride(0) if has_dst else 0, _p(u[0]),
+               _p(u[1]) if has_dst else None, float(meta["slope"]), V, F, heads, _p(pooled), F, st)
+        out = torch.empty((V, heads * C), dtype=torch.float32, device=dev)
+        for h in range(heads):
+            L.call("ghscn_small_linear_fwd", _p(pooled[h]), F, w_src_c.data_ptr() + 4 * h * C * F, F, None, 0, V, F, C,
+                   out.data_ptr() + 4 * h * C, heads * C, st)
+        ctx.meta = meta
+        ctx.save_for_backward(x_src, x_dst)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x_src, x_dst = ctx.saved_tensors
+        meta = ctx.meta
+        with torch.enable_grad():
+            xs = x_src.detach().requires_grad_()
+            xd = xs if meta["shared_x"] else (x_dst.detach().requires_grad_() if x_dst is not None else None)
+            out = meta["unfused"](xs, xd)
+            params = list(meta["params"])               # the tensors this function received (w_dst None if shared)
+            wanted = [xs] + ([] if (xd is None or xd is xs) else [xd]) + [p for p in params if p is not None]
+            grads = list(torch.autograd.grad(out, wanted, dout.contiguous(), allow_unused=True))
+        it = iter(grads)
+        dxs = next(it)
+        dxd = None if (xd is None or xd is xs) else next(it)
+        pg = [next(it) if p is not None else None for p in params]
+        # att_* enter as [1, heads, C]; the function received them in that shape
+        return dxs, dxd, pg[0], pg[1], pg[2], pg[3], None

@@ -12,6 +12,7 @@ import sys
 import types
 
 from ..data import Batch, Data, DataLoader, HeteroBatch, HeteroData
+from .. import ops as _ops
 from . import _device, functional, nn
 from ._device import auto_device, set_auto_device
 from .functional import (SparseAdj, dense_mincut_pool, gcn_norm, global_add_pool, global_mean_pool,
@@ -31,7 +32,7 @@ def namespace() -> types.SimpleNamespace:
         HeteroConv=HeteroConv, Linear=Linear, Sequential=Sequential, MessagePassing=MessagePassing,
         dense_mincut_pool=dense_mincut_pool, mincut_pool_ragged=mincut_pool_ragged, to_dense_adj=to_dense_adj,
         global_mean_pool=global_mean_pool, scatter_mean=scatter_mean, gcn_norm=gcn_norm,
-        scn_logits_fused=scn_logits_fused, linear_act=functional.linear_act)
+        scn_logits_fused=scn_logits_fused, linear_act=functional.linear_act, relu_dropout=_ops.relu_dropout)
 
 
 def build_modules(ns: types.SimpleNamespace, data_mod=None) -> dict:

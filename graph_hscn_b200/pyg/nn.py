@@ -280,9 +280,34 @@ class GATConv(MessagePassing):
                 x_src, x_dst, w_src, w_dst if x_dst is not None else None,
                 att_src.view(-1), att_dst.view(-1), bias, float(self.negative_slope),
                 d.rowptr, d.col, s.rowptr, s.col, st.slot_map_t)
-        # heads > 1 (never built by the reference's configs): every head is the single-head operator
-        # on its own row block of lin_src / lin_dst and its own attention vectors, over the same structure
-        C, outs = self.out_channels, []
+        # heads > 1 (never built by the reference's configs)
+        C = self.out_channels
+
+        def head_by_head(xs_, xd_):
+            """every head is the single-head operator on its own row block of lin_src / lin_dst and its own attention
+            vectors, over the same structure (differentiable; the fused forward's backward runs this)"""
+            parts = []
+            for h in range(self.heads):
+                rows = slice(h * C, (h + 1) * C)
+                parts.append(ops.GatPoolInputWidth.apply(
+                    xs_, xd_, w_src[rows], w_dst[rows] if xd_ is not None else None,
+                    att_src[0, h], att_dst[0, h], None, float(self.negative_slope),
+                    d.rowptr, d.col, s.rowptr, s.col, st.slot_map_t))
+            return torch.cat(parts, dim=1)
+
+        f_in = x_src.size(1)
+        from .._lib import lib as _lib
+        if (FUSED_MULTIHEAD and x_src.is_cuda and (x_dst is None or x_dst.size(1) == f_in)
+                and _lib().query("ghscn_gat_pool_fused_supported", f_in, x_src.stride(0), f_in)):
+            shared = x_dst is x_src
+            meta = dict(heads=self.heads, out_channels=C, num_dst=n_dst, by_dst=d, slope=self.negative_slope,
+                        unfused=head_by_head, shared_x=shared,
+                        params=(w_src, None if (x_dst is None or w_dst is w_src) else w_dst, att_src, att_dst))
+            cat = ops.GatMultiHead.apply(x_src, x_dst, w_src, w_dst if x_dst is not None else None, att_src, att_dst,
+                                         meta)
+            out = cat if self.concat else cat.view(n_dst, self.heads, C).mean(dim=1)
+            return out + bias if bias is not None else out
+        outs = []
         for h in range(self.heads):
             rows = slice(h * C, (h + 1) * C)
             outs.append(ops.GatPoolInputWidth.apply(
@@ -294,6 +319,7 @@ class GATConv(MessagePassing):
 
 
 FUSED_VIRTUAL = os.environ.get("GHSCN_FUSED_VIRTUAL", "1") != "0"
+FUSED_MULTIHEAD = os.environ.get("GHSCN_FUSED_MULTIHEAD", "1") != "0"
 PARALLEL_BRANCHES = os.environ.get("GHSCN_PARALLEL_BRANCHES", "1") != "0"
 PARALLEL_RELATIONS = os.environ.get("GHSCN_PARALLEL_RELATIONS", "1") != "0"
 _SIDE_STREAMS: Dict[Tuple[str, int], List["torch.cuda.Stream"]] = {}

@@ -164,6 +164,16 @@ GHSCN_API int ghscn_segment_broadcast(const float* dy, int64_t lddy, const int32
                                       int64_t num_segments, int64_t num_feat, int32_t mean, float* dx, int64_t lddx,
                                       ghscn_stream_t stream);
 
+/* y = dropout(relu(x), p) in one pass, training mode (model/mpnn.py:57-58, `F.dropout(self.activation(x), ...)` with
+ * the ReLU activation of config/config.py:13-18).  `state` = two device uint64 {seed, call counter}: the mask is
+ * Philox4x32-10(counter = element index, call counter; key = seed), and the call increments the counter on the device,
+ * so replays of a captured CUDA graph draw fresh masks.  The backward needs only the output:
+ * dx = y > 0 ? dy / (1 - p) : 0 (a dropped element and a negative input both give y = 0). */
+GHSCN_API int ghscn_relu_dropout_fwd(const float* x, int64_t n, float p, uint64_t* state, float* y,
+                                     ghscn_stream_t stream);
+GHSCN_API int ghscn_relu_dropout_bwd(const float* dy, const float* y, int64_t n, float p, float* dx,
+                                     ghscn_stream_t stream);
+
 /* Column sum out[f] = sum_r x[r,f] (bias gradients db = sum_rows dY of GCNConv / GATConv); two-stage,
  * fixed order => deterministic.  workspace >= ghscn_colsum_workspace_bytes(). */
 GHSCN_API size_t ghscn_colsum_workspace_bytes(int64_t num_rows, int64_t num_feat);
@@ -270,15 +280,18 @@ GHSCN_API int ghscn_grad_clip_scale(const float* grad, int64_t n, float max_norm
  *   pooled[r,:] = sum_s softmax_s(leaky_relu(<x_src[col[s]], u_src> + <x_dst[r], u_dst>)) x_src[col[s],:]
  * so that out = pooled W_src^T + bias is one small GEMM.  One warp per destination row, one pass over its members
  * (online softmax), replaces ghscn_row_dot x2 + ghscn_gat_scores + ghscn_spmm_pool.  x_dst / u_dst may both be NULL.
- * Supported widths: <= 32 (any alignment) or a multiple of 4 up to 512 with 16-byte aligned rows. */
+ * Supported widths: <= 32 (any alignment) or a multiple of 4 up to 512 with 16-byte aligned rows.
+ * heads > 1 (GATConv(heads=h)): head i uses rows i*out_feat.. of W / att, u_src / u_dst are
+ * [heads, feat] and pooled is [heads, num_rows, ldp]; all heads run in the same two launches. */
 GHSCN_API int ghscn_gat_fold_attention(const float* w_src, int64_t ldws, const float* att_src, const float* w_dst,
                                        int64_t ldwd, const float* att_dst, int64_t out_feat, int64_t src_feat,
-                                       int64_t dst_feat, float* u_src, float* u_dst, ghscn_stream_t stream);
+                                       int64_t dst_feat, int64_t heads, float* u_src, float* u_dst,
+                                       ghscn_stream_t stream);
 GHSCN_API int ghscn_gat_pool_fused_supported(int64_t num_feat, int64_t ldxs, int64_t ldp);
 GHSCN_API int ghscn_gat_pool_fused_fwd(const int32_t* rowptr, const int32_t* col, const float* x_src, int64_t ldxs,
                                        const float* x_dst, int64_t ldxd, const float* u_src, const float* u_dst,
-                                       float negative_slope, int64_t num_rows, int64_t num_feat, float* pooled,
-                                       int64_t ldp, ghscn_stream_t stream);
+                                       float negative_slope, int64_t num_rows, int64_t num_feat, int64_t heads,
+                                       float* pooled, int64_t ldp, ghscn_stream_t stream);
 
 /* ---- small dense layers + task loss (readout head, virtual-node projections) --------------------------------------
  * Replaces the library GEMM + bias + activation kernels of `lin_1`, activation, `lin_2` on the [B, H] graph embeddings

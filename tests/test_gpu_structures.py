@@ -288,3 +288,57 @@ def test_graph_loss_matches_criterion(cuda, loss_fn, rows, total, c):
     assert_close(st_, sr, 1e-6, "score")
     assert_close(pt.grad, pr.grad, 1e-6, "d pred")
     assert not pt.grad[rows:].any()
+
+
+def test_relu_dropout_fused(cuda):
+    """model/mpnn.py:57-58 `F.dropout(self.activation(x), p)` as one kernel: keep rate, scaling, zeros where relu is
+    zero, a fresh mask per call (also across CUDA-graph replays), backward from the output alone."""
+    from graph_hscn_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4000, 300, generator=g).to(cuda).requires_grad_()
+    p = 0.2
+    y = ops.relu_dropout(x, p, True)
+    pos = x.detach() > 0
+    kept = y.detach() > 0
+    assert not kept[~pos].any()                                              # relu zeros stay zero
+    rate = float(kept[pos].float().mean())
+    assert abs(rate - (1 - p)) < 5e-3, rate                                  # ~480k positive elements
+    assert torch.allclose(y.detach()[kept], x.detach()[kept] / (1 - p), rtol=1e-6)
+    gy = torch.randn(y.shape, generator=g).to(cuda)
+    y.backward(gy)
+    want = torch.where(kept, gy / (1 - p), torch.zeros_like(gy))
+    assert torch.allclose(x.grad, want, rtol=1e-6)
+    y2 = ops.relu_dropout(x.detach(), p, True)
+    assert float(((y2 > 0) != kept).float().mean()) > 0.05                   # a different mask on the next call
+    assert torch.equal(ops.relu_dropout(x.detach(), p, False), torch.relu(x.detach()))
+    # replays of a captured graph draw new masks (the call counter lives on the device)
+    xs = x.detach()
+    out = torch.empty_like(xs)
+    ops.relu_dropout(xs, p, True)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out.copy_(ops.relu_dropout(xs, p, True))
+    graph.replay()
+    a = out.clone()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert float(((a > 0) != (out > 0)).float().mean()) > 0.05
+
+
+def test_mpnn_with_dropout_trains_on_the_fused_path(cuda):
+    """Config #1's throughput variant (dropout 0.2): forward + backward run, outputs are finite, eval mode is exact."""
+    import torch.nn.functional as F
+    from graph_hscn_b200 import models, pyg, synthetic
+    b = synthetic.peptides_batch(8, seed=9).to(cuda)
+    b.x = b.x.float()
+    torch.manual_seed(0)
+    m = models.MPNN("gcn", F.relu, 9, 64, 10, 4, dropout=0.2, ops=pyg.namespace()).to(cuda)
+    m.train()
+    out = m(b)
+    loss, _ = models.criterion("cross_entropy", out, b.y)
+    loss.backward()
+    assert torch.isfinite(out).all() and all(torch.isfinite(p.grad).all() for p in m.parameters())
+    m.eval()
+    o1, o2 = m(b), m(b)
+    assert torch.equal(o1, o2)
