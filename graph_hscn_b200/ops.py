@@ -698,6 +698,11 @@ def graph_loss(loss_fn: str, pred: Tensor, target: Tensor, rows: Optional[int] =
 # =============================================================================================
 # fused "virtual" destination of the HeteroConv: v->v GCN + l->v GAT pool, summed (model/hscn.py:83-96)
 # =============================================================================================
+# measured slower in the step (0.665 vs 0.653 ms): a tcgen05 CTA owns its SM outright for ~27 us, the fp32 tile kernel
+# shares SMs with the local chain's kernels; kept selectable
+VIRTUAL_TCGEN05 = os.environ.get("GHSCN_VIRTUAL_TCGEN05", "0") != "0"
+
+
 class VirtualLayerFused(torch.autograd.Function):
     """out = [relu]( GCNConv_vv(x_v) + GATConv_lv((x_l, x_v)) ) computed at the INPUT width:
         P = sum_s alpha_s x_l[s]            one-pass attention pool (ghscn_gat_pool_fused_fwd)
@@ -718,15 +723,28 @@ class VirtualLayerFused(torch.autograd.Function):
         u = torch.empty((2, F), dtype=torch.float32, device=dev)
         L.call("ghscn_gat_fold_attention", _p(w_src_c), F, _p(att_src.contiguous()), _p(w_dst_c), F,
                _p(att_dst.contiguous()), H, F, F, 1, _p(u[0]), _p(u[1]), st)
-        pooled = torch.empty((V, F), dtype=torch.float32, device=dev)
+        from . import gemm
+        # wide layers: the projection of [Q | P] by [W_vv | W_src] runs on the tcgen05 tensor cores, one CTA per
+        # (128-row tile, N half) -- ~22 CTAs for 1.3 k virtual nodes, which leaves the other SMs to the local chain
+        # that runs concurrently (the fp32 tile kernel spreads 410 CTAs over every SM and both chains stall)
+        tc = (VIRTUAL_TCGEN05 and gemm.USE_TCGEN05 and F % 4 == 0 and F >= 64
+              and gemm.gemm3x_supported(V, H, 2 * F))
+        ld = 2 * F if tc else F
+        both = torch.empty((V, 2 * F), dtype=torch.float32, device=dev) if tc else None
+        agg = both[:, :F] if tc else torch.empty((V, F), dtype=torch.float32, device=dev)
+        pooled = both[:, F:] if tc else torch.empty((V, F), dtype=torch.float32, device=dev)
         L.call("ghscn_gat_pool_fused_fwd", _p(lvd.rowptr), _p(lvd.col), _p(x_src), x_src.stride(0), _p(x_dst),
-               x_dst.stride(0), _p(u[0]), _p(u[1]), float(meta["slope"]), V, F, 1, _p(pooled), F, st)
-        agg = torch.empty((V, F), dtype=torch.float32, device=dev)
-        L.call("ghscn_spmm", _p(vvd.rowptr), _p(vvd.col), _p(vv_w), _p(x_dst), x_dst.stride(0), _p(agg), F, None, V, F,
-               0, st)
-        out = torch.empty((V, H), dtype=torch.float32, device=dev)
-        L.call("ghscn_small_linear2_fwd", _p(agg), F, _p(w_vv_c), F, _p(b_vv), F, _p(pooled), F, _p(w_src_c), F,
-               _p(b_gat), F, 2 if meta["relu"] else 0, V, H, _p(out), H, st)
+               x_dst.stride(0), _p(u[0]), _p(u[1]), float(meta["slope"]), V, F, 1, _p(pooled), ld, st)
+        L.call("ghscn_spmm", _p(vvd.rowptr), _p(vvd.col), _p(vv_w), _p(x_dst), x_dst.stride(0), _p(agg), ld, None, V,
+               F, 0, st)
+        if tc:
+            wcat = torch.cat([w_vv_c, w_src_c], dim=1)
+            bias = b_vv if b_gat is None else (b_gat if b_vv is None else b_vv + b_gat)
+            out = gemm.gemm3x(both, gemm.gemm3x_prep(wcat), H, bias, relu=bool(meta["relu"]))
+        else:
+            out = torch.empty((V, H), dtype=torch.float32, device=dev)
+            L.call("ghscn_small_linear2_fwd", _p(agg), F, _p(w_vv_c), F, _p(b_vv), F, _p(pooled), F, _p(w_src_c), F,
+                   _p(b_gat), F, 2 if meta["relu"] else 0, V, H, _p(out), H, st)
         ctx.meta = meta
         ctx.save_for_backward(x_src, x_dst)
         return out
