@@ -328,7 +328,7 @@ def test_new_entry_points_validate_arguments_without_a_gpu(built_lib):
     from graph_hscn_b200._lib import GhscnError, lib
     L = lib()
     assert L.query("ghscn_csr_blocked_smem_bytes", 444, 920) == (4 * 444 + 2 + 4 * 920) * 4
-    assert L.query("ghscn_scn_backward_workspace_bytes", 18269, 9, 16, 10) == 72 * 474 * 4
+    assert L.query("ghscn_scn_backward_workspace_bytes", 18269, 9, 16, 10) == 143 * 474 * 4
     with pytest.raises(GhscnError, match="invalid"):
         L.call("ghscn_csr_build_blocked", None, None, 10, None, 1, 10, 10, 10, None, None, None, None, None, None,
                None, None)
