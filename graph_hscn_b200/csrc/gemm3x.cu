@@ -850,7 +850,11 @@ int ghscn_gemm3x(const float* a, int64_t lda, int64_t m, int64_t k, const void* 
     const char* e = getenv("GHSCN_GEMM3X_SPLIT");       // tuning: 0 = never, 1 = always, unset = by wave count
     return e ? atoi(e) : -1;
   }();
-  int split = (p.hv.count == 2) && (tiles > (unsigned)kNumSMs || 2 * tiles <= (unsigned)kNumSMs);
+  // a half CTA costs ~0.54 of a full one (its prologue and drain do not shrink): split only where the finer grid
+  // saves enough waves -- 156 tiles: 3 x 0.54 vs 2 waves; 1 224 tiles (B = 1024): 17 x 0.54 vs 9 waves -> keep full
+  const unsigned waves_full = ceil_div<unsigned>(tiles, (unsigned)kNumSMs);
+  const unsigned waves_half = ceil_div<unsigned>(2 * tiles, (unsigned)kNumSMs);
+  int split = (p.hv.count == 2) && (0.54 * waves_half < waves_full - 0.05);
   if (force_split >= 0) split = force_split && p.hv.count == 2;
   dim3 grid(tiles, split ? 2u : 1u);
   gemm3x_kernel<<<grid, kNnThreads, kNnSmem, as_stream(stream)>>>(
