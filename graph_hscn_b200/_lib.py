@@ -56,6 +56,8 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_small_linear_dx": (I32, [P, I64, P, I64, I32, P, I64, I64, I64, I64, P, I64, P]),
     "ghscn_small_linear_dw_workspace_bytes": (SZ, [I64, I64, I64]),
     "ghscn_small_linear_dw": (I32, [P, I64, P, I64, I32, P, I64, I64, I64, I64, P, P, P, SZ, P]),
+    "ghscn_head_out_loss_supported": (I32, [I64, I64, I64]),
+    "ghscn_head_out_loss": (I32, [P, I64, P, I64, P, P, I64, I64, I64, I64, I64, I32, P, P, P, P, P, P, P]),
     "ghscn_graph_loss": (I32, [P, I64, P, I64, I64, I64, I64, I32, P, P, P, P]),
     "ghscn_relu_dropout_fwd": (I32, [P, I64, F32, P, P, P]),
     "ghscn_relu_dropout_bwd": (I32, [P, P, I64, F32, P, P]),

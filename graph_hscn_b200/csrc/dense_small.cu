@@ -10,6 +10,7 @@
 // fp32 FMA tiles, one launch per product, activation / bias / activation-derivative folded into the loads and the
 // epilogue; every reduction runs in a fixed order (deterministic).  fp32 throughout: same accuracy class as the
 // cuBLAS fp32 path they replace.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -613,6 +614,118 @@ __global__ void __launch_bounds__(1024) graph_loss_kernel(const float* __restric
   if (threadIdx.x == 0) loss[0] = acc * inv;
 }
 
+// ---- output layer + task loss + their backward in ONE launch (small batches) ---------------------------------------
+// model/hscn.py:112 `self.lin_2(...)`, loss.py:6-19 `criterion`, and the backward of both w.r.t. lin_2's parameters and
+// its input: pred = h W2^T + b2, loss / score / d_pred as in graph_loss_kernel, dW2 = d_pred^T h, db2 = colsum(d_pred),
+// dh = d_pred W2.  ONE cluster of 8 CTAs: each CTA owns total_rows/8 rows (their h rows, W2 and d_pred live in its
+// shared memory), the loss and dW2 / db2 partials are combined through distributed shared memory in rank order, so
+// every reduction runs in a fixed order.  Five launches of ~3 us dependent-launch latency each become one.
+constexpr int kHeadCluster = 8;
+
+__global__ void __launch_bounds__(1024) head_out_loss_kernel(const float* __restrict__ h, int64_t ldh,
+                                                             const float* __restrict__ w2, int64_t ldw,
+                                                             const float* __restrict__ b2,
+                                                             const float* __restrict__ target, int64_t ldt, int rows,
+                                                             int total_rows, int H, int C, int mode,
+                                                             float* __restrict__ pred, float* __restrict__ loss,
+                                                             float* __restrict__ score, float* __restrict__ d_w2,
+                                                             float* __restrict__ d_b2, float* __restrict__ d_h) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ float hs_sm[];
+  __shared__ float red[32];
+  const int rank = (int)cluster.block_rank();
+  const int per = (total_rows + kHeadCluster - 1) / kHeadCluster;
+  const int g0 = min(rank * per, total_rows), nloc = min(total_rows, g0 + per) - g0;
+  float* s_w = hs_sm;                         // [C][H]
+  float* s_h = s_w + (size_t)C * H;           // [per][H]
+  float* s_dp = s_h + (size_t)per * H;        // [per][C]: pred, then d_pred
+  float* s_dw = s_dp + (size_t)per * C;       // [C*H + C + 1]: this CTA's dW2 | db2 | loss partial
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
+  const int CH = C * H;
+  for (int i = tid; i < CH; i += blockDim.x) s_w[i] = w2[(int64_t)(i / H) * ldw + i % H];
+  for (int i = tid; i < nloc * H; i += blockDim.x) s_h[i] = h[(int64_t)(g0 + i / H) * ldh + i % H];
+  __syncthreads();
+  // 1. pred: one warp per row
+  for (int g = wid; g < nloc; g += nwarps) {
+    float hv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int k = lane + 32 * j;
+      hv[j] = k < H ? s_h[g * H + k] : 0.f;
+    }
+    for (int c = 0; c < C; ++c) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k = lane + 32 * j;
+        if (k < H) acc = fmaf(hv[j], s_w[c * H + k], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) s_dp[g * C + c] = acc + (b2 ? b2[c] : 0.f);
+    }
+  }
+  __syncthreads();
+  // 2. loss partial, score, d_pred (in place)
+  const float inv = 1.0f / (float)max(rows * C, 1);
+  float acc = 0.f;
+  for (int e = tid; e < nloc * C; e += blockDim.x) {
+    const int r = g0 + e / C, c = e % C;
+    const int64_t o = (int64_t)r * C + c;
+    const float x = s_dp[e];
+    pred[o] = x;
+    const float sg = 1.0f / (1.0f + expf(-x));
+    if (score) score[o] = sg;
+    float d = 0.f;
+    if (r < rows) {
+      const float t = target[(int64_t)r * ldt + c];
+      if (mode == 0) {
+        acc += (1.0f - t) * x - (fminf(x, 0.f) - log1pf(expf(-fabsf(x))));
+        d = (sg - t) * inv;
+      } else {
+        const float df = x - t;
+        acc += fabsf(df);
+        d = (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)) * inv;
+      }
+    }
+    s_dp[e] = d;
+  }
+  acc = block_sum(acc, red);
+  if (tid == 0) s_dw[CH + C] = acc;
+  __syncthreads();
+  // 3. this CTA's partial dW2 [C, H] | db2 [C] over its rows, in row order
+  for (int o = tid; o < CH + C; o += blockDim.x) {
+    float a = 0.f;
+    if (o < CH) {
+      const int c = o / H, k = o - c * H;
+      for (int g = 0; g < nloc; ++g) a = fmaf(s_dp[g * C + c], s_h[g * H + k], a);
+    } else {
+      const int c = o - CH;
+      for (int g = 0; g < nloc; ++g) a += s_dp[g * C + c];
+    }
+    s_dw[o] = a;
+  }
+  // 4. dh = d_pred W2 for this CTA's rows (zero for the padding rows: their d_pred is zero)
+  for (int o = tid; o < nloc * H; o += blockDim.x) {
+    const int g = o / H, k = o - g * H;
+    float a = 0.f;
+    for (int c = 0; c < C; ++c) a = fmaf(s_dp[g * C + c], s_w[c * H + k], a);
+    d_h[(int64_t)(g0 + g) * H + k] = a;
+  }
+  cluster.sync();
+  // 5. combine the partials in rank order: CTA r owns a slice of dW2 | db2 | loss
+  const int n_out = CH + C + 1, chunk = (n_out + kHeadCluster - 1) / kHeadCluster;
+  for (int o = rank * chunk + tid; o < min(n_out, (rank + 1) * chunk); o += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int q = 0; q < kHeadCluster; ++q) a += cluster.map_shared_rank(s_dw, q)[o];
+    if (o < CH) d_w2[o] = a;
+    else if (o < CH + C) { if (d_b2 != nullptr) d_b2[o - CH] = a; }
+    else loss[0] = a * inv;
+  }
+  cluster.sync();                              // nobody leaves while a peer still reads its shared memory
+}
+
 }  // namespace ghscn
 
 using namespace ghscn;
@@ -706,6 +819,49 @@ int ghscn_small_linear_dw(const float* dy, int64_t lddy, const float* y_ref, int
         static_cast<const float*>(workspace), z, (int64_t)N * K, N, dw, db);
   }
   GHSCN_LAUNCH_CHECK_N(z > 1 ? 2 : 1);
+  return GHSCN_OK;
+}
+
+static size_t head_out_loss_smem(int64_t total_rows, int64_t hidden, int64_t num_targets) {
+  const int64_t per = (total_rows + kHeadCluster - 1) / kHeadCluster;
+  return (size_t)(2 * num_targets * hidden + per * hidden + per * num_targets + num_targets + 1) * sizeof(float);
+}
+
+int ghscn_head_out_loss_supported(int64_t total_rows, int64_t hidden, int64_t num_targets) {
+  if (total_rows <= 0 || total_rows > 256 || hidden <= 0 || hidden > 512 || num_targets <= 0 || num_targets > 32) return 0;
+  return head_out_loss_smem(total_rows, hidden, num_targets) <= 200 * 1024;
+}
+
+int ghscn_head_out_loss(const float* h, int64_t ldh, const float* w2, int64_t ldw, const float* b2, const float* target,
+                        int64_t ldt, int64_t rows, int64_t total_rows, int64_t hidden, int64_t num_targets,
+                        int32_t mode, float* pred, float* loss, float* score, float* d_w2, float* d_b2, float* d_h,
+                        ghscn_stream_t stream) {
+  GHSCN_REQUIRE(rows >= 0 && total_rows >= rows && (mode == 0 || mode == 1));
+  if (!ghscn_head_out_loss_supported(total_rows, hidden, num_targets)) return GHSCN_E_UNSUPPORTED;
+  GHSCN_REQUIRE(h && w2 && pred && loss && d_w2 && d_h && ldh >= hidden && ldw >= hidden);
+  GHSCN_REQUIRE(rows == 0 || (target && ldt >= num_targets));
+  const size_t shm = head_out_loss_smem(total_rows, hidden, num_targets);
+  if (shm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(head_out_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+    if (e != cudaSuccess) return (int)e;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kHeadCluster);
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = shm;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kHeadCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, head_out_loss_kernel, h, ldh, w2, ldw, b2, target, ldt, (int)rows,
+                                     (int)total_rows, (int)hidden, (int)num_targets, (int)mode, pred, loss, score,
+                                     d_w2, d_b2, d_h);
+  if (e != cudaSuccess) return (int)e;
+  GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }
 

@@ -177,6 +177,11 @@ class HSCN(nn.Module):
                 self._fused_virtual = True
 
     def forward(self, x_dict: Dict[str, Tensor], edge_index_dict, batch) -> Tensor:
+        return self.lin_2(self.forward_hidden(x_dict, edge_index_dict, batch))
+
+    def forward_hidden(self, x_dict: Dict[str, Tensor], edge_index_dict, batch) -> Tensor:
+        """model/hscn.py:102-111: everything in front of the output layer `lin_2` (the training step fuses that layer
+        with the loss and their backward, ops.head_out_loss)."""
         # Operator sets whose HeteroConv runs the destination types on parallel CUDA streams (`last_streams`) keep
         # every type's tensors on its own stream across the layers: the "virtual" branch never feeds "local"
         # (model/hscn.py:84-94 has no virtual->local relation), so the caller's stream only waits for it once, at the
@@ -209,12 +214,11 @@ class HSCN(nn.Module):
             hidden = self.ops.linear_act(self.lin_1, pooled, self.activation)
         if hidden is None:
             hidden = self.activation(self.lin_1(pooled))
-        pred = self.lin_2(hidden)
         if streams is not None and not getattr(self, "defer_branch_join", False):
             for st in streams.values():
                 if st is not main:
                     main.wait_stream(st)
-        return pred
+        return hidden
 
 
 def criterion(loss_fn: str, pred: Tensor, true: Tensor):

@@ -695,6 +695,61 @@ def graph_loss(loss_fn: str, pred: Tensor, target: Tensor, rows: Optional[int] =
     return loss, score[:rows]
 
 
+class HeadOutLoss(torch.autograd.Function):
+    """lin_2 (model/hscn.py:112) + criterion (loss.py:6-19) + the backward of both in ONE launch (batches of <= 256
+    graphs): the forward already produces d loss / d hidden, d loss / d W2 and d loss / d b2 for an incoming gradient
+    of 1; the backward scales them by the incoming scalar (skipped with `unit_grad`, for callers that differentiate the
+    loss itself -- `loss.backward()` -- and nothing derived from it)."""
+
+    @staticmethod
+    def forward(ctx, hidden: Tensor, weight: Tensor, bias: Optional[Tensor], target: Tensor, rows: int, mode: int,
+                unit_grad: bool):
+        hidden = _rowmajor(hidden)
+        weight = _rowmajor(weight)
+        target = _rowmajor(target.float())
+        total, h = hidden.shape
+        c = weight.size(0)
+        dev = hidden.device
+        out = torch.empty(1 + 2 * total * c, dtype=torch.float32, device=dev)
+        loss, pred, score = out[:1], out[1:1 + total * c].view(total, c), out[1 + total * c:].view(total, c)
+        grads = torch.empty(total * h + c * h + c, dtype=torch.float32, device=dev)
+        d_h = grads[:total * h].view(total, h)
+        d_w = grads[total * h:total * h + c * h].view(c, h)
+        d_b = grads[total * h + c * h:]
+        lib().call("ghscn_head_out_loss", _p(hidden), hidden.stride(0), _p(weight), weight.stride(0),
+                   _p(bias) if bias is not None else None, _p(target), target.stride(0), int(rows), total, h, c,
+                   int(mode), _p(pred), _p(loss), _p(score), _p(d_w), _p(d_b) if bias is not None else None, _p(d_h),
+                   _stream())
+        ctx.save_for_backward(grads)
+        ctx.dims = (total, h, c, bias is not None, bool(unit_grad))
+        ctx.mark_non_differentiable(pred, score)
+        return loss.view(()), pred, score
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_pred, _g_score):
+        (grads,) = ctx.saved_tensors
+        total, h, c, has_bias, unit = ctx.dims
+        if not unit:
+            grads = grads * g_loss
+        d_h = grads[:total * h].view(total, h)
+        d_w = grads[total * h:total * h + c * h].view(c, h)
+        d_b = grads[total * h + c * h:] if has_bias else None
+        return d_h, d_w, d_b, None, None, None, None
+
+
+def head_out_loss_ok(total_rows: int, hidden: int, num_targets: int) -> bool:
+    return bool(lib().query("ghscn_head_out_loss_supported", int(total_rows), int(hidden), int(num_targets)))
+
+
+def head_out_loss(loss_fn: str, hidden: Tensor, weight: Tensor, bias: Optional[Tensor], target: Tensor,
+                  rows: Optional[int] = None, unit_grad: bool = False):
+    """-> (loss, pred, sigmoid(pred[:rows])): `criterion(loss_fn, lin_2(hidden), target)` of model/hscn.py:112 +
+    loss.py:6-19 for [B, C] float targets, forward and backward in one kernel."""
+    rows = hidden.size(0) if rows is None else int(rows)
+    loss, pred, score = HeadOutLoss.apply(hidden, weight, bias, target, rows, LOSS_MODES[loss_fn], unit_grad)
+    return loss, pred, score[:rows]
+
+
 # =============================================================================================
 # fused "virtual" destination of the HeteroConv: v->v GCN + l->v GAT pool, summed (model/hscn.py:83-96)
 # =============================================================================================

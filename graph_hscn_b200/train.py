@@ -698,6 +698,22 @@ class GraphHSCNStep:
                                          self.cfg.num_clusters, y=d["y"], padded=self.padded,
                                          num_graphs=shape.graphs + shape.dummies, x_float=x_f)
 
+    def _hscn_loss(self, hb) -> Tensor:
+        """pred = HSCN(batch); loss = criterion(pred, y) (train/train.py:81-82).  On CUDA, for [B, C] float targets and
+        <= 256 graphs, the output layer, the loss and their backward are one kernel (the step differentiates the loss
+        itself, so the incoming gradient is 1)."""
+        y = hb["local"].y
+        lin = self.hscn.lin_2
+        if (self.device.type == "cuda" and y.dim() == 2 and self.cfg.loss_fn in ops.LOSS_MODES
+                and os.environ.get("GHSCN_FUSED_HEAD", "1") != "0" and torch.is_floating_point(y)
+                and ops.head_out_loss_ok(self.runner.shape.graphs + self.runner.shape.dummies, lin.weight.size(1),
+                                         lin.weight.size(0))):
+            hidden = self.hscn.forward_hidden(hb.x_dict, hb.edge_index_dict, hb)
+            return ops.head_out_loss(self.cfg.loss_fn, hidden, lin.weight, lin.bias, y, rows=self.B,
+                                     unit_grad=True)[0]
+        pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)
+        return self._task_loss(pred, y)
+
     def _task_loss(self, pred: Tensor, y: Tensor) -> Tensor:
         """criterion(loss_fn, pred, true) of train/train.py:82 over the B real graphs (the dummy graphs' rows carry no
         loss and no gradient); on CUDA the loss, its gradient and the sigmoid score come from one kernel."""
@@ -717,8 +733,7 @@ class GraphHSCNStep:
             ei, ew, _, mc, ol = self._forward_scn(x_f)
             scn_live = live_parameter_names(self.scn, mc + ol)
             hb = self._assign(x_f, ei, ew)
-            pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)            # materialises lazy weights
-            loss = self._task_loss(pred, hb["local"].y)
+            loss = self._hscn_loss(hb)                                     # materialises lazy weights
             hscn_live = live_parameter_names(self.hscn, loss)
         self.scn_grads = FlatGradients(self.scn, scn_live)
         self.hscn_grads = FlatGradients(self.hscn, hscn_live)
@@ -770,8 +785,7 @@ class GraphHSCNStep:
         self.scn_grads.all_reduce_mean(world)
         self.scn_opt.step()
         hb = self._assign(x_f, ei, ew)
-        pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)
-        loss = self._task_loss(pred, hb["local"].y)
+        loss = self._hscn_loss(hb)
         self.hscn_grads.backward_into(loss, accumulate=accumulate)
         self.losses[2:3].copy_(loss.detach().view(1))
         if update:
@@ -811,10 +825,9 @@ class GraphHSCNStep:
             hb = self._assign(x_f, ei, ew)
         self.hscn.defer_branch_join = True
         try:
-            pred = self.hscn(hb.x_dict, hb.edge_index_dict, hb)
+            loss = self._hscn_loss(hb)
         finally:
             self.hscn.defer_branch_join = False
-        loss = self._task_loss(pred, hb["local"].y)
         self.hscn_grads.backward_into(loss, accumulate=accumulate)
         self.losses[2:3].copy_(loss.detach().view(1))
         if update:

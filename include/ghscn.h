@@ -325,6 +325,16 @@ GHSCN_API int ghscn_graph_loss(const float* pred, int64_t ldp, const float* targ
                                int64_t total_rows, int64_t num_targets, int32_t mode, float* loss, float* d_pred,
                                float* score, ghscn_stream_t stream);
 
+/* Output layer + task loss + their backward in ONE launch, for batches of <= 256 graphs (model/hscn.py:112 `lin_2`,
+ * loss.py:6-19, train/train.py:82-87): pred = h W2^T + b2 [total_rows, C]; loss / score / d_pred as ghscn_graph_loss over
+ * the first `rows` rows; d_w2 [C, H] = d_pred^T h, d_b2 [C], d_h [total_rows, H] = d_pred W2 -- all for d loss = 1 (the
+ * caller scales by the incoming gradient).  hidden <= 512, num_targets <= 32. */
+GHSCN_API int ghscn_head_out_loss_supported(int64_t total_rows, int64_t hidden, int64_t num_targets);
+GHSCN_API int ghscn_head_out_loss(const float* h, int64_t ldh, const float* w2, int64_t ldw, const float* b2,
+                                  const float* target, int64_t ldt, int64_t rows, int64_t total_rows, int64_t hidden,
+                                  int64_t num_targets, int32_t mode, float* pred, float* loss, float* score,
+                                  float* d_w2, float* d_b2, float* d_h, ghscn_stream_t stream);
+
 /* ---- K5: bipartite GAT cluster pool (local -> virtual) ---------------------------------------
  * Replaces GATConv((-1,-1), H, add_self_loops=False) on ("local","to","virtual")
  * (model/hscn.py:85-87,118-125).  SURVEY 8a row a9, Appendix A.8.  heads = 1.

@@ -290,6 +290,38 @@ def test_graph_loss_matches_criterion(cuda, loss_fn, rows, total, c):
     assert not pt.grad[rows:].any()
 
 
+@pytest.mark.parametrize("loss_fn,rows,total,h,c,bias,unit", [("cross_entropy", 128, 130, 300, 10, True, False),
+                                                             ("l1", 200, 256, 128, 11, True, True),
+                                                             ("cross_entropy", 5, 5, 512, 3, False, False)])
+def test_head_out_loss_matches_unfused(cuda, loss_fn, rows, total, h, c, bias, unit):
+    """Output layer + criterion + their backward in one launch (model/hscn.py:112, loss.py:6-19) vs the float64
+    composition F.linear -> criterion -> autograd; padding rows get no gradient."""
+    import torch.nn.functional as F
+    from graph_hscn_b200 import models, ops
+    g = torch.Generator().manual_seed(total + c)
+    hid = torch.randn(total, h, generator=g)
+    w = torch.randn(c, h, generator=g) / h ** 0.5
+    b = torch.randn(c, generator=g) if bias else None
+    y = (torch.rand(total, c, generator=g) < 0.3).float() if loss_fn == "cross_entropy" else torch.randn(total, c, generator=g)
+    scale = 1.0 if unit else 1.7
+    ref = [t.double().requires_grad_() if t is not None else None for t in (hid, w, b)]
+    pred_r = F.linear(ref[0], ref[1], ref[2])
+    lr, sr = models.criterion(loss_fn, pred_r[:rows], y[:rows].double())
+    (lr * scale).backward()
+    dev = [t.to(cuda).requires_grad_() if t is not None else None for t in (hid, w, b)]
+    assert ops.head_out_loss_ok(total, h, c)
+    lt, pred, score = ops.head_out_loss(loss_fn, dev[0], dev[1], dev[2], y.to(cuda), rows=rows, unit_grad=unit)
+    (lt * scale).backward()
+    assert_close(lt, lr.float(), 2e-6, "loss")
+    assert_close(pred, pred_r.float(), 2e-6, "pred")
+    assert_close(score, sr.float(), 2e-6, "score")
+    for name, a, r in zip(("d hidden", "d W2", "d b2"), dev, ref):
+        if a is not None:
+            assert_close(a.grad, r.grad.float(), 2e-6, name)
+    assert not dev[0].grad[rows:].any()
+    assert not ops.head_out_loss_ok(1027, 300, 11)                  # larger batches keep the separate kernels
+
+
 def test_relu_dropout_fused(cuda):
     """model/mpnn.py:57-58 `F.dropout(self.activation(x), p)` as one kernel: keep rate, scaling, zeros where relu is
     zero, a fresh mask per call (also across CUDA-graph replays), backward from the output alone."""
