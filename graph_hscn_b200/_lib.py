@@ -73,6 +73,8 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_spmm_masked_supported": (I32, [I64, I64, I64, I64]),
     "ghscn_spmm_masked": (I32, [P, P, P, P, I64, P, I64, P, I64, I64, I64, P]),
     "ghscn_colsum_masked": (I32, [P, I64, P, I64, I64, I64, P, P, SZ, P]),
+    "ghscn_relu_grad_colsum_partial": (I32, [P, I64, P, I64, I64, I64, P, I64, P, SZ, P]),
+    "ghscn_colsum_finish": (I32, [P, SZ, I64, I64, P, P]),
     "ghscn_spmm_pool": (I32, [P, P, P, P, I64, P, I64, P, I64, I64, P]),
     "ghscn_gat_scores": (I32, [P, P, P, P, F32, I64, P, P]),
     "ghscn_spmm_edge_grad": (I32, [P, P, P, P, I64, P, I64, I64, I64, I64, P, P]),

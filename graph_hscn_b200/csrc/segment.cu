@@ -115,14 +115,15 @@ __global__ void __launch_bounds__(256) segment_broadcast_kernel(const float* __r
 
 // ---- column sum (bias gradients: db = sum_rows dY) ---------------------------------------------------
 // Stage 1: CTA (rows chunk, 128-column tile) -> partial[chunk, :];  stage 2: fixed-order sum over chunks.
-constexpr int kColsumRows = 256;  // rows per CTA (32 per warp)
+constexpr int kColsumRows = 64;  // rows per CTA
 
 template <int VEC>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int64_t ldx,
                                                              int num_rows, int num_feat,
                                                              float* __restrict__ partial,
                                                              const float* __restrict__ mask = nullptr,
-                                                             int64_t ldm = 0) {
+                                                             int64_t ldm = 0, float* __restrict__ masked = nullptr,
+                                                             int64_t ldo = 0) {
   __shared__ float part[8][32 * VEC];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = (blockIdx.x * 32 + lane) * VEC;
@@ -142,11 +143,15 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
             const float4 m = ldg_f4(mask + (int64_t)r * ldm + f);
             a.x = m.x > 0.f ? a.x : 0.f; a.y = m.y > 0.f ? a.y : 0.f;
             a.z = m.z > 0.f ? a.z : 0.f; a.w = m.w > 0.f ? a.w : 0.f;
+            if (masked != nullptr) *reinterpret_cast<float4*>(masked + (int64_t)r * ldo + f) = a;
           }
           acc[0] += a.x; acc[1 % VEC] += a.y; acc[2 % VEC] += a.z; acc[3 % VEC] += a.w;
         } else {
           float a = __ldg(x + (int64_t)r * ldx + f);
-          if (mask != nullptr && !(__ldg(mask + (int64_t)r * ldm + f) > 0.f)) a = 0.f;
+          if (mask != nullptr) {
+            if (!(__ldg(mask + (int64_t)r * ldm + f) > 0.f)) a = 0.f;
+            if (masked != nullptr) masked[(int64_t)r * ldo + f] = a;
+          }
           acc[0] += a;
         }
       }
@@ -163,6 +168,43 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
       for (int w = 0; w < 8; ++w) t += part[w][lane * VEC + v];
       partial[(int64_t)blockIdx.y * num_feat + f + v] = t;
     }
+  }
+}
+
+// Row-coalesced stage 1 for feature widths that are a multiple of 4 (<= 1280 columns): a CTA owns kColsumRows rows, its
+// threads tile (rows-per-pass x float4 columns), so every warp reads whole contiguous row segments (the 128-column tile
+// kernel above leaves 27 % of its lanes idle at 300 columns).  Optional ReLU mask, optional write of the masked rows.
+template <bool MASK, bool WRITE>
+__global__ void __launch_bounds__(320) colsum_rows_kernel(const float* __restrict__ x, int64_t ldx, int num_rows,
+                                                          int f4, int rows_per_pass, float* __restrict__ partial,
+                                                          const float* __restrict__ mask, int64_t ldm,
+                                                          float* __restrict__ masked, int64_t ldo) {
+  extern __shared__ float4 cs_part[];            // [rows_per_pass][f4]
+  const int rp = threadIdx.x / f4, c4 = threadIdx.x - rp * f4;
+  const int r0 = blockIdx.x * kColsumRows, r1 = min(num_rows, r0 + kColsumRows);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rp < rows_per_pass) {
+#pragma unroll 4
+    for (int r = r0 + rp; r < r1; r += rows_per_pass) {
+      float4 a = ldg_f4(x + (int64_t)r * ldx + c4 * 4);
+      if (MASK) {
+        const float4 m = ldg_f4(mask + (int64_t)r * ldm + c4 * 4);
+        a.x = m.x > 0.f ? a.x : 0.f; a.y = m.y > 0.f ? a.y : 0.f;
+        a.z = m.z > 0.f ? a.z : 0.f; a.w = m.w > 0.f ? a.w : 0.f;
+        if (WRITE) *reinterpret_cast<float4*>(masked + (int64_t)r * ldo + c4 * 4) = a;
+      }
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    cs_part[rp * f4 + c4] = acc;
+  }
+  __syncthreads();
+  if (rp == 0) {
+    float4 t = cs_part[c4];
+    for (int q = 1; q < rows_per_pass; ++q) {
+      const float4 u = cs_part[q * f4 + c4];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    *reinterpret_cast<float4*>(partial + (int64_t)blockIdx.x * f4 * 4 + c4 * 4) = t;
   }
 }
 
@@ -479,30 +521,69 @@ int ghscn_colsum(const float* x, int64_t ldx, int64_t num_rows, int64_t num_feat
 int ghscn_colsum_masked(const float* x, int64_t ldx, const float* mask, int64_t ldm, int64_t num_rows,
                         int64_t num_feat, float* out, void* workspace, size_t workspace_bytes,
                         ghscn_stream_t stream_) {
+  const int rc = ghscn_relu_grad_colsum_partial(x, ldx, mask, ldm, num_rows, num_feat, nullptr, 0, workspace,
+                                                workspace_bytes, stream_);
+  if (rc != GHSCN_OK) return rc;
+  return ghscn_colsum_finish(workspace, workspace_bytes, num_rows, num_feat, out, stream_);
+}
+
+int ghscn_colsum_finish(const void* workspace, size_t workspace_bytes, int64_t num_rows, int64_t num_feat, float* out,
+                        ghscn_stream_t stream_) {
   GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && num_rows < ((int64_t)1 << 31) && num_feat < ((int64_t)1 << 24));
   if (num_feat == 0) return GHSCN_OK;
-  GHSCN_REQUIRE(out && (num_rows == 0 || (x && ldx >= num_feat)));
+  GHSCN_REQUIRE(out != nullptr);
+  if (workspace_bytes < ghscn_colsum_workspace_bytes(num_rows, num_feat) || workspace == nullptr)
+    return GHSCN_E_WORKSPACE;
+  const int chunks = (int)ceil_div<int64_t>(num_rows, kColsumRows);
+  colsum_final_kernel<<<(unsigned)ceil_div<int64_t>(num_feat, 32), 256, 0, as_stream(stream_)>>>(
+      static_cast<const float*>(workspace), chunks, (int)num_feat, out);
+  GHSCN_LAUNCH_CHECK();
+  return GHSCN_OK;
+}
+
+int ghscn_relu_grad_colsum_partial(const float* x, int64_t ldx, const float* mask, int64_t ldm, int64_t num_rows,
+                                   int64_t num_feat, float* masked, int64_t ldo, void* workspace,
+                                   size_t workspace_bytes, ghscn_stream_t stream_) {
+  GHSCN_REQUIRE(num_rows >= 0 && num_feat >= 0 && num_rows < ((int64_t)1 << 31) && num_feat < ((int64_t)1 << 24));
+  if (num_feat == 0) return GHSCN_OK;
+  GHSCN_REQUIRE(num_rows == 0 || (x && ldx >= num_feat));
   GHSCN_REQUIRE(mask == nullptr || ldm >= num_feat);
+  GHSCN_REQUIRE(masked == nullptr || (mask != nullptr && ldo >= num_feat));
   if (workspace_bytes < ghscn_colsum_workspace_bytes(num_rows, num_feat) || workspace == nullptr)
     return GHSCN_E_WORKSPACE;
   cudaStream_t stream = as_stream(stream_);
   float* partial = static_cast<float*>(workspace);
   const int chunks = (int)ceil_div<int64_t>(num_rows, kColsumRows);
-  if (chunks > 65535) return GHSCN_E_UNSUPPORTED;
   if (chunks > 0) {
     const bool vec4 = num_feat % 4 == 0 && ldx % 4 == 0 && aligned16(x, x) &&
-                      (mask == nullptr || (ldm % 4 == 0 && aligned16(mask, mask)));
-    if (vec4) {
+                      (mask == nullptr || (ldm % 4 == 0 && aligned16(mask, mask))) &&
+                      (masked == nullptr || (ldo % 4 == 0 && aligned16(masked, masked)));
+    if (!(vec4 && num_feat <= 1280) && chunks > 65535) return GHSCN_E_UNSUPPORTED;      // grid.y of the tile kernel
+    if (vec4 && num_feat <= 1280) {
+      const int f4 = (int)num_feat / 4;
+      const int rpp = f4 >= 320 ? 1 : 320 / f4;
+      const int threads = (rpp * f4 + 31) / 32 * 32;
+      const size_t shm = (size_t)rpp * f4 * sizeof(float4);
+      if (mask == nullptr)
+        colsum_rows_kernel<false, false><<<chunks, threads, shm, stream>>>(x, ldx, (int)num_rows, f4, rpp, partial,
+                                                                          nullptr, 0, nullptr, 0);
+      else if (masked == nullptr)
+        colsum_rows_kernel<true, false><<<chunks, threads, shm, stream>>>(x, ldx, (int)num_rows, f4, rpp, partial,
+                                                                         mask, ldm, nullptr, 0);
+      else
+        colsum_rows_kernel<true, true><<<chunks, threads, shm, stream>>>(x, ldx, (int)num_rows, f4, rpp, partial,
+                                                                        mask, ldm, masked, ldo);
+    } else if (vec4) {
       dim3 grid((unsigned)ceil_div<int64_t>(num_feat, 128), (unsigned)chunks);
-      colsum_partial_kernel<4><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial, mask, ldm);
+      colsum_partial_kernel<4><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial, mask, ldm,
+                                                         masked, ldo);
     } else {
       dim3 grid((unsigned)ceil_div<int64_t>(num_feat, 32), (unsigned)chunks);
-      colsum_partial_kernel<1><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial, mask, ldm);
+      colsum_partial_kernel<1><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial, mask, ldm,
+                                                         masked, ldo);
     }
+    GHSCN_LAUNCH_CHECK();
   }
-  colsum_final_kernel<<<(unsigned)ceil_div<int64_t>(num_feat, 32), 256, 0, stream>>>(partial, chunks,
-                                                                                     (int)num_feat, out);
-  GHSCN_LAUNCH_CHECK_N(chunks > 0 ? 2 : 1);
   return GHSCN_OK;
 }
 

@@ -22,6 +22,9 @@ _STATS_STRIDE = 8
 
 
 PARALLEL_AUX = os.environ.get("GHSCN_PARALLEL_AUX", "1") != "0"
+# measured in the step: 0.641 ms fused vs 0.637 ms separate (the step is bound by SM occupancy, not by the length of
+# the backward chain; the separate column sum already overlaps the transposed aggregation) -- kept selectable
+FUSED_RELU_COLSUM = os.environ.get("GHSCN_FUSED_RELU_COLSUM", "0") != "0"
 _AUX_STREAMS: dict = {}
 
 
@@ -82,6 +85,32 @@ def colsum_masked(x: Tensor, mask: Tensor) -> Tensor:
 @colsum_masked.register_fake
 def _(x, mask):
     return x.new_empty((x.size(1),))
+
+
+def relu_grad_colsum(dy: Tensor, y: Tensor, fork: bool = True):
+    """-> (dy (.) [y > 0], its column sums): ReLU backward and GCNConv's bias gradient from ONE pass over dy (the
+    separate threshold + column-sum kernels read dy twice).  The tiny second reduction stage runs on the auxiliary
+    stream when `fork` is set; the caller joins with `join()` after launching what follows on its own stream."""
+    dy, y = _rowmajor(dy), _rowmajor(y)
+    N, F = dy.shape
+    dev = dy.device
+    out = torch.empty((N, F), dtype=torch.float32, device=dev)
+    L = lib()
+    ws_bytes = L.query("ghscn_colsum_workspace_bytes", N, F)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    L.call("ghscn_relu_grad_colsum_partial", _p(dy), dy.stride(0), _p(y), y.stride(0), N, F, _p(out), F, _p(ws),
+           ws_bytes, _stream())
+    main = torch.cuda.current_stream()
+    side = _aux_stream(dev) if fork and PARALLEL_AUX else None
+    if side is not None:
+        side.wait_stream(main)
+    with torch.cuda.stream(side if side is not None else main):
+        db = torch.empty(F, dtype=torch.float32, device=dev)
+        L.call("ghscn_colsum_finish", _p(ws), ws_bytes, N, F, _p(db), _stream())
+    if side is not None:
+        db.record_stream(main)
+        ws.record_stream(side)
+    return out, db, (lambda: main.wait_stream(side)) if side is not None else (lambda: None)
 
 
 # =============================================================================================
@@ -168,10 +197,15 @@ def _spmm_backward(ctx, dy):
     # the kernels support it, instead of a separate pass that reads dy and y and writes dy (.) [y > 0]
     masked = (ctx.relu and FUSED_RELU_BACKWARD and not ctx.w_needs_grad and dy.is_cuda and dy.dim() == 2
               and bool(lib().query("ghscn_spmm_masked_supported", dy.size(1), dy.stride(0), y.stride(0), dy.size(1))))
-    if ctx.relu and not masked:
-        dy = torch.ops.aten.threshold_backward(dy, y, 0.0)      # dy * (y > 0), one vectorised pass
     dx = dw = dbias = None
     want_bias = ctx.has_bias and ctx.needs_input_grad[7]
+    join = None
+    if ctx.relu and not masked:
+        if want_bias and FUSED_RELU_COLSUM and dy.is_cuda and dy.dim() == 2:
+            dy, dbias, join = relu_grad_colsum(dy, y, fork=bool(ctx.needs_input_grad[6]))
+            want_bias = False
+        else:
+            dy = torch.ops.aten.threshold_backward(dy, y, 0.0)      # dy * (y > 0), one vectorised pass
     # The bias gradient (a column sum of dy) and the transposed aggregation both only read dy: the column sum runs on
     # an auxiliary stream, forked here and joined before returning (graph-capturable; same kernels, same results).
     side = main = None
@@ -193,6 +227,8 @@ def _spmm_backward(ctx, dy):
         main.wait_stream(side)
     elif want_bias:
         dbias = colsum_masked(dy, y) if masked else colsum(dy)
+    if join is not None:
+        join()
     return None, None, dw, None, None, None, dx, dbias, None
 
 
@@ -723,12 +759,15 @@ class HeadOutLoss(torch.autograd.Function):
         ctx.save_for_backward(grads)
         ctx.dims = (total, h, c, bias is not None, bool(unit_grad))
         ctx.mark_non_differentiable(pred, score)
+        ctx.set_materialize_grads(False)        # no zero fills for the gradients of pred / score
         return loss.view(()), pred, score
 
     @staticmethod
     def backward(ctx, g_loss, _g_pred, _g_score):
         (grads,) = ctx.saved_tensors
         total, h, c, has_bias, unit = ctx.dims
+        if g_loss is None:
+            return None, None, None, None, None, None, None
         if not unit:
             grads = grads * g_loss
         d_h = grads[:total * h].view(total, h)

@@ -185,6 +185,16 @@ GHSCN_API int ghscn_colsum_masked(const float* x, int64_t ldx, const float* mask
                                   int64_t num_feat, float* out, void* workspace, size_t workspace_bytes,
                                   ghscn_stream_t stream);
 
+/* ReLU backward and the first stage of the bias gradient in ONE pass over dY (the backward of `.relu()` behind
+ * GCNConv, model/hscn.py:110, followed by GCNConv's db = sum_rows dY): masked[r,f] = mask[r,f] > 0 ? x[r,f] : 0 (skipped
+ * when masked is NULL) and the per-row-chunk column partials of the masked values in `workspace`;
+ * ghscn_colsum_finish adds the partials in chunk order.  ghscn_colsum_masked = partial (masked NULL) + finish. */
+GHSCN_API int ghscn_relu_grad_colsum_partial(const float* x, int64_t ldx, const float* mask, int64_t ldm,
+                                             int64_t num_rows, int64_t num_feat, float* masked, int64_t ldo,
+                                             void* workspace, size_t workspace_bytes, ghscn_stream_t stream);
+GHSCN_API int ghscn_colsum_finish(const void* workspace, size_t workspace_bytes, int64_t num_rows, int64_t num_feat,
+                                  float* out, ghscn_stream_t stream);
+
 /* hi/lo split for the 3xTF32 GEMM scheme used by the layers' dense projections (x W^T of GCNConv / GATConv /
  * Linear): hi = x with the low 13 mantissa bits cleared (exact in TF32), lo = x - hi.  16-byte aligned buffers. */
 GHSCN_API int ghscn_split_tf32(const float* x, int64_t n, float* hi, float* lo, ghscn_stream_t stream);

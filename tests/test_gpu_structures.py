@@ -322,6 +322,22 @@ def test_head_out_loss_matches_unfused(cuda, loss_fn, rows, total, h, c, bias, u
     assert not ops.head_out_loss_ok(1027, 300, 11)                  # larger batches keep the separate kernels
 
 
+@pytest.mark.parametrize("n,f", [(5000, 300), (777, 37), (1, 4)])
+def test_relu_grad_colsum_matches_threshold_and_sum(cuda, n, f):
+    """ReLU backward + first stage of the bias gradient in one pass (model/hscn.py:110 `.relu()` behind GCNConv): the
+    masked gradient is bit-identical to threshold_backward, the column sums match float64."""
+    from graph_hscn_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    dy = torch.randn(n, f, generator=g).to(cuda)
+    y = torch.relu(torch.randn(n, f, generator=g)).to(cuda)
+    for fork in (True, False):
+        out, db, join = ops.relu_grad_colsum(dy, y, fork=fork)
+        join()
+        want = torch.ops.aten.threshold_backward(dy, y, 0.0)
+        assert torch.equal(out, want)
+        assert_close(db, want.double().sum(0).float(), 2e-6, "db")
+
+
 def test_relu_dropout_fused(cuda):
     """model/mpnn.py:57-58 `F.dropout(self.activation(x), p)` as one kernel: keep rate, scaling, zeros where relu is
     zero, a fresh mask per call (also across CUDA-graph replays), backward from the output alone."""
