@@ -95,6 +95,10 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
                                      P, P, P, P, P, P, P, P, SZ, P, I32]),
     "ghscn_mincut_bwd": (I32, [P, P, I64, P, P, P, P, P, P, P, F32, I64, I64, I64, I64, I32,
                                P, P, P, P, P, P, P, I64, P, I64, P, SZ, P]),
+    "ghscn_mincut_bwd_split_workspace_bytes": (SZ, [I64, I64, I64]),
+    "ghscn_mincut_bwd_split_supported": (I32, [I64, I64, I64, I64, I32]),
+    "ghscn_mincut_bwd_split": (I32, [P, P, I64, P, P, P, P, P, P, P, F32, I64, I64, I64, I64, I32,
+                                     P, P, P, P, P, P, P, I64, P, I64, P, SZ, P]),
     "ghscn_cluster_argmax": (I32, [P, I64, I64, I64, P, P]),
     "ghscn_virtual_build": (I32, [P, P, P, I32, I64, I64, I64, I64, P, P, P, P]),
     "ghscn_virtual_offsets": (I32, [P, I64, P, P, P]),

@@ -239,6 +239,8 @@ torch.library.register_autograd("ghscn::spmm", _spmm_backward, setup_context=_sp
 # fused SCN node pipeline: GraphConv aggregation + lin_rel + lin_root + activation + cluster Linear
 # =============================================================================================
 MINCUT_TC_MIN_K = int(os.environ.get("GHSCN_MINCUT_TC_MIN_K", "64"))
+MINCUT_TC_PHASE1 = int(os.environ.get("GHSCN_MINCUT_TC_PHASE1", "3"))      # 3: A S by the batch SpMM; 1: per-graph CTAs
+MINCUT_SPLIT_MIN_K = int(os.environ.get("GHSCN_MINCUT_SPLIT_MIN_K", "64"))   # backward as per-graph tiled GEMMs
 MINCUT_TC_KK = os.environ.get("GHSCN_MINCUT_TC_KK", "1") != "0"      # S^T S and S^T A S on the tensor cores too
 FUSED_SCN_BACKWARD = os.environ.get("GHSCN_FUSED_SCN_BACKWARD", "1") != "0"
 SCN_ACTS = {"identity": 0, "elu": 1, "relu": 2, "tanh": 3}
@@ -543,11 +545,17 @@ def mincut_bwd(s_soft: Tensor, x: Optional[Tensor], ptr: Tensor, rowptr: Tensor,
     dz = torch.empty((N, K), dtype=torch.float32, device=dev)
     dx = torch.empty((N, num_feat), dtype=torch.float32, device=dev) if want_dx else torch.empty(0, device=dev)
     L = lib()
-    ws_bytes = L.query("ghscn_mincut_workspace_bytes", N, B, K)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     if x is not None:
         x = _rowmajor(x)
-    L.call("ghscn_mincut_bwd", _p(s_soft), _p(x), x.stride(0) if x is not None else 0, _p(ptr), _p(rowptr), _p(col),
+    if g_out is not None:
+        g_out = g_out.contiguous()
+    ldx = x.stride(0) if x is not None else 0
+    # dense-bound corner: the per-graph products as tiled GEMMs over all graphs at once
+    split = (K >= MINCUT_SPLIT_MIN_K and s_soft.is_contiguous()
+             and bool(L.query("ghscn_mincut_bwd_split_supported", K, num_feat, ldx, num_feat, max_nodes)))
+    ws_bytes = L.query("ghscn_mincut_bwd_split_workspace_bytes" if split else "ghscn_mincut_workspace_bytes", N, B, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    L.call("ghscn_mincut_bwd_split" if split else "ghscn_mincut_bwd", _p(s_soft), _p(x), x.stride(0) if x is not None else 0, _p(ptr), _p(rowptr), _p(col),
            _p(adj_val), _p(rowptr_t), _p(col_t), _p(adj_val_t), float(temp), B, N, K, num_feat, max_nodes,
            _p(ss_raw), _p(adj_raw), _p(stats), _p(g_out), _p(g_out_adj), _p(g_losses), _p(dz), K,
            _p(dx) if want_dx else None, num_feat, _p(ws), ws_bytes, _stream())
@@ -595,7 +603,7 @@ def mincut_pool(logits: Tensor, x: Tensor, ptr: Tensor, rowptr: Tensor, col: Ten
             _p(out_adj) if want_adj else None, _p(ss_raw), _p(adj_raw), _p(stats), _p(losses), _p(ws), ws_bytes,
             _stream())
     if tc_kk:                               # S, A S and the traces; then every contraction on the tensor cores
-        L.call("ghscn_mincut_fwd_phase", *args, 1)
+        L.call("ghscn_mincut_fwd_phase", *args, MINCUT_TC_PHASE1)
         a_s = ws[:N * K * 4].view(torch.float32).view(N, K)
         gemm.gemm3x_tn_segmented(s_soft, s_soft, ptr, max_nodes, out=ss_raw)
         gemm.gemm3x_tn_segmented(s_soft, a_s, ptr, max_nodes, out=adj_raw)

@@ -429,7 +429,10 @@ GHSCN_API int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x,
  *   phase 1  S = softmax, A S (-> workspace, [N,K] fp32), the traces num / den (-> stats); no contraction;
  *   caller   ss_raw = S^T S, adj_raw = S^T (A S), out = S^T X per graph on the tensor cores;
  *   phase 2  norms, orthogonality loss, normalised coarse adjacency from ss_raw / adj_raw, then the loss means.
- * phase 0 == ghscn_mincut_fwd.  Arguments as above; out is ignored by phases 1 and 2. */
+ *   phase 3  = phase 1 with A S computed by one launch of the K2 SpMM over the whole batch (valid for collated
+ *            batches: no edge between graphs) and num left to phase 2, which takes it as Tr(adj_raw) -- literally
+ *            dense_mincut_pool's `_rank3_trace(out_adj)`.
+ * phase 0 == ghscn_mincut_fwd.  Arguments as above; out is ignored by phases 1, 2 and 3. */
 GHSCN_API int ghscn_mincut_fwd_phase(const float* logits, int64_t ldz, const float* x, int64_t ldx, const int32_t* ptr,
                                      const int32_t* rowptr, const int32_t* col, const float* adj_val, float temp,
                                      int64_t num_graphs, int64_t num_nodes, int64_t num_clusters, int64_t num_feat,
@@ -445,6 +448,24 @@ GHSCN_API int ghscn_mincut_bwd(const float* s_soft, const float* x, int64_t ldx,
                                const float* g_out_adj /*[B,K,K]|NULL*/, const float* g_losses /*[2] device*/,
                                float* d_logits, int64_t lddz, float* d_x /*nullable*/, int64_t lddx,
                                void* workspace, size_t workspace_bytes, ghscn_stream_t stream);
+
+/* The same backward in split form for the dense-bound corner (K >= 64, K % 4 == 0, num_feat % 4 == 0, 16-byte aligned
+ * rows): one pass per graph leaves [A S | A^T S | S], the stacked [Gamma^T; Gamma; Gsym] and the elementwise part of
+ * dS in the workspace; the [n,3K]x[3K,K], [n,H]x[H,K] (x g_out^T) and [n,K]x[K,H] (dX = S g_out) products run as tiled
+ * per-graph GEMMs (64 x 64 tiles over every graph at once instead of one CTA walking a graph's products serially);
+ * a last pass is the softmax backward.  Same arguments and results as ghscn_mincut_bwd. */
+GHSCN_API size_t ghscn_mincut_bwd_split_workspace_bytes(int64_t num_nodes, int64_t num_graphs, int64_t num_clusters);
+GHSCN_API int ghscn_mincut_bwd_split_supported(int64_t num_clusters, int64_t num_feat, int64_t ldx, int64_t lddx,
+                                               int32_t max_nodes_per_graph);
+GHSCN_API int ghscn_mincut_bwd_split(const float* s_soft, const float* x, int64_t ldx, const int32_t* ptr,
+                                     const int32_t* rowptr, const int32_t* col, const float* adj_val,
+                                     const int32_t* rowptr_t, const int32_t* col_t, const float* adj_val_t, float temp,
+                                     int64_t num_graphs, int64_t num_nodes, int64_t num_clusters, int64_t num_feat,
+                                     int32_t max_nodes_per_graph, const float* ss_raw, const float* adj_raw,
+                                     const float* stats, const float* g_out /*[B,K,H]|NULL*/,
+                                     const float* g_out_adj /*[B,K,K]|NULL*/, const float* g_losses /*[2] device*/,
+                                     float* d_logits, int64_t lddz, float* d_x /*nullable*/, int64_t lddx,
+                                     void* workspace, size_t workspace_bytes, ghscn_stream_t stream);
 
 /* ---- K7: cluster assignment -> virtual-node construction --------------------------------------
  * Replaces softmax(s).max(1)[1] (train/train_clustering.py:68) and the Python/numpy loops of

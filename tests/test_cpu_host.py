@@ -341,7 +341,32 @@ def test_new_entry_points_validate_arguments_without_a_gpu(built_lib):
         L.call("ghscn_gemm3x_tn_segmented", None, 64, None, 300, None, 4, 100, 64, 300, None, 300, 64 * 300, None)
     with pytest.raises(GhscnError, match="invalid"):          # phase out of range
         L.call("ghscn_mincut_fwd_phase", None, 0, None, 0, None, None, None, None, 1.0, 1, 1, 10, 1, 1,
-               None, None, None, None, None, None, None, None, 0, None, 3)
+               None, None, None, None, None, None, None, None, 0, None, 4)
+    # round 2: split MinCUT backward, fused output layer + loss, fused ReLU-backward + column sums
+    assert L.query("ghscn_mincut_bwd_split_supported", 128, 512, 512, 512, 444) == 1
+    assert L.query("ghscn_mincut_bwd_split_supported", 10, 16, 16, 16, 444) == 0       # K % 4 != 0
+    assert L.query("ghscn_mincut_bwd_split_supported", 64, 301, 301, 301, 444) == 0    # rows not 16-byte aligned
+    assert L.query("ghscn_mincut_bwd_split_workspace_bytes", 1000, 8, 64) == (4 * 1000 * 64 + 3 * 8 * 64 * 64) * 4 + 256
+    with pytest.raises(GhscnError, match="unsupported"):
+        L.call("ghscn_mincut_bwd_split", None, None, 0, None, None, None, None, None, None, None, 1.0, 4, 100, 10, 16,
+               50, None, None, None, None, None, None, None, 10, None, 16, None, 0, None)
+    with pytest.raises(GhscnError, match="workspace"):
+        L.call("ghscn_mincut_bwd_split", ctypes.c_void_p(16), None, 0, ctypes.c_void_p(16), ctypes.c_void_p(16), None,
+               None, ctypes.c_void_p(16), None, None, 1.0, 4, 100, 64, 16, 50, ctypes.c_void_p(16), ctypes.c_void_p(16),
+               ctypes.c_void_p(16), None, None, None, ctypes.c_void_p(16), 64, None, 16, None, 0, None)
+    assert L.query("ghscn_head_out_loss_supported", 130, 300, 10) == 1
+    assert L.query("ghscn_head_out_loss_supported", 1027, 300, 11) == 0
+    with pytest.raises(GhscnError, match="unsupported"):
+        L.call("ghscn_head_out_loss", None, 300, None, 300, None, None, 10, 1000, 1000, 300, 10, 0, None, None, None,
+               None, None, None, None)
+    with pytest.raises(GhscnError, match="invalid"):          # loss mode out of range
+        L.call("ghscn_head_out_loss", None, 300, None, 300, None, None, 10, 100, 100, 300, 10, 2, None, None, None,
+               None, None, None, None)
+    with pytest.raises(GhscnError, match="invalid"):          # masked output without a mask
+        L.call("ghscn_relu_grad_colsum_partial", ctypes.c_void_p(16), 8, None, 0, 4, 8, ctypes.c_void_p(16), 8,
+               ctypes.c_void_p(16), 1 << 20, None)
+    with pytest.raises(GhscnError, match="workspace"):
+        L.call("ghscn_colsum_finish", None, 0, 100, 8, ctypes.c_void_p(16), None)
     assert L.query("ghscn_grad_clip_workspace_bytes", 277_000) == 148 * 4
     with pytest.raises(GhscnError, match="workspace"):        # clip_grad_norm: workspace too small
         L.call("ghscn_grad_clip_scale", None, 0, 1.0, None, 0, ctypes.c_void_p(8), None)
