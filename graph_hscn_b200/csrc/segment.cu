@@ -115,7 +115,9 @@ __global__ void __launch_bounds__(256) segment_broadcast_kernel(const float* __r
 
 // ---- column sum (bias gradients: db = sum_rows dY) ---------------------------------------------------
 // Stage 1: CTA (rows chunk, 128-column tile) -> partial[chunk, :];  stage 2: fixed-order sum over chunks.
-constexpr int kColsumRows = 64;  // rows per CTA
+constexpr int kColsumRows = 64;  // rows per CTA of the 128-column tile kernel (and the workspace granularity)
+// rows per CTA of the row-coalesced kernel: 64 keeps a 20 k-row batch on 300+ CTAs, 256 keeps the second stage short
+__host__ __device__ inline int colsum_chunk_rows(int64_t num_rows) { return num_rows > 65536 ? 256 : 64; }
 
 template <int VEC>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int64_t ldx,
@@ -123,8 +125,9 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
                                                              float* __restrict__ partial,
                                                              const float* __restrict__ mask = nullptr,
                                                              int64_t ldm = 0, float* __restrict__ masked = nullptr,
-                                                             int64_t ldo = 0) {
+                                                             int64_t ldo = 0, int* __restrict__ chunk_count = nullptr) {
   __shared__ float part[8][32 * VEC];
+  if (chunk_count != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *chunk_count = gridDim.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = (blockIdx.x * 32 + lane) * VEC;
   const bool on = f < num_feat;
@@ -176,12 +179,15 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
 // kernel above leaves 27 % of its lanes idle at 300 columns).  Optional ReLU mask, optional write of the masked rows.
 template <bool MASK, bool WRITE>
 __global__ void __launch_bounds__(320) colsum_rows_kernel(const float* __restrict__ x, int64_t ldx, int num_rows,
-                                                          int f4, int rows_per_pass, float* __restrict__ partial,
+                                                          int chunk_rows, int f4, int rows_per_pass,
+                                                          float* __restrict__ partial,
                                                           const float* __restrict__ mask, int64_t ldm,
-                                                          float* __restrict__ masked, int64_t ldo) {
+                                                          float* __restrict__ masked, int64_t ldo,
+                                                          int* __restrict__ chunk_count) {
   extern __shared__ float4 cs_part[];            // [rows_per_pass][f4]
+  if (blockIdx.x == 0 && threadIdx.x == 0) *chunk_count = gridDim.x;
   const int rp = threadIdx.x / f4, c4 = threadIdx.x - rp * f4;
-  const int r0 = blockIdx.x * kColsumRows, r1 = min(num_rows, r0 + kColsumRows);
+  const int r0 = blockIdx.x * chunk_rows, r1 = min(num_rows, r0 + chunk_rows);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (rp < rows_per_pass) {
 #pragma unroll 4
@@ -209,8 +215,10 @@ __global__ void __launch_bounds__(320) colsum_rows_kernel(const float* __restric
 }
 
 // One CTA per 32 columns: 8 warps stride the chunk partials (4 loads in flight each), fixed-order combine.
-__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int num_chunks,
-                                                           int num_feat, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial,
+                                                           const int* __restrict__ chunk_count, int num_feat,
+                                                           float* __restrict__ out) {
+  const int num_chunks = *chunk_count;           // written by the first stage (its row-chunk size depends on the kernel)
   __shared__ float part[8][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = blockIdx.x * 32 + lane;
@@ -508,6 +516,12 @@ int ghscn_relu_dropout_bwd(const float* dy, const float* y, int64_t n, float p, 
   return GHSCN_OK;
 }
 
+// the first stage leaves its number of row chunks behind the partials (inside the 256 bytes of slack)
+static inline int* colsum_chunk_count(const void* workspace, int64_t num_rows, int64_t num_feat) {
+  const size_t off = (size_t)ceil_div<int64_t>(num_rows > 0 ? num_rows : 1, kColsumRows) * num_feat * 4;
+  return reinterpret_cast<int*>(const_cast<char*>(static_cast<const char*>(workspace)) + off);
+}
+
 size_t ghscn_colsum_workspace_bytes(int64_t num_rows, int64_t num_feat) {
   if (num_rows < 0 || num_feat < 0) return 0;
   return (size_t)ceil_div<int64_t>(num_rows > 0 ? num_rows : 1, kColsumRows) * num_feat * 4 + 256;
@@ -534,9 +548,8 @@ int ghscn_colsum_finish(const void* workspace, size_t workspace_bytes, int64_t n
   GHSCN_REQUIRE(out != nullptr);
   if (workspace_bytes < ghscn_colsum_workspace_bytes(num_rows, num_feat) || workspace == nullptr)
     return GHSCN_E_WORKSPACE;
-  const int chunks = (int)ceil_div<int64_t>(num_rows, kColsumRows);
   colsum_final_kernel<<<(unsigned)ceil_div<int64_t>(num_feat, 32), 256, 0, as_stream(stream_)>>>(
-      static_cast<const float*>(workspace), chunks, (int)num_feat, out);
+      static_cast<const float*>(workspace), colsum_chunk_count(workspace, num_rows, num_feat), (int)num_feat, out);
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;
 }
@@ -553,8 +566,12 @@ int ghscn_relu_grad_colsum_partial(const float* x, int64_t ldx, const float* mas
     return GHSCN_E_WORKSPACE;
   cudaStream_t stream = as_stream(stream_);
   float* partial = static_cast<float*>(workspace);
-  const int chunks = (int)ceil_div<int64_t>(num_rows, kColsumRows);
-  if (chunks > 0) {
+  int* count = colsum_chunk_count(workspace, num_rows, num_feat);
+  int chunks = (int)ceil_div<int64_t>(num_rows, kColsumRows);
+  if (chunks == 0) {
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return (int)e;
+  } else {
     const bool vec4 = num_feat % 4 == 0 && ldx % 4 == 0 && aligned16(x, x) &&
                       (mask == nullptr || (ldm % 4 == 0 && aligned16(mask, mask))) &&
                       (masked == nullptr || (ldo % 4 == 0 && aligned16(masked, masked)));
@@ -564,23 +581,25 @@ int ghscn_relu_grad_colsum_partial(const float* x, int64_t ldx, const float* mas
       const int rpp = f4 >= 320 ? 1 : 320 / f4;
       const int threads = (rpp * f4 + 31) / 32 * 32;
       const size_t shm = (size_t)rpp * f4 * sizeof(float4);
+      const int cr = colsum_chunk_rows(num_rows);
+      chunks = (int)ceil_div<int64_t>(num_rows, cr);
       if (mask == nullptr)
-        colsum_rows_kernel<false, false><<<chunks, threads, shm, stream>>>(x, ldx, (int)num_rows, f4, rpp, partial,
-                                                                          nullptr, 0, nullptr, 0);
+        colsum_rows_kernel<false, false><<<chunks, threads, shm, stream>>>(x, ldx, (int)num_rows, cr, f4, rpp, partial,
+                                                                          nullptr, 0, nullptr, 0, count);
       else if (masked == nullptr)
-        colsum_rows_kernel<true, false><<<chunks, threads, shm, stream>>>(x, ldx, (int)num_rows, f4, rpp, partial,
-                                                                         mask, ldm, nullptr, 0);
+        colsum_rows_kernel<true, false><<<chunks, threads, shm, stream>>>(x, ldx, (int)num_rows, cr, f4, rpp, partial,
+                                                                         mask, ldm, nullptr, 0, count);
       else
-        colsum_rows_kernel<true, true><<<chunks, threads, shm, stream>>>(x, ldx, (int)num_rows, f4, rpp, partial,
-                                                                        mask, ldm, masked, ldo);
+        colsum_rows_kernel<true, true><<<chunks, threads, shm, stream>>>(x, ldx, (int)num_rows, cr, f4, rpp, partial,
+                                                                        mask, ldm, masked, ldo, count);
     } else if (vec4) {
       dim3 grid((unsigned)ceil_div<int64_t>(num_feat, 128), (unsigned)chunks);
       colsum_partial_kernel<4><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial, mask, ldm,
-                                                         masked, ldo);
+                                                         masked, ldo, count);
     } else {
       dim3 grid((unsigned)ceil_div<int64_t>(num_feat, 32), (unsigned)chunks);
       colsum_partial_kernel<1><<<grid, 256, 0, stream>>>(x, ldx, (int)num_rows, (int)num_feat, partial, mask, ldm,
-                                                         masked, ldo);
+                                                         masked, ldo, count);
     }
     GHSCN_LAUNCH_CHECK();
   }
