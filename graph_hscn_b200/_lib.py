@@ -86,7 +86,7 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_gat_pool_bwd_src": (I32, [P, P, P, P, P, P, I64, P, I64, I64, P, I64, P, P]),
     "ghscn_gat_fold_attention": (I32, [P, I64, P, P, I64, P, I64, I64, I64, I64, P, P, P]),
     "ghscn_gat_pool_fused_supported": (I32, [I64, I64, I64]),
-    "ghscn_gat_pool_fused_fwd": (I32, [P, P, P, I64, P, I64, P, P, F32, I64, I64, I64, P, I64, P]),
+    "ghscn_gat_pool_fused_fwd": (I32, [P, P, P, I64, P, I64, P, P, F32, I64, I64, I64, P, I64, I32, P]),
     "ghscn_slot_map": (I32, [P, P, I64, I64, P, P, P]),
     "ghscn_mincut_workspace_bytes": (SZ, [I64, I64, I64]),
     "ghscn_mincut_fwd": (I32, [P, I64, P, I64, P, P, P, P, F32, I64, I64, I64, I64, I32,

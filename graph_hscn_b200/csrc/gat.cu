@@ -142,12 +142,16 @@ __global__ void __launch_bounds__(256) gat_pool_fused_kernel(const int* __restri
                                                              const float* __restrict__ u_src,
                                                              const float* __restrict__ u_dst, float slope,
                                                              int num_rows, int num_feat, float* __restrict__ pooled,
-                                                             int64_t ldp) {
+                                                             int64_t ldp, int wpr) {
   constexpr int W = VEC * ITERS;
   constexpr int kLong = 32;                              // rows with more members are pooled by the whole CTA
   extern __shared__ float part[];                        // [8 warps][2 + 32 * W]: (m, ssum, acc...) per warp
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int row0 = blockIdx.x * 8;
+  // wpr = warps per (short) row: 1, 2, 4 or 8.  The grid has only ~num_rows warps of work (1.3 k virtual nodes at the
+  // bench shape = 9 warps per SM), so rows of ~15 members are split over several warps whose partials are merged
+  // like those of the long rows: 4x the loads in flight, a quarter of the dependent batches per warp.
+  const int rpc = 8 / wpr;                               // rows per CTA
+  const int row0 = blockIdx.x * rpc;
   // attention head = blockIdx.y: its own folded vectors and its own [num_rows, num_feat] slab of `pooled`
   u_src += (int64_t)blockIdx.y * num_feat;
   if (u_dst != nullptr) u_dst += (int64_t)blockIdx.y * num_feat;
@@ -227,45 +231,57 @@ __global__ void __launch_bounds__(256) gat_pool_fused_kernel(const int* __restri
       }
     }
   };
-  // ---- short rows: one warp each, in one pass
+  auto park = [&]() {                                    // this warp's (max, sum, weighted sum) partial -> shared memory
+    float* mine = part + wid * (2 + 32 * W);
+    if (lane == 0) { mine[0] = m; mine[1] = ssum; }
+#pragma unroll
+    for (int j = 0; j < W; ++j) mine[2 + j * 32 + lane] = acc[j];
+  };
+  // the log-sum-exp merge of the partials of warps w0 .. w0 + nw - 1, in warp order (deterministic)
+  auto merge_store = [&](int row, int w0, int nw) {
+    float mm = -INFINITY;
+    for (int w = w0; w < w0 + nw; ++w) mm = fmaxf(mm, part[w * (2 + 32 * W)]);
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < W; ++j) acc[j] = 0.f;
+    for (int w = w0; w < w0 + nw; ++w) {
+      const float* pw = part + w * (2 + 32 * W);
+      const float sc = pw[1] > 0.f ? expf(pw[0] - mm) : 0.f;   // a warp without members holds (m = -inf, sum = 0)
+      tot = fmaf(pw[1], sc, tot);
+#pragma unroll
+      for (int j = 0; j < W; ++j) acc[j] = fmaf(pw[2 + j * 32 + lane], sc, acc[j]);
+    }
+    store(row, 1.0f / (tot + 1e-16f));                   // PyG softmax: + 1e-16 in the denominator
+  };
+  // ---- short rows: `wpr` warps each, in one pass
   {
-    const int row = row0 + wid;
+    const int row = row0 + wid / wpr, sub = wid % wpr;
+    bool mine_short = false;
     if (row < num_rows) {
       const int beg = rowptr[row], end = rowptr[row + 1];
       if (end - beg <= kLong) {
-        pool(row, beg, end, 1);
-        store(row, 1.0f / (ssum + 1e-16f));              // PyG softmax: + 1e-16 in the denominator
+        mine_short = true;
+        pool(row, beg + sub, end, wpr);
+        if (wpr == 1) store(row, 1.0f / (ssum + 1e-16f));
+        else park();
       }
     }
+    if (wpr > 1) {
+      __syncthreads();
+      if (mine_short && sub == 0) merge_store(row, wid, wpr);
+      __syncthreads();
+    }
   }
-  // ---- long rows (a cluster that swallowed most of its graph): the 8 warps take every 8th member each and their
-  //      (max, sum, weighted sum) partials are merged in warp order -- the log-sum-exp merge, deterministic
-  for (int r = 0; r < 8; ++r) {
+  // ---- long rows (a cluster that swallowed most of its graph): the 8 warps take every 8th member each
+  for (int r = 0; r < rpc; ++r) {
     const int row = row0 + r;
     if (row >= num_rows) break;
     const int beg = rowptr[row], end = rowptr[row + 1];
     if (end - beg <= kLong) continue;                    // CTA-uniform
     pool(row, beg + wid, end, 8);
-    float* mine = part + wid * (2 + 32 * W);
-    if (lane == 0) { mine[0] = m; mine[1] = ssum; }
-#pragma unroll
-    for (int j = 0; j < W; ++j) mine[2 + j * 32 + lane] = acc[j];
+    park();
     __syncthreads();
-    if (wid == 0) {
-      float mm = -INFINITY;
-      for (int w = 0; w < 8; ++w) mm = fmaxf(mm, part[w * (2 + 32 * W)]);
-      float tot = 0.f;
-#pragma unroll
-      for (int j = 0; j < W; ++j) acc[j] = 0.f;
-      for (int w = 0; w < 8; ++w) {
-        const float* pw = part + w * (2 + 32 * W);
-        const float sc = pw[1] > 0.f ? expf(pw[0] - mm) : 0.f;   // a warp without members holds (m = -inf, sum = 0)
-        tot = fmaf(pw[1], sc, tot);
-#pragma unroll
-        for (int j = 0; j < W; ++j) acc[j] = fmaf(pw[2 + j * 32 + lane], sc, acc[j]);
-      }
-      store(row, 1.0f / (tot + 1e-16f));
-    }
+    if (wid == 0) merge_store(row, 0, 8);
     __syncthreads();
   }
 }
@@ -385,16 +401,20 @@ int ghscn_gat_pool_fused_supported(int64_t num_feat, int64_t ldxs, int64_t ldp) 
 int ghscn_gat_pool_fused_fwd(const int32_t* rowptr, const int32_t* col, const float* x_src, int64_t ldxs,
                              const float* x_dst, int64_t ldxd, const float* u_src, const float* u_dst,
                              float negative_slope, int64_t num_rows, int64_t num_feat, int64_t heads, float* pooled,
-                             int64_t ldp, ghscn_stream_t stream_) {
+                             int64_t ldp, int32_t warps_per_row, ghscn_stream_t stream_) {
   GHSCN_REQUIRE(num_rows >= 0 && num_feat > 0 && num_rows < ((int64_t)1 << 31) && heads >= 1 && heads <= 64);
+  GHSCN_REQUIRE(warps_per_row == 0 || warps_per_row == 1 || warps_per_row == 2 || warps_per_row == 4 ||
+                warps_per_row == 8);
+  const int wpr = warps_per_row == 0 ? 1 : warps_per_row;
   if (num_rows == 0) return GHSCN_OK;
   GHSCN_REQUIRE(rowptr && x_src && u_src && pooled && ldxs >= num_feat && ldp >= num_feat);
   GHSCN_REQUIRE((x_dst == nullptr) == (u_dst == nullptr) && (x_dst == nullptr || ldxd >= num_feat));
   cudaStream_t stream = as_stream(stream_);
-  const dim3 blocks((unsigned)ceil_div<int64_t>(num_rows, 8), (unsigned)heads);
+  const dim3 blocks((unsigned)ceil_div<int64_t>(num_rows, 8 / wpr), (unsigned)heads);
 #define GHSCN_POOL_LAUNCH(VEC, ITERS)                                                                          \
   gat_pool_fused_kernel<VEC, ITERS><<<blocks, 256, 8 * (2 + 32 * (VEC) * (ITERS)) * 4, stream>>>(              \
-      rowptr, col, x_src, ldxs, x_dst, ldxd, u_src, u_dst, negative_slope, (int)num_rows, (int)num_feat, pooled, ldp)
+      rowptr, col, x_src, ldxs, x_dst, ldxd, u_src, u_dst, negative_slope, (int)num_rows, (int)num_feat, pooled, ldp, \
+      wpr)
   const bool vec4 = num_feat % 4 == 0 && ldxs % 4 == 0 && ldp % 4 == 0 && (x_dst == nullptr || ldxd % 4 == 0) &&
                     ((reinterpret_cast<uintptr_t>(x_src) | reinterpret_cast<uintptr_t>(x_dst) |
                       reinterpret_cast<uintptr_t>(pooled) | reinterpret_cast<uintptr_t>(u_src) |

@@ -805,6 +805,21 @@ def head_out_loss(loss_fn: str, hidden: Tensor, weight: Tensor, bias: Optional[T
 VIRTUAL_TCGEN05 = os.environ.get("GHSCN_VIRTUAL_TCGEN05", "0") != "0"
 
 
+# 0 = from the mean row length.  Timed alone the split wins (F = 300: 15.5 -> 12.8 us with 2 warps per row, F = 9: 13.4 ->
+# 8.1 us with 4); inside the step, where the pool shares the SMs with the local chain's GEMMs, one warp per row is as
+# fast or faster (0.641 vs 0.646-0.648 ms per step), so that is the default.
+POOL_WARPS_PER_ROW = int(os.environ.get("GHSCN_POOL_WPR", "1"))
+
+
+def pool_warps_per_row(nnz: int, num_rows: int) -> int:
+    """Warps that share one destination row of the fused attention pool (a pooling relation has only ~num_rows warps
+    of work: 9 per SM at the bench shape)."""
+    if POOL_WARPS_PER_ROW:
+        return POOL_WARPS_PER_ROW
+    mean = nnz / max(num_rows, 1)
+    return 1 if mean < 6 else (2 if mean < 12 else 4)
+
+
 class VirtualLayerFused(torch.autograd.Function):
     """out = [relu]( GCNConv_vv(x_v) + GATConv_lv((x_l, x_v)) ) computed at the INPUT width:
         P = sum_s alpha_s x_l[s]            one-pass attention pool (ghscn_gat_pool_fused_fwd)
@@ -836,7 +851,8 @@ class VirtualLayerFused(torch.autograd.Function):
         agg = both[:, :F] if tc else torch.empty((V, F), dtype=torch.float32, device=dev)
         pooled = both[:, F:] if tc else torch.empty((V, F), dtype=torch.float32, device=dev)
         L.call("ghscn_gat_pool_fused_fwd", _p(lvd.rowptr), _p(lvd.col), _p(x_src), x_src.stride(0), _p(x_dst),
-               x_dst.stride(0), _p(u[0]), _p(u[1]), float(meta["slope"]), V, F, 1, _p(pooled), ld, st)
+               x_dst.stride(0), _p(u[0]), _p(u[1]), float(meta["slope"]), V, F, 1, _p(pooled), ld,
+               pool_warps_per_row(lvd.col.numel(), V), st)
         L.call("ghscn_spmm", _p(vvd.rowptr), _p(vvd.col), _p(vv_w), _p(x_dst), x_dst.stride(0), _p(agg), ld, None, V,
                F, 0, st)
         if tc:
@@ -944,7 +960,8 @@ class GatMultiHead(torch.autograd.Function):
         pooled = torch.empty((heads, V, F), dtype=torch.float32, device=dev)
         L.call("ghscn_gat_pool_fused_fwd", _p(d.rowptr), _p(d.col), _p(x_src), x_src.stride(0),
                _p(x_dst) if has_dst else None, x_dst.stride(0) if has_dst else 0, _p(u[0]),
-               _p(u[1]) if has_dst else None, float(meta["slope"]), V, F, heads, _p(pooled), F, st)
+               _p(u[1]) if has_dst else None, float(meta["slope"]), V, F, heads, _p(pooled), F,
+               pool_warps_per_row(d.col.numel(), V), st)
         out = torch.empty((V, heads * C), dtype=torch.float32, device=dev)
         for h in range(heads):
             L.call("ghscn_small_linear_fwd", _p(pooled[h]), F, w_src_c.data_ptr() + 4 * h * C * F, F, None, 0, V, F, C,

@@ -355,11 +355,15 @@ def _uses(t, stream) -> None:
         t.record_stream(stream)
 
 
+# priority of the branch streams (-1 = high): inherited by the kernel nodes of a captured graph
+SIDE_STREAM_PRIORITY = int(os.environ.get("GHSCN_SIDE_PRIORITY", "0"))
+
+
 def _side_streams(device: torch.device, n: int):
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     pool = _SIDE_STREAMS.setdefault(key, [])
     while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=device))
+        pool.append(torch.cuda.Stream(device=device, priority=SIDE_STREAM_PRIORITY))
     return pool[:n]
 
 

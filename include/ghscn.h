@@ -292,7 +292,9 @@ GHSCN_API int ghscn_grad_clip_scale(const float* grad, int64_t n, float max_norm
  * (online softmax), replaces ghscn_row_dot x2 + ghscn_gat_scores + ghscn_spmm_pool.  x_dst / u_dst may both be NULL.
  * Supported widths: <= 32 (any alignment) or a multiple of 4 up to 512 with 16-byte aligned rows.
  * heads > 1 (GATConv(heads=h)): head i uses rows i*out_feat.. of W / att, u_src / u_dst are
- * [heads, feat] and pooled is [heads, num_rows, ldp]; all heads run in the same two launches. */
+ * [heads, feat] and pooled is [heads, num_rows, ldp]; all heads run in the same two launches.
+ * warps_per_row (0 = 1, 2, 4, 8): warps that share a destination row of <= 32 members (their partial (max, sum,
+ * weighted sum) are merged in warp order); callers pick it from the mean row length col.numel() / num_rows. */
 GHSCN_API int ghscn_gat_fold_attention(const float* w_src, int64_t ldws, const float* att_src, const float* w_dst,
                                        int64_t ldwd, const float* att_dst, int64_t out_feat, int64_t src_feat,
                                        int64_t dst_feat, int64_t heads, float* u_src, float* u_dst,
@@ -301,7 +303,7 @@ GHSCN_API int ghscn_gat_pool_fused_supported(int64_t num_feat, int64_t ldxs, int
 GHSCN_API int ghscn_gat_pool_fused_fwd(const int32_t* rowptr, const int32_t* col, const float* x_src, int64_t ldxs,
                                        const float* x_dst, int64_t ldxd, const float* u_src, const float* u_dst,
                                        float negative_slope, int64_t num_rows, int64_t num_feat, int64_t heads,
-                                       float* pooled, int64_t ldp, ghscn_stream_t stream);
+                                       float* pooled, int64_t ldp, int32_t warps_per_row, ghscn_stream_t stream);
 
 /* ---- small dense layers + task loss (readout head, virtual-node projections) --------------------------------------
  * Replaces the library GEMM + bias + activation kernels of `lin_1`, activation, `lin_2` on the [B, H] graph embeddings

@@ -70,9 +70,10 @@ for mode in ("random clusters", "one big cluster per graph"):
         xs = torch.randn(N, F, device=dev); xd = torch.randn(V, F, device=dev)
         u = torch.randn(2, F, device=dev); pooled = torch.empty(V, F, device=dev)
         wsrc = torch.randn(300, F, device=dev); att = torch.randn(300, device=dev)
-        report(f"gat_pool_fused F={F} ({mode})", graph_time(lambda i: L.call("ghscn_gat_pool_fused_fwd", _p(d.rowptr), _p(d.col), _p(xs), F, _p(xd), F, _p(u[0]), _p(u[1]), 0.2, V, F, _p(pooled), F, _stream())),
-               f"maxlen {int((d.rowptr[1:] - d.rowptr[:-1]).max())}")
-        report(f"gat_fold_attention F={F}", graph_time(lambda i: L.call("ghscn_gat_fold_attention", _p(wsrc), F, _p(att), _p(wsrc), F, _p(att), 300, F, F, _p(u[0]), _p(u[1]), _stream())))
+        for wpr in (1, 2, 4, 8):
+            report(f"gat_pool_fused F={F} warps/row={wpr} ({mode})", graph_time(lambda i: L.call("ghscn_gat_pool_fused_fwd", _p(d.rowptr), _p(d.col), _p(xs), F, _p(xd), F, _p(u[0]), _p(u[1]), 0.2, V, F, 1, _p(pooled), F, wpr, _stream())),
+                   f"maxlen {int((d.rowptr[1:] - d.rowptr[:-1]).max())}")
+        report(f"gat_fold_attention F={F}", graph_time(lambda i: L.call("ghscn_gat_fold_attention", _p(wsrc), F, _p(att), _p(wsrc), F, _p(att), 300, F, F, 1, _p(u[0]), _p(u[1]), _stream())))
 # ---- loss
 pred = torch.randn(129, 10, device=dev); yt = torch.rand(129, 10, device=dev)
 loss = torch.empty(1, device=dev); dp = torch.empty(129, 10, device=dev); sc = torch.empty(129, 10, device=dev)

@@ -241,7 +241,7 @@ def kernel_table():
 
             def k5f(i):
                 L.call("ghscn_gat_pool_fused_fwd", _p(lvd.rowptr), _p(lvd.col), _p(xs[i % nset]), H, _p(xv), H, _p(u[0]),
-                       _p(u[1]), 0.2, V, H, 1, _p(pooled), H, _stream())
+                       _p(u[1]), 0.2, V, H, 1, _p(pooled), H, ops.pool_warps_per_row(lvd.col.numel(), V), _stream())
             row("K5 fused attention pool at input width (one pass, online softmax)", graph_time(k5f),
                 4 * H * N + 4 * N + 4 * H * V * 2, "what HeteroConv's fused virtual destination launches")
         s_log = torch.randn(N, K, device=dev)

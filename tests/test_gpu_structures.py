@@ -338,6 +338,39 @@ def test_relu_grad_colsum_matches_threshold_and_sum(cuda, n, f):
         assert_close(db, want.double().sum(0).float(), 2e-6, "db")
 
 
+@pytest.mark.parametrize("feat", [9, 300])
+def test_attention_pool_warps_per_row_agree(cuda, feat):
+    """The fused attention pool (model/hscn.py:88 GATConv local -> virtual) gives the same softmax-weighted sums whether
+    a destination row is pooled by 1, 2, 4 or 8 warps (partials merged by log-sum-exp), for empty, short and long rows,
+    and matches a float64 evaluation of the same formula."""
+    from graph_hscn_b200._lib import lib
+    from graph_hscn_b200.structure import _p, _stream
+    g = torch.Generator().manual_seed(feat)
+    lens = torch.tensor([0, 1, 2, 5, 15, 16, 31, 32, 33, 70, 200] * 3)
+    V, N = lens.numel(), int(lens.sum())
+    rowptr = torch.zeros(V + 1, dtype=torch.int32)
+    rowptr[1:] = lens.cumsum(0)
+    col = torch.randperm(N, generator=g).int()
+    xs, xd = torch.randn(N, feat, generator=g), torch.randn(V, feat, generator=g)
+    u = torch.randn(2, feat, generator=g) / feat ** 0.5
+    want = torch.zeros(V, feat, dtype=torch.float64)
+    for r in range(V):
+        m = col[rowptr[r]:rowptr[r + 1]].long()
+        if m.numel():
+            z = torch.nn.functional.leaky_relu(xs[m].double() @ u[0].double() + xd[r].double() @ u[1].double(), 0.2)
+            a = torch.softmax(z, 0)
+            want[r] = (a[:, None] * xs[m].double()).sum(0)
+    dev = [t.to(cuda) for t in (rowptr, col, xs, xd, u)]
+    outs = []
+    for wpr in (1, 2, 4, 8):
+        pooled = torch.full((V, feat), float("nan"), device=cuda)
+        lib().call("ghscn_gat_pool_fused_fwd", _p(dev[0]), _p(dev[1]), _p(dev[2]), feat, _p(dev[3]), feat, _p(dev[4][0]),
+                   _p(dev[4][1]), 0.2, V, feat, 1, _p(pooled), feat, wpr, _stream())
+        assert_close(pooled, want.float(), 2e-6, f"pool, {wpr} warps per row")
+        outs.append(pooled)
+    assert not outs[0][lens == 0].any()                             # empty rows pool to zero
+
+
 def test_relu_dropout_fused(cuda):
     """model/mpnn.py:57-58 `F.dropout(self.activation(x), p)` as one kernel: keep rate, scaling, zeros where relu is
     zero, a fresh mask per call (also across CUDA-graph replays), backward from the output alone."""
