@@ -165,6 +165,7 @@ class HSCN(nn.Module):
         self.lin_2 = o.Linear(hidden_channels, num_classes)
         # "local" receives only the l->l GCN, so its `.relu()` can run in that layer's aggregation epilogue
         self._fused_local = self._fused_virtual = False
+        self.first_layer_output: Optional[Tensor] = None
         if getattr(o, "fused_relu", False):
             lls = [c.convs["local__to__local"] for c in self.convs]
             if all(hasattr(c, "fuse_relu") for c in lls):
@@ -208,6 +209,10 @@ class HSCN(nn.Module):
                         x_dict[k] = v.relu()
                 else:
                     x_dict[k] = v.relu()
+            if conv is self.convs[0]:
+                # the activation every later parameter's gradient is complete behind (train.py overlaps the
+                # data-parallel exchange of those gradients with the first layer's backward)
+                self.first_layer_output = x_dict.get("local") if torch.is_grad_enabled() else None
         pooled = self.ops.global_mean_pool(x_dict["local"], batch["local"].batch)
         hidden = None
         if hasattr(self.ops, "linear_act"):          # bias + activation in the projection's epilogue (same values)

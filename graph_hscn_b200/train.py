@@ -109,7 +109,12 @@ class FlatGradients:
         grads = torch.autograd.grad(loss, self.params)
         if accumulate:
             torch._foreach_add_([p.grad for p in self.params], list(grads))
-        elif self.flat.is_cuda and all(g.dtype == torch.float32 for g in grads):
+        else:
+            self._place(self.params, grads, self.flat)
+
+    def _place(self, params: Sequence[Tensor], grads: Sequence[Tensor], flat: Tensor) -> None:
+        """Copies the finished gradients of `params` (consecutive in the flat layout) into `flat`, their slice of it."""
+        if flat.is_cuda and all(g.dtype == torch.float32 for g in grads):
             # the parameters' gradient views tile the flat buffer in order: one gather launch (pointers travel as
             # kernel arguments) instead of a multi-tensor copy that runs ~10 thread blocks for 1.1 MB
             import ctypes
@@ -119,9 +124,33 @@ class FlatGradients:
             n = len(gs)
             ptrs = (ctypes.c_void_p * n)(*[g.data_ptr() for g in gs])
             sizes = (ctypes.c_int64 * n)(*[g.numel() for g in gs])
-            lib().call("ghscn_gather_flat", ptrs, sizes, n, _p(self.flat), _stream())
+            lib().call("ghscn_gather_flat", ptrs, sizes, n, _p(flat), _stream())
         else:
-            torch._foreach_copy_([p.grad for p in self.params], list(grads))
+            torch._foreach_copy_([p.grad for p in params], list(grads))
+
+    def leading(self, prefix: str) -> int:
+        """Number of leading parameters whose name starts with `prefix` (0 if they are not a prefix of the layout)."""
+        k = 0
+        while k < len(self.names) and self.names[k].startswith(prefix):
+            k += 1
+        return 0 if any(n.startswith(prefix) for n in self.names[k:]) else k
+
+    def backward_reduce_overlapped(self, loss: Tensor, boundary: Tensor, split: int, group=None) -> None:
+        """`backward_into` + `all_reduce_mean` with the exchange overlapped with the end of the backward pass: the
+        gradients of the parameters behind `boundary` (an activation; everything but the first `split` parameters)
+        are complete once the backward has reached it, so their all-reduce (99 % of the bytes for the HSCN: every
+        h x h layer and the head) runs while the first layer's backward is still computing; only the first layer's
+        few kilobytes are exchanged after it.  Same sums as the single all-reduce (the AVG of a slice is the slice
+        of the AVG).  NCCL only (the caller falls back to the two separate calls otherwise)."""
+        late, early = self.params[split:], self.params[:split]
+        n_early = sum(p.numel() for p in early)
+        grads = torch.autograd.grad(loss, late + [boundary])
+        self._place(late, grads[:-1], self.flat[n_early:])
+        work = dist.all_reduce(self.flat[n_early:], op=dist.ReduceOp.AVG, group=group, async_op=True)
+        g_early = torch.autograd.grad(boundary, early, grad_outputs=grads[-1])
+        self._place(early, g_early, self.flat[:n_early])
+        dist.all_reduce(self.flat[:n_early], op=dist.ReduceOp.AVG, group=group)
+        work.wait()
 
     def flatten_parameters(self) -> Tensor:
         """Re-home the live parameters as views of ONE flat fp32 leaf whose .grad is the flat gradient buffer:
@@ -152,6 +181,9 @@ class FlatGradients:
         if local_graphs is not None and global_graphs:
             self.flat.mul_(float(local_graphs) / float(global_graphs))
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            return
+        if self.flat.is_cuda and dist.get_backend(group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)      # the division happens inside NCCL's kernel
             return
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         self.flat.mul_(1.0 / world)
@@ -466,6 +498,8 @@ class StagingCollate:
 # the step
 # ---------------------------------------------------------------------------------------------
 TWO_STREAMS = os.environ.get("GHSCN_TWO_STREAMS", "1") != "0"
+# data parallel: exchange the gradients of everything behind the first layer while that layer's backward still runs
+OVERLAP_ALLREDUCE = os.environ.get("GHSCN_OVERLAP_ALLREDUCE", "1") != "0"
 
 
 @dataclass
@@ -765,8 +799,23 @@ class GraphHSCNStep:
         acc = max(int(self.cfg.batch_accumulation), 1)
         return (self._micro > 0, self._micro + 1 >= acc, bool(self.staged.raw))
 
-    def _hscn_update(self, world: int) -> None:
-        self.hscn_grads.all_reduce_mean(world)
+    def _hscn_backward(self, loss: Tensor, world: int, accumulate: bool, update: bool) -> bool:
+        """Backward of the HSCN stage into the flat gradient buffer; -> True if the data-parallel exchange is already
+        done (overlapped with the first layer's backward, NCCL only)."""
+        b = getattr(self.hscn, "first_layer_output", None)
+        self.hscn.first_layer_output = None
+        if (update and not accumulate and world > 1 and OVERLAP_ALLREDUCE and b is not None and b.requires_grad
+                and b.is_cuda and dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"):
+            split = self.hscn_grads.leading("convs.0.")
+            if 0 < split < len(self.hscn_grads.params):
+                self.hscn_grads.backward_reduce_overlapped(loss, b, split)
+                return True
+        self.hscn_grads.backward_into(loss, accumulate=accumulate)
+        return False
+
+    def _hscn_update(self, world: int, reduced: bool = False) -> None:
+        if not reduced:
+            self.hscn_grads.all_reduce_mean(world)
         if self.cfg.clip_grad_norm:
             if isinstance(self.hscn_opt, FlatAdamW):
                 self.hscn_opt.clip_grad_norm(1.0)
@@ -786,10 +835,10 @@ class GraphHSCNStep:
         self.scn_opt.step()
         hb = self._assign(x_f, ei, ew)
         loss = self._hscn_loss(hb)
-        self.hscn_grads.backward_into(loss, accumulate=accumulate)
+        reduced = self._hscn_backward(loss, world, accumulate, update)
         self.losses[2:3].copy_(loss.detach().view(1))
         if update:
-            self._hscn_update(world)
+            self._hscn_update(world, reduced)
         if self._prep_stream is not None:
             torch.cuda.current_stream().wait_stream(self._prep_stream)
 
@@ -828,10 +877,10 @@ class GraphHSCNStep:
             loss = self._hscn_loss(hb)
         finally:
             self.hscn.defer_branch_join = False
-        self.hscn_grads.backward_into(loss, accumulate=accumulate)
+        reduced = self._hscn_backward(loss, world, accumulate, update)
         self.losses[2:3].copy_(loss.detach().view(1))
         if update:
-            self._hscn_update(world)
+            self._hscn_update(world, reduced)
         main.wait_stream(side)
         for st in pnn.take_forked_streams(self.device):          # every stream the HeteroConv layers forked
             if st is not side:

@@ -294,3 +294,42 @@ def test_staging_collate_in_a_dataloader(cuda):
         assert torch.isfinite(losses).all()
         seen += 1
     assert seen == 3 and step.num_graphs_captured >= 1
+
+
+def test_overlapped_gradient_exchange_equals_plain_backward(cuda):
+    """Data parallel: the all-reduce of everything behind the first HSCN layer is issued while that layer's
+    backward still runs (two autograd passes split at the layer's output).  On a one-rank NCCL group the flat gradient
+    buffer must equal the one of the plain backward bit for bit."""
+    import torch.distributed as dist
+    from graph_hscn_b200 import synthetic
+    from graph_hscn_b200.structure import structure_cache, structure_hints
+    from graph_hscn_b200.train import GraphHSCNStep
+    if dist.is_initialized():
+        pytest.skip("a process group is already active")
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29547", rank=0, world_size=1)
+    try:
+        step = GraphHSCNStep(_cfg(), synthetic.peptides_batch(12, seed=5), cuda, padded=True)
+        g = step.hscn_grads
+        split = g.leading("convs.0.")
+        assert 0 < split < len(g.params) and g.leading("lin_") == 0
+        flats = []
+        for overlapped in (False, True):
+            with structure_hints(**step.hints):
+                structure_cache().clear()
+                step._register_blocks()
+                x_f = step._cast(step.dev["x"])
+                ei, ew, *_ = step._forward_scn(x_f)
+                hb = step._assign(x_f, ei, ew)
+                loss = step._hscn_loss(hb)
+                boundary = step.hscn.first_layer_output
+                assert boundary is not None and boundary.requires_grad
+                g.flat.fill_(float("nan"))
+                if overlapped:
+                    g.backward_reduce_overlapped(loss, boundary, split)
+                else:
+                    g.backward_into(loss)
+            torch.cuda.synchronize()
+            flats.append(g.flat.clone())
+        assert torch.isfinite(flats[0]).all() and torch.equal(flats[0], flats[1])
+    finally:
+        dist.destroy_process_group()
