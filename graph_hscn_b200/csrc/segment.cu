@@ -116,8 +116,11 @@ __global__ void __launch_bounds__(256) segment_broadcast_kernel(const float* __r
 // ---- column sum (bias gradients: db = sum_rows dY) ---------------------------------------------------
 // Stage 1: CTA (rows chunk, 128-column tile) -> partial[chunk, :];  stage 2: fixed-order sum over chunks.
 constexpr int kColsumRows = 64;  // rows per CTA of the 128-column tile kernel (and the workspace granularity)
-// rows per CTA of the row-coalesced kernel: 64 keeps a 20 k-row batch on 300+ CTAs, 256 keeps the second stage short
-__host__ __device__ inline int colsum_chunk_rows(int64_t num_rows) { return num_rows > 65536 ? 256 : 64; }
+// rows per CTA of the row-coalesced kernel: one wave of CTAs for a 20 k-row batch (128 rows), and a second stage that
+// stays short (it walks one partial row per chunk)
+__host__ __device__ inline int colsum_chunk_rows(int64_t num_rows) {
+  return num_rows > 65536 ? 256 : (num_rows > 16384 ? 128 : 64);
+}
 
 template <int VEC>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int64_t ldx,
