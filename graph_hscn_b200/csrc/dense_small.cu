@@ -643,8 +643,29 @@ __global__ void __launch_bounds__(1024) head_out_loss_kernel(const float* __rest
   float* s_dw = s_dp + (size_t)per * C;       // [C*H + C + 1]: this CTA's dW2 | db2 | loss partial
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
   const int CH = C * H;
-  for (int i = tid; i < CH; i += blockDim.x) s_w[i] = w2[(int64_t)(i / H) * ldw + i % H];
-  for (int i = tid; i < nloc * H; i += blockDim.x) s_h[i] = h[(int64_t)(g0 + i / H) * ldh + i % H];
+  // staging: every thread issues all of its loads before the first store (one memory round trip, not one per element)
+  if (H % 4 == 0 && ldw % 4 == 0 && ldh % 4 == 0 && (((uintptr_t)w2 | (uintptr_t)h) & 15) == 0) {
+    const int H4 = H / 4, nw = C * H4, nh = nloc * H4;
+    float4 v[6];
+    for (int i0 = 0; i0 < nw + nh; i0 += 6 * blockDim.x) {
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = i0 + u * blockDim.x + tid;
+        if (i < nw) v[u] = *reinterpret_cast<const float4*>(w2 + (int64_t)(i / H4) * ldw + (i % H4) * 4);
+        else if (i < nw + nh)
+          v[u] = *reinterpret_cast<const float4*>(h + (int64_t)(g0 + (i - nw) / H4) * ldh + ((i - nw) % H4) * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = i0 + u * blockDim.x + tid;
+        if (i < nw) *reinterpret_cast<float4*>(s_w + (size_t)i * 4) = v[u];
+        else if (i < nw + nh) *reinterpret_cast<float4*>(s_h + (size_t)(i - nw) * 4) = v[u];
+      }
+    }
+  } else {
+    for (int i = tid; i < CH; i += blockDim.x) s_w[i] = w2[(int64_t)(i / H) * ldw + i % H];
+    for (int i = tid; i < nloc * H; i += blockDim.x) s_h[i] = h[(int64_t)(g0 + i / H) * ldh + i % H];
+  }
   __syncthreads();
   // 1. pred: one warp per row
   for (int g = wid; g < nloc; g += nwarps) {

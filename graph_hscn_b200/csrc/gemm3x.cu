@@ -541,12 +541,18 @@ gemm3x_kernel(const float* __restrict__ a, int64_t lda, int m_rows, int k_dim, c
 // Grid = (M tiles of 128 x N halves, row slabs).  Every CTA reduces its slab into the three accumulators and writes an
 // fp32 partial; gemm3x_tn_reduce_kernel adds the slab partials in slab order (deterministic).
 //   warp 0            MMA issuer, convergent (owns TMEM)
-//   warps 1..8        producers: P slice [16 rows x 128] and Q slice [16 rows x <=160] per stage, 128-bit loads along
-//                     M/N land on 16-byte halves of the swizzle units (no transposition); per-thread item geometry is
-//                     hoisted out of the loop; register ring 4 stages ahead.  Afterwards the same warps drain TMEM.
+//   warps 1..16       producers: P slice [16 rows x 128] and Q slice [16 rows x <=160] per stage, 128-bit loads along
+//                     M/N land on 16-byte halves of the swizzle units (no transposition).  A chunk is shared by TWO
+//                     warps (8 rows of P and half of Q each): the pipeline trace showed the MMA warp waiting for
+//                     its producers two thirds of the time -- a warp needs ~10 k cycles per chunk, almost all of it
+//                     the latency of its 18 KB of loads -- so eight chunks in flight of 9 KB per warp were replaced
+//                     by eight chunks in flight of 2 x 4.5 KB: twice the loads in the air per SM.  Afterwards the
+//                     same warps drain TMEM.
 // =====================================================================================================================
 constexpr int kTnRows = 16;                        // reduction rows per pipeline stage (two K = 8 MMAs)
-constexpr int kTnProducers = 256;                  // warps 1..8
+constexpr int kTnSplit = 2;                        // producer warps that share one chunk (each stages half of its items)
+constexpr int kTnChunkWarps = 8;                   // chunks in flight = producer warps / kTnSplit
+constexpr int kTnProducers = 32 * kTnChunkWarps * kTnSplit;   // warps 1..16
 constexpr int kTnThreads = 32 + kTnProducers;
 constexpr int kTnABlocks = 4, kTnBBlocks = kHalfMax / 32;                 // 32-wide M/N blocks per operand
 constexpr int kTnAPart = (kTnRows / 4) * kTnABlocks * 512;                 // 8 KB  (hi or lo)
@@ -621,7 +627,7 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
 
   if (tid == 0) {
     for (int s = 0; s < kTnStages; ++s) {
-      bar_init(smem_addr(&full_bar[s]), 1);            // the one producer warp that owns the stage's chunk
+      bar_init(smem_addr(&full_bar[s]), kTnSplit);     // the producer warps that share the stage's chunk
       bar_init(smem_addr(&empty_bar[s]), 1);
     }
     bar_init(smem_addr(&accum_bar), 1);
@@ -670,66 +676,70 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
     // outstanding global loads, and here there are none left, while the other seven warps have their chunks'
     // loads in flight.  (A register-prefetch ring inside the fencing thread is drained by every fence: that
     // version ran at one memory latency per chunk.)
-    const int pw = warp - 1;                         // 0..7
+    const int pw = (warp - 1) / kTnSplit;            // chunk slot 0..7
+    const int part = (warp - 1) % kTnSplit;          // which half of the chunk's items
     constexpr int kQ4 = kHalfMax / 4;                // float4 slots per Q row (padded to 160 columns)
-    constexpr int kAItems = kTnRows;                 // P: one row per item, lane = float4 column     (16)
-    constexpr int kBItems = kTnRows * kQ4 / 32;      // Q: item = lane + 32 i -> (row, float4 column) (20)
+    constexpr int kAItems = kTnRows / kTnSplit;      // P: one row per item, lane = float4 column     (8 per warp)
+    constexpr int kBItems = kTnRows * kQ4 / 32 / kTnSplit;   // Q: item = lane + 32 i -> (row, float4 column) (10)
+    const int a0 = part * kAItems, b0 = part * kBItems;
     const bool a_col_ok = m0 + lane * 4 < m_out;
-    for (int c = pw; c < nchunks; c += kTnProducers / 32) {
+    for (int c = pw; c < nchunks; c += kTnChunkWarps) {
       const int r_base = row_begin + c * kTnRows;
       const float* pb = pmat + (int64_t)r_base * ldp + m0 + lane * 4;
       const float* qb = qmat + (int64_t)r_base * ldq + hcol;
       float4 va[kAItems], vb[kBItems];
 #pragma unroll
       for (int i = 0; i < kAItems; ++i)
-        va[i] = (a_col_ok && r_base + i < row_end) ? ldg_f4(pb + (int64_t)i * ldp) : make_float4(0.f, 0.f, 0.f, 0.f);
+        va[i] = (a_col_ok && r_base + a0 + i < row_end) ? ldg_f4(pb + (int64_t)(a0 + i) * ldp)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < kBItems; ++i) {
-        const int item = lane + 32 * i, rr = item / kQ4, f4 = item - rr * kQ4;
+        const int item = lane + 32 * (b0 + i), rr = item / kQ4, f4 = item - rr * kQ4;
         vb[i] = (f4 * 4 < hvalid && r_base + rr < row_end) ? ldg_f4(qb + (int64_t)rr * ldq + f4 * 4)
                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const int s = c % kTnStages;
-      if (pw == 0) GHSCN_TR(200 + 5 * (c / 8));
-      while (turn != c) { }                          // empty barriers are tested in chunk order (parity waits must
+      if (warp == 1) GHSCN_TR(200 + 5 * (c / 8));
+      while (turn != c * kTnSplit + part) { }        // empty barriers are tested in chunk order (parity waits must
       bar_wait(smem_addr(&empty_bar[s]), ((uint32_t)(c / kTnStages) & 1u) ^ 1u);   // be at most one phase behind)
       __syncwarp();
-      if (lane == 0) turn = c + 1;
-      if (pw == 0) GHSCN_TR(200 + 5 * (c / 8) + 1);
+      if (lane == 0) turn = c * kTnSplit + part + 1;
+      if (warp == 1) GHSCN_TR(200 + 5 * (c / 8) + 1);
       unsigned char* st = smem_gen + (size_t)s * kTnStageBytes;
 #pragma unroll
       for (int i = 0; i < kAItems; ++i) {
-        const uint32_t off = mn_offset(i, lane, kTnABlocks);
+        const uint32_t off = mn_offset(a0 + i, lane, kTnABlocks);
         split_store(st + off, st + kTnAPart + off, va[i]);
       }
 #pragma unroll
       for (int i = 0; i < kBItems; ++i) {
-        const int item = lane + 32 * i, rr = item / kQ4, f4 = item - rr * kQ4;
+        const int item = lane + 32 * (b0 + i), rr = item / kQ4, f4 = item - rr * kQ4;
         if (f4 * 4 < hpad) {
           const uint32_t off = 2 * kTnAPart + mn_offset(rr, f4, kTnBBlocks);
           split_store(st + off, st + kTnBPart + off, vb[i]);
         }
       }
-      if (pw == 0) GHSCN_TR(200 + 5 * (c / 8) + 2);
+      if (warp == 1) GHSCN_TR(200 + 5 * (c / 8) + 2);
       fence_proxy_async();
-      if (pw == 0) GHSCN_TR(200 + 5 * (c / 8) + 3);
+      if (warp == 1) GHSCN_TR(200 + 5 * (c / 8) + 3);
       __syncwarp();
       if (lane == 0) bar_arrive(smem_addr(&full_bar[s]));
-      if (pw == 0) GHSCN_TR(200 + 5 * (c / 8) + 4);
+      if (warp == 1) GHSCN_TR(200 + 5 * (c / 8) + 4);
     }
 
-    // ----- epilogue: two warps per TMEM lane quadrant, each takes every other 16-column group -----
+    // ----- epilogue: kEpi warps per TMEM lane quadrant, each takes every kEpi-th 16-column group -----
+    constexpr int kEpi = kTnProducers / 32 / 4;      // 4
     bar_wait(smem_addr(&accum_bar), 0);
-    if (pw == 0) GHSCN_TR(500);
+    if (warp == 1) GHSCN_TR(500);
     tc_fence_after();
     const int quad = warp & 3;
-    const int half = (warp - 1) >> 2;                // warps 1..4 -> 0, warps 5..8 -> 1
+    const int half = (warp - 1) >> 2;                // warps 1..4 -> 0, warps 5..8 -> 1, ...
     const int row = quad * 32 + lane;
     const int sstride = hvalid + ((hvalid & 4) ? 0 : 4);       // floats; odd multiple of 4 words: conflict-free float4
     float* srow = reinterpret_cast<float*>(smem_gen) + (size_t)row * sstride;
     const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int groups = (hvalid + 15) / 16;
-    for (int gi = half; gi < groups; gi += 2) {
+    for (int gi = half; gi < groups; gi += kEpi) {
       const int c0 = gi * 16;
       float v[16];
       if (nchunks > 0) {
@@ -746,10 +756,10 @@ gemm3x_tn_kernel(const float* __restrict__ pmat, int64_t ldp, const float* __res
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kTnProducers) : "memory");      // both column sets of every row are staged
-    // coalesced stores: each warp writes 16 rows of its quadrant, hvalid contiguous floats per row
+    // coalesced stores: each warp writes 32 / kEpi rows of its quadrant, hvalid contiguous floats per row
     const int nf4 = hvalid / 4;
-    for (int r = 0; r < 16; ++r) {
-      const int trow = quad * 32 + half * 16 + r;
+    for (int r = 0; r < 32 / kEpi; ++r) {
+      const int trow = quad * 32 + half * (32 / kEpi) + r;
       if (m0 + trow < m_out) {
         float* dst = kSegmented ? partial + (int64_t)slab * out_slab_stride + (int64_t)(m0 + trow) * ldo + hcol
                                 : partial + ((int64_t)slab * m_out + (m0 + trow)) * n_out + hcol;
