@@ -7,6 +7,8 @@
 // S^T X, S^T A S, S^T S, both traces and both losses without any other round trip through HBM.
 // HBM-bound at the reference's sizes (K <= 32): algorithmic bytes per graph
 //   4nK (logits) + 4nH (X, only if `out` is requested) + 4(n+1) + 4 nnz  ->  4nK (S) + 4KH + 8K^2 + 32.
+#include <algorithm>
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include <cstdlib>
@@ -25,12 +27,70 @@ static inline int mincut_threads(int64_t num_graphs) {
   if (forced) return forced;
   return num_graphs >= 4 * kNumSMs ? 256 : (num_graphs >= 2 * kNumSMs ? 512 : 1024);
 }
+// GHSCN_MINCUT_STAGE=1 stages the graph's logits tile (one TMA bulk copy) and CSR slice in shared memory before the
+// fused forward's phases.  Off by default: measured 18.3 vs 17.0 us (B = 128, K = 10), 90.6 vs 89.5 us (B = 1024,
+// K = 16) -- the kernel is bound by its instruction count and barrier phases, not by the global round trips.
+static inline bool mincut_stage_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("GHSCN_MINCUT_STAGE");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+// GHSCN_MINCUT_STREAM_X=0 keeps S^T X / x g_out^T / S g_out inside the per-graph kernels (A/B measurements)
+static inline bool mincut_stream_x_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("GHSCN_MINCUT_STREAM_X");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 constexpr int kMaxClusters = 128;
 constexpr int kStatsStride = 8;  // per graph: num, den, ||SS||_F, ||R||_F (= ortho_g), mc_g, -, -, -
 constexpr size_t kSmemBudget = 200 * 1024;
 
 __device__ __forceinline__ float adj_value(const float* __restrict__ adj_val, int s) {
   return adj_val ? adj_val[s] : 1.0f;
+}
+
+// ---- mbarrier / TMA bulk-copy helpers for the tile staging of the forward kernel --------------------------------------
+__device__ __forceinline__ uint32_t mc_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mc_bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mc_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mc_bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+// (A S) from a CSR slice staged in shared memory: rp = the graph's n + 1 row pointers, cs / vs = its slots (global slot
+// e0 + s), same slot order and roundings as csr_times_s.
+__device__ __forceinline__ void csr_times_s_staged(const int* __restrict__ rp, const int* __restrict__ cs,
+                                                   const float* __restrict__ vs, int e0, const float* __restrict__ S,
+                                                   int base, int n, int K, float* __restrict__ buf) {
+  for (int e = threadIdx.x; e < n * K; e += blockDim.x) {
+    const int i = e / K, k = e - i * K;
+    float acc = 0.f;
+    const int beg = rp[i] - e0, end = rp[i + 1] - e0;
+    for (int s = beg; s < end; ++s) {
+      const int c = cs[s] - base;
+      if (c >= 0 && c < n) acc += (vs ? vs[s] : 1.0f) * S[c * K + k];
+    }
+    buf[e] = acc;
+  }
 }
 
 // rows of `buf` (n x K) <- (A S) using the CSR slice whose rows are the graph's nodes.
@@ -233,13 +293,15 @@ __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
     const int* __restrict__ ptr, const int* __restrict__ rowptr, const int* __restrict__ col,
     const float* __restrict__ adj_val, float temp, int K, int H, int n_cap, float* __restrict__ s_soft,
     float* __restrict__ out, float* __restrict__ out_adj, float* __restrict__ ss_raw,
-    float* __restrict__ adj_raw, float* __restrict__ stats, float* __restrict__ as_ws, int phase) {
+    float* __restrict__ adj_raw, float* __restrict__ stats, float* __restrict__ as_ws, int phase, int e_cap) {
   // phase 0: everything.  phase 1: S, A S, the two traces (num, den -> stats) and nothing else: the K x K and K x H
   // contractions are then done by ghscn_gemm3x_tn_segmented on the tensor cores (dense-bound for K >= 64), and
   // phase 2 finishes from ss_raw / adj_raw: norms, orthogonality loss, normalised coarse adjacency.
   extern __shared__ float smem[];
   __shared__ float red[32];
   __shared__ float dk[kMaxClusters];
+  __shared__ __align__(8) unsigned long long tile_bar;
+  __shared__ float kpart[1024];
   const int g = blockIdx.x;
   const int base = ptr[g];
   const int n = ptr[g + 1] - base;
@@ -259,42 +321,102 @@ __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
   float* AS = SMEM ? smem + (size_t)n_cap * K : as_ws + (int64_t)base * K;
   float* deg = SMEM ? smem + 2 * (size_t)n_cap * K : smem;
 
+  // Staging (fused path with room for it, e_cap > 0): the graph's logits tile -> the S tile (ONE TMA bulk copy when
+  // the rows are contiguous and 16-byte aligned, else coalesced loads with every load of the CTA in flight at once),
+  // its n + 1 row pointers and -- one dependent round trip later -- its column / value slots.  Every later phase
+  // then runs out of shared memory: the round-1 kernel walked rowptr -> values, logits, rowptr -> col -> S as
+  // separate dependent global round trips per thread.  Graphs with more than e_cap slots keep the global CSR reads.
+  int* rp = nullptr;
+  int* cs = nullptr;
+  float* vs = nullptr;
+  float* kk = nullptr;                               // [2][K*K] S^T S and S^T A S (K <= 32)
+  bool tile_staged = false, csr_staged = false;
+  int e0 = 0;
+  if (SMEM && phase == 0 && e_cap > 0) {
+    rp = reinterpret_cast<int*>(deg + n_cap);
+    cs = rp + ((n_cap + 4) & ~3);
+    vs = reinterpret_cast<float*>(cs + e_cap);
+    if (K <= 32) kk = vs + e_cap;
+    const float* zt = logits + (int64_t)base * ldz;
+    const uint32_t bytes = (uint32_t)n * K * 4u;
+    const bool bulk = ldz == K && n > 0 && ((reinterpret_cast<uintptr_t>(zt) | bytes) & 15u) == 0;   // CTA-uniform
+    const uint32_t bar = mc_smem_addr(&tile_bar);
+    if (bulk) {
+      if (tid == 0) mc_bar_init(bar, 1);
+      __syncthreads();
+      if (tid == 0) mc_bulk_load(mc_smem_addr(S), zt, bytes, bar);
+    } else {
+      for (int e = tid; e < n * K; e += blockDim.x) S[e] = zt[(int64_t)(e / K) * ldz + e % K];
+    }
+    for (int i = tid; i <= n; i += blockDim.x) rp[i] = rowptr[base + i];
+    if (bulk) mc_bar_wait(bar, 0);
+    __syncthreads();
+    tile_staged = true;
+    e0 = rp[0];
+    const int ne = rp[n] - e0;
+    csr_staged = ne >= 0 && ne <= e_cap;             // CTA-uniform
+    if (csr_staged) {
+      for (int s2 = tid; s2 < ne; s2 += blockDim.x) {
+        cs[s2] = col[e0 + s2];
+        if (adj_val) vs[s2] = adj_val[e0 + s2];
+      }
+      if (!adj_val) vs = nullptr;
+    }
+    __syncthreads();
+  }
+
+  // lane-group geometry for K <= 32: G = 4 / 8 / 16 / 32 lanes per node row, 32 / G rows per warp pass
+  const int gsh = K <= 4 ? 2 : (K <= 8 ? 3 : (K <= 16 ? 4 : 5));
+  const int G = 1 << gsh, sub = lane >> gsh, kl = lane & (G - 1), rpw = 32 >> gsh;
   float num = 0.f, den = 0.f;
   if (phase != 2) {
   // A. S = softmax(logits / temp).  Small K: one thread per node row (all rows of the graph in flight at once);
   //    large K: one warp per row.  Row degrees (row sums of A) by one thread per row.
   for (int i = tid; i < n; i += blockDim.x) {
-    const int beg = rowptr[base + i], end = rowptr[base + i + 1];
-    float d = (float)(end - beg);
-    if (adj_val) {
-      d = 0.f;
-      for (int s = beg; s < end; ++s) d += adj_val[s];
+    float d;
+    if (csr_staged) {
+      const int beg = rp[i] - e0, end = rp[i + 1] - e0;
+      d = (float)(end - beg);
+      if (vs) {
+        d = 0.f;
+        for (int s = beg; s < end; ++s) d += vs[s];
+      }
+    } else {
+      const int beg = rowptr[base + i], end = rowptr[base + i + 1];
+      d = (float)(end - beg);
+      if (adj_val) {
+        d = 0.f;
+        for (int s = beg; s < end; ++s) d += adj_val[s];
+      }
     }
     deg[i] = d;
   }
   if (K <= 32) {
-    for (int i = tid; i < n; i += blockDim.x) {
-      const float* zr = logits + (int64_t)(base + i) * ldz;
-      float z[32];
-      float m = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if (k < K) { z[k] = temp != 1.0f ? __fdiv_rn(zr[k], temp) : zr[k]; m = fmaxf(m, z[k]); }
-      float sum = 0.f;
-#pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if (k < K) { z[k] = expf(z[k] - m); sum += z[k]; }
-#pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if (k < K) {
-          const float p = __fdiv_rn(z[k], sum);
-          S[i * K + k] = p;
-          if (SMEM) Sg[i * K + k] = p;
-        }
+    // G lanes per node row: max / sum by shuffles inside the lane group, every warp busy.  (The round-1 form -- one
+    // thread per row with the row in registers -- ran ~800 dependent instructions on 5 of the CTA's 32 warps while
+    // the others waited at the barrier; ncu counted 57 k warp instructions per graph for 1.5 k matrix elements.)
+    for (int i0 = wid * rpw; i0 < n; i0 += nwarps * rpw) {
+      const int i = i0 + sub;
+      const bool on = i < n && kl < K;
+      float z = -INFINITY;
+      if (on) {
+        z = tile_staged ? S[i * K + kl] : logits[(int64_t)(base + i) * ldz + kl];
+        if (temp != 1.0f) z = __fdiv_rn(z, temp);
+      }
+      float m = z;
+      for (int o = G >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+      float pz = on ? expf(z - m) : 0.f;
+      float sum = pz;
+      for (int o = G >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(kFullMask, sum, o);
+      if (on) {
+        pz = __fdiv_rn(pz, sum);
+        S[i * K + kl] = pz;
+        if (SMEM) Sg[i * K + kl] = pz;
+      }
     }
   } else {
     for (int i = wid; i < n; i += nwarps) {
-      const float* zr = logits + (int64_t)(base + i) * ldz;
+      const float* zr = tile_staged ? S + i * K : logits + (int64_t)(base + i) * ldz;
       float m = -INFINITY;
       for (int k = lane; k < K; k += 32) {
         const float z = temp != 1.0f ? __fdiv_rn(zr[k], temp) : zr[k];
@@ -318,19 +440,42 @@ __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
   }
   __syncthreads();
 
-  // B. AS = A S (phase 3: the caller runs the K2 SpMM over the whole batch instead)
-  if (phase != 3) {
-    csr_times_s(rowptr, col, adj_val, S, base, n, K, AS);
-    __syncthreads();
-  }
-
-  // C. traces, S^T S, S^T A S, S^T X
+  // B. AS = A S (phase 3: the caller runs the K2 SpMM over the whole batch instead) and C. the two traces
   float pnum = 0.f, pden = 0.f;
+  if (K <= 32 && phase != 3) {
+    // lane group per row again: the row's slots are walked once by its K lanes (no e / K divisions), and the trace
+    // terms are taken while S and A S of the element are in registers
+    for (int i0 = wid * rpw; i0 < n; i0 += nwarps * rpw) {
+      const int i = i0 + sub;
+      if (i < n && kl < K) {
+        int beg, end;
+        const int* cp;
+        const float* vp;
+        if (csr_staged) { beg = rp[i] - e0; end = rp[i + 1] - e0; cp = cs; vp = vs; }
+        else { beg = rowptr[base + i]; end = rowptr[base + i + 1]; cp = col; vp = adj_val; }
+        float acc = 0.f;
+        for (int s2 = beg; s2 < end; ++s2) {
+          const int c = cp[s2] - base;
+          if (c >= 0 && c < n) acc += (vp ? vp[s2] : 1.0f) * S[c * K + kl];
+        }
+        AS[i * K + kl] = acc;
+        const float sv = S[i * K + kl];
+        pnum += sv * acc;
+        pden += deg[i] * sv * sv;
+      }
+    }
+  } else {
+    if (phase != 3) {
+      if (csr_staged) csr_times_s_staged(rp, cs, vs, e0, S, base, n, K, AS);
+      else csr_times_s(rowptr, col, adj_val, S, base, n, K, AS);
+      __syncthreads();
+    }
 #pragma unroll 4
-  for (int e = tid; e < n * K; e += blockDim.x) {
-    const float sv = S[e];
-    if (phase != 3) pnum += sv * AS[e];
-    pden += deg[e / K] * sv * sv;
+    for (int e = tid; e < n * K; e += blockDim.x) {
+      const float sv = S[e];
+      if (phase != 3) pnum += sv * AS[e];
+      pden += deg[e / K] * sv * sv;
+    }
   }
   num = block_sum(pnum, red);
   den = block_sum(pden, red);
@@ -351,14 +496,42 @@ __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
     den = stats[(int64_t)g * kStatsStride + 1];
   }
 
-  float* ssg = ss_raw + (int64_t)g * K * K;
-  float* oag = adj_raw + (int64_t)g * K * K;
+  float* ssg_g = ss_raw + (int64_t)g * K * K;
+  float* oag_g = adj_raw + (int64_t)g * K * K;
+  // the K x K blocks stay in shared memory for the norms below when there is room (no write -> barrier -> re-read
+  // through L2); the global copies are for the backward
+  float* ssg = kk ? kk : ssg_g;
+  float* oag = kk ? kk + K * K : oag_g;
   if (phase == 0) {
-    atb_tiled<4, 4>(S, K, K, S, K, K, n, ssg, K);    // S^T S
-    atb_tiled<4, 4>(S, K, K, AS, K, K, n, oag, K);   // S^T (A S)
+    const int items = 2 * K * K;
+    if (items <= (int)blockDim.x) {
+      // small K: one thread per (output element, node slice) of [S^T S | S^T A S], slices combined in order
+      const int parts = blockDim.x / items;
+      if (tid < parts * items) {
+        const int part = tid / items, item = tid - part * items;
+        const bool second = item >= K * K;
+        const int pe = item - (second ? K * K : 0), k = pe / K, l = pe - k * K;
+        const float* Bm = second ? AS : S;
+        float a = 0.f;
+        for (int i = part; i < n; i += parts) a = fmaf(S[i * K + k], Bm[i * K + l], a);
+        kpart[tid] = a;
+      }
+      __syncthreads();
+      if (tid < items) {
+        float t = 0.f;
+        for (int q = 0; q < parts; ++q) t += kpart[q * items + tid];
+        if (tid < K * K) ssg[tid] = t;
+        else oag[tid - K * K] = t;
+      }
+    } else {
+      atb_tiled<4, 4>(S, K, K, S, K, K, n, ssg, K);    // S^T S
+      atb_tiled<4, 4>(S, K, K, AS, K, K, n, oag, K);   // S^T (A S)
+    }
     if (out != nullptr)                               // S^T X, X streamed from global memory
       atb_tiled<8, 4>(S, K, K, x + (int64_t)base * ldx, ldx, H, n, out + (int64_t)g * K * H, H);
     __syncthreads();  // ssg / oag visible to the whole CTA
+    if (kk)
+      for (int p2 = tid; p2 < K * K; p2 += blockDim.x) { ssg_g[p2] = ssg[p2]; oag_g[p2] = oag[p2]; }
   }
 
   // D. losses and the normalised coarse adjacency
@@ -562,7 +735,8 @@ __global__ void __launch_bounds__(1024) mincut_bwd_kernel(
     float temp, int B, int N, int K, int H, int n_cap, const float* __restrict__ ss_raw,
     const float* __restrict__ adj_raw, const float* __restrict__ stats, const float* __restrict__ g_out,
     const float* __restrict__ g_out_adj, const float* __restrict__ g_losses, float* __restrict__ d_logits,
-    int64_t lddz, float* __restrict__ d_x, int64_t lddx, float* __restrict__ ws) {
+    int64_t lddz, float* __restrict__ d_x, int64_t lddx, float* __restrict__ ws, const float* __restrict__ xg) {
+  // xg != nullptr: x g_out^T ([N, K]) and d_x = S g_out were already produced by mincut_pool_x_bwd_kernel
   extern __shared__ float smem[];
   __shared__ MincutBwdScratch sc;
   __shared__ MincutTile tiles[4];
@@ -630,7 +804,12 @@ __global__ void __launch_bounds__(1024) mincut_bwd_kernel(
   ab_tiled<4, 4>(Sr, K, n, Gsym, K, K, K, 1.f, dS, K, true);             // S (G' + G'^T) go
   if (gog) {
     __syncthreads();
-    abt_tiled<4, 4>(x + (int64_t)base * ldx, ldx, n, gog, H, K, H, 1.f, dS, K, true);   // x g_out^T
+    if (xg) {
+      const float* xgg = xg + (int64_t)base * K;
+      for (int e = tid; e < n * K; e += blockDim.x) dS[e] += xgg[e];
+    } else {
+      abt_tiled<4, 4>(x + (int64_t)base * ldx, ldx, n, gog, H, K, H, 1.f, dS, K, true);   // x g_out^T
+    }
   }
   __syncthreads();
   // softmax backward, one warp per node row
@@ -644,7 +823,7 @@ __global__ void __launch_bounds__(1024) mincut_bwd_kernel(
       d_logits[(int64_t)(base + i) * lddz + k] = dz;
     }
   }
-  if (d_x != nullptr) {
+  if (d_x != nullptr && !(xg && gog)) {
     float* dxg = d_x + (int64_t)base * lddx;
     if (gog) {
       // dX = S g_out: [n,K] x [K,H]; thread tile 4 rows x 4 columns, columns contiguous
@@ -880,8 +1059,418 @@ static void launch_seg_gemm(const float* A, int64_t lda, const int* ptr, const f
   }
 }
 
+// ---- pooled features for K <= 32: streaming kernels over the whole batch --------------------------------------------
+// S^T X, x g_out^T and S g_out read / write the graph's [n, H] feature rows exactly once and are bandwidth work: one
+// CTA per graph walking them alone is held to one SM's share of HBM (round 1 / early round 2: 46 us of the 65 us
+// pooled forward at the bench shape for 23 MB).  These kernels spread the rows of every graph over the whole device.
+
+// S rows are short (K floats, 4- / 8- / 16-byte aligned depending on K): widest aligned load that K allows
+template <int KT>
+__device__ __forceinline__ void load_s_row(const float* __restrict__ sr, int K, float (&sv)[KT]) {
+  if ((K & 3) == 0) {
+#pragma unroll
+    for (int k = 0; k < KT; k += 4)
+      if (k < K) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(sr + k));
+        sv[k] = v.x; sv[k + 1] = v.y; sv[k + 2] = v.z; sv[k + 3] = v.w;
+      }
+  } else if ((K & 1) == 0) {
+#pragma unroll
+    for (int k = 0; k < KT; k += 2)
+      if (k < K) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(sr + k));
+        sv[k] = v.x; sv[k + 1] = v.y;
+      }
+  } else {
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (k < K) sv[k] = __ldg(sr + k);
+  }
+}
+
+// out[g, k, c] = sum_i S[i, k] X[i, c].  One CTA per graph over the full feature width.  The graph's feature rows
+// are contiguous ([n, H], ldx == H), so they stream through a ring of kPoolStages shared-memory stages filled by ONE
+// TMA bulk copy per chunk of rows (12 - 16 KB): every byte of the next stages is in flight while the current chunk is
+// consumed, at no register cost.  (Measured alternatives: register-staged rows, 4 in flight per thread: 0.6 - 0.8 TB/s;
+// column-tiled CTAs with one 400-byte bulk copy per row: 0.7 TB/s -- the copy engine is bound by the number of bulk
+// requests, not by their bytes.)  The graph's S tile sits in shared memory too (one coalesced load, overlapped with
+// the ring's prologue).  Thread = (float4 column group, row slice) with a K x 4 accumulator tile; a chunk is 4 rows
+// per slice.  Slices are combined by a fixed-order tree through shared memory (deterministic).
+// KT = K rounded up to a multiple of 4.
+constexpr int kPoolMaxStages = 8;
+static inline int pool_stages() {                  // GHSCN_POOL_STAGES=2..8: ring depth (A/B measurements)
+  static const int v = [] {
+    const char* e = getenv("GHSCN_POOL_STAGES");
+    const int q = e ? atoi(e) : 0;
+    return (q >= 2 && q <= kPoolMaxStages) ? q : 4;
+  }();
+  return v;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256, (KT <= 16 ? 2 : 1))
+    mincut_pool_x_kernel(const float* __restrict__ s_soft, const float* __restrict__ x, const int* __restrict__ ptr,
+                         int K, int H, int s_cap, int s_off, int segs, int kPoolStages,
+                         float* __restrict__ out) {
+  // s_off: float4 offset of the S tile = max(ring, reduction tiles).  segs > 1: the graph's rows are cut into `segs`
+  // equal ranges, one per CTA of a thread-block cluster (gridDim.x = cluster size = segs); the partial tiles are
+  // combined over distributed shared memory in rank order.
+  extern __shared__ __align__(128) float4 pool_smem[];
+  __shared__ __align__(8) unsigned long long full[kPoolMaxStages];
+  constexpr int KQ = KT / 4;
+  const int g = blockIdx.y, rank = blockIdx.x;
+  int base = ptr[g], n = ptr[g + 1] - base;
+  if (segs > 1) {
+    const int per = ceil_div(max(n, 0), segs), lo = min(n, rank * per);
+    n = max(0, min(n, lo + per) - lo);
+    base += lo;
+  }
+  const bool bad = n > s_cap;                                      // stale max-nodes hint: poison the output tile
+  if (bad) n = 0;
+  const int H4 = H >> 2;                                           // <= blockDim.x
+  const int slices = blockDim.x / H4, rows = 4 * slices;           // rows per chunk
+  const int grp = threadIdx.x % H4, slice = threadIdx.x / H4;
+  const bool on = slice < slices;
+  float4* ring = pool_smem;                                        // [kPoolStages][rows][H4]
+  float4* s_tile = pool_smem + s_off;                              // [s_cap][KT / 4], columns K .. KT - 1 are zero
+  const int nchunks = ceil_div(n, rows);
+  const float* xt = x + (int64_t)base * H;
+
+  auto issue = [&](int c) {                                        // thread 0 fills stage c % kPoolStages with chunk c
+    const int st = c % kPoolStages, r0 = c * rows, rc = min(rows, n - r0);
+    mc_bulk_load(mc_smem_addr(ring + (size_t)st * rows * H4), xt + (int64_t)r0 * H, (uint32_t)rc * H * 4u,
+                 mc_smem_addr(&full[st]));
+  };
+
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < kPoolStages; ++st) mc_bar_init(mc_smem_addr(&full[st]), 1);
+    for (int c = 0; c < min(nchunks, kPoolStages); ++c) issue(c);
+  }
+  {
+    const float* sp = s_soft + (int64_t)base * K;
+    float* st = reinterpret_cast<float*>(s_tile);
+    const int total = n * KT;                                      // four loads in flight per thread and round
+    for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * blockDim.x, i = e / KT, k = e - i * KT;
+        v[u] = (e < total && k < K) ? __ldg(sp + i * K + k) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < total) st[e] = v[u];
+      }
+    }
+  }
+  __syncthreads();
+
+  float4 acc[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c % kPoolStages, r0 = c * rows, rc = min(rows, n - r0);
+    mc_bar_wait(mc_smem_addr(&full[st]), (uint32_t)(c / kPoolStages) & 1u);
+    if (on) {
+      const float4* src = ring + (size_t)st * rows * H4 + grp;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = slice + u * slices;
+        if (r < rc) {
+          const float4 q = src[(size_t)r * H4];
+          const float4* srow = s_tile + (size_t)(r0 + r) * KQ;
+#pragma unroll
+          for (int j = 0; j < KQ; ++j) {
+            const float4 s4 = srow[j];
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float4& a = acc[4 * j + t];
+              a.x = fmaf(sv[t], q.x, a.x); a.y = fmaf(sv[t], q.y, a.y);
+              a.z = fmaf(sv[t], q.z, a.z); a.w = fmaf(sv[t], q.w, a.w);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();                                               // the stage is free again
+    if (threadIdx.x == 0 && c + kPoolStages < nchunks) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(c + kPoolStages);
+    }
+  }
+  float4* part = ring;                                             // [ceil(slices / 2)][KT][H4], the ring is drained
+  for (int cnt = slices; cnt > 1;) {               // slices [half, cnt) hand their tiles to slices [0, cnt - half)
+    const int half = (cnt + 1) >> 1;
+    if (on && slice >= half && slice < cnt) {
+#pragma unroll
+      for (int k = 0; k < KT; ++k) part[((slice - half) * KT + k) * H4 + grp] = acc[k];
+    }
+    __syncthreads();
+    if (on && slice + half < cnt) {
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        const float4 v = part[(slice * KT + k) * H4 + grp];
+        acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+      }
+    }
+    __syncthreads();
+    cnt = half;
+  }
+  if (bad) {
+#pragma unroll
+    for (int k = 0; k < KT; ++k) acc[k] = make_float4(NAN, NAN, NAN, NAN);
+  }
+  if (segs == 1) {
+    if (on && slice == 0) {
+      float* og = out + (int64_t)g * K * H + grp * 4;
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k < K) *reinterpret_cast<float4*>(og + (int64_t)k * H) = acc[k];
+    }
+  } else {
+    namespace cgr = cooperative_groups;
+    cgr::cluster_group cluster = cgr::this_cluster();
+    float4* cpart = ring;                                          // [K][H4]; the tree above is done with `part`
+    if (on && slice == 0) {
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k < K) cpart[k * H4 + grp] = acc[k];
+    }
+    cluster.sync();
+    float4* og = reinterpret_cast<float4*>(out + (int64_t)g * K * H);
+    for (int e = rank * blockDim.x + threadIdx.x; e < K * H4; e += segs * blockDim.x) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < segs; ++q) {
+        const float4 v = cluster.map_shared_rank(cpart, q)[e];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      og[e] = a;
+    }
+    cluster.sync();                                                // nobody leaves while a peer still reads its tile
+  }
+}
+
+// Backward of the pooled features in one pass over the rows: xg[i, :] = x[i, :] g_out[g]^T (the term of dS) and, when
+// WANT_DX, d_x[i, :] = S[i, :] g_out[g].  CTA = (chunk of `rows_per_cta` rows, graph): g_out[g] ([K, H], <= 64 KB) and
+// the chunk's feature rows land in shared memory by TMA bulk copies issued up front (one each when the rows are
+// contiguous, else one per row), so everything the CTA reads is in flight at once; a warp then owns two rows at a
+// time: its lanes walk the float4 column groups, d_x is written once (coalesced 128-bit stores), the K partial dot
+// products are combined by shuffles.
+template <int KT, bool WANT_DX>
+__global__ void __launch_bounds__(256) mincut_pool_x_bwd_kernel(const float* __restrict__ s_soft,
+                                                                const float* __restrict__ x, int64_t ldx,
+                                                                const int* __restrict__ ptr,
+                                                                const float* __restrict__ g_out, int K, int H,
+                                                                int rows_per_cta, float* __restrict__ xg,
+                                                                float* __restrict__ d_x, int64_t lddx) {
+  extern __shared__ __align__(128) float4 pool_smem[];
+  __shared__ __align__(8) unsigned long long bar_mem;
+  const int g = blockIdx.y;
+  const int base = ptr[g], n = ptr[g + 1] - base;
+  const int row0 = blockIdx.x * rows_per_cta;
+  if (row0 >= n) return;
+  const int rc = min(n - row0, rows_per_cta);
+  const int H4 = H >> 2;
+  float4* gs = pool_smem;                          // [KT][H4], rows K .. KT - 1 zero
+  float4* xs = pool_smem + (size_t)KT * H4;        // [rows_per_cta][H4]
+  const uint32_t bar = mc_smem_addr(&bar_mem);
+  const float* xc = x + (int64_t)(base + row0) * ldx;
+  if (threadIdx.x == 0) mc_bar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const uint32_t gbytes = (uint32_t)K * H * 4u, rbytes = (uint32_t)H * 4u;
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                   "r"(gbytes + rbytes * (uint32_t)rc)
+                   : "memory");
+    __syncwarp();
+    if (lane == 0)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       mc_smem_addr(gs)),
+                   "l"(g_out + (int64_t)g * K * H), "r"(gbytes), "r"(bar)
+                   : "memory");
+    if (ldx == H) {
+      if (lane == 1)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         mc_smem_addr(xs)),
+                     "l"(xc), "r"(rbytes * (uint32_t)rc), "r"(bar)
+                     : "memory");
+    } else {
+      for (int r = lane; r < rc; r += 32)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         mc_smem_addr(xs + (size_t)r * H4)),
+                     "l"(xc + (int64_t)r * ldx), "r"(rbytes), "r"(bar)
+                     : "memory");
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int e = K * H4 + threadIdx.x; e < KT * H4; e += blockDim.x) gs[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the S rows of this warp's first pair travel while the bulk copies land
+  float sn0[KT], sn1[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) { sn0[k] = 0.f; sn1[k] = 0.f; }
+  if (WANT_DX && 2 * wid < rc) {
+    load_s_row<KT>(s_soft + (int64_t)(base + row0 + 2 * wid) * K, K, sn0);
+    load_s_row<KT>(s_soft + (int64_t)(base + row0 + min(2 * wid + 1, rc - 1)) * K, K, sn1);
+  }
+  __syncthreads();
+  mc_bar_wait(bar, 0);
+  for (int r0 = 2 * wid; r0 < rc; r0 += 2 * nwarps) {
+    const bool two = r0 + 1 < rc;
+    const int r1 = two ? r0 + 1 : r0;
+    const int64_t i0 = base + row0 + r0, i1 = base + row0 + r1;
+    float sv0[KT], sv1[KT], t0[KT], t1[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { t0[k] = 0.f; t1[k] = 0.f; sv0[k] = sn0[k]; sv1[k] = sn1[k]; }
+    if (WANT_DX && r0 + 2 * nwarps < rc) {           // next pair's S rows during this pair's arithmetic
+      load_s_row<KT>(s_soft + (int64_t)(base + row0 + r0 + 2 * nwarps) * K, K, sn0);
+      load_s_row<KT>(s_soft + (int64_t)(base + row0 + min(r0 + 2 * nwarps + 1, rc - 1)) * K, K, sn1);
+    }
+    const float4* x0 = xs + (size_t)r0 * H4;
+    const float4* x1 = xs + (size_t)r1 * H4;
+    for (int c = lane; c < H4; c += 32) {
+      const float4 q0 = x0[c], q1 = x1[c];
+      float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        const float4 gv = gs[k * H4 + c];
+        t0[k] = fmaf(q0.x, gv.x, fmaf(q0.y, gv.y, fmaf(q0.z, gv.z, fmaf(q0.w, gv.w, t0[k]))));
+        t1[k] = fmaf(q1.x, gv.x, fmaf(q1.y, gv.y, fmaf(q1.z, gv.z, fmaf(q1.w, gv.w, t1[k]))));
+        if (WANT_DX) {
+          d0.x = fmaf(sv0[k], gv.x, d0.x); d0.y = fmaf(sv0[k], gv.y, d0.y);
+          d0.z = fmaf(sv0[k], gv.z, d0.z); d0.w = fmaf(sv0[k], gv.w, d0.w);
+          d1.x = fmaf(sv1[k], gv.x, d1.x); d1.y = fmaf(sv1[k], gv.y, d1.y);
+          d1.z = fmaf(sv1[k], gv.z, d1.z); d1.w = fmaf(sv1[k], gv.w, d1.w);
+        }
+      }
+      if (WANT_DX) {
+        reinterpret_cast<float4*>(d_x + i0 * lddx)[c] = d0;
+        if (two) reinterpret_cast<float4*>(d_x + i1 * lddx)[c] = d1;
+      }
+    }
+    float w0 = 0.f, w1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (k < K) {
+        const float a = warp_sum(t0[k]), b = warp_sum(t1[k]);
+        if (lane == k) { w0 = a; w1 = b; }
+      }
+    if (lane < K) {
+      xg[i0 * K + lane] = w0;
+      if (two) xg[i1 * K + lane] = w1;
+    }
+  }
+}
+
+static inline bool pool_x_supported(int K, int H, const float* x, int64_t ldx, const float* other, int n_cap) {
+  return K <= 32 && H >= 4 && H % 4 == 0 && H <= 2048 && ldx % 4 == 0 && n_cap > 0 &&
+         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(other)) & 15) == 0;
+}
+constexpr int kPoolBwdRows = 32;
+static inline size_t pool_x_bwd_smem(int K, int H) { return ((size_t)((K + 3) & ~3) + kPoolBwdRows) * H * 4; }
+
+// forward: feature rows back to back (ldx == H), one pass over the width (H <= 1024), ring + padded S tile in smem
+constexpr size_t kPoolSmemLimit = 160 * 1024;
+static inline int pool_x_segs(int B, int n_cap) {
+  // few graphs: a cluster of 2 / 4 / 8 CTAs per graph (>= 2 CTAs per SM in total, >= 32 rows per CTA at the hint) --
+  // B CTAs of 8 warps with the largest graph (3x the mean) as the critical path would leave most of the device idle
+  static const int forced = [] {                   // GHSCN_POOL_SEGS=1|2|4|8: A/B measurements
+    const char* e = getenv("GHSCN_POOL_SEGS");
+    const int v = e ? atoi(e) : 0;
+    return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0;
+  }();
+  if (forced) return forced;
+  int segs = 1;
+  while (segs < 8 && (int64_t)B * segs < 2 * kNumSMs && n_cap / (2 * segs) >= 32) segs *= 2;
+  return segs;
+}
+static inline size_t pool_x_ring_bytes(int KT, int H) {
+  const int H4 = H / 4, slices = 256 / H4, rows = 4 * slices;
+  return std::max((size_t)pool_stages() * rows * H4, (size_t)((slices + 1) / 2) * KT * H4) * sizeof(float4);
+}
+static inline bool pool_x_fwd_supported(int K, int H, int64_t ldx, int B, int n_cap) {
+  if (ldx != H || H > 1024) return false;
+  const int KT = (K + 3) & ~3, s_cap = ceil_div(n_cap, pool_x_segs(B, n_cap));
+  return pool_x_ring_bytes(KT, H) + (size_t)s_cap * KT * 4 <= kPoolSmemLimit;
+}
+
+template <int KT>
+static void launch_pool_x(const float* s_soft, const float* x, const int* ptr, int K, int H, int B, int n_cap,
+                          float* out, cudaStream_t stream) {
+  const size_t ring = pool_x_ring_bytes(KT, H);
+  const int segs = pool_x_segs(B, n_cap), s_cap = ceil_div(n_cap, segs);
+  const size_t shm = ring + (size_t)s_cap * KT * 4;   // the reduction tree and the cluster tiles reuse the ring
+  cudaFuncSetAttribute(mincut_pool_x_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmemLimit);
+  for (int g0 = 0; g0 < B; g0 += 65535) {
+    const int gb = std::min(65535, B - g0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)segs, (unsigned)gb);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = shm;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)segs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, mincut_pool_x_kernel<KT>, s_soft, x, ptr + g0, K, H, s_cap, (int)(ring / sizeof(float4)),
+                       segs, pool_stages(), out + (int64_t)g0 * K * H);
+  }
+}
+
+template <int KT>
+static void launch_pool_x_bwd(const float* s_soft, const float* x, int64_t ldx, const int* ptr, const float* g_out,
+                              int K, int H, int B, int n_cap, float* xg, float* d_x, int64_t lddx,
+                              cudaStream_t stream) {
+  const size_t shm = pool_x_bwd_smem(K, H);
+  cudaFuncSetAttribute(mincut_pool_x_bwd_kernel<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)kSmemBudget);
+  cudaFuncSetAttribute(mincut_pool_x_bwd_kernel<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)kSmemBudget);
+  for (int g0 = 0; g0 < B; g0 += 65535) {
+    const int gb = min(65535, B - g0);
+    const dim3 grid((unsigned)ceil_div(n_cap, kPoolBwdRows), (unsigned)gb);
+    if (d_x)
+      mincut_pool_x_bwd_kernel<KT, true><<<grid, 256, shm, stream>>>(s_soft, x, ldx, ptr + g0,
+                                                                      g_out + (int64_t)g0 * K * H, K, H, kPoolBwdRows,
+                                                                      xg, d_x, lddx);
+    else
+      mincut_pool_x_bwd_kernel<KT, false><<<grid, 256, shm, stream>>>(s_soft, x, ldx, ptr + g0,
+                                                                       g_out + (int64_t)g0 * K * H, K, H, kPoolBwdRows,
+                                                                       xg, nullptr, 0);
+  }
+}
+
+#define GHSCN_POOL_X_DISPATCH(K, CALL)                                           \
+  switch (((K) + 3) / 4) {                                                       \
+    case 1: CALL(4); break;                                                      \
+    case 2: CALL(8); break;                                                      \
+    case 3: CALL(12); break;                                                     \
+    case 4: CALL(16); break;                                                     \
+    case 5: CALL(20); break;                                                     \
+    case 6: CALL(24); break;                                                     \
+    case 7: CALL(28); break;                                                     \
+    default: CALL(32); break;                                                    \
+  }
+
 static inline size_t fwd_smem_bytes(int n_cap, int K, bool smem) {
   return smem ? (2 * (size_t)n_cap * K + n_cap) * 4 : (size_t)n_cap * 4;
+}
+// slots of a graph's CSR slice staged in shared memory by the fused forward (0 = no staging): 8 per node when the CTA
+// then still fits three times on an SM, else 4 per node, else none; graphs with more slots read the global CSR
+static inline int fwd_stage_slots(int n_cap, int K, size_t* total_bytes) {
+  const size_t base = fwd_smem_bytes(n_cap, K, true);
+  const size_t fixed = (size_t)((n_cap + 4) & ~3) * 4 + (K <= 32 ? 2 * (size_t)K * K * 4 : 0);
+  int e_cap = 0;
+  if (base + fixed + (size_t)8 * n_cap * 8 <= 72 * 1024) e_cap = 8 * n_cap;
+  else if (base + fixed + (size_t)4 * n_cap * 8 <= kSmemBudget) e_cap = 4 * n_cap;
+  *total_bytes = e_cap ? base + fixed + (size_t)e_cap * 8 : base;
+  return e_cap;
 }
 static inline size_t bwd_smem_bytes(int n_cap, int K, bool smem) {
   return (2 * (size_t)K * K + n_cap + (smem ? 4 * (size_t)n_cap * K : 0)) * 4;
@@ -896,7 +1485,7 @@ extern "C" {
 size_t ghscn_mincut_workspace_bytes(int64_t num_nodes, int64_t num_graphs, int64_t num_clusters) {
   (void)num_graphs;
   if (num_nodes < 0 || num_clusters < 0) return 0;
-  return (size_t)3 * num_nodes * num_clusters * 4 + 256;
+  return (size_t)4 * num_nodes * num_clusters * 4 + 256;   // [A S | A^T S | dS] (no-smem variant) + x g_out^T
 }
 
 static int mincut_fwd_impl(const float* logits, int64_t ldz, const float* x, int64_t ldx, const int32_t* ptr,
@@ -917,25 +1506,33 @@ static int mincut_fwd_impl(const float* logits, int64_t ldz, const float* x, int
   const int threads = mincut_threads(num_graphs);
   // the split phases exchange S and A S through HBM (s_soft, workspace): they use the workspace variant
   const bool smem = phase == 0 && fwd_smem_bytes(n_cap, K, true) <= kSmemBudget;
+  size_t staged_bytes = 0;
+  const int e_cap = (smem && mincut_stage_enabled()) ? fwd_stage_slots(n_cap, K, &staged_bytes) : 0;
   if (phase == 3) {                                // S, degrees, den; A S = one SpMM over the whole batch
     GHSCN_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)num_nodes * num_clusters * 4);
   }
-  const size_t shm = fwd_smem_bytes(n_cap, K, smem);
+  const size_t shm = e_cap ? staged_bytes : fwd_smem_bytes(n_cap, K, smem);
   if (shm > kSmemBudget) return GHSCN_E_UNSUPPORTED;
   float* as_ws = nullptr;
   if (!smem) {
     if (workspace == nullptr || workspace_bytes < (size_t)num_nodes * K * 4) return GHSCN_E_WORKSPACE;
     as_ws = static_cast<float*>(workspace);
   }
+  // pooled features S^T X (K <= 32): streamed by a batch-wide kernel behind the fused one, not by the graph's CTA
+  const bool stream_out = out != nullptr && phase == 0 && mincut_stream_x_enabled() &&
+                          pool_x_supported(K, H, x, ldx, out, n_cap) &&
+                          pool_x_fwd_supported(K, H, ldx, (int)num_graphs, n_cap);
+  float* out_all = out;
+  if (stream_out) out = nullptr;
   if (smem) {
     cudaFuncSetAttribute(mincut_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
     mincut_fwd_kernel<true><<<(unsigned)num_graphs, threads, shm, stream>>>(
         logits, ldz, x, ldx, ptr, rowptr, col, adj_val, temp, K, H, n_cap, s_soft, out, out_adj, ss_raw, adj_raw,
-        stats, as_ws, phase);
+        stats, as_ws, phase, e_cap);
   } else {
     mincut_fwd_kernel<false><<<(unsigned)num_graphs, threads, shm, stream>>>(
         logits, ldz, x, ldx, ptr, rowptr, col, adj_val, temp, K, H, n_cap, s_soft, out, out_adj, ss_raw, adj_raw,
-        stats, as_ws, phase);
+        stats, as_ws, phase, e_cap);
   }
   if (phase == 3)
     return ghscn_spmm(rowptr, col, adj_val, s_soft, K, as_ws, K, nullptr, num_nodes, K, 0, stream_);
@@ -944,6 +1541,13 @@ static int mincut_fwd_impl(const float* logits, int64_t ldz, const float* x, int
     return GHSCN_OK;
   }
   mincut_reduce_losses_kernel<<<1, 256, 0, stream>>>(stats, (int)num_graphs, losses);
+  if (stream_out) {
+#define GHSCN_CALL(KT) launch_pool_x<KT>(s_soft, x, ptr, K, H, (int)num_graphs, n_cap, out_all, stream)
+    GHSCN_POOL_X_DISPATCH(K, GHSCN_CALL);
+#undef GHSCN_CALL
+    GHSCN_LAUNCH_CHECK_N(3);
+    return GHSCN_OK;
+  }
   GHSCN_LAUNCH_CHECK_N(2);
   return GHSCN_OK;
 }
@@ -991,16 +1595,30 @@ int ghscn_mincut_bwd(const float* s_soft, const float* x, int64_t ldx, const int
     if (workspace == nullptr || workspace_bytes < (size_t)3 * num_nodes * K * 4) return GHSCN_E_WORKSPACE;
     ws = static_cast<float*>(workspace);
   }
+  // gradients through the pooled features (K <= 32): one streaming pass over x / d_x for the whole batch; the
+  // per-graph kernel then only adds the [n, K] block it left in the workspace
+  float* xg = nullptr;
+  if (g_out != nullptr && mincut_stream_x_enabled() && workspace != nullptr &&
+      workspace_bytes >= (size_t)4 * num_nodes * K * 4 && pool_x_supported(K, H, x, ldx, g_out, n_cap) &&
+      (d_x == nullptr || (lddx % 4 == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0)) &&
+      pool_x_bwd_smem(K, H) <= kSmemBudget) {
+    xg = static_cast<float*>(workspace) + (size_t)3 * num_nodes * K;
+#define GHSCN_CALL(KT) \
+  launch_pool_x_bwd<KT>(s_soft, x, ldx, ptr, g_out, K, H, (int)num_graphs, n_cap, xg, d_x, lddx, stream)
+    GHSCN_POOL_X_DISPATCH(K, GHSCN_CALL);
+#undef GHSCN_CALL
+    ghscn::note_launches(1);
+  }
   if (smem) {
     cudaFuncSetAttribute(mincut_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
     mincut_bwd_kernel<true><<<(unsigned)num_graphs, threads, shm, stream>>>(
         s_soft, x, ldx, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, temp, (int)num_graphs, (int)num_nodes, K,
-        H, n_cap, ss_raw, adj_raw, stats, g_out, g_out_adj, g_losses, d_logits, lddz, d_x, lddx, ws);
+        H, n_cap, ss_raw, adj_raw, stats, g_out, g_out_adj, g_losses, d_logits, lddz, d_x, lddx, ws, xg);
   } else {
     cudaFuncSetAttribute(mincut_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
     mincut_bwd_kernel<false><<<(unsigned)num_graphs, threads, shm, stream>>>(
         s_soft, x, ldx, ptr, rowptr, col, adj_val, rowptr_t, col_t, adj_val_t, temp, (int)num_graphs, (int)num_nodes, K,
-        H, n_cap, ss_raw, adj_raw, stats, g_out, g_out_adj, g_losses, d_logits, lddz, d_x, lddx, ws);
+        H, n_cap, ss_raw, adj_raw, stats, g_out, g_out_adj, g_losses, d_logits, lddz, d_x, lddx, ws, xg);
   }
   GHSCN_LAUNCH_CHECK();
   return GHSCN_OK;

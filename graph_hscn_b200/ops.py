@@ -238,9 +238,9 @@ torch.library.register_autograd("ghscn::spmm", _spmm_backward, setup_context=_sp
 # =============================================================================================
 # fused SCN node pipeline: GraphConv aggregation + lin_rel + lin_root + activation + cluster Linear
 # =============================================================================================
-MINCUT_TC_MIN_K = int(os.environ.get("GHSCN_MINCUT_TC_MIN_K", "64"))
+MINCUT_TC_MIN_K = int(os.environ.get("GHSCN_MINCUT_TC_MIN_K", "32"))
 MINCUT_TC_PHASE1 = int(os.environ.get("GHSCN_MINCUT_TC_PHASE1", "3"))      # 3: A S by the batch SpMM; 1: per-graph CTAs
-MINCUT_SPLIT_MIN_K = int(os.environ.get("GHSCN_MINCUT_SPLIT_MIN_K", "64"))   # backward as per-graph tiled GEMMs
+MINCUT_SPLIT_MIN_K = int(os.environ.get("GHSCN_MINCUT_SPLIT_MIN_K", "32"))   # backward as per-graph tiled GEMMs
 MINCUT_TC_KK = os.environ.get("GHSCN_MINCUT_TC_KK", "1") != "0"      # S^T S and S^T A S on the tensor cores too
 FUSED_SCN_BACKWARD = os.environ.get("GHSCN_FUSED_SCN_BACKWARD", "1") != "0"
 SCN_ACTS = {"identity": 0, "elu": 1, "relu": 2, "tanh": 3}

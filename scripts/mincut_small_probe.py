@@ -1,5 +1,8 @@
-"""MinCUT pool at the bench shape (B = 128 Peptides graphs, K = 10, losses only): forward and forward+backward device
-time, alone on the GPU.  GHSCN_MINCUT_THREADS=256|512|1024 selects the CTA size.  python scripts/mincut_small_probe.py"""
+"""MinCUT pool at the bench shape (B = 128 Peptides graphs, K = 10): forward and forward+backward device time, alone on
+the GPU.  PROBE_H=0 (default): losses only (what hscn.py:63 keeps), on 16 features; PROBE_H=300: with the pooled
+features and coarse adjacency and their gradients.  PROBE_GRAPHS / PROBE_K pick the batch and cluster count;
+GHSCN_MINCUT_THREADS=256|512|1024 selects the CTA size, GHSCN_MINCUT_STREAM_X=0 / GHSCN_MINCUT_STAGE=1 the A/B
+switches of csrc/mincut.cu.  python scripts/mincut_small_probe.py"""
 import os
 import statistics
 import sys
@@ -13,6 +16,7 @@ from graph_hscn_b200.structure import structure_cache, structure_hints  # noqa: 
 dev = torch.device("cuda:0")
 B = int(os.environ.get("PROBE_GRAPHS", "128"))
 K = int(os.environ.get("PROBE_K", "10"))
+H = int(os.environ.get("PROBE_H", "0"))
 b = synthetic.peptides_batch(B, seed=1239)
 N = b.x.size(0)
 counts = b.ptr[1:] - b.ptr[:-1]
@@ -40,18 +44,23 @@ def graph_time(fn, reps=20, trials=5):
 with structure_hints(**hints):
     ei, _ = pyg.gcn_norm(b.edge_index.to(dev), None, N, add_self_loops=True)
     g = torch.Generator().manual_seed(1)
-    x = torch.randn(N, 16, generator=g).to(dev)
+    x = torch.randn(N, H or 16, generator=g).to(dev).requires_grad_(H > 0)
     s = torch.randn(N, K, generator=g).to(dev).requires_grad_()
     batch = b.batch.to(dev)
 
     def fwd():
-        return pyg.mincut_pool_ragged(x, ei, s, batch, want_out=False, want_adj=False)
+        return pyg.mincut_pool_ragged(x, ei, s, batch, want_out=H > 0, want_adj=H > 0)
 
     def fb():
-        _, _, mc, ol = fwd()
-        (mc + ol).backward()
+        out, adj, mc, ol = fwd()
+        loss = mc + ol
+        if H > 0:
+            loss = loss + out.sum() + adj.sum()
+        loss.backward()
         s.grad = None
-    tf = graph_time(fwd)
+        x.grad = None
+    tf = graph_time(fwd) if os.environ.get('PROBE_SKIP_FWD') != '1' else float('nan')
     tfb = graph_time(fb)
-print(f"B={B} K={K} N={N} threads={os.environ.get('GHSCN_MINCUT_THREADS', 'auto')}: fwd {tf:.1f} us, fwd+bwd {tfb:.1f} us")
+print(f"B={B} K={K} H={H} N={N} stream_x={os.environ.get('GHSCN_MINCUT_STREAM_X', '1')} "
+      f"stage={os.environ.get('GHSCN_MINCUT_STAGE', 'default')} threads={os.environ.get('GHSCN_MINCUT_THREADS', 'auto')}: fwd {tf:.1f} us, fwd+bwd {tfb:.1f} us")
 structure_cache().clear()

@@ -295,12 +295,14 @@ def test_mincut_ragged_fwd_bwd(cuda, K, H):
     assert_close(xt.grad, xr.grad, 5 * RTOL, "mincut d x")
 
 
-def test_mincut_losses_only_backward(cuda):
-    """The reference keeps only the two losses (hscn.py:63): the diag-only fast path."""
+@pytest.mark.parametrize("K,H", [(10, 16), (64, 16), (128, 300)])
+def test_mincut_losses_only_backward(cuda, K, H):
+    """The reference keeps only the two losses (hscn.py:63): the diag-only fast path (K < 64) and the split backward
+    without pooled-feature / coarse-adjacency gradients (K >= 64)."""
     o, p = _oracle(), _product()
     b = _peptide_batch(9, seed=77)
     g = torch.Generator().manual_seed(1)
-    N, K, H = b.x.size(0), 10, 16
+    N = b.x.size(0)
     ei, _ = o.gcn_norm(b.edge_index, None, N, add_self_loops=True)
     x = torch.randn(N, H, generator=g)
     s = torch.randn(N, K, generator=g)
@@ -313,6 +315,28 @@ def test_mincut_losses_only_backward(cuda):
     assert_close(mc_t, mc_r, RTOL, "mc")
     assert_close(or_t, or_r, RTOL, "ortho")
     assert_close(st_.grad, sr.grad, 5 * RTOL, "d logits")
+
+
+@pytest.mark.parametrize("which", ["out", "adj"])
+def test_mincut_split_backward_partial_objectives(cuda, which):
+    """K >= 64: the split backward with only ONE of the two dense outputs in the objective (the other's gradient arrives
+    as None) and features that carry no gradient (d_x not requested); rows of a trailing graph the batch vector does
+    not cover get zero gradients."""
+    o, p = _oracle(), _product()
+    K, H = 64, 40
+    b = _peptide_batch(5, seed=3)
+    g = torch.Generator().manual_seed(7)
+    N = b.x.size(0)
+    ei, _ = o.gcn_norm(b.edge_index, None, N, add_self_loops=True)
+    x = torch.randn(N, H, generator=g)
+    s = torch.randn(N, K, generator=g)
+    sr, st_ = s.clone().requires_grad_(), s.to(cuda).requires_grad_()
+    out_r, adj_r, mc_r, or_r = o.mincut_pool_ragged(x, ei, sr, b.batch)
+    out_t, adj_t, mc_t, or_t = p.mincut_pool_ragged(x.to(cuda), ei.to(cuda), st_, b.batch.to(cuda))
+    w = torch.randn((out_r if which == "out" else adj_r).shape, generator=g)
+    ((out_r if which == "out" else adj_r) * w).sum().add(mc_r * 0.5).backward()
+    ((out_t if which == "out" else adj_t) * w.to(cuda)).sum().add(mc_t * 0.5).backward()
+    assert_close(st_.grad, sr.grad, 5 * RTOL, f"d logits through {which}")
 
 
 def test_dense_mincut_pool_single_graph_api(cuda):
