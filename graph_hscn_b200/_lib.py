@@ -69,6 +69,8 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "ghscn_gcn_deg_inv_sqrt": (I32, [P, P, P, P, I64, I64, P, P]),
     "ghscn_edge_weights": (I32, [P, P, P, P, P, P, I64, I64, I32, I32, P, P]),
     "ghscn_loop_weights": (I32, [P, P, P, I64, I64, F32, P, P, P]),
+    "ghscn_laplacian_eig_workspace_bytes": (SZ, [I64, I64, I32]),
+    "ghscn_laplacian_eig": (I32, [P, P, P, I64, I64, I32, I32, I32, I32, I32, P, P, P, P, SZ, P]),
     "ghscn_spmm": (I32, [P, P, P, P, I64, P, I64, P, I64, I64, I32, P]),
     "ghscn_spmm_masked_supported": (I32, [I64, I64, I64, I64]),
     "ghscn_spmm_masked": (I32, [P, P, P, P, I64, P, I64, P, I64, I64, I64, P]),

@@ -191,6 +191,15 @@ class GINConv(MessagePassing):
             self.register_buffer("eps", torch.tensor([eps]))
 
     def forward(self, x, edge_index: Tensor, size=None) -> Tensor:
+        if isinstance(x, Tensor) and x.dim() == 3:
+            # PyG propagates along node_dim = -2: the [K, N, C] stack of encoder/signnet.py:227-229 is ONE
+            # aggregation over [N, K*C] (the sum over neighbours is per column), then `nn` on the last dim
+            k, n, c = x.shape
+            dev, back = _device.plan(x, edge_index)
+            flat = _device.to_dev(x, dev).permute(1, 0, 2).reshape(n, k * c)
+            agg = _aggregate(flat, _device.index_to_dev(edge_index, dev), None, n).view(n, k, c).permute(1, 0, 2)
+            agg = _device.back_to(agg, back)
+            return self.nn(agg + (1 + _device.to_dev(self.eps, agg.device)) * x)
         if isinstance(x, Tensor):
             x = (x, x)
         dev, back = _device.plan(x[0], x[1], edge_index)

@@ -509,6 +509,26 @@ GHSCN_API int ghscn_virtual_compact(const float* virt_x_padded, const int32_t* n
                                     int64_t num_feat, float* virt_x /*[V,F]*/, int64_t* virt_batch /*[V]*/,
                                     ghscn_stream_t stream);
 
+/* ---- Laplacian positional encoding -------------------------------------------
+ * Replaces the per-graph host loop of transform/posenc.py:14-82 (get_laplacian -> scipy toarray ->
+ * np.linalg.eigh -> get_lap_decomp_stats :50-82 -> eigvec_normalizer :85-108) for a whole collated batch:
+ * one CTA per graph builds the dense Laplacian from the graph's CSR slice (rows = edge_index[0], float32
+ * entries like PyG's, lower triangle mirrored like LAPACK's UPLO='L'), diagonalises it with a float64
+ * one-sided Jacobi iteration and writes, per node, the `max_freqs` smallest eigenvalues (clamped at 0) and
+ * the matching normalised eigenvector entries; graphs with fewer nodes than max_freqs get NaN padding.
+ *   laplacian_norm: 0 = none (D - A), 1 = sym, 2 = rw (posenc.py:33-41);  symmetrize != 0 = to_undirected
+ *   (posenc.py:28-31) with coalescing;  eigvec_norm: 0 = L1, 1 = L2, 2 = abs-max.
+ * Eigenvector signs / bases of repeated eigenvalues are LAPACK's choice in the reference and not reproduced.
+ * sweeps [B] (nullable) receives the Jacobi sweep count per graph (40 = not converged). */
+GHSCN_API size_t ghscn_laplacian_eig_workspace_bytes(int64_t num_nodes, int64_t num_graphs,
+                                                    int32_t max_nodes_per_graph);
+GHSCN_API int ghscn_laplacian_eig(const int32_t* ptr, const int32_t* rowptr, const int32_t* col, int64_t num_graphs,
+                                  int64_t num_nodes, int32_t max_nodes_per_graph, int32_t laplacian_norm,
+                                  int32_t symmetrize, int32_t max_freqs, int32_t eigvec_norm,
+                                  float* eigvals /*[N,max_freqs]*/, float* eigvecs /*[N,max_freqs]*/,
+                                  int32_t* sweeps /*[B]|NULL*/, void* workspace, size_t workspace_bytes,
+                                  ghscn_stream_t stream);
+
 /* ---- small fused elementwise epilogues ------------------------------------ */
 GHSCN_API int ghscn_cast_i64_f32(const int64_t* in, int64_t n, float* out, ghscn_stream_t stream);
 

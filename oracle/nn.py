@@ -137,6 +137,12 @@ class GINConv(MessagePassing):
             self.register_buffer("eps", torch.tensor([eps]))
 
     def forward(self, x, edge_index: Tensor, size=None) -> Tensor:
+        if isinstance(x, Tensor) and x.dim() == 3:
+            # PyG propagates along node_dim = -2: [K, N, C] (encoder/signnet.py:227-229) is aggregated per slice
+            k, n, c = x.shape
+            flat = x.permute(1, 0, 2).reshape(n, k * c)
+            agg = ops.propagate_add(flat, edge_index, None, n).view(n, k, c).permute(1, 0, 2)
+            return self.nn(agg + (1 + self.eps) * x)
         if isinstance(x, Tensor):
             x = (x, x)
         out = ops.propagate_add(x[0], edge_index, None, x[1].size(0))
