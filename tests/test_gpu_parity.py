@@ -269,7 +269,8 @@ def _peptide_batch(num_graphs, seed):
     return synthetic.peptides_batch(num_graphs, seed=seed)
 
 
-@pytest.mark.parametrize("K,H", [(10, 16), (4, 64), (32, 40), (128, 24), (64, 300), (128, 512), (68, 332)])
+@pytest.mark.parametrize("K,H", [(10, 16), (4, 64), (32, 40), (128, 24), (64, 300), (128, 512), (68, 332),
+                                 (10, 300), (5, 132), (6, 256), (16, 128), (31, 512)])   # streamed pooled features, fwd + bwd
 def test_mincut_ragged_fwd_bwd(cuda, K, H):
     o, p = _oracle(), _product()
     b = _peptide_batch(6, seed=K)
