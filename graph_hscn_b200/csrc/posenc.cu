@@ -14,6 +14,7 @@
 // eigenvalues, keeps the `max_freqs` smallest, normalises the float32 eigenvectors and writes the per-node rows.
 // Eigenvector signs / the basis inside a repeated eigenvalue are not defined by the reference either (LAPACK's
 // choice); the encoder that consumes them (encoder/signnet.py) is sign invariant by construction.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -118,7 +119,8 @@ __global__ void __launch_bounds__(kEigThreads) laplacian_build_kernel(
 // L2-resident workspace; a pair's two columns stay in registers between the dot products and the rotation (n <= 256).
 // One column pair on one warp.  R > 0: the pair's 2 * 32 * R elements stay in registers between the dot products and
 // the rotation (n <= 32 R); R = 0: columns of any length are read twice.  Returns whether the pair was rotated.
-template <int R>
+// CG: the columns are shared with the other CTAs of a cluster through L2, so loads bypass L1 (ld.global.cg).
+template <int R, bool CG>
 __device__ __forceinline__ bool jacobi_pair(double* gp, double* gq, int n, int lane) {
   constexpr int RR = R > 0 ? R : 1;
   double x[RR], y[RR];
@@ -127,14 +129,14 @@ __device__ __forceinline__ bool jacobi_pair(double* gp, double* gq, int n, int l
 #pragma unroll
     for (int u = 0; u < RR; ++u) {
       const int i = lane + 32 * u;
-      x[u] = i < n ? gp[i] : 0.0;
-      y[u] = i < n ? gq[i] : 0.0;
+      x[u] = i < n ? (CG ? __ldcg(gp + i) : gp[i]) : 0.0;
+      y[u] = i < n ? (CG ? __ldcg(gq + i) : gq[i]) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < RR; ++u) { a = fma(x[u], x[u], a); b = fma(y[u], y[u], b); c = fma(x[u], y[u], c); }
   } else {
     for (int i = lane; i < n; i += 32) {
-      const double xv = gp[i], yv = gq[i];
+      const double xv = CG ? __ldcg(gp + i) : gp[i], yv = CG ? __ldcg(gq + i) : gq[i];
       a = fma(xv, xv, a); b = fma(yv, yv, b); c = fma(xv, yv, c);
     }
   }
@@ -154,7 +156,7 @@ __device__ __forceinline__ bool jacobi_pair(double* gp, double* gq, int n, int l
     }
   } else {
     for (int i = lane; i < n; i += 32) {
-      const double xv = gp[i], yv = gq[i];
+      const double xv = CG ? __ldcg(gp + i) : gp[i], yv = CG ? __ldcg(gq + i) : gq[i];
       gp[i] = cs * xv - sn * yv;
       gq[i] = sn * xv + cs * yv;
     }
@@ -162,54 +164,92 @@ __device__ __forceinline__ bool jacobi_pair(double* gp, double* gq, int n, int l
   return true;
 }
 
+template <bool CG>
+__device__ __forceinline__ bool jacobi_step_pairs(double* G, int n, int m, int half, int s, int first, int stride,
+                                                  int lane) {
+  const int mode = n <= 128 ? 4 : (n <= 256 ? 8 : 0);
+  bool mine = false;
+  for (int k = first; k < half; k += stride) {     // a warp per pair; warp-uniform control flow
+    int p, q;
+    if (k == 0) { p = m - 1; q = s; }
+    else { p = (s + k) % (m - 1); q = (s - k + (m - 1)) % (m - 1); }
+    if (p >= n || q >= n) continue;
+    double* gp = G + (size_t)p * n;
+    double* gq = G + (size_t)q * n;
+    if (mode == 4) mine |= jacobi_pair<4, CG>(gp, gq, n, lane);
+    else if (mode == 8) mine |= jacobi_pair<8, CG>(gp, gq, n, lane);
+    else mine |= jacobi_pair<0, CG>(gp, gq, n, lane);
+  }
+  return mine;
+}
+
+// grid = (cluster size C, graphs), cluster dims (C, 1, 1).  A graph whose matrix fits in shared memory is handled by
+// rank 0 alone (the other ranks leave at once).  A larger graph -- the tail of a small batch: its matrix streams from
+// L2 at ONE SM's bandwidth -- is shared by the C CTAs of the cluster: each takes every C-th warp's worth of a step's
+// pairs on the L2-resident matrix, with a cluster barrier (release / acquire) between steps.
+template <bool CLUSTER>
 __global__ void __launch_bounds__(kEigThreads) jacobi_eig_kernel(const int* __restrict__ ptr, int n_cap, int smem_n,
-                                                                 double* gmat, int* __restrict__ sweeps_out) {
+                                                                 double* gmat, int* flags, int* __restrict__ sweeps_out) {
+  namespace cgr = cooperative_groups;
   extern __shared__ double gs[];                   // [smem_n * smem_n] when the graph fits
   __shared__ int rotated;
-  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
+  const int g = blockIdx.y, rank = blockIdx.x, csize = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
   const int base = ptr[g], n = ptr[g + 1] - base;
   if (n <= 1 || n > n_cap) {
-    if (tid == 0 && sweeps_out) sweeps_out[g] = 0;
+    if (rank == 0 && tid == 0 && sweeps_out) sweeps_out[g] = 0;
     return;
   }
   double* Gg = gmat + (size_t)base * n_cap;
   const bool in_smem = n <= smem_n;
-  double* G = in_smem ? gs : Gg;
-  const int nn = n * n;
-  if (in_smem) {
-    for (int e = tid; e < nn; e += blockDim.x) gs[e] = Gg[e];
-    __syncthreads();
-  }
-  const int mode = n <= 128 ? 4 : (n <= 256 ? 8 : 0);
   const int m = n + (n & 1), half = m >> 1;        // round-robin over m players; player n (odd n) sits out
   int sweep = 0;
-  for (; sweep < kEigMaxSweeps; ++sweep) {
-    if (tid == 0) rotated = 0;
-    __syncthreads();
-    bool mine = false;
-    for (int s = 0; s < m - 1; ++s) {
-      for (int k = wid; k < half; k += nwarps) {   // a warp per pair; warp-uniform control flow
-        int p, q;
-        if (k == 0) { p = m - 1; q = s; }
-        else { p = (s + k) % (m - 1); q = (s - k + (m - 1)) % (m - 1); }
-        if (p >= n || q >= n) continue;
-        double* gp = G + (size_t)p * n;
-        double* gq = G + (size_t)q * n;
-        if (mode == 4) mine |= jacobi_pair<4>(gp, gq, n, lane);
-        else if (mode == 8) mine |= jacobi_pair<8>(gp, gq, n, lane);
-        else mine |= jacobi_pair<0>(gp, gq, n, lane);
-      }
-      __syncthreads();                             // the next step pairs the columns differently
+  if (!CLUSTER || in_smem || csize == 1) {
+    if (rank != 0) return;
+    double* G = in_smem ? gs : Gg;
+    const int nn = n * n;
+    if (in_smem) {
+      for (int e = tid; e < nn; e += blockDim.x) gs[e] = Gg[e];
+      __syncthreads();
     }
-    if (mine) rotated = 1;
-    __syncthreads();
-    const int any = rotated;
-    __syncthreads();
-    if (!any) { ++sweep; break; }
+    for (; sweep < kEigMaxSweeps; ++sweep) {
+      if (tid == 0) rotated = 0;
+      __syncthreads();
+      bool mine = false;
+      for (int s = 0; s < m - 1; ++s) {
+        mine |= jacobi_step_pairs<false>(G, n, m, half, s, wid, nwarps, lane);
+        __syncthreads();                           // the next step pairs the columns differently
+      }
+      if (mine) rotated = 1;
+      __syncthreads();
+      const int any = rotated;
+      __syncthreads();
+      if (!any) { ++sweep; break; }
+    }
+    if (in_smem)
+      for (int e = tid; e < nn; e += blockDim.x) Gg[e] = gs[e];
+  } else if (CLUSTER) {
+    cgr::cluster_group cluster = cgr::this_cluster();
+    volatile int* flag = flags + g;
+    for (; sweep < kEigMaxSweeps; ++sweep) {
+      if (rank == 0 && tid == 0) *flag = 0;
+      __threadfence();
+      cluster.sync();
+      bool mine = false;
+      for (int s = 0; s < m - 1; ++s) {
+        mine |= jacobi_step_pairs<true>(Gg, n, m, half, s, rank * nwarps + wid, csize * nwarps, lane);
+        __threadfence();
+        cluster.sync();
+      }
+      if (mine && lane == 0) *flag = 1;
+      __threadfence();
+      cluster.sync();
+      const int any = *flag;
+      cluster.sync();                              // everyone has read the flag before rank 0 clears it
+      if (!any) { ++sweep; break; }
+    }
   }
-  if (in_smem)
-    for (int e = tid; e < nn; e += blockDim.x) Gg[e] = gs[e];
-  if (tid == 0 && sweeps_out) sweeps_out[g] = sweep;
+  if (rank == 0 && tid == 0 && sweeps_out) sweeps_out[g] = sweep;
 }
 
 // ---- kernel 3: eigenvalues = column norms - shift, the max_freqs smallest, normalised float32 rows ---------------------
@@ -285,7 +325,8 @@ extern "C" {
 size_t ghscn_laplacian_eig_workspace_bytes(int64_t num_nodes, int64_t num_graphs, int32_t max_nodes_per_graph) {
   if (num_nodes < 0 || num_graphs < 0 || max_nodes_per_graph < 0) return 0;
   // G and V: a graph's n x n block starts at ptr[g] * n_cap (n^2 <= n * n_cap); + one shift per graph
-  return ((size_t)2 * num_nodes * max_nodes_per_graph + (size_t)num_graphs) * sizeof(double) + 256;
+  // ... + per graph: one shift (double) and one convergence flag (int, 8-byte slot)
+  return ((size_t)2 * num_nodes * max_nodes_per_graph + (size_t)2 * num_graphs) * sizeof(double) + 256;
 }
 
 int ghscn_laplacian_eig(const int32_t* ptr, const int32_t* rowptr, const int32_t* col, int64_t num_graphs,
@@ -294,7 +335,7 @@ int ghscn_laplacian_eig(const int32_t* ptr, const int32_t* rowptr, const int32_t
                         void* workspace, size_t workspace_bytes, ghscn_stream_t stream_) {
   GHSCN_REQUIRE(num_graphs >= 0 && num_nodes >= 0 && max_freqs > 0);
   GHSCN_REQUIRE(laplacian_norm >= 0 && laplacian_norm <= 2 && eigvec_norm >= 0 && eigvec_norm <= 2);
-  GHSCN_REQUIRE(num_graphs < ((int64_t)1 << 31) && num_nodes < ((int64_t)1 << 31));
+  GHSCN_REQUIRE(num_graphs < 65536 && num_nodes < ((int64_t)1 << 31));   // grid.y
   if (num_graphs == 0 || num_nodes == 0) return GHSCN_OK;
   GHSCN_REQUIRE(ptr && rowptr && col && eigvals && eigvecs && max_nodes_per_graph > 0);
   const int n_cap = max_nodes_per_graph;
@@ -312,8 +353,28 @@ int ghscn_laplacian_eig(const int32_t* ptr, const int32_t* rowptr, const int32_t
   // the Jacobi kernel keeps a graph's matrix in shared memory when it fits: room for min(n_cap, 168)^2 doubles
   const int smem_n = n_cap < 168 ? n_cap : 168;
   const size_t jac_shm = (size_t)smem_n * smem_n * sizeof(double);
-  cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(168 * 168 * sizeof(double)));
-  jacobi_eig_kernel<<<(unsigned)num_graphs, kEigThreads, jac_shm, stream>>>(ptr, n_cap, smem_n, gmat, sweeps);
+  cudaFuncSetAttribute(jacobi_eig_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(168 * 168 * sizeof(double)));
+  cudaFuncSetAttribute(jacobi_eig_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(168 * 168 * sizeof(double)));
+  // small batches with graphs beyond the shared-memory size: a cluster of 4 CTAs shares each of those (the tail)
+  const int csize = (n_cap > smem_n && num_graphs <= 2 * kNumSMs) ? 4 : 1;
+  int* flags = reinterpret_cast<int*>(shift + num_graphs);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)csize, (unsigned)num_graphs);
+    cfg.blockDim = dim3(kEigThreads);
+    cfg.dynamicSmemBytes = jac_shm;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = csize > 1 ? cudaLaunchKernelEx(&cfg, jacobi_eig_kernel<true>, ptr, n_cap, smem_n, gmat, flags, sweeps)
+                              : cudaLaunchKernelEx(&cfg, jacobi_eig_kernel<false>, ptr, n_cap, smem_n, gmat, flags, sweeps);
+    if (e != cudaSuccess) return (int)e;
+  }
   eig_select_kernel<<<(unsigned)num_graphs, kEigThreads, (size_t)n_cap * 12, stream>>>(
       ptr, n_cap, max_freqs, eigvec_norm, gmat, shift, eigvals, eigvecs);
   GHSCN_LAUNCH_CHECK_N(3);

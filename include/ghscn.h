@@ -519,7 +519,7 @@ GHSCN_API int ghscn_virtual_compact(const float* virt_x_padded, const int32_t* n
  *   laplacian_norm: 0 = none (D - A), 1 = sym, 2 = rw (posenc.py:33-41);  symmetrize != 0 = to_undirected
  *   (posenc.py:28-31) with coalescing;  eigvec_norm: 0 = L1, 1 = L2, 2 = abs-max.
  * Eigenvector signs / bases of repeated eigenvalues are LAPACK's choice in the reference and not reproduced.
- * sweeps [B] (nullable) receives the Jacobi sweep count per graph (40 = not converged). */
+ * sweeps [B] (nullable) receives the Jacobi sweep count per graph (40 = not converged).  B <= 65535 per call. */
 GHSCN_API size_t ghscn_laplacian_eig_workspace_bytes(int64_t num_nodes, int64_t num_graphs,
                                                     int32_t max_nodes_per_graph);
 GHSCN_API int ghscn_laplacian_eig(const int32_t* ptr, const int32_t* rowptr, const int32_t* col, int64_t num_graphs,

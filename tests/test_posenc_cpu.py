@@ -128,7 +128,7 @@ def test_laplacian_eig_argument_errors(built_lib):
     """C-ABI argument validation (no GPU work is launched for a rejected call)."""
     from graph_hscn_b200._lib import lib
     L = lib()
-    assert L.query("ghscn_laplacian_eig_workspace_bytes", 100, 4, 50) == (2 * 100 * 50 + 4) * 8 + 256
+    assert L.query("ghscn_laplacian_eig_workspace_bytes", 100, 4, 50) == (2 * 100 * 50 + 2 * 4) * 8 + 256
     assert L.query("ghscn_laplacian_eig_workspace_bytes", -1, 4, 50) == 0
     fn = L._fns["ghscn_laplacian_eig"]
     one = 8                                                        # fake non-null pointers; rejected before any use
