@@ -53,7 +53,10 @@ def build_modules(ns: types.SimpleNamespace, data_mod=None) -> dict:
     nn_mod = mod("torch_geometric.nn", conv=conv, Linear=ns.Linear, Sequential=ns.Sequential,
                  dense_mincut_pool=ns.dense_mincut_pool, global_mean_pool=ns.global_mean_pool, **conv_attrs)
     nn_mod.__path__ = []
-    utils = mod("torch_geometric.utils", to_dense_adj=ns.to_dense_adj)
+    from . import utils as _utils          # transform/posenc.py:5-9 imports these three (+ remove_self_loops)
+    utils = mod("torch_geometric.utils", to_dense_adj=ns.to_dense_adj,
+                **{name: getattr(ns, name, getattr(_utils, name))
+                   for name in ("get_laplacian", "to_undirected", "to_scipy_sparse_matrix", "remove_self_loops")})
     batch_mod = mod("torch_geometric.data.batch", Batch=data_mod.Batch)
     data = mod("torch_geometric.data", Data=data_mod.Data, HeteroData=data_mod.HeteroData, Batch=data_mod.Batch,
                batch=batch_mod)

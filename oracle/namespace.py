@@ -12,6 +12,7 @@ from torch import Tensor
 
 from . import nn as onn
 from . import ops as oops
+from . import posenc as oposenc
 
 
 def mincut_pool_ragged(x: Tensor, edge_index: Tensor, s: Tensor, batch: Optional[Tensor] = None,
@@ -33,4 +34,6 @@ def namespace() -> SimpleNamespace:
         HeteroConv=onn.HeteroConv, Linear=onn.Linear, Sequential=onn.Sequential, MessagePassing=onn.MessagePassing,
         dense_mincut_pool=oops.dense_mincut_pool, mincut_pool_ragged=mincut_pool_ragged,
         to_dense_adj=oops.to_dense_adj, global_mean_pool=oops.global_mean_pool, scatter_mean=oops.scatter_mean,
-        gcn_norm=oops.gcn_norm, scatter=oops.scatter, scatter_add=oops.scatter_add)
+        gcn_norm=oops.gcn_norm, scatter=oops.scatter, scatter_add=oops.scatter_add,
+        get_laplacian=oposenc.get_laplacian, to_undirected=oposenc.to_undirected,
+        to_scipy_sparse_matrix=oposenc.to_scipy_sparse_matrix, remove_self_loops=oposenc.remove_self_loops)

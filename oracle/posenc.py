@@ -7,7 +7,8 @@ Follows, line by line,
 and PyG 2.2/2.3's `get_laplacian`, `to_undirected`, `remove_self_loops`, `to_scipy_sparse_matrix` (not vendored in
 /root/reference; restated from their published behaviour -- "parity unpinned" for those four, like the rest of the PyG
 operator layer).  `get_lap_decomp_stats` / `eigvec_normalizer` ARE pinned: tests/golden/posenc.pt holds the outputs of
-the reference's own source text for them (tests/golden/make_golden_posenc.py executes it unmodified).
+the reference's own source text for them (tests/golden/make_golden_posenc.py executes it unmodified), and the rows that
+the reference's whole `compute_posenc_stats`, imported unchanged, produces on top of the four restated utilities.
 
 Precision note: PyG builds the Laplacian weights in float32 and scipy's `.toarray()` keeps that dtype, so the
 reference's `np.linalg.eigh` is LAPACK single precision (ssyevd).  Eigenvector signs, and the basis inside a repeated
@@ -68,6 +69,17 @@ def get_laplacian(edge_index: Tensor, edge_weight: Optional[Tensor] = None, norm
         edge_index = torch.cat([edge_index, loop_index], 1)
         edge_weight = torch.cat([-edge_weight, torch.ones(n, dtype=edge_weight.dtype)])
     return edge_index, edge_weight
+
+
+def to_scipy_sparse_matrix(edge_index: Tensor, edge_attr: Optional[Tensor] = None, num_nodes: Optional[int] = None):
+    """PyG to_scipy_sparse_matrix: COO matrix of the edge list (duplicates add up on `.toarray()`), dtype of the
+    weights (float32 for a Laplacian from get_laplacian)."""
+    import scipy.sparse
+    row, col = edge_index.cpu().numpy()
+    if edge_attr is None:
+        edge_attr = torch.ones(row.shape[0])
+    n = int(edge_index.max()) + 1 if num_nodes is None else int(num_nodes)
+    return scipy.sparse.coo_matrix((edge_attr.view(-1).cpu().numpy(), (row, col)), (n, n))
 
 
 def laplacian_dense(edge_index: Tensor, num_nodes: int, is_undirected: bool, norm: Optional[str]) -> np.ndarray:

@@ -5,9 +5,10 @@ not exist on the GPU box):
 
 Pinned here
   * graph_hscn/transform/posenc.py: `get_lap_decomp_stats` and `eigvec_normalizer` -- their source text is cut out of
-    the file with `ast` and executed as is (the module itself cannot be imported: it pulls `get_laplacian`,
-    `to_scipy_sparse_matrix`, `to_undirected` from torch_geometric, which is not installable offline; those three are
-    restated in oracle/posenc.py and stay "parity unpinned");
+    the file with `ast` and executed as is on explicit LAPACK outputs; and the whole module imported unchanged, its
+    `compute_posenc_stats` run per graph on top of the oracle's restatement of the three PyG utilities it imports
+    (`get_laplacian`, `to_scipy_sparse_matrix`, `to_undirected`: torch_geometric is not installable offline, so those
+    three stay "parity unpinned") -- the stored rows are asserted to be exactly what that function produces;
   * graph_hscn/encoder/signnet.py: imported unchanged on top of the oracle operator namespace.  `MLP.__init__` reads
     `ACT_DICT["activation"]` (signnet.py:49), a key the reference's dictionary does not have, so
     the generator adds that ONE key (-> relu, the value every call site passes) to the imported dictionary; no source
@@ -73,6 +74,17 @@ def main() -> None:
     install_reference_imports()
     import graph_hscn.config.config as ref_config
     ref_config.ACT_DICT["activation"] = F.relu          # see the module docstring
+    # ---- transform/posenc.py imported whole and run unmodified on the oracle's get_laplacian / to_undirected /
+    #      to_scipy_sparse_matrix: the rows stored above must be what compute_posenc_stats itself produces
+    from graph_hscn.transform.posenc import compute_posenc_stats as ref_compute
+    pe_cfg = types.SimpleNamespace(eigen_laplacian_norm="sym", eigen_max_freqs=10, eigvec_norm="L2")
+    for g in graphs:
+        d = ref_compute(Data(x=g.x, edge_index=g.edge_index), True, pe_cfg)
+        assert torch.equal(torch.nan_to_num(d.eigvals_sn), torch.nan_to_num(g.eigvals_sn))
+        assert torch.equal(torch.nan_to_num(d.eigvecs_sn), torch.nan_to_num(g.eigvecs_sn))
+    und = graphs[0].edge_index[:, graphs[0].edge_index[0] < graphs[0].edge_index[1]]
+    d = ref_compute(Data(x=graphs[0].x, edge_index=und), False, pe_cfg)          # is_undirected = False branch
+    out["directed"] = dict(x=graphs[0].x, edge_index=und, eigvals_sn=d.eigvals_sn, eigvecs_sn=d.eigvecs_sn)
     from graph_hscn.encoder.signnet import SignNetNodeEncoder
     base = dict(dim_pe=8, layers=2, post_layers=2, eigen_max_freqs=10, phi_hidden_dim=16, phi_out_dim=4,
                 pass_as_var=True, use_bn=False)

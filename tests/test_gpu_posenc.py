@@ -99,6 +99,16 @@ def test_directed_input_is_symmetrised(cuda):
     _check_graph(half, n, vals.cpu(), vecs.cpu(), False, "sym", "L2")
 
 
+def test_directed_golden_rows(cuda, gold):
+    """Rows produced by the reference's own compute_posenc_stats(..., is_undirected=False) (unmodified source)."""
+    from graph_hscn_b200 import posenc
+    d = gold["directed"]
+    n = d["x"].size(0)
+    vals, vecs = posenc.laplacian_eig(d["edge_index"].to(cuda), torch.tensor([0, n]), n, n, is_undirected=False)
+    assert torch.allclose(vals.cpu(), d["eigvals_sn"].squeeze(2), atol=2e-5)
+    _check_graph(d["edge_index"], n, vals.cpu(), vecs.cpu(), False, "sym", "L2")
+
+
 def test_edge_cases(cuda):
     """single node, isolated node (degree 0), n < max_freqs, duplicate edges with is_undirected = True (they add up),
     a self loop (dropped), an empty graph in the middle of the batch."""

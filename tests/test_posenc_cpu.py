@@ -138,3 +138,33 @@ def test_laplacian_eig_argument_errors(built_lib):
     assert fn(one, one, one, 2, 10, 5, 1, 0, 10, 1, one, one, None, one, 16, None) == -2        # workspace
     assert fn(one, one, one, 2, 10, 5000, 1, 0, 10, 1, one, one, None, one, 1 << 40, None) == -3  # n_cap
     assert fn(None, None, None, 0, 0, 0, 1, 0, 10, 1, None, None, None, None, 0, None) == 0     # empty batch
+
+
+def test_shim_utils_equal_oracle_restatement(gold):
+    """graph_hscn_b200/pyg/utils.py (what `torch_geometric.utils` resolves to under pyg.install(), so that
+    transform/posenc.py imports and runs unchanged) == the oracle's restatement of the same PyG functions, bit for bit;
+    and the golden rows of the reference's is_undirected = False branch."""
+    from graph_hscn_b200 import pyg
+    from graph_hscn_b200.pyg import utils as pu
+    from oracle import posenc as op
+    mods = pyg.build_modules(pyg.namespace())
+    for name in ("get_laplacian", "to_undirected", "to_scipy_sparse_matrix", "remove_self_loops", "to_dense_adj"):
+        assert callable(getattr(mods["torch_geometric.utils"], name)), name
+    g = gold["graphs"][0]
+    n = g["x"].size(0)
+    ei = torch.cat([g["edge_index"], torch.tensor([[3, 3, 0], [3, 3, 1]])], 1)      # self loops + a duplicate
+    for norm in (None, "sym", "rw"):
+        a_i, a_w = pu.get_laplacian(ei, normalization=norm, num_nodes=n)
+        b_i, b_w = op.get_laplacian(ei, normalization=norm, num_nodes=n)
+        assert torch.equal(a_i, b_i) and torch.equal(a_w, b_w), norm
+        dense_a = pu.to_scipy_sparse_matrix(a_i, a_w, n).toarray()
+        dense_b = op.to_scipy_sparse_matrix(b_i, b_w, n).toarray()
+        assert dense_a.dtype == np.float32 and np.array_equal(dense_a, dense_b)
+    half = ei[:, ei[0] <= ei[1]]
+    assert torch.equal(pu.to_undirected(half, num_nodes=n), op.to_undirected(half, n))
+    with pytest.raises(ValueError):
+        pu.get_laplacian(ei, normalization="bad", num_nodes=n)
+    d = gold["directed"]
+    vals, vecs = op.compute_posenc_stats(d["edge_index"], d["x"].size(0), False, 10, "L2", "sym")
+    assert torch.allclose(vals, d["eigvals_sn"], atol=2e-6)
+
