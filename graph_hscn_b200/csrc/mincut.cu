@@ -391,10 +391,35 @@ __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
     }
     deg[i] = d;
   }
-  if (K <= 32) {
-    // G lanes per node row: max / sum by shuffles inside the lane group, every warp busy.  (The round-1 form -- one
-    // thread per row with the row in registers -- ran ~800 dependent instructions on 5 of the CTA's 32 warps while
-    // the others waited at the barrier; ncu counted 57 k warp instructions per graph for 1.5 k matrix elements.)
+  if (K <= 32 && blockDim.x <= 512 && 8 * K <= 5 * G) {
+    // Many graphs (256 / 512 threads per graph, several CTAs per SM): the kernel is bound by instruction issue.  Where
+    // the lane groups below would leave more than 3/8 of their lanes idle (K = 5, 9-10, 17-20), one thread per node
+    // row with the row in registers needs fewer warp instructions (ncu source counters, B = 1 024, K = 10: 10 k of the
+    // 38 k warp instructions per graph were this softmax; forward 65.3 -> 55.3 us).  Measured slower at K = 4 and
+    // K = 16, where the groups are full.
+    for (int i = tid; i < n; i += blockDim.x) {
+      const float* zr = tile_staged ? S + i * K : logits + (int64_t)(base + i) * ldz;
+      float z[32];
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < K) { z[k] = temp != 1.0f ? __fdiv_rn(zr[k], temp) : zr[k]; m = fmaxf(m, z[k]); }
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < K) { z[k] = expf(z[k] - m); sum += z[k]; }
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < K) {
+          const float pv = __fdiv_rn(z[k], sum);
+          S[i * K + k] = pv;
+          if (SMEM) Sg[i * K + k] = pv;
+        }
+    }
+  } else if (K <= 32) {
+    // Few graphs (1 024 threads per graph, one CTA per SM: latency-bound): G lanes per node row, max / sum by shuffles
+    // inside the lane group, every warp busy.  (One thread per row ran ~800 dependent instructions on 5 of the CTA's
+    // 32 warps while the others waited at the barrier: 19.5 vs 17.0 us at B = 128.)
     for (int i0 = wid * rpw; i0 < n; i0 += nwarps * rpw) {
       const int i = i0 + sub;
       const bool on = i < n && kl < K;
@@ -504,7 +529,41 @@ __global__ void __launch_bounds__(1024) mincut_fwd_kernel(
   float* oag = kk ? kk + K * K : oag_g;
   if (phase == 0) {
     const int items = 2 * K * K;
-    if (items <= (int)blockDim.x) {
+    if (K > 4 && K <= 12 && blockDim.x <= 512 && 8 * K <= (int)blockDim.x) {
+      // [S^T S | S^T A S] for 4 < K <= 12, many graphs (issue-bound regime): a group of SL consecutive lanes per output ROW (k of either matrix), each lane
+      // walking every SL-th node with the row's K accumulators in registers: 1 + K shared loads for K FMAs per node
+      // (the one-thread-per-output-element form below spends 2 loads per FMA: 9.6 k of 38 k warp instructions per
+      // graph at B = 1 024, K = 10), slices combined by shuffles inside the group
+      int SL = 32;
+      while (2 * K * SL > (int)blockDim.x) SL >>= 1;
+      const int row_id = tid / SL, sl = tid - row_id * SL;
+      const bool act = row_id < 2 * K;
+      const bool second = row_id >= K;
+      const int k = row_id - (second ? K : 0);
+      const float* Bm = second ? AS : S;
+      float acc[12];
+#pragma unroll
+      for (int l = 0; l < 12; ++l) acc[l] = 0.f;
+      if (act) {
+        for (int i = sl; i < n; i += SL) {
+          const float a = S[i * K + k];
+          const float* br = Bm + i * K;
+#pragma unroll
+          for (int l = 0; l < 12; ++l)
+            if (l < K) acc[l] = fmaf(a, br[l], acc[l]);
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < 12; ++l)
+        if (l < K)
+          for (int o = SL >> 1; o > 0; o >>= 1) acc[l] += __shfl_xor_sync(kFullMask, acc[l], o);
+      if (act && sl == 0) {
+        float* dst = (second ? oag : ssg) + k * K;
+#pragma unroll
+        for (int l = 0; l < 12; ++l)
+          if (l < K) dst[l] = acc[l];
+      }
+    } else if (items <= (int)blockDim.x) {
       // small K: one thread per (output element, node slice) of [S^T S | S^T A S], slices combined in order
       const int parts = blockDim.x / items;
       if (tid < parts * items) {
@@ -812,15 +871,33 @@ __global__ void __launch_bounds__(1024) mincut_bwd_kernel(
     }
   }
   __syncthreads();
-  // softmax backward, one warp per node row
-  for (int i = wid; i < n; i += nwarps) {
-    float dot = 0.f;
-    for (int k = lane; k < K; k += 32) dot += dS[i * K + k] * Sr[i * K + k];
-    dot = warp_sum(dot);
-    for (int k = lane; k < K; k += 32) {
-      float dz = Sr[i * K + k] * (dS[i * K + k] - dot);
+  // softmax backward
+  if (K <= 32) {
+    // small K: row dot products by one thread per row (into the degree array, which is no longer needed), then one
+    // thread per element with coalesced stores.  (A warp per row kept 10 of 32 lanes busy at K = 10 and was 36 % of
+    // the kernel's warp instructions.)
+    for (int i = tid; i < n; i += blockDim.x) {
+      float dot = 0.f;
+      for (int k = 0; k < K; ++k) dot = fmaf(dS[i * K + k], Sr[i * K + k], dot);
+      deg[i] = dot;
+    }
+    __syncthreads();
+    for (int e = tid; e < n * K; e += blockDim.x) {
+      const int i = e / K;
+      float dz = Sr[e] * (dS[e] - deg[i]);
       if (temp != 1.0f) dz = dz / temp;
-      d_logits[(int64_t)(base + i) * lddz + k] = dz;
+      d_logits[(int64_t)(base + i) * lddz + (e - i * K)] = dz;
+    }
+  } else {
+    for (int i = wid; i < n; i += nwarps) {      // one warp per node row
+      float dot = 0.f;
+      for (int k = lane; k < K; k += 32) dot += dS[i * K + k] * Sr[i * K + k];
+      dot = warp_sum(dot);
+      for (int k = lane; k < K; k += 32) {
+        float dz = Sr[i * K + k] * (dS[i * K + k] - dot);
+        if (temp != 1.0f) dz = dz / temp;
+        d_logits[(int64_t)(base + i) * lddz + k] = dz;
+      }
     }
   }
   if (d_x != nullptr && !(xg && gog)) {
