@@ -1329,6 +1329,37 @@ __global__ void __launch_bounds__(256, (KT <= 16 ? 2 : 1))
   }
 }
 
+// Sums of N (= 4, 8 or 16) per-lane values over the 32 lanes of a warp, "transposed": every halving step exchanges
+// half of the values with the partner lane (the lanes with the step's bit clear keep the lower half), so N values cost
+// N shuffles instead of 5 N; lane l ends up with the total of value index rev(l): bit 4 of l selects the upper half
+// of 16, bit 3 the upper half of those 8, ... -- `warp_transpose_index` gives that index (-1: no value on this lane).
+template <int N>
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[N], int lane) {
+  static_assert(N == 4 || N == 8 || N == 16, "N must be 4, 8 or 16");
+  int off = 16;
+#pragma unroll
+  for (int half = N / 2; half >= 1; half >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = up ? v[j] : v[j + half];
+      const float keep = up ? v[j + half] : v[j];
+      v[j] = keep + __shfl_xor_sync(kFullMask, send, off);
+    }
+  }
+  float r = v[0];
+  for (; off >= 1; off >>= 1) r += __shfl_xor_sync(kFullMask, r, off);   // remaining bits hold the same index
+  return r;
+}
+template <int N>
+__device__ __forceinline__ int warp_transpose_index(int lane) {
+  int idx = 0, off = 16;
+#pragma unroll
+  for (int half = N / 2; half >= 1; half >>= 1, off >>= 1)
+    if (lane & off) idx += half;
+  return idx;
+}
+
 // Backward of the pooled features in one pass over the rows: xg[i, :] = x[i, :] g_out[g]^T (the term of dS) and, when
 // WANT_DX, d_x[i, :] = S[i, :] g_out[g].  CTA = (chunk of `rows_per_cta` rows, graph): g_out[g] ([K, H], <= 64 KB) and
 // the chunk's feature rows land in shared memory by TMA bulk copies issued up front (one each when the rows are
@@ -1336,7 +1367,7 @@ __global__ void __launch_bounds__(256, (KT <= 16 ? 2 : 1))
 // time: its lanes walk the float4 column groups, d_x is written once (coalesced 128-bit stores), the K partial dot
 // products are combined by shuffles.
 template <int KT, bool WANT_DX>
-__global__ void __launch_bounds__(256) mincut_pool_x_bwd_kernel(const float* __restrict__ s_soft,
+__global__ void __launch_bounds__(256, (KT <= 16 ? 2 : 1)) mincut_pool_x_bwd_kernel(const float* __restrict__ s_soft,
                                                                 const float* __restrict__ x, int64_t ldx,
                                                                 const int* __restrict__ ptr,
                                                                 const float* __restrict__ g_out, int K, int H,
@@ -1428,16 +1459,32 @@ __global__ void __launch_bounds__(256) mincut_pool_x_bwd_kernel(const float* __r
         if (two) reinterpret_cast<float4*>(d_x + i1 * lddx)[c] = d1;
       }
     }
-    float w0 = 0.f, w1 = 0.f;
+    if (KT <= 16) {
+      // transposed reduction: KT <= 16 partial sums per row over the warp in N shuffles (the plain butterflies were 28 %
+      // of the kernel's warp instructions at K = 10)
+      constexpr int N = KT <= 4 ? 4 : (KT <= 8 ? 8 : 16);
+      float a[N], b[N];
 #pragma unroll
-    for (int k = 0; k < KT; ++k)
-      if (k < K) {
-        const float a = warp_sum(t0[k]), b = warp_sum(t1[k]);
-        if (lane == k) { w0 = a; w1 = b; }
+      for (int k = 0; k < N; ++k) { a[k] = k < KT ? t0[k] : 0.f; b[k] = k < KT ? t1[k] : 0.f; }
+      const float w0 = warp_transpose_sum<N>(a, lane), w1 = warp_transpose_sum<N>(b, lane);
+      const int k = warp_transpose_index<N>(lane);
+      constexpr int kRest = 32 / N;                 // lanes holding the same index: the lowest of them writes
+      if ((lane & (kRest - 1)) == 0 && k < K) {
+        xg[i0 * K + k] = w0;
+        if (two) xg[i1 * K + k] = w1;
       }
-    if (lane < K) {
-      xg[i0 * K + lane] = w0;
-      if (two) xg[i1 * K + lane] = w1;
+    } else {
+      float w0 = 0.f, w1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k < K) {
+          const float a = warp_sum(t0[k]), b = warp_sum(t1[k]);
+          if (lane == k) { w0 = a; w1 = b; }
+        }
+      if (lane < K) {
+        xg[i0 * K + lane] = w0;
+        if (two) xg[i1 * K + lane] = w1;
+      }
     }
   }
 }
