@@ -296,6 +296,31 @@ def test_mincut_ragged_fwd_bwd(cuda, K, H):
     assert_close(xt.grad, xr.grad, 5 * RTOL, "mincut d x")
 
 
+def test_mincut_strided_features_fwd_bwd(cuda):
+    """x as a column slice of a wider matrix (row stride != H): the pooled-feature forward stays in the per-graph
+    kernel, the backward streams the rows with one bulk copy per row."""
+    o, p = _oracle(), _product()
+    b = _peptide_batch(5, seed=31)
+    g = torch.Generator().manual_seed(31)
+    N, K, H = b.x.size(0), 10, 128
+    ei, _ = o.gcn_norm(b.edge_index, None, N, add_self_loops=True)
+    wide = torch.randn(N, H + 8, generator=g)
+    s = torch.randn(N, K, generator=g)
+    xr, sr = wide[:, :H].clone().requires_grad_(), s.clone().requires_grad_()
+    wide_t = wide.to(cuda).requires_grad_()
+    xt, st_ = wide_t[:, :H], s.to(cuda).requires_grad_()
+    assert xt.stride(0) == H + 8
+    out_r, adj_r, mc_r, or_r = o.mincut_pool_ragged(xr, ei, sr, b.batch)
+    out_t, adj_t, mc_t, or_t = p.mincut_pool_ragged(xt, ei.to(cuda), st_, b.batch.to(cuda))
+    assert_close(out_t, out_r, RTOL, "mincut out (strided x)")
+    go = torch.randn(out_r.shape, generator=g)
+    (mc_r + or_r + (out_r * go).sum() * 0.01 + adj_r.sum()).backward()
+    (mc_t + or_t + (out_t * go.to(cuda)).sum() * 0.01 + adj_t.sum()).backward()
+    assert_close(st_.grad, sr.grad, 5 * RTOL, "d logits (strided x)")
+    assert_close(wide_t.grad[:, :H], xr.grad, 5 * RTOL, "d x (strided x)")
+    assert float(wide_t.grad[:, H:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("K,H", [(10, 16), (64, 16), (128, 300)])
 def test_mincut_losses_only_backward(cuda, K, H):
     """The reference keeps only the two losses (hscn.py:63): the diag-only fast path (K < 64) and the split backward
