@@ -1435,13 +1435,17 @@ __global__ void __launch_bounds__(256, (KT <= 16 ? 2 : 1)) mincut_pool_x_bwd_ker
                                                                 const float* __restrict__ x, int64_t ldx,
                                                                 const int* __restrict__ ptr,
                                                                 const float* __restrict__ g_out, int K, int H,
-                                                                int rows_per_cta, float* __restrict__ xg,
+                                                                int rows_per_cta, int n_cap, float* __restrict__ xg,
                                                                 float* __restrict__ d_x, int64_t lddx) {
   extern __shared__ __align__(128) float4 pool_smem[];
   __shared__ __align__(8) unsigned long long bar_mem;
   const int g = blockIdx.y;
   const int base = ptr[g], n = ptr[g + 1] - base;
   const int row0 = blockIdx.x * rows_per_cta;
+  if (n > n_cap) {                                 // stale max-nodes hint (the grid does not cover the graph): poison
+    if (WANT_DX && blockIdx.x == 0 && threadIdx.x == 0) d_x[(int64_t)base * lddx] = NAN;
+    return;
+  }
   if (row0 >= n) return;
   const int rc = min(n - row0, rows_per_cta);
   const int H4 = H >> 2;
@@ -1626,11 +1630,11 @@ static void launch_pool_x_bwd(const float* s_soft, const float* x, int64_t ldx, 
     if (d_x)
       mincut_pool_x_bwd_kernel<KT, true><<<grid, 256, shm, stream>>>(s_soft, x, ldx, ptr + g0,
                                                                       g_out + (int64_t)g0 * K * H, K, H, kPoolBwdRows,
-                                                                      xg, d_x, lddx);
+                                                                      n_cap, xg, d_x, lddx);
     else
       mincut_pool_x_bwd_kernel<KT, false><<<grid, 256, shm, stream>>>(s_soft, x, ldx, ptr + g0,
                                                                        g_out + (int64_t)g0 * K * H, K, H, kPoolBwdRows,
-                                                                       xg, nullptr, 0);
+                                                                       n_cap, xg, nullptr, 0);
   }
 }
 

@@ -109,3 +109,33 @@ def test_gat_destination_without_members_gets_bias_only(cuda):
     yr, yt = ref((xs, xd), ei), tst((xs.to(cuda), xd.to(cuda)), ei.to(cuda))
     assert_close(yt, yr, RTOL, "GAT with an empty destination")
     assert torch.allclose(yt[1].cpu(), ref.bias)
+
+
+
+def test_mincut_stale_max_nodes_hint_poisons_instead_of_overrunning(cuda):
+    """A max-nodes-per-graph hint smaller than the largest graph (the hint sizes the kernels' shared tiles and grids):
+    the affected graph's losses, pooled features and gradients come back NaN -- nothing is written past a tile and the
+    graphs inside the hint are untouched."""
+    from graph_hscn_b200 import pyg, synthetic
+    from graph_hscn_b200.structure import structure_cache, structure_hints
+    b = synthetic.peptides_batch(4, seed=11)
+    counts = (b.ptr[1:] - b.ptr[:-1])
+    big = int(counts.argmax())
+    small_cap = int(counts.sort().values[-2])            # fits every graph but the largest
+    assert small_cap < int(counts.max())
+    N, K, H = b.x.size(0), 10, 128
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, H, generator=g).to(cuda).requires_grad_()
+    s = torch.randn(N, K, generator=g).to(cuda).requires_grad_()
+    ei, _ = pyg.gcn_norm(b.edge_index.to(cuda), None, N, add_self_loops=True)     # structures built without the hint
+    with structure_hints(num_graphs=4, batch_sorted=1, max_nodes_per_graph=small_cap):
+        out, adj, mc, ol = pyg.mincut_pool_ragged(x, ei, s, b.batch.to(cuda))
+        (mc + ol + out.sum() + adj.sum()).backward()
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(mc)) and bool(torch.isnan(ol))
+    assert bool(torch.isnan(out[big]).all())
+    ok = [i for i in range(4) if i != big]
+    assert bool(torch.isfinite(out[ok]).all())
+    lo, hi = int(b.ptr[big]), int(b.ptr[big + 1])
+    assert bool(torch.isnan(s.grad[lo:hi]).any()) and bool(torch.isnan(x.grad[lo:hi]).any())
+    structure_cache().clear()
