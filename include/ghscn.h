@@ -419,6 +419,14 @@ GHSCN_API int ghscn_scn_backward(const float* ds, const float* h, const float* p
  *   stats    [B,8]   per graph: num, den, ||SS||_F, ortho_g, mc_g, reserved...
  *   mc_loss / ortho_loss scalars are the batch means, reduced deterministically by
  *   ghscn_mincut_reduce_losses.
+ * Pooled features for K <= 32 (round 2): when `out` is requested and x is a contiguous, 16-byte aligned [N,H] matrix
+ * with H a multiple of 4 (H <= 1024), S^T X is computed behind the per-graph kernel by a batch-wide streaming kernel
+ * (TMA bulk-copy ring; a thread-block cluster of 2/4/8 CTAs per graph when graphs are few); in the backward,
+ * x g_out^T and d_x = S g_out come from one streaming pass over the rows (H >= 128) that parks x g_out^T in the
+ * fourth [N,K] block of the workspace.  Same results up to summation order; without a workspace of
+ * ghscn_mincut_workspace_bytes() the per-graph kernels do that work themselves.  GHSCN_MINCUT_STREAM_X=0 turns the
+ * streaming kernels off.  A max_nodes_per_graph smaller than a graph's node count poisons that graph's losses,
+ * pooled features and gradients with NaN instead of overrunning the shared tiles.
  */
 GHSCN_API size_t ghscn_mincut_workspace_bytes(int64_t num_nodes, int64_t num_graphs, int64_t num_clusters);
 GHSCN_API int ghscn_mincut_fwd(const float* logits, int64_t ldz, const float* x, int64_t ldx, const int32_t* ptr,
