@@ -18,13 +18,17 @@
 namespace ghscn {
 
 // few graphs: one big CTA per graph keeps an SM busy; many graphs: several small CTAs per SM
-static inline int mincut_threads(int64_t num_graphs) {
+static inline int mincut_threads(int64_t num_graphs, int64_t num_clusters) {
   static const int forced = [] {                       // tuning experiments: GHSCN_MINCUT_THREADS=256|512|1024
     const char* e = getenv("GHSCN_MINCUT_THREADS");
     const int v = e ? atoi(e) : 0;
     return (v == 128 || v == 256 || v == 512 || v == 1024) ? v : 0;
   }();
   if (forced) return forced;
+  // K <= 12 (the row-wise code paths of the <= 512-thread regime, late round 2), losses only, K = 10, forward /
+  // forward + backward: B = 128: 16.6 / 38.6 us (256 threads), 13.0 / 30.3 (512), 16.5 / 38.8 (1 024);
+  // B = 300: 19.1 / 40.7 (256), 22.0 / 45.7 (512); B = 600: 24.2 / 55.8 (256), 32.3 / 64.1 (512)
+  if (num_clusters <= 12) return num_graphs >= 2 * kNumSMs ? 256 : 512;
   return num_graphs >= 4 * kNumSMs ? 256 : (num_graphs >= 2 * kNumSMs ? 512 : 1024);
 }
 // GHSCN_MINCUT_STAGE=1 stages the graph's logits tile (one TMA bulk copy) and CSR slice in shared memory before the
@@ -1695,7 +1699,7 @@ static int mincut_fwd_impl(const float* logits, int64_t ldz, const float* x, int
   GHSCN_REQUIRE(max_nodes_per_graph > 0);
   cudaStream_t stream = as_stream(stream_);
   const int K = (int)num_clusters, H = (int)num_feat, n_cap = max_nodes_per_graph;
-  const int threads = mincut_threads(num_graphs);
+  const int threads = mincut_threads(num_graphs, num_clusters);
   // the split phases exchange S and A S through HBM (s_soft, workspace): they use the workspace variant
   const bool smem = phase == 0 && fwd_smem_bytes(n_cap, K, true) <= kSmemBudget;
   size_t staged_bytes = 0;
@@ -1778,7 +1782,7 @@ int ghscn_mincut_bwd(const float* s_soft, const float* x, int64_t ldx, const int
   GHSCN_REQUIRE((g_out == nullptr && d_x == nullptr) || x != nullptr);
   cudaStream_t stream = as_stream(stream_);
   const int K = (int)num_clusters, H = (int)num_feat, n_cap = max_nodes_per_graph;
-  const int threads = mincut_threads(num_graphs);
+  const int threads = mincut_threads(num_graphs, num_clusters);
   const bool smem = bwd_smem_bytes(n_cap, K, true) <= kSmemBudget;
   const size_t shm = bwd_smem_bytes(n_cap, K, smem);
   if (shm > kSmemBudget) return GHSCN_E_UNSUPPORTED;
