@@ -252,7 +252,7 @@ def kernel_table():
             pyg.mincut_pool_ragged(xs[i % nset], ei1, s_log, batch, want_out=False, want_adj=False)
         E1 = ei1.size(1)
         row("K6 MinCUT losses forward, K = 10 (a4/a5; what hscn.py:63 keeps)", graph_time(k6f),
-            4 * N * K * 2 + 4 * (N + 1) + 4 * E1 + B * (8 * K * K + 32), "latency-bound: one CTA per graph, ~10 barrier phases")
+            4 * N * K * 2 + 4 * (N + 1) + 4 * E1 + B * (8 * K * K + 32), "latency-bound: one CTA (512 threads) per graph, ~10 barrier phases")
 
         def k6o(i):
             pyg.mincut_pool_ragged(xs[i % nset], ei1, s_log, batch)
