@@ -168,3 +168,30 @@ def test_shim_utils_equal_oracle_restatement(gold):
     vals, vecs = op.compute_posenc_stats(d["edge_index"], d["x"].size(0), False, 10, "L2", "sym")
     assert torch.allclose(vals, d["eigvals_sn"], atol=2e-6)
 
+
+def test_product_pe_path_is_cuda_only_and_fails_loudly():
+    """No CPU fallback: the device eigensolver refuses CPU tensors instead of quietly running numpy."""
+    from graph_hscn_b200 import posenc
+    ei = torch.tensor([[0, 1], [1, 0]])
+    with pytest.raises(RuntimeError):
+        posenc.laplacian_eig(ei, torch.tensor([0, 2]), 2, 2)
+    import inspect
+    src = inspect.getsource(posenc)
+    assert "oracle" not in src.replace("oracle/posenc.py", "") and "numpy" not in src
+
+
+def test_gin_three_dimensional_input_equals_per_slice(gold):
+    """GINConv on the [K, N, C] stack of encoder/signnet.py:227-229 (PyG propagates along node_dim = -2) == the 2-D
+    layer applied slice by slice (oracle operators)."""
+    from oracle import nn as onn
+    g = gold["graphs"][1]
+    n = g["x"].size(0)
+    torch.manual_seed(4)
+    lin = torch.nn.Linear(3, 5)
+    conv = onn.GINConv(lin)
+    x = torch.randn(4, n, 3)
+    full = conv(x, g["edge_index"])
+    per = torch.stack([conv(x[k], g["edge_index"]) for k in range(4)])
+    assert full.shape == (4, n, 5)
+    assert torch.allclose(full, per, atol=1e-6)
+
