@@ -51,6 +51,7 @@ def main() -> None:
     get_stats, _norm = reference_functions(os.path.join(REFERENCE, "graph_hscn/transform/posenc.py"),
                                            ["get_lap_decomp_stats", "eigvec_normalizer"])
     out = {"decomp": [], "graphs": []}
+    torch.manual_seed(404)                              # the hand-made path graph below draws its features
     graphs = synthetic.peptides_graphs(5, seed=404, task="func")
     path6 = torch.tensor([[0, 1, 1, 2, 2, 3, 3, 4, 4, 5], [1, 0, 2, 1, 3, 2, 4, 3, 5, 4]])
     graphs.append(Data(x=torch.randint(0, 5, (6, 9)), edge_index=path6, y=torch.zeros(1, 10)))   # n < max_freqs
@@ -82,6 +83,12 @@ def main() -> None:
         d = ref_compute(Data(x=g.x, edge_index=g.edge_index), True, pe_cfg)
         assert torch.equal(torch.nan_to_num(d.eigvals_sn), torch.nan_to_num(g.eigvals_sn))
         assert torch.equal(torch.nan_to_num(d.eigvecs_sn), torch.nan_to_num(g.eigvecs_sn))
+    out["other_norms"] = []
+    for lap_norm, vec_norm in (("none", "L1"), ("rw", "abs-max")):        # the non-default PEConfig choices, whole function
+        cfg2 = types.SimpleNamespace(eigen_laplacian_norm=lap_norm, eigen_max_freqs=10, eigvec_norm=vec_norm)
+        d = ref_compute(Data(x=graphs[1].x, edge_index=graphs[1].edge_index), True, cfg2)
+        out["other_norms"].append(dict(lap_norm=lap_norm, vec_norm=vec_norm, eigvals_sn=d.eigvals_sn.clone(),
+                                       eigvecs_sn=d.eigvecs_sn.clone()))
     und = graphs[0].edge_index[:, graphs[0].edge_index[0] < graphs[0].edge_index[1]]
     d = ref_compute(Data(x=graphs[0].x, edge_index=und), False, pe_cfg)          # is_undirected = False branch
     out["directed"] = dict(x=graphs[0].x, edge_index=und, eigvals_sn=d.eigvals_sn, eigvecs_sn=d.eigvecs_sn)

@@ -195,3 +195,20 @@ def test_gin_three_dimensional_input_equals_per_slice(gold):
     assert full.shape == (4, n, 5)
     assert torch.allclose(full, per, atol=1e-6)
 
+
+def test_oracle_matches_reference_function_for_other_normalisations(gold):
+    """compute_posenc_stats of the reference (unmodified) with eigen_laplacian_norm = none / rw and eigvec_norm = L1 /
+    abs-max: eigenvalues and, for isolated eigenvalues, eigenvectors up to sign."""
+    from oracle import posenc as op
+    g = gold["graphs"][1]
+    n = g["x"].size(0)
+    for row in gold["other_norms"]:
+        vals, vecs = op.compute_posenc_stats(g["edge_index"], n, True, 10, row["vec_norm"], row["lap_norm"])
+        assert torch.allclose(vals, row["eigvals_sn"], atol=5e-6 * max(1.0, float(row["eigvals_sn"].max())))
+        lam = vals[0, :, 0]
+        for k in range(9):
+            if min(abs(float(lam[k] - lam[j])) for j in range(10) if j != k) > 1e-3:
+                a, b = vecs[:, k], row["eigvecs_sn"][:, k]
+                sign = 1.0 if float((a * b).sum()) >= 0 else -1.0
+                assert float((a - sign * b).abs().max()) < 1e-4, (row["lap_norm"], k)
+
